@@ -1,0 +1,269 @@
+/*
+ * povar_b200.h -- C ABI of the B200-native PoVar hot path (libpovar_b200.so).
+ *
+ * This is the drop-in boundary for the reference's `Linearizor<Scalar>` plugin
+ * interface (/root/reference/src/rootba_povar/solver/linearizor.hpp:47-82) and for
+ * the two-step driver built on it (solver/bal_bundle_adjustment.cpp:848-876).
+ * The reference keeps cameras/landmarks in host structs and mutates them through
+ * the Linearizor; here the state lives in HBM behind an opaque handle, so the
+ * caller-side backup/restore/normalise steps of the reference move behind the
+ * ABI as well.  Every entry point cites the reference interface it replaces.
+ *
+ * Conventions
+ *   - plain C types, host pointers owned by the caller, sizes in elements;
+ *   - return 0 = OK; < 0 = CUDA / NCCL / usage error (text via povar_last_error);
+ *     > 0 = numerical condition (POVAR_NUM_*), which the reference surfaces as a
+ *     non-finite increment or a failed CHECK;
+ *   - one driving host thread per handle; one handle per GPU (one process per GPU
+ *     when sharded, landmarks partitioned across ranks, cameras replicated);
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point
+ *     returns POVAR_ERR_NO_DEVICE.
+ */
+#ifndef POVAR_B200_H_
+#define POVAR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define POVAR_ABI_VERSION 1
+
+/* status codes */
+enum {
+  POVAR_OK = 0,
+  POVAR_NUM_NONFINITE_INC = 1,     /* increment has NaN/Inf: "Invalid" step, bal_bundle_adjustment.cpp:362-401 */
+  POVAR_NUM_LINEARIZATION = 2,     /* non-finite residual/Jacobian: the reference CHECK-aborts, linearizor_power_varproj.cpp:59 */
+  POVAR_ERR_INVALID = -1,
+  POVAR_ERR_CUDA = -2,
+  POVAR_ERR_NCCL = -3,
+  POVAR_ERR_NO_DEVICE = -4,
+  POVAR_ERR_IO = -5,
+  POVAR_ERR_UNSUPPORTED = -6
+};
+
+/* SolverOptions::SolverType / SolverTypeRiemannian, bal/solver_options.hpp:60-69 (same order) */
+enum { POVAR_PCG = 0, POVAR_POWER_SCHUR_COMPLEMENT = 1, POVAR_POWER_VARPROJ = 2, POVAR_CHOLESKY = 3 };
+enum { POVAR_RIPOBA = 0, POVAR_RIPCG = 1 };
+/* BalResidualOptions::RobustNorm, bal/bal_residual_options.hpp:44-48 */
+enum { POVAR_NORM_NONE = 0, POVAR_NORM_HUBER = 1, POVAR_NORM_CAUCHY = 2 };
+/* SolverOptions::OptimizedCost, bal/solver_options.hpp:48-53 */
+enum { POVAR_COST_ERROR = 0, POVAR_COST_ERROR_VALID = 1, POVAR_COST_ERROR_VALID_AVG = 2 };
+enum { POVAR_STATE_POSE = 0, POVAR_STATE_JOINT = 1 };
+
+/* The fields of SolverOptions (bal/solver_options.hpp:88-307) that the path reads;
+ * povar_options_default() fills the reference's CODE defaults (alpha 0.01,
+ * power_sc_iterations 10, eta 0.01 ... -- not the README's). */
+typedef struct povar_options {
+  int32_t solver_type_step_1;          /* POVAR_POWER_VARPROJ */
+  int32_t solver_type_step_2;          /* POVAR_RIPOBA */
+  int32_t robust_norm;                 /* POVAR_NORM_NONE */
+  int32_t optimized_cost;              /* POVAR_COST_ERROR */
+  double huber_parameter;              /* 1.0 */
+  double alpha;                        /* 0.01 */
+  int32_t max_num_iterations_step_1;   /* 50 */
+  int32_t max_num_iterations_step_2;   /* 50 */
+  double min_relative_decrease;        /* 0 */
+  double initial_trust_region_radius;  /* 1e4 */
+  double min_trust_region_radius;      /* 1e-32 */
+  double max_trust_region_radius;      /* 1e16 */
+  int32_t min_linear_solver_iterations; /* 0 */
+  int32_t max_linear_solver_iterations; /* 500 */
+  double eta;                          /* 1e-2 */
+  double r_tolerance;                  /* -1 */
+  double jacobi_scaling_epsilon;       /* 0 => sqrt(1e-10) */
+  double function_tolerance;           /* 1e-6 */
+  int32_t power_sc_iterations;         /* 10 */
+  int32_t verbosity_level;             /* 2 */
+  double initial_vee;                  /* 2 */
+  double vee_factor;                   /* 2 */
+} povar_options;
+
+void povar_options_default(povar_options* opt);
+
+/* One shard of a BAL problem in the reference's canonical order: landmark index,
+ * then camera index ascending (std::map<cam,obs> per landmark, bal_problem.hpp:226;
+ * pose_idx_ of landmark_block.hpp:104-108).  Image coordinates are the values AFTER
+ * the loader's y flip (bal_problem.cpp:240). */
+typedef struct povar_problem_desc {
+  int32_t num_cams;        /* C, all cameras (replicated on every rank) */
+  int32_t num_lms;         /* landmarks in this shard */
+  int64_t num_obs;         /* observations in this shard */
+  const int64_t* lm_ptr;   /* [num_lms+1] CSR offsets into obs_* */
+  const int32_t* obs_cam;  /* [num_obs] camera index, ascending inside a landmark */
+  const double* obs_uv;    /* [num_obs*2] */
+  const double* cam_P;     /* [C*12] 3x4 camera matrices, row-major */
+} povar_problem_desc;
+
+/* bal/residual_info.hpp:59-102 */
+typedef struct povar_residual_info {
+  int64_t num_obs_all;
+  double error_all;
+  double residual_sum_all;
+  int64_t num_obs_valid;
+  double error_valid;
+  double residual_sum_valid;
+  int32_t is_numerically_valid;
+} povar_residual_info;
+
+/* how ranks find each other when landmarks are sharded over several GPUs */
+typedef struct povar_comm_desc {
+  int32_t rank;
+  int32_t world_size;
+  int32_t device;            /* CUDA device ordinal for this rank */
+  uint8_t nccl_id[128];      /* from povar_comm_unique_id() on rank 0, broadcast by the launcher */
+} povar_comm_desc;
+
+typedef struct povar_handle povar_handle;
+
+/* ---------- host-side, no GPU needed ------------------------------------------------ */
+
+int povar_abi_version(void);
+
+/* BAL text reader for the 15-parameter format written by --create-dataset:
+ * replaces BalProblem::load_bal_eccv (bal/bal_problem.cpp:182-303) up to and including
+ * the y flip and the canonical re-ordering; duplicate (cam,lm) pairs are an error
+ * (bal_problem.cpp:227).  Output arrays are malloc'ed; release with povar_bal_free. */
+typedef struct povar_bal_data {
+  int32_t num_cams;
+  int32_t num_lms;
+  int64_t num_obs;
+  int64_t* lm_ptr;      /* [num_lms+1] */
+  int32_t* obs_cam;     /* [num_obs] */
+  double* obs_uv;       /* [num_obs*2] */
+  double* cam_params;   /* [num_cams*15]: 12 matrix entries + f,k1,k2 (intrinsics unused by the path) */
+} povar_bal_data;
+
+int povar_bal_read(const char* path, povar_bal_data* out, char* err, size_t err_len);
+void povar_bal_free(povar_bal_data* data);
+
+/* canonical order of an unordered observation list: fills perm[num_obs] (indices into the
+ * input, landmark-major, camera ascending) and lm_ptr[num_lms+1]; returns POVAR_ERR_INVALID on
+ * a duplicate pair or an index out of range. */
+int povar_canonical_order(int32_t num_cams, int32_t num_lms, int64_t num_obs, const int32_t* cam,
+                          const int32_t* lm, int64_t* perm, int64_t* lm_ptr);
+
+/* contiguous landmark ranges balanced by observation count: bounds[world_size+1]. */
+int povar_partition_landmarks(int32_t num_lms, const int64_t* lm_ptr, int32_t world_size,
+                              int32_t* bounds);
+
+/* ---------- life cycle ---------------------------------------------------------------- */
+
+int povar_comm_unique_id(uint8_t id[128]);
+
+/* replaces Linearizor<Scalar>::create / create_homogeneous (solver/linearizor.cpp:47-79):
+ * uploads the shard, builds the camera-major index, allocates all device state.
+ * comm == NULL means a single GPU (device 0). */
+int povar_create(const povar_problem_desc* desc, const povar_options* opt,
+                 const povar_comm_desc* comm, povar_handle** out);
+void povar_destroy(povar_handle* h);
+const char* povar_last_error(const povar_handle* h);
+
+/* ---------- the Linearizor interface, in call order ------------------------------------ */
+
+/* initialize_varproj_lm_pOSE (solver/linearizor_base.cpp:60-67; helper.cpp:75-114) */
+int povar_init_varproj(povar_handle* h, double alpha);
+/* compute_error_pOSE / compute_error_homogeneous (solver/linearizor_base.cpp:69-87) */
+int povar_cost_pose(povar_handle* h, double alpha, povar_residual_info* out);
+int povar_cost_homogeneous(povar_handle* h, povar_residual_info* out);
+/* linearize_pOSE / linearize_projective_space_homogeneous
+ * (solver/linearizor_power_varproj.cpp:44-110, solver/linearizor_sc.cpp:174-239) */
+int povar_linearize_pose(povar_handle* h, double alpha);
+int povar_linearize_homogeneous(povar_handle* h);
+/* solve / solve_joint (solver/linearizor_power_varproj.cpp:113-243, linearizor_sc.cpp:91-325).
+ * The increment stays on the device for the following apply; `inc` (C*12 resp. C*11 doubles)
+ * may be NULL.  Returns POVAR_NUM_NONFINITE_INC if the increment is not finite. */
+int povar_solve_pose(povar_handle* h, double lambda, double* inc, int32_t* linear_solver_iterations);
+int povar_solve_joint(povar_handle* h, double lambda, double* inc, int32_t* linear_solver_iterations);
+/* apply / apply_joint (solver/linearizor_power_varproj.cpp:245-308): back-substitution,
+ * camera update, model cost change l_diff. */
+int povar_apply_pose(povar_handle* h, double alpha, double* l_diff);
+int povar_apply_joint(povar_handle* h, double* l_diff);
+
+/* ---------- what the reference's caller does on host structs --------------------------- */
+
+/* BalProblem::backup_pOSE/restore_pOSE/backup_joint/restore_joint (bal/bal_problem.cpp:647-708) */
+int povar_backup(povar_handle* h, int32_t which);
+int povar_restore(povar_handle* h, int32_t which);
+/* create_homogeneous_landmark (solver/bal_bundle_adjustment.cpp:544-553) */
+int povar_to_homogeneous(povar_handle* h);
+/* per-trial normalisation P/|P|_F, X/X[3] (solver/bal_bundle_adjustment.cpp:700-705) */
+int povar_normalize_joint(povar_handle* h);
+
+/* cameras [C*12]; landmarks of this shard [num_lms*3] (POVAR_STATE_POSE) or [num_lms*4] (JOINT) */
+int povar_get_state(povar_handle* h, int32_t which, double* cam_P, double* lms);
+int povar_set_state(povar_handle* h, int32_t which, const double* cam_P, const double* lms);
+
+/* ---------- the two-step driver -------------------------------------------------------- */
+
+/* one entry per LM trial, the columns of ba_log.json the parity harness reads
+ * (bal/ba_log.hpp:147-245, bal/ba_log_utils.cpp:99-160) */
+typedef struct povar_iteration {
+  int32_t step;                       /* 1 or 2 */
+  int32_t iteration;                  /* restarts at 0 with step 2 */
+  int32_t step_is_valid;
+  int32_t step_is_successful;
+  double cost;                        /* as logged: previous cost for failed trials */
+  double cost_valid;
+  double trial_cost;                  /* cost evaluated in this trial (NaN if none) */
+  int64_t num_obs_valid;
+  double relative_decrease;
+  double trust_region_radius;
+  int32_t linear_solver_iterations;
+  double iteration_time;              /* seconds, host clock around the trial */
+  double cumulative_time;
+  /* phase times from CUDA events, seconds (solver/solver_summary.hpp:172-212) */
+  double residual_evaluation_time;
+  double jacobian_evaluation_time;    /* linearize_* */
+  double prepare_time;                /* solve: everything before the reduced solve */
+  double solve_reduced_system_time;   /* power series / PCG / Cholesky */
+  double back_substitution_time;      /* apply_* */
+} povar_iteration;
+
+typedef struct povar_solve_summary {
+  int32_t num_iterations;             /* entries written to `iterations` */
+  int32_t termination_type_step_1;    /* 0 CONVERGENCE, 1 NO_CONVERGENCE (solver_summary.hpp) */
+  int32_t termination_type_step_2;
+  int32_t num_successful_steps;
+  int32_t num_unsuccessful_steps;
+  double initial_cost;
+  double final_cost;
+  double total_time;                  /* seconds, both steps (the reference's timing.optimize) */
+  double step1_time;
+  double step2_time;
+  int64_t power_terms;                /* sum of linear_solver_iterations over power-series solves */
+  double power_series_time;           /* device seconds spent in them */
+  char message[256];
+} povar_solve_summary;
+
+/* bundle_adjust_manual (solver/bal_bundle_adjustment.cpp:848-876): step 1 (pOSE LM/VarPro loop,
+ * :252-542), conversion to homogeneous (:544-553), step 2 (Riemannian LM loop, :557-843) on the
+ * state held by the handle.  `iterations` has room for `max_iterations` entries. */
+int povar_bundle_adjust(povar_handle* h, const povar_options* opt, povar_iteration* iterations,
+                        int32_t max_iterations, povar_solve_summary* summary);
+
+/* ---------- instrumentation ------------------------------------------------------------ */
+
+/* copy an internal device array to the host for parity tests.  Names: "pose_scale" [C*12],
+ * "lm_scale" [L*4], "hll_inv" [L*6], "b_inv" [C*D*D], "b" [C*D], "inc" [C*D], "lm_ptr", ...
+ * returns the element count, or < 0. */
+int64_t povar_debug_read(povar_handle* h, const char* name, double* out, int64_t capacity);
+
+/* E0 * x for a caller-supplied camera-space vector (C*12 for POSE, C*11 for JOINT) with the
+ * current linearisation: right_mul_e0_pOSE / right_mul_e0_joint
+ * (sc/linearization_power_varproj.hpp:364-453).  Used by tests and by the SpMV benchmark. */
+int povar_right_mul_e0(povar_handle* h, int32_t which, const double* x, double* out);
+
+/* run `terms` power-series terms back to back on the current linearisation (no early exit) and
+ * return the device time per term in seconds: the SpMV roofline measurement of bench.py. */
+int povar_bench_power_terms(povar_handle* h, int32_t which, int32_t terms, double* seconds_per_term);
+
+/* kernels launched by this handle since creation (bench.py's gpu_launches) */
+int64_t povar_launch_count(const povar_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POVAR_B200_H_ */

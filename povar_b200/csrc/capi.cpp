@@ -1,0 +1,191 @@
+// extern "C" surface of libpovar_b200.so (include/povar_b200.h): thin forwarding to Engine.
+#include <cstring>
+#include <string>
+
+#include "engine.h"
+
+namespace povar {
+int nccl_unique_id(uint8_t id[128], std::string* err);
+}
+
+struct povar_handle {
+  povar::Engine* engine = nullptr;
+  std::string create_error;
+};
+
+static thread_local std::string g_last_global_error;
+
+extern "C" {
+
+int povar_abi_version(void) { return POVAR_ABI_VERSION; }
+
+void povar_options_default(povar_options* o) {
+  if (!o) return;
+  // code defaults of bal/solver_options.hpp:88-307 and bal_residual_options.hpp:52-60
+  o->solver_type_step_1 = POVAR_POWER_VARPROJ;
+  o->solver_type_step_2 = POVAR_RIPOBA;
+  o->robust_norm = POVAR_NORM_NONE;
+  o->optimized_cost = POVAR_COST_ERROR;
+  o->huber_parameter = 1.0;
+  o->alpha = 0.01;
+  o->max_num_iterations_step_1 = 50;
+  o->max_num_iterations_step_2 = 50;
+  o->min_relative_decrease = 0.0;
+  o->initial_trust_region_radius = 1e4;
+  o->min_trust_region_radius = 1e-32;
+  o->max_trust_region_radius = 1e16;
+  o->min_linear_solver_iterations = 0;
+  o->max_linear_solver_iterations = 500;
+  o->eta = 1e-2;
+  o->r_tolerance = -1.0;
+  o->jacobi_scaling_epsilon = 0.0;
+  o->function_tolerance = 1e-6;
+  o->power_sc_iterations = 10;
+  o->verbosity_level = 2;
+  o->initial_vee = 2.0;
+  o->vee_factor = 2.0;
+}
+
+int povar_comm_unique_id(uint8_t id[128]) {
+  std::string err;
+  const int rc = povar::nccl_unique_id(id, &err);
+  if (rc != POVAR_OK) g_last_global_error = err;
+  return rc;
+}
+
+int povar_create(const povar_problem_desc* desc, const povar_options* opt, const povar_comm_desc* comm,
+                 povar_handle** out) {
+  if (!out) return POVAR_ERR_INVALID;
+  *out = nullptr;
+  povar_handle* h = new povar_handle();
+  const int rc = povar::Engine::create(desc, opt, comm, &h->engine, &h->create_error);
+  if (rc != POVAR_OK) {
+    g_last_global_error = h->create_error;
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return POVAR_OK;
+}
+
+void povar_destroy(povar_handle* h) {
+  if (!h) return;
+  delete h->engine;
+  delete h;
+}
+
+const char* povar_last_error(const povar_handle* h) {
+  if (!h || !h->engine) return g_last_global_error.c_str();
+  return h->engine->last_error();
+}
+
+#define PV_ENGINE(h)                              \
+  if (!(h) || !(h)->engine) return POVAR_ERR_INVALID; \
+  povar::Engine& e = *(h)->engine
+
+int povar_init_varproj(povar_handle* h, double alpha) {
+  PV_ENGINE(h);
+  return e.init_varproj(alpha);
+}
+
+int povar_cost_pose(povar_handle* h, double alpha, povar_residual_info* out) {
+  PV_ENGINE(h);
+  if (!out) return POVAR_ERR_INVALID;
+  return e.cost(false, alpha, out);
+}
+
+int povar_cost_homogeneous(povar_handle* h, povar_residual_info* out) {
+  PV_ENGINE(h);
+  if (!out) return POVAR_ERR_INVALID;
+  return e.cost(true, 0.0, out);
+}
+
+int povar_linearize_pose(povar_handle* h, double alpha) {
+  PV_ENGINE(h);
+  return e.linearize(false, alpha);
+}
+
+int povar_linearize_homogeneous(povar_handle* h) {
+  PV_ENGINE(h);
+  return e.linearize(true, 0.0);
+}
+
+int povar_solve_pose(povar_handle* h, double lambda, double* inc, int32_t* its) {
+  PV_ENGINE(h);
+  return e.solve(false, lambda, inc, its);
+}
+
+int povar_solve_joint(povar_handle* h, double lambda, double* inc, int32_t* its) {
+  PV_ENGINE(h);
+  return e.solve(true, lambda, inc, its);
+}
+
+int povar_apply_pose(povar_handle* h, double alpha, double* l_diff) {
+  PV_ENGINE(h);
+  return e.apply(false, alpha, l_diff);
+}
+
+int povar_apply_joint(povar_handle* h, double* l_diff) {
+  PV_ENGINE(h);
+  return e.apply(true, 0.0, l_diff);
+}
+
+int povar_backup(povar_handle* h, int32_t which) {
+  PV_ENGINE(h);
+  return e.backup(which);
+}
+
+int povar_restore(povar_handle* h, int32_t which) {
+  PV_ENGINE(h);
+  return e.restore(which);
+}
+
+int povar_to_homogeneous(povar_handle* h) {
+  PV_ENGINE(h);
+  return e.to_homogeneous();
+}
+
+int povar_normalize_joint(povar_handle* h) {
+  PV_ENGINE(h);
+  return e.normalize_joint();
+}
+
+int povar_get_state(povar_handle* h, int32_t which, double* cam_P, double* lms) {
+  PV_ENGINE(h);
+  return e.get_state(which, cam_P, lms);
+}
+
+int povar_set_state(povar_handle* h, int32_t which, const double* cam_P, const double* lms) {
+  PV_ENGINE(h);
+  return e.set_state(which, cam_P, lms);
+}
+
+int64_t povar_debug_read(povar_handle* h, const char* name, double* out, int64_t capacity) {
+  if (!h || !h->engine) return POVAR_ERR_INVALID;
+  return h->engine->debug_read(name, out, capacity);
+}
+
+int povar_right_mul_e0(povar_handle* h, int32_t which, const double* x, double* out) {
+  PV_ENGINE(h);
+  if (!x || !out) return POVAR_ERR_INVALID;
+  return e.right_mul_e0(which == POVAR_STATE_JOINT, x, out);
+}
+
+int povar_bench_power_terms(povar_handle* h, int32_t which, int32_t terms, double* seconds_per_term) {
+  PV_ENGINE(h);
+  return e.bench_power_terms(which == POVAR_STATE_JOINT, terms, seconds_per_term);
+}
+
+int64_t povar_launch_count(const povar_handle* h) {
+  if (!h || !h->engine) return 0;
+  return h->engine->launches();
+}
+
+}  // extern "C"
+
+// used by the driver (host/lm_driver.cpp) to pull phase times without widening the ABI
+namespace povar {
+const PhaseTimes& handle_times(povar_handle* h) { return h->engine->last_times(); }
+void handle_reset_times(povar_handle* h) { h->engine->reset_times(); }
+int handle_rank(povar_handle* h) { return h->engine->rank(); }
+}  // namespace povar

@@ -1,0 +1,739 @@
+// Engine: device state of one landmark shard + kernel sequencing for the PoVar hot path.
+//
+// Mirrors, per call, what LinearizorPowerVarproj / LinearizorSC do
+// (/root/reference/src/rootba_povar/solver/linearizor_power_varproj.cpp, linearizor_sc.cpp):
+//   linearize  -> landmark pass (Jl^T Jl, Jl^T r, column scales) + camera pass (Jp^T Jp) + scales
+//   solve      -> Hll^-1, B^-1, b, then the power series (or PCG / Cholesky)
+//   apply      -> back-substitution + camera update, model cost change
+// The Jacobian blocks are never stored: see device_math.cuh.
+#include "engine.h"
+
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+
+namespace povar {
+
+// ---------------------------------------------------------------------------------------------
+// NCCL through dlopen: libpovar_b200.so stays loadable on a box without NCCL; the entry points
+// are only needed when world_size > 1.
+// ---------------------------------------------------------------------------------------------
+struct Id128 {   // ncclUniqueId: 128 opaque bytes, passed by value
+  char bytes[128];
+};
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi* load_nccl(std::string* err) {
+  static NcclApi api;
+  if (api.lib) return &api;
+  const char* names[] = {getenv("POVAR_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    if (!n) continue;
+    api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (api.lib) break;
+  }
+  if (!api.lib) {
+    if (err) *err = "cannot dlopen libnccl.so.2 (set POVAR_NCCL_LIB)";
+    return nullptr;
+  }
+  api.GetUniqueId = reinterpret_cast<int (*)(void*)>(dlsym(api.lib, "ncclGetUniqueId"));
+  api.CommInitRank =
+      reinterpret_cast<int (*)(void**, int, Id128, int)>(dlsym(api.lib, "ncclCommInitRank"));
+  api.AllReduce = reinterpret_cast<int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t)>(
+      dlsym(api.lib, "ncclAllReduce"));
+  api.CommDestroy = reinterpret_cast<int (*)(void*)>(dlsym(api.lib, "ncclCommDestroy"));
+  api.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(api.lib, "ncclGetErrorString"));
+  if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy) {
+    if (err) *err = "libnccl is missing expected symbols";
+    dlclose(api.lib);
+    api.lib = nullptr;
+    return nullptr;
+  }
+  return &api;
+}
+
+int nccl_unique_id(uint8_t id[128], std::string* err) {
+  NcclApi* api = load_nccl(err);
+  if (!api) return POVAR_ERR_NCCL;
+  const int rc = api->GetUniqueId(id);
+  if (rc != 0) {
+    if (err) *err = std::string("ncclGetUniqueId: ") + (api->GetErrorString ? api->GetErrorString(rc) : "?");
+    return POVAR_ERR_NCCL;
+  }
+  return POVAR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side index construction
+// ---------------------------------------------------------------------------------------------
+// Tiles of the landmark-sorted observation array: runs of whole landmarks with <= 32
+// observations together, or a single landmark with more than 32.
+void build_tiles(const std::vector<int>& lm_ptr, std::vector<int>* tile_ptr) {
+  tile_ptr->clear();
+  const int L = static_cast<int>(lm_ptr.size()) - 1;
+  tile_ptr->push_back(0);
+  int cur = 0;  // observations in the open tile
+  for (int l = 0; l < L; ++l) {
+    const int deg = lm_ptr[l + 1] - lm_ptr[l];
+    if (deg == 0) continue;
+    if (deg > 32) {
+      if (cur > 0) {
+        tile_ptr->push_back(lm_ptr[l]);
+        cur = 0;
+      }
+      tile_ptr->push_back(lm_ptr[l + 1]);
+      continue;
+    }
+    if (cur + deg > 32) {
+      tile_ptr->push_back(lm_ptr[l]);
+      cur = 0;
+    }
+    cur += deg;
+  }
+  if (cur > 0) tile_ptr->push_back(lm_ptr[L]);
+  if (tile_ptr->size() == 1 && L >= 0 && lm_ptr[L] == 0) tile_ptr->clear(), tile_ptr->push_back(0);
+}
+
+int choose_item_len(long long nnz) {
+  // enough items to fill 148 SMs x 64 warps a couple of times, at most 256 entries per item
+  long long len = nnz / (148LL * 64 * 2);
+  len = (len + 31) / 32 * 32;
+  if (len < 32) len = 32;
+  if (len > 256) len = 256;
+  return static_cast<int>(len);
+}
+
+void build_items(const std::vector<int>& cam_ptr, int item_len, std::vector<int>* item_ptr,
+                 std::vector<int>* item_cam, std::vector<int>* cam_item_ptr) {
+  const int C = static_cast<int>(cam_ptr.size()) - 1;
+  item_ptr->clear();
+  item_cam->clear();
+  cam_item_ptr->assign(C + 1, 0);
+  item_ptr->push_back(0);
+  for (int c = 0; c < C; ++c) {
+    (*cam_item_ptr)[c] = static_cast<int>(item_cam->size());
+    for (int b = cam_ptr[c]; b < cam_ptr[c + 1]; b += item_len) {
+      item_cam->push_back(c);
+      item_ptr->push_back(std::min(b + item_len, cam_ptr[c + 1]));
+    }
+  }
+  (*cam_item_ptr)[C] = static_cast<int>(item_cam->size());
+}
+
+// ---------------------------------------------------------------------------------------------
+int Engine::fail(int code, const std::string& what) {
+  err_ = what;
+  return code;
+}
+
+int Engine::check(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return POVAR_OK;
+  err_ = std::string(what) + ": " + cudaGetErrorString(e);
+  return POVAR_ERR_CUDA;
+}
+
+#define PV_CUDA(call)                                   \
+  do {                                                  \
+    const int rc_ = check((call), #call);               \
+    if (rc_ != POVAR_OK) return rc_;                    \
+  } while (0)
+
+double Engine::elapsed(cudaEvent_t a, cudaEvent_t b) {
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, a, b);
+  return ms * 1e-3;
+}
+
+template <typename T>
+static int dev_alloc(std::vector<void*>& allocs, T** p, size_t n) {
+  void* q = nullptr;
+  if (n == 0) n = 1;
+  const cudaError_t e = cudaMalloc(&q, n * sizeof(T));
+  if (e != cudaSuccess) return POVAR_ERR_CUDA;
+  cudaMemset(q, 0, n * sizeof(T));
+  allocs.push_back(q);
+  *p = static_cast<T*>(q);
+  return POVAR_OK;
+}
+
+#define PV_ALLOC(ptr, n)                                                        \
+  do {                                                                          \
+    if (dev_alloc(allocs_, &(ptr), static_cast<size_t>(n)) != POVAR_OK)         \
+      return fail(POVAR_ERR_CUDA, std::string("cudaMalloc failed for ") + #ptr); \
+  } while (0)
+
+int Engine::create(const povar_problem_desc* desc, const povar_options* opt,
+                   const povar_comm_desc* comm, Engine** out, std::string* err) {
+  *out = nullptr;
+  if (!desc || !opt || desc->num_cams <= 0 || desc->num_lms < 0 || desc->num_obs < 0 ||
+      !desc->lm_ptr || !desc->cam_P || (desc->num_obs > 0 && (!desc->obs_cam || !desc->obs_uv))) {
+    if (err) *err = "povar_create: invalid problem description";
+    return POVAR_ERR_INVALID;
+  }
+  if (desc->num_obs >= (1LL << 31)) {
+    if (err) *err = "povar_create: more than 2^31 observations in one shard";
+    return POVAR_ERR_UNSUPPORTED;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    if (err) *err = "povar_create: no CUDA device (this library has no CPU fallback)";
+    return POVAR_ERR_NO_DEVICE;
+  }
+  Engine* e = new Engine();
+  e->opt_ = *opt;
+  e->rank_ = comm ? comm->rank : 0;
+  e->world_ = comm ? comm->world_size : 1;
+  e->device_ = comm ? comm->device : 0;
+  if (e->device_ < 0 || e->device_ >= ndev) {
+    if (err) *err = "povar_create: device ordinal out of range";
+    delete e;
+    return POVAR_ERR_INVALID;
+  }
+  int rc = e->check(cudaSetDevice(e->device_), "cudaSetDevice");
+  if (rc == POVAR_OK) rc = e->check(cudaStreamCreateWithFlags(&e->stream_, cudaStreamNonBlocking), "cudaStreamCreate");
+  for (int i = 0; i < 4 && rc == POVAR_OK; ++i) rc = e->check(cudaEventCreate(&e->ev_[i]), "cudaEventCreate");
+  if (rc == POVAR_OK && e->world_ > 1) {
+    std::string nerr;
+    e->nccl_ = load_nccl(&nerr);
+    if (!e->nccl_) {
+      rc = e->fail(POVAR_ERR_NCCL, nerr);
+    } else {
+      Id128 id;
+      std::memcpy(id.bytes, comm->nccl_id, 128);
+      const int nrc = e->nccl_->CommInitRank(&e->nccl_comm_, e->world_, id, e->rank_);
+      if (nrc != 0) rc = e->fail(POVAR_ERR_NCCL, "ncclCommInitRank failed");
+    }
+  }
+  if (rc == POVAR_OK) rc = e->upload(desc);
+  if (rc != POVAR_OK) {
+    if (err) *err = e->err_;
+    delete e;
+    return rc;
+  }
+  *out = e;
+  return POVAR_OK;
+}
+
+Engine::~Engine() {
+  if (device_ >= 0) cudaSetDevice(device_);
+  if (stream_) cudaStreamSynchronize(stream_);
+  if (nccl_comm_ && nccl_) nccl_->CommDestroy(nccl_comm_);
+  for (void* p : allocs_) cudaFree(p);
+  for (auto& ev : ev_) {
+    if (ev) cudaEventDestroy(ev);
+  }
+  if (stream_) cudaStreamDestroy(stream_);
+}
+
+int Engine::upload(const povar_problem_desc* desc) {
+  const int C = desc->num_cams, L = desc->num_lms;
+  const int nnz = static_cast<int>(desc->num_obs);
+  C_ = C;
+  L_ = L;
+  nnz_ = nnz;
+  // ---- validate + landmark-major arrays
+  std::vector<int> lm_ptr(L + 1), obs_lm(nnz);
+  if (desc->lm_ptr[0] != 0 || desc->lm_ptr[L] != nnz) return fail(POVAR_ERR_INVALID, "lm_ptr does not span the observations");
+  for (int l = 0; l < L; ++l) {
+    const int64_t b = desc->lm_ptr[l], e = desc->lm_ptr[l + 1];
+    if (e < b) return fail(POVAR_ERR_INVALID, "lm_ptr is not monotone");
+    lm_ptr[l] = static_cast<int>(b);
+    for (int64_t o = b; o < e; ++o) {
+      const int c = desc->obs_cam[o];
+      if (c < 0 || c >= C) return fail(POVAR_ERR_INVALID, "camera index out of range");
+      if (o > b && desc->obs_cam[o - 1] >= c) return fail(POVAR_ERR_INVALID, "observations of a landmark must have strictly ascending camera indices");
+      obs_lm[o] = l;
+    }
+  }
+  lm_ptr[L] = nnz;
+  // ---- camera-major copy (stable counting sort => landmarks ascending inside a camera)
+  std::vector<int> cam_ptr(C + 1, 0);
+  for (int o = 0; o < nnz; ++o) cam_ptr[desc->obs_cam[o] + 1]++;
+  for (int c = 0; c < C; ++c) cam_ptr[c + 1] += cam_ptr[c];
+  std::vector<int> fill(cam_ptr.begin(), cam_ptr.end() - 1), csc_lm(nnz);
+  std::vector<double> csc_uv(2 * static_cast<size_t>(nnz));
+  for (int o = 0; o < nnz; ++o) {
+    const int pos = fill[desc->obs_cam[o]]++;
+    csc_lm[pos] = obs_lm[o];
+    csc_uv[2 * static_cast<size_t>(pos)] = desc->obs_uv[2 * static_cast<size_t>(o)];
+    csc_uv[2 * static_cast<size_t>(pos) + 1] = desc->obs_uv[2 * static_cast<size_t>(o) + 1];
+  }
+  std::vector<int> tile_ptr, item_ptr, item_cam, cam_item_ptr;
+  build_tiles(lm_ptr, &tile_ptr);
+  build_items(cam_ptr, choose_item_len(nnz), &item_ptr, &item_cam, &cam_item_ptr);
+
+  DeviceIndex& ix = d_.ix;
+  ix.C = C;
+  ix.L = L;
+  ix.nnz = nnz;
+  ix.num_tiles = static_cast<int>(tile_ptr.size()) - 1;
+  ix.num_items = static_cast<int>(item_cam.size());
+  PV_ALLOC(ix.lm_ptr, L + 1);
+  PV_ALLOC(ix.obs_cam, nnz);
+  PV_ALLOC(ix.obs_lm, nnz);
+  PV_ALLOC(ix.obs_uv, nnz);
+  PV_ALLOC(ix.tile_ptr, tile_ptr.size());
+  PV_ALLOC(ix.cam_ptr, C + 1);
+  PV_ALLOC(ix.csc_lm, nnz);
+  PV_ALLOC(ix.csc_uv, nnz);
+  PV_ALLOC(ix.item_cam, item_cam.size());
+  PV_ALLOC(ix.item_ptr, item_ptr.size());
+  PV_ALLOC(ix.cam_item_ptr, C + 1);
+#define PV_UP(dst, src, n) PV_CUDA(cudaMemcpy((dst), (src), (n), cudaMemcpyHostToDevice))
+  PV_UP(ix.lm_ptr, lm_ptr.data(), sizeof(int) * (L + 1));
+  if (nnz > 0) {
+    PV_UP(ix.obs_cam, desc->obs_cam, sizeof(int) * static_cast<size_t>(nnz));
+    PV_UP(ix.obs_lm, obs_lm.data(), sizeof(int) * static_cast<size_t>(nnz));
+    PV_UP(ix.obs_uv, desc->obs_uv, sizeof(double) * 2 * static_cast<size_t>(nnz));
+    PV_UP(ix.csc_lm, csc_lm.data(), sizeof(int) * static_cast<size_t>(nnz));
+    PV_UP(ix.csc_uv, csc_uv.data(), sizeof(double) * 2 * static_cast<size_t>(nnz));
+    PV_UP(ix.item_cam, item_cam.data(), sizeof(int) * item_cam.size());
+  }
+  PV_UP(ix.tile_ptr, tile_ptr.data(), sizeof(int) * tile_ptr.size());
+  PV_UP(ix.cam_ptr, cam_ptr.data(), sizeof(int) * (C + 1));
+  PV_UP(ix.item_ptr, item_ptr.data(), sizeof(int) * item_ptr.size());
+  PV_UP(ix.cam_item_ptr, cam_item_ptr.data(), sizeof(int) * (C + 1));
+
+  // ---- state and work arrays
+  const size_t C12 = static_cast<size_t>(C) * 12, C144 = static_cast<size_t>(C) * 144;
+  PV_ALLOC(d_.P, C12);
+  PV_ALLOC(d_.P_bak, C12);
+  PV_ALLOC(P_prev_, C12);
+  PV_ALLOC(d_.X, static_cast<size_t>(L) * 4);
+  PV_ALLOC(d_.X_bak, static_cast<size_t>(L) * 4);
+  PV_ALLOC(d_.pose_scale, C12);
+  PV_ALLOC(d_.lm_scale, static_cast<size_t>(L) * 4);
+  PV_ALLOC(d_.lm_hraw, static_cast<size_t>(L) * 10);
+  PV_ALLOC(d_.lm_graw, static_cast<size_t>(L) * 4);
+  PV_ALLOC(d_.hll_inv, static_cast<size_t>(L) * 6);
+  PV_ALLOC(d_.lm_rec, static_cast<size_t>(L) * kLmRec);
+  PV_ALLOC(d_.kron, static_cast<size_t>(C) * kKron);
+  PV_ALLOC(d_.item_kron, static_cast<size_t>(ix.num_items) * kKron);
+  PV_ALLOC(d_.item_part, static_cast<size_t>(ix.num_items) * 12);
+  PV_ALLOC(d_.cam_raw, C12);
+  PV_ALLOC(d_.Bmat, C144);
+  PV_ALLOC(d_.Binv, C144);
+  PV_ALLOC(d_.Mprec, C144);
+  PV_ALLOC(d_.b, C12);
+  PV_ALLOC(d_.vec_tmp, C12);
+  PV_ALLOC(d_.vec_acc, C12);
+  PV_ALLOC(d_.vec_y, C12);
+  PV_ALLOC(d_.vec_x, C12);
+  PV_ALLOC(d_.cg_r, C12);
+  PV_ALLOC(d_.cg_p, C12);
+  PV_ALLOC(d_.cg_z, C12);
+  PV_ALLOC(d_.cg_q, C12);
+  PV_ALLOC(d_.cg_x, C12);
+  PV_ALLOC(d_.norm_part, static_cast<size_t>(C) * 4);
+  PV_ALLOC(d_.cost_part, static_cast<size_t>(cost_blocks(d_)) * 8);
+  PV_ALLOC(d_.cost_out, 1);
+  PV_ALLOC(d_.scalar_part, static_cast<size_t>(scalar_blocks(d_)) + 8);
+  PV_ALLOC(d_.scalar_out, 8);
+  PV_ALLOC(d_.flags, 4);
+  PV_ALLOC(d_.ctl, 1);
+  PV_UP(d_.P, desc->cam_P, sizeof(double) * C12);
+#undef PV_UP
+  return POVAR_OK;
+}
+
+int Engine::allreduce(double* buf, size_t n) {
+  if (world_ <= 1) return POVAR_OK;
+  // ncclDouble = 8, ncclSum = 0
+  const int rc = nccl_->AllReduce(buf, buf, n, 8, 0, nccl_comm_, stream_);
+  if (rc != 0) return fail(POVAR_ERR_NCCL, "ncclAllReduce failed");
+  return POVAR_OK;
+}
+
+void Engine::set_model(bool joint, double alpha) {
+  mp_.c1 = std::sqrt(1.0 - alpha);
+  mp_.c2 = std::sqrt(alpha);
+  mp_.robust_norm = opt_.robust_norm;
+  mp_.huber = opt_.huber_parameter;
+  mp_.jacobi_eps = opt_.jacobi_scaling_epsilon > 0 ? opt_.jacobi_scaling_epsilon : kEpsSqrtHost;
+  (void)joint;
+}
+
+// ---------------------------------------------------------------------------------------------
+int Engine::init_varproj(double alpha) {
+  PV_CUDA(cudaSetDevice(device_));
+  set_model(false, alpha);
+  launch_init_varproj(d_, mp_, lc());
+  PV_CUDA(cudaGetLastError());
+  return POVAR_OK;
+}
+
+int Engine::cost(bool joint, double alpha, povar_residual_info* out) {
+  PV_CUDA(cudaSetDevice(device_));
+  set_model(joint, joint ? opt_.alpha : alpha);
+  PV_CUDA(cudaEventRecord(ev_[0], stream_));
+  launch_cost(d_, mp_, joint, lc());
+  PV_CUDA(cudaGetLastError());
+  CostAccum h{};
+  if (world_ > 1) {
+    // sums travel as doubles: {err_all, rsum_all, err_valid, rsum_valid, n_all, n_valid, nonfinite}
+    PV_CUDA(cudaMemcpyAsync(&h, d_.cost_out, sizeof(h), cudaMemcpyDeviceToHost, stream_));
+    PV_CUDA(cudaStreamSynchronize(stream_));
+    double v[8] = {h.err_all, h.rsum_all, h.err_valid, h.rsum_valid, static_cast<double>(h.n_all),
+                   static_cast<double>(h.n_valid), static_cast<double>(h.nonfinite), 0.0};
+    PV_CUDA(cudaMemcpyAsync(d_.scalar_out, v, sizeof(v), cudaMemcpyHostToDevice, stream_));
+    const int rc = allreduce(d_.scalar_out, 8);
+    if (rc != POVAR_OK) return rc;
+    PV_CUDA(cudaMemcpyAsync(v, d_.scalar_out, sizeof(v), cudaMemcpyDeviceToHost, stream_));
+    PV_CUDA(cudaEventRecord(ev_[1], stream_));
+    PV_CUDA(cudaStreamSynchronize(stream_));
+    h.err_all = v[0];
+    h.rsum_all = v[1];
+    h.err_valid = v[2];
+    h.rsum_valid = v[3];
+    h.n_all = static_cast<long long>(v[4] + 0.5);
+    h.n_valid = static_cast<long long>(v[5] + 0.5);
+    h.nonfinite = v[6] > 0 ? 1 : 0;
+  } else {
+    PV_CUDA(cudaMemcpyAsync(&h, d_.cost_out, sizeof(h), cudaMemcpyDeviceToHost, stream_));
+    PV_CUDA(cudaEventRecord(ev_[1], stream_));
+    PV_CUDA(cudaStreamSynchronize(stream_));
+  }
+  times_.residual += elapsed(ev_[0], ev_[1]);
+  out->num_obs_all = h.n_all;
+  out->error_all = h.err_all;
+  out->residual_sum_all = h.rsum_all;
+  out->num_obs_valid = h.n_valid;
+  out->error_valid = h.err_valid;
+  out->residual_sum_valid = h.rsum_valid;
+  out->is_numerically_valid = h.nonfinite ? 0 : 1;
+  return POVAR_OK;
+}
+
+int Engine::linearize(bool joint, double alpha) {
+  PV_CUDA(cudaSetDevice(device_));
+  set_model(joint, joint ? opt_.alpha : alpha);
+  joint_lin_ = joint;
+  dim_ = joint ? 11 : 12;
+  const bool power = joint ? true
+                           : (opt_.solver_type_step_1 == POVAR_POWER_VARPROJ ||
+                              opt_.solver_type_step_1 == POVAR_POWER_SCHUR_COMPLEMENT);
+  PV_CUDA(cudaEventRecord(ev_[0], stream_));
+  PV_CUDA(cudaMemsetAsync(d_.flags, 0, 4 * sizeof(int), stream_));
+  // landmark side: Jl^T Jl, Jl^T r, column scales (LinearizorSC step 1 does not scale Jl:
+  // solver/linearizor_sc.cpp:174-203)
+  launch_lin_landmark(d_, mp_, joint, power, lc());
+  // camera side: Jp^T Jp as Kronecker sums, then the pose scales
+  launch_kron(d_, mp_, joint, KRON_HPP, lc());
+  launch_reduce_items(d_, d_.item_kron, kKron, d_.kron, false, lc());
+  {
+    const int rc = allreduce(d_.kron, static_cast<size_t>(C_) * kKron);
+    if (rc != POVAR_OK) return rc;
+  }
+  launch_cam_scale(d_, mp_, lc());
+  PV_CUDA(cudaGetLastError());
+  int flags[4] = {0, 0, 0, 0};
+  PV_CUDA(cudaMemcpyAsync(flags, d_.flags, sizeof(flags), cudaMemcpyDeviceToHost, stream_));
+  PV_CUDA(cudaEventRecord(ev_[1], stream_));
+  PV_CUDA(cudaStreamSynchronize(stream_));
+  times_.linearize += elapsed(ev_[0], ev_[1]);
+  if (world_ > 1) {
+    double v[1] = {static_cast<double>(flags[0])};
+    PV_CUDA(cudaMemcpyAsync(d_.scalar_out, v, sizeof(v), cudaMemcpyHostToDevice, stream_));
+    const int rc = allreduce(d_.scalar_out, 1);
+    if (rc != POVAR_OK) return rc;
+    PV_CUDA(cudaMemcpyAsync(v, d_.scalar_out, sizeof(v), cudaMemcpyDeviceToHost, stream_));
+    PV_CUDA(cudaStreamSynchronize(stream_));
+    flags[0] = v[0] > 0 ? 1 : 0;
+  }
+  if (flags[0]) return fail(POVAR_NUM_LINEARIZATION, "did not expect numerical failure during linearization");
+  return POVAR_OK;
+}
+
+// raw_c = sum over the observations of camera c of the camera half of E0 (or of b), all ranks
+void Engine::e0_product(bool joint, const double* y, bool in_series) {
+  launch_e0_landmark(d_, mp_, joint, y, in_series, lc());
+  launch_passB(d_, mp_, joint, PASSB_E0, in_series, lc());
+  launch_reduce_items(d_, d_.item_part, 12, d_.cam_raw, in_series, lc());
+  allreduce(d_.cam_raw, static_cast<size_t>(C_) * 12);
+}
+
+int Engine::solve_power(bool joint, double lambda) {
+  const bool poba = !joint && opt_.solver_type_step_1 == POVAR_POWER_SCHUR_COMPLEMENT;
+  const double lambda_lm = joint ? lambda : (poba ? lambda : 0.0);
+  PV_CUDA(cudaEventRecord(ev_[0], stream_));
+  // prepare_Hb_*: Hll^-1 and Hll^-1 Jl^T r per landmark; B^-1 per camera; b
+  launch_prep_landmark(d_, joint, lambda_lm, lc());
+  launch_cam_binv(d_, joint, lambda, lc());
+  launch_passB(d_, mp_, joint, PASSB_B, false, lc());
+  launch_reduce_items(d_, d_.item_part, 12, d_.cam_raw, false, lc());
+  {
+    const int rc = allreduce(d_.cam_raw, static_cast<size_t>(C_) * 12);
+    if (rc != POVAR_OK) return rc;
+  }
+  PV_CUDA(cudaEventRecord(ev_[1], stream_));
+  // solve_*: accum = B^-1(-b); tmp = B^-1 E0 tmp; accum += tmp; early exit on zeta < eta
+  launch_finish_b(d_, joint, lc());
+  const int m = opt_.power_sc_iterations;
+  launch_series_start(d_, opt_.r_tolerance, m, lc());
+  for (int i = 1; i <= m; ++i) {
+    e0_product(joint, d_.vec_y, true);
+    launch_series_term(d_, joint, i, opt_.eta, opt_.r_tolerance, lc());
+  }
+  PV_CUDA(cudaEventRecord(ev_[2], stream_));
+  PV_CUDA(cudaGetLastError());
+  return POVAR_OK;
+}
+
+int Engine::finish_solve(bool joint, double* inc, int32_t* iterations) {
+  SeriesCtl h{};
+  PV_CUDA(cudaMemcpyAsync(&h, d_.ctl, sizeof(h), cudaMemcpyDeviceToHost, stream_));
+  if (inc) {
+    PV_CUDA(cudaMemcpyAsync(inc, d_.vec_acc, sizeof(double) * static_cast<size_t>(C_) * (joint ? 11 : 12),
+                            cudaMemcpyDeviceToHost, stream_));
+  }
+  PV_CUDA(cudaStreamSynchronize(stream_));
+  times_.prepare += elapsed(ev_[0], ev_[1]);
+  times_.reduced_solve += elapsed(ev_[1], ev_[2]);
+  if (iterations) *iterations = h.iterations;
+  if (h.nonfinite) return POVAR_NUM_NONFINITE_INC;
+  return POVAR_OK;
+}
+
+int Engine::solve(bool joint, double lambda, double* inc, int32_t* iterations) {
+  PV_CUDA(cudaSetDevice(device_));
+  if (joint != joint_lin_) return fail(POVAR_ERR_INVALID, "solve called without a matching linearize");
+  lambda_ = lambda;
+  int rc;
+  if (joint) {
+    rc = opt_.solver_type_step_2 == POVAR_RIPOBA ? solve_power(true, lambda) : solve_pcg(true, lambda);
+  } else {
+    switch (opt_.solver_type_step_1) {
+      case POVAR_POWER_VARPROJ:
+      case POVAR_POWER_SCHUR_COMPLEMENT:
+        rc = solve_power(false, lambda);
+        break;
+      case POVAR_PCG:
+        rc = solve_pcg(false, lambda);
+        break;
+      case POVAR_CHOLESKY:
+        rc = solve_cholesky(lambda);
+        break;
+      default:
+        return fail(POVAR_ERR_INVALID, "unknown solver_type_step_1");
+    }
+  }
+  if (rc != POVAR_OK) return rc;
+  return finish_solve(joint, inc, iterations);
+}
+
+int Engine::solve_pcg(bool joint, double lambda) {
+  (void)joint;
+  (void)lambda;
+  return fail(POVAR_ERR_UNSUPPORTED, "PCG / RIPCG: not built yet");
+}
+
+int Engine::solve_cholesky(double lambda) {
+  (void)lambda;
+  return fail(POVAR_ERR_UNSUPPORTED, "CHOLESKY: not built yet");
+}
+
+int Engine::apply(bool joint, double alpha, double* l_diff) {
+  PV_CUDA(cudaSetDevice(device_));
+  if (joint != joint_lin_) return fail(POVAR_ERR_INVALID, "apply called without a matching linearize");
+  set_model(joint, joint ? opt_.alpha : alpha);
+  PV_CUDA(cudaEventRecord(ev_[0], stream_));
+  const size_t C12 = static_cast<size_t>(C_) * 12;
+  if (joint) {
+    // apply_joint (linearizor_power_varproj.cpp:276-308): landmarks first, then P += s o (Pi inc)
+    launch_make_y(d_, true, d_.vec_acc, d_.vec_y, lc());
+    launch_backsub_joint(d_, mp_, d_.vec_y, lc());
+    launch_cam_update_joint(d_, d_.vec_y, lc());
+  } else if (opt_.solver_type_step_1 == POVAR_POWER_SCHUR_COMPLEMENT) {
+    // linearizor_power_varproj.cpp:260-270
+    launch_make_y(d_, false, d_.vec_acc, d_.vec_y, lc());
+    launch_backsub_poba(d_, mp_, d_.vec_y, lc());
+    launch_cam_update_pose(d_, d_.vec_acc, lc());
+  } else {
+    // VarPro flavours (linearizor_power_varproj.cpp:250-259, linearizor_sc.cpp:69-89):
+    // cameras first, then the closed-form landmark re-solve
+    PV_CUDA(cudaMemcpyAsync(P_prev_, d_.P, sizeof(double) * C12, cudaMemcpyDeviceToDevice, stream_));
+    launch_cam_update_pose(d_, d_.vec_acc, lc());
+    DeviceState tmp = d_;
+    tmp.P_bak = P_prev_;
+    launch_backsub_varpro(tmp, mp_, d_.vec_acc, lc());
+  }
+  PV_CUDA(cudaGetLastError());
+  {
+    const int rc = allreduce(d_.scalar_out, 1);
+    if (rc != POVAR_OK) return rc;
+  }
+  double v = 0.0;
+  PV_CUDA(cudaMemcpyAsync(&v, d_.scalar_out, sizeof(double), cudaMemcpyDeviceToHost, stream_));
+  PV_CUDA(cudaEventRecord(ev_[1], stream_));
+  PV_CUDA(cudaStreamSynchronize(stream_));
+  times_.back_substitution += elapsed(ev_[0], ev_[1]);
+  if (l_diff) *l_diff = v;
+  return POVAR_OK;
+}
+
+int Engine::backup(int which) {
+  (void)which;
+  PV_CUDA(cudaSetDevice(device_));
+  PV_CUDA(cudaMemcpyAsync(d_.P_bak, d_.P, sizeof(double) * static_cast<size_t>(C_) * 12, cudaMemcpyDeviceToDevice, stream_));
+  PV_CUDA(cudaMemcpyAsync(d_.X_bak, d_.X, sizeof(double) * static_cast<size_t>(L_) * 4, cudaMemcpyDeviceToDevice, stream_));
+  return POVAR_OK;
+}
+
+int Engine::restore(int which) {
+  (void)which;
+  PV_CUDA(cudaSetDevice(device_));
+  PV_CUDA(cudaMemcpyAsync(d_.P, d_.P_bak, sizeof(double) * static_cast<size_t>(C_) * 12, cudaMemcpyDeviceToDevice, stream_));
+  PV_CUDA(cudaMemcpyAsync(d_.X, d_.X_bak, sizeof(double) * static_cast<size_t>(L_) * 4, cudaMemcpyDeviceToDevice, stream_));
+  return POVAR_OK;
+}
+
+int Engine::to_homogeneous() {
+  PV_CUDA(cudaSetDevice(device_));
+  launch_to_homogeneous(d_, lc());
+  launch_normalize_cams(d_, lc());
+  PV_CUDA(cudaGetLastError());
+  return POVAR_OK;
+}
+
+int Engine::normalize_joint() {
+  PV_CUDA(cudaSetDevice(device_));
+  launch_normalize_cams(d_, lc());
+  launch_normalize_joint(d_, lc());
+  PV_CUDA(cudaGetLastError());
+  return POVAR_OK;
+}
+
+int Engine::get_state(int which, double* cam_P, double* lms) {
+  PV_CUDA(cudaSetDevice(device_));
+  PV_CUDA(cudaStreamSynchronize(stream_));
+  if (cam_P) PV_CUDA(cudaMemcpy(cam_P, d_.P, sizeof(double) * static_cast<size_t>(C_) * 12, cudaMemcpyDeviceToHost));
+  if (lms) {
+    std::vector<double> h(static_cast<size_t>(L_) * 4);
+    PV_CUDA(cudaMemcpy(h.data(), d_.X, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
+    if (which == POVAR_STATE_JOINT) {
+      std::memcpy(lms, h.data(), sizeof(double) * h.size());
+    } else {
+      for (int l = 0; l < L_; ++l) {
+        for (int k = 0; k < 3; ++k) lms[3 * static_cast<size_t>(l) + k] = h[4 * static_cast<size_t>(l) + k];
+      }
+    }
+  }
+  return POVAR_OK;
+}
+
+int Engine::set_state(int which, const double* cam_P, const double* lms) {
+  PV_CUDA(cudaSetDevice(device_));
+  PV_CUDA(cudaStreamSynchronize(stream_));
+  if (cam_P) PV_CUDA(cudaMemcpy(d_.P, cam_P, sizeof(double) * static_cast<size_t>(C_) * 12, cudaMemcpyHostToDevice));
+  if (lms) {
+    std::vector<double> h(static_cast<size_t>(L_) * 4);
+    for (int l = 0; l < L_; ++l) {
+      if (which == POVAR_STATE_JOINT) {
+        for (int k = 0; k < 4; ++k) h[4 * static_cast<size_t>(l) + k] = lms[4 * static_cast<size_t>(l) + k];
+      } else {
+        for (int k = 0; k < 3; ++k) h[4 * static_cast<size_t>(l) + k] = lms[3 * static_cast<size_t>(l) + k];
+        h[4 * static_cast<size_t>(l) + 3] = 1.0;
+      }
+    }
+    PV_CUDA(cudaMemcpy(d_.X, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice));
+  }
+  return POVAR_OK;
+}
+
+int64_t Engine::debug_read(const char* name, double* out, int64_t capacity) {
+  if (cudaSetDevice(device_) != cudaSuccess) return POVAR_ERR_CUDA;
+  cudaStreamSynchronize(stream_);
+  const std::string n(name ? name : "");
+  const double* dsrc = nullptr;
+  const int* isrc = nullptr;
+  int64_t count = 0;
+  const int D = dim_;
+  if (n == "P") dsrc = d_.P, count = 12LL * C_;
+  else if (n == "X") dsrc = d_.X, count = 4LL * L_;
+  else if (n == "pose_scale") dsrc = d_.pose_scale, count = 12LL * C_;
+  else if (n == "lm_scale") dsrc = d_.lm_scale, count = 4LL * L_;
+  else if (n == "lm_hraw") dsrc = d_.lm_hraw, count = 10LL * L_;
+  else if (n == "lm_graw") dsrc = d_.lm_graw, count = 4LL * L_;
+  else if (n == "hll_inv") dsrc = d_.hll_inv, count = 6LL * L_;
+  else if (n == "lm_rec") dsrc = d_.lm_rec, count = static_cast<int64_t>(kLmRec) * L_;
+  else if (n == "kron") dsrc = d_.kron, count = static_cast<int64_t>(kKron) * C_;
+  else if (n == "b_mat") dsrc = d_.Bmat, count = 144LL * C_;
+  else if (n == "b_inv") dsrc = d_.Binv, count = 144LL * C_;
+  else if (n == "b") dsrc = d_.b, count = static_cast<int64_t>(D) * C_;
+  else if (n == "inc") dsrc = d_.vec_acc, count = static_cast<int64_t>(D) * C_;
+  else if (n == "cam_raw") dsrc = d_.cam_raw, count = 12LL * C_;
+  else if (n == "vec_y") dsrc = d_.vec_y, count = 12LL * C_;
+  else if (n == "lm_ptr") isrc = d_.ix.lm_ptr, count = L_ + 1;
+  else if (n == "obs_cam") isrc = d_.ix.obs_cam, count = nnz_;
+  else if (n == "obs_lm") isrc = d_.ix.obs_lm, count = nnz_;
+  else if (n == "tile_ptr") isrc = d_.ix.tile_ptr, count = d_.ix.num_tiles + 1;
+  else if (n == "cam_ptr") isrc = d_.ix.cam_ptr, count = C_ + 1;
+  else if (n == "csc_lm") isrc = d_.ix.csc_lm, count = nnz_;
+  else if (n == "item_ptr") isrc = d_.ix.item_ptr, count = d_.ix.num_items + 1;
+  else if (n == "item_cam") isrc = d_.ix.item_cam, count = d_.ix.num_items;
+  else {
+    fail(POVAR_ERR_INVALID, "debug_read: unknown array '" + n + "'");
+    return POVAR_ERR_INVALID;
+  }
+  if (!out) return count;
+  if (capacity < count) {
+    fail(POVAR_ERR_INVALID, "debug_read: buffer too small");
+    return POVAR_ERR_INVALID;
+  }
+  if (dsrc) {
+    if (cudaMemcpy(out, dsrc, sizeof(double) * count, cudaMemcpyDeviceToHost) != cudaSuccess) return POVAR_ERR_CUDA;
+  } else {
+    std::vector<int> h(count);
+    if (cudaMemcpy(h.data(), isrc, sizeof(int) * count, cudaMemcpyDeviceToHost) != cudaSuccess) return POVAR_ERR_CUDA;
+    for (int64_t i = 0; i < count; ++i) out[i] = h[i];
+  }
+  return count;
+}
+
+// E0 x with the current linearisation and the Hll^-1 of the last solve
+int Engine::right_mul_e0(bool joint, const double* x, double* out) {
+  PV_CUDA(cudaSetDevice(device_));
+  if (joint != joint_lin_) return fail(POVAR_ERR_INVALID, "right_mul_e0: no matching linearisation");
+  const size_t n = static_cast<size_t>(C_) * (joint ? 11 : 12);
+  PV_CUDA(cudaMemcpyAsync(d_.vec_x, x, sizeof(double) * n, cudaMemcpyHostToDevice, stream_));
+  launch_make_y(d_, joint, d_.vec_x, d_.vec_y, lc());
+  e0_product(joint, d_.vec_y, false);
+  launch_e0_finish(d_, joint, d_.vec_x, lc());
+  PV_CUDA(cudaGetLastError());
+  PV_CUDA(cudaMemcpyAsync(out, d_.vec_x, sizeof(double) * n, cudaMemcpyDeviceToHost, stream_));
+  PV_CUDA(cudaStreamSynchronize(stream_));
+  return POVAR_OK;
+}
+
+// `terms` full power-series terms (landmark pass, camera pass, item reduction, allreduce, B^-1
+// and norms) on the current linearisation, no early exit: the SpMV measurement of bench.py.
+int Engine::bench_power_terms(bool joint, int terms, double* seconds_per_term) {
+  PV_CUDA(cudaSetDevice(device_));
+  if (joint != joint_lin_) return fail(POVAR_ERR_INVALID, "bench_power_terms: no matching linearisation");
+  if (terms <= 0) return fail(POVAR_ERR_INVALID, "bench_power_terms: terms must be positive");
+  launch_finish_b(d_, joint, lc());
+  launch_series_start(d_, -1.0, terms, lc());
+  PV_CUDA(cudaEventRecord(ev_[0], stream_));
+  for (int i = 1; i <= terms; ++i) {
+    e0_product(joint, d_.vec_y, true);
+    launch_series_term(d_, joint, i, /*eta=*/-1.0, /*r_tolerance=*/-1.0, lc());
+  }
+  PV_CUDA(cudaEventRecord(ev_[1], stream_));
+  PV_CUDA(cudaGetLastError());
+  PV_CUDA(cudaStreamSynchronize(stream_));
+  if (seconds_per_term) *seconds_per_term = elapsed(ev_[0], ev_[1]) / terms;
+  return POVAR_OK;
+}
+
+}  // namespace povar

@@ -1,0 +1,90 @@
+// Engine: owns the device state of one shard and sequences the kernels of the hot path.
+#pragma once
+
+#include <string>
+#include <vector>
+
+#include "povar_internal.h"
+
+namespace povar {
+
+struct NcclApi;  // dlopen'ed entry points (engine.cu)
+
+struct PhaseTimes {
+  double residual = 0, linearize = 0, prepare = 0, reduced_solve = 0, back_substitution = 0;
+};
+
+class Engine {
+ public:
+  static int create(const povar_problem_desc* desc, const povar_options* opt,
+                    const povar_comm_desc* comm, Engine** out, std::string* err);
+  ~Engine();
+
+  int init_varproj(double alpha);
+  int cost(bool joint, double alpha, povar_residual_info* out);
+  int linearize(bool joint, double alpha);
+  int solve(bool joint, double lambda, double* inc, int32_t* iterations);
+  int apply(bool joint, double alpha, double* l_diff);
+  int backup(int which);
+  int restore(int which);
+  int to_homogeneous();
+  int normalize_joint();
+  int get_state(int which, double* cam_P, double* lms);
+  int set_state(int which, const double* cam_P, const double* lms);
+  int64_t debug_read(const char* name, double* out, int64_t capacity);
+  int right_mul_e0(bool joint, const double* x, double* out);
+  int bench_power_terms(bool joint, int terms, double* seconds_per_term);
+
+  const char* last_error() const { return err_.c_str(); }
+  long long launches() const { return launches_; }
+  const povar_options& options() const { return opt_; }
+  const PhaseTimes& last_times() const { return times_; }
+  void reset_times() { times_ = PhaseTimes(); }
+  int world_size() const { return world_; }
+  int rank() const { return rank_; }
+
+ private:
+  Engine() = default;
+  int fail(int code, const std::string& what);
+  int check(cudaError_t e, const char* what);
+  int upload(const povar_problem_desc* desc);
+  int allreduce(double* buf, size_t n);
+  void set_model(bool joint, double alpha);
+  int solve_power(bool joint, double lambda);
+  int solve_pcg(bool joint, double lambda);
+  int solve_cholesky(double lambda);
+  void e0_product(bool joint, const double* y, bool in_series);
+  int finish_solve(bool joint, double* inc, int32_t* iterations);
+  LaunchCfg lc() { return LaunchCfg{stream_, &launches_}; }
+  double elapsed(cudaEvent_t a, cudaEvent_t b);
+
+  povar_options opt_{};
+  DeviceState d_{};
+  ModelParams mp_{};
+  std::vector<void*> allocs_;
+  cudaStream_t stream_ = nullptr;
+  cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
+  long long launches_ = 0;
+  std::string err_;
+  PhaseTimes times_;
+  // solver state
+  bool joint_lin_ = false;        // which model the current linearisation belongs to
+  double lambda_ = 0.0;           // damping of the last solve (landmark damping of apply)
+  int dim_ = 12;
+  double* P_prev_ = nullptr;      // cameras of the linearisation point during a VarPro apply
+  // distributed
+  int rank_ = 0, world_ = 1, device_ = 0;
+  void* nccl_comm_ = nullptr;
+  NcclApi* nccl_ = nullptr;
+  // host mirrors
+  int C_ = 0, L_ = 0;
+  long long nnz_ = 0;
+};
+
+// host-side index construction (engine.cu), exposed for the CPU tests through the C ABI
+void build_tiles(const std::vector<int>& lm_ptr, std::vector<int>* tile_ptr);
+void build_items(const std::vector<int>& cam_ptr, int item_len, std::vector<int>* item_ptr,
+                 std::vector<int>* item_cam, std::vector<int>* cam_item_ptr);
+int choose_item_len(long long nnz);
+
+}  // namespace povar

@@ -1,0 +1,196 @@
+// Host-side problem plumbing behind the C ABI: BAL text reader, canonical ordering, sharding.
+// No CUDA in this file.
+//
+// Replaces BalProblem::load_bal_eccv (/root/reference/src/rootba_povar/bal/bal_problem.cpp:182-303)
+// for the 15-parameter files written by --create-dataset (bal_problem.cpp:306-471):
+//   C L N / N x (cam lm x y) / C x 15 / L x 3
+// The reference keeps a landmark's observations in a std::map<cam, obs> (bal_problem.hpp:226), so
+// its canonical order is landmark index, then camera index ascending, whatever the file order;
+// the loader flips the image y axis (bal_problem.cpp:240) and treats a repeated (cam, lm) pair as
+// fatal (bal_problem.cpp:227).  The random landmark draw of the loader (bal_problem.cpp:255-268) is
+// not reproduced: iteration 0 of step 1 overwrites all landmarks.
+#include <algorithm>
+#include <cerrno>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../../include/povar_b200.h"
+
+namespace {
+
+void set_err(char* err, size_t len, const std::string& msg) {
+  if (err && len > 0) {
+    std::snprintf(err, len, "%s", msg.c_str());
+  }
+}
+
+// minimal fast tokenizer over a whole-file buffer
+struct Cursor {
+  const char* p;
+  const char* end;
+  void skip_ws() {
+    while (p < end && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) ++p;
+  }
+  bool next_int(long long* out) {
+    skip_ws();
+    if (p >= end) return false;
+    char* q = nullptr;
+    errno = 0;
+    const long long v = std::strtoll(p, &q, 10);
+    if (q == p || errno != 0) return false;
+    p = q;
+    *out = v;
+    return true;
+  }
+  bool next_double(double* out) {
+    skip_ws();
+    if (p >= end) return false;
+    char* q = nullptr;
+    errno = 0;
+    const double v = std::strtod(p, &q);
+    if (q == p) return false;
+    p = q;
+    *out = v;
+    return true;
+  }
+};
+
+}  // namespace
+
+extern "C" int povar_canonical_order(int32_t num_cams, int32_t num_lms, int64_t num_obs,
+                                     const int32_t* cam, const int32_t* lm, int64_t* perm,
+                                     int64_t* lm_ptr) {
+  if (num_cams <= 0 || num_lms < 0 || num_obs < 0 || !perm || !lm_ptr) return POVAR_ERR_INVALID;
+  if (num_obs > 0 && (!cam || !lm)) return POVAR_ERR_INVALID;
+  // counting sort by landmark (stable), then sort each landmark's run by camera
+  std::vector<int64_t> count(static_cast<size_t>(num_lms) + 1, 0);
+  for (int64_t i = 0; i < num_obs; ++i) {
+    if (lm[i] < 0 || lm[i] >= num_lms || cam[i] < 0 || cam[i] >= num_cams) return POVAR_ERR_INVALID;
+    count[static_cast<size_t>(lm[i]) + 1]++;
+  }
+  for (int32_t l = 0; l < num_lms; ++l) count[l + 1] += count[l];
+  for (int32_t l = 0; l <= num_lms; ++l) lm_ptr[l] = count[l];
+  std::vector<int64_t> fill(count.begin(), count.end() - 1);
+  for (int64_t i = 0; i < num_obs; ++i) perm[fill[lm[i]]++] = i;
+  for (int32_t l = 0; l < num_lms; ++l) {
+    int64_t* b = perm + lm_ptr[l];
+    int64_t* e = perm + lm_ptr[l + 1];
+    std::sort(b, e, [cam](int64_t a, int64_t c) { return cam[a] < cam[c]; });
+    for (int64_t* q = b + 1; q < e; ++q) {
+      if (cam[*q] == cam[*(q - 1)]) return POVAR_ERR_INVALID;  // duplicate observation
+    }
+  }
+  return POVAR_OK;
+}
+
+extern "C" int povar_partition_landmarks(int32_t num_lms, const int64_t* lm_ptr, int32_t world_size,
+                                         int32_t* bounds) {
+  if (num_lms < 0 || world_size <= 0 || !lm_ptr || !bounds) return POVAR_ERR_INVALID;
+  // contiguous landmark ranges with (nearly) equal observation counts: rank r ends at the first
+  // landmark whose cumulative observation count reaches (r+1)/world of the total
+  const int64_t total = lm_ptr[num_lms];
+  bounds[0] = 0;
+  for (int32_t r = 1; r < world_size; ++r) {
+    const int64_t target = (total * r + world_size / 2) / world_size;
+    // first landmark boundary at or after the target, or the one before it if that is closer
+    int64_t l = std::lower_bound(lm_ptr, lm_ptr + num_lms + 1, target) - lm_ptr;
+    if (l > num_lms) l = num_lms;
+    if (l > 0 && (target - lm_ptr[l - 1]) <= (lm_ptr[l] - target)) --l;
+    if (l < bounds[r - 1]) l = bounds[r - 1];
+    bounds[r] = static_cast<int32_t>(l);
+  }
+  bounds[world_size] = num_lms;
+  return POVAR_OK;
+}
+
+extern "C" void povar_bal_free(povar_bal_data* data) {
+  if (!data) return;
+  std::free(data->lm_ptr);
+  std::free(data->obs_cam);
+  std::free(data->obs_uv);
+  std::free(data->cam_params);
+  std::memset(data, 0, sizeof(*data));
+}
+
+extern "C" int povar_bal_read(const char* path, povar_bal_data* out, char* err, size_t err_len) {
+  if (!path || !out) return POVAR_ERR_INVALID;
+  std::memset(out, 0, sizeof(*out));
+  FILE* f = std::fopen(path, "rb");
+  if (!f) {
+    set_err(err, err_len, std::string("Could not open '") + path + "'");
+    return POVAR_ERR_IO;
+  }
+  std::fseek(f, 0, SEEK_END);
+  const long size = std::ftell(f);
+  std::fseek(f, 0, SEEK_SET);
+  std::vector<char> buf(static_cast<size_t>(size) + 1);
+  const size_t got = std::fread(buf.data(), 1, static_cast<size_t>(size), f);
+  std::fclose(f);
+  buf[got] = '\0';
+  Cursor cur{buf.data(), buf.data() + got};
+
+  long long C = 0, L = 0, N = 0;
+  if (!cur.next_int(&C) || !cur.next_int(&L) || !cur.next_int(&N) || C <= 0 || L <= 0 || N <= 0) {
+    set_err(err, err_len, std::string("Failed to parse header of '") + path + "'");
+    return POVAR_ERR_IO;
+  }
+  std::vector<int32_t> cam(static_cast<size_t>(N)), lm(static_cast<size_t>(N));
+  std::vector<double> xy(2 * static_cast<size_t>(N));
+  for (long long i = 0; i < N; ++i) {
+    long long c = 0, l = 0;
+    double x = 0, y = 0;
+    if (!cur.next_int(&c) || !cur.next_int(&l) || !cur.next_double(&x) || !cur.next_double(&y)) {
+      set_err(err, err_len, std::string("Failed to parse observations of '") + path + "'");
+      return POVAR_ERR_IO;
+    }
+    if (c < 0 || c >= C || l < 0 || l >= L) {
+      set_err(err, err_len, std::string("Index out of range in '") + path + "'");
+      return POVAR_ERR_INVALID;
+    }
+    cam[i] = static_cast<int32_t>(c);
+    lm[i] = static_cast<int32_t>(l);
+    xy[2 * i] = x;
+    xy[2 * i + 1] = -y;  // invert y axis, bal_problem.cpp:240
+  }
+  out->cam_params = static_cast<double*>(std::malloc(sizeof(double) * 15 * static_cast<size_t>(C)));
+  for (long long i = 0; i < 15 * C; ++i) {
+    if (!cur.next_double(&out->cam_params[i])) {
+      set_err(err, err_len, std::string("Failed to parse cameras of '") + path + "'");
+      povar_bal_free(out);
+      return POVAR_ERR_IO;
+    }
+  }
+  // the L x 3 landmark block must be present (the reference's loader reads it) but is not used
+  for (long long i = 0; i < 3 * L; ++i) {
+    double v;
+    if (!cur.next_double(&v)) {
+      set_err(err, err_len, std::string("Failed to parse landmarks of '") + path + "'");
+      povar_bal_free(out);
+      return POVAR_ERR_IO;
+    }
+  }
+  std::vector<int64_t> perm(static_cast<size_t>(N));
+  out->lm_ptr = static_cast<int64_t*>(std::malloc(sizeof(int64_t) * (static_cast<size_t>(L) + 1)));
+  const int rc = povar_canonical_order(static_cast<int32_t>(C), static_cast<int32_t>(L), N, cam.data(),
+                                       lm.data(), perm.data(), out->lm_ptr);
+  if (rc != POVAR_OK) {
+    set_err(err, err_len, std::string("Invalid file '") + path + "' (duplicate observation)");
+    povar_bal_free(out);
+    return rc;
+  }
+  out->obs_cam = static_cast<int32_t*>(std::malloc(sizeof(int32_t) * static_cast<size_t>(N)));
+  out->obs_uv = static_cast<double*>(std::malloc(sizeof(double) * 2 * static_cast<size_t>(N)));
+  for (long long i = 0; i < N; ++i) {
+    const int64_t s = perm[i];
+    out->obs_cam[i] = cam[s];
+    out->obs_uv[2 * i] = xy[2 * s];
+    out->obs_uv[2 * i + 1] = xy[2 * s + 1];
+  }
+  out->num_cams = static_cast<int32_t>(C);
+  out->num_lms = static_cast<int32_t>(L);
+  out->num_obs = N;
+  return POVAR_OK;
+}

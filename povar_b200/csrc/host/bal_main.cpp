@@ -1,0 +1,308 @@
+// `bal`: command-line front end with the reference's flag names
+// (/root/reference/src/app/bal.cpp:44-103; flags generated from bal/solver_options.hpp:88-307,
+// bal/bal_dataset_options.hpp, bal/ba_log_options.hpp by cli/cli_options.cpp:61) on top of
+// libpovar_b200.so.  Writes ba_log.json with the per-iteration keys the reference writes
+// (bal/ba_log.hpp:147-245, bal/ba_log.cpp:63-150).
+//
+// --num-gpus N forks one process per GPU (landmarks sharded by observation count, cameras
+// replicated); rank 0 hands the NCCL id to the others through pipes.
+#include <sys/wait.h>
+#include <unistd.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../../include/povar_b200.h"
+
+namespace {
+
+struct AppOptions {
+  std::string input;
+  std::string log_path = "ba_log.json";
+  int num_gpus = 1;
+  bool create_dataset = false;
+  povar_options solver;
+};
+
+[[noreturn]] void die(const std::string& msg) {
+  std::fprintf(stderr, "bal: %s\n", msg.c_str());
+  std::exit(1);
+}
+
+int parse_enum(const std::string& flag, const std::string& v, const std::map<std::string, int>& table) {
+  auto it = table.find(v);
+  if (it == table.end()) die("Could not convert value " + v + " for " + flag + " to enum");
+  return it->second;
+}
+
+void usage() {
+  std::printf(
+      "Solve BAL problem with solver determined by config (B200 build).\n\n"
+      "  --input <STR>\n  --create-dataset (not supported: use the reference or povar_b200.synthetic)\n"
+      "  --num-gpus <INT>\n  --num-threads <INT> (ignored)\n"
+      "  --solver-type-step-1 {POWER_VARPROJ,POWER_SCHUR_COMPLEMENT,POWER_BUNDLE_ADJUSTMENT,PCG,CHOLESKY}\n"
+      "  --solver-type-step-2 {RIPOBA,RIPCG}\n  --power-sc-iterations <INT>\n"
+      "  --residual-robust-norm {NONE,HUBER,CAUCHY}\n  --residual-huber-parameter <FLOAT>\n  --alpha <FLOAT>\n"
+      "  --max-num-iterations-step-1 <INT>\n  --max-num-iterations-step-2 <INT>\n  --eta <FLOAT>\n"
+      "  --r-tolerance <FLOAT>\n  --function-tolerance <FLOAT>\n  --initial-trust-region-radius <FLOAT>\n"
+      "  --min-trust-region-radius <FLOAT>\n  --max-trust-region-radius <FLOAT>\n  --initial-vee <FLOAT>\n"
+      "  --vee-factor <FLOAT>\n  --min-relative-decrease <FLOAT>\n  --optimized-cost {ERROR,ERROR_VALID,ERROR_VALID_AVG}\n"
+      "  --jacobi-scaling-epsilon <FLOAT>\n  --min-linear-solver-iterations <INT>\n"
+      "  --max-linear-solver-iterations <INT>\n  --preconditioner-type {JACOBI,SCHUR_JACOBI}\n"
+      "  --verbosity-level <INT>\n  --log-log-path <STR>\n");
+}
+
+AppOptions parse(int argc, char** argv) {
+  AppOptions o;
+  povar_options_default(&o.solver);
+  const std::map<std::string, int> step1 = {{"PCG", POVAR_PCG},
+                                            {"POWER_SCHUR_COMPLEMENT", POVAR_POWER_SCHUR_COMPLEMENT},
+                                            // README name; the reference's own enum rejects it
+                                            {"POWER_BUNDLE_ADJUSTMENT", POVAR_POWER_SCHUR_COMPLEMENT},
+                                            {"POWER_VARPROJ", POVAR_POWER_VARPROJ},
+                                            {"CHOLESKY", POVAR_CHOLESKY}};
+  const std::map<std::string, int> step2 = {{"RIPOBA", POVAR_RIPOBA}, {"RIPCG", POVAR_RIPCG}};
+  const std::map<std::string, int> norm = {{"NONE", POVAR_NORM_NONE}, {"HUBER", POVAR_NORM_HUBER}, {"CAUCHY", POVAR_NORM_CAUCHY}};
+  const std::map<std::string, int> oc = {{"ERROR", POVAR_COST_ERROR}, {"ERROR_VALID", POVAR_COST_ERROR_VALID},
+                                         {"ERROR_VALID_AVG", POVAR_COST_ERROR_VALID_AVG}};
+  for (int i = 1; i < argc; ++i) {
+    const std::string f = argv[i];
+    auto val = [&]() -> std::string {
+      if (i + 1 >= argc) die("missing value for " + f);
+      return argv[++i];
+    };
+    if (f == "--help" || f == "-h") {
+      usage();
+      std::exit(0);
+    } else if (f == "--input") o.input = val();
+    else if (f == "--create-dataset") o.create_dataset = true;
+    else if (f == "--no-create-dataset") o.create_dataset = false;
+    else if (f == "--num-gpus") o.num_gpus = std::atoi(val().c_str());
+    else if (f == "--num-threads") val();
+    else if (f == "--solver-type-step-1") o.solver.solver_type_step_1 = parse_enum(f, val(), step1);
+    else if (f == "--solver-type-step-2") o.solver.solver_type_step_2 = parse_enum(f, val(), step2);
+    else if (f == "--power-sc-iterations") o.solver.power_sc_iterations = std::atoi(val().c_str());
+    else if (f == "--residual-robust-norm") o.solver.robust_norm = parse_enum(f, val(), norm);
+    else if (f == "--residual-huber-parameter") o.solver.huber_parameter = std::atof(val().c_str());
+    else if (f == "--alpha") o.solver.alpha = std::atof(val().c_str());
+    else if (f == "--max-num-iterations-step-1") o.solver.max_num_iterations_step_1 = std::atoi(val().c_str());
+    else if (f == "--max-num-iterations-step-2") o.solver.max_num_iterations_step_2 = std::atoi(val().c_str());
+    else if (f == "--eta") o.solver.eta = std::atof(val().c_str());
+    else if (f == "--r-tolerance") o.solver.r_tolerance = std::atof(val().c_str());
+    else if (f == "--function-tolerance") o.solver.function_tolerance = std::atof(val().c_str());
+    else if (f == "--initial-trust-region-radius") o.solver.initial_trust_region_radius = std::atof(val().c_str());
+    else if (f == "--min-trust-region-radius") o.solver.min_trust_region_radius = std::atof(val().c_str());
+    else if (f == "--max-trust-region-radius") o.solver.max_trust_region_radius = std::atof(val().c_str());
+    else if (f == "--initial-vee") o.solver.initial_vee = std::atof(val().c_str());
+    else if (f == "--vee-factor") o.solver.vee_factor = std::atof(val().c_str());
+    else if (f == "--min-relative-decrease") o.solver.min_relative_decrease = std::atof(val().c_str());
+    else if (f == "--optimized-cost") o.solver.optimized_cost = parse_enum(f, val(), oc);
+    else if (f == "--jacobi-scaling-epsilon") o.solver.jacobi_scaling_epsilon = std::atof(val().c_str());
+    else if (f == "--min-linear-solver-iterations") o.solver.min_linear_solver_iterations = std::atoi(val().c_str());
+    else if (f == "--max-linear-solver-iterations") o.solver.max_linear_solver_iterations = std::atoi(val().c_str());
+    else if (f == "--preconditioner-type") {
+      const std::string v = val();
+      if (v != "SCHUR_JACOBI" && v != "JACOBI") die("predonditioner " + v + " not implemented");
+    } else if (f == "--verbosity-level") o.solver.verbosity_level = std::atoi(val().c_str());
+    else if (f == "--log-log-path") o.log_path = val();
+    else if (f == "--quiet" || f == "--no-quiet" || f == "--normalize" || f == "--no-normalize" ||
+             f == "--debug" || f == "--no-debug") {
+      // accepted for command-line compatibility; no effect on this path
+    } else {
+      die("unknown argument " + f);
+    }
+  }
+  if (o.input.empty()) die("--input is required");
+  if (o.num_gpus < 1) die("--num-gpus must be >= 1");
+  return o;
+}
+
+const char* step1_name(int t) {
+  switch (t) {   // finish_solve, bal_bundle_adjustment.cpp:98-113
+    case POVAR_PCG: return "bal_pcg";
+    case POVAR_POWER_SCHUR_COMPLEMENT: return "bal_power_sc";
+    case POVAR_POWER_VARPROJ: return "power_variable_projection";
+    default: return "variable_projection";
+  }
+}
+
+template <typename F>
+void json_array(FILE* f, const char* key, const std::vector<povar_iteration>& its, F get, const char* fmt,
+                bool last = false) {
+  std::fprintf(f, "    \"%s\": [", key);
+  for (size_t i = 0; i < its.size(); ++i) {
+    std::fprintf(f, fmt, get(its[i]));
+    if (i + 1 < its.size()) std::fprintf(f, ", ");
+  }
+  std::fprintf(f, "]%s\n", last ? "" : ",");
+}
+
+void json_number(FILE* f, double v) {
+  if (std::isfinite(v)) std::fprintf(f, "%.17g", v);
+  else std::fprintf(f, "null");
+}
+
+void write_log(const AppOptions& o, const povar_bal_data& data, const std::vector<povar_iteration>& its,
+               const povar_solve_summary& s, double load_time) {
+  FILE* f = std::fopen(o.log_path.c_str(), "w");
+  if (!f) {
+    std::fprintf(stderr, "bal: Could not save BA log to %s.\n", o.log_path.c_str());
+    return;
+  }
+  std::fprintf(f, "{\n");
+  std::fprintf(f, "    \"_type\": \"rootba_povar\",\n");
+  std::fprintf(f, "    \"_static\": {\n");
+  std::fprintf(f, "        \"problem_info\": {\"type\": \"bal\", \"input_path\": \"%s\", \"num_cameras\": %d, "
+                  "\"num_landmarks\": %d, \"num_observations\": %lld},\n",
+               o.input.c_str(), data.num_cams, data.num_lms, static_cast<long long>(data.num_obs));
+  std::fprintf(f, "        \"timing\": {\"load\": %.9g, \"preprocess\": 0.0, \"optimize\": %.9g, \"postprocess\": 0.0, \"total\": %.9g},\n",
+               load_time, s.total_time, load_time + s.total_time);
+  std::fprintf(f, "        \"solver\": {\"solver_type\": \"%s\", \"termination_type\": %d, \"termination_type_step_1\": %d, "
+                  "\"message\": \"%s\", \"num_successful_steps\": %d, \"num_unsuccessful_steps\": %d, "
+                  "\"total_time_in_seconds\": %.9g, \"step_1_time_in_seconds\": %.9g, \"step_2_time_in_seconds\": %.9g, "
+                  "\"power_series_terms\": %lld, \"power_series_time_in_seconds\": %.9g, \"num_gpus\": %d, ",
+               step1_name(o.solver.solver_type_step_1), s.termination_type_step_2, s.termination_type_step_1,
+               s.message, s.num_successful_steps, s.num_unsuccessful_steps, s.total_time, s.step1_time,
+               s.step2_time, static_cast<long long>(s.power_terms), s.power_series_time, o.num_gpus);
+  std::fprintf(f, "\"initial_cost\": ");
+  json_number(f, s.initial_cost);
+  std::fprintf(f, ", \"final_cost\": ");
+  json_number(f, s.final_cost);
+  std::fprintf(f, "}\n    },\n");
+  json_array(f, "iteration", its, [](const povar_iteration& e) { return e.iteration; }, "%d");
+  json_array(f, "step", its, [](const povar_iteration& e) { return e.step; }, "%d");
+  json_array(f, "step_is_valid", its, [](const povar_iteration& e) { return e.step_is_valid ? "true" : "false"; }, "%s");
+  json_array(f, "step_is_successful", its, [](const povar_iteration& e) { return e.step_is_successful ? "true" : "false"; }, "%s");
+  json_array(f, "cost", its, [](const povar_iteration& e) { return e.cost; }, "%.17g");
+  json_array(f, "cost_valid", its, [](const povar_iteration& e) { return e.cost_valid; }, "%.17g");
+  json_array(f, "num_obs_valid", its, [](const povar_iteration& e) { return static_cast<long long>(e.num_obs_valid); }, "%lld");
+  json_array(f, "relative_decrease", its, [](const povar_iteration& e) { return std::isfinite(e.relative_decrease) ? e.relative_decrease : 0.0; }, "%.17g");
+  json_array(f, "trust_region_radius", its, [](const povar_iteration& e) { return e.trust_region_radius; }, "%.17g");
+  json_array(f, "linear_solver_iterations", its, [](const povar_iteration& e) { return e.linear_solver_iterations; }, "%d");
+  json_array(f, "iteration_time", its, [](const povar_iteration& e) { return e.iteration_time; }, "%.9g");
+  json_array(f, "cumulative_time", its, [](const povar_iteration& e) { return e.cumulative_time; }, "%.9g");
+  json_array(f, "residual_evaluation_time", its, [](const povar_iteration& e) { return e.residual_evaluation_time; }, "%.9g");
+  json_array(f, "jacobian_evaluation_time", its, [](const povar_iteration& e) { return e.jacobian_evaluation_time; }, "%.9g");
+  json_array(f, "prepare_time", its, [](const povar_iteration& e) { return e.prepare_time; }, "%.9g");
+  json_array(f, "solve_reduced_system_time", its, [](const povar_iteration& e) { return e.solve_reduced_system_time; }, "%.9g");
+  json_array(f, "back_substitution_time", its, [](const povar_iteration& e) { return e.back_substitution_time; }, "%.9g", true);
+  std::fprintf(f, "}\n");
+  std::fclose(f);
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  AppOptions o = parse(argc, argv);
+  if (o.create_dataset) {
+    die("--create-dataset is outside the accelerated path: generate the data_custom file with the "
+        "reference or with `python -m povar_b200.synthetic` (SURVEY 8f)");
+  }
+
+  // fork the other ranks BEFORE any CUDA / NCCL call
+  int rank = 0;
+  std::vector<int> write_fds;
+  int read_fd = -1;
+  std::vector<pid_t> children;
+  for (int r = 1; r < o.num_gpus; ++r) {
+    int fds[2];
+    if (pipe(fds) != 0) die("pipe failed");
+    const pid_t pid = fork();
+    if (pid < 0) die("fork failed");
+    if (pid == 0) {
+      rank = r;
+      read_fd = fds[0];
+      close(fds[1]);
+      for (int w : write_fds) close(w);
+      write_fds.clear();
+      children.clear();
+      break;
+    }
+    close(fds[0]);
+    write_fds.push_back(fds[1]);
+    children.push_back(pid);
+  }
+
+  const auto t_load = std::chrono::steady_clock::now();
+  povar_bal_data data;
+  char err[512] = {0};
+  int rc = povar_bal_read(o.input.c_str(), &data, err, sizeof(err));
+  if (rc != POVAR_OK) die(err);
+  const double load_time = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_load).count();
+  if (rank == 0 && o.solver.verbosity_level >= 1) {
+    std::printf("Loaded BAL problem (%d cams, %d lms, %lld obs) from '%s'\n", data.num_cams, data.num_lms,
+                static_cast<long long>(data.num_obs), o.input.c_str());
+  }
+
+  povar_comm_desc comm;
+  std::memset(&comm, 0, sizeof(comm));
+  comm.rank = rank;
+  comm.world_size = o.num_gpus;
+  comm.device = rank;
+  if (o.num_gpus > 1) {
+    if (rank == 0) {
+      rc = povar_comm_unique_id(comm.nccl_id);
+      if (rc != POVAR_OK) die(std::string("NCCL: ") + povar_last_error(nullptr));
+      for (int w : write_fds) {
+        if (write(w, comm.nccl_id, 128) != 128) die("pipe write failed");
+        close(w);
+      }
+    } else {
+      if (read(read_fd, comm.nccl_id, 128) != 128) die("pipe read failed");
+      close(read_fd);
+    }
+  }
+
+  std::vector<int32_t> bounds(o.num_gpus + 1);
+  povar_partition_landmarks(data.num_lms, data.lm_ptr, o.num_gpus, bounds.data());
+  const int32_t lb = bounds[rank], le = bounds[rank + 1];
+  std::vector<int64_t> lm_ptr(le - lb + 1);
+  for (int32_t l = lb; l <= le; ++l) lm_ptr[l - lb] = data.lm_ptr[l] - data.lm_ptr[lb];
+  std::vector<double> cam_P(static_cast<size_t>(data.num_cams) * 12);
+  for (int c = 0; c < data.num_cams; ++c) std::memcpy(&cam_P[12 * c], &data.cam_params[15 * c], 12 * sizeof(double));
+
+  povar_problem_desc desc;
+  desc.num_cams = data.num_cams;
+  desc.num_lms = le - lb;
+  desc.num_obs = data.lm_ptr[le] - data.lm_ptr[lb];
+  desc.lm_ptr = lm_ptr.data();
+  desc.obs_cam = data.obs_cam + data.lm_ptr[lb];
+  desc.obs_uv = data.obs_uv + 2 * data.lm_ptr[lb];
+  desc.cam_P = cam_P.data();
+
+  povar_handle* h = nullptr;
+  rc = povar_create(&desc, &o.solver, o.num_gpus > 1 ? &comm : nullptr, &h);
+  if (rc != POVAR_OK) die(std::string("povar_create: ") + povar_last_error(nullptr));
+
+  const int cap = o.solver.max_num_iterations_step_1 + o.solver.max_num_iterations_step_2 + 4;
+  std::vector<povar_iteration> its(cap);
+  povar_solve_summary summary;
+  rc = povar_bundle_adjust(h, &o.solver, its.data(), cap, &summary);
+  if (rc != POVAR_OK) {
+    std::fprintf(stderr, "bal: solve failed (%d): %s / %s\n", rc, summary.message, povar_last_error(h));
+  } else if (rank == 0) {
+    its.resize(summary.num_iterations);
+    if (o.solver.verbosity_level >= 1) {
+      std::printf("Final Cost: error: %.4e; %s\n", summary.final_cost, summary.message);
+      std::printf("solve %.4f s (step 1 %.4f s, step 2 %.4f s), %d LM iterations, %lld power terms in %.4f s\n",
+                  summary.total_time, summary.step1_time, summary.step2_time, summary.num_iterations,
+                  static_cast<long long>(summary.power_terms), summary.power_series_time);
+    }
+    write_log(o, data, its, summary, load_time);
+  }
+  povar_destroy(h);
+  povar_bal_free(&data);
+  int status = rc == POVAR_OK ? 0 : 2;
+  for (pid_t pid : children) {
+    int st = 0;
+    waitpid(pid, &st, 0);
+    if (!WIFEXITED(st) || WEXITSTATUS(st) != 0) status = 2;
+  }
+  return status;
+}

@@ -1,0 +1,691 @@
+// Camera-major kernels: everything that reduces over the observations of one camera, plus the
+// per-camera dense work (12x12 / 11x11 blocks) and the power-series bookkeeping.
+//
+// The reference scatters per-landmark results into per-camera vectors and blocks under one
+// std::mutex per camera (sc/landmark_block.hpp:531-537, sc/linearization_power_varproj.hpp:393-397),
+// which makes it non-reproducible with more than one thread.  Here the observation
+// list is also kept camera-major (CSC, built once); a work ITEM is a fixed run of CSC entries of a
+// single camera, one warp reduces an item with a fixed tree, and items are summed per camera in
+// index order => bit-reproducible, no atomics.
+//
+// Reference loops replaced (paths relative to /root/reference/src/rootba_povar/):
+//   k_kron          sc/landmark_block.hpp:272-282, 658-668 (Jp diag), :498/:530/:563 (Jp^T Jp)
+//   k_cam_scale     solver/linearizor_power_varproj.cpp:66-70, 101-105
+//   k_cam_binv      sc/linearization_power_varproj.hpp:91-121, 141-154
+//   k_passB         sc/linearization_power_varproj.hpp:364-453 second half (Jp^T Jl ...), and the
+//                   b part of sc/landmark_block.hpp:474-572
+//   k_finish_b / k_term / k_series_*   sc/linearization_power_varproj.hpp:191-360
+#include <cuda_runtime.h>
+
+#include "device_math.cuh"
+#include "povar_internal.h"
+
+namespace povar {
+
+namespace {
+
+constexpr int kBlock = 256;
+
+inline void count(const LaunchCfg& lc, int n = 1) {
+  if (lc.launch_counter) *lc.launch_counter += n;
+}
+
+inline int item_grid(const DeviceState& d) {
+  const int warps_per_block = kBlock / 32;
+  long long blocks = (static_cast<long long>(d.ix.num_items) + warps_per_block - 1) / warps_per_block;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+__device__ __forceinline__ void load_rec(const double* __restrict__ rec, int lm, double (&x)[4],
+                                         double (&h)[4]) {
+  const double* p = rec + kLmRec * static_cast<size_t>(lm);
+  load4(p, x);
+  load4(p + 4, h);
+}
+
+// ------------------------------------------------------------------------------------------
+// sum_i E_i (x) (X_i X_i^T) per camera: 6 x 10 unique entries.  E_i is the 3x3 symmetric matrix
+// with Jp_raw^T W Jp_raw = E (x) X X^T (both observation models have Jp_raw = K (x) X^T).
+// ------------------------------------------------------------------------------------------
+template <bool JOINT>
+__global__ void __launch_bounds__(kBlock)
+k_kron(DeviceIndex ix, const double* __restrict__ P, const double* __restrict__ X, double c1,
+       double c2, Robust rb, double* __restrict__ item_kron) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= ix.num_items) return;
+  const int c = __ldg(ix.item_cam + warp);
+  const int eb = __ldg(ix.item_ptr + warp), ee = __ldg(ix.item_ptr + warp + 1);
+  Cam3x4 cam;
+  load_cam(P, c, cam);
+  double acc[kKron];
+#pragma unroll
+  for (int k = 0; k < kKron; ++k) acc[k] = 0.0;
+  for (int e = eb + lane; e < ee; e += 32) {
+    const int lm = __ldg(ix.csc_lm + e);
+    const double2 uv = ix.csc_uv[e];
+    double x[4];
+    load4(X + 4 * static_cast<size_t>(lm), x);
+    double E[6];
+    if (JOINT) {
+      JointObs ob;
+      ob.eval(cam, uv.x, uv.y, x, rb);
+      const double w = ob.sw * ob.sw;
+      E[0] = w * ob.iz * ob.iz;
+      E[1] = 0.0;
+      E[2] = w * ob.iz * ob.d02;
+      E[3] = E[0];
+      E[4] = w * ob.iz * ob.d12;
+      E[5] = w * (ob.d02 * ob.d02 + ob.d12 * ob.d12);
+    } else {
+      PoseObs ob;
+      ob.eval(cam, uv.x, uv.y, x, c1, c2, rb);
+      const double w = ob.sw * ob.sw;
+      const double a = c1 * c1, bq = c2 * c2;
+      E[0] = w * (a + bq);
+      E[1] = 0.0;
+      E[2] = -w * a * uv.x;
+      E[3] = E[0];
+      E[4] = -w * a * uv.y;
+      E[5] = w * a * (uv.x * uv.x + uv.y * uv.y);
+    }
+    double Y[10];
+    {
+      int n = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int j = i; j < 4; ++j) Y[n++] = x[i] * x[j];
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+#pragma unroll
+      for (int k = 0; k < 10; ++k) acc[a * 10 + k] += E[a] * Y[k];
+    }
+  }
+  warp_allreduce<kKron>(acc);
+  if (lane == 0) {
+    double* out = item_kron + kKron * static_cast<size_t>(warp);
+#pragma unroll
+    for (int k = 0; k < kKron; ++k) out[k] = acc[k];
+  }
+}
+
+// out[c*width + k] = sum over the items of camera c, in item order
+__global__ void __launch_bounds__(kBlock)
+k_reduce_items(int C, int width, const int* __restrict__ cam_item_ptr,
+               const double* __restrict__ item_vals, double* __restrict__ out,
+               const SeriesCtl* __restrict__ ctl) {
+  if (ctl != nullptr && ctl->done) return;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(C) * width) return;
+  const int c = static_cast<int>(idx / width), k = static_cast<int>(idx % width);
+  double sum = 0.0;
+  const int ie = cam_item_ptr[c + 1];
+  for (int it = cam_item_ptr[c]; it < ie; ++it) sum += item_vals[static_cast<size_t>(it) * width + k];
+  out[idx] = sum;
+}
+
+__device__ __forceinline__ int e_index(int a, int b) {   // a <= b, 3x3 packed
+  return a * 3 - (a * (a - 1)) / 2 + (b - a);
+}
+
+// M[(a,j),(b,k)] of the 12x12 matrix sum_i E_i (x) X X^T
+__device__ __forceinline__ double kron_entry(const double* __restrict__ kr, int row, int col) {
+  int a = row >> 2, j = row & 3, b = col >> 2, k = col & 3;
+  if (a > b) {
+    const int t = a;
+    a = b;
+    b = t;
+  }
+  if (j > k) {
+    const int t = j;
+    j = k;
+    k = t;
+  }
+  return kr[e_index(a, b) * 10 + sym4_index(j, k)];
+}
+
+// pose_scale = 1 / (eps + sqrt(diag(Jp^T Jp)))
+__global__ void __launch_bounds__(kBlock)
+k_cam_scale(int C, const double* __restrict__ kron, double eps, double* __restrict__ pose_scale) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= C * 12) return;
+  const int c = idx / 12, r = idx % 12;
+  const double d2 = kron_entry(kron + kKron * static_cast<size_t>(c), r, r);
+  pose_scale[idx] = 1.0 / (eps + sqrt(d2));
+}
+
+// ------------------------------------------------------------------------------------------
+// per camera: B = (s s^T) o Jp^T Jp + lambda I  (step 2: tangent-space projection first),
+// B^-1 by Cholesky solves of the identity.  One thread per camera, matrix in local memory.
+// ------------------------------------------------------------------------------------------
+template <int D>
+__device__ __forceinline__ bool chol_inverse(double (&A)[D][D], double (&Inv)[D][D]) {
+  // lower Cholesky in place (reads the lower triangle)
+  bool ok = true;
+  for (int j = 0; j < D; ++j) {
+    double d = A[j][j];
+    for (int k = 0; k < j; ++k) d -= A[j][k] * A[j][k];
+    if (!(d > 0.0)) ok = false;
+    const double l = sqrt(d);
+    A[j][j] = l;
+    const double il = 1.0 / l;
+    for (int i = j + 1; i < D; ++i) {
+      double v = A[i][j];
+      for (int k = 0; k < j; ++k) v -= A[i][k] * A[j][k];
+      A[i][j] = v * il;
+    }
+  }
+  // solve L L^T x = e_c for every column
+  for (int c = 0; c < D; ++c) {
+    double yv[D];
+    for (int i = 0; i < D; ++i) {
+      double v = (i == c) ? 1.0 : 0.0;
+      for (int k = 0; k < i; ++k) v -= A[i][k] * yv[k];
+      yv[i] = v / A[i][i];
+    }
+    for (int i = D - 1; i >= 0; --i) {
+      double v = yv[i];
+      for (int k = i + 1; k < D; ++k) v -= A[k][i] * Inv[k][c];
+      Inv[i][c] = v / A[i][i];
+    }
+  }
+  return ok;
+}
+
+template <bool JOINT>
+__global__ void __launch_bounds__(128)
+k_cam_binv(int C, const double* __restrict__ P, const double* __restrict__ kron,
+           const double* __restrict__ pose_scale, double lambda, double* __restrict__ Bmat,
+           double* __restrict__ Binv) {
+  constexpr int D = JOINT ? 11 : 12;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double* kr = kron + kKron * static_cast<size_t>(c);
+  const double* s = pose_scale + 12 * static_cast<size_t>(c);
+  double A12[12][12];
+  for (int i = 0; i < 12; ++i) {
+    for (int j = 0; j < 12; ++j) A12[i][j] = s[i] * s[j] * kron_entry(kr, i, j);
+  }
+  double A[D][D], Inv[D][D];
+  if (JOINT) {
+    // Pi^T A Pi = (H S A S H)[1:,1:]  with S the 0<->p exchange and H = I - tau w w^T
+    double pv[12];
+    for (int i = 0; i < 12; ++i) pv[i] = P[12 * static_cast<size_t>(c) + i];
+    Reflector<12> pi;
+    pi.make(pv);
+    const int p = pi.p;
+    if (p != 0) {
+      for (int j = 0; j < 12; ++j) {
+        const double t = A12[0][j];
+        A12[0][j] = A12[p][j];
+        A12[p][j] = t;
+      }
+      for (int i = 0; i < 12; ++i) {
+        const double t = A12[i][0];
+        A12[i][0] = A12[i][p];
+        A12[i][p] = t;
+      }
+    }
+    double u[12], alpha = 0.0;
+    for (int i = 0; i < 12; ++i) {
+      double v = 0.0;
+      for (int j = 0; j < 12; ++j) v += A12[i][j] * pi.w[j];
+      u[i] = v;
+    }
+    for (int i = 0; i < 12; ++i) alpha += pi.w[i] * u[i];
+    const double tau = pi.tau;
+    for (int i = 1; i < 12; ++i) {
+      for (int j = 1; j < 12; ++j) {
+        A[i - 1][j - 1] = A12[i][j] - tau * (pi.w[i] * u[j] + u[i] * pi.w[j]) +
+                          tau * tau * alpha * pi.w[i] * pi.w[j];
+      }
+    }
+  } else {
+    for (int i = 0; i < 12; ++i) {
+      for (int j = 0; j < 12; ++j) A[i][j] = A12[i][j];
+    }
+  }
+  for (int i = 0; i < D; ++i) A[i][i] += lambda;
+  double* bm = Bmat + 144 * static_cast<size_t>(c);
+  for (int i = 0; i < D; ++i) {
+    for (int j = 0; j < D; ++j) bm[i * D + j] = A[i][j];
+  }
+  chol_inverse<D>(A, Inv);
+  double* bi = Binv + 144 * static_cast<size_t>(c);
+  for (int i = 0; i < D; ++i) {
+    for (int j = 0; j < D; ++j) bi[i * D + j] = Inv[i][j];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// camera half of a product:  raw_c = sum_i (Jp_raw^T W t_i), t_i = Jl_i H_l  (E0)  or
+// t_i = r_i - Jl_i H_l (b).  Output per item; k_reduce_items adds the items of a camera.
+// ------------------------------------------------------------------------------------------
+template <bool JOINT, int MODE>
+__global__ void __launch_bounds__(kBlock)
+k_passB(DeviceIndex ix, const double* __restrict__ P, const double* __restrict__ lm_rec, double c1,
+        double c2, Robust rb, double* __restrict__ item_part, const SeriesCtl* __restrict__ ctl) {
+  if (ctl != nullptr && ctl->done) return;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= ix.num_items) return;
+  const int c = __ldg(ix.item_cam + warp);
+  const int eb = __ldg(ix.item_ptr + warp), ee = __ldg(ix.item_ptr + warp + 1);
+  Cam3x4 cam;
+  load_cam(P, c, cam);
+  double acc[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) acc[k] = 0.0;
+  for (int e = eb + lane; e < ee; e += 32) {
+    const int lm = __ldg(ix.csc_lm + e);
+    const double2 uv = ix.csc_uv[e];
+    double x[4], H[4], m[3];
+    load_rec(lm_rec, lm, x, H);
+    if (JOINT) {
+      JointObs ob;
+      ob.eval(cam, uv.x, uv.y, x, rb);
+      double j0[4], j1[4], t[2];
+      ob.jl_rows(cam, j0, j1);
+      const double l0 = dot4(j0, H), l1 = dot4(j1, H);
+      const double w = ob.sw * ob.sw;
+      if (MODE == PASSB_E0) {
+        t[0] = w * l0;
+        t[1] = w * l1;
+      } else {
+        t[0] = w * (ob.r[0] - l0);
+        t[1] = w * (ob.r[1] - l1);
+      }
+      ob.jpT_coef(t, m);
+    } else {
+      PoseObs ob;
+      ob.eval(cam, uv.x, uv.y, x, c1, c2, rb);
+      const double w = ob.sw * ob.sw;
+      double t[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const double l = ob.T[q][0] * H[0] + ob.T[q][1] * H[1] + ob.T[q][2] * H[2];
+        t[q] = (MODE == PASSB_E0) ? w * l : w * (ob.r[q] - l);
+      }
+      pose_jpT_coef(t, uv.x, uv.y, c1, c2, m);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[4 * k + j] += m[k] * x[j];
+    }
+  }
+  warp_allreduce<12>(acc);
+  if (lane == 0) {
+    double* out = item_part + 12 * static_cast<size_t>(warp);
+#pragma unroll
+    for (int k = 0; k < 12; ++k) out[k] = acc[k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// per-camera vector plumbing.  D = 12 (step 1) or 11 (step 2, tangent space of vec(P)).
+// ------------------------------------------------------------------------------------------
+// e (D) from the raw 12-vector of the camera pass:  s o raw   or   Pi^T (s o raw)
+template <bool JOINT>
+__device__ __forceinline__ void raw_to_reduced(const double* __restrict__ raw,
+                                               const double* __restrict__ s,
+                                               const double* __restrict__ Pc, double* e) {
+  double v[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) v[i] = s[i] * raw[i];
+  if (JOINT) {
+    double pv[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) pv[i] = Pc[i];
+    Reflector<12> pi;
+    pi.make(pv);
+    pi.apply_t(v, e);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) e[i] = v[i];
+  }
+}
+
+// y (12) gathered by the passes:  s o x   or   s o (Pi x)
+template <bool JOINT>
+__device__ __forceinline__ void reduced_to_y(const double* x, const double* __restrict__ s,
+                                             const double* __restrict__ Pc, double* __restrict__ y) {
+  if (JOINT) {
+    double pv[12], full[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) pv[i] = Pc[i];
+    Reflector<12> pi;
+    pi.make(pv);
+    pi.apply(x, full);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) y[i] = s[i] * full[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) y[i] = s[i] * x[i];
+  }
+}
+
+// b = reduced(raw);  accum = tmp = B^-1 (-b);  y = y(tmp)     (solve_*: "accum = right_mul_b_inv(-b_p)")
+template <bool JOINT>
+__global__ void __launch_bounds__(128)
+k_finish_b(int C, const double* __restrict__ raw, const double* __restrict__ pose_scale,
+           const double* __restrict__ P, const double* __restrict__ Binv, double* __restrict__ b,
+           double* __restrict__ tmp, double* __restrict__ acc, double* __restrict__ y,
+           double* __restrict__ norm_part) {
+  constexpr int D = JOINT ? 11 : 12;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double* s = pose_scale + 12 * static_cast<size_t>(c);
+  const double* Pc = P + 12 * static_cast<size_t>(c);
+  double e[12];
+  raw_to_reduced<JOINT>(raw + 12 * static_cast<size_t>(c), s, Pc, e);
+  const double* bi = Binv + 144 * static_cast<size_t>(c);
+  double x0[12];
+  double n2 = 0.0;
+  for (int i = 0; i < D; ++i) {
+    b[static_cast<size_t>(c) * D + i] = e[i];
+    double v = 0.0;
+    for (int j = 0; j < D; ++j) v += bi[i * D + j] * (-e[j]);
+    x0[i] = v;
+    n2 += v * v;
+    tmp[static_cast<size_t>(c) * D + i] = v;
+    acc[static_cast<size_t>(c) * D + i] = v;
+  }
+  reduced_to_y<JOINT>(x0, s, Pc, y + 12 * static_cast<size_t>(c));
+  norm_part[2 * c] = n2;
+  norm_part[2 * c + 1] = n2;
+}
+
+// one power-series term, camera side:  tmp = B^-1 reduced(raw);  accum += tmp;  y = y(tmp)
+template <bool JOINT>
+__global__ void __launch_bounds__(128)
+k_term(int C, const double* __restrict__ raw, const double* __restrict__ pose_scale,
+       const double* __restrict__ P, const double* __restrict__ Binv, double* __restrict__ tmp,
+       double* __restrict__ acc, double* __restrict__ y, double* __restrict__ norm_part,
+       const SeriesCtl* __restrict__ ctl) {
+  if (ctl->done) return;
+  constexpr int D = JOINT ? 11 : 12;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double* s = pose_scale + 12 * static_cast<size_t>(c);
+  const double* Pc = P + 12 * static_cast<size_t>(c);
+  double e[12];
+  raw_to_reduced<JOINT>(raw + 12 * static_cast<size_t>(c), s, Pc, e);
+  const double* bi = Binv + 144 * static_cast<size_t>(c);
+  double t[12];
+  double nt = 0.0, na = 0.0;
+  for (int i = 0; i < D; ++i) {
+    double v = 0.0;
+    for (int j = 0; j < D; ++j) v += bi[i * D + j] * e[j];
+    t[i] = v;
+    nt += v * v;
+    const double a = acc[static_cast<size_t>(c) * D + i] + v;
+    acc[static_cast<size_t>(c) * D + i] = a;
+    na += a * a;
+    tmp[static_cast<size_t>(c) * D + i] = v;
+  }
+  reduced_to_y<JOINT>(t, s, Pc, y + 12 * static_cast<size_t>(c));
+  norm_part[2 * c] = nt;
+  norm_part[2 * c + 1] = na;
+}
+
+// ordered sum of the per-camera partial norms; single block
+__device__ __forceinline__ void sum_norm_parts(int C, const double* __restrict__ norm_part,
+                                               double* smem, double& s0, double& s1) {
+  double acc[2] = {0.0, 0.0};
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    acc[0] += norm_part[2 * c];
+    acc[1] += norm_part[2 * c + 1];
+  }
+  block_reduce<2>(acc, smem);
+  s0 = acc[0];
+  s1 = acc[1];
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_series_start(int C, const double* __restrict__ norm_part, double r_tolerance, int max_terms,
+               SeriesCtl* ctl) {
+  __shared__ double smem[2 * (kBlock / 32)];
+  double s0, s1;
+  sum_norm_parts(C, norm_part, smem, s0, s1);
+  if (threadIdx.x == 0) {
+    ctl->done = max_terms > 0 ? 0 : 1;
+    ctl->iterations = max_terms > 0 ? max_terms : 0;   // "Maximum number of iterations reached."
+    ctl->nonfinite = isfinite(s1) ? 0 : 1;
+    ctl->norm0 = r_tolerance > 0 ? sqrt(s0) : 0.0;
+    ctl->last_tmp_norm = sqrt(s0);
+    ctl->last_acc_norm = sqrt(s1);
+  }
+}
+
+// convergence test after term i (linearization_power_varproj.hpp:205-229)
+__global__ void __launch_bounds__(kBlock)
+k_series_decide(int C, const double* __restrict__ norm_part, int term, double eta,
+                double r_tolerance, SeriesCtl* ctl) {
+  if (ctl->done) return;
+  __shared__ double smem[2 * (kBlock / 32)];
+  double s0, s1;
+  sum_norm_parts(C, norm_part, smem, s0, s1);
+  if (threadIdx.x == 0) {
+    const double it_norm = sqrt(s0), acc_norm = sqrt(s1);
+    ctl->last_tmp_norm = it_norm;
+    ctl->last_acc_norm = acc_norm;
+    ctl->nonfinite = isfinite(s1) ? 0 : 1;
+    bool stop = false;
+    if (eta > 0) {
+      const double zeta = term * it_norm / acc_norm;
+      if (zeta < eta) stop = true;
+    }
+    if (!stop && r_tolerance > 0 && it_norm / ctl->norm0 < r_tolerance) stop = true;
+    if (stop) {
+      ctl->done = 1;
+      ctl->iterations = term;
+    }
+  }
+}
+
+// out = reduced(raw)   (E0 x for callers outside the series: tests, PCG)
+template <bool JOINT>
+__global__ void __launch_bounds__(128)
+k_e0_finish(int C, const double* __restrict__ raw, const double* __restrict__ pose_scale,
+            const double* __restrict__ P, double* __restrict__ out) {
+  constexpr int D = JOINT ? 11 : 12;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double e[12];
+  raw_to_reduced<JOINT>(raw + 12 * static_cast<size_t>(c), pose_scale + 12 * static_cast<size_t>(c),
+                        P + 12 * static_cast<size_t>(c), e);
+  for (int i = 0; i < D; ++i) out[static_cast<size_t>(c) * D + i] = e[i];
+}
+
+template <bool JOINT>
+__global__ void __launch_bounds__(128)
+k_make_y(int C, const double* __restrict__ x, const double* __restrict__ pose_scale,
+         const double* __restrict__ P, double* __restrict__ y) {
+  constexpr int D = JOINT ? 11 : 12;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double xv[12];
+  for (int i = 0; i < D; ++i) xv[i] = x[static_cast<size_t>(c) * D + i];
+  reduced_to_y<JOINT>(xv, pose_scale + 12 * static_cast<size_t>(c), P + 12 * static_cast<size_t>(c),
+                      y + 12 * static_cast<size_t>(c));
+}
+
+// P += reshape(v)   (Camera::inc_pose_pOSE / inc_pose_projective_space, bal_problem.hpp:132-163)
+__global__ void __launch_bounds__(kBlock)
+k_cam_add(int n, const double* __restrict__ v, const double* __restrict__ scale, double* __restrict__ P) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  P[i] += scale != nullptr ? v[i] * scale[i] : v[i];
+}
+
+// P <- P / |P|_F   (space_matrix.normalize(), bal_bundle_adjustment.cpp:550-552, 700-702)
+__global__ void __launch_bounds__(128)
+k_normalize_cams(int C, double* __restrict__ P) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double* p = P + 12 * static_cast<size_t>(c);
+  double n2 = 0.0;
+  for (int i = 0; i < 12; ++i) n2 += p[i] * p[i];
+  const double n = sqrt(n2);
+  for (int i = 0; i < 12; ++i) p[i] = p[i] / n;
+}
+
+// out_c = blocks_c * x_c  (D x D blocks with leading dimension D, stored 144 apart)
+__global__ void __launch_bounds__(128)
+k_block_matvec(int C, int D, const double* __restrict__ blocks, const double* __restrict__ x,
+               double* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double* bm = blocks + 144 * static_cast<size_t>(c);
+  for (int i = 0; i < D; ++i) {
+    double v = 0.0;
+    for (int j = 0; j < D; ++j) v += bm[i * D + j] * x[static_cast<size_t>(c) * D + j];
+    out[static_cast<size_t>(c) * D + i] = v;
+  }
+}
+
+}  // namespace
+
+void launch_kron(const DeviceState& d, const ModelParams& mp, bool joint, KronKind kind,
+                 const LaunchCfg& lc) {
+  (void)kind;
+  const Robust rb = {mp.robust_norm, mp.huber};
+  const int blocks = item_grid(d);
+  if (joint) {
+    k_kron<true><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.X, mp.c1, mp.c2, rb, d.item_kron);
+  } else {
+    k_kron<false><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.X, mp.c1, mp.c2, rb, d.item_kron);
+  }
+  count(lc);
+}
+
+void launch_reduce_items(const DeviceState& d, const double* item_vals, int width, double* out,
+                         bool in_series, const LaunchCfg& lc) {
+  const long long n = static_cast<long long>(d.ix.C) * width;
+  const int blocks = static_cast<int>((n + kBlock - 1) / kBlock);
+  k_reduce_items<<<blocks, kBlock, 0, lc.stream>>>(d.ix.C, width, d.ix.cam_item_ptr, item_vals, out,
+                                                   in_series ? d.ctl : nullptr);
+  count(lc);
+}
+
+void launch_cam_scale(const DeviceState& d, const ModelParams& mp, const LaunchCfg& lc) {
+  const int blocks = (d.ix.C * 12 + kBlock - 1) / kBlock;
+  k_cam_scale<<<blocks, kBlock, 0, lc.stream>>>(d.ix.C, d.kron, mp.jacobi_eps, d.pose_scale);
+  count(lc);
+}
+
+void launch_cam_binv(const DeviceState& d, bool joint, double lambda, const LaunchCfg& lc) {
+  const int blocks = (d.ix.C + 127) / 128;
+  if (joint) {
+    k_cam_binv<true><<<blocks, 128, 0, lc.stream>>>(d.ix.C, d.P, d.kron, d.pose_scale, lambda, d.Bmat, d.Binv);
+  } else {
+    k_cam_binv<false><<<blocks, 128, 0, lc.stream>>>(d.ix.C, d.P, d.kron, d.pose_scale, lambda, d.Bmat, d.Binv);
+  }
+  count(lc);
+}
+
+void launch_passB(const DeviceState& d, const ModelParams& mp, bool joint, PassBMode mode,
+                  bool in_series, const LaunchCfg& lc) {
+  const Robust rb = {mp.robust_norm, mp.huber};
+  const int blocks = item_grid(d);
+  const SeriesCtl* ctl = in_series ? d.ctl : nullptr;
+  if (joint) {
+    if (mode == PASSB_E0) {
+      k_passB<true, PASSB_E0><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.lm_rec, mp.c1, mp.c2, rb,
+                                                                d.item_part, ctl);
+    } else {
+      k_passB<true, PASSB_B><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.lm_rec, mp.c1, mp.c2, rb,
+                                                               d.item_part, ctl);
+    }
+  } else {
+    if (mode == PASSB_E0) {
+      k_passB<false, PASSB_E0><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.lm_rec, mp.c1, mp.c2, rb,
+                                                                 d.item_part, ctl);
+    } else {
+      k_passB<false, PASSB_B><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.lm_rec, mp.c1, mp.c2, rb,
+                                                                d.item_part, ctl);
+    }
+  }
+  count(lc);
+}
+
+void launch_finish_b(const DeviceState& d, bool joint, const LaunchCfg& lc) {
+  const int blocks = (d.ix.C + 127) / 128;
+  if (joint) {
+    k_finish_b<true><<<blocks, 128, 0, lc.stream>>>(d.ix.C, d.cam_raw, d.pose_scale, d.P, d.Binv, d.b,
+                                                    d.vec_tmp, d.vec_acc, d.vec_y, d.norm_part);
+  } else {
+    k_finish_b<false><<<blocks, 128, 0, lc.stream>>>(d.ix.C, d.cam_raw, d.pose_scale, d.P, d.Binv, d.b,
+                                                     d.vec_tmp, d.vec_acc, d.vec_y, d.norm_part);
+  }
+  count(lc);
+}
+
+void launch_series_start(const DeviceState& d, double r_tolerance, int max_terms, const LaunchCfg& lc) {
+  k_series_start<<<1, kBlock, 0, lc.stream>>>(d.ix.C, d.norm_part, r_tolerance, max_terms, d.ctl);
+  count(lc);
+}
+
+void launch_series_term(const DeviceState& d, bool joint, int term, double eta, double r_tolerance,
+                        const LaunchCfg& lc) {
+  const int blocks = (d.ix.C + 127) / 128;
+  if (joint) {
+    k_term<true><<<blocks, 128, 0, lc.stream>>>(d.ix.C, d.cam_raw, d.pose_scale, d.P, d.Binv, d.vec_tmp,
+                                                d.vec_acc, d.vec_y, d.norm_part, d.ctl);
+  } else {
+    k_term<false><<<blocks, 128, 0, lc.stream>>>(d.ix.C, d.cam_raw, d.pose_scale, d.P, d.Binv, d.vec_tmp,
+                                                 d.vec_acc, d.vec_y, d.norm_part, d.ctl);
+  }
+  k_series_decide<<<1, kBlock, 0, lc.stream>>>(d.ix.C, d.norm_part, term, eta, r_tolerance, d.ctl);
+  count(lc, 2);
+}
+
+void launch_e0_finish(const DeviceState& d, bool joint, double* out, const LaunchCfg& lc) {
+  const int blocks = (d.ix.C + 127) / 128;
+  if (joint) {
+    k_e0_finish<true><<<blocks, 128, 0, lc.stream>>>(d.ix.C, d.cam_raw, d.pose_scale, d.P, out);
+  } else {
+    k_e0_finish<false><<<blocks, 128, 0, lc.stream>>>(d.ix.C, d.cam_raw, d.pose_scale, d.P, out);
+  }
+  count(lc);
+}
+
+void launch_make_y(const DeviceState& d, bool joint, const double* x, double* y, const LaunchCfg& lc) {
+  const int blocks = (d.ix.C + 127) / 128;
+  if (joint) {
+    k_make_y<true><<<blocks, 128, 0, lc.stream>>>(d.ix.C, x, d.pose_scale, d.P, y);
+  } else {
+    k_make_y<false><<<blocks, 128, 0, lc.stream>>>(d.ix.C, x, d.pose_scale, d.P, y);
+  }
+  count(lc);
+}
+
+void launch_cam_update_pose(const DeviceState& d, const double* inc, const LaunchCfg& lc) {
+  const int n = d.ix.C * 12;
+  k_cam_add<<<(n + kBlock - 1) / kBlock, kBlock, 0, lc.stream>>>(n, inc, d.pose_scale, d.P);
+  count(lc);
+}
+
+void launch_cam_update_joint(const DeviceState& d, const double* y, const LaunchCfg& lc) {
+  const int n = d.ix.C * 12;
+  k_cam_add<<<(n + kBlock - 1) / kBlock, kBlock, 0, lc.stream>>>(n, y, nullptr, d.P);
+  count(lc);
+}
+
+void launch_normalize_cams(const DeviceState& d, const LaunchCfg& lc) {
+  k_normalize_cams<<<(d.ix.C + 127) / 128, 128, 0, lc.stream>>>(d.ix.C, d.P);
+  count(lc);
+}
+
+void launch_block_matvec(const DeviceState& d, int dim, const double* blocks, const double* x,
+                         double* out, const LaunchCfg& lc) {
+  k_block_matvec<<<(d.ix.C + 127) / 128, 128, 0, lc.stream>>>(d.ix.C, dim, blocks, x, out);
+  count(lc);
+}
+
+}  // namespace povar

@@ -1,0 +1,933 @@
+// Landmark-major kernels: everything that reduces over the observations of one landmark.
+//
+// Work decomposition: one warp per TILE of the landmark-sorted observation array.  A tile is
+// either a run of whole landmarks with at most 32 observations together (one observation per
+// lane, segmented warp reductions between them) or one long landmark (> 32 observations, lanes
+// stride over it, full-warp reduction).  The tile table is built once on the host
+// (engine.cu: build_tiles).  All reductions use fixed trees => results are bit-reproducible.
+//
+// Reference loops replaced (paths relative to /root/reference/src/rootba_povar/):
+//   k_init_varproj      bal/bal_bundle_adjustment_helper.cpp:75-99, 220-241
+//   k_cost              helper.cpp:116-196, bal/residual_info.cpp:97-117
+//   k_lin_landmark      sc/landmark_block.hpp:135-225 (Jl part), 284-309 (scale_Jl_cols_*)
+//   k_prep_landmark     sc/landmark_block.hpp:474-572 (Hll^-1, Hll^-1 Jl^T r)
+//   k_e0_landmark       sc/linearization_power_varproj.hpp:364-453, first half (Jl^T Jp x, Hll^-1)
+//   k_backsub_*         sc/landmark_block.hpp:574-707
+#include <cuda_runtime.h>
+
+#include "device_math.cuh"
+#include "povar_internal.h"
+
+namespace povar {
+
+namespace {
+
+constexpr int kBlock = 256;
+
+__device__ __forceinline__ void load_lm4(const double* __restrict__ X, int lm, double (&x)[4]) {
+  load4(X + 4 * static_cast<size_t>(lm), x);
+}
+
+struct TileLane {
+  int tb, te;
+  bool is_long;
+  int lane;
+  __device__ __forceinline__ TileLane(const int* __restrict__ tile_ptr, int tile) {
+    tb = __ldg(tile_ptr + tile);
+    te = __ldg(tile_ptr + tile + 1);
+    is_long = (te - tb) > 32;
+    lane = threadIdx.x & 31;
+  }
+};
+
+// landmark totals of per-lane accumulators; seg bounds from the landmark of this lane
+template <int NV>
+__device__ __forceinline__ void tile_allreduce(double (&acc)[NV], const TileLane& t, bool has_obs,
+                                               int lm, const int* __restrict__ lm_ptr) {
+  if (t.is_long) {
+    warp_allreduce<NV>(acc);
+  } else {
+    int first = t.lane, last = t.lane;
+    if (has_obs) {
+      first = __ldg(lm_ptr + lm) - t.tb;
+      last = __ldg(lm_ptr + lm + 1) - 1 - t.tb;
+    }
+    segment_allreduce<NV>(acc, t.lane, first, last);
+  }
+}
+
+__device__ __forceinline__ bool is_head(const TileLane& t, bool has_obs, int lm,
+                                        const int* __restrict__ lm_ptr, int o) {
+  if (t.is_long) return t.lane == 0;
+  return has_obs && (o == __ldg(lm_ptr + lm));
+}
+
+// ------------------------------------------------------------------------------------------
+// VarPro initialisation: X_l = argmin | G X - z | by Givens row updates of a 3x3 triangular
+// factor (backward stable; the reference uses bdcSvd on the stacked 4n x 3 system).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void givens_row(double (&R)[6], double (&d)[3], double g0, double g1,
+                                           double g2, double z) {
+  // R packed upper: [00 01 02 11 12 22]
+  if (g0 != 0.0) {
+    const double rot = hypot(R[0], g0);
+    const double c = R[0] / rot, s = g0 / rot;
+    R[0] = rot;
+    double t;
+    t = c * R[1] + s * g1;  g1 = -s * R[1] + c * g1;  R[1] = t;
+    t = c * R[2] + s * g2;  g2 = -s * R[2] + c * g2;  R[2] = t;
+    t = c * d[0] + s * z;   z = -s * d[0] + c * z;    d[0] = t;
+  }
+  if (g1 != 0.0) {
+    const double rot = hypot(R[3], g1);
+    const double c = R[3] / rot, s = g1 / rot;
+    R[3] = rot;
+    double t;
+    t = c * R[4] + s * g2;  g2 = -s * R[4] + c * g2;  R[4] = t;
+    t = c * d[1] + s * z;   z = -s * d[1] + c * z;    d[1] = t;
+  }
+  if (g2 != 0.0) {
+    const double rot = hypot(R[5], g2);
+    const double c = R[5] / rot, s = g2 / rot;
+    R[5] = rot;
+    const double t = c * d[2] + s * z;
+    d[2] = t;
+  }
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_init_varproj(int L, const int* __restrict__ lm_ptr, const int* __restrict__ obs_cam,
+               const double2* __restrict__ obs_uv, const double* __restrict__ P, double c1,
+               double c2, double* __restrict__ X) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= L) return;
+  double R[6] = {0, 0, 0, 0, 0, 0};
+  double d[3] = {0, 0, 0};
+  const int e = lm_ptr[l + 1];
+  for (int o = lm_ptr[l]; o < e; ++o) {
+    Cam3x4 cam;
+    load_cam(P, obs_cam[o], cam);
+    const double2 uv = obs_uv[o];
+    // rows of G = T[:, 0:3], z = -(T[:,3]) + [0 0 c2 u c2 v]   (helper.cpp:224-237)
+    givens_row(R, d, c1 * (cam.r0[0] - cam.r2[0] * uv.x), c1 * (cam.r0[1] - cam.r2[1] * uv.x),
+               c1 * (cam.r0[2] - cam.r2[2] * uv.x), c1 * (cam.r2[3] * uv.x - cam.r0[3]));
+    givens_row(R, d, c1 * (cam.r1[0] - cam.r2[0] * uv.y), c1 * (cam.r1[1] - cam.r2[1] * uv.y),
+               c1 * (cam.r1[2] - cam.r2[2] * uv.y), c1 * (cam.r2[3] * uv.y - cam.r1[3]));
+    givens_row(R, d, c2 * cam.r0[0], c2 * cam.r0[1], c2 * cam.r0[2], c2 * (uv.x - cam.r0[3]));
+    givens_row(R, d, c2 * cam.r1[0], c2 * cam.r1[1], c2 * cam.r1[2], c2 * (uv.y - cam.r1[3]));
+  }
+  // rank-deficient systems (fewer than 3 independent rows): zero the free component.  The
+  // reference's SVD solve returns the minimum-norm solution there; BAL landmarks have >= 2 views.
+  double x2 = R[5] != 0.0 ? d[2] / R[5] : 0.0;
+  double x1 = R[3] != 0.0 ? (d[1] - R[4] * x2) / R[3] : 0.0;
+  double x0 = R[0] != 0.0 ? (d[0] - R[1] * x1 - R[2] * x2) / R[0] : 0.0;
+  double* out = X + 4 * static_cast<size_t>(l);
+  out[0] = x0;
+  out[1] = x1;
+  out[2] = x2;
+  out[3] = 1.0;
+}
+
+// ------------------------------------------------------------------------------------------
+// cost
+// ------------------------------------------------------------------------------------------
+template <bool JOINT>
+__global__ void __launch_bounds__(kBlock)
+k_cost(int nnz, const int* __restrict__ obs_cam, const int* __restrict__ obs_lm,
+       const double2* __restrict__ obs_uv, const double* __restrict__ P,
+       const double* __restrict__ X, double c1, double c2, Robust rb,
+       double* __restrict__ part) {
+  __shared__ double smem[6 * (kBlock / 32)];
+  double acc[6] = {0, 0, 0, 0, 0, 0};  // err_all rsum_all err_valid rsum_valid n_valid nonfinite
+  for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < nnz; o += gridDim.x * blockDim.x) {
+    Cam3x4 cam;
+    load_cam(P, __ldg(obs_cam + o), cam);
+    double x[4];
+    load_lm4(X, __ldg(obs_lm + o), x);
+    const double2 uv = obs_uv[o];
+    double res_sq;
+    bool valid = true, finite;
+    if (JOINT) {
+      JointObs ob;
+      ob.eval(cam, uv.x, uv.y, x, rb);
+      res_sq = ob.res_sq();
+      valid = ob.valid;
+      finite = isfinite(ob.r[0]) && isfinite(ob.r[1]);
+    } else {
+      PoseObs ob;
+      ob.eval(cam, uv.x, uv.y, x, c1, c2, rb);
+      res_sq = ob.res_sq();
+      finite = isfinite(ob.r[0]) && isfinite(ob.r[1]) && isfinite(ob.r[2]) && isfinite(ob.r[3]);
+    }
+    double err, w;
+    error_weight(rb, res_sq, err, w);
+    const double rn = sqrt(res_sq);
+    acc[0] += err;
+    acc[1] += rn;
+    if (valid) {
+      acc[2] += err;
+      acc[3] += rn;
+      acc[4] += 1.0;
+    }
+    if (!finite) acc[5] += 1.0;
+  }
+  block_reduce<6>(acc, smem);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) part[blockIdx.x * 8 + k] = acc[k];
+  }
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_cost_final(int nblocks, long long nnz, const double* __restrict__ part, CostAccum* out) {
+  __shared__ double smem[6 * (kBlock / 32)];
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) acc[k] += part[b * 8 + k];
+  }
+  block_reduce<6>(acc, smem);
+  if (threadIdx.x == 0) {
+    out->err_all = acc[0];
+    out->rsum_all = acc[1];
+    out->err_valid = acc[2];
+    out->rsum_valid = acc[3];
+    out->n_all = nnz;
+    out->n_valid = static_cast<long long>(acc[4] + 0.5);
+    out->nonfinite = acc[5] > 0.0 ? 1 : 0;
+  }
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_scalar_final(int nblocks, const double* __restrict__ part, double* out) {
+  __shared__ double smem[kBlock / 32];
+  double acc[1] = {0};
+  for (int b = threadIdx.x; b < nblocks; b += blockDim.x) acc[0] += part[b];
+  block_reduce<1>(acc, smem);
+  if (threadIdx.x == 0) out[0] = acc[0];
+}
+
+// ------------------------------------------------------------------------------------------
+// linearisation, landmark side: sum_i w Jl_raw^T Jl_raw, sum_i w Jl_raw^T r, column scales
+// ------------------------------------------------------------------------------------------
+template <bool JOINT>
+__global__ void __launch_bounds__(kBlock)
+k_lin_landmark(DeviceIndex ix, const double* __restrict__ P, const double* __restrict__ X,
+               double c1, double c2, Robust rb, double eps, int scale_jl,
+               double* __restrict__ lm_hraw, double* __restrict__ lm_graw,
+               double* __restrict__ lm_scale, int* __restrict__ flags) {
+  constexpr int NV = JOINT ? 14 : 9;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int tile = warp; tile < ix.num_tiles; tile += nwarps) {
+    const TileLane t(ix.tile_ptr, tile);
+    double acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+    int lm = __ldg(ix.obs_lm + t.tb), o_first = -1;
+    bool has_obs = false, bad = false;
+    for (int o = t.tb + t.lane; o < t.te; o += 32) {
+      has_obs = true;
+      if (o_first < 0) o_first = o;
+      lm = __ldg(ix.obs_lm + o);
+      Cam3x4 cam;
+      load_cam(P, __ldg(ix.obs_cam + o), cam);
+      double x[4];
+      load_lm4(X, lm, x);
+      const double2 uv = ix.obs_uv[o];
+      if (JOINT) {
+        JointObs ob;
+        ob.eval(cam, uv.x, uv.y, x, rb);
+        double j0[4], j1[4];
+        ob.jl_rows(cam, j0, j1);
+        const double w = ob.sw * ob.sw;
+        int n = 0;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+#pragma unroll
+          for (int b2 = a; b2 < 4; ++b2) acc[n++] += w * (j0[a] * j0[b2] + j1[a] * j1[b2]);
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) acc[10 + a] += w * (j0[a] * ob.r[0] + j1[a] * ob.r[1]);
+        bad = bad || !(isfinite(ob.r[0]) && isfinite(ob.r[1]) && isfinite(ob.iz) &&
+                       isfinite(ob.d02) && isfinite(ob.d12));
+      } else {
+        PoseObs ob;
+        ob.eval(cam, uv.x, uv.y, x, c1, c2, rb);
+        const double w = ob.sw * ob.sw;
+        int n = 0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+#pragma unroll
+          for (int b2 = a; b2 < 3; ++b2) {
+            acc[n++] += w * (ob.T[0][a] * ob.T[0][b2] + ob.T[1][a] * ob.T[1][b2] +
+                             ob.T[2][a] * ob.T[2][b2] + ob.T[3][a] * ob.T[3][b2]);
+          }
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          acc[6 + a] += w * (ob.T[0][a] * ob.r[0] + ob.T[1][a] * ob.r[1] + ob.T[2][a] * ob.r[2] +
+                             ob.T[3][a] * ob.r[3]);
+        }
+        bad = bad || !(isfinite(ob.r[0]) && isfinite(ob.r[1]) && isfinite(ob.r[2]) &&
+                       isfinite(ob.r[3]));
+      }
+      bad = bad || !(isfinite(x[0]) && isfinite(x[1]) && isfinite(x[2]) && isfinite(x[3]));
+    }
+    tile_allreduce<NV>(acc, t, has_obs, lm, ix.lm_ptr);
+    if (is_head(t, has_obs, lm, ix.lm_ptr, o_first)) {
+      double* h = lm_hraw + 10 * static_cast<size_t>(lm);
+      double* g = lm_graw + 4 * static_cast<size_t>(lm);
+      double* s = lm_scale + 4 * static_cast<size_t>(lm);
+      if (JOINT) {
+#pragma unroll
+        for (int k = 0; k < 10; ++k) h[k] = acc[k];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) g[k] = acc[10 + k];
+        s[0] = 1.0 / (eps + sqrt(acc[0]));
+        s[1] = 1.0 / (eps + sqrt(acc[4]));
+        s[2] = 1.0 / (eps + sqrt(acc[7]));
+        s[3] = 1.0 / (eps + sqrt(acc[9]));
+      } else {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) h[k] = acc[k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) g[k] = acc[6 + k];
+        g[3] = 0.0;
+        s[0] = scale_jl ? 1.0 / (eps + sqrt(acc[0])) : 1.0;
+        s[1] = scale_jl ? 1.0 / (eps + sqrt(acc[3])) : 1.0;
+        s[2] = scale_jl ? 1.0 / (eps + sqrt(acc[5])) : 1.0;
+        s[3] = 1.0;
+      }
+      bool fin = true;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) fin = fin && isfinite(acc[k]);
+      bad = bad || !fin;
+    }
+    if (bad) atomicOr(flags, 1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// per solve, per landmark: Hll^-1 (with landmark damping), H_r = scale o (Pi) Hll^-1 Jl^T r,
+// and the [X | H] record the camera-major pass gathers
+// ------------------------------------------------------------------------------------------
+template <bool JOINT>
+__global__ void __launch_bounds__(kBlock)
+k_prep_landmark(int L, const double* __restrict__ X, const double* __restrict__ lm_hraw,
+                const double* __restrict__ lm_graw, const double* __restrict__ lm_scale,
+                double lambda_lm, double* __restrict__ hll_inv, double* __restrict__ lm_rec) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= L) return;
+  double x[4], s[4];
+  load_lm4(X, l, x);
+  load_lm4(lm_scale, l, s);
+  const double* h = lm_hraw + 10 * static_cast<size_t>(l);
+  const double* g = lm_graw + 4 * static_cast<size_t>(l);
+  double hll[6], inv[6], H[4] = {0, 0, 0, 0};
+  if (JOINT) {
+    // A = (s s^T) o hraw (4x4), Hll = Pi^T A Pi + lambda I
+    double A[4][4];
+    {
+      int n = 0;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+#pragma unroll
+        for (int b2 = a; b2 < 4; ++b2) {
+          const double v = s[a] * s[b2] * h[n++];
+          A[a][b2] = v;
+          A[b2][a] = v;
+        }
+      }
+    }
+    Reflector<4> pi;
+    pi.make(x);
+    double col[3][4];   // columns of Pi
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      double e[3] = {0, 0, 0};
+      e[k] = 1.0;
+      pi.apply(e, col[k]);
+    }
+    double M[3][3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      double ac[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        ac[a] = A[a][0] * col[k][0] + A[a][1] * col[k][1] + A[a][2] * col[k][2] + A[a][3] * col[k][3];
+      }
+#pragma unroll
+      for (int j = 0; j < 3; ++j) M[j][k] = dot4(col[j], ac);
+    }
+    hll[0] = M[0][0] + lambda_lm;
+    hll[1] = 0.5 * (M[0][1] + M[1][0]);
+    hll[2] = 0.5 * (M[0][2] + M[2][0]);
+    hll[3] = M[1][1] + lambda_lm;
+    hll[4] = 0.5 * (M[1][2] + M[2][1]);
+    hll[5] = M[2][2] + lambda_lm;
+    inv3_sym(hll, inv);
+    double sg[4], g3[3], h3[3], h4[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) sg[a] = s[a] * g[a];
+    pi.apply_t(sg, g3);
+    sym3_mul(inv, g3, h3);
+    pi.apply(h3, h4);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) H[a] = s[a] * h4[a];
+  } else {
+    hll[0] = s[0] * s[0] * h[0] + lambda_lm;
+    hll[1] = s[0] * s[1] * h[1];
+    hll[2] = s[0] * s[2] * h[2];
+    hll[3] = s[1] * s[1] * h[3] + lambda_lm;
+    hll[4] = s[1] * s[2] * h[4];
+    hll[5] = s[2] * s[2] * h[5] + lambda_lm;
+    inv3_sym(hll, inv);
+    double sg[3], h3[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) sg[a] = s[a] * g[a];
+    sym3_mul(inv, sg, h3);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) H[a] = s[a] * h3[a];
+  }
+  double* hi = hll_inv + 6 * static_cast<size_t>(l);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) hi[k] = inv[k];
+  double* rec = lm_rec + kLmRec * static_cast<size_t>(l);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) rec[k] = x[k];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) rec[4 + k] = H[k];
+}
+
+// landmark-level tail shared by the E0 pass: G (sum of Jl_raw^T a over the landmark) -> H
+template <bool JOINT>
+__device__ __forceinline__ void landmark_solve(const double* acc, const double (&x)[4],
+                                               const double (&s)[4], const double (&inv)[6],
+                                               double (&H)[4]) {
+  if (JOINT) {
+    Reflector<4> pi;
+    pi.make(x);
+    double sg[4], g3[3], h3[3], h4[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) sg[a] = s[a] * acc[a];
+    pi.apply_t(sg, g3);
+    sym3_mul(inv, g3, h3);
+    pi.apply(h3, h4);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) H[a] = s[a] * h4[a];
+  } else {
+    double sg[3], h3[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) sg[a] = s[a] * acc[a];
+    sym3_mul(inv, sg, h3);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) H[a] = s[a] * h3[a];
+    H[3] = 0.0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// E0 product, landmark half:  H_l = scale o (Pi) Hll^-1 (Pi^T) scale o sum_i Jl_raw^T (w Jp_raw y)
+// ------------------------------------------------------------------------------------------
+template <bool JOINT>
+__global__ void __launch_bounds__(kBlock)
+k_e0_landmark(DeviceIndex ix, const double* __restrict__ P, const double* __restrict__ X,
+              const double* __restrict__ y, double c1, double c2, Robust rb,
+              const double* __restrict__ lm_scale, const double* __restrict__ hll_inv,
+              double* __restrict__ lm_rec, const SeriesCtl* __restrict__ ctl) {
+  if (ctl != nullptr && ctl->done) return;
+  constexpr int NV = JOINT ? 4 : 3;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int tile = warp; tile < ix.num_tiles; tile += nwarps) {
+    const TileLane t(ix.tile_ptr, tile);
+    double acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+    int lm = __ldg(ix.obs_lm + t.tb), o_first = -1;
+    bool has_obs = false;
+    double x[4] = {0, 0, 0, 0};
+    for (int o = t.tb + t.lane; o < t.te; o += 32) {
+      has_obs = true;
+      if (o_first < 0) o_first = o;
+      lm = __ldg(ix.obs_lm + o);
+      const int c = __ldg(ix.obs_cam + o);
+      Cam3x4 cam;
+      load_cam(P, c, cam);
+      load_lm4(X, lm, x);
+      const double2 uv = ix.obs_uv[o];
+      double y0[4], y1[4], y2[4];
+      const double* yc = y + 12 * static_cast<size_t>(c);
+      load4(yc, y0);
+      load4(yc + 4, y1);
+      load4(yc + 8, y2);
+      if (JOINT) {
+        JointObs ob;
+        ob.eval(cam, uv.x, uv.y, x, rb);
+        double a[2], j0[4], j1[4];
+        ob.jp_mul(x, y0, y1, y2, a);
+        ob.jl_rows(cam, j0, j1);
+        const double w = ob.sw * ob.sw;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[k] += w * (j0[k] * a[0] + j1[k] * a[1]);
+      } else {
+        PoseObs ob;
+        ob.eval(cam, uv.x, uv.y, x, c1, c2, rb);
+        double a[4];
+        pose_jp_mul(x, uv.x, uv.y, c1, c2, y0, y1, y2, a);
+        const double w = ob.sw * ob.sw;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          acc[k] += w * (ob.T[0][k] * a[0] + ob.T[1][k] * a[1] + ob.T[2][k] * a[2] + ob.T[3][k] * a[3]);
+        }
+      }
+    }
+    tile_allreduce<NV>(acc, t, has_obs, lm, ix.lm_ptr);
+    if (is_head(t, has_obs, lm, ix.lm_ptr, o_first)) {
+      double s[4], inv[6], H[4];
+      load_lm4(X, lm, x);
+      load_lm4(lm_scale, lm, s);
+      const double* hi = hll_inv + 6 * static_cast<size_t>(lm);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) inv[k] = hi[k];
+      landmark_solve<JOINT>(acc, x, s, inv, H);
+      double* rec = lm_rec + kLmRec * static_cast<size_t>(lm) + 4;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) rec[k] = H[k];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// back-substitutions.  l_diff partial sums go to scalar_part[block]; k_scalar_final adds them.
+// ------------------------------------------------------------------------------------------
+// VarPro (landmark_block.hpp:670-707): cameras are ALREADY updated (P), P_old is the backup.
+// Fresh raw Jp/Jl/res at (P, X_old); stored scaled Jl and r are those of the linearisation
+// (P_old, X_old, weights, lm_scale).  `inc` is the scaled-space pose increment.
+__global__ void __launch_bounds__(kBlock)
+k_backsub_varpro(DeviceIndex ix, const double* __restrict__ P, const double* __restrict__ P_old,
+                 double* __restrict__ X, const double* __restrict__ inc, double c1, double c2,
+                 Robust rb, const double* __restrict__ lm_scale, double* __restrict__ scalar_part) {
+  __shared__ double smem[kBlock / 32];
+  const Robust none = {NORM_NONE, 1.0};
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  double ld[1] = {0.0};
+  for (int tile = warp; tile < ix.num_tiles; tile += nwarps) {
+    const TileLane t(ix.tile_ptr, tile);
+    double acc[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc[k] = 0.0;
+    int lm = __ldg(ix.obs_lm + t.tb), o_first = -1;
+    bool has_obs = false;
+    double x[4] = {0, 0, 0, 0};
+    for (int o = t.tb + t.lane; o < t.te; o += 32) {
+      has_obs = true;
+      if (o_first < 0) o_first = o;
+      lm = __ldg(ix.obs_lm + o);
+      Cam3x4 cam;
+      load_cam(P, __ldg(ix.obs_cam + o), cam);
+      load_lm4(X, lm, x);
+      const double2 uv = ix.obs_uv[o];
+      PoseObs ob;
+      ob.eval(cam, uv.x, uv.y, x, c1, c2, none);   // helper.cpp:382-454: no robust weight
+      int n = 0;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int b2 = a; b2 < 3; ++b2) {
+          acc[n++] += ob.T[0][a] * ob.T[0][b2] + ob.T[1][a] * ob.T[1][b2] + ob.T[2][a] * ob.T[2][b2] +
+                      ob.T[3][a] * ob.T[3][b2];
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        acc[6 + a] += ob.T[0][a] * ob.r[0] + ob.T[1][a] * ob.r[1] + ob.T[2][a] * ob.r[2] +
+                      ob.T[3][a] * ob.r[3];
+      }
+    }
+    tile_allreduce<9>(acc, t, has_obs, lm, ix.lm_ptr);
+    double hll[6], inv[6], tmp[3], il[3];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) hll[k] = acc[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) tmp[k] = acc[6 + k];
+    inv3_sym(hll, inv);
+    sym3_mul(inv, tmp, il);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) il[k] = -il[k];
+    double s[4];
+    load_lm4(lm_scale, lm, s);
+    for (int o = t.tb + t.lane; o < t.te; o += 32) {
+      const int c = __ldg(ix.obs_cam + o);
+      load_lm4(X, lm, x);
+      const double2 uv = ix.obs_uv[o];
+      double i0[4], i1[4], i2[4], jp[4];
+      const double* ic = inc + 12 * static_cast<size_t>(c);
+      load4(ic, i0);
+      load4(ic + 4, i1);
+      load4(ic + 8, i2);
+      pose_jp_mul(x, uv.x, uv.y, c1, c2, i0, i1, i2, jp);   // fresh, unscaled, unweighted Jp
+      Cam3x4 cam_old;
+      load_cam(P_old, c, cam_old);
+      PoseObs old;
+      old.eval(cam_old, uv.x, uv.y, x, c1, c2, rb);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const double jl = old.sw * (old.T[q][0] * s[0] * il[0] + old.T[q][1] * s[1] * il[1] +
+                                    old.T[q][2] * s[2] * il[2]);
+        const double ji = jp[q] + jl;
+        ld[0] -= ji * (0.5 * ji + old.sw * old.r[q]);
+      }
+    }
+    __syncwarp();
+    if (is_head(t, has_obs, lm, ix.lm_ptr, o_first)) {
+      double* xo = X + 4 * static_cast<size_t>(lm);
+      xo[0] += il[0];
+      xo[1] += il[1];
+      xo[2] += il[2];
+    }
+  }
+  block_reduce<1>(ld, smem);
+  if (threadIdx.x == 0) scalar_part[blockIdx.x] = ld[0];
+}
+
+// PoBA (landmark_block.hpp:625-656): stored scaled Jp, Jl, r at the linearisation point, which is
+// the current state; y = pose_scale o inc.
+__global__ void __launch_bounds__(kBlock)
+k_backsub_poba(DeviceIndex ix, const double* __restrict__ P, double* __restrict__ X,
+               const double* __restrict__ y, double c1, double c2, Robust rb,
+               const double* __restrict__ lm_scale, const double* __restrict__ hll_inv,
+               double* __restrict__ scalar_part) {
+  __shared__ double smem[kBlock / 32];
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  double ld[1] = {0.0};
+  for (int tile = warp; tile < ix.num_tiles; tile += nwarps) {
+    const TileLane t(ix.tile_ptr, tile);
+    double acc[3] = {0, 0, 0};
+    int lm = __ldg(ix.obs_lm + t.tb), o_first = -1;
+    bool has_obs = false;
+    double x[4] = {0, 0, 0, 0};
+    for (int o = t.tb + t.lane; o < t.te; o += 32) {
+      has_obs = true;
+      if (o_first < 0) o_first = o;
+      lm = __ldg(ix.obs_lm + o);
+      const int c = __ldg(ix.obs_cam + o);
+      Cam3x4 cam;
+      load_cam(P, c, cam);
+      load_lm4(X, lm, x);
+      const double2 uv = ix.obs_uv[o];
+      PoseObs ob;
+      ob.eval(cam, uv.x, uv.y, x, c1, c2, rb);
+      double y0[4], y1[4], y2[4], a[4];
+      const double* yc = y + 12 * static_cast<size_t>(c);
+      load4(yc, y0);
+      load4(yc + 4, y1);
+      load4(yc + 8, y2);
+      pose_jp_mul(x, uv.x, uv.y, c1, c2, y0, y1, y2, a);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        double sum = 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sum += ob.T[q][k] * (ob.sw * ob.r[q] + ob.sw * a[q]);
+        acc[k] += ob.sw * sum;
+      }
+    }
+    tile_allreduce<3>(acc, t, has_obs, lm, ix.lm_ptr);
+    double s[4], inv[6], st[3], il[3];
+    load_lm4(lm_scale, lm, s);
+    {
+      const double* hi = hll_inv + 6 * static_cast<size_t>(lm);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) inv[k] = hi[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) st[k] = s[k] * acc[k];
+    sym3_mul(inv, st, il);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) il[k] = -il[k];
+    for (int o = t.tb + t.lane; o < t.te; o += 32) {
+      const int c = __ldg(ix.obs_cam + o);
+      Cam3x4 cam;
+      load_cam(P, c, cam);
+      load_lm4(X, lm, x);
+      const double2 uv = ix.obs_uv[o];
+      PoseObs ob;
+      ob.eval(cam, uv.x, uv.y, x, c1, c2, rb);
+      double y0[4], y1[4], y2[4], a[4];
+      const double* yc = y + 12 * static_cast<size_t>(c);
+      load4(yc, y0);
+      load4(yc + 4, y1);
+      load4(yc + 8, y2);
+      pose_jp_mul(x, uv.x, uv.y, c1, c2, y0, y1, y2, a);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const double jl = ob.sw * (ob.T[q][0] * s[0] * il[0] + ob.T[q][1] * s[1] * il[1] +
+                                   ob.T[q][2] * s[2] * il[2]);
+        const double ji = ob.sw * a[q] + jl;
+        ld[0] -= ji * (0.5 * ji + ob.sw * ob.r[q]);
+      }
+    }
+    __syncwarp();
+    if (is_head(t, has_obs, lm, ix.lm_ptr, o_first)) {
+      double* xo = X + 4 * static_cast<size_t>(lm);
+      xo[0] += s[0] * il[0];   // "scale only after computing model cost change", :653
+      xo[1] += s[1] * il[1];
+      xo[2] += s[2] * il[2];
+    }
+  }
+  block_reduce<1>(ld, smem);
+  if (threadIdx.x == 0) scalar_part[blockIdx.x] = ld[0];
+}
+
+// joint (landmark_block.hpp:574-623): y = pose_scale o (Pi_c inc11)
+__global__ void __launch_bounds__(kBlock)
+k_backsub_joint(DeviceIndex ix, const double* __restrict__ P, double* __restrict__ X,
+                const double* __restrict__ y, Robust rb, const double* __restrict__ lm_scale,
+                const double* __restrict__ hll_inv, double* __restrict__ scalar_part) {
+  __shared__ double smem[kBlock / 32];
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  double ld[1] = {0.0};
+  for (int tile = warp; tile < ix.num_tiles; tile += nwarps) {
+    const TileLane t(ix.tile_ptr, tile);
+    double acc[4] = {0, 0, 0, 0};
+    int lm = __ldg(ix.obs_lm + t.tb), o_first = -1;
+    bool has_obs = false;
+    double x[4] = {0, 0, 0, 0};
+    for (int o = t.tb + t.lane; o < t.te; o += 32) {
+      has_obs = true;
+      if (o_first < 0) o_first = o;
+      lm = __ldg(ix.obs_lm + o);
+      const int c = __ldg(ix.obs_cam + o);
+      Cam3x4 cam;
+      load_cam(P, c, cam);
+      load_lm4(X, lm, x);
+      const double2 uv = ix.obs_uv[o];
+      JointObs ob;
+      ob.eval(cam, uv.x, uv.y, x, rb);
+      double y0[4], y1[4], y2[4], a[2], j0[4], j1[4];
+      const double* yc = y + 12 * static_cast<size_t>(c);
+      load4(yc, y0);
+      load4(yc + 4, y1);
+      load4(yc + 8, y2);
+      ob.jp_mul(x, y0, y1, y2, a);
+      ob.jl_rows(cam, j0, j1);
+      const double e0 = ob.sw * ob.r[0] + ob.sw * a[0], e1 = ob.sw * ob.r[1] + ob.sw * a[1];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[k] += ob.sw * (j0[k] * e0 + j1[k] * e1);
+    }
+    tile_allreduce<4>(acc, t, has_obs, lm, ix.lm_ptr);
+    if (!t.is_long && !has_obs) {
+      // idle lane of a short tile: keep the reflector well defined
+      x[0] = 1.0;
+    } else if (t.is_long) {
+      load_lm4(X, lm, x);
+    }
+    double s[4], inv[6];
+    load_lm4(lm_scale, lm, s);
+    {
+      const double* hi = hll_inv + 6 * static_cast<size_t>(lm);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) inv[k] = hi[k];
+    }
+    Reflector<4> pi;
+    pi.make(x);
+    double st[4], t3[3], i3[3], i4[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) st[k] = s[k] * acc[k];
+    pi.apply_t(st, t3);
+    sym3_mul(inv, t3, i3);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) i3[k] = -i3[k];
+    pi.apply(i3, i4);
+    for (int o = t.tb + t.lane; o < t.te; o += 32) {
+      const int c = __ldg(ix.obs_cam + o);
+      Cam3x4 cam;
+      load_cam(P, c, cam);
+      load_lm4(X, lm, x);
+      const double2 uv = ix.obs_uv[o];
+      JointObs ob;
+      ob.eval(cam, uv.x, uv.y, x, rb);
+      double y0[4], y1[4], y2[4], a[2], j0[4], j1[4];
+      const double* yc = y + 12 * static_cast<size_t>(c);
+      load4(yc, y0);
+      load4(yc + 4, y1);
+      load4(yc + 8, y2);
+      ob.jp_mul(x, y0, y1, y2, a);
+      ob.jl_rows(cam, j0, j1);
+      double l0 = 0.0, l1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        l0 += j0[k] * s[k] * i4[k];
+        l1 += j1[k] * s[k] * i4[k];
+      }
+      const double ji0 = ob.sw * a[0] + ob.sw * l0, ji1 = ob.sw * a[1] + ob.sw * l1;
+      ld[0] -= ji0 * (0.5 * ji0 + ob.sw * ob.r[0]) + ji1 * (0.5 * ji1 + ob.sw * ob.r[1]);
+    }
+    __syncwarp();
+    if (is_head(t, has_obs, lm, ix.lm_ptr, o_first)) {
+      double* xo = X + 4 * static_cast<size_t>(lm);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) xo[k] += s[k] * i4[k];   // :621-622
+    }
+  }
+  block_reduce<1>(ld, smem);
+  if (threadIdx.x == 0) scalar_part[blockIdx.x] = ld[0];
+}
+
+// create_homogeneous_landmark, landmark part (bal_bundle_adjustment.cpp:546-549): the 4th entry is
+// already 1 in step-1 storage, written explicitly for clarity
+__global__ void k_to_homogeneous(int L, double* __restrict__ X) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l < L) X[4 * static_cast<size_t>(l) + 3] = 1.0;
+}
+
+// X_h <- X_h / X_h[3]  (bal_bundle_adjustment.cpp:703-705)
+__global__ void k_normalize_lms(int L, double* __restrict__ X) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= L) return;
+  double* x = X + 4 * static_cast<size_t>(l);
+  const double w = x[3];
+  x[0] = x[0] / w;
+  x[1] = x[1] / w;
+  x[2] = x[2] / w;
+  x[3] = w / w;
+}
+
+inline int tile_grid(const DeviceState& d) {
+  const int warps_per_block = kBlock / 32;
+  long long blocks = (static_cast<long long>(d.ix.num_tiles) + warps_per_block - 1) / warps_per_block;
+  const long long cap = 148LL * 8 * 4;   // a few waves of 148 SMs x 8 resident blocks
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+inline void count(const LaunchCfg& lc, int n = 1) {
+  if (lc.launch_counter) *lc.launch_counter += n;
+}
+
+}  // namespace
+
+int cost_blocks(const DeviceState& d) {
+  long long blocks = (static_cast<long long>(d.ix.nnz) + kBlock - 1) / kBlock;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+int scalar_blocks(const DeviceState& d) { return tile_grid(d); }
+
+void launch_init_varproj(const DeviceState& d, const ModelParams& mp, const LaunchCfg& lc) {
+  const int blocks = (d.ix.L + kBlock - 1) / kBlock;
+  if (blocks == 0) return;
+  k_init_varproj<<<blocks, kBlock, 0, lc.stream>>>(d.ix.L, d.ix.lm_ptr, d.ix.obs_cam, d.ix.obs_uv, d.P,
+                                                   mp.c1, mp.c2, d.X);
+  count(lc);
+}
+
+void launch_cost(const DeviceState& d, const ModelParams& mp, bool joint, const LaunchCfg& lc) {
+  const int blocks = cost_blocks(d);
+  const Robust rb = {mp.robust_norm, mp.huber};
+  if (joint) {
+    k_cost<true><<<blocks, kBlock, 0, lc.stream>>>(d.ix.nnz, d.ix.obs_cam, d.ix.obs_lm, d.ix.obs_uv, d.P,
+                                                   d.X, mp.c1, mp.c2, rb, d.cost_part);
+  } else {
+    k_cost<false><<<blocks, kBlock, 0, lc.stream>>>(d.ix.nnz, d.ix.obs_cam, d.ix.obs_lm, d.ix.obs_uv, d.P,
+                                                    d.X, mp.c1, mp.c2, rb, d.cost_part);
+  }
+  k_cost_final<<<1, kBlock, 0, lc.stream>>>(blocks, d.ix.nnz, d.cost_part, d.cost_out);
+  count(lc, 2);
+}
+
+void launch_lin_landmark(const DeviceState& d, const ModelParams& mp, bool joint, bool scale_jl,
+                         const LaunchCfg& lc) {
+  const Robust rb = {mp.robust_norm, mp.huber};
+  const int blocks = tile_grid(d);
+  if (joint) {
+    k_lin_landmark<true><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.X, mp.c1, mp.c2, rb, mp.jacobi_eps, 1,
+                                                           d.lm_hraw, d.lm_graw, d.lm_scale, d.flags);
+  } else {
+    k_lin_landmark<false><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.X, mp.c1, mp.c2, rb, mp.jacobi_eps,
+                                                            scale_jl ? 1 : 0, d.lm_hraw, d.lm_graw,
+                                                            d.lm_scale, d.flags);
+  }
+  count(lc);
+}
+
+void launch_prep_landmark(const DeviceState& d, bool joint, double lambda_lm, const LaunchCfg& lc) {
+  const int blocks = (d.ix.L + kBlock - 1) / kBlock;
+  if (blocks == 0) return;
+  if (joint) {
+    k_prep_landmark<true><<<blocks, kBlock, 0, lc.stream>>>(d.ix.L, d.X, d.lm_hraw, d.lm_graw, d.lm_scale,
+                                                            lambda_lm, d.hll_inv, d.lm_rec);
+  } else {
+    k_prep_landmark<false><<<blocks, kBlock, 0, lc.stream>>>(d.ix.L, d.X, d.lm_hraw, d.lm_graw, d.lm_scale,
+                                                             lambda_lm, d.hll_inv, d.lm_rec);
+  }
+  count(lc);
+}
+
+void launch_e0_landmark(const DeviceState& d, const ModelParams& mp, bool joint, const double* y,
+                        bool in_series, const LaunchCfg& lc) {
+  const Robust rb = {mp.robust_norm, mp.huber};
+  const int blocks = tile_grid(d);
+  const SeriesCtl* ctl = in_series ? d.ctl : nullptr;
+  if (joint) {
+    k_e0_landmark<true><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.X, y, mp.c1, mp.c2, rb, d.lm_scale,
+                                                          d.hll_inv, d.lm_rec, ctl);
+  } else {
+    k_e0_landmark<false><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.X, y, mp.c1, mp.c2, rb, d.lm_scale,
+                                                           d.hll_inv, d.lm_rec, ctl);
+  }
+  count(lc);
+}
+
+void launch_backsub_varpro(const DeviceState& d, const ModelParams& mp, const double* inc,
+                           const LaunchCfg& lc) {
+  const Robust rb = {mp.robust_norm, mp.huber};
+  const int blocks = tile_grid(d);
+  k_backsub_varpro<<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.P_bak, d.X, inc, mp.c1, mp.c2, rb,
+                                                     d.lm_scale, d.scalar_part);
+  k_scalar_final<<<1, kBlock, 0, lc.stream>>>(blocks, d.scalar_part, d.scalar_out);
+  count(lc, 2);
+}
+
+void launch_backsub_poba(const DeviceState& d, const ModelParams& mp, const double* y,
+                         const LaunchCfg& lc) {
+  const Robust rb = {mp.robust_norm, mp.huber};
+  const int blocks = tile_grid(d);
+  k_backsub_poba<<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.X, y, mp.c1, mp.c2, rb, d.lm_scale,
+                                                   d.hll_inv, d.scalar_part);
+  k_scalar_final<<<1, kBlock, 0, lc.stream>>>(blocks, d.scalar_part, d.scalar_out);
+  count(lc, 2);
+}
+
+void launch_backsub_joint(const DeviceState& d, const ModelParams& mp, const double* y,
+                          const LaunchCfg& lc) {
+  const Robust rb = {mp.robust_norm, mp.huber};
+  const int blocks = tile_grid(d);
+  k_backsub_joint<<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.X, y, rb, d.lm_scale, d.hll_inv,
+                                                    d.scalar_part);
+  k_scalar_final<<<1, kBlock, 0, lc.stream>>>(blocks, d.scalar_part, d.scalar_out);
+  count(lc, 2);
+}
+
+void launch_to_homogeneous(const DeviceState& d, const LaunchCfg& lc) {
+  const int blocks = (d.ix.L + kBlock - 1) / kBlock;
+  if (blocks == 0) return;
+  k_to_homogeneous<<<blocks, kBlock, 0, lc.stream>>>(d.ix.L, d.X);
+  count(lc);
+}
+
+void launch_normalize_joint(const DeviceState& d, const LaunchCfg& lc) {
+  const int blocks = (d.ix.L + kBlock - 1) / kBlock;
+  if (blocks == 0) return;
+  k_normalize_lms<<<blocks, kBlock, 0, lc.stream>>>(d.ix.L, d.X);
+  count(lc);
+}
+
+}  // namespace povar

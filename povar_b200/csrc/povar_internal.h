@@ -1,0 +1,160 @@
+// Internal declarations shared by the CUDA translation units and the host driver.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/povar_b200.h"
+
+namespace povar {
+
+// per-observation arrays, landmark-major (canonical order) and camera-major (CSC)
+struct DeviceIndex {
+  int C = 0;          // cameras (global)
+  int L = 0;          // landmarks in this shard
+  int nnz = 0;        // observations in this shard
+  // landmark-major
+  int* lm_ptr = nullptr;      // [L+1]
+  int* obs_cam = nullptr;     // [nnz]
+  int* obs_lm = nullptr;      // [nnz]
+  double2* obs_uv = nullptr;  // [nnz]
+  int* tile_ptr = nullptr;    // [num_tiles+1] observation ranges: whole short landmarks
+                              //   (<= 32 obs together) or one long landmark
+  int num_tiles = 0;
+  // camera-major
+  int* cam_ptr = nullptr;     // [C+1]
+  int* csc_lm = nullptr;      // [nnz] landmark of the entry (ascending inside a camera)
+  double2* csc_uv = nullptr;  // [nnz]
+  int* item_cam = nullptr;    // [num_items] camera of the work item
+  int* item_ptr = nullptr;    // [num_items+1] entry ranges, never crossing a camera boundary
+  int* cam_item_ptr = nullptr;  // [C+1] items of a camera
+  int num_items = 0;
+};
+
+constexpr double kEpsSqrtHost = 1e-5;  // Sophus::Constants<double>::epsilonSqrt()
+constexpr int kKron = 60;     // unique entries of sum_i E_i (x) (X X^T): 6 x 10
+constexpr int kLmRec = 8;     // per-landmark record read by the camera-major pass: [X(4) | H(4)]
+
+// series control block, lives in device memory
+struct SeriesCtl {
+  int done;            // early exit taken: later kernels of the series return at once
+  int iterations;      // summary.num_iterations
+  int nonfinite;       // increment has NaN/Inf
+  int pad;
+  double norm0;        // |accum_0| when r_tolerance > 0
+  double last_tmp_norm;
+  double last_acc_norm;
+  unsigned int ticket; // last-block election
+  unsigned int pad2;
+};
+
+struct CostAccum {
+  double err_all, rsum_all, err_valid, rsum_valid;
+  long long n_all, n_valid;
+  int nonfinite;
+  int pad;
+};
+
+// everything a kernel launcher needs
+struct DeviceState {
+  DeviceIndex ix;
+  // state (current and backup)
+  double* P = nullptr;        // [C*12]
+  double* P_bak = nullptr;
+  double* X = nullptr;        // [L*4]  step 1: [x y z 1]; step 2: homogeneous
+  double* X_bak = nullptr;
+  // linearisation
+  double* pose_scale = nullptr;  // [C*12]
+  double* lm_scale = nullptr;    // [L*4]
+  double* lm_hraw = nullptr;     // [L*10] sum_i w Jl_raw^T Jl_raw (packed symmetric; 6 used in step 1)
+  double* lm_graw = nullptr;     // [L*4]  sum_i w Jl_raw^T r
+  double* hll_inv = nullptr;     // [L*6]
+  double* lm_rec = nullptr;      // [L*8]  [X | H] for the camera-major pass
+  double* kron = nullptr;        // [C*60]
+  double* item_kron = nullptr;   // [num_items*60]
+  double* item_part = nullptr;   // [num_items*12]
+  double* cam_raw = nullptr;     // [C*12] per-camera sums of the camera-major pass (allreduced)
+  double* Bmat = nullptr;        // [C*144]
+  double* Binv = nullptr;        // [C*144]
+  double* b = nullptr;           // [C*12]
+  double* vec_tmp = nullptr;     // [C*12]
+  double* vec_acc = nullptr;     // [C*12]  the increment
+  double* vec_y = nullptr;       // [C*12]  s o x (step 1) / s o (Pi x) (step 2): what the passes gather
+  double* vec_x = nullptr;       // [C*12]  scratch (right_mul_e0 input, PCG vectors)
+  double* cg_r = nullptr;        // PCG work vectors [C*12] each
+  double* cg_p = nullptr;
+  double* cg_z = nullptr;
+  double* cg_q = nullptr;
+  double* cg_x = nullptr;
+  double* Mprec = nullptr;       // [C*144] block-Jacobi preconditioner (inverse blocks)
+  double* norm_part = nullptr;   // [C*4]   per-camera partial norms / dots
+  double* cost_part = nullptr;   // [blocks * 8]
+  CostAccum* cost_out = nullptr;
+  double* scalar_part = nullptr; // [blocks] l_diff partials
+  double* scalar_out = nullptr;  // [8]
+  int* flags = nullptr;          // [4] numerical-failure flags
+  SeriesCtl* ctl = nullptr;
+  double* dense_S = nullptr;     // CHOLESKY: [12C x 12C]
+};
+
+struct LaunchCfg {
+  cudaStream_t stream = nullptr;
+  long long* launch_counter = nullptr;
+};
+
+struct ModelParams {
+  double c1, c2;        // sqrt(1-alpha), sqrt(alpha)
+  int robust_norm;
+  double huber;
+  double jacobi_eps;
+};
+
+// ---- landmark-major kernels (kernels_landmark.cu) ----
+void launch_init_varproj(const DeviceState& d, const ModelParams& mp, const LaunchCfg& lc);
+void launch_cost(const DeviceState& d, const ModelParams& mp, bool joint, const LaunchCfg& lc);
+void launch_lin_landmark(const DeviceState& d, const ModelParams& mp, bool joint, bool scale_jl,
+                         const LaunchCfg& lc);
+void launch_prep_landmark(const DeviceState& d, bool joint, double lambda_lm, const LaunchCfg& lc);
+void launch_e0_landmark(const DeviceState& d, const ModelParams& mp, bool joint, const double* y,
+                        bool in_series, const LaunchCfg& lc);
+void launch_backsub_varpro(const DeviceState& d, const ModelParams& mp, const double* inc,
+                           const LaunchCfg& lc);
+void launch_backsub_poba(const DeviceState& d, const ModelParams& mp, const double* y,
+                         const LaunchCfg& lc);
+void launch_backsub_joint(const DeviceState& d, const ModelParams& mp, const double* y,
+                          const LaunchCfg& lc);
+void launch_to_homogeneous(const DeviceState& d, const LaunchCfg& lc);
+void launch_normalize_joint(const DeviceState& d, const LaunchCfg& lc);
+int cost_blocks(const DeviceState& d);
+int scalar_blocks(const DeviceState& d);
+
+// ---- camera-major kernels (kernels_camera.cu) ----
+enum KronKind { KRON_HPP = 0, KRON_SDIAG = 1 };
+void launch_kron(const DeviceState& d, const ModelParams& mp, bool joint, KronKind kind,
+                 const LaunchCfg& lc);
+void launch_reduce_items(const DeviceState& d, const double* item_vals, int width, double* out,
+                         bool in_series, const LaunchCfg& lc);
+void launch_cam_scale(const DeviceState& d, const ModelParams& mp, const LaunchCfg& lc);
+void launch_cam_binv(const DeviceState& d, bool joint, double lambda, const LaunchCfg& lc);
+enum PassBMode { PASSB_E0 = 0, PASSB_B = 1 };
+void launch_passB(const DeviceState& d, const ModelParams& mp, bool joint, PassBMode mode,
+                  bool in_series, const LaunchCfg& lc);
+// series bookkeeping
+void launch_series_start(const DeviceState& d, double r_tolerance, int max_terms, const LaunchCfg& lc);
+void launch_series_term(const DeviceState& d, bool joint, int term, double eta, double r_tolerance,
+                        const LaunchCfg& lc);
+void launch_finish_b(const DeviceState& d, bool joint, const LaunchCfg& lc);
+void launch_e0_finish(const DeviceState& d, bool joint, double* out, const LaunchCfg& lc);
+void launch_make_y(const DeviceState& d, bool joint, const double* x, double* y, const LaunchCfg& lc);
+void launch_cam_update_pose(const DeviceState& d, const double* inc, const LaunchCfg& lc);
+void launch_cam_update_joint(const DeviceState& d, const double* y, const LaunchCfg& lc);
+void launch_normalize_cams(const DeviceState& d, const LaunchCfg& lc);
+// PCG helpers
+void launch_block_matvec(const DeviceState& d, int dim, const double* blocks, const double* x,
+                         double* out, const LaunchCfg& lc);
+
+}  // namespace povar
