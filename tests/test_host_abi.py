@@ -1,0 +1,154 @@
+"""CPU-side checks of the C ABI: the library loads, exports every declared symbol, host-side
+entry points (reader, canonical order, sharding) agree with the oracle, and compute entry points
+refuse to run without a GPU instead of falling back to anything."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import povar_testlib as common
+from oracle import povar_oracle as O
+from povar_b200 import capi, synthetic
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "povar_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(povar_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = capi.load()
+    names = _declared_symbols()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/povar_b200.h but not exported"
+    assert set(names) == set(capi.SIGNATURES), set(names) ^ set(capi.SIGNATURES)
+    assert lib.povar_abi_version() == 1
+
+
+def test_option_defaults_are_the_reference_code_defaults():
+    o = capi.default_options()
+    ref = O.Options()       # bal/solver_options.hpp:88-307
+    for f in ("solver_type_step_1", "solver_type_step_2", "robust_norm", "huber_parameter", "alpha",
+              "max_num_iterations_step_1", "max_num_iterations_step_2", "min_relative_decrease",
+              "initial_trust_region_radius", "min_trust_region_radius", "max_trust_region_radius",
+              "min_linear_solver_iterations", "max_linear_solver_iterations", "eta", "r_tolerance",
+              "jacobi_scaling_epsilon", "function_tolerance", "power_sc_iterations", "initial_vee",
+              "vee_factor"):
+        assert getattr(o, f) == getattr(ref, f), f
+    assert o.alpha == 0.01 and o.power_sc_iterations == 10      # not the README's 0.1 / 20
+
+
+@pytest.mark.parametrize("shape", ["tiny", "small"])
+def test_bal_reader_matches_oracle_loader_bit_exactly(shape, tmp_path):
+    path = common.golden_file(shape)
+    hp = capi.HostProblem.read(path)
+    op = O.load_bal(path)
+    assert (hp.num_cams, hp.num_lms, hp.num_obs) == (op.C, op.L, op.nnz)
+    assert np.array_equal(hp.lm_ptr, op.lm_ptr)
+    assert np.array_equal(hp.obs_cam, op.obs_cam)
+    assert np.array_equal(hp.obs_uv, op.uv)                      # y already flipped
+    assert np.array_equal(hp.cam_P.reshape(-1, 3, 4), op.P)
+    # canonical order does not depend on the order of the observation lines
+    prob = synthetic.generate_named(shape)
+    shuffled = tmp_path / "shuffled.txt"
+    synthetic.write_bal(prob, str(shuffled), shuffle_seed=11)
+    hs = capi.HostProblem.read(str(shuffled))
+    assert np.array_equal(hs.lm_ptr, hp.lm_ptr) and np.array_equal(hs.obs_cam, hp.obs_cam)
+    assert np.array_equal(hs.obs_uv, hp.obs_uv)
+
+
+def test_bal_reader_errors(tmp_path):
+    with pytest.raises(capi.PovarError) as e:
+        capi.HostProblem.read(str(tmp_path / "missing.txt"))
+    assert e.value.code == capi.ERR_IO
+    dup = tmp_path / "dup.txt"                                   # duplicate (cam, lm): bal_problem.cpp:227
+    dup.write_text("2 1 2\n0 0 1.0 2.0\n0 0 1.5 2.5\n" + "\n".join(["0"] * 30) + "\n0 0 0\n")
+    with pytest.raises(capi.PovarError) as e:
+        capi.HostProblem.read(str(dup))
+    assert e.value.code == capi.ERR_INVALID
+    short = tmp_path / "short.txt"
+    short.write_text("2 1 2\n0 0 1.0 2.0\n")
+    with pytest.raises(capi.PovarError):
+        capi.HostProblem.read(str(short))
+    oob = tmp_path / "oob.txt"
+    oob.write_text("2 1 1\n5 0 1.0 2.0\n" + "\n".join(["0"] * 30) + "\n0 0 0\n")
+    with pytest.raises(capi.PovarError):
+        capi.HostProblem.read(str(oob))
+
+
+def test_canonical_order_from_generator_arrays():
+    sp = synthetic.generate_named("small")
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(sp.num_obs)
+    hp = capi.HostProblem.from_unordered(sp.num_cams, sp.num_lms, sp.obs_cam[perm], sp.obs_lm[perm],
+                                         sp.obs_xy[perm], sp.cam_params)
+    op = O.build_problem(sp.num_cams, sp.num_lms, sp.obs_cam, sp.obs_lm, sp.obs_xy, sp.cam_params)
+    assert np.array_equal(hp.lm_ptr, op.lm_ptr)
+    assert np.array_equal(hp.obs_cam, op.obs_cam)
+    assert np.array_equal(hp.obs_uv, op.uv)
+    with pytest.raises(capi.PovarError):
+        capi.HostProblem.from_unordered(3, 3, np.array([0, 1, 0]), np.array([2, 2, 2]),
+                                        np.zeros((3, 2)), np.zeros((3, 15)))
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_partition_is_contiguous_and_balanced(world):
+    hp = capi.HostProblem.read(common.golden_file("small"))
+    shards = [hp.shard(r, world) for r in range(world)]
+    assert shards[0].lm_begin == 0 and shards[-1].lm_end == hp.num_lms
+    for a, b in zip(shards[:-1], shards[1:]):
+        assert a.lm_end == b.lm_begin
+    assert sum(s.num_obs for s in shards) == hp.num_obs
+    assert np.array_equal(np.concatenate([s.obs_cam for s in shards]), hp.obs_cam)
+    ideal = hp.num_obs / world
+    max_deg = int(np.max(np.diff(hp.lm_ptr)))
+    for s in shards:
+        assert abs(s.num_obs - ideal) <= max_deg + 1
+        assert s.lm_ptr[0] == 0 and s.lm_ptr[-1] == s.num_obs
+
+
+def test_partition_edge_cases():
+    lib = capi.load()
+    lm_ptr = np.array([0, 2, 4], dtype=np.int64)
+    bounds = np.empty(5, dtype=np.int32)
+    assert lib.povar_partition_landmarks(2, lm_ptr.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), 4,
+                                         bounds.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))) == 0
+    assert bounds[0] == 0 and bounds[4] == 2 and np.all(np.diff(bounds) >= 0)   # empty shards allowed
+    assert lib.povar_partition_landmarks(2, lm_ptr.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), 0,
+                                         bounds.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))) == capi.ERR_INVALID
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    hp = capi.HostProblem.read(common.golden_file("tiny"))
+    with pytest.raises(capi.PovarError) as e:
+        capi.Solver(hp)
+    assert e.value.code == capi.ERR_NO_DEVICE
+    # the package itself never imports the oracle
+    import povar_b200
+    pkg = os.path.dirname(povar_b200.__file__)
+    for root, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cpp", ".h", ".cuh")):
+                text = open(os.path.join(root, fn), errors="ignore").read()
+                assert "povar_oracle" not in text and "import oracle" not in text, fn
+
+
+def test_bal_binary_refuses_to_run_without_a_gpu():
+    import subprocess
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from povar_b200 import build
+    res = subprocess.run([build.BAL, "--input", common.golden_file("tiny"), "--verbosity-level", "0"],
+                         capture_output=True, text=True)
+    assert res.returncode != 0
+    assert "no CUDA device" in res.stderr
