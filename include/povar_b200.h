@@ -260,6 +260,12 @@ int povar_right_mul_e0(povar_handle* h, int32_t which, const double* x, double* 
  * return the device time per term in seconds: the SpMV roofline measurement of bench.py. */
 int povar_bench_power_terms(povar_handle* h, int32_t which, int32_t terms, double* seconds_per_term);
 
+/* average device time (seconds) of each kernel of one power-series term, each launched `reps`
+ * times back to back between two CUDA events on the handle's stream:
+ * seconds[0] landmark half of E0, [1] camera half of E0, [2] per-camera item reduction,
+ * [3] B^-1 apply + accumulate + norms + convergence test. */
+int povar_bench_power_kernels(povar_handle* h, int32_t which, int32_t reps, double seconds[4]);
+
 /* kernels launched by this handle since creation (bench.py's gpu_launches) */
 int64_t povar_launch_count(const povar_handle* h);
 

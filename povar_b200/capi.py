@@ -133,6 +133,7 @@ SIGNATURES = {
     "povar_debug_read": (C.c_int64, [_H, C.c_char_p, _DP, C.c_int64]),
     "povar_right_mul_e0": (C.c_int, [_H, C.c_int32, _DP, _DP]),
     "povar_bench_power_terms": (C.c_int, [_H, C.c_int32, C.c_int32, _DP]),
+    "povar_bench_power_kernels": (C.c_int, [_H, C.c_int32, C.c_int32, _DP]),
     "povar_launch_count": (C.c_int64, [_H]),
 }
 
@@ -383,6 +384,11 @@ class Solver:
         s = C.c_double(0)
         self._check(self.lib.povar_bench_power_terms(self.h, which, terms, C.byref(s)))
         return s.value
+
+    def bench_power_kernels(self, which, reps: int) -> np.ndarray:
+        out = np.zeros(4)
+        self._check(self.lib.povar_bench_power_kernels(self.h, which, reps, _dp(out)))
+        return out
 
     def launch_count(self) -> int:
         return int(self.lib.povar_launch_count(self.h))

@@ -176,6 +176,11 @@ int povar_bench_power_terms(povar_handle* h, int32_t which, int32_t terms, doubl
   return e.bench_power_terms(which == POVAR_STATE_JOINT, terms, seconds_per_term);
 }
 
+int povar_bench_power_kernels(povar_handle* h, int32_t which, int32_t reps, double seconds[4]) {
+  PV_ENGINE(h);
+  return e.bench_power_kernels(which == POVAR_STATE_JOINT, reps, seconds);
+}
+
 int64_t povar_launch_count(const povar_handle* h) {
   if (!h || !h->engine) return 0;
   return h->engine->launches();

@@ -736,4 +736,30 @@ int Engine::bench_power_terms(bool joint, int terms, double* seconds_per_term) {
   return POVAR_OK;
 }
 
+// average device time of each kernel of a power-series term, launched `reps` times back to back:
+// [0] landmark half, [1] camera half, [2] item reduction, [3] B^-1 / accumulate / norms / test
+int Engine::bench_power_kernels(bool joint, int reps, double* seconds) {
+  PV_CUDA(cudaSetDevice(device_));
+  if (joint != joint_lin_) return fail(POVAR_ERR_INVALID, "bench_power_kernels: no matching linearisation");
+  if (reps <= 0 || !seconds) return fail(POVAR_ERR_INVALID, "bench_power_kernels: bad arguments");
+  launch_finish_b(d_, joint, lc());
+  launch_series_start(d_, -1.0, reps, lc());
+  for (int k = 0; k < 4; ++k) {
+    PV_CUDA(cudaEventRecord(ev_[0], stream_));
+    for (int i = 0; i < reps; ++i) {
+      switch (k) {
+        case 0: launch_e0_landmark(d_, mp_, joint, d_.vec_y, true, lc()); break;
+        case 1: launch_passB(d_, mp_, joint, PASSB_E0, true, lc()); break;
+        case 2: launch_reduce_items(d_, d_.item_part, 12, d_.cam_raw, true, lc()); break;
+        default: launch_series_term(d_, joint, i + 1, -1.0, -1.0, lc()); break;
+      }
+    }
+    PV_CUDA(cudaEventRecord(ev_[1], stream_));
+    PV_CUDA(cudaGetLastError());
+    PV_CUDA(cudaStreamSynchronize(stream_));
+    seconds[k] = elapsed(ev_[0], ev_[1]) / reps;
+  }
+  return POVAR_OK;
+}
+
 }  // namespace povar

@@ -34,6 +34,7 @@ class Engine {
   int64_t debug_read(const char* name, double* out, int64_t capacity);
   int right_mul_e0(bool joint, const double* x, double* out);
   int bench_power_terms(bool joint, int terms, double* seconds_per_term);
+  int bench_power_kernels(bool joint, int reps, double* seconds);
 
   const char* last_error() const { return err_.c_str(); }
   long long launches() const { return launches_; }
