@@ -131,6 +131,8 @@ void build_items(const std::vector<int>& cam_ptr, int item_len, std::vector<int>
   (*cam_item_ptr)[C] = static_cast<int>(item_cam->size());
 }
 
+static void destroy_cusolver(void* handle);   // defined next to the dlopen'ed cuSOLVER entry points
+
 // ---------------------------------------------------------------------------------------------
 int Engine::fail(int code, const std::string& what) {
   err_ = what;
@@ -229,6 +231,7 @@ Engine::~Engine() {
   if (device_ >= 0) cudaSetDevice(device_);
   if (stream_) cudaStreamSynchronize(stream_);
   if (nccl_comm_ && nccl_) nccl_->CommDestroy(nccl_comm_);
+  if (cusolver_) destroy_cusolver(cusolver_);
   for (void* p : allocs_) cudaFree(p);
   for (auto& ev : ev_) {
     if (ev) cudaEventDestroy(ev);
@@ -319,6 +322,7 @@ int Engine::upload(const povar_problem_desc* desc) {
   PV_ALLOC(d_.hll_inv, static_cast<size_t>(L) * 6);
   PV_ALLOC(d_.lm_rec, static_cast<size_t>(L) * kLmRec);
   PV_ALLOC(d_.kron, static_cast<size_t>(C) * kKron);
+  PV_ALLOC(d_.kron2, static_cast<size_t>(C) * kKron);
   PV_ALLOC(d_.item_kron, static_cast<size_t>(ix.num_items) * kKron);
   PV_ALLOC(d_.item_part, static_cast<size_t>(ix.num_items) * 12);
   PV_ALLOC(d_.cam_raw, C12);
@@ -532,15 +536,229 @@ int Engine::solve(bool joint, double lambda, double* inc, int32_t* iterations) {
   return finish_solve(joint, inc, iterations);
 }
 
-int Engine::solve_pcg(bool joint, double lambda) {
-  (void)joint;
-  (void)lambda;
-  return fail(POVAR_ERR_UNSUPPORTED, "PCG / RIPCG: not built yet");
+// b (and B, B^-1) exactly as the power solvers build them; shared by PCG / RIPCG / CHOLESKY
+int Engine::prepare_reduced_system(bool joint, double lambda, double lambda_lm) {
+  launch_prep_landmark(d_, joint, lambda_lm, lc());
+  launch_cam_binv(d_, joint, lambda, lc());
+  launch_passB(d_, mp_, joint, PASSB_B, false, lc());
+  launch_reduce_items(d_, d_.item_part, 12, d_.cam_raw, false, lc());
+  const int rc = allreduce(d_.cam_raw, static_cast<size_t>(C_) * 12);
+  if (rc != POVAR_OK) return rc;
+  launch_finish_b(d_, joint, lc());
+  return POVAR_OK;
 }
 
+int Engine::read_scalars(double* out, int n) {
+  PV_CUDA(cudaMemcpyAsync(out, d_.scalar_out, sizeof(double) * n, cudaMemcpyDeviceToHost, stream_));
+  PV_CUDA(cudaStreamSynchronize(stream_));
+  return POVAR_OK;
+}
+
+// out = S p = B p - E0 p   (the reduced camera system applied implicitly)
+void Engine::schur_product(bool joint, const double* p, double* out) {
+  const int n = C_ * (joint ? 11 : 12);
+  launch_make_y(d_, joint, p, d_.vec_y, lc());
+  e0_product(joint, d_.vec_y, false);
+  launch_e0_finish(d_, joint, d_.vec_x, lc());
+  launch_block_matvec(d_, joint ? 11 : 12, d_.Bmat, p, out, lc());
+  launch_axpby(d_, n, 1.0, out, -1.0, d_.vec_x, out, lc());
+}
+
+// ConjugateGradientsSolver::solve / solve_joint (cg/conjugate_gradient.hpp:114-489) with the block-Jacobi
+// preconditioner (cg/preconditioner.hpp:70-144), x0 = 0, r_tolerance = -1, then x = -x
+// (solver/linearizor_base.cpp:102-147).  Scalars (rho, p'q, Q) are reduced on the device with fixed trees
+// and read back; the control flow is the reference's, including its NaN behaviour.
+int Engine::solve_pcg(bool joint, double lambda) {
+  const int D = joint ? 11 : 12;
+  const int n = C_ * D;
+  const size_t bytes = sizeof(double) * static_cast<size_t>(n);
+  PV_CUDA(cudaEventRecord(ev_[0], stream_));
+  // LinearizorSC step 1 has no landmark damping (landmark_block.hpp:360-374); step 2 has (:414-431)
+  int rc = prepare_reduced_system(joint, lambda, joint ? lambda : 0.0);
+  if (rc != POVAR_OK) return rc;
+  launch_kron(d_, mp_, joint, KRON_SDIAG, lc());
+  launch_reduce_items(d_, d_.item_kron, kKron, d_.kron2, false, lc());
+  rc = allreduce(d_.kron2, static_cast<size_t>(C_) * kKron);
+  if (rc != POVAR_OK) return rc;
+  launch_cam_precond(d_, joint, d_.kron2, lc());
+  PV_CUDA(cudaEventRecord(ev_[1], stream_));
+
+  const double* b = d_.b;
+  double *x = d_.cg_x, *r = d_.cg_r, *p = d_.cg_p, *z = d_.cg_z, *q = d_.cg_q, *tmp = d_.vec_tmp;
+  int iterations = 0;
+  double s[4];
+  PV_CUDA(cudaMemsetAsync(x, 0, bytes, stream_));
+  launch_dot(d_, n, b, b, 0, lc());
+  rc = read_scalars(s, 1);
+  if (rc != POVAR_OK) return rc;
+  const double norm_b = std::sqrt(s[0]);
+  if (norm_b != 0.0) {
+    const double tol_r = opt_.r_tolerance < 0 ? -1.0 * norm_b : -1.0 * norm_b;   // pso.r_tolerance = -1
+    PV_CUDA(cudaMemcpyAsync(r, b, bytes, cudaMemcpyDeviceToDevice, stream_));   // r = b - S*0
+    (void)tol_r;
+    double rho = 1.0, q0 = 0.0;   // q0 = -x.(b + r) = 0
+    const int min_it = opt_.min_linear_solver_iterations, max_it = opt_.max_linear_solver_iterations;
+    for (iterations = 1;; ++iterations) {
+      launch_block_matvec(d_, D, d_.Mprec, r, z, lc());
+      const double last_rho = rho;
+      launch_dot(d_, n, r, z, 0, lc());
+      rc = read_scalars(s, 1);
+      if (rc != POVAR_OK) return rc;
+      rho = s[0];
+      if (rho == 0.0 || std::isinf(rho)) break;               // LINEAR_SOLVER_FAILURE
+      if (iterations == 1) {
+        PV_CUDA(cudaMemcpyAsync(p, z, bytes, cudaMemcpyDeviceToDevice, stream_));
+      } else {
+        const double beta = rho / last_rho;
+        if (beta == 0.0 || std::isinf(beta)) break;
+        launch_axpby(d_, n, 1.0, z, beta, p, p, lc());
+      }
+      schur_product(joint, p, q);
+      launch_dot(d_, n, p, q, 0, lc());
+      rc = read_scalars(s, 1);
+      if (rc != POVAR_OK) return rc;
+      const double pq = s[0];
+      if (pq <= 0 || std::isinf(pq)) break;                   // "Matrix is indefinite"
+      const double alpha = rho / pq;
+      if (std::isinf(alpha)) break;
+      launch_axpby(d_, n, 1.0, x, alpha, p, x, lc());
+      if (iterations % 10 == 0) {                             // residual_reset_period
+        schur_product(joint, x, tmp);
+        launch_axpby(d_, n, 1.0, b, -1.0, tmp, r, lc());
+      } else {
+        launch_axpby(d_, n, 1.0, r, -alpha, q, r, lc());
+      }
+      launch_axpby(d_, n, 1.0, b, 1.0, r, tmp, lc());
+      launch_dot(d_, n, x, tmp, 0, lc());
+      rc = read_scalars(s, 1);
+      if (rc != POVAR_OK) return rc;
+      const double q1 = -1.0 * s[0];
+      const double zeta = iterations * (q1 - q0) / q1;
+      if (zeta < opt_.eta && iterations >= min_it) break;     // LINEAR_SOLVER_SUCCESS
+      q0 = q1;
+      // residual-based termination never fires: tol_r = r_tolerance * |b| < 0
+      if (iterations >= max_it) break;
+    }
+  }
+  launch_axpby(d_, n, -1.0, x, 0.0, nullptr, d_.vec_acc, lc());   // "negate the pose increment"
+  SeriesCtl h{};
+  h.done = 1;
+  h.iterations = iterations;
+  PV_CUDA(cudaMemcpyAsync(d_.ctl, &h, sizeof(h), cudaMemcpyHostToDevice, stream_));
+  PV_CUDA(cudaStreamSynchronize(stream_));   // h lives on this stack frame
+  launch_finite_check(d_, n, d_.vec_acc, lc());
+  PV_CUDA(cudaEventRecord(ev_[2], stream_));
+  PV_CUDA(cudaGetLastError());
+  return POVAR_OK;
+}
+
+// ---- cuSOLVER through dlopen (dense Cholesky of the reduced camera system) ----
+struct CusolverApi {
+  void* lib = nullptr;
+  int (*Create)(void**) = nullptr;
+  int (*Destroy)(void*) = nullptr;
+  int (*SetStream)(void*, cudaStream_t) = nullptr;
+  int (*PotrfBuf)(void*, int, int, double*, int, int*) = nullptr;
+  int (*Potrf)(void*, int, int, double*, int, double*, int, int*) = nullptr;
+  int (*Potrs)(void*, int, int, int, const double*, int, double*, int, int*) = nullptr;
+};
+
+static CusolverApi* load_cusolver(std::string* err) {
+  static CusolverApi api;
+  if (api.lib) return &api;
+  const char* names[] = {getenv("POVAR_CUSOLVER_LIB"), "libcusolver.so.11", "libcusolver.so",
+                         "/usr/local/cuda/lib64/libcusolver.so.11"};
+  for (const char* nme : names) {
+    if (!nme) continue;
+    api.lib = dlopen(nme, RTLD_NOW | RTLD_GLOBAL);
+    if (api.lib) break;
+  }
+  if (!api.lib) {
+    if (err) *err = "cannot dlopen libcusolver.so.11 (set POVAR_CUSOLVER_LIB)";
+    return nullptr;
+  }
+  api.Create = reinterpret_cast<int (*)(void**)>(dlsym(api.lib, "cusolverDnCreate"));
+  api.Destroy = reinterpret_cast<int (*)(void*)>(dlsym(api.lib, "cusolverDnDestroy"));
+  api.SetStream = reinterpret_cast<int (*)(void*, cudaStream_t)>(dlsym(api.lib, "cusolverDnSetStream"));
+  api.PotrfBuf = reinterpret_cast<int (*)(void*, int, int, double*, int, int*)>(dlsym(api.lib, "cusolverDnDpotrf_bufferSize"));
+  api.Potrf = reinterpret_cast<int (*)(void*, int, int, double*, int, double*, int, int*)>(dlsym(api.lib, "cusolverDnDpotrf"));
+  api.Potrs = reinterpret_cast<int (*)(void*, int, int, int, const double*, int, double*, int, int*)>(dlsym(api.lib, "cusolverDnDpotrs"));
+  if (!api.Create || !api.Destroy || !api.SetStream || !api.PotrfBuf || !api.Potrf || !api.Potrs) {
+    if (err) *err = "libcusolver is missing expected symbols";
+    dlclose(api.lib);
+    api.lib = nullptr;
+    return nullptr;
+  }
+  return &api;
+}
+
+static void destroy_cusolver(void* handle) {
+  CusolverApi* cs = load_cusolver(nullptr);
+  if (cs && handle) cs->Destroy(handle);
+}
+
+// CHOLESKY, step 1 (solver/linearizor_sc.cpp:121-128, sc/linearization_sc.hpp:236-245): the reference
+// factorises the sparse reduced camera system with Eigen::SimplicialLLT; here S is assembled densely
+// (12C x 12C, FP64) and factorised by cuSOLVER's potrf -- the solution of S x = -b is unique, so the
+// ordering / sparsity handling does not change the result beyond rounding.
 int Engine::solve_cholesky(double lambda) {
-  (void)lambda;
-  return fail(POVAR_ERR_UNSUPPORTED, "CHOLESKY: not built yet");
+  const long long n = 12LL * C_;
+  if (n * n * 8 > (96LL << 30)) return fail(POVAR_ERR_UNSUPPORTED, "CHOLESKY: dense reduced system would exceed 96 GB");
+  std::string cerr;
+  CusolverApi* cs = load_cusolver(&cerr);
+  if (!cs) return fail(POVAR_ERR_UNSUPPORTED, cerr);
+  PV_CUDA(cudaEventRecord(ev_[0], stream_));
+  int rc = prepare_reduced_system(false, lambda, 0.0);
+  if (rc != POVAR_OK) return rc;
+  if (!d_.dense_S) PV_ALLOC(d_.dense_S, static_cast<size_t>(n) * n);
+  PV_CUDA(cudaMemsetAsync(d_.dense_S, 0, sizeof(double) * static_cast<size_t>(n) * n, stream_));
+  launch_dense_schur(d_, mp_, d_.dense_S, lc());
+  if (world_ > 1) {
+    // the diagonal blocks were added on every rank: undo on all but rank 0 before the sum
+    return fail(POVAR_ERR_UNSUPPORTED, "CHOLESKY is single-GPU (the dense reduced system is not sharded)");
+  }
+  PV_CUDA(cudaEventRecord(ev_[1], stream_));
+  launch_axpby(d_, static_cast<int>(n), -1.0, d_.b, 0.0, nullptr, d_.vec_acc, lc());
+  if (!cusolver_) {
+    if (cs->Create(&cusolver_) != 0) return fail(POVAR_ERR_CUDA, "cusolverDnCreate failed");
+    cs->SetStream(cusolver_, stream_);
+  }
+  int lwork = 0;
+  const int kLower = 0;   // CUBLAS_FILL_MODE_LOWER
+  if (cs->PotrfBuf(cusolver_, kLower, static_cast<int>(n), d_.dense_S, static_cast<int>(n), &lwork) != 0) {
+    return fail(POVAR_ERR_CUDA, "cusolverDnDpotrf_bufferSize failed");
+  }
+  if (lwork > chol_work_size_) {
+    PV_ALLOC(chol_work_, static_cast<size_t>(lwork));
+    chol_work_size_ = lwork;
+  }
+  int* info = d_.flags + 2;
+  if (cs->Potrf(cusolver_, kLower, static_cast<int>(n), d_.dense_S, static_cast<int>(n), chol_work_, lwork, info) != 0) {
+    return fail(POVAR_ERR_CUDA, "cusolverDnDpotrf failed");
+  }
+  if (cs->Potrs(cusolver_, kLower, static_cast<int>(n), 1, d_.dense_S, static_cast<int>(n), d_.vec_acc,
+                static_cast<int>(n), d_.flags + 3) != 0) {
+    return fail(POVAR_ERR_CUDA, "cusolverDnDpotrs failed");
+  }
+  launches_ += 2;
+  int hinfo = 0;
+  PV_CUDA(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+  SeriesCtl h{};
+  h.done = 1;
+  h.iterations = 0;   // the reference reports 0 linear solver iterations for the direct solve
+  PV_CUDA(cudaMemcpyAsync(d_.ctl, &h, sizeof(h), cudaMemcpyHostToDevice, stream_));
+  PV_CUDA(cudaStreamSynchronize(stream_));
+  if (hinfo != 0) {
+    // not positive definite: SimplicialLLT would report NumericalIssue; surface it as an invalid step
+    h.nonfinite = 1;
+    PV_CUDA(cudaMemcpyAsync(d_.ctl, &h, sizeof(h), cudaMemcpyHostToDevice, stream_));
+    PV_CUDA(cudaStreamSynchronize(stream_));
+  } else {
+    launch_finite_check(d_, static_cast<int>(n), d_.vec_acc, lc());
+  }
+  PV_CUDA(cudaEventRecord(ev_[2], stream_));
+  PV_CUDA(cudaGetLastError());
+  return POVAR_OK;
 }
 
 int Engine::apply(bool joint, double alpha, double* l_diff) {

@@ -54,6 +54,9 @@ class Engine {
   int solve_power(bool joint, double lambda);
   int solve_pcg(bool joint, double lambda);
   int solve_cholesky(double lambda);
+  int prepare_reduced_system(bool joint, double lambda, double lambda_lm);
+  int read_scalars(double* out, int n);
+  void schur_product(bool joint, const double* p, double* out);
   void e0_product(bool joint, const double* y, bool in_series);
   int finish_solve(bool joint, double* inc, int32_t* iterations);
   LaunchCfg lc() { return LaunchCfg{stream_, &launches_}; }
@@ -73,6 +76,9 @@ class Engine {
   double lambda_ = 0.0;           // damping of the last solve (landmark damping of apply)
   int dim_ = 12;
   double* P_prev_ = nullptr;      // cameras of the linearisation point during a VarPro apply
+  void* cusolver_ = nullptr;      // cusolverDnHandle_t (CHOLESKY only)
+  double* chol_work_ = nullptr;
+  int chol_work_size_ = 0;
   // distributed
   int rank_ = 0, world_ = 1, device_ = 0;
   void* nccl_comm_ = nullptr;

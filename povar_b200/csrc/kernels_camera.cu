@@ -48,10 +48,14 @@ __device__ __forceinline__ void load_rec(const double* __restrict__ rec, int lm,
 // sum_i E_i (x) (X_i X_i^T) per camera: 6 x 10 unique entries.  E_i is the 3x3 symmetric matrix
 // with Jp_raw^T W Jp_raw = E (x) X X^T (both observation models have Jp_raw = K (x) X^T).
 // ------------------------------------------------------------------------------------------
-template <bool JOINT>
+// KIND 0 (KRON_HPP):   E_i = W K_i^T K_i            -> Jp^T Jp
+// KIND 1 (KRON_SDIAG): E_i = W^2 K_i^T N_i K_i,  N_i = Jl_i Hll^-1 Jl_i^T (scaled, tangent-projected
+//                      in step 2)                  -> diagonal blocks of sum_l Hpl Hll^-1 Hlp
+template <bool JOINT, int KIND>
 __global__ void __launch_bounds__(kBlock)
 k_kron(DeviceIndex ix, const double* __restrict__ P, const double* __restrict__ X, double c1,
-       double c2, Robust rb, double* __restrict__ item_kron) {
+       double c2, Robust rb, const double* __restrict__ lm_scale, const double* __restrict__ hll_inv,
+       double* __restrict__ item_kron) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= ix.num_items) return;
@@ -68,7 +72,79 @@ k_kron(DeviceIndex ix, const double* __restrict__ P, const double* __restrict__ 
     double x[4];
     load4(X + 4 * static_cast<size_t>(lm), x);
     double E[6];
-    if (JOINT) {
+    if (KIND == KRON_SDIAG) {
+      double sl[4], inv[6];
+      load4(lm_scale + 4 * static_cast<size_t>(lm), sl);
+      {
+        const double* hi = hll_inv + 6 * static_cast<size_t>(lm);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) inv[k] = hi[k];
+      }
+      if (JOINT) {
+        JointObs ob;
+        ob.eval(cam, uv.x, uv.y, x, rb);
+        double j0[4], j1[4];
+        ob.jl_rows(cam, j0, j1);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          j0[k] *= sl[k];
+          j1[k] *= sl[k];
+        }
+        Reflector<4> pi;
+        pi.make(x);
+        double t0[3], t1[3], v0[3], v1[3];
+        pi.apply_t(j0, t0);             // rows of Jl_t = (Jl_raw o scale) Pi_l
+        pi.apply_t(j1, t1);
+        sym3_mul(inv, t0, v0);
+        sym3_mul(inv, t1, v1);
+        const double n00 = t0[0] * v0[0] + t0[1] * v0[1] + t0[2] * v0[2];
+        const double n01 = t0[0] * v1[0] + t0[1] * v1[1] + t0[2] * v1[2];
+        const double n11 = t1[0] * v1[0] + t1[1] * v1[1] + t1[2] * v1[2];
+        const double w2 = ob.sw * ob.sw * ob.sw * ob.sw;
+        // E = w^2 d^T N d with d = [[iz 0 d02],[0 iz d12]]
+        const double a0 = n00 * ob.d02 + n01 * ob.d12, a1 = n01 * ob.d02 + n11 * ob.d12;
+        E[0] = w2 * ob.iz * ob.iz * n00;
+        E[1] = w2 * ob.iz * ob.iz * n01;
+        E[2] = w2 * ob.iz * a0;
+        E[3] = w2 * ob.iz * ob.iz * n11;
+        E[4] = w2 * ob.iz * a1;
+        E[5] = w2 * (ob.d02 * a0 + ob.d12 * a1);
+      } else {
+        PoseObs ob;
+        ob.eval(cam, uv.x, uv.y, x, c1, c2, rb);
+        double Z[4][3], V[4][3], N[4][4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) Z[q][k] = ob.T[q][k] * sl[k];
+          sym3_mul(inv, Z[q], V[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) N[q][r] = Z[q][0] * V[r][0] + Z[q][1] * V[r][1] + Z[q][2] * V[r][2];
+        }
+        // K rows: c1 (1 0 -u), c1 (0 1 -v), c2 (1 0 0), c2 (0 1 0);  E = w^2 K^T N K
+        const double K[4][3] = {{c1, 0.0, -c1 * uv.x}, {0.0, c1, -c1 * uv.y}, {c2, 0.0, 0.0}, {0.0, c2, 0.0}};
+        double G[4][3];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            G[q][k] = N[q][0] * K[0][k] + N[q][1] * K[1][k] + N[q][2] * K[2][k] + N[q][3] * K[3][k];
+          }
+        }
+        const double w2 = ob.sw * ob.sw * ob.sw * ob.sw;
+        int n = 0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+#pragma unroll
+          for (int b2 = a; b2 < 3; ++b2) {
+            E[n++] = w2 * (K[0][a] * G[0][b2] + K[1][a] * G[1][b2] + K[2][a] * G[2][b2] + K[3][a] * G[3][b2]);
+          }
+        }
+      }
+    } else if (JOINT) {
       JointObs ob;
       ob.eval(cam, uv.x, uv.y, x, rb);
       const double w = ob.sw * ob.sw;
@@ -164,12 +240,18 @@ k_cam_scale(int C, const double* __restrict__ kron, double eps, double* __restri
 // ------------------------------------------------------------------------------------------
 template <int D>
 __device__ __forceinline__ bool chol_inverse(double (&A)[D][D], double (&Inv)[D][D]) {
-  // lower Cholesky in place (reads the lower triangle)
+  // lower Cholesky in place (reads the lower triangle).  Like Eigen's unblocked LLT
+  // (external/eigen/Eigen/src/Cholesky/LLT.h) the factorisation STOPS at the first pivot <= 0 and
+  // leaves the remaining columns untouched; the reference never checks info(), so the solves below
+  // then run on the half-factored triangle (finite garbage, not NaN).  Kept for parity.
   bool ok = true;
-  for (int j = 0; j < D; ++j) {
+  for (int j = 0; j < D && ok; ++j) {
     double d = A[j][j];
     for (int k = 0; k < j; ++k) d -= A[j][k] * A[j][k];
-    if (!(d > 0.0)) ok = false;
+    if (!(d > 0.0)) {
+      ok = false;
+      break;
+    }
     const double l = sqrt(d);
     A[j][j] = l;
     const double il = 1.0 / l;
@@ -196,7 +278,11 @@ __device__ __forceinline__ bool chol_inverse(double (&A)[D][D], double (&Inv)[D]
   return ok;
 }
 
-template <bool JOINT>
+// MODE 0: R = proj((s s^T) o kron) + lambda I -> Bmat, R^-1 -> Binv           (prepare_Hb_*)
+// MODE 1: R = Bmat - proj((s s^T) o kron)               , R^-1 -> Binv(=Mprec) (block-Jacobi
+//         preconditioner of the reduced camera system, cg/preconditioner.hpp:78-124; kron then holds
+//         the diagonal blocks of sum_l Hpl Hll^-1 Hlp)
+template <bool JOINT, int MODE>
 __global__ void __launch_bounds__(128)
 k_cam_binv(int C, const double* __restrict__ P, const double* __restrict__ kron,
            const double* __restrict__ pose_scale, double lambda, double* __restrict__ Bmat,
@@ -249,10 +335,16 @@ k_cam_binv(int C, const double* __restrict__ P, const double* __restrict__ kron,
       for (int j = 0; j < 12; ++j) A[i][j] = A12[i][j];
     }
   }
-  for (int i = 0; i < D; ++i) A[i][i] += lambda;
   double* bm = Bmat + 144 * static_cast<size_t>(c);
-  for (int i = 0; i < D; ++i) {
-    for (int j = 0; j < D; ++j) bm[i * D + j] = A[i][j];
+  if (MODE == 0) {
+    for (int i = 0; i < D; ++i) A[i][i] += lambda;
+    for (int i = 0; i < D; ++i) {
+      for (int j = 0; j < D; ++j) bm[i * D + j] = A[i][j];
+    }
+  } else {
+    for (int i = 0; i < D; ++i) {
+      for (int j = 0; j < D; ++j) A[i][j] = bm[i * D + j] - A[i][j];
+    }
   }
   chol_inverse<D>(A, Inv);
   double* bi = Binv + 144 * static_cast<size_t>(c);
@@ -553,13 +645,24 @@ k_block_matvec(int C, int D, const double* __restrict__ blocks, const double* __
 
 void launch_kron(const DeviceState& d, const ModelParams& mp, bool joint, KronKind kind,
                  const LaunchCfg& lc) {
-  (void)kind;
   const Robust rb = {mp.robust_norm, mp.huber};
   const int blocks = item_grid(d);
-  if (joint) {
-    k_kron<true><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.X, mp.c1, mp.c2, rb, d.item_kron);
+  if (kind == KRON_HPP) {
+    if (joint) {
+      k_kron<true, KRON_HPP><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.X, mp.c1, mp.c2, rb, d.lm_scale,
+                                                               d.hll_inv, d.item_kron);
+    } else {
+      k_kron<false, KRON_HPP><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.X, mp.c1, mp.c2, rb, d.lm_scale,
+                                                                d.hll_inv, d.item_kron);
+    }
   } else {
-    k_kron<false><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.X, mp.c1, mp.c2, rb, d.item_kron);
+    if (joint) {
+      k_kron<true, KRON_SDIAG><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.X, mp.c1, mp.c2, rb, d.lm_scale,
+                                                                 d.hll_inv, d.item_kron);
+    } else {
+      k_kron<false, KRON_SDIAG><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.X, mp.c1, mp.c2, rb, d.lm_scale,
+                                                                  d.hll_inv, d.item_kron);
+    }
   }
   count(lc);
 }
@@ -582,9 +685,20 @@ void launch_cam_scale(const DeviceState& d, const ModelParams& mp, const LaunchC
 void launch_cam_binv(const DeviceState& d, bool joint, double lambda, const LaunchCfg& lc) {
   const int blocks = (d.ix.C + 127) / 128;
   if (joint) {
-    k_cam_binv<true><<<blocks, 128, 0, lc.stream>>>(d.ix.C, d.P, d.kron, d.pose_scale, lambda, d.Bmat, d.Binv);
+    k_cam_binv<true, 0><<<blocks, 128, 0, lc.stream>>>(d.ix.C, d.P, d.kron, d.pose_scale, lambda, d.Bmat, d.Binv);
   } else {
-    k_cam_binv<false><<<blocks, 128, 0, lc.stream>>>(d.ix.C, d.P, d.kron, d.pose_scale, lambda, d.Bmat, d.Binv);
+    k_cam_binv<false, 0><<<blocks, 128, 0, lc.stream>>>(d.ix.C, d.P, d.kron, d.pose_scale, lambda, d.Bmat, d.Binv);
+  }
+  count(lc);
+}
+
+// block-Jacobi preconditioner: Mprec = (Bmat - proj((s s^T) o kron_sdiag))^-1
+void launch_cam_precond(const DeviceState& d, bool joint, const double* kron_sdiag, const LaunchCfg& lc) {
+  const int blocks = (d.ix.C + 127) / 128;
+  if (joint) {
+    k_cam_binv<true, 1><<<blocks, 128, 0, lc.stream>>>(d.ix.C, d.P, kron_sdiag, d.pose_scale, 0.0, d.Bmat, d.Mprec);
+  } else {
+    k_cam_binv<false, 1><<<blocks, 128, 0, lc.stream>>>(d.ix.C, d.P, kron_sdiag, d.pose_scale, 0.0, d.Bmat, d.Mprec);
   }
   count(lc);
 }

@@ -75,6 +75,7 @@ struct DeviceState {
   double* hll_inv = nullptr;     // [L*6]
   double* lm_rec = nullptr;      // [L*8]  [X | H] for the camera-major pass
   double* kron = nullptr;        // [C*60]
+  double* kron2 = nullptr;       // [C*60] diagonal blocks of sum_l Hpl Hll^-1 Hlp (PCG preconditioner)
   double* item_kron = nullptr;   // [num_items*60]
   double* item_part = nullptr;   // [num_items*12]
   double* cam_raw = nullptr;     // [C*12] per-camera sums of the camera-major pass (allreduced)
@@ -140,6 +141,7 @@ void launch_reduce_items(const DeviceState& d, const double* item_vals, int widt
                          bool in_series, const LaunchCfg& lc);
 void launch_cam_scale(const DeviceState& d, const ModelParams& mp, const LaunchCfg& lc);
 void launch_cam_binv(const DeviceState& d, bool joint, double lambda, const LaunchCfg& lc);
+void launch_cam_precond(const DeviceState& d, bool joint, const double* kron_sdiag, const LaunchCfg& lc);
 enum PassBMode { PASSB_E0 = 0, PASSB_B = 1 };
 void launch_passB(const DeviceState& d, const ModelParams& mp, bool joint, PassBMode mode,
                   bool in_series, const LaunchCfg& lc);
@@ -153,8 +155,16 @@ void launch_make_y(const DeviceState& d, bool joint, const double* x, double* y,
 void launch_cam_update_pose(const DeviceState& d, const double* inc, const LaunchCfg& lc);
 void launch_cam_update_joint(const DeviceState& d, const double* y, const LaunchCfg& lc);
 void launch_normalize_cams(const DeviceState& d, const LaunchCfg& lc);
-// PCG helpers
+// PCG / Cholesky helpers (kernels_schur.cu)
 void launch_block_matvec(const DeviceState& d, int dim, const double* blocks, const double* x,
                          double* out, const LaunchCfg& lc);
+// out = a * x + b * y (y may be nullptr)
+void launch_axpby(const DeviceState& d, int n, double a, const double* x, double b, const double* y,
+                  double* out, const LaunchCfg& lc);
+// scalar_out[slot] = x . y (deterministic two-stage reduction); slot in [0, 8)
+void launch_dot(const DeviceState& d, int n, const double* x, const double* y, int slot, const LaunchCfg& lc);
+// dense reduced camera system of step 1 (CHOLESKY): S = blockdiag(Bmat) - sum_l Hpl Hll^-1 Hlp
+void launch_dense_schur(const DeviceState& d, const ModelParams& mp, double* S, const LaunchCfg& lc);
+void launch_finite_check(const DeviceState& d, int n, const double* x, const LaunchCfg& lc);
 
 }  // namespace povar
