@@ -422,7 +422,8 @@ int Engine::cost(bool joint, double alpha, povar_residual_info* out) {
 int Engine::linearize(bool joint, double alpha) {
   PV_CUDA(cudaSetDevice(device_));
   set_model(joint, joint ? opt_.alpha : alpha);
-  joint_lin_ = joint;
+  joint_lin_ = joint ? 1 : 0;
+  have_solve_ = false;
   dim_ = joint ? 11 : 12;
   const bool power = joint ? true
                            : (opt_.solver_type_step_1 == POVAR_POWER_VARPROJ ||
@@ -511,7 +512,8 @@ int Engine::finish_solve(bool joint, double* inc, int32_t* iterations) {
 
 int Engine::solve(bool joint, double lambda, double* inc, int32_t* iterations) {
   PV_CUDA(cudaSetDevice(device_));
-  if (joint != joint_lin_) return fail(POVAR_ERR_INVALID, "solve called without a matching linearize");
+  if (static_cast<int>(joint) != joint_lin_) return fail(POVAR_ERR_INVALID, "solve called without a matching linearize");
+  have_solve_ = true;
   lambda_ = lambda;
   int rc;
   if (joint) {
@@ -763,7 +765,9 @@ int Engine::solve_cholesky(double lambda) {
 
 int Engine::apply(bool joint, double alpha, double* l_diff) {
   PV_CUDA(cudaSetDevice(device_));
-  if (joint != joint_lin_) return fail(POVAR_ERR_INVALID, "apply called without a matching linearize");
+  if (static_cast<int>(joint) != joint_lin_ || !have_solve_) {
+    return fail(POVAR_ERR_INVALID, "apply called without a matching linearize + solve");
+  }
   set_model(joint, joint ? opt_.alpha : alpha);
   PV_CUDA(cudaEventRecord(ev_[0], stream_));
   const size_t C12 = static_cast<size_t>(C_) * 12;
@@ -922,7 +926,9 @@ int64_t Engine::debug_read(const char* name, double* out, int64_t capacity) {
 // E0 x with the current linearisation and the Hll^-1 of the last solve
 int Engine::right_mul_e0(bool joint, const double* x, double* out) {
   PV_CUDA(cudaSetDevice(device_));
-  if (joint != joint_lin_) return fail(POVAR_ERR_INVALID, "right_mul_e0: no matching linearisation");
+  if (static_cast<int>(joint) != joint_lin_ || !have_solve_) {
+    return fail(POVAR_ERR_INVALID, "right_mul_e0: needs a matching linearize + solve");
+  }
   const size_t n = static_cast<size_t>(C_) * (joint ? 11 : 12);
   PV_CUDA(cudaMemcpyAsync(d_.vec_x, x, sizeof(double) * n, cudaMemcpyHostToDevice, stream_));
   launch_make_y(d_, joint, d_.vec_x, d_.vec_y, lc());
@@ -938,7 +944,9 @@ int Engine::right_mul_e0(bool joint, const double* x, double* out) {
 // and norms) on the current linearisation, no early exit: the SpMV measurement of bench.py.
 int Engine::bench_power_terms(bool joint, int terms, double* seconds_per_term) {
   PV_CUDA(cudaSetDevice(device_));
-  if (joint != joint_lin_) return fail(POVAR_ERR_INVALID, "bench_power_terms: no matching linearisation");
+  if (static_cast<int>(joint) != joint_lin_ || !have_solve_) {
+    return fail(POVAR_ERR_INVALID, "bench_power_terms: needs a matching linearize + solve");
+  }
   if (terms <= 0) return fail(POVAR_ERR_INVALID, "bench_power_terms: terms must be positive");
   launch_finish_b(d_, joint, lc());
   launch_series_start(d_, -1.0, terms, lc());
@@ -958,7 +966,9 @@ int Engine::bench_power_terms(bool joint, int terms, double* seconds_per_term) {
 // [0] landmark half, [1] camera half, [2] item reduction, [3] B^-1 / accumulate / norms / test
 int Engine::bench_power_kernels(bool joint, int reps, double* seconds) {
   PV_CUDA(cudaSetDevice(device_));
-  if (joint != joint_lin_) return fail(POVAR_ERR_INVALID, "bench_power_kernels: no matching linearisation");
+  if (static_cast<int>(joint) != joint_lin_ || !have_solve_) {
+    return fail(POVAR_ERR_INVALID, "bench_power_kernels: needs a matching linearize + solve");
+  }
   if (reps <= 0 || !seconds) return fail(POVAR_ERR_INVALID, "bench_power_kernels: bad arguments");
   launch_finish_b(d_, joint, lc());
   launch_series_start(d_, -1.0, reps, lc());

@@ -72,7 +72,8 @@ class Engine {
   std::string err_;
   PhaseTimes times_;
   // solver state
-  bool joint_lin_ = false;        // which model the current linearisation belongs to
+  int joint_lin_ = -1;            // model of the current linearisation: -1 none, 0 pOSE, 1 joint
+  bool have_solve_ = false;       // a solve ran on the current linearisation (apply needs its increment)
   double lambda_ = 0.0;           // damping of the last solve (landmark damping of apply)
   int dim_ = 12;
   double* P_prev_ = nullptr;      // cameras of the linearisation point during a VarPro apply
