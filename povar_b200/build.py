@@ -27,6 +27,7 @@ LIB_SOURCES = [
     "kernels_landmark.cu",
     "kernels_camera.cu",
     "kernels_schur.cu",
+    "kernels_series.cu",
     "engine.cu",
     "capi.cpp",
     "host/bal_io.cpp",

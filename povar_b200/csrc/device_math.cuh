@@ -294,6 +294,26 @@ struct Reflector {
   }
 };
 
+// ---- per-camera record gathered by the landmark-major half of E0 (kernels_series.cu) -----------
+// Four lanes share one observation; lane `sub` reads 16-byte chunk (p, sub) in its p-th load, so
+// the lanes of a group touch consecutive bytes (whole sectors) instead of one line per lane.
+//   p = 0, 1 : y_sub[0..1], y_sub[2..3]      (sub < 3; y = what the product is applied to)
+//   p = 2, 3 : (M[0][sub], M[1][sub]), (M[2][sub], 0)   M = P[:, 0:3] (step 1) or P (step 2)
+// Dense packing: 12 chunks (192 B) in step 1, 14 chunks (224 B) in step 2.
+template <bool JOINT>
+struct CamRec {
+  static constexpr int kStride = JOINT ? 28 : 24;   // doubles per camera
+  __host__ __device__ static constexpr int chunk(int p, int sub) {
+    return JOINT ? (p < 2 ? 3 * p + sub : 6 + 4 * (p - 2) + sub) : 3 * p + sub;
+  }
+  __host__ __device__ static constexpr int y_index(int k, int j) {
+    return 2 * chunk(j >> 1, k) + (j & 1);
+  }
+  __host__ __device__ static constexpr int m_index(int r, int n) {
+    return r < 2 ? 2 * chunk(2, n) + r : 2 * chunk(3, n);
+  }
+};
+
 // ---- warp helpers ----------------------------------------------------------------------------
 __device__ __forceinline__ double shfl_double(double v, int src) {
   return __shfl_sync(kFullMask, v, src);

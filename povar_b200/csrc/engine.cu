@@ -105,6 +105,46 @@ void build_tiles(const std::vector<int>& lm_ptr, std::vector<int>* tile_ptr) {
   if (tile_ptr->size() == 1 && L >= 0 && lm_ptr[L] == 0) tile_ptr->clear(), tile_ptr->push_back(0);
 }
 
+// Sliced ELL order of the landmarks with 1..32 observations (the landmark half of E0 gives a group of
+// four lanes to each landmark and walks its observations serially, so the eight landmarks of a slice
+// should have the same degree): stable sort by descending degree inside windows of `window`
+// landmarks, eight landmarks per slice, slice length = largest degree in it.
+void build_sell(const std::vector<int>& lm_ptr, int window, SellLayout* out) {
+  const int L = static_cast<int>(lm_ptr.size()) - 1;
+  out->slice_ptr.assign(1, 0);
+  out->sell_lm.clear();
+  out->long_lms.clear();
+  out->obs_slot.assign(static_cast<size_t>(lm_ptr[L]), -1);
+  std::vector<int> order;
+  int rows = 0;
+  for (int w0 = 0; w0 < L; w0 += window) {
+    const int w1 = std::min(L, w0 + window);
+    order.clear();
+    for (int l = w0; l < w1; ++l) {
+      const int deg = lm_ptr[l + 1] - lm_ptr[l];
+      if (deg > 32) out->long_lms.push_back(l);
+      else if (deg > 0) order.push_back(l);
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+      return lm_ptr[a + 1] - lm_ptr[a] > lm_ptr[b + 1] - lm_ptr[b];
+    });
+    for (size_t i = 0; i < order.size(); i += 8) {
+      const int len = lm_ptr[order[i] + 1] - lm_ptr[order[i]];
+      for (int g = 0; g < 8; ++g) {
+        const int l = i + g < order.size() ? order[i + g] : -1;
+        out->sell_lm.push_back(l);
+        if (l < 0) continue;
+        for (int o = lm_ptr[l]; o < lm_ptr[l + 1]; ++o) {
+          out->obs_slot[o] = 8 * (rows + (o - lm_ptr[l])) + g;
+        }
+      }
+      rows += len;
+      out->slice_ptr.push_back(rows);
+    }
+  }
+  out->rows = rows;
+}
+
 int choose_item_len(long long nnz) {
   // enough items to fill 148 SMs x 64 warps a couple of times, at most 256 entries per item
   long long len = nnz / (148LL * 64 * 2);
@@ -197,6 +237,12 @@ int Engine::create(const povar_problem_desc* desc, const povar_options* opt,
   e->rank_ = comm ? comm->rank : 0;
   e->world_ = comm ? comm->world_size : 1;
   e->device_ = comm ? comm->device : 0;
+  {
+    // POVAR_E0_IMPL=v1 selects the one-observation-per-lane term kernels (A/B timing, debugging)
+    const char* impl = getenv("POVAR_E0_IMPL");
+    e->e0_v1_ = impl != nullptr && std::strcmp(impl, "v1") == 0;
+    e->e0_layout_ = (impl != nullptr && std::strcmp(impl, "tiles") == 0) ? 1 : 0;
+  }
   if (e->device_ < 0 || e->device_ >= ndev) {
     if (err) *err = "povar_create: device ordinal out of range";
     delete e;
@@ -276,6 +322,12 @@ int Engine::upload(const povar_problem_desc* desc) {
   build_tiles(lm_ptr, &tile_ptr);
   build_items(cam_ptr, choose_item_len(nnz), &item_ptr, &item_cam, &cam_item_ptr);
 
+  SellLayout sell;
+  build_sell(lm_ptr, kSellWindow, &sell);
+  if (static_cast<long long>(sell.rows) * 8 >= (1LL << 31)) {
+    return fail(POVAR_ERR_UNSUPPORTED, "sliced-ELL layout exceeds 2^31 slots in one shard");
+  }
+
   DeviceIndex& ix = d_.ix;
   ix.C = C;
   ix.L = L;
@@ -287,6 +339,7 @@ int Engine::upload(const povar_problem_desc* desc) {
   PV_ALLOC(ix.obs_lm, nnz);
   PV_ALLOC(ix.obs_uv, nnz);
   PV_ALLOC(ix.tile_ptr, tile_ptr.size());
+  PV_ALLOC(ix.tile_info, ix.num_tiles);
   PV_ALLOC(ix.cam_ptr, C + 1);
   PV_ALLOC(ix.csc_lm, nnz);
   PV_ALLOC(ix.csc_uv, nnz);
@@ -304,6 +357,46 @@ int Engine::upload(const povar_problem_desc* desc) {
     PV_UP(ix.item_cam, item_cam.data(), sizeof(int) * item_cam.size());
   }
   PV_UP(ix.tile_ptr, tile_ptr.data(), sizeof(int) * tile_ptr.size());
+  {
+    std::vector<int4> tile_info(ix.num_tiles);
+    for (int t = 0; t < ix.num_tiles; ++t) {
+      const int tb = tile_ptr[t], te = tile_ptr[t + 1];
+      tile_info[t] = make_int4(tb, te - tb, obs_lm[tb], obs_lm[te - 1] - obs_lm[tb] + 1);
+    }
+    if (ix.num_tiles > 0) PV_UP(ix.tile_info, tile_info.data(), sizeof(int4) * tile_info.size());
+  }
+  {
+    // sliced-ELL copy of the observation stream for the landmark half of E0
+    ix.num_slices = static_cast<int>(sell.slice_ptr.size()) - 1;
+    ix.sell_slots = 8LL * sell.rows;
+    const size_t slots = static_cast<size_t>(ix.sell_slots);
+    std::vector<int> sell_cam(slots, -1);
+    std::vector<double> sell_uv(2 * slots, 0.0);
+    for (int o = 0; o < nnz; ++o) {
+      const int slot = sell.obs_slot[o];
+      if (slot < 0) continue;
+      sell_cam[slot] = desc->obs_cam[o];
+      sell_uv[2 * static_cast<size_t>(slot)] = desc->obs_uv[2 * static_cast<size_t>(o)];
+      sell_uv[2 * static_cast<size_t>(slot) + 1] = desc->obs_uv[2 * static_cast<size_t>(o) + 1];
+    }
+    std::vector<int4> long_info;
+    for (int l : sell.long_lms) long_info.push_back(make_int4(lm_ptr[l], lm_ptr[l + 1] - lm_ptr[l], l, 1));
+    ix.num_long_tiles = static_cast<int>(long_info.size());
+    PV_ALLOC(ix.slice_ptr, sell.slice_ptr.size());
+    PV_ALLOC(ix.sell_lm, sell.sell_lm.size());
+    PV_ALLOC(ix.sell_cam, slots);
+    PV_ALLOC(ix.sell_uv, slots);
+    PV_ALLOC(ix.obs_slot, nnz);
+    PV_ALLOC(ix.long_tile_info, long_info.size());
+    PV_UP(ix.slice_ptr, sell.slice_ptr.data(), sizeof(int) * sell.slice_ptr.size());
+    if (!sell.sell_lm.empty()) PV_UP(ix.sell_lm, sell.sell_lm.data(), sizeof(int) * sell.sell_lm.size());
+    if (slots > 0) {
+      PV_UP(ix.sell_cam, sell_cam.data(), sizeof(int) * slots);
+      PV_UP(ix.sell_uv, sell_uv.data(), sizeof(double) * 2 * slots);
+    }
+    if (nnz > 0) PV_UP(ix.obs_slot, sell.obs_slot.data(), sizeof(int) * static_cast<size_t>(nnz));
+    if (!long_info.empty()) PV_UP(ix.long_tile_info, long_info.data(), sizeof(int4) * long_info.size());
+  }
   PV_UP(ix.cam_ptr, cam_ptr.data(), sizeof(int) * (C + 1));
   PV_UP(ix.item_ptr, item_ptr.data(), sizeof(int) * item_ptr.size());
   PV_UP(ix.cam_item_ptr, cam_item_ptr.data(), sizeof(int) * (C + 1));
@@ -321,6 +414,8 @@ int Engine::upload(const povar_problem_desc* desc) {
   PV_ALLOC(d_.lm_graw, static_cast<size_t>(L) * 4);
   PV_ALLOC(d_.hll_inv, static_cast<size_t>(L) * 6);
   PV_ALLOC(d_.lm_rec, static_cast<size_t>(L) * kLmRec);
+  PV_ALLOC(d_.lm_fold, static_cast<size_t>(L) * 10);
+  PV_ALLOC(d_.cam_rec, static_cast<size_t>(C) * 28);
   PV_ALLOC(d_.kron, static_cast<size_t>(C) * kKron);
   PV_ALLOC(d_.kron2, static_cast<size_t>(C) * kKron);
   PV_ALLOC(d_.item_kron, static_cast<size_t>(ix.num_items) * kKron);
@@ -428,6 +523,17 @@ int Engine::linearize(bool joint, double alpha) {
   const bool power = joint ? true
                            : (opt_.solver_type_step_1 == POVAR_POWER_VARPROJ ||
                               opt_.solver_type_step_1 == POVAR_POWER_SCHUR_COMPLEMENT);
+  // per-observation coefficients the term kernels stream (kernels_series.cu): first use allocates
+  if (joint && !d_.obs_d) {
+    PV_ALLOC(d_.obs_d, static_cast<size_t>(nnz_) * 3);
+    PV_ALLOC(d_.csc_d, static_cast<size_t>(nnz_) * 3);
+    PV_ALLOC(d_.sell_d, static_cast<size_t>(d_.ix.sell_slots) * 3);
+  }
+  if (!joint && opt_.robust_norm == POVAR_NORM_HUBER && !d_.obs_w) {
+    PV_ALLOC(d_.obs_w, static_cast<size_t>(nnz_));
+    PV_ALLOC(d_.csc_w, static_cast<size_t>(nnz_));
+    PV_ALLOC(d_.sell_w, static_cast<size_t>(d_.ix.sell_slots));
+  }
   PV_CUDA(cudaEventRecord(ev_[0], stream_));
   PV_CUDA(cudaMemsetAsync(d_.flags, 0, 4 * sizeof(int), stream_));
   // landmark side: Jl^T Jl, Jl^T r, column scales (LinearizorSC step 1 does not scale Jl:
@@ -441,6 +547,7 @@ int Engine::linearize(bool joint, double alpha) {
     if (rc != POVAR_OK) return rc;
   }
   launch_cam_scale(d_, mp_, lc());
+  launch_cam_rec_static(d_, joint, lc());
   PV_CUDA(cudaGetLastError());
   int flags[4] = {0, 0, 0, 0};
   PV_CUDA(cudaMemcpyAsync(flags, d_.flags, sizeof(flags), cudaMemcpyDeviceToHost, stream_));
@@ -462,8 +569,13 @@ int Engine::linearize(bool joint, double alpha) {
 
 // raw_c = sum over the observations of camera c of the camera half of E0 (or of b), all ranks
 void Engine::e0_product(bool joint, const double* y, bool in_series) {
-  launch_e0_landmark(d_, mp_, joint, y, in_series, lc());
-  launch_passB(d_, mp_, joint, PASSB_E0, in_series, lc());
+  if (e0_v1_) {
+    launch_e0_landmark(d_, mp_, joint, y, in_series, lc());
+    launch_passB(d_, mp_, joint, PASSB_E0, in_series, lc());
+  } else {
+    launch_e0_landmark_v2(d_, mp_, joint, in_series, e0_layout_, lc());
+    launch_passB_e0_v2(d_, mp_, joint, in_series, lc());
+  }
   launch_reduce_items(d_, d_.item_part, 12, d_.cam_raw, in_series, lc());
   allreduce(d_.cam_raw, static_cast<size_t>(C_) * 12);
 }
@@ -904,6 +1016,10 @@ int64_t Engine::debug_read(const char* name, double* out, int64_t capacity) {
   else if (n == "csc_lm") isrc = d_.ix.csc_lm, count = nnz_;
   else if (n == "item_ptr") isrc = d_.ix.item_ptr, count = d_.ix.num_items + 1;
   else if (n == "item_cam") isrc = d_.ix.item_cam, count = d_.ix.num_items;
+  else if (n == "slice_ptr") isrc = d_.ix.slice_ptr, count = d_.ix.num_slices + 1;
+  else if (n == "sell_lm") isrc = d_.ix.sell_lm, count = 8LL * d_.ix.num_slices;
+  else if (n == "sell_cam") isrc = d_.ix.sell_cam, count = d_.ix.sell_slots;
+  else if (n == "obs_slot") isrc = d_.ix.obs_slot, count = nnz_;
   else {
     fail(POVAR_ERR_INVALID, "debug_read: unknown array '" + n + "'");
     return POVAR_ERR_INVALID;
@@ -976,8 +1092,14 @@ int Engine::bench_power_kernels(bool joint, int reps, double* seconds) {
     PV_CUDA(cudaEventRecord(ev_[0], stream_));
     for (int i = 0; i < reps; ++i) {
       switch (k) {
-        case 0: launch_e0_landmark(d_, mp_, joint, d_.vec_y, true, lc()); break;
-        case 1: launch_passB(d_, mp_, joint, PASSB_E0, true, lc()); break;
+        case 0:
+          if (e0_v1_) launch_e0_landmark(d_, mp_, joint, d_.vec_y, true, lc());
+          else launch_e0_landmark_v2(d_, mp_, joint, true, e0_layout_, lc());
+          break;
+        case 1:
+          if (e0_v1_) launch_passB(d_, mp_, joint, PASSB_E0, true, lc());
+          else launch_passB_e0_v2(d_, mp_, joint, true, lc());
+          break;
         case 2: launch_reduce_items(d_, d_.item_part, 12, d_.cam_raw, true, lc()); break;
         default: launch_series_term(d_, joint, i + 1, -1.0, -1.0, lc()); break;
       }

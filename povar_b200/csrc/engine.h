@@ -76,6 +76,8 @@ class Engine {
   bool have_solve_ = false;       // a solve ran on the current linearisation (apply needs its increment)
   double lambda_ = 0.0;           // damping of the last solve (landmark damping of apply)
   int dim_ = 12;
+  int e0_layout_ = 0;             // landmark half of E0: 0 sliced ELL, 1 tiles (POVAR_E0_IMPL=tiles)
+  bool e0_v1_ = false;            // POVAR_E0_IMPL=v1: old term kernels (kernels_landmark.cu / kernels_camera.cu)
   double* P_prev_ = nullptr;      // cameras of the linearisation point during a VarPro apply
   void* cusolver_ = nullptr;      // cusolverDnHandle_t (CHOLESKY only)
   double* chol_work_ = nullptr;
@@ -88,6 +90,15 @@ class Engine {
   int C_ = 0, L_ = 0;
   long long nnz_ = 0;
 };
+
+struct SellLayout {
+  std::vector<int> slice_ptr;   // [num_slices+1] rows
+  std::vector<int> sell_lm;     // [8*num_slices]
+  std::vector<int> obs_slot;    // [nnz]
+  std::vector<int> long_lms;    // landmarks with more than 32 observations
+  int rows = 0;
+};
+void build_sell(const std::vector<int>& lm_ptr, int window, SellLayout* out);
 
 // host-side index construction (engine.cu), exposed for the CPU tests through the C ABI
 void build_tiles(const std::vector<int>& lm_ptr, std::vector<int>* tile_ptr);

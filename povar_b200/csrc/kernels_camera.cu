@@ -55,7 +55,7 @@ template <bool JOINT, int KIND>
 __global__ void __launch_bounds__(kBlock)
 k_kron(DeviceIndex ix, const double* __restrict__ P, const double* __restrict__ X, double c1,
        double c2, Robust rb, const double* __restrict__ lm_scale, const double* __restrict__ hll_inv,
-       double* __restrict__ item_kron) {
+       double* __restrict__ item_kron, double* __restrict__ csc_d, double* __restrict__ csc_w) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= ix.num_items) return;
@@ -148,6 +148,12 @@ k_kron(DeviceIndex ix, const double* __restrict__ P, const double* __restrict__ 
       JointObs ob;
       ob.eval(cam, uv.x, uv.y, x, rb);
       const double w = ob.sw * ob.sw;
+      if (csc_d != nullptr) {
+        double* dp = csc_d + 3 * static_cast<size_t>(e);
+        dp[0] = ob.sw * ob.iz;
+        dp[1] = ob.sw * ob.d02;
+        dp[2] = ob.sw * ob.d12;
+      }
       E[0] = w * ob.iz * ob.iz;
       E[1] = 0.0;
       E[2] = w * ob.iz * ob.d02;
@@ -158,6 +164,7 @@ k_kron(DeviceIndex ix, const double* __restrict__ P, const double* __restrict__ 
       PoseObs ob;
       ob.eval(cam, uv.x, uv.y, x, c1, c2, rb);
       const double w = ob.sw * ob.sw;
+      if (csc_w != nullptr) csc_w[e] = w;
       const double a = c1 * c1, bq = c2 * c2;
       E[0] = w * (a + bq);
       E[1] = 0.0;
@@ -443,9 +450,12 @@ __device__ __forceinline__ void raw_to_reduced(const double* __restrict__ raw,
 }
 
 // y (12) gathered by the passes:  s o x   or   s o (Pi x)
+// `rec` is the camera's record of the landmark-major E0 pass (CamRec<JOINT>): y is stored there too
 template <bool JOINT>
 __device__ __forceinline__ void reduced_to_y(const double* x, const double* __restrict__ s,
-                                             const double* __restrict__ Pc, double* __restrict__ y) {
+                                             const double* __restrict__ Pc, double* __restrict__ y,
+                                             double* __restrict__ rec) {
+  double yv[12];
   if (JOINT) {
     double pv[12], full[12];
 #pragma unroll
@@ -454,10 +464,17 @@ __device__ __forceinline__ void reduced_to_y(const double* x, const double* __re
     pi.make(pv);
     pi.apply(x, full);
 #pragma unroll
-    for (int i = 0; i < 12; ++i) y[i] = s[i] * full[i];
+    for (int i = 0; i < 12; ++i) yv[i] = s[i] * full[i];
   } else {
 #pragma unroll
-    for (int i = 0; i < 12; ++i) y[i] = s[i] * x[i];
+    for (int i = 0; i < 12; ++i) yv[i] = s[i] * x[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 12; ++i) y[i] = yv[i];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) rec[CamRec<JOINT>::y_index(k, j)] = yv[4 * k + j];
   }
 }
 
@@ -467,7 +484,7 @@ __global__ void __launch_bounds__(128)
 k_finish_b(int C, const double* __restrict__ raw, const double* __restrict__ pose_scale,
            const double* __restrict__ P, const double* __restrict__ Binv, double* __restrict__ b,
            double* __restrict__ tmp, double* __restrict__ acc, double* __restrict__ y,
-           double* __restrict__ norm_part) {
+           double* __restrict__ cam_rec, double* __restrict__ norm_part) {
   constexpr int D = JOINT ? 11 : 12;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
@@ -487,7 +504,8 @@ k_finish_b(int C, const double* __restrict__ raw, const double* __restrict__ pos
     tmp[static_cast<size_t>(c) * D + i] = v;
     acc[static_cast<size_t>(c) * D + i] = v;
   }
-  reduced_to_y<JOINT>(x0, s, Pc, y + 12 * static_cast<size_t>(c));
+  reduced_to_y<JOINT>(x0, s, Pc, y + 12 * static_cast<size_t>(c),
+                      cam_rec + CamRec<JOINT>::kStride * static_cast<size_t>(c));
   norm_part[2 * c] = n2;
   norm_part[2 * c + 1] = n2;
 }
@@ -497,8 +515,8 @@ template <bool JOINT>
 __global__ void __launch_bounds__(128)
 k_term(int C, const double* __restrict__ raw, const double* __restrict__ pose_scale,
        const double* __restrict__ P, const double* __restrict__ Binv, double* __restrict__ tmp,
-       double* __restrict__ acc, double* __restrict__ y, double* __restrict__ norm_part,
-       const SeriesCtl* __restrict__ ctl) {
+       double* __restrict__ acc, double* __restrict__ y, double* __restrict__ cam_rec,
+       double* __restrict__ norm_part, const SeriesCtl* __restrict__ ctl) {
   if (ctl->done) return;
   constexpr int D = JOINT ? 11 : 12;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -520,7 +538,8 @@ k_term(int C, const double* __restrict__ raw, const double* __restrict__ pose_sc
     na += a * a;
     tmp[static_cast<size_t>(c) * D + i] = v;
   }
-  reduced_to_y<JOINT>(t, s, Pc, y + 12 * static_cast<size_t>(c));
+  reduced_to_y<JOINT>(t, s, Pc, y + 12 * static_cast<size_t>(c),
+                      cam_rec + CamRec<JOINT>::kStride * static_cast<size_t>(c));
   norm_part[2 * c] = nt;
   norm_part[2 * c + 1] = na;
 }
@@ -597,14 +616,15 @@ k_e0_finish(int C, const double* __restrict__ raw, const double* __restrict__ po
 template <bool JOINT>
 __global__ void __launch_bounds__(128)
 k_make_y(int C, const double* __restrict__ x, const double* __restrict__ pose_scale,
-         const double* __restrict__ P, double* __restrict__ y) {
+         const double* __restrict__ P, double* __restrict__ y, double* __restrict__ cam_rec) {
   constexpr int D = JOINT ? 11 : 12;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double xv[12];
   for (int i = 0; i < D; ++i) xv[i] = x[static_cast<size_t>(c) * D + i];
   reduced_to_y<JOINT>(xv, pose_scale + 12 * static_cast<size_t>(c), P + 12 * static_cast<size_t>(c),
-                      y + 12 * static_cast<size_t>(c));
+                      y + 12 * static_cast<size_t>(c),
+                      cam_rec + CamRec<JOINT>::kStride * static_cast<size_t>(c));
 }
 
 // P += reshape(v)   (Camera::inc_pose_pOSE / inc_pose_projective_space, bal_problem.hpp:132-163)
@@ -650,18 +670,19 @@ void launch_kron(const DeviceState& d, const ModelParams& mp, bool joint, KronKi
   if (kind == KRON_HPP) {
     if (joint) {
       k_kron<true, KRON_HPP><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.X, mp.c1, mp.c2, rb, d.lm_scale,
-                                                               d.hll_inv, d.item_kron);
+                                                               d.hll_inv, d.item_kron, d.csc_d, nullptr);
     } else {
-      k_kron<false, KRON_HPP><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.X, mp.c1, mp.c2, rb, d.lm_scale,
-                                                                d.hll_inv, d.item_kron);
+      k_kron<false, KRON_HPP><<<blocks, kBlock, 0, lc.stream>>>(
+          d.ix, d.P, d.X, mp.c1, mp.c2, rb, d.lm_scale, d.hll_inv, d.item_kron, nullptr,
+          mp.robust_norm == NORM_HUBER ? d.csc_w : nullptr);
     }
   } else {
     if (joint) {
       k_kron<true, KRON_SDIAG><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.X, mp.c1, mp.c2, rb, d.lm_scale,
-                                                                 d.hll_inv, d.item_kron);
+                                                                 d.hll_inv, d.item_kron, nullptr, nullptr);
     } else {
       k_kron<false, KRON_SDIAG><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.X, mp.c1, mp.c2, rb, d.lm_scale,
-                                                                  d.hll_inv, d.item_kron);
+                                                                  d.hll_inv, d.item_kron, nullptr, nullptr);
     }
   }
   count(lc);
@@ -732,10 +753,10 @@ void launch_finish_b(const DeviceState& d, bool joint, const LaunchCfg& lc) {
   const int blocks = (d.ix.C + 127) / 128;
   if (joint) {
     k_finish_b<true><<<blocks, 128, 0, lc.stream>>>(d.ix.C, d.cam_raw, d.pose_scale, d.P, d.Binv, d.b,
-                                                    d.vec_tmp, d.vec_acc, d.vec_y, d.norm_part);
+                                                    d.vec_tmp, d.vec_acc, d.vec_y, d.cam_rec, d.norm_part);
   } else {
     k_finish_b<false><<<blocks, 128, 0, lc.stream>>>(d.ix.C, d.cam_raw, d.pose_scale, d.P, d.Binv, d.b,
-                                                     d.vec_tmp, d.vec_acc, d.vec_y, d.norm_part);
+                                                     d.vec_tmp, d.vec_acc, d.vec_y, d.cam_rec, d.norm_part);
   }
   count(lc);
 }
@@ -750,10 +771,10 @@ void launch_series_term(const DeviceState& d, bool joint, int term, double eta, 
   const int blocks = (d.ix.C + 127) / 128;
   if (joint) {
     k_term<true><<<blocks, 128, 0, lc.stream>>>(d.ix.C, d.cam_raw, d.pose_scale, d.P, d.Binv, d.vec_tmp,
-                                                d.vec_acc, d.vec_y, d.norm_part, d.ctl);
+                                                d.vec_acc, d.vec_y, d.cam_rec, d.norm_part, d.ctl);
   } else {
     k_term<false><<<blocks, 128, 0, lc.stream>>>(d.ix.C, d.cam_raw, d.pose_scale, d.P, d.Binv, d.vec_tmp,
-                                                 d.vec_acc, d.vec_y, d.norm_part, d.ctl);
+                                                 d.vec_acc, d.vec_y, d.cam_rec, d.norm_part, d.ctl);
   }
   k_series_decide<<<1, kBlock, 0, lc.stream>>>(d.ix.C, d.norm_part, term, eta, r_tolerance, d.ctl);
   count(lc, 2);
@@ -772,9 +793,9 @@ void launch_e0_finish(const DeviceState& d, bool joint, double* out, const Launc
 void launch_make_y(const DeviceState& d, bool joint, const double* x, double* y, const LaunchCfg& lc) {
   const int blocks = (d.ix.C + 127) / 128;
   if (joint) {
-    k_make_y<true><<<blocks, 128, 0, lc.stream>>>(d.ix.C, x, d.pose_scale, d.P, y);
+    k_make_y<true><<<blocks, 128, 0, lc.stream>>>(d.ix.C, x, d.pose_scale, d.P, y, d.cam_rec);
   } else {
-    k_make_y<false><<<blocks, 128, 0, lc.stream>>>(d.ix.C, x, d.pose_scale, d.P, y);
+    k_make_y<false><<<blocks, 128, 0, lc.stream>>>(d.ix.C, x, d.pose_scale, d.P, y, d.cam_rec);
   }
   count(lc);
 }

@@ -215,7 +215,9 @@ __global__ void __launch_bounds__(kBlock)
 k_lin_landmark(DeviceIndex ix, const double* __restrict__ P, const double* __restrict__ X,
                double c1, double c2, Robust rb, double eps, int scale_jl,
                double* __restrict__ lm_hraw, double* __restrict__ lm_graw,
-               double* __restrict__ lm_scale, int* __restrict__ flags) {
+               double* __restrict__ lm_scale, int* __restrict__ flags,
+               double* __restrict__ obs_d, double* __restrict__ obs_w,
+               double* __restrict__ sell_d, double* __restrict__ sell_w) {
   constexpr int NV = JOINT ? 14 : 9;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -241,6 +243,21 @@ k_lin_landmark(DeviceIndex ix, const double* __restrict__ P, const double* __res
         double j0[4], j1[4];
         ob.jl_rows(cam, j0, j1);
         const double w = ob.sw * ob.sw;
+        {
+          // what the power-series term kernels stream instead of re-deriving it (kernels_series.cu)
+          const double d0 = ob.sw * ob.iz, d1 = ob.sw * ob.d02, d2 = ob.sw * ob.d12;
+          double* dp = obs_d + 3 * static_cast<size_t>(o);
+          dp[0] = d0;
+          dp[1] = d1;
+          dp[2] = d2;
+          const int slot = __ldg(ix.obs_slot + o);
+          if (slot >= 0) {
+            double* sp = sell_d + 3 * static_cast<size_t>(slot);
+            sp[0] = d0;
+            sp[1] = d1;
+            sp[2] = d2;
+          }
+        }
         int n = 0;
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
@@ -255,6 +272,11 @@ k_lin_landmark(DeviceIndex ix, const double* __restrict__ P, const double* __res
         PoseObs ob;
         ob.eval(cam, uv.x, uv.y, x, c1, c2, rb);
         const double w = ob.sw * ob.sw;
+        if (obs_w != nullptr) {
+          obs_w[o] = w;
+          const int slot = __ldg(ix.obs_slot + o);
+          if (slot >= 0) sell_w[slot] = w;
+        }
         int n = 0;
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
@@ -316,7 +338,8 @@ template <bool JOINT>
 __global__ void __launch_bounds__(kBlock)
 k_prep_landmark(int L, const double* __restrict__ X, const double* __restrict__ lm_hraw,
                 const double* __restrict__ lm_graw, const double* __restrict__ lm_scale,
-                double lambda_lm, double* __restrict__ hll_inv, double* __restrict__ lm_rec) {
+                double lambda_lm, double* __restrict__ hll_inv, double* __restrict__ lm_rec,
+                double* __restrict__ lm_fold) {
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
   if (l >= L) return;
   double x[4], s[4];
@@ -375,6 +398,27 @@ k_prep_landmark(int L, const double* __restrict__ X, const double* __restrict__ 
     pi.apply(h3, h4);
 #pragma unroll
     for (int a = 0; a < 4; ++a) H[a] = s[a] * h4[a];
+    // fold = S Pi Hll^-1 Pi^T S (4x4, symmetric): H_l = fold G_l in the power-series term
+    double F[4][4];
+#pragma unroll
+    for (int nn = 0; nn < 4; ++nn) {
+      double e4[4] = {0, 0, 0, 0}, f3[3], k3[3], k4[4];
+      e4[nn] = s[nn];
+      pi.apply_t(e4, f3);
+      sym3_mul(inv, f3, k3);
+      pi.apply(k3, k4);
+#pragma unroll
+      for (int a = 0; a < 4; ++a) F[a][nn] = s[a] * k4[a];
+    }
+    double* fo = lm_fold + 10 * static_cast<size_t>(l);
+    {
+      int nn = 0;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+#pragma unroll
+        for (int b2 = a; b2 < 4; ++b2) fo[nn++] = 0.5 * (F[a][b2] + F[b2][a]);
+      }
+    }
   } else {
     hll[0] = s[0] * s[0] * h[0] + lambda_lm;
     hll[1] = s[0] * s[1] * h[1];
@@ -389,6 +433,13 @@ k_prep_landmark(int L, const double* __restrict__ X, const double* __restrict__ 
     sym3_mul(inv, sg, h3);
 #pragma unroll
     for (int a = 0; a < 3; ++a) H[a] = s[a] * h3[a];
+    double* fo = lm_fold + 10 * static_cast<size_t>(l);
+    fo[0] = s[0] * s[0] * inv[0];
+    fo[1] = s[0] * s[1] * inv[1];
+    fo[2] = s[0] * s[2] * inv[2];
+    fo[3] = s[1] * s[1] * inv[3];
+    fo[4] = s[1] * s[2] * inv[4];
+    fo[5] = s[2] * s[2] * inv[5];
   }
   double* hi = hll_inv + 6 * static_cast<size_t>(l);
 #pragma unroll
@@ -849,11 +900,14 @@ void launch_lin_landmark(const DeviceState& d, const ModelParams& mp, bool joint
   const int blocks = tile_grid(d);
   if (joint) {
     k_lin_landmark<true><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.X, mp.c1, mp.c2, rb, mp.jacobi_eps, 1,
-                                                           d.lm_hraw, d.lm_graw, d.lm_scale, d.flags);
+                                                           d.lm_hraw, d.lm_graw, d.lm_scale, d.flags,
+                                                           d.obs_d, nullptr, d.sell_d, nullptr);
   } else {
     k_lin_landmark<false><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.X, mp.c1, mp.c2, rb, mp.jacobi_eps,
                                                             scale_jl ? 1 : 0, d.lm_hraw, d.lm_graw,
-                                                            d.lm_scale, d.flags);
+                                                            d.lm_scale, d.flags, nullptr,
+                                                            mp.robust_norm == NORM_HUBER ? d.obs_w : nullptr,
+                                                            nullptr, d.sell_w);
   }
   count(lc);
 }
@@ -863,10 +917,10 @@ void launch_prep_landmark(const DeviceState& d, bool joint, double lambda_lm, co
   if (blocks == 0) return;
   if (joint) {
     k_prep_landmark<true><<<blocks, kBlock, 0, lc.stream>>>(d.ix.L, d.X, d.lm_hraw, d.lm_graw, d.lm_scale,
-                                                            lambda_lm, d.hll_inv, d.lm_rec);
+                                                            lambda_lm, d.hll_inv, d.lm_rec, d.lm_fold);
   } else {
     k_prep_landmark<false><<<blocks, kBlock, 0, lc.stream>>>(d.ix.L, d.X, d.lm_hraw, d.lm_graw, d.lm_scale,
-                                                             lambda_lm, d.hll_inv, d.lm_rec);
+                                                             lambda_lm, d.hll_inv, d.lm_rec, d.lm_fold);
   }
   count(lc);
 }

@@ -25,6 +25,19 @@ struct DeviceIndex {
   int* tile_ptr = nullptr;    // [num_tiles+1] observation ranges: whole short landmarks
                               //   (<= 32 obs together) or one long landmark
   int num_tiles = 0;
+  int4* tile_info = nullptr;  // [num_tiles] {first obs, obs count, first landmark, landmark span}
+  // landmark-major, sliced ELL for the landmark half of E0 (kernels_series.cu): landmarks with 1..32
+  // observations, sorted by degree inside windows of kSellWindow landmarks, eight per slice; slot
+  // 8 * row + g holds the row-th observation of the g-th landmark of the slice (camera -1 = padding)
+  int num_slices = 0;
+  int* slice_ptr = nullptr;   // [num_slices+1] first row of the slice
+  int* sell_lm = nullptr;     // [8*num_slices] landmark of group g, -1 = none
+  int* sell_cam = nullptr;    // [8*rows]
+  double2* sell_uv = nullptr; // [8*rows]
+  int* obs_slot = nullptr;    // [nnz] slot of the observation, -1 for landmarks outside the SELL set
+  long long sell_slots = 0;   // 8 * rows
+  int num_long_tiles = 0;     // landmarks with more than 32 observations: one warp each
+  int4* long_tile_info = nullptr;
   // camera-major
   int* cam_ptr = nullptr;     // [C+1]
   int* csc_lm = nullptr;      // [nnz] landmark of the entry (ascending inside a camera)
@@ -37,6 +50,7 @@ struct DeviceIndex {
 
 constexpr double kEpsSqrtHost = 1e-5;  // Sophus::Constants<double>::epsilonSqrt()
 constexpr int kKron = 60;     // unique entries of sum_i E_i (x) (X X^T): 6 x 10
+constexpr int kSellWindow = 4096;   // sorting window of the sliced-ELL landmark order
 constexpr int kLmRec = 8;     // per-landmark record read by the camera-major pass: [X(4) | H(4)]
 
 // series control block, lives in device memory
@@ -74,6 +88,14 @@ struct DeviceState {
   double* lm_graw = nullptr;     // [L*4]  sum_i w Jl_raw^T r
   double* hll_inv = nullptr;     // [L*6]
   double* lm_rec = nullptr;      // [L*8]  [X | H] for the camera-major pass
+  double* lm_fold = nullptr;     // [L*10] S (Pi) Hll^-1 (Pi^T) S, packed symmetric: H_l = fold_l G_l
+  double* cam_rec = nullptr;     // [C*28] per-camera record of the landmark-major E0 pass (CamRec<>)
+  double* obs_d = nullptr;       // [nnz*3] step 2: sqrt(w) (1/z, -x/z^2, -y/z^2) at the linearisation point
+  double* csc_d = nullptr;       // [nnz*3] the same, camera-major
+  double* obs_w = nullptr;       // [nnz]   step 1, HUBER only: robust weight at the linearisation point
+  double* sell_d = nullptr;      // [slots*3] obs_d in SELL order
+  double* sell_w = nullptr;      // [slots]   obs_w in SELL order
+  double* csc_w = nullptr;       // [nnz]   the same, camera-major
   double* kron = nullptr;        // [C*60]
   double* kron2 = nullptr;       // [C*60] diagonal blocks of sum_l Hpl Hll^-1 Hlp (PCG preconditioner)
   double* item_kron = nullptr;   // [num_items*60]
@@ -152,6 +174,13 @@ void launch_series_term(const DeviceState& d, bool joint, int term, double eta, 
 void launch_finish_b(const DeviceState& d, bool joint, const LaunchCfg& lc);
 void launch_e0_finish(const DeviceState& d, bool joint, double* out, const LaunchCfg& lc);
 void launch_make_y(const DeviceState& d, bool joint, const double* x, double* y, const LaunchCfg& lc);
+// cam_rec: matrix part (after a linearisation) -- the y part is written by whoever makes y
+void launch_cam_rec_static(const DeviceState& d, bool joint, const LaunchCfg& lc);
+// ---- power-series term kernels, lane-group layout (kernels_series.cu) ----
+void launch_e0_landmark_v2(const DeviceState& d, const ModelParams& mp, bool joint, bool in_series,
+                           int layout, const LaunchCfg& lc);
+void launch_passB_e0_v2(const DeviceState& d, const ModelParams& mp, bool joint, bool in_series,
+                        const LaunchCfg& lc);
 void launch_cam_update_pose(const DeviceState& d, const double* inc, const LaunchCfg& lc);
 void launch_cam_update_joint(const DeviceState& d, const double* y, const LaunchCfg& lc);
 void launch_normalize_cams(const DeviceState& d, const LaunchCfg& lc);

@@ -67,7 +67,15 @@ def test_two_step_trace_matches_reference_golden(name):
     # step 1 is stable everywhere: every trial within 1e-9, its final cost within 1e-6 (north_star)
     for i in range(k2):
         assert abs(its[i].cost - ref["cost"][i]) <= 1e-9 * ref["cost"][i]
-    assert abs(summary.num_successful_steps - ref["num_successful_steps"]) <= 1 or worst == 0.0
+    # accepted steps within +-1 of the reference -- where the reference agrees with itself; where its own
+    # 8-thread run takes a different number of steps (chaotic tail of step 2) the count has
+    # to lie in the range the two reference runs span
+    n1 = ref["num_successful_steps"]
+    # (the log's step_is_successful also flags the two initial cost evaluations: same offset in both runs)
+    n8 = n1 + int(sum(bool(v) for v in meta["threads8"]["step_is_successful"])) - \
+        int(sum(bool(v) for v in ref["step_is_successful"]))
+    lo, hi = min(n1, n8) - 1, max(n1, n8) + 1
+    assert lo <= summary.num_successful_steps <= hi or worst == 0.0, (summary.num_successful_steps, n1, n8)
     for i in range(min(len(its), k2)):
         assert its[i].iteration == ref["iteration"][i]
         assert abs(its[i].trust_region_radius - ref["trust_region_radius"][i]) <= 1e-6 * ref["trust_region_radius"][i]
