@@ -295,22 +295,20 @@ struct Reflector {
 };
 
 // ---- per-camera record gathered by the landmark-major half of E0 (kernels_series.cu) -----------
-// Four lanes share one observation; lane `sub` reads 16-byte chunk (p, sub) in its p-th load, so
-// the lanes of a group touch consecutive bytes (whole sectors) instead of one line per lane.
-//   p = 0, 1 : y_sub[0..1], y_sub[2..3]      (sub < 3; y = what the product is applied to)
-//   p = 2, 3 : (M[0][sub], M[1][sub]), (M[2][sub], 0)   M = P[:, 0:3] (step 1) or P (step 2)
-// Dense packing: 12 chunks (192 B) in step 1, 14 chunks (224 B) in step 2.
-template <bool JOINT>
+// Four lanes share one observation; lane `sub` reads 16-byte chunk 4 p + sub in its p-th load, so
+// each load of a group covers 64 aligned bytes (two whole sectors) instead of one line per lane.
+// 24 doubles = 192 bytes per camera, both models:
+//   lanes 0..2:  (y_sub[0], y_sub[1]) | (y_sub[2], y_sub[3]) | (M[0][sub], M[1][sub])
+//   lane 3:      (M[2][0], M[2][1])   | (M[2][2], M[2][3])   | (M[0][3], M[1][3])
+// y = the vector the product is applied to (three 4-blocks), M = P (step 1 uses M[:, 0:3] only and
+// keeps zeros in column 3).
 struct CamRec {
-  static constexpr int kStride = JOINT ? 28 : 24;   // doubles per camera
-  __host__ __device__ static constexpr int chunk(int p, int sub) {
-    return JOINT ? (p < 2 ? 3 * p + sub : 6 + 4 * (p - 2) + sub) : 3 * p + sub;
-  }
+  static constexpr int kStride = 24;   // doubles per camera
   __host__ __device__ static constexpr int y_index(int k, int j) {
-    return 2 * chunk(j >> 1, k) + (j & 1);
+    return 2 * (4 * (j >> 1) + k) + (j & 1);
   }
   __host__ __device__ static constexpr int m_index(int r, int n) {
-    return r < 2 ? 2 * chunk(2, n) + r : 2 * chunk(3, n);
+    return r < 2 ? (n < 3 ? 16 + 2 * n + r : 22 + r) : (n < 2 ? 6 + n : 12 + n);
   }
 };
 

@@ -241,7 +241,6 @@ int Engine::create(const povar_problem_desc* desc, const povar_options* opt,
     // POVAR_E0_IMPL=v1 selects the one-observation-per-lane term kernels (A/B timing, debugging)
     const char* impl = getenv("POVAR_E0_IMPL");
     e->e0_v1_ = impl != nullptr && std::strcmp(impl, "v1") == 0;
-    e->e0_layout_ = (impl != nullptr && std::strcmp(impl, "tiles") == 0) ? 1 : 0;
   }
   if (e->device_ < 0 || e->device_ >= ndev) {
     if (err) *err = "povar_create: device ordinal out of range";
@@ -339,7 +338,6 @@ int Engine::upload(const povar_problem_desc* desc) {
   PV_ALLOC(ix.obs_lm, nnz);
   PV_ALLOC(ix.obs_uv, nnz);
   PV_ALLOC(ix.tile_ptr, tile_ptr.size());
-  PV_ALLOC(ix.tile_info, ix.num_tiles);
   PV_ALLOC(ix.cam_ptr, C + 1);
   PV_ALLOC(ix.csc_lm, nnz);
   PV_ALLOC(ix.csc_uv, nnz);
@@ -358,14 +356,6 @@ int Engine::upload(const povar_problem_desc* desc) {
   }
   PV_UP(ix.tile_ptr, tile_ptr.data(), sizeof(int) * tile_ptr.size());
   {
-    std::vector<int4> tile_info(ix.num_tiles);
-    for (int t = 0; t < ix.num_tiles; ++t) {
-      const int tb = tile_ptr[t], te = tile_ptr[t + 1];
-      tile_info[t] = make_int4(tb, te - tb, obs_lm[tb], obs_lm[te - 1] - obs_lm[tb] + 1);
-    }
-    if (ix.num_tiles > 0) PV_UP(ix.tile_info, tile_info.data(), sizeof(int4) * tile_info.size());
-  }
-  {
     // sliced-ELL copy of the observation stream for the landmark half of E0
     ix.num_slices = static_cast<int>(sell.slice_ptr.size()) - 1;
     ix.sell_slots = 8LL * sell.rows;
@@ -379,15 +369,13 @@ int Engine::upload(const povar_problem_desc* desc) {
       sell_uv[2 * static_cast<size_t>(slot)] = desc->obs_uv[2 * static_cast<size_t>(o)];
       sell_uv[2 * static_cast<size_t>(slot) + 1] = desc->obs_uv[2 * static_cast<size_t>(o) + 1];
     }
-    std::vector<int4> long_info;
-    for (int l : sell.long_lms) long_info.push_back(make_int4(lm_ptr[l], lm_ptr[l + 1] - lm_ptr[l], l, 1));
-    ix.num_long_tiles = static_cast<int>(long_info.size());
+    ix.num_long = static_cast<int>(sell.long_lms.size());
     PV_ALLOC(ix.slice_ptr, sell.slice_ptr.size());
     PV_ALLOC(ix.sell_lm, sell.sell_lm.size());
     PV_ALLOC(ix.sell_cam, slots);
     PV_ALLOC(ix.sell_uv, slots);
     PV_ALLOC(ix.obs_slot, nnz);
-    PV_ALLOC(ix.long_tile_info, long_info.size());
+    PV_ALLOC(ix.long_lm, sell.long_lms.size());
     PV_UP(ix.slice_ptr, sell.slice_ptr.data(), sizeof(int) * sell.slice_ptr.size());
     if (!sell.sell_lm.empty()) PV_UP(ix.sell_lm, sell.sell_lm.data(), sizeof(int) * sell.sell_lm.size());
     if (slots > 0) {
@@ -395,7 +383,7 @@ int Engine::upload(const povar_problem_desc* desc) {
       PV_UP(ix.sell_uv, sell_uv.data(), sizeof(double) * 2 * slots);
     }
     if (nnz > 0) PV_UP(ix.obs_slot, sell.obs_slot.data(), sizeof(int) * static_cast<size_t>(nnz));
-    if (!long_info.empty()) PV_UP(ix.long_tile_info, long_info.data(), sizeof(int4) * long_info.size());
+    if (ix.num_long > 0) PV_UP(ix.long_lm, sell.long_lms.data(), sizeof(int) * sell.long_lms.size());
   }
   PV_UP(ix.cam_ptr, cam_ptr.data(), sizeof(int) * (C + 1));
   PV_UP(ix.item_ptr, item_ptr.data(), sizeof(int) * item_ptr.size());
@@ -573,7 +561,7 @@ void Engine::e0_product(bool joint, const double* y, bool in_series) {
     launch_e0_landmark(d_, mp_, joint, y, in_series, lc());
     launch_passB(d_, mp_, joint, PASSB_E0, in_series, lc());
   } else {
-    launch_e0_landmark_v2(d_, mp_, joint, in_series, e0_layout_, lc());
+    launch_e0_landmark_v2(d_, mp_, joint, in_series, lc());
     launch_passB_e0_v2(d_, mp_, joint, in_series, lc());
   }
   launch_reduce_items(d_, d_.item_part, 12, d_.cam_raw, in_series, lc());
@@ -1094,7 +1082,7 @@ int Engine::bench_power_kernels(bool joint, int reps, double* seconds) {
       switch (k) {
         case 0:
           if (e0_v1_) launch_e0_landmark(d_, mp_, joint, d_.vec_y, true, lc());
-          else launch_e0_landmark_v2(d_, mp_, joint, true, e0_layout_, lc());
+          else launch_e0_landmark_v2(d_, mp_, joint, true, lc());
           break;
         case 1:
           if (e0_v1_) launch_passB(d_, mp_, joint, PASSB_E0, true, lc());

@@ -76,7 +76,6 @@ class Engine {
   bool have_solve_ = false;       // a solve ran on the current linearisation (apply needs its increment)
   double lambda_ = 0.0;           // damping of the last solve (landmark damping of apply)
   int dim_ = 12;
-  int e0_layout_ = 0;             // landmark half of E0: 0 sliced ELL, 1 tiles (POVAR_E0_IMPL=tiles)
   bool e0_v1_ = false;            // POVAR_E0_IMPL=v1: old term kernels (kernels_landmark.cu / kernels_camera.cu)
   double* P_prev_ = nullptr;      // cameras of the linearisation point during a VarPro apply
   void* cusolver_ = nullptr;      // cusolverDnHandle_t (CHOLESKY only)

@@ -474,7 +474,7 @@ __device__ __forceinline__ void reduced_to_y(const double* x, const double* __re
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) rec[CamRec<JOINT>::y_index(k, j)] = yv[4 * k + j];
+    for (int j = 0; j < 4; ++j) rec[CamRec::y_index(k, j)] = yv[4 * k + j];
   }
 }
 
@@ -505,7 +505,7 @@ k_finish_b(int C, const double* __restrict__ raw, const double* __restrict__ pos
     acc[static_cast<size_t>(c) * D + i] = v;
   }
   reduced_to_y<JOINT>(x0, s, Pc, y + 12 * static_cast<size_t>(c),
-                      cam_rec + CamRec<JOINT>::kStride * static_cast<size_t>(c));
+                      cam_rec + CamRec::kStride * static_cast<size_t>(c));
   norm_part[2 * c] = n2;
   norm_part[2 * c + 1] = n2;
 }
@@ -539,7 +539,7 @@ k_term(int C, const double* __restrict__ raw, const double* __restrict__ pose_sc
     tmp[static_cast<size_t>(c) * D + i] = v;
   }
   reduced_to_y<JOINT>(t, s, Pc, y + 12 * static_cast<size_t>(c),
-                      cam_rec + CamRec<JOINT>::kStride * static_cast<size_t>(c));
+                      cam_rec + CamRec::kStride * static_cast<size_t>(c));
   norm_part[2 * c] = nt;
   norm_part[2 * c + 1] = na;
 }
@@ -624,7 +624,7 @@ k_make_y(int C, const double* __restrict__ x, const double* __restrict__ pose_sc
   for (int i = 0; i < D; ++i) xv[i] = x[static_cast<size_t>(c) * D + i];
   reduced_to_y<JOINT>(xv, pose_scale + 12 * static_cast<size_t>(c), P + 12 * static_cast<size_t>(c),
                       y + 12 * static_cast<size_t>(c),
-                      cam_rec + CamRec<JOINT>::kStride * static_cast<size_t>(c));
+                      cam_rec + CamRec::kStride * static_cast<size_t>(c));
 }
 
 // P += reshape(v)   (Camera::inc_pose_pOSE / inc_pose_projective_space, bal_problem.hpp:132-163)

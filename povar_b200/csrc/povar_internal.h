@@ -25,7 +25,6 @@ struct DeviceIndex {
   int* tile_ptr = nullptr;    // [num_tiles+1] observation ranges: whole short landmarks
                               //   (<= 32 obs together) or one long landmark
   int num_tiles = 0;
-  int4* tile_info = nullptr;  // [num_tiles] {first obs, obs count, first landmark, landmark span}
   // landmark-major, sliced ELL for the landmark half of E0 (kernels_series.cu): landmarks with 1..32
   // observations, sorted by degree inside windows of kSellWindow landmarks, eight per slice; slot
   // 8 * row + g holds the row-th observation of the g-th landmark of the slice (camera -1 = padding)
@@ -36,8 +35,8 @@ struct DeviceIndex {
   double2* sell_uv = nullptr; // [8*rows]
   int* obs_slot = nullptr;    // [nnz] slot of the observation, -1 for landmarks outside the SELL set
   long long sell_slots = 0;   // 8 * rows
-  int num_long_tiles = 0;     // landmarks with more than 32 observations: one warp each
-  int4* long_tile_info = nullptr;
+  int num_long = 0;           // landmarks with more than 32 observations: one warp each, CSR arrays
+  int* long_lm = nullptr;     // [num_long]
   // camera-major
   int* cam_ptr = nullptr;     // [C+1]
   int* csc_lm = nullptr;      // [nnz] landmark of the entry (ascending inside a camera)
@@ -50,7 +49,7 @@ struct DeviceIndex {
 
 constexpr double kEpsSqrtHost = 1e-5;  // Sophus::Constants<double>::epsilonSqrt()
 constexpr int kKron = 60;     // unique entries of sum_i E_i (x) (X X^T): 6 x 10
-constexpr int kSellWindow = 4096;   // sorting window of the sliced-ELL landmark order
+constexpr int kSellWindow = 128;    // sorting window of the sliced-ELL landmark order
 constexpr int kLmRec = 8;     // per-landmark record read by the camera-major pass: [X(4) | H(4)]
 
 // series control block, lives in device memory
@@ -178,7 +177,7 @@ void launch_make_y(const DeviceState& d, bool joint, const double* x, double* y,
 void launch_cam_rec_static(const DeviceState& d, bool joint, const LaunchCfg& lc);
 // ---- power-series term kernels, lane-group layout (kernels_series.cu) ----
 void launch_e0_landmark_v2(const DeviceState& d, const ModelParams& mp, bool joint, bool in_series,
-                           int layout, const LaunchCfg& lc);
+                           const LaunchCfg& lc);
 void launch_passB_e0_v2(const DeviceState& d, const ModelParams& mp, bool joint, bool in_series,
                         const LaunchCfg& lc);
 void launch_cam_update_pose(const DeviceState& d, const double* inc, const LaunchCfg& lc);
