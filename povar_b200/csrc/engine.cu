@@ -107,36 +107,57 @@ void build_tiles(const std::vector<int>& lm_ptr, std::vector<int>* tile_ptr) {
 
 // Sliced ELL order of the landmarks with 1..32 observations (the landmark half of E0 gives a group of
 // four lanes to each landmark and walks its observations serially, so the eight landmarks of a slice
-// should have the same degree): stable sort by descending degree inside windows of `window`
-// landmarks, eight landmarks per slice, slice length = largest degree in it.
-void build_sell(const std::vector<int>& lm_ptr, int window, SellLayout* out) {
+// should have the same degree).  Landmarks are first put in the order of their MEDIAN camera (stable
+// counting sort): neighbouring slices then gather from neighbouring camera records, which is what lets
+// the per-camera table stay in L1 (the slices of one SM come from one stretch of this order,
+// kernels_series.cu).  Inside windows of `window` landmarks of that order: stable sort by descending
+// degree, eight landmarks per slice, slice length = largest degree in it.  The order of the
+// observations INSIDE a landmark is untouched (camera ascending), so every H_l keeps its bits.
+void build_sell(const std::vector<int>& lm_ptr, const int* obs_cam, int num_cams, int window,
+                SellLayout* out) {
   const int L = static_cast<int>(lm_ptr.size()) - 1;
   out->slice_ptr.assign(1, 0);
   out->sell_lm.clear();
   out->long_lms.clear();
   out->obs_slot.assign(static_cast<size_t>(lm_ptr[L]), -1);
-  std::vector<int> order;
-  int rows = 0;
-  for (int w0 = 0; w0 < L; w0 += window) {
-    const int w1 = std::min(L, w0 + window);
-    order.clear();
-    for (int l = w0; l < w1; ++l) {
+  // landmarks with 1..32 observations by median camera
+  std::vector<int> by_cam;
+  {
+    std::vector<int> bucket(static_cast<size_t>(num_cams) + 1, 0);
+    auto key = [&](int l) { return obs_cam[(lm_ptr[l] + lm_ptr[l + 1]) / 2]; };
+    for (int l = 0; l < L; ++l) {
       const int deg = lm_ptr[l + 1] - lm_ptr[l];
       if (deg > 32) out->long_lms.push_back(l);
-      else if (deg > 0) order.push_back(l);
+      else if (deg > 0) bucket[key(l) + 1]++;
     }
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-      return lm_ptr[a + 1] - lm_ptr[a] > lm_ptr[b + 1] - lm_ptr[b];
-    });
-    for (size_t i = 0; i < order.size(); i += 8) {
+    for (int c = 0; c < num_cams; ++c) bucket[c + 1] += bucket[c];
+    by_cam.resize(bucket[num_cams]);
+    for (int l = 0; l < L; ++l) {
+      const int deg = lm_ptr[l + 1] - lm_ptr[l];
+      if (deg > 0 && deg <= 32) by_cam[bucket[key(l)]++] = l;
+    }
+  }
+  const int n = static_cast<int>(by_cam.size());
+  out->sell_lm.reserve(static_cast<size_t>(n) + 8);
+  int rows = 0;
+  int head[34];
+  std::vector<int> order(window);
+  for (int w0 = 0; w0 < n; w0 += window) {
+    const int w1 = std::min(n, w0 + window);
+    // stable counting sort by descending degree
+    for (int k = 0; k < 34; ++k) head[k] = 0;
+    for (int i = w0; i < w1; ++i) head[32 - (lm_ptr[by_cam[i] + 1] - lm_ptr[by_cam[i]]) + 1]++;
+    for (int k = 0; k < 33; ++k) head[k + 1] += head[k];
+    for (int i = w0; i < w1; ++i) order[head[32 - (lm_ptr[by_cam[i] + 1] - lm_ptr[by_cam[i]])]++] = by_cam[i];
+    const int cnt = w1 - w0;
+    for (int i = 0; i < cnt; i += 8) {
       const int len = lm_ptr[order[i] + 1] - lm_ptr[order[i]];
       for (int g = 0; g < 8; ++g) {
-        const int l = i + g < order.size() ? order[i + g] : -1;
+        const int l = i + g < cnt ? order[i + g] : -1;
         out->sell_lm.push_back(l);
         if (l < 0) continue;
-        for (int o = lm_ptr[l]; o < lm_ptr[l + 1]; ++o) {
-          out->obs_slot[o] = 8 * (rows + (o - lm_ptr[l])) + g;
-        }
+        const int b = lm_ptr[l], e = lm_ptr[l + 1];
+        for (int o = b; o < e; ++o) out->obs_slot[o] = 8 * (rows + (o - b)) + g;
       }
       rows += len;
       out->slice_ptr.push_back(rows);
@@ -322,7 +343,7 @@ int Engine::upload(const povar_problem_desc* desc) {
   build_items(cam_ptr, choose_item_len(nnz), &item_ptr, &item_cam, &cam_item_ptr);
 
   SellLayout sell;
-  build_sell(lm_ptr, kSellWindow, &sell);
+  build_sell(lm_ptr, desc->obs_cam, C, kSellWindow, &sell);
   if (static_cast<long long>(sell.rows) * 8 >= (1LL << 31)) {
     return fail(POVAR_ERR_UNSUPPORTED, "sliced-ELL layout exceeds 2^31 slots in one shard");
   }
@@ -564,6 +585,7 @@ void Engine::e0_product(bool joint, const double* y, bool in_series) {
     launch_e0_landmark_v2(d_, mp_, joint, in_series, lc());
     launch_passB_e0_v2(d_, mp_, joint, in_series, lc());
   }
+  if (in_series && world_ == 1) return;   // the term kernel adds the item partials itself
   launch_reduce_items(d_, d_.item_part, 12, d_.cam_raw, in_series, lc());
   allreduce(d_.cam_raw, static_cast<size_t>(C_) * 12);
 }
@@ -588,7 +610,7 @@ int Engine::solve_power(bool joint, double lambda) {
   launch_series_start(d_, opt_.r_tolerance, m, lc());
   for (int i = 1; i <= m; ++i) {
     e0_product(joint, d_.vec_y, true);
-    launch_series_term(d_, joint, i, opt_.eta, opt_.r_tolerance, lc());
+    launch_series_term(d_, joint, i, opt_.eta, opt_.r_tolerance, world_ == 1, lc());
   }
   PV_CUDA(cudaEventRecord(ev_[2], stream_));
   PV_CUDA(cudaGetLastError());
@@ -1057,7 +1079,7 @@ int Engine::bench_power_terms(bool joint, int terms, double* seconds_per_term) {
   PV_CUDA(cudaEventRecord(ev_[0], stream_));
   for (int i = 1; i <= terms; ++i) {
     e0_product(joint, d_.vec_y, true);
-    launch_series_term(d_, joint, i, /*eta=*/-1.0, /*r_tolerance=*/-1.0, lc());
+    launch_series_term(d_, joint, i, /*eta=*/-1.0, /*r_tolerance=*/-1.0, world_ == 1, lc());
   }
   PV_CUDA(cudaEventRecord(ev_[1], stream_));
   PV_CUDA(cudaGetLastError());
@@ -1089,7 +1111,7 @@ int Engine::bench_power_kernels(bool joint, int reps, double* seconds) {
           else launch_passB_e0_v2(d_, mp_, joint, true, lc());
           break;
         case 2: launch_reduce_items(d_, d_.item_part, 12, d_.cam_raw, true, lc()); break;
-        default: launch_series_term(d_, joint, i + 1, -1.0, -1.0, lc()); break;
+        default: launch_series_term(d_, joint, i + 1, -1.0, -1.0, world_ == 1, lc()); break;
       }
     }
     PV_CUDA(cudaEventRecord(ev_[1], stream_));

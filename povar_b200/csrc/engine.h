@@ -97,7 +97,8 @@ struct SellLayout {
   std::vector<int> long_lms;    // landmarks with more than 32 observations
   int rows = 0;
 };
-void build_sell(const std::vector<int>& lm_ptr, int window, SellLayout* out);
+void build_sell(const std::vector<int>& lm_ptr, const int* obs_cam, int num_cams, int window,
+                SellLayout* out);
 
 // host-side index construction (engine.cu), exposed for the CPU tests through the C ABI
 void build_tiles(const std::vector<int>& lm_ptr, std::vector<int>* tile_ptr);

@@ -450,6 +450,25 @@ __device__ __forceinline__ void raw_to_reduced(const double* __restrict__ raw,
 }
 
 // y (12) gathered by the passes:  s o x   or   s o (Pi x)
+// y values only (12): s o x  or  s o (Pi x)
+template <bool JOINT>
+__device__ __forceinline__ void reduced_to_y_values(const double* x, const double* __restrict__ s,
+                                                    const double* __restrict__ Pc, double (&yv)[12]) {
+  if (JOINT) {
+    double pv[12], full[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) pv[i] = Pc[i];
+    Reflector<12> pi;
+    pi.make(pv);
+    pi.apply(x, full);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) yv[i] = s[i] * full[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) yv[i] = s[i] * x[i];
+  }
+}
+
 // `rec` is the camera's record of the landmark-major E0 pass (CamRec<JOINT>): y is stored there too
 template <bool JOINT>
 __device__ __forceinline__ void reduced_to_y(const double* x, const double* __restrict__ s,
@@ -549,12 +568,120 @@ __device__ __forceinline__ void sum_norm_parts(int C, const double* __restrict__
                                                double* smem, double& s0, double& s1) {
   double acc[2] = {0.0, 0.0};
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    acc[0] += norm_part[2 * c];
-    acc[1] += norm_part[2 * c + 1];
+    acc[0] += __ldcg(norm_part + 2 * c);       // written by other blocks of the same launch (k_term16)
+    acc[1] += __ldcg(norm_part + 2 * c + 1);
   }
   block_reduce<2>(acc, smem);
   s0 = acc[0];
   s1 = acc[1];
+}
+
+// convergence test after term i (linearization_power_varproj.hpp:205-229), one thread
+__device__ __forceinline__ void series_decide(double s0, double s1, int term, double eta,
+                                              double r_tolerance, SeriesCtl* ctl) {
+  const double it_norm = sqrt(s0), acc_norm = sqrt(s1);
+  ctl->last_tmp_norm = it_norm;
+  ctl->last_acc_norm = acc_norm;
+  ctl->nonfinite = isfinite(s1) ? 0 : 1;
+  bool stop = false;
+  if (eta > 0) {
+    const double zeta = term * it_norm / acc_norm;
+    if (zeta < eta) stop = true;
+  }
+  if (!stop && r_tolerance > 0 && it_norm / ctl->norm0 < r_tolerance) stop = true;
+  if (stop) {
+    ctl->done = 1;
+    ctl->iterations = term;
+  }
+}
+
+// one power-series term, camera side, sixteen lanes per camera (lane i owns row i of B^-1 -- the
+// 144 loads of the block are the expensive part -- and everything else is recomputed per lane in the
+// order of k_term, so the two kernels give identical bits):
+//   [FUSED] raw = sum of the camera's item partials (k_reduce_items);  tmp = B^-1 reduced(raw);
+//   accum += tmp;  y = y(tmp);  per-camera norms;  then the LAST block to finish applies the
+//   convergence test of k_series_decide.  Block = 256 threads = 16 cameras.
+template <bool JOINT, bool FUSED>
+__global__ void __launch_bounds__(kBlock)
+k_term16(int C, const double* __restrict__ raw_in, const int* __restrict__ cam_item_ptr,
+         const double* __restrict__ item_part, const double* __restrict__ pose_scale,
+         const double* __restrict__ P, const double* __restrict__ Binv, double* __restrict__ tmp,
+         double* __restrict__ acc, double* __restrict__ y, double* __restrict__ cam_rec,
+         double* __restrict__ norm_part, int term, double eta, double r_tolerance, SeriesCtl* ctl) {
+  if (ctl->done) return;
+  constexpr int D = JOINT ? 11 : 12;
+  __shared__ double smem[2 * (kBlock / 32)];
+  __shared__ int is_last;
+  const int lane16 = threadIdx.x & 15;
+  const int base = (threadIdx.x & 31) & ~15;   // first lane of this half-warp
+  const int c_raw = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+  const bool live = c_raw < C;
+  const int c = live ? c_raw : C - 1;          // idle half-warps shadow the last camera (no stores)
+  double raw[12];
+  if (FUSED) {
+    double mine = 0.0;
+    if (lane16 < 12) {
+      const int ie = cam_item_ptr[c + 1];
+      for (int it = cam_item_ptr[c]; it < ie; ++it) mine += item_part[static_cast<size_t>(it) * 12 + lane16];
+    }
+#pragma unroll
+    for (int k = 0; k < 12; ++k) raw[k] = __shfl_sync(kFullMask, mine, base + k);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 12; ++k) raw[k] = raw_in[12 * static_cast<size_t>(c) + k];
+  }
+  const double* s = pose_scale + 12 * static_cast<size_t>(c);
+  const double* Pc = P + 12 * static_cast<size_t>(c);
+  double e[12];
+  raw_to_reduced<JOINT>(raw, s, Pc, e);
+  double ti = 0.0;
+  if (lane16 < D) {
+    const double* bi = Binv + 144 * static_cast<size_t>(c) + lane16 * D;
+    for (int j = 0; j < D; ++j) ti += bi[j] * e[j];
+  }
+  double t[12];
+  double nt = 0.0, na = 0.0;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) t[i] = __shfl_sync(kFullMask, ti, base + i);
+  for (int i = 0; i < D; ++i) {
+    nt += t[i] * t[i];
+    const double a = acc[static_cast<size_t>(c) * D + i] + t[i];
+    na += a * a;
+  }
+  __syncwarp();   // every lane has read accum before lane i overwrites entry i
+  if (live && lane16 < D) {
+    acc[static_cast<size_t>(c) * D + lane16] += ti;
+    tmp[static_cast<size_t>(c) * D + lane16] = ti;
+  }
+  double yv[12];
+  reduced_to_y_values<JOINT>(t, s, Pc, yv);
+  if (live && lane16 < 12) {
+    double mine = 0.0;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) mine = (i == lane16) ? yv[i] : mine;
+    y[12 * static_cast<size_t>(c) + lane16] = mine;
+    cam_rec[CamRec::kStride * static_cast<size_t>(c) + CamRec::y_index(lane16 >> 2, lane16 & 3)] = mine;
+  }
+  if (live && lane16 == 0) {
+    norm_part[2 * c] = nt;
+    norm_part[2 * c + 1] = na;
+  }
+  // last block to arrive applies the convergence test (linearization_power_varproj.hpp:205-229)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(&ctl->ticket, 1u);
+    is_last = (prev == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double s0, s1;
+  sum_norm_parts(C, norm_part, smem, s0, s1);
+  if (threadIdx.x == 0) {
+    ctl->ticket = 0;
+    series_decide(s0, s1, term, eta, r_tolerance, ctl);
+  }
 }
 
 __global__ void __launch_bounds__(kBlock)
@@ -581,22 +708,7 @@ k_series_decide(int C, const double* __restrict__ norm_part, int term, double et
   __shared__ double smem[2 * (kBlock / 32)];
   double s0, s1;
   sum_norm_parts(C, norm_part, smem, s0, s1);
-  if (threadIdx.x == 0) {
-    const double it_norm = sqrt(s0), acc_norm = sqrt(s1);
-    ctl->last_tmp_norm = it_norm;
-    ctl->last_acc_norm = acc_norm;
-    ctl->nonfinite = isfinite(s1) ? 0 : 1;
-    bool stop = false;
-    if (eta > 0) {
-      const double zeta = term * it_norm / acc_norm;
-      if (zeta < eta) stop = true;
-    }
-    if (!stop && r_tolerance > 0 && it_norm / ctl->norm0 < r_tolerance) stop = true;
-    if (stop) {
-      ctl->done = 1;
-      ctl->iterations = term;
-    }
-  }
+  if (threadIdx.x == 0) series_decide(s0, s1, term, eta, r_tolerance, ctl);
 }
 
 // out = reduced(raw)   (E0 x for callers outside the series: tests, PCG)
@@ -767,17 +879,22 @@ void launch_series_start(const DeviceState& d, double r_tolerance, int max_terms
 }
 
 void launch_series_term(const DeviceState& d, bool joint, int term, double eta, double r_tolerance,
-                        const LaunchCfg& lc) {
-  const int blocks = (d.ix.C + 127) / 128;
+                        bool fused_reduce, const LaunchCfg& lc) {
+  const int blocks = (d.ix.C + 15) / 16;
+#define POVAR_TERM(J, F)                                                                              \
+  k_term16<J, F><<<blocks, kBlock, 0, lc.stream>>>(d.ix.C, d.cam_raw, d.ix.cam_item_ptr, d.item_part,  \
+                                                   d.pose_scale, d.P, d.Binv, d.vec_tmp, d.vec_acc,    \
+                                                   d.vec_y, d.cam_rec, d.norm_part, term, eta,         \
+                                                   r_tolerance, d.ctl)
   if (joint) {
-    k_term<true><<<blocks, 128, 0, lc.stream>>>(d.ix.C, d.cam_raw, d.pose_scale, d.P, d.Binv, d.vec_tmp,
-                                                d.vec_acc, d.vec_y, d.cam_rec, d.norm_part, d.ctl);
+    if (fused_reduce) POVAR_TERM(true, true);
+    else POVAR_TERM(true, false);
   } else {
-    k_term<false><<<blocks, 128, 0, lc.stream>>>(d.ix.C, d.cam_raw, d.pose_scale, d.P, d.Binv, d.vec_tmp,
-                                                 d.vec_acc, d.vec_y, d.cam_rec, d.norm_part, d.ctl);
+    if (fused_reduce) POVAR_TERM(false, true);
+    else POVAR_TERM(false, false);
   }
-  k_series_decide<<<1, kBlock, 0, lc.stream>>>(d.ix.C, d.norm_part, term, eta, r_tolerance, d.ctl);
-  count(lc, 2);
+#undef POVAR_TERM
+  count(lc);
 }
 
 void launch_e0_finish(const DeviceState& d, bool joint, double* out, const LaunchCfg& lc) {

@@ -196,7 +196,13 @@ k_e0_landmark_sell(DeviceIndex ix, const double* __restrict__ X, const double* _
   if (ctl != nullptr && ctl->done) return;
   const int lane = threadIdx.x & 31;
   const int grp = lane >> 2, sub = lane & 3, gb = lane & ~3;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  // Blocks that share an SM should work on neighbouring slices (same stretch of the camera table in
+  // L1).  With a grid of 148 k blocks, all resident, blocks b, b + 148, ... land on the same SM.
+  const int per_sm = gridDim.x / 148;
+  const int chunk = (per_sm * 148 == static_cast<int>(gridDim.x))
+                        ? static_cast<int>(blockIdx.x % 148) * per_sm + static_cast<int>(blockIdx.x / 148)
+                        : static_cast<int>(blockIdx.x);
+  const int warp = chunk * kWarps + (threadIdx.x >> 5);
   const int s0 = warp * slices_per_warp;
   if (s0 >= ix.num_slices) return;
   const int s1 = min(s0 + slices_per_warp, ix.num_slices);
@@ -253,20 +259,25 @@ k_e0_landmark_sell(DeviceIndex ix, const double* __restrict__ X, const double* _
 
   st.lm = __ldg(ix.sell_lm + 8 * s0 + grp);
   st.row1 = __ldg(ix.slice_ptr + s0 + 1);
-  // ring of NR rows in flight; camera indices run NR rows further ahead
+  // ring of NR rows in flight; camera indices run kCamAhead rows ahead of the records
+  constexpr int kCamAhead = 4;
+  constexpr int kUnroll = NR * kCamAhead;   // both rings keep static indices
   RowData ring[NR];
-  int cam[NR];
+  int camq[kCamAhead];                      // camq[j]: camera index of row (next record row) + j
 #pragma unroll
   for (int i = 0; i < NR; ++i) {
     const int r = min(row_first + i, row_last);
     const int c = __ldcs(ix.sell_cam + 8 * static_cast<size_t>(r) + grp);
     load_row<JOINT, HASW>(ix, cam_rec, sell_d, sell_w, r, c, grp, sub, ring[i]);
-    cam[i] = __ldcs(ix.sell_cam + 8 * static_cast<size_t>(min(r + NR, row_last)) + grp);
+  }
+#pragma unroll
+  for (int j = 0; j < kCamAhead; ++j) {
+    camq[j] = __ldcs(ix.sell_cam + 8 * static_cast<size_t>(min(row_first + NR + j, row_last)) + grp);
   }
   open_slice();
-  for (int row = row_first; row < row_end; row += NR) {
-    // pull the observation stream ahead of the loads (one 128-byte line of uv per row)
-    if (lane < NR && stream_ahead > 0) {
+  for (int row = row_first; row < row_end; row += kUnroll) {
+    // pull the observation stream towards L2 ahead of the loads (one 128-byte line of uv per row)
+    if (stream_ahead > 0 && lane < kUnroll) {
       const int rp = row + stream_ahead + lane;
       if (rp <= row_last) {
         if (JOINT) {
@@ -275,22 +286,23 @@ k_e0_landmark_sell(DeviceIndex ix, const double* __restrict__ X, const double* _
         } else {
           prefetch_l2(ix.sell_uv + 8 * static_cast<size_t>(rp));
         }
-        if (lane == 0) prefetch_l2(ix.sell_cam + 8 * static_cast<size_t>(rp));
+        if ((lane & 3) == 0) prefetch_l2(ix.sell_cam + 8 * static_cast<size_t>(rp));
       }
     }
 #pragma unroll
-    for (int i = 0; i < NR; ++i) {
+    for (int i = 0; i < kUnroll; ++i) {
       const int r = row + i;
       if (r < row_end) {           // warp-uniform
         if (r == st.row1) {        // warp-uniform: the previous slice is complete
           close_slice();
           open_slice();
         }
-        landmark_obs<JOINT>(ring[i].L0, ring[i].L1, ring[i].L2, st.x, ring[i].k, c1, c2, sub, gb,
-                            ring[i].act, st.acc);
-        const int rn = min(r + NR, row_last);
-        load_row<JOINT, HASW>(ix, cam_rec, sell_d, sell_w, rn, cam[i], grp, sub, ring[i]);
-        cam[i] = __ldcs(ix.sell_cam + 8 * static_cast<size_t>(min(r + 2 * NR, row_last)) + grp);
+        RowData& cur = ring[i % NR];
+        landmark_obs<JOINT>(cur.L0, cur.L1, cur.L2, st.x, cur.k, c1, c2, sub, gb, cur.act, st.acc);
+        load_row<JOINT, HASW>(ix, cam_rec, sell_d, sell_w, min(r + NR, row_last), camq[i % kCamAhead],
+                              grp, sub, cur);
+        camq[i % kCamAhead] =
+            __ldcs(ix.sell_cam + 8 * static_cast<size_t>(min(r + NR + kCamAhead, row_last)) + grp);
       }
     }
   }
@@ -469,14 +481,14 @@ template <bool JOINT, bool HASW>
 void launch_landmark_half(const DeviceState& d, const ModelParams& mp, const SeriesCtl* ctl,
                           const LaunchCfg& lc) {
   if (d.ix.num_slices > 0) {
-    // contiguous slice ranges per warp, whole sorting windows (kSellWindow / 8 slices) so that every
-    // warp sees the same mix of degrees; about four rounds of 148 SMs x 24 resident warps
-    const int per_window = kSellWindow / 8;
-    const long long target = 148LL * 24 * 4;
-    long long per_warp = (d.ix.num_slices + target - 1) / target;
-    per_warp = (per_warp + per_window - 1) / per_window * per_window;
+    // one wave of persistent-style blocks: 148 SMs x 4 resident blocks x 8 warps, contiguous slice
+    // ranges per warp (small problems: one range of 16 slices per warp)
+    const long long full = 148LL * 4 * kWarps;
+    long long per_warp = (d.ix.num_slices + full - 1) / full;
+    if (per_warp < 16) per_warp = 16;
     const long long warps = (d.ix.num_slices + per_warp - 1) / per_warp;
-    const int blocks = static_cast<int>((warps + kWarps - 1) / kWarps);
+    int blocks = static_cast<int>((warps + kWarps - 1) / kWarps);
+    if (blocks > 148) blocks = (blocks + 147) / 148 * 148;   // whole multiples of 148: see the chunk map
     static const int nr = getenv("POVAR_SELL_NR") ? atoi(getenv("POVAR_SELL_NR")) : 1;
     static const int ahead = getenv("POVAR_SELL_AHEAD") ? atoi(getenv("POVAR_SELL_AHEAD")) : kStreamAhead;
 #define POVAR_SELL_LAUNCH(NRV)                                                                     \

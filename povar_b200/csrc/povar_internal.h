@@ -168,8 +168,10 @@ void launch_passB(const DeviceState& d, const ModelParams& mp, bool joint, PassB
                   bool in_series, const LaunchCfg& lc);
 // series bookkeeping
 void launch_series_start(const DeviceState& d, double r_tolerance, int max_terms, const LaunchCfg& lc);
+// fused_reduce: the term kernel adds the item partials of the camera half itself (single GPU);
+// otherwise it reads cam_raw (after launch_reduce_items and the all-reduce)
 void launch_series_term(const DeviceState& d, bool joint, int term, double eta, double r_tolerance,
-                        const LaunchCfg& lc);
+                        bool fused_reduce, const LaunchCfg& lc);
 void launch_finish_b(const DeviceState& d, bool joint, const LaunchCfg& lc);
 void launch_e0_finish(const DeviceState& d, bool joint, double* out, const LaunchCfg& lc);
 void launch_make_y(const DeviceState& d, bool joint, const double* x, double* y, const LaunchCfg& lc);
