@@ -308,7 +308,15 @@ def main():
     solver.close()
 
     # ---- end to end from host buffers: create (H2D) + solve + read back (D2H) + destroy
-    h2d = (hp.lm_ptr.nbytes + hp.obs_cam.nbytes * 3 + hp.obs_uv.nbytes * 2 + hp.cam_P.nbytes)
+    # inputs are page-locked once, outside the timed region (the contract: H2D from pinned host memory);
+    # every per-observation index array is built on the device from the canonical list, so the upload
+    # is that list plus the small host-built tables
+    pinned = []
+    rt = torch.cuda.cudart()
+    for arr in (hp.lm_ptr, hp.obs_cam, hp.obs_uv, hp.cam_P):
+        if int(rt.cudaHostRegister(arr.ctypes.data, arr.nbytes, 0)) == 0:
+            pinned.append(arr)
+    h2d = (hp.lm_ptr.nbytes // 2 + hp.obs_cam.nbytes + hp.obs_uv.nbytes + hp.cam_P.nbytes)
     d2h = hp.cam_P.nbytes + hp.num_lms * 4 * 8
 
     def e2e_step():
@@ -326,6 +334,8 @@ def main():
         e2e_trials += e2e_step()
     barrier()
     t_e2e = reduce_max(time.perf_counter() - t0)
+    for arr in pinned:
+        rt.cudaHostUnregister(arr.ctypes.data)
 
     if rank != 0:
         if world > 1:

@@ -28,6 +28,7 @@ LIB_SOURCES = [
     "kernels_camera.cu",
     "kernels_schur.cu",
     "kernels_series.cu",
+    "kernels_index.cu",
     "engine.cu",
     "capi.cpp",
     "host/bal_io.cpp",

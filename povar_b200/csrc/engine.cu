@@ -119,7 +119,6 @@ void build_sell(const std::vector<int>& lm_ptr, const int* obs_cam, int num_cams
   out->slice_ptr.assign(1, 0);
   out->sell_lm.clear();
   out->long_lms.clear();
-  out->obs_slot.assign(static_cast<size_t>(lm_ptr[L]), -1);
   // landmarks with 1..32 observations by median camera
   std::vector<int> by_cam;
   {
@@ -155,9 +154,6 @@ void build_sell(const std::vector<int>& lm_ptr, const int* obs_cam, int num_cams
       for (int g = 0; g < 8; ++g) {
         const int l = i + g < cnt ? order[i + g] : -1;
         out->sell_lm.push_back(l);
-        if (l < 0) continue;
-        const int b = lm_ptr[l], e = lm_ptr[l + 1];
-        for (int o = b; o < e; ++o) out->obs_slot[o] = 8 * (rows + (o - b)) + g;
       }
       rows += len;
       out->slice_ptr.push_back(rows);
@@ -218,13 +214,15 @@ double Engine::elapsed(cudaEvent_t a, cudaEvent_t b) {
   return ms * 1e-3;
 }
 
+// Stream-ordered allocation from the device's default memory pool, which is told to keep what it is
+// given back: creating a handle after another one was destroyed costs no cudaMalloc.
 template <typename T>
-static int dev_alloc(std::vector<void*>& allocs, T** p, size_t n) {
+static int dev_alloc(std::vector<void*>& allocs, cudaStream_t stream, T** p, size_t n) {
   void* q = nullptr;
   if (n == 0) n = 1;
-  const cudaError_t e = cudaMalloc(&q, n * sizeof(T));
+  const cudaError_t e = cudaMallocAsync(&q, n * sizeof(T), stream);
   if (e != cudaSuccess) return POVAR_ERR_CUDA;
-  cudaMemset(q, 0, n * sizeof(T));
+  cudaMemsetAsync(q, 0, n * sizeof(T), stream);
   allocs.push_back(q);
   *p = static_cast<T*>(q);
   return POVAR_OK;
@@ -232,7 +230,7 @@ static int dev_alloc(std::vector<void*>& allocs, T** p, size_t n) {
 
 #define PV_ALLOC(ptr, n)                                                        \
   do {                                                                          \
-    if (dev_alloc(allocs_, &(ptr), static_cast<size_t>(n)) != POVAR_OK)         \
+    if (dev_alloc(allocs_, stream_, &(ptr), static_cast<size_t>(n)) != POVAR_OK) \
       return fail(POVAR_ERR_CUDA, std::string("cudaMalloc failed for ") + #ptr); \
   } while (0)
 
@@ -269,6 +267,13 @@ int Engine::create(const povar_problem_desc* desc, const povar_options* opt,
     return POVAR_ERR_INVALID;
   }
   int rc = e->check(cudaSetDevice(e->device_), "cudaSetDevice");
+  if (rc == POVAR_OK) {
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, e->device_) == cudaSuccess) {
+      unsigned long long keep = ~0ULL;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   if (rc == POVAR_OK) rc = e->check(cudaStreamCreateWithFlags(&e->stream_, cudaStreamNonBlocking), "cudaStreamCreate");
   for (int i = 0; i < 4 && rc == POVAR_OK; ++i) rc = e->check(cudaEventCreate(&e->ev_[i]), "cudaEventCreate");
   if (rc == POVAR_OK && e->world_ > 1) {
@@ -298,7 +303,8 @@ Engine::~Engine() {
   if (stream_) cudaStreamSynchronize(stream_);
   if (nccl_comm_ && nccl_) nccl_->CommDestroy(nccl_comm_);
   if (cusolver_) destroy_cusolver(cusolver_);
-  for (void* p : allocs_) cudaFree(p);
+  for (void* p : allocs_) cudaFreeAsync(p, stream_);
+  if (stream_) cudaStreamSynchronize(stream_);
   for (auto& ev : ev_) {
     if (ev) cudaEventDestroy(ev);
   }
@@ -311,8 +317,9 @@ int Engine::upload(const povar_problem_desc* desc) {
   C_ = C;
   L_ = L;
   nnz_ = nnz;
-  // ---- validate + landmark-major arrays
-  std::vector<int> lm_ptr(L + 1), obs_lm(nnz);
+  // ---- host: validation, per-camera counts and the small tables (one pass over the observations);
+  // everything per observation is built on the device (kernels_index.cu)
+  std::vector<int> lm_ptr(L + 1), cam_ptr(C + 1, 0);
   if (desc->lm_ptr[0] != 0 || desc->lm_ptr[L] != nnz) return fail(POVAR_ERR_INVALID, "lm_ptr does not span the observations");
   for (int l = 0; l < L; ++l) {
     const int64_t b = desc->lm_ptr[l], e = desc->lm_ptr[l + 1];
@@ -322,26 +329,14 @@ int Engine::upload(const povar_problem_desc* desc) {
       const int c = desc->obs_cam[o];
       if (c < 0 || c >= C) return fail(POVAR_ERR_INVALID, "camera index out of range");
       if (o > b && desc->obs_cam[o - 1] >= c) return fail(POVAR_ERR_INVALID, "observations of a landmark must have strictly ascending camera indices");
-      obs_lm[o] = l;
+      cam_ptr[c + 1]++;
     }
   }
   lm_ptr[L] = nnz;
-  // ---- camera-major copy (stable counting sort => landmarks ascending inside a camera)
-  std::vector<int> cam_ptr(C + 1, 0);
-  for (int o = 0; o < nnz; ++o) cam_ptr[desc->obs_cam[o] + 1]++;
   for (int c = 0; c < C; ++c) cam_ptr[c + 1] += cam_ptr[c];
-  std::vector<int> fill(cam_ptr.begin(), cam_ptr.end() - 1), csc_lm(nnz);
-  std::vector<double> csc_uv(2 * static_cast<size_t>(nnz));
-  for (int o = 0; o < nnz; ++o) {
-    const int pos = fill[desc->obs_cam[o]]++;
-    csc_lm[pos] = obs_lm[o];
-    csc_uv[2 * static_cast<size_t>(pos)] = desc->obs_uv[2 * static_cast<size_t>(o)];
-    csc_uv[2 * static_cast<size_t>(pos) + 1] = desc->obs_uv[2 * static_cast<size_t>(o) + 1];
-  }
   std::vector<int> tile_ptr, item_ptr, item_cam, cam_item_ptr;
   build_tiles(lm_ptr, &tile_ptr);
   build_items(cam_ptr, choose_item_len(nnz), &item_ptr, &item_cam, &cam_item_ptr);
-
   SellLayout sell;
   build_sell(lm_ptr, desc->obs_cam, C, kSellWindow, &sell);
   if (static_cast<long long>(sell.rows) * 8 >= (1LL << 31)) {
@@ -354,6 +349,10 @@ int Engine::upload(const povar_problem_desc* desc) {
   ix.nnz = nnz;
   ix.num_tiles = static_cast<int>(tile_ptr.size()) - 1;
   ix.num_items = static_cast<int>(item_cam.size());
+  ix.num_slices = static_cast<int>(sell.slice_ptr.size()) - 1;
+  ix.sell_slots = 8LL * sell.rows;
+  ix.num_long = static_cast<int>(sell.long_lms.size());
+  const size_t slots = static_cast<size_t>(ix.sell_slots);
   PV_ALLOC(ix.lm_ptr, L + 1);
   PV_ALLOC(ix.obs_cam, nnz);
   PV_ALLOC(ix.obs_lm, nnz);
@@ -365,51 +364,43 @@ int Engine::upload(const povar_problem_desc* desc) {
   PV_ALLOC(ix.item_cam, item_cam.size());
   PV_ALLOC(ix.item_ptr, item_ptr.size());
   PV_ALLOC(ix.cam_item_ptr, C + 1);
-#define PV_UP(dst, src, n) PV_CUDA(cudaMemcpy((dst), (src), (n), cudaMemcpyHostToDevice))
+  PV_ALLOC(ix.slice_ptr, sell.slice_ptr.size());
+  PV_ALLOC(ix.sell_lm, sell.sell_lm.size());
+  PV_ALLOC(ix.sell_cam, slots);
+  PV_ALLOC(ix.sell_uv, slots);
+  PV_ALLOC(ix.obs_slot, nnz);
+  PV_ALLOC(ix.long_lm, sell.long_lms.size());
+#define PV_UP(dst, src, n) PV_CUDA(cudaMemcpyAsync((dst), (src), (n), cudaMemcpyHostToDevice, stream_))
   PV_UP(ix.lm_ptr, lm_ptr.data(), sizeof(int) * (L + 1));
   if (nnz > 0) {
     PV_UP(ix.obs_cam, desc->obs_cam, sizeof(int) * static_cast<size_t>(nnz));
-    PV_UP(ix.obs_lm, obs_lm.data(), sizeof(int) * static_cast<size_t>(nnz));
     PV_UP(ix.obs_uv, desc->obs_uv, sizeof(double) * 2 * static_cast<size_t>(nnz));
-    PV_UP(ix.csc_lm, csc_lm.data(), sizeof(int) * static_cast<size_t>(nnz));
-    PV_UP(ix.csc_uv, csc_uv.data(), sizeof(double) * 2 * static_cast<size_t>(nnz));
     PV_UP(ix.item_cam, item_cam.data(), sizeof(int) * item_cam.size());
   }
   PV_UP(ix.tile_ptr, tile_ptr.data(), sizeof(int) * tile_ptr.size());
-  {
-    // sliced-ELL copy of the observation stream for the landmark half of E0
-    ix.num_slices = static_cast<int>(sell.slice_ptr.size()) - 1;
-    ix.sell_slots = 8LL * sell.rows;
-    const size_t slots = static_cast<size_t>(ix.sell_slots);
-    std::vector<int> sell_cam(slots, -1);
-    std::vector<double> sell_uv(2 * slots, 0.0);
-    for (int o = 0; o < nnz; ++o) {
-      const int slot = sell.obs_slot[o];
-      if (slot < 0) continue;
-      sell_cam[slot] = desc->obs_cam[o];
-      sell_uv[2 * static_cast<size_t>(slot)] = desc->obs_uv[2 * static_cast<size_t>(o)];
-      sell_uv[2 * static_cast<size_t>(slot) + 1] = desc->obs_uv[2 * static_cast<size_t>(o) + 1];
-    }
-    ix.num_long = static_cast<int>(sell.long_lms.size());
-    PV_ALLOC(ix.slice_ptr, sell.slice_ptr.size());
-    PV_ALLOC(ix.sell_lm, sell.sell_lm.size());
-    PV_ALLOC(ix.sell_cam, slots);
-    PV_ALLOC(ix.sell_uv, slots);
-    PV_ALLOC(ix.obs_slot, nnz);
-    PV_ALLOC(ix.long_lm, sell.long_lms.size());
-    PV_UP(ix.slice_ptr, sell.slice_ptr.data(), sizeof(int) * sell.slice_ptr.size());
-    if (!sell.sell_lm.empty()) PV_UP(ix.sell_lm, sell.sell_lm.data(), sizeof(int) * sell.sell_lm.size());
-    if (slots > 0) {
-      PV_UP(ix.sell_cam, sell_cam.data(), sizeof(int) * slots);
-      PV_UP(ix.sell_uv, sell_uv.data(), sizeof(double) * 2 * slots);
-    }
-    if (nnz > 0) PV_UP(ix.obs_slot, sell.obs_slot.data(), sizeof(int) * static_cast<size_t>(nnz));
-    if (ix.num_long > 0) PV_UP(ix.long_lm, sell.long_lms.data(), sizeof(int) * sell.long_lms.size());
-  }
+  PV_UP(ix.slice_ptr, sell.slice_ptr.data(), sizeof(int) * sell.slice_ptr.size());
+  if (!sell.sell_lm.empty()) PV_UP(ix.sell_lm, sell.sell_lm.data(), sizeof(int) * sell.sell_lm.size());
+  if (ix.num_long > 0) PV_UP(ix.long_lm, sell.long_lms.data(), sizeof(int) * sell.long_lms.size());
   PV_UP(ix.cam_ptr, cam_ptr.data(), sizeof(int) * (C + 1));
   PV_UP(ix.item_ptr, item_ptr.data(), sizeof(int) * item_ptr.size());
   PV_UP(ix.cam_item_ptr, cam_item_ptr.data(), sizeof(int) * (C + 1));
-
+  {
+    // scratch of the device-side build, returned to the pool right after
+    int *iota = nullptr, *keys_out = nullptr, *perm = nullptr, *lm_slot = nullptr;
+    char* sort_temp = nullptr;
+    const size_t temp_bytes = index_sort_temp_bytes(nnz, C);
+    const size_t keep = allocs_.size();
+    PV_ALLOC(iota, nnz);
+    PV_ALLOC(keys_out, nnz);
+    PV_ALLOC(perm, nnz);
+    PV_ALLOC(lm_slot, L);
+    PV_ALLOC(sort_temp, temp_bytes);
+    PV_CUDA(build_device_index(ix, iota, keys_out, perm, lm_slot, sort_temp, temp_bytes, lc()));
+    while (allocs_.size() > keep) {
+      cudaFreeAsync(allocs_.back(), stream_);
+      allocs_.pop_back();
+    }
+  }
   // ---- state and work arrays
   const size_t C12 = static_cast<size_t>(C) * 12, C144 = static_cast<size_t>(C) * 144;
   PV_ALLOC(d_.P, C12);
@@ -452,6 +443,8 @@ int Engine::upload(const povar_problem_desc* desc) {
   PV_ALLOC(d_.ctl, 1);
   PV_UP(d_.P, desc->cam_P, sizeof(double) * C12);
 #undef PV_UP
+  // the host tables above live on this stack frame
+  PV_CUDA(cudaStreamSynchronize(stream_));
   return POVAR_OK;
 }
 

@@ -1,0 +1,121 @@
+// Device-side construction of the per-observation index arrays from the canonical landmark-major
+// list (lm_ptr, obs_cam, obs_uv):  obs_lm, the camera-major copy (csc_lm, csc_uv) and the sliced-ELL
+// copy (sell_cam, sell_uv, obs_slot).  The host only derives the small tables (tiles, items, slice
+// table) -- scattering 5 M observations into three orders is a few hundred milliseconds of cache
+// misses on one host core and well under a millisecond here.
+//
+// Canonical order = the reference's: landmark index, then camera index ascending
+// (/root/reference/src/rootba_povar/bal/bal_problem.hpp:226); the camera-major order is the STABLE
+// sort of it by camera (landmarks ascending inside a camera), made with a stable LSD radix sort.
+#include <cuda_runtime.h>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "povar_internal.h"
+
+namespace povar {
+
+namespace {
+
+constexpr int kBlock = 256;
+
+__global__ void __launch_bounds__(kBlock)
+k_obs_lm(int L, const int* __restrict__ lm_ptr, int* __restrict__ obs_lm) {
+  // one warp per 32 landmarks would do; degrees are small, a thread per landmark is enough
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= L) return;
+  const int e = lm_ptr[l + 1];
+  for (int o = lm_ptr[l]; o < e; ++o) obs_lm[o] = l;
+}
+
+__global__ void __launch_bounds__(kBlock) k_iota(int n, int* __restrict__ v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = i;
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_csc_gather(int nnz, const int* __restrict__ perm, const int* __restrict__ obs_lm,
+             const double2* __restrict__ obs_uv, int* __restrict__ csc_lm, double2* __restrict__ csc_uv) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nnz) return;
+  const int o = perm[e];
+  csc_lm[e] = obs_lm[o];
+  csc_uv[e] = obs_uv[o];
+}
+
+// first slot of every landmark in the sliced-ELL order (-1: not in the set)
+__global__ void __launch_bounds__(kBlock)
+k_lm_slot(int groups, const int* __restrict__ slice_ptr, const int* __restrict__ sell_lm,
+          int* __restrict__ lm_slot) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= groups) return;
+  const int lm = sell_lm[i];
+  if (lm >= 0) lm_slot[lm] = 8 * slice_ptr[i >> 3] + (i & 7);
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_sell_fill(int nnz, const int* __restrict__ lm_ptr, const int* __restrict__ obs_lm,
+            const int* __restrict__ obs_cam, const double2* __restrict__ obs_uv,
+            const int* __restrict__ lm_slot, int* __restrict__ sell_cam, double2* __restrict__ sell_uv,
+            int* __restrict__ obs_slot) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= nnz) return;
+  const int l = obs_lm[o];
+  const int base = lm_slot[l];
+  int slot = -1;
+  if (base >= 0) {
+    slot = base + 8 * (o - lm_ptr[l]);
+    sell_cam[slot] = obs_cam[o];
+    sell_uv[slot] = obs_uv[o];
+  }
+  obs_slot[o] = slot;
+}
+
+}  // namespace
+
+size_t index_sort_temp_bytes(int nnz, int num_cams) {
+  size_t bytes = 0;
+  int bits = 1;
+  while ((1 << bits) < num_cams) ++bits;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, static_cast<const int*>(nullptr), static_cast<int*>(nullptr),
+                                  static_cast<const int*>(nullptr), static_cast<int*>(nullptr), nnz, 0, bits);
+  return bytes;
+}
+
+// scratch: iota [nnz], keys_out [nnz], perm [nnz], lm_slot [L], cub temp
+cudaError_t build_device_index(const DeviceIndex& ix, int* iota, int* keys_out, int* perm, int* lm_slot,
+                               void* sort_temp, size_t sort_temp_bytes, const LaunchCfg& lc) {
+  const int nnz = ix.nnz, L = ix.L;
+  cudaStream_t st = lc.stream;
+  int launches = 0;
+  if (L > 0) {
+    k_obs_lm<<<(L + kBlock - 1) / kBlock, kBlock, 0, st>>>(L, ix.lm_ptr, ix.obs_lm);
+    ++launches;
+  }
+  if (nnz > 0) {
+    const int blocks = (nnz + kBlock - 1) / kBlock;
+    k_iota<<<blocks, kBlock, 0, st>>>(nnz, iota);
+    int bits = 1;
+    while ((1 << bits) < ix.C) ++bits;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(sort_temp, sort_temp_bytes, ix.obs_cam, keys_out, iota,
+                                                    perm, nnz, 0, bits, st);
+    if (e != cudaSuccess) return e;
+    k_csc_gather<<<blocks, kBlock, 0, st>>>(nnz, perm, ix.obs_lm, ix.obs_uv, ix.csc_lm, ix.csc_uv);
+    e = cudaMemsetAsync(lm_slot, 0xFF, sizeof(int) * static_cast<size_t>(L), st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(ix.sell_cam, 0xFF, sizeof(int) * static_cast<size_t>(ix.sell_slots), st);
+    if (e != cudaSuccess) return e;
+    const int groups = 8 * ix.num_slices;
+    if (groups > 0) {
+      k_lm_slot<<<(groups + kBlock - 1) / kBlock, kBlock, 0, st>>>(groups, ix.slice_ptr, ix.sell_lm, lm_slot);
+      ++launches;
+    }
+    k_sell_fill<<<blocks, kBlock, 0, st>>>(nnz, ix.lm_ptr, ix.obs_lm, ix.obs_cam, ix.obs_uv, lm_slot,
+                                           ix.sell_cam, ix.sell_uv, ix.obs_slot);
+    launches += 5;   // iota, radix sort (counted once), gather, fill
+  }
+  if (lc.launch_counter) *lc.launch_counter += launches;
+  return cudaGetLastError();
+}
+
+}  // namespace povar

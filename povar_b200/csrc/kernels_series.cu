@@ -175,6 +175,56 @@ __device__ __forceinline__ void load_row(const DeviceIndex& ix, const double* __
   }
 }
 
+// landmarks with more than 32 observations (outside the sliced-ELL set): one warp per landmark (the
+// first blocks of the grid of k_e0_landmark_sell, so that they overlap with the slices),
+// group g takes observations g, g + 8, ... of the CSR list, fixed-tree sum over the groups
+template <bool JOINT, bool HASW>
+__device__ __forceinline__ void long_landmark_warp(const DeviceIndex& ix, int warp,
+                                                   const double* __restrict__ X,
+                                                   const double* __restrict__ cam_rec,
+                                                   const double* __restrict__ obs_d,
+                                                   const double* __restrict__ obs_w, double c1, double c2,
+                                                   const double* __restrict__ lm_fold,
+                                                   double* __restrict__ lm_rec) {
+  const int lane = threadIdx.x & 31;
+  const int grp = lane >> 2, sub = lane & 3, gb = lane & ~3;
+  if (warp >= ix.num_long) return;
+  const int lm = __ldg(ix.long_lm + warp);
+  const int ob = __ldg(ix.lm_ptr + lm), oe = __ldg(ix.lm_ptr + lm + 1);
+  double x[4];
+  load4(X + 4 * static_cast<size_t>(lm), x);
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int base = ob; base < oe; base += 8) {
+    const bool act = base + grp < oe;
+    const int o = act ? base + grp : ob;
+    const int c = __ldg(ix.obs_cam + o);
+    const double* r = cam_rec + CamRec::kStride * static_cast<size_t>(c) + 2 * sub;
+    const double2 A0 = ldg2(r), A1 = ldg2(r + 8), A2 = ldg2(r + 16);
+    ObsCoef k;
+    if (JOINT) {
+      const double* dp = obs_d + 3 * static_cast<size_t>(o);
+      k.a = __ldg(dp);
+      k.b = __ldg(dp + 1);
+      k.c = __ldg(dp + 2);
+    } else {
+      const double2 uv = ix.obs_uv[o];
+      k.a = uv.x;
+      k.b = uv.y;
+      k.c = HASW ? __ldg(obs_w + o) : 1.0;
+    }
+    landmark_obs<JOINT>(A0, A1, A2, x, k, c1, c2, sub, gb, act, acc);
+  }
+#pragma unroll
+  for (int off = 4; off < 32; off <<= 1) {
+#pragma unroll
+    for (int n = 0; n < 4; ++n) acc[n] += __shfl_xor_sync(kFullMask, acc[n], off);
+  }
+  double G[4];
+  group_totals<JOINT>(acc, gb, G);
+  const double H = fold_row<JOINT>(lm_fold + 10 * static_cast<size_t>(lm), sub, G);
+  if (grp == 0) lm_rec[kLmRec * static_cast<size_t>(lm) + 4 + sub] = H;
+}
+
 constexpr int kStreamAhead = 24;   // rows
 
 // per-warp state of the slice being accumulated
@@ -188,20 +238,25 @@ struct SliceState {
 };
 
 template <bool JOINT, bool HASW, int NR>
-__global__ void __launch_bounds__(kBlock, NR == 1 ? 4 : (NR == 2 ? 3 : 2))
+__global__ void __launch_bounds__(kBlock, NR == 1 ? 4 : 3)
 k_e0_landmark_sell(DeviceIndex ix, const double* __restrict__ X, const double* __restrict__ cam_rec,
                    const double* __restrict__ sell_d, const double* __restrict__ sell_w, double c1,
                    double c2, const double* __restrict__ lm_fold, double* __restrict__ lm_rec,
-                   const SeriesCtl* __restrict__ ctl, int slices_per_warp, int stream_ahead) {
+                   const double* __restrict__ obs_d, const double* __restrict__ obs_w,
+                   const SeriesCtl* __restrict__ ctl, int slices_per_warp, int stream_ahead, int long_blocks) {
   if (ctl != nullptr && ctl->done) return;
+  if (static_cast<int>(blockIdx.x) < long_blocks) {
+    long_landmark_warp<JOINT, HASW>(ix, blockIdx.x * kWarps + (threadIdx.x >> 5), X, cam_rec, obs_d, obs_w,
+                                    c1, c2, lm_fold, lm_rec);
+    return;
+  }
   const int lane = threadIdx.x & 31;
   const int grp = lane >> 2, sub = lane & 3, gb = lane & ~3;
   // Blocks that share an SM should work on neighbouring slices (same stretch of the camera table in
   // L1).  With a grid of 148 k blocks, all resident, blocks b, b + 148, ... land on the same SM.
-  const int per_sm = gridDim.x / 148;
-  const int chunk = (per_sm * 148 == static_cast<int>(gridDim.x))
-                        ? static_cast<int>(blockIdx.x % 148) * per_sm + static_cast<int>(blockIdx.x / 148)
-                        : static_cast<int>(blockIdx.x);
+  const int bid = static_cast<int>(blockIdx.x) - long_blocks, nblk = static_cast<int>(gridDim.x) - long_blocks;
+  const int per_sm = nblk / 148;
+  const int chunk = (per_sm * 148 == nblk) ? (bid % 148) * per_sm + bid / 148 : bid;
   const int warp = chunk * kWarps + (threadIdx.x >> 5);
   const int s0 = warp * slices_per_warp;
   if (s0 >= ix.num_slices) return;
@@ -307,55 +362,6 @@ k_e0_landmark_sell(DeviceIndex ix, const double* __restrict__ X, const double* _
     }
   }
   close_slice();
-}
-
-// landmarks with more than 32 observations (outside the sliced-ELL set): one warp per landmark,
-// group g takes observations g, g + 8, ... of the CSR list, fixed-tree sum over the groups
-template <bool JOINT, bool HASW>
-__global__ void __launch_bounds__(kBlock)
-k_e0_landmark_long(DeviceIndex ix, const double* __restrict__ X, const double* __restrict__ cam_rec,
-                   const double* __restrict__ obs_d, const double* __restrict__ obs_w, double c1,
-                   double c2, const double* __restrict__ lm_fold, double* __restrict__ lm_rec,
-                   const SeriesCtl* __restrict__ ctl) {
-  if (ctl != nullptr && ctl->done) return;
-  const int lane = threadIdx.x & 31;
-  const int grp = lane >> 2, sub = lane & 3, gb = lane & ~3;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (warp >= ix.num_long) return;
-  const int lm = __ldg(ix.long_lm + warp);
-  const int ob = __ldg(ix.lm_ptr + lm), oe = __ldg(ix.lm_ptr + lm + 1);
-  double x[4];
-  load4(X + 4 * static_cast<size_t>(lm), x);
-  double acc[4] = {0.0, 0.0, 0.0, 0.0};
-  for (int base = ob; base < oe; base += 8) {
-    const bool act = base + grp < oe;
-    const int o = act ? base + grp : ob;
-    const int c = __ldg(ix.obs_cam + o);
-    const double* r = cam_rec + CamRec::kStride * static_cast<size_t>(c) + 2 * sub;
-    const double2 A0 = ldg2(r), A1 = ldg2(r + 8), A2 = ldg2(r + 16);
-    ObsCoef k;
-    if (JOINT) {
-      const double* dp = obs_d + 3 * static_cast<size_t>(o);
-      k.a = __ldg(dp);
-      k.b = __ldg(dp + 1);
-      k.c = __ldg(dp + 2);
-    } else {
-      const double2 uv = ix.obs_uv[o];
-      k.a = uv.x;
-      k.b = uv.y;
-      k.c = HASW ? __ldg(obs_w + o) : 1.0;
-    }
-    landmark_obs<JOINT>(A0, A1, A2, x, k, c1, c2, sub, gb, act, acc);
-  }
-#pragma unroll
-  for (int off = 4; off < 32; off <<= 1) {
-#pragma unroll
-    for (int n = 0; n < 4; ++n) acc[n] += __shfl_xor_sync(kFullMask, acc[n], off);
-  }
-  double G[4];
-  group_totals<JOINT>(acc, gb, G);
-  const double H = fold_row<JOINT>(lm_fold + 10 * static_cast<size_t>(lm), sub, G);
-  if (grp == 0) lm_rec[kLmRec * static_cast<size_t>(lm) + 4 + sub] = H;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -480,40 +486,33 @@ k_cam_rec_static(int C, const double* __restrict__ P, double* __restrict__ cam_r
 template <bool JOINT, bool HASW>
 void launch_landmark_half(const DeviceState& d, const ModelParams& mp, const SeriesCtl* ctl,
                           const LaunchCfg& lc) {
-  if (d.ix.num_slices > 0) {
-    // one wave of persistent-style blocks: 148 SMs x 4 resident blocks x 8 warps, contiguous slice
-    // ranges per warp (small problems: one range of 16 slices per warp)
-    const long long full = 148LL * 4 * kWarps;
-    long long per_warp = (d.ix.num_slices + full - 1) / full;
-    if (per_warp < 16) per_warp = 16;
-    const long long warps = (d.ix.num_slices + per_warp - 1) / per_warp;
-    int blocks = static_cast<int>((warps + kWarps - 1) / kWarps);
-    if (blocks > 148) blocks = (blocks + 147) / 148 * 148;   // whole multiples of 148: see the chunk map
-    static const int nr = getenv("POVAR_SELL_NR") ? atoi(getenv("POVAR_SELL_NR")) : 1;
-    static const int ahead = getenv("POVAR_SELL_AHEAD") ? atoi(getenv("POVAR_SELL_AHEAD")) : kStreamAhead;
+  if (d.ix.num_slices == 0 && d.ix.num_long == 0) return;
+  // one wave of persistent-style blocks for the slices: 148 SMs x 4 resident blocks x 8 warps,
+  // contiguous slice ranges per warp (small problems: one range of 16 slices per warp); in front of
+  // them one warp per long landmark
+  const long long full = 148LL * 4 * kWarps;
+  long long per_warp = (d.ix.num_slices + full - 1) / full;
+  if (per_warp < 16) per_warp = 16;
+  const long long warps = (d.ix.num_slices + per_warp - 1) / per_warp;
+  int blocks = static_cast<int>((warps + kWarps - 1) / kWarps);
+  if (blocks > 148) blocks = (blocks + 147) / 148 * 148;   // whole multiples of 148: see the chunk map
+  const int long_blocks = (d.ix.num_long + kWarps - 1) / kWarps;
+  static const int nr = getenv("POVAR_SELL_NR") ? atoi(getenv("POVAR_SELL_NR")) : 1;
+  static const int ahead = getenv("POVAR_SELL_AHEAD") ? atoi(getenv("POVAR_SELL_AHEAD")) : kStreamAhead;
 #define POVAR_SELL_LAUNCH(NRV)                                                                     \
   {                                                                                                \
-  static const cudaError_t carve_##NRV = cudaFuncSetAttribute(                                     \
-      k_e0_landmark_sell<JOINT, HASW, NRV>, cudaFuncAttributePreferredSharedMemoryCarveout,        \
-      cudaSharedmemCarveoutMaxL1);   /* no shared memory: all of it to L1 (the camera table) */    \
-  (void)carve_##NRV;                                                                               \
-  k_e0_landmark_sell<JOINT, HASW, NRV><<<blocks, kBlock, 0, lc.stream>>>(                          \
-      d.ix, d.X, d.cam_rec, d.sell_d, d.sell_w, mp.c1, mp.c2, d.lm_fold, d.lm_rec, ctl,            \
-      static_cast<int>(per_warp), ahead);                                                          \
+    static const cudaError_t carve_##NRV = cudaFuncSetAttribute(                                   \
+        k_e0_landmark_sell<JOINT, HASW, NRV>, cudaFuncAttributePreferredSharedMemoryCarveout,      \
+        cudaSharedmemCarveoutMaxL1); /* no shared memory: all of it to L1 (the camera table) */    \
+    (void)carve_##NRV;                                                                             \
+    k_e0_landmark_sell<JOINT, HASW, NRV><<<blocks + long_blocks, kBlock, 0, lc.stream>>>(          \
+        d.ix, d.X, d.cam_rec, d.sell_d, d.sell_w, mp.c1, mp.c2, d.lm_fold, d.lm_rec, d.obs_d,      \
+        d.obs_w, ctl, static_cast<int>(per_warp), ahead, long_blocks);                             \
   }
-    if (nr == 1) POVAR_SELL_LAUNCH(1)
-    else if (nr == 3) POVAR_SELL_LAUNCH(3)
-    else if (nr == 4) POVAR_SELL_LAUNCH(4)
-    else POVAR_SELL_LAUNCH(2)
+  if (nr == 2) POVAR_SELL_LAUNCH(2)
+  else POVAR_SELL_LAUNCH(1)
 #undef POVAR_SELL_LAUNCH
-    count(lc);
-  }
-  if (d.ix.num_long > 0) {
-    const int blocks = (d.ix.num_long + kWarps - 1) / kWarps;
-    k_e0_landmark_long<JOINT, HASW><<<blocks, kBlock, 0, lc.stream>>>(
-        d.ix, d.X, d.cam_rec, d.obs_d, d.obs_w, mp.c1, mp.c2, d.lm_fold, d.lm_rec, ctl);
-    count(lc);
-  }
+  count(lc);
 }
 
 }  // namespace

@@ -135,6 +135,11 @@ struct ModelParams {
   double jacobi_eps;
 };
 
+// ---- device-side index construction (kernels_index.cu) ----
+size_t index_sort_temp_bytes(int nnz, int num_cams);
+cudaError_t build_device_index(const DeviceIndex& ix, int* iota, int* keys_out, int* perm, int* lm_slot,
+                               void* sort_temp, size_t sort_temp_bytes, const LaunchCfg& lc);
+
 // ---- landmark-major kernels (kernels_landmark.cu) ----
 void launch_init_varproj(const DeviceState& d, const ModelParams& mp, const LaunchCfg& lc);
 void launch_cost(const DeviceState& d, const ModelParams& mp, bool joint, const LaunchCfg& lc);
