@@ -250,8 +250,13 @@ def main():
     if sampler:
         sampler.start()
     launches0 = solver.launch_count()
+    # device clock: CUDA events on the stream the handle launches on (torch's current stream sees
+    # none of it); the host LM loop between the launches is inside the bracket, as it must be
+    hstream = torch.cuda.ExternalStream(solver.cuda_stream(), device=torch.device("cuda", local_rank))
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t0 = time.perf_counter()
+    ev0.record(hstream)
     trials = 0
     terms = 0
     series_t = 0.0
@@ -260,8 +265,10 @@ def main():
         trials += len(its)
         terms += summ.power_terms
         series_t += summ.power_series_time
+    ev1.record(hstream)
     barrier()
-    t_res = reduce_max(time.perf_counter() - t0)
+    t_res_host = time.perf_counter() - t0
+    t_res = reduce_max(ev0.elapsed_time(ev1) * 1e-3)
     launches = solver.launch_count() - launches0
     clocks = sampler.stop() if sampler else None
     final_cost = its[-1].cost
@@ -327,13 +334,19 @@ def main():
         return len(its_)
 
     e2e_step()
+    # every step makes (and destroys) its own handle and stream and ends with a blocking read-back, so
+    # the bracket is two events on torch's stream: device timestamps taken while nothing is in flight
+    ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t0 = time.perf_counter()
+    ee0.record()
     e2e_trials = 0
     for _ in range(args.steps):
         e2e_trials += e2e_step()
+    ee1.record()
     barrier()
-    t_e2e = reduce_max(time.perf_counter() - t0)
+    t_e2e_host = time.perf_counter() - t0
+    t_e2e = reduce_max(ee0.elapsed_time(ee1) * 1e-3)
     for arr in pinned:
         rt.cudaHostUnregister(arr.ctypes.data)
 
@@ -371,6 +384,9 @@ def main():
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "timing": "CUDA events on the handle's stream (value) / on torch's stream around blocking calls (e2e), "
+                  "max over ranks; host perf_counter beside them",
+        "host_clock_s": {"resident": t_res_host, "e2e": t_e2e_host},
         "setup_s": {"generate": t_gen},
     }
     print(json.dumps(line))

@@ -135,6 +135,7 @@ SIGNATURES = {
     "povar_bench_power_terms": (C.c_int, [_H, C.c_int32, C.c_int32, _DP]),
     "povar_bench_power_kernels": (C.c_int, [_H, C.c_int32, C.c_int32, _DP]),
     "povar_launch_count": (C.c_int64, [_H]),
+    "povar_cuda_stream": (C.c_void_p, [_H]),
 }
 
 _lib = None
@@ -389,6 +390,10 @@ class Solver:
         out = np.zeros(4)
         self._check(self.lib.povar_bench_power_kernels(self.h, which, reps, _dp(out)))
         return out
+
+    def cuda_stream(self) -> int:
+        """cudaStream_t of the handle as an integer (for torch.cuda.ExternalStream)."""
+        return int(self.lib.povar_cuda_stream(self.h) or 0)
 
     def launch_count(self) -> int:
         return int(self.lib.povar_launch_count(self.h))

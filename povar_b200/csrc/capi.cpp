@@ -186,6 +186,11 @@ int64_t povar_launch_count(const povar_handle* h) {
   return h->engine->launches();
 }
 
+void* povar_cuda_stream(const povar_handle* h) {
+  if (!h || !h->engine) return nullptr;
+  return reinterpret_cast<void*>(h->engine->stream());
+}
+
 }  // extern "C"
 
 // used by the driver (host/lm_driver.cpp) to pull phase times without widening the ABI

@@ -38,6 +38,7 @@ class Engine {
 
   const char* last_error() const { return err_.c_str(); }
   long long launches() const { return launches_; }
+  cudaStream_t stream() const { return stream_; }
   const povar_options& options() const { return opt_; }
   const PhaseTimes& last_times() const { return times_; }
   void reset_times() { times_ = PhaseTimes(); }
