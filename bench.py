@@ -46,8 +46,10 @@ def ref_layout_bytes(nnz, L, C, joint=False):
 
 # bytes the matrix-free kernels have to move per launch (DESIGN.md "kernels"): index + observation
 # streams, per-landmark records, per-camera vectors, each counted once
-def own_bytes_landmark_pass(nnz, L, C):
-    return 24 * nnz + (32 + 32 + 48 + 32) * L + (96 + 96) * C
+def own_bytes_landmark_pass(slots, slices, L, C):
+    # sliced-ELL landmark half (k_e0_landmark_sell<pose>): camera index + uv per slot (padding included: it is
+    # streamed), slice header, X + fold record read and H written per landmark, camera records once
+    return 20 * slots + 36 * slices + (32 + 80 + 32) * L + 224 * C
 
 
 def own_bytes_camera_pass(nnz, L, C, items):
@@ -282,9 +284,10 @@ def main():
     ksec = solver.bench_power_kernels(capi.STATE_POSE, 20)
     ksec = solver.bench_power_kernels(capi.STATE_POSE, 50)
     term_s = solver.bench_power_terms(capi.STATE_POSE, 100)
-    items = int(solver.debug_read("item_cam").shape[0])
+    items = solver.debug_count("item_cam")
+    slots, slices = solver.debug_count("sell_cam"), solver.debug_count("slice_ptr") - 1
     lnnz, lL = hp.num_obs, hp.num_lms
-    own_a, own_b = own_bytes_landmark_pass(lnnz, lL, C), own_bytes_camera_pass(lnnz, lL, C, items)
+    own_a, own_b = own_bytes_landmark_pass(slots, slices, lL, C), own_bytes_camera_pass(lnnz, lL, C, items)
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -294,15 +297,25 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     dom = 0 if ksec[0] >= ksec[1] else 1
     dom_bytes = own_a if dom == 0 else own_b
+    dom_name = "k_e0_landmark_sell<pose>" if dom == 0 else "k_passB_e0_v2<pose>"
+    traffic = None
+    try:   # measured DRAM bytes per launch of that kernel (one ncu --set full capture, committed)
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f).get(args.workload, {})
+        if tj.get("n_gpus") == world:
+            traffic = tj.get(dom_name)
+    except Exception:
+        pass
     achieved = dom_bytes / ksec[dom] / 1e9
     roofline = {
-        "bound": "hbm", "kernel": "k_e0_landmark<pose>" if dom == 0 else "k_passB<pose,E0>",
+        "bound": "hbm", "kernel": dom_name,
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
-        "traffic": None,
+        "traffic": traffic,
         "bytes_per_launch": dom_bytes, "kernel_us": 1e6 * ksec[dom],
         "term_kernels_us": {"landmark_pass": 1e6 * ksec[0], "camera_pass": 1e6 * ksec[1],
-                            "item_reduce": 1e6 * ksec[2], "binv_norms_test": 1e6 * ksec[3]},
+                            "item_reduce_multi_gpu_only": 1e6 * ksec[2], "binv_norms_test": 1e6 * ksec[3]},
+        "sell_slots": slots, "sell_padding": slots / max(lnnz, 1) - 1.0,
         "term_us": 1e6 * term_s,
         "term_own_bytes": own_a + own_b,
         "term_own_gbs": (own_a + own_b) / term_s / 1e9,

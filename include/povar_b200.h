@@ -152,6 +152,11 @@ int povar_partition_landmarks(int32_t num_lms, const int64_t* lm_ptr, int32_t wo
 /* ---------- life cycle ---------------------------------------------------------------- */
 
 int povar_comm_unique_id(uint8_t id[128]);
+/* The NCCL communicator of a (nccl_id, rank) pair is made by the first povar_create that names it and
+ * shared by every later handle of this process with the same descriptor (the reference makes a step-1
+ * and a step-2 linearizor per solve, solver/linearizor.cpp:47-79; both ride on one communicator).
+ * povar_comm_finalize destroys the cached communicators; call it after the last povar_destroy. */
+int povar_comm_finalize(void);
 
 /* replaces Linearizor<Scalar>::create / create_homogeneous (solver/linearizor.cpp:47-79):
  * uploads the shard, builds the camera-major index, allocates all device state.

@@ -130,6 +130,7 @@ SIGNATURES = {
     "povar_set_state": (C.c_int, [_H, C.c_int32, _DP, _DP]),
     "povar_bundle_adjust": (C.c_int, [_H, C.POINTER(Options), C.POINTER(Iteration), C.c_int32,
                                       C.POINTER(SolveSummary)]),
+    "povar_comm_finalize": (C.c_int, []),
     "povar_debug_read": (C.c_int64, [_H, C.c_char_p, _DP, C.c_int64]),
     "povar_right_mul_e0": (C.c_int, [_H, C.c_int32, _DP, _DP]),
     "povar_bench_power_terms": (C.c_int, [_H, C.c_int32, C.c_int32, _DP]),
@@ -374,6 +375,13 @@ class Solver:
         out = np.empty(int(n))
         self.lib.povar_debug_read(self.h, name.encode(), _dp(out), n)
         return out
+
+    def debug_count(self, name: str) -> int:
+        """Number of elements of a device array (no copy)."""
+        n = self.lib.povar_debug_read(self.h, name.encode(), None, 0)
+        if n < 0:
+            raise PovarError(n, self.lib.povar_last_error(self.h).decode())
+        return int(n)
 
     def right_mul_e0(self, which, x: np.ndarray) -> np.ndarray:
         x = np.ascontiguousarray(x, dtype=np.float64)

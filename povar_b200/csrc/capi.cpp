@@ -6,6 +6,7 @@
 
 namespace povar {
 int nccl_unique_id(uint8_t id[128], std::string* err);
+int nccl_finalize();
 }
 
 struct povar_handle {
@@ -52,6 +53,8 @@ int povar_comm_unique_id(uint8_t id[128]) {
   if (rc != POVAR_OK) g_last_global_error = err;
   return rc;
 }
+
+int povar_comm_finalize(void) { return povar::nccl_finalize(); }
 
 int povar_create(const povar_problem_desc* desc, const povar_options* opt, const povar_comm_desc* comm,
                  povar_handle** out) {

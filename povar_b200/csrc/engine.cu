@@ -15,6 +15,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <numeric>
 
 namespace povar {
@@ -61,6 +63,31 @@ static NcclApi* load_nccl(std::string* err) {
     return nullptr;
   }
   return &api;
+}
+
+static std::mutex& comm_cache_mutex() {
+  static std::mutex m;
+  return m;
+}
+static std::map<std::string, void*>& comm_cache() {
+  static std::map<std::string, void*> cache;
+  return cache;
+}
+static std::string comm_key(const povar_comm_desc& c) {
+  std::string key(reinterpret_cast<const char*>(c.nccl_id), 128);
+  key += ":" + std::to_string(c.rank) + ":" + std::to_string(c.world_size) + ":" + std::to_string(c.device);
+  return key;
+}
+
+// destroys every cached communicator; handles made with them must have been destroyed before
+int nccl_finalize() {
+  std::lock_guard<std::mutex> lock(comm_cache_mutex());
+  NcclApi* api = comm_cache().empty() ? nullptr : load_nccl(nullptr);
+  for (auto& kv : comm_cache()) {
+    if (api && kv.second) api->CommDestroy(kv.second);
+  }
+  comm_cache().clear();
+  return POVAR_OK;
 }
 
 int nccl_unique_id(uint8_t id[128], std::string* err) {
@@ -282,10 +309,25 @@ int Engine::create(const povar_problem_desc* desc, const povar_options* opt,
     if (!e->nccl_) {
       rc = e->fail(POVAR_ERR_NCCL, nerr);
     } else {
-      Id128 id;
-      std::memcpy(id.bytes, comm->nccl_id, 128);
-      const int nrc = e->nccl_->CommInitRank(&e->nccl_comm_, e->world_, id, e->rank_);
-      if (nrc != 0) rc = e->fail(POVAR_ERR_NCCL, "ncclCommInitRank failed");
+      // one communicator per (id, rank) and process: the step-1 and step-2 linearizors of a solve, and
+      // every later handle made with the same descriptor, share it (ncclCommInitRank accepts an id once)
+      const std::string key = comm_key(*comm);
+      std::lock_guard<std::mutex> lock(comm_cache_mutex());
+      auto& cache = comm_cache();
+      auto it = cache.find(key);
+      if (it != cache.end()) {
+        e->nccl_comm_ = it->second;
+      } else {
+        Id128 id;
+        std::memcpy(id.bytes, comm->nccl_id, 128);
+        const int nrc = e->nccl_->CommInitRank(&e->nccl_comm_, e->world_, id, e->rank_);
+        if (nrc != 0) {
+          e->nccl_comm_ = nullptr;
+          rc = e->fail(POVAR_ERR_NCCL, "ncclCommInitRank failed");
+        } else {
+          cache[key] = e->nccl_comm_;
+        }
+      }
     }
   }
   if (rc == POVAR_OK) rc = e->upload(desc);
@@ -301,7 +343,7 @@ int Engine::create(const povar_problem_desc* desc, const povar_options* opt,
 Engine::~Engine() {
   if (device_ >= 0) cudaSetDevice(device_);
   if (stream_) cudaStreamSynchronize(stream_);
-  if (nccl_comm_ && nccl_) nccl_->CommDestroy(nccl_comm_);
+  // the communicator belongs to the process-wide cache (povar_comm_finalize releases it)
   if (cusolver_) destroy_cusolver(cusolver_);
   for (void* p : allocs_) cudaFreeAsync(p, stream_);
   if (stream_) cudaStreamSynchronize(stream_);
