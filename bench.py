@@ -241,6 +241,9 @@ def main():
     # ---- resident: one handle, state reset between steps
     solver = capi.Solver(hp, opt, comm)
     P0 = hp.cam_P.copy()
+    config["series_exchange"] = ("none (1 GPU)" if world == 1 else
+                                 "peer-memory stores fused into the term kernel (CUDA IPC over NVLink)"
+                                 if solver.peer_exchange_active() else "ncclAllReduce per term")
 
     def resident_step():
         solver.set_state(capi.STATE_POSE, P0, None)

@@ -274,6 +274,11 @@ int povar_bench_power_kernels(povar_handle* h, int32_t which, int32_t reps, doub
 /* kernels launched by this handle since creation (bench.py's gpu_launches) */
 int64_t povar_launch_count(const povar_handle* h);
 
+/* 1 if this handle exchanges the per-term camera sums over peer memory (CUDA IPC + NVLink stores fused
+ * into the term kernel), 0 if it uses ncclAllReduce per term (single GPU: 0).  POVAR_PEER_EXCHANGE=0 in
+ * the environment forces NCCL, =1 makes povar_create fail instead of falling back. */
+int povar_peer_exchange_active(const povar_handle* h);
+
 /* the cudaStream_t every kernel of this handle is launched on, so that a caller can bracket calls
  * with its own CUDA events (the reference's counterpart is the wall-clock Timer around
  * optimize_lm_ours_pOSE, solver/bal_bundle_adjustment.cpp:256, 868-871) */

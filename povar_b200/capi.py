@@ -136,6 +136,7 @@ SIGNATURES = {
     "povar_bench_power_terms": (C.c_int, [_H, C.c_int32, C.c_int32, _DP]),
     "povar_bench_power_kernels": (C.c_int, [_H, C.c_int32, C.c_int32, _DP]),
     "povar_launch_count": (C.c_int64, [_H]),
+    "povar_peer_exchange_active": (C.c_int, [_H]),
     "povar_cuda_stream": (C.c_void_p, [_H]),
 }
 
@@ -402,6 +403,9 @@ class Solver:
     def cuda_stream(self) -> int:
         """cudaStream_t of the handle as an integer (for torch.cuda.ExternalStream)."""
         return int(self.lib.povar_cuda_stream(self.h) or 0)
+
+    def peer_exchange_active(self) -> bool:
+        return bool(self.lib.povar_peer_exchange_active(self.h))
 
     def launch_count(self) -> int:
         return int(self.lib.povar_launch_count(self.h))

@@ -189,6 +189,11 @@ int64_t povar_launch_count(const povar_handle* h) {
   return h->engine->launches();
 }
 
+int povar_peer_exchange_active(const povar_handle* h) {
+  if (!h || !h->engine) return 0;
+  return h->engine->peer_exchange_active() ? 1 : 0;
+}
+
 void* povar_cuda_stream(const povar_handle* h) {
   if (!h || !h->engine) return nullptr;
   return reinterpret_cast<void*>(h->engine->stream());

@@ -73,6 +73,25 @@ static std::map<std::string, void*>& comm_cache() {
   static std::map<std::string, void*> cache;
   return cache;
 }
+struct PeerShared {
+  void* mem = nullptr;            // this rank's receive buffer + flags (cudaMalloc, IPC-exported)
+  std::vector<void*> opened;      // the peers' buffers as mapped here
+  PeerExchange px{};
+  unsigned int epoch = 0;
+  bool ok = false;
+  void release() {
+    ok = false;
+    for (void* p : opened) cudaIpcCloseMemHandle(p);
+    opened.clear();
+    if (mem) cudaFree(mem);
+    mem = nullptr;
+    cudaGetLastError();
+  }
+};
+static std::map<std::string, PeerShared*>& peer_cache() {
+  static std::map<std::string, PeerShared*> cache;
+  return cache;
+}
 static std::string comm_key(const povar_comm_desc& c) {
   std::string key(reinterpret_cast<const char*>(c.nccl_id), 128);
   key += ":" + std::to_string(c.rank) + ":" + std::to_string(c.world_size) + ":" + std::to_string(c.device);
@@ -83,6 +102,11 @@ static std::string comm_key(const povar_comm_desc& c) {
 int nccl_finalize() {
   std::lock_guard<std::mutex> lock(comm_cache_mutex());
   NcclApi* api = comm_cache().empty() ? nullptr : load_nccl(nullptr);
+  for (auto& kv : peer_cache()) {
+    kv.second->release();
+    delete kv.second;
+  }
+  peer_cache().clear();
   for (auto& kv : comm_cache()) {
     if (api && kv.second) api->CommDestroy(kv.second);
   }
@@ -312,6 +336,7 @@ int Engine::create(const povar_problem_desc* desc, const povar_options* opt,
       // one communicator per (id, rank) and process: the step-1 and step-2 linearizors of a solve, and
       // every later handle made with the same descriptor, share it (ncclCommInitRank accepts an id once)
       const std::string key = comm_key(*comm);
+      e->comm_key_ = key;
       std::lock_guard<std::mutex> lock(comm_cache_mutex());
       auto& cache = comm_cache();
       auto it = cache.find(key);
@@ -331,6 +356,7 @@ int Engine::create(const povar_problem_desc* desc, const povar_options* opt,
     }
   }
   if (rc == POVAR_OK) rc = e->upload(desc);
+  if (rc == POVAR_OK && e->world_ > 1) rc = e->setup_peer_exchange();
   if (rc != POVAR_OK) {
     if (err) *err = e->err_;
     delete e;
@@ -490,6 +516,117 @@ int Engine::upload(const povar_problem_desc* desc) {
   return POVAR_OK;
 }
 
+// Peer-memory exchange for the per-term camera sums: one cudaMalloc per rank (receive buffer + flags),
+// exported with CUDA IPC, handles swapped through the NCCL communicator, mapped with peer access over
+// NVLink.  Every rank takes the same decisions (the inputs of each decision are all-reduced), because a
+// rank that fell back to NCCL alone would deadlock the others.  The mapping is made once per
+// (communicator, camera count) and process -- like the communicator itself -- and shared by later
+// handles: ranks create their handles in the same order, so cache hits are symmetric.
+int Engine::setup_peer_exchange() {
+  const char* env = getenv("POVAR_PEER_EXCHANGE");
+  if (env != nullptr && std::strcmp(env, "0") == 0) return POVAR_OK;
+  if (world_ > kMaxPeers || C_ <= 0) return POVAR_OK;
+  const int nblk = (C_ + 15) / 16;
+  // the whole grid of the term kernel has to be resident (blocks wait for their peers); C and the GPUs
+  // are the same on every rank, so this test needs no agreement round
+  const int cap = std::min(series_term_peer_capacity(false), series_term_peer_capacity(true));
+  if (nblk > cap) return POVAR_OK;
+  const std::string key = comm_key_ + ":" + std::to_string(C_);
+  std::lock_guard<std::mutex> lock(comm_cache_mutex());
+  auto& cache = peer_cache();
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    peer_ = it->second;
+    peer_ok_ = peer_->ok;
+    if (!peer_ok_ && env != nullptr) {
+      return fail(POVAR_ERR_NCCL, "peer exchange requested but CUDA IPC / peer access is unavailable");
+    }
+    return POVAR_OK;
+  }
+  PeerShared* ps = new PeerShared();
+  cache[key] = ps;
+  peer_ = ps;
+  const size_t recv_bytes = sizeof(double) * 2 * static_cast<size_t>(world_) * C_ * 12;
+  const size_t flag_bytes = sizeof(unsigned int) * 2 * static_cast<size_t>(world_) * nblk;
+  const size_t recv_pad = (recv_bytes + 255) / 256 * 256;
+  unsigned int ok = 1;
+  cudaIpcMemHandle_t mine{};
+  if (cudaMalloc(&ps->mem, recv_pad + flag_bytes) != cudaSuccess) {
+    ps->mem = nullptr;
+    ok = 0;
+  }
+  if (ok && cudaMemsetAsync(ps->mem, 0, recv_pad + flag_bytes, stream_) != cudaSuccess) ok = 0;
+  if (ok && cudaIpcGetMemHandle(&mine, ps->mem) != cudaSuccess) ok = 0;
+  cudaGetLastError();
+  // swap: [world][16 words of handle] + [world] ok flags, summed as uint32 (everything else is zero)
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+  const int words = world_ * 17;
+  std::vector<unsigned int> host(words, 0u);
+  if (ok) std::memcpy(host.data() + 16 * rank_, &mine, 64);
+  host[16 * world_ + rank_] = ok;
+  unsigned int* dev = nullptr;
+  PV_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&dev), sizeof(unsigned int) * words, stream_));
+  PV_CUDA(cudaMemcpyAsync(dev, host.data(), sizeof(unsigned int) * words, cudaMemcpyHostToDevice, stream_));
+  if (nccl_->AllReduce(dev, dev, words, /*ncclUint32*/ 3, /*ncclSum*/ 0, nccl_comm_, stream_) != 0) {
+    return fail(POVAR_ERR_NCCL, "ncclAllReduce failed (peer exchange setup)");
+  }
+  PV_CUDA(cudaMemcpyAsync(host.data(), dev, sizeof(unsigned int) * words, cudaMemcpyDeviceToHost, stream_));
+  PV_CUDA(cudaStreamSynchronize(stream_));
+  unsigned int all_ok = 1;
+  for (int r = 0; r < world_; ++r) all_ok &= host[16 * world_ + r];
+  std::vector<void*> base(world_, nullptr);
+  if (all_ok) {
+    for (int r = 0; r < world_; ++r) {
+      if (r == rank_) {
+        base[r] = ps->mem;
+        continue;
+      }
+      cudaIpcMemHandle_t h;
+      std::memcpy(&h, host.data() + 16 * r, 64);
+      void* ptr = nullptr;
+      if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        all_ok = 0;
+        break;
+      }
+      ps->opened.push_back(ptr);
+      base[r] = ptr;
+    }
+  }
+  // second round: did everybody map everybody?
+  unsigned int mapped = all_ok;
+  PV_CUDA(cudaMemcpyAsync(dev, &mapped, sizeof(unsigned int), cudaMemcpyHostToDevice, stream_));
+  if (nccl_->AllReduce(dev, dev, 1, 3, 0, nccl_comm_, stream_) != 0) {
+    return fail(POVAR_ERR_NCCL, "ncclAllReduce failed (peer exchange setup)");
+  }
+  PV_CUDA(cudaMemcpyAsync(&mapped, dev, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream_));
+  PV_CUDA(cudaStreamSynchronize(stream_));
+  PV_CUDA(cudaFreeAsync(dev, stream_));
+  if (mapped != static_cast<unsigned int>(world_)) {
+    ps->release();   // the entry stays, marked unavailable: later handles do not try again
+    if (env != nullptr) {   // asked for explicitly: do not hide it
+      return fail(POVAR_ERR_NCCL, "peer exchange requested but CUDA IPC / peer access is unavailable");
+    }
+    return POVAR_OK;   // ncclAllReduce per term instead
+  }
+  for (int r = 0; r < world_; ++r) {
+    ps->px.recv[r] = static_cast<double*>(base[r]);
+    ps->px.flags[r] = reinterpret_cast<unsigned int*>(static_cast<char*>(base[r]) + recv_pad);
+  }
+  ps->px.rank = rank_;
+  ps->px.world = world_;
+  ps->px.nblk = nblk;
+  ps->ok = true;
+  peer_ok_ = true;
+  return POVAR_OK;
+}
+
+const PeerExchange* Engine::next_exchange() {
+  if (!peer_ok_) return nullptr;
+  peer_->px.epoch = ++peer_->epoch;
+  return &peer_->px;
+}
+
 int Engine::allreduce(double* buf, size_t n) {
   if (world_ <= 1) return POVAR_OK;
   // ncclDouble = 8, ncclSum = 0
@@ -620,7 +757,8 @@ void Engine::e0_product(bool joint, const double* y, bool in_series) {
     launch_e0_landmark_v2(d_, mp_, joint, in_series, lc());
     launch_passB_e0_v2(d_, mp_, joint, in_series, lc());
   }
-  if (in_series && world_ == 1) return;   // the term kernel adds the item partials itself
+  // the term kernel adds the item partials itself (and, sharded, exchanges them over peer memory)
+  if (in_series && term_mode() != kTermRaw) return;
   launch_reduce_items(d_, d_.item_part, 12, d_.cam_raw, in_series, lc());
   allreduce(d_.cam_raw, static_cast<size_t>(C_) * 12);
 }
@@ -645,7 +783,7 @@ int Engine::solve_power(bool joint, double lambda) {
   launch_series_start(d_, opt_.r_tolerance, m, lc());
   for (int i = 1; i <= m; ++i) {
     e0_product(joint, d_.vec_y, true);
-    launch_series_term(d_, joint, i, opt_.eta, opt_.r_tolerance, world_ == 1, lc());
+    launch_series_term(d_, joint, i, opt_.eta, opt_.r_tolerance, term_mode(), next_exchange(), lc());
   }
   PV_CUDA(cudaEventRecord(ev_[2], stream_));
   PV_CUDA(cudaGetLastError());
@@ -663,6 +801,7 @@ int Engine::finish_solve(bool joint, double* inc, int32_t* iterations) {
   times_.prepare += elapsed(ev_[0], ev_[1]);
   times_.reduced_solve += elapsed(ev_[1], ev_[2]);
   if (iterations) *iterations = h.iterations;
+  if (h.peer_timeout) return fail(POVAR_ERR_NCCL, "peer exchange of the camera sums timed out (a rank is gone?)");
   if (h.nonfinite) return POVAR_NUM_NONFINITE_INC;
   return POVAR_OK;
 }
@@ -1114,7 +1253,7 @@ int Engine::bench_power_terms(bool joint, int terms, double* seconds_per_term) {
   PV_CUDA(cudaEventRecord(ev_[0], stream_));
   for (int i = 1; i <= terms; ++i) {
     e0_product(joint, d_.vec_y, true);
-    launch_series_term(d_, joint, i, /*eta=*/-1.0, /*r_tolerance=*/-1.0, world_ == 1, lc());
+    launch_series_term(d_, joint, i, /*eta=*/-1.0, /*r_tolerance=*/-1.0, term_mode(), next_exchange(), lc());
   }
   PV_CUDA(cudaEventRecord(ev_[1], stream_));
   PV_CUDA(cudaGetLastError());
@@ -1146,7 +1285,7 @@ int Engine::bench_power_kernels(bool joint, int reps, double* seconds) {
           else launch_passB_e0_v2(d_, mp_, joint, true, lc());
           break;
         case 2: launch_reduce_items(d_, d_.item_part, 12, d_.cam_raw, true, lc()); break;
-        default: launch_series_term(d_, joint, i + 1, -1.0, -1.0, world_ == 1, lc()); break;
+        default: launch_series_term(d_, joint, i + 1, -1.0, -1.0, term_mode(), next_exchange(), lc()); break;
       }
     }
     PV_CUDA(cudaEventRecord(ev_[1], stream_));

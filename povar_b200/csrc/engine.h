@@ -9,6 +9,7 @@
 namespace povar {
 
 struct NcclApi;  // dlopen'ed entry points (engine.cu)
+struct PeerShared;
 
 struct PhaseTimes {
   double residual = 0, linearize = 0, prepare = 0, reduced_solve = 0, back_substitution = 0;
@@ -43,6 +44,7 @@ class Engine {
   const PhaseTimes& last_times() const { return times_; }
   void reset_times() { times_ = PhaseTimes(); }
   int world_size() const { return world_; }
+  bool peer_exchange_active() const { return peer_ok_; }
   int rank() const { return rank_; }
 
  private:
@@ -51,6 +53,9 @@ class Engine {
   int check(cudaError_t e, const char* what);
   int upload(const povar_problem_desc* desc);
   int allreduce(double* buf, size_t n);
+  int setup_peer_exchange();
+  TermMode term_mode() const { return world_ == 1 ? kTermFused : (peer_ok_ ? kTermPeer : kTermRaw); }
+  const PeerExchange* next_exchange();   // one epoch per term launch, on every rank alike
   void set_model(bool joint, double alpha);
   int solve_power(bool joint, double lambda);
   int solve_pcg(bool joint, double lambda);
@@ -86,6 +91,13 @@ class Engine {
   int rank_ = 0, world_ = 1, device_ = 0;
   void* nccl_comm_ = nullptr;
   NcclApi* nccl_ = nullptr;
+  // peer-memory exchange of the per-term camera sums (world_ > 1; falls back to ncclAllReduce when
+  // CUDA IPC / peer access is not available or the term grid would not be resident)
+  // The mapping belongs to a process-wide cache next to the communicator (one per communicator and
+  // camera count; povar_comm_finalize releases it): one solve in flight per communicator.
+  PeerShared* peer_ = nullptr;
+  std::string comm_key_;
+  bool peer_ok_ = false;
   // host mirrors
   int C_ = 0, L_ = 0;
   long long nnz_ = 0;

@@ -17,6 +17,9 @@
 //   k_finish_b / k_term / k_series_*   sc/linearization_power_varproj.hpp:191-360
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+#include <cstring>
+
 #include "device_math.cuh"
 #include "povar_internal.h"
 
@@ -283,6 +286,144 @@ __device__ __forceinline__ bool chol_inverse(double (&A)[D][D], double (&Inv)[D]
     }
   }
   return ok;
+}
+
+// The same computation with sixteen lanes per camera and the block in shared memory: lane i owns row i
+// during assembly and factorisation, lane c solves column c of the inverse.  Every entry is produced by
+// the same sequence of operations as in the one-thread version below (k_cam_binv, kept for A/B runs
+// with POVAR_CAM_BINV=v1), including Eigen's stop-at-the-first-bad-pivot behaviour.
+template <bool JOINT, int MODE>
+__global__ void __launch_bounds__(kBlock)
+k_cam_binv16(int C, const double* __restrict__ P, const double* __restrict__ kron,
+             const double* __restrict__ pose_scale, double lambda, double* __restrict__ Bmat,
+             double* __restrict__ Binv) {
+  constexpr int D = JOINT ? 11 : 12;
+  constexpr int kCams = kBlock / 16;
+  __shared__ double As[kCams][12][13];
+  __shared__ double Us[kCams][12];
+  const int lane16 = threadIdx.x & 15;
+  const int slot = threadIdx.x >> 4;
+  const int c_raw = blockIdx.x * kCams + slot;
+  const bool live = c_raw < C;
+  const int c = live ? c_raw : C - 1;   // idle half-warps shadow the last camera (no stores)
+  double (*A)[13] = As[slot];
+  const double* kr = kron + kKron * static_cast<size_t>(c);
+  const double* s = pose_scale + 12 * static_cast<size_t>(c);
+  const int i = lane16;
+  if (i < 12) {
+    const double si = s[i];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) A[i][j] = si * s[j] * kron_entry(kr, i, j);
+  }
+  __syncwarp();
+  if (JOINT) {
+    // Pi^T A Pi = (H S A S H)[1:,1:]  with S the 0<->p exchange and H = I - tau w w^T
+    double pv[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) pv[k] = P[12 * static_cast<size_t>(c) + k];
+    Reflector<12> pi;
+    pi.make(pv);
+    const int p = pi.p;
+    if (p != 0 && i < 12) {
+      const double t = A[0][i];
+      A[0][i] = A[p][i];
+      A[p][i] = t;
+    }
+    __syncwarp();
+    if (p != 0 && i < 12) {
+      const double t = A[i][0];
+      A[i][0] = A[i][p];
+      A[i][p] = t;
+    }
+    __syncwarp();
+    double row[12];
+    if (i < 12) {
+      double v = 0.0;
+#pragma unroll
+      for (int j = 0; j < 12; ++j) {
+        row[j] = A[i][j];
+        v += row[j] * pi.w[j];
+      }
+      Us[slot][i] = v;
+    }
+    __syncwarp();
+    double u[12], alpha = 0.0;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) u[k] = Us[slot][k];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) alpha += pi.w[k] * u[k];
+    const double tau = pi.tau;
+    if (i >= 1 && i < 12) {
+      double wi = 0.0, ui = 0.0;
+#pragma unroll
+      for (int k = 0; k < 12; ++k) {   // static indexing keeps w / u in registers
+        wi = (k == i) ? pi.w[k] : wi;
+        ui = (k == i) ? u[k] : ui;
+      }
+#pragma unroll
+      for (int j = 1; j < 12; ++j) {
+        A[i - 1][j - 1] = row[j] - tau * (wi * u[j] + ui * pi.w[j]) + tau * tau * alpha * wi * pi.w[j];
+      }
+    }
+    __syncwarp();
+  }
+  double* bm = Bmat + 144 * static_cast<size_t>(c);
+  if (i < D) {
+    if (MODE == 0) {
+      A[i][i] += lambda;
+      if (live) {
+#pragma unroll
+        for (int j = 0; j < D; ++j) bm[i * D + j] = A[i][j];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < D; ++j) A[i][j] = bm[i * D + j] - A[i][j];
+    }
+  }
+  __syncwarp();
+  // lower Cholesky in place, column by column; rows below the pivot in parallel
+  bool ok = true;
+  for (int j = 0; j < D; ++j) {
+    double d = A[j][j];
+    for (int k = 0; k < j; ++k) d -= A[j][k] * A[j][k];
+    if (!(d > 0.0)) ok = false;
+    __syncwarp();
+    if (ok) {
+      const double l = sqrt(d);
+      const double il = 1.0 / l;
+      if (i > j && i < D) {
+        double v = A[i][j];
+        for (int k = 0; k < j; ++k) v -= A[i][k] * A[j][k];
+        A[i][j] = v * il;
+      }
+      if (i == j) A[j][j] = l;
+    }
+    __syncwarp();
+  }
+  // lane cc solves L L^T x = e_cc
+  if (i < D) {
+    const int cc = i;
+    double yv[D], x[D];
+#pragma unroll
+    for (int r = 0; r < D; ++r) {
+      double v = (r == cc) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < r; ++k) v -= A[r][k] * yv[k];
+      yv[r] = v / A[r][r];
+    }
+#pragma unroll
+    for (int r = D - 1; r >= 0; --r) {
+      double v = yv[r];
+#pragma unroll
+      for (int k = r + 1; k < D; ++k) v -= A[k][r] * x[k];
+      x[r] = v / A[r][r];
+    }
+    if (live) {
+      double* bi = Binv + 144 * static_cast<size_t>(c);
+#pragma unroll
+      for (int r = 0; r < D; ++r) bi[r * D + cc] = x[r];
+    }
+  }
 }
 
 // MODE 0: R = proj((s s^T) o kron) + lambda I -> Bmat, R^-1 -> Binv           (prepare_Hb_*)
@@ -595,19 +736,45 @@ __device__ __forceinline__ void series_decide(double s0, double s1, int term, do
   }
 }
 
+// system-scope flag traffic of the peer exchange
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_relaxed_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return static_cast<long long>(t);
+}
+constexpr long long kPeerSpinNs = 4000000000LL;   // give up after 4 s: a peer died; fail the solve
+
 // one power-series term, camera side, sixteen lanes per camera (lane i owns row i of B^-1 -- the
 // 144 loads of the block are the expensive part -- and everything else is recomputed per lane in the
 // order of k_term, so the two kernels give identical bits):
-//   [FUSED] raw = sum of the camera's item partials (k_reduce_items);  tmp = B^-1 reduced(raw);
-//   accum += tmp;  y = y(tmp);  per-camera norms;  then the LAST block to finish applies the
-//   convergence test of k_series_decide.  Block = 256 threads = 16 cameras.
-template <bool JOINT, bool FUSED>
+//   [kTermFused, kTermPeer] raw = sum of the camera's item partials (k_reduce_items);
+//   [kTermPeer] the all-reduce over the landmark shards, fused: the block stores its 16 cameras' sums
+//       into every rank's receive buffer (NVLink peer stores), raises its flag on every rank, waits
+//       for the same block of every peer and adds the ranks' sums in rank order -- every rank gets the
+//       same bits, no NCCL launch, no separate reduction kernel;
+//   tmp = B^-1 reduced(raw);  accum += tmp;  y = y(tmp);  per-camera norms;  then the LAST block to
+//   finish applies the convergence test of k_series_decide.  Block = 256 threads = 16 cameras.
+template <bool JOINT, int MODE>
 __global__ void __launch_bounds__(kBlock)
 k_term16(int C, const double* __restrict__ raw_in, const int* __restrict__ cam_item_ptr,
          const double* __restrict__ item_part, const double* __restrict__ pose_scale,
          const double* __restrict__ P, const double* __restrict__ Binv, double* __restrict__ tmp,
          double* __restrict__ acc, double* __restrict__ y, double* __restrict__ cam_rec,
-         double* __restrict__ norm_part, int term, double eta, double r_tolerance, SeriesCtl* ctl) {
+         double* __restrict__ norm_part, int term, double eta, double r_tolerance, SeriesCtl* ctl,
+         PeerExchange px) {
   if (ctl->done) return;
   constexpr int D = JOINT ? 11 : 12;
   __shared__ double smem[2 * (kBlock / 32)];
@@ -618,11 +785,48 @@ k_term16(int C, const double* __restrict__ raw_in, const int* __restrict__ cam_i
   const bool live = c_raw < C;
   const int c = live ? c_raw : C - 1;          // idle half-warps shadow the last camera (no stores)
   double raw[12];
-  if (FUSED) {
+  if (MODE != kTermRaw) {
     double mine = 0.0;
     if (lane16 < 12) {
       const int ie = cam_item_ptr[c + 1];
       for (int it = cam_item_ptr[c]; it < ie; ++it) mine += item_part[static_cast<size_t>(it) * 12 + lane16];
+    }
+    if (MODE == kTermPeer) {
+      const int par = static_cast<int>(px.epoch & 1u);
+      const size_t vec = static_cast<size_t>(C) * 12;
+      const size_t slot = (static_cast<size_t>(par) * px.world + px.rank) * vec + 12 * static_cast<size_t>(c) + lane16;
+      if (live && lane16 < 12) {
+        for (int r = 0; r < px.world; ++r) px.recv[r][slot] = mine;
+      }
+      // the flag store below is a release at system scope; it covers the block's data stores through
+      // the barrier (causality order), so the other threads need no fence of their own
+      __syncthreads();
+      if (static_cast<int>(threadIdx.x) < px.world) {
+        const int r = threadIdx.x;
+        st_release_sys(px.flags[r] + (static_cast<size_t>(par) * px.world + px.rank) * px.nblk + blockIdx.x, px.epoch);
+        // wait for rank r's block of the same index (flags only grow; a peer is at most one exchange ahead,
+        // and that one uses the other parity)
+        const unsigned int* f = px.flags[px.rank] + (static_cast<size_t>(par) * px.world + r) * px.nblk + blockIdx.x;
+        long long t0 = 0;
+        unsigned int spins = 0;
+        while (static_cast<int>(ld_relaxed_sys(f) - px.epoch) < 0) {
+          if ((++spins & 1023u) == 0) {
+            const long long now = global_ns();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > kPeerSpinNs) {
+              atomicExch(&ctl->peer_timeout, 1);
+              break;
+            }
+          }
+        }
+        (void)ld_acquire_sys(f);
+      }
+      __syncthreads();
+      mine = 0.0;
+      if (lane16 < 12) {
+        const double* rb = px.recv[px.rank] + static_cast<size_t>(par) * px.world * vec + 12 * static_cast<size_t>(c) + lane16;
+        for (int r = 0; r < px.world; ++r) mine += __ldcg(rb + r * vec);   // L2: the peers' stores land there
+      }
     }
 #pragma unroll
     for (int k = 0; k < 12; ++k) raw[k] = __shfl_sync(kFullMask, mine, base + k);
@@ -694,6 +898,7 @@ k_series_start(int C, const double* __restrict__ norm_part, double r_tolerance, 
     ctl->done = max_terms > 0 ? 0 : 1;
     ctl->iterations = max_terms > 0 ? max_terms : 0;   // "Maximum number of iterations reached."
     ctl->nonfinite = isfinite(s1) ? 0 : 1;
+    ctl->peer_timeout = 0;
     ctl->norm0 = r_tolerance > 0 ? sqrt(s0) : 0.0;
     ctl->last_tmp_norm = sqrt(s0);
     ctl->last_acc_norm = sqrt(s1);
@@ -815,9 +1020,21 @@ void launch_cam_scale(const DeviceState& d, const ModelParams& mp, const LaunchC
   count(lc);
 }
 
+static bool cam_binv_v1() {
+  static const bool v1 = getenv("POVAR_CAM_BINV") != nullptr && std::strcmp(getenv("POVAR_CAM_BINV"), "v1") == 0;
+  return v1;
+}
+
 void launch_cam_binv(const DeviceState& d, bool joint, double lambda, const LaunchCfg& lc) {
   const int blocks = (d.ix.C + 127) / 128;
-  if (joint) {
+  const int blocks16 = (d.ix.C + kBlock / 16 - 1) / (kBlock / 16);
+  if (!cam_binv_v1()) {
+    if (joint) {
+      k_cam_binv16<true, 0><<<blocks16, kBlock, 0, lc.stream>>>(d.ix.C, d.P, d.kron, d.pose_scale, lambda, d.Bmat, d.Binv);
+    } else {
+      k_cam_binv16<false, 0><<<blocks16, kBlock, 0, lc.stream>>>(d.ix.C, d.P, d.kron, d.pose_scale, lambda, d.Bmat, d.Binv);
+    }
+  } else if (joint) {
     k_cam_binv<true, 0><<<blocks, 128, 0, lc.stream>>>(d.ix.C, d.P, d.kron, d.pose_scale, lambda, d.Bmat, d.Binv);
   } else {
     k_cam_binv<false, 0><<<blocks, 128, 0, lc.stream>>>(d.ix.C, d.P, d.kron, d.pose_scale, lambda, d.Bmat, d.Binv);
@@ -828,7 +1045,14 @@ void launch_cam_binv(const DeviceState& d, bool joint, double lambda, const Laun
 // block-Jacobi preconditioner: Mprec = (Bmat - proj((s s^T) o kron_sdiag))^-1
 void launch_cam_precond(const DeviceState& d, bool joint, const double* kron_sdiag, const LaunchCfg& lc) {
   const int blocks = (d.ix.C + 127) / 128;
-  if (joint) {
+  const int blocks16 = (d.ix.C + kBlock / 16 - 1) / (kBlock / 16);
+  if (!cam_binv_v1()) {
+    if (joint) {
+      k_cam_binv16<true, 1><<<blocks16, kBlock, 0, lc.stream>>>(d.ix.C, d.P, kron_sdiag, d.pose_scale, 0.0, d.Bmat, d.Mprec);
+    } else {
+      k_cam_binv16<false, 1><<<blocks16, kBlock, 0, lc.stream>>>(d.ix.C, d.P, kron_sdiag, d.pose_scale, 0.0, d.Bmat, d.Mprec);
+    }
+  } else if (joint) {
     k_cam_binv<true, 1><<<blocks, 128, 0, lc.stream>>>(d.ix.C, d.P, kron_sdiag, d.pose_scale, 0.0, d.Bmat, d.Mprec);
   } else {
     k_cam_binv<false, 1><<<blocks, 128, 0, lc.stream>>>(d.ix.C, d.P, kron_sdiag, d.pose_scale, 0.0, d.Bmat, d.Mprec);
@@ -879,22 +1103,37 @@ void launch_series_start(const DeviceState& d, double r_tolerance, int max_terms
 }
 
 void launch_series_term(const DeviceState& d, bool joint, int term, double eta, double r_tolerance,
-                        bool fused_reduce, const LaunchCfg& lc) {
+                        TermMode mode, const PeerExchange* px, const LaunchCfg& lc) {
   const int blocks = (d.ix.C + 15) / 16;
-#define POVAR_TERM(J, F)                                                                              \
-  k_term16<J, F><<<blocks, kBlock, 0, lc.stream>>>(d.ix.C, d.cam_raw, d.ix.cam_item_ptr, d.item_part,  \
+  const PeerExchange none{};
+  const PeerExchange& pe = (mode == kTermPeer && px != nullptr) ? *px : none;
+#define POVAR_TERM(J, M)                                                                              \
+  k_term16<J, M><<<blocks, kBlock, 0, lc.stream>>>(d.ix.C, d.cam_raw, d.ix.cam_item_ptr, d.item_part,  \
                                                    d.pose_scale, d.P, d.Binv, d.vec_tmp, d.vec_acc,    \
                                                    d.vec_y, d.cam_rec, d.norm_part, term, eta,         \
-                                                   r_tolerance, d.ctl)
+                                                   r_tolerance, d.ctl, pe)
   if (joint) {
-    if (fused_reduce) POVAR_TERM(true, true);
-    else POVAR_TERM(true, false);
+    if (mode == kTermPeer) POVAR_TERM(true, kTermPeer);
+    else if (mode == kTermFused) POVAR_TERM(true, kTermFused);
+    else POVAR_TERM(true, kTermRaw);
   } else {
-    if (fused_reduce) POVAR_TERM(false, true);
-    else POVAR_TERM(false, false);
+    if (mode == kTermPeer) POVAR_TERM(false, kTermPeer);
+    else if (mode == kTermFused) POVAR_TERM(false, kTermFused);
+    else POVAR_TERM(false, kTermRaw);
   }
 #undef POVAR_TERM
   count(lc);
+}
+
+int series_term_peer_capacity(bool joint) {
+  int dev = 0, sms = 0, per_sm = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  const cudaError_t e = joint
+      ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_term16<true, kTermPeer>, kBlock, 0)
+      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_term16<false, kTermPeer>, kBlock, 0);
+  if (e != cudaSuccess) return 0;
+  return sms * per_sm;
 }
 
 void launch_e0_finish(const DeviceState& d, bool joint, double* out, const LaunchCfg& lc) {

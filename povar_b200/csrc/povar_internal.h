@@ -57,13 +57,27 @@ struct SeriesCtl {
   int done;            // early exit taken: later kernels of the series return at once
   int iterations;      // summary.num_iterations
   int nonfinite;       // increment has NaN/Inf
-  int pad;
+  int peer_timeout;    // a peer's camera sums never arrived (PeerExchange): the solve fails loudly
   double norm0;        // |accum_0| when r_tolerance > 0
   double last_tmp_norm;
   double last_acc_norm;
   unsigned int ticket; // last-block election
   unsigned int pad2;
 };
+
+// Peer-memory exchange of the per-term camera sums when landmarks are sharded over several GPUs
+// (engine.cu Engine::setup_peer_exchange, kernels_camera.cu k_term16<.., kTermPeer>).  Every rank owns
+// a receive buffer [2 parities][world][C*12] and a flag array [2][world][blocks]; recv[r] / flags[r] are
+// rank r's arrays as mapped into this process (CUDA IPC over NVLink; recv[rank] is the local one).
+constexpr int kMaxPeers = 8;
+struct PeerExchange {
+  double* recv[kMaxPeers];
+  unsigned int* flags[kMaxPeers];
+  int rank, world, nblk;
+  unsigned int epoch;   // number of this exchange; parity = epoch & 1
+};
+// where k_term16 takes the reduced camera sums from
+enum TermMode { kTermRaw = 0, kTermFused = 1, kTermPeer = 2 };
 
 struct CostAccum {
   double err_all, rsum_all, err_valid, rsum_valid;
@@ -173,10 +187,15 @@ void launch_passB(const DeviceState& d, const ModelParams& mp, bool joint, PassB
                   bool in_series, const LaunchCfg& lc);
 // series bookkeeping
 void launch_series_start(const DeviceState& d, double r_tolerance, int max_terms, const LaunchCfg& lc);
-// fused_reduce: the term kernel adds the item partials of the camera half itself (single GPU);
-// otherwise it reads cam_raw (after launch_reduce_items and the all-reduce)
+// mode kTermFused: the term kernel adds the item partials of the camera half itself (single GPU);
+// kTermPeer: it also pushes them to every rank's receive buffer and adds the ranks' sums in rank order
+// (px, with px->epoch set for this exchange); kTermRaw: it reads cam_raw (after launch_reduce_items and
+// the NCCL all-reduce)
 void launch_series_term(const DeviceState& d, bool joint, int term, double eta, double r_tolerance,
-                        bool fused_reduce, const LaunchCfg& lc);
+                        TermMode mode, const PeerExchange* px, const LaunchCfg& lc);
+// most blocks of the peer-mode term kernel that can be resident at once on the current device (every
+// block waits for its peers' block of the same index, so the whole grid has to be resident)
+int series_term_peer_capacity(bool joint);
 void launch_finish_b(const DeviceState& d, bool joint, const LaunchCfg& lc);
 void launch_e0_finish(const DeviceState& d, bool joint, double* out, const LaunchCfg& lc);
 void launch_make_y(const DeviceState& d, bool joint, const double* x, double* y, const LaunchCfg& lc);

@@ -13,8 +13,9 @@ import povar_testlib as common
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, path, kw, out_dir):
+def _worker(rank, world, port, path, kw, out_dir, exchange):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["POVAR_PEER_EXCHANGE"] = exchange     # "1": peer memory or fail; "0": ncclAllReduce
     os.environ["MASTER_PORT"] = str(port)
     import torch.distributed as dist
     from povar_b200 import capi
@@ -24,6 +25,7 @@ def _worker(rank, world, port, path, kw, out_dir):
     dist.broadcast_object_list(ids, src=0)
     hp = capi.HostProblem.read(path).shard(rank, world)
     s = capi.Solver(hp, capi.default_options(verbosity_level=0, **kw), capi.make_comm(rank, world, rank, ids[0]))
+    assert s.peer_exchange_active() == (exchange == "1")
     its, summary = s.bundle_adjust()
     P, X = s.get_state(capi.STATE_JOINT)
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), cost=[e.cost for e in its],
@@ -34,8 +36,9 @@ def _worker(rank, world, port, path, kw, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name", ["small_povar", "ladybug49_poba"])
-def test_two_gpu_shards_reproduce_single_gpu_trace(name, tmp_path):
+@pytest.mark.parametrize("name,exchange", [("small_povar", "1"), ("small_povar", "0"), ("ladybug49_poba", "1"),
+                                           ("ladybug49_pcg_ripcg", "1")])
+def test_two_gpu_shards_reproduce_single_gpu_trace(name, exchange, tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
@@ -44,7 +47,8 @@ def test_two_gpu_shards_reproduce_single_gpu_trace(name, tmp_path):
     kw = common.flags_to_options(meta["flags"])
     path = common.golden_file(meta["shape"])
     world = 2
-    mp.spawn(_worker, args=(world, 29700 + os.getpid() % 200, path, kw, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, 29700 + os.getpid() % 200, path, kw, str(tmp_path), exchange), nprocs=world,
+             join=True)
     r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
     # replicated control flow: both ranks log the same trace, bit for bit
     assert np.array_equal(r0["cost"], r1["cost"]) and np.array_equal(r0["lin"], r1["lin"])

@@ -1,0 +1,74 @@
+"""Golden traces of the reference for BASELINE.json's larger configurations (c2, c3, c4).
+
+Same recipe as tools/make_golden.py (`bal_ref --num-threads 1` and `--num-threads 8` on the
+data_custom file of the seeded generator), but the problem files are far too large to commit:
+only the ba_log.json columns and the sha256 of each file go to tests/golden/traces_large.json, and
+the GPU tests regenerate the files from the seed and check the hash before comparing.
+
+  c2  trafalgar257  x {POWER_VARPROJ, POWER_SCHUR_COMPLEMENT, PCG, CHOLESKY}   (+ RIPOBA)
+  c3  venice89      POWER_SCHUR_COMPLEMENT + RIPOBA, 20 terms
+  c4  venice1778    POWER_VARPROJ + RIPOBA, CAUCHY  (the benchmark configuration)
+
+Runs HERE (needs oracle/_ref/bal_ref); takes tens of minutes on 8 cores.
+Usage: python tools/make_golden_large.py [config-name ...]   (merges into the existing json)
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+from povar_b200 import synthetic  # noqa: E402
+import make_golden as mg  # noqa: E402
+
+OUT = os.path.join(mg.GOLD, "traces_large.json")
+CONFIGS = [
+    ("trafalgar257_povar", "trafalgar257", []),
+    ("trafalgar257_poba", "trafalgar257", ["--solver-type-step-1", "POWER_SCHUR_COMPLEMENT"]),
+    ("trafalgar257_pcg", "trafalgar257", ["--solver-type-step-1", "PCG"]),
+    ("trafalgar257_cholesky", "trafalgar257", ["--solver-type-step-1", "CHOLESKY"]),
+    ("venice89_poba", "venice89", ["--solver-type-step-1", "POWER_SCHUR_COMPLEMENT"]),
+    ("venice1778_povar_cauchy", "venice1778", ["--residual-robust-norm", "CAUCHY"]),
+]
+
+
+def main():
+    want = set(sys.argv[1:])
+    doc = {"files": {}, "traces": {},
+           "reference_flags": "--alpha 0.1 --power-sc-iterations 20 (+ per-config flags)"}
+    if os.path.exists(OUT):
+        with open(OUT) as f:
+            doc = json.load(f)
+    with tempfile.TemporaryDirectory() as tmp:
+        paths = {}
+        for name, shape, flags in CONFIGS:
+            if want and name not in want:
+                continue
+            if shape not in paths:
+                prob = synthetic.generate_named(shape)
+                paths[shape] = os.path.join(tmp, f"{shape}.txt")
+                synthetic.write_bal(prob, paths[shape])
+                doc["files"][shape] = {"sha256": mg.sha256(paths[shape]), "num_cams": prob.num_cams,
+                                       "num_lms": prob.num_lms, "num_obs": prob.num_obs, "committed": False}
+            t0 = time.time()
+            one = mg.run_ref(paths[shape], flags, 1, tmp)
+            t1 = time.time()
+            many = mg.run_ref(paths[shape], flags, 8, tmp)
+            t2 = time.time()
+            doc["traces"][name] = {"shape": shape, "flags": flags, "threads1": one,
+                                   "threads8": {"cost": many["cost"], "step_is_successful": many["step_is_successful"],
+                                                "iteration": many["iteration"]},
+                                   "wall_s": {"threads1": round(t1 - t0, 1), "threads8": round(t2 - t1, 1)}}
+            print(f"{name}: {len(one['cost'])} trials (8 threads: {len(many['cost'])}), final cost "
+                  f"{one['cost'][-1]:.9e} vs {many['cost'][-1]:.9e}; {t1 - t0:.0f}s / {t2 - t1:.0f}s", flush=True)
+            with open(OUT, "w") as f:
+                json.dump(doc, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
