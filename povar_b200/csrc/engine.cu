@@ -546,9 +546,9 @@ int Engine::setup_peer_exchange() {
   PeerShared* ps = new PeerShared();
   cache[key] = ps;
   peer_ = ps;
-  const size_t recv_bytes = sizeof(double) * 2 * static_cast<size_t>(world_) * C_ * 12;
-  const size_t flag_bytes = sizeof(unsigned int) * 2 * static_cast<size_t>(world_) * nblk;
-  const size_t recv_pad = (recv_bytes + 255) / 256 * 256;
+  // 16-byte tagged slots, [2 parities][world][C*12]; zero = "exchange 0", never waited for
+  const size_t recv_pad = 16 * 2 * static_cast<size_t>(world_) * C_ * 12;
+  const size_t flag_bytes = 0;
   unsigned int ok = 1;
   cudaIpcMemHandle_t mine{};
   if (cudaMalloc(&ps->mem, recv_pad + flag_bytes) != cudaSuccess) {
@@ -611,11 +611,9 @@ int Engine::setup_peer_exchange() {
   }
   for (int r = 0; r < world_; ++r) {
     ps->px.recv[r] = static_cast<double*>(base[r]);
-    ps->px.flags[r] = reinterpret_cast<unsigned int*>(static_cast<char*>(base[r]) + recv_pad);
   }
   ps->px.rank = rank_;
   ps->px.world = world_;
-  ps->px.nblk = nblk;
   ps->ok = true;
   peer_ok_ = true;
   return POVAR_OK;

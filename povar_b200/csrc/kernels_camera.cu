@@ -736,19 +736,25 @@ __device__ __forceinline__ void series_decide(double s0, double s1, int term, do
   }
 }
 
-// system-scope flag traffic of the peer exchange
-__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+// Peer exchange, low-latency protocol: a double travels as ONE 16-byte store {lo, epoch, hi, epoch};
+// the receiver polls the slot until both tags carry the epoch it waits for (each 8-byte half is written
+// atomically, so a torn line is recognised and re-read).  No fence, no separate flag: the latency of an
+// exchange is one NVLink store.
+__device__ __forceinline__ void st_tagged(double* slot, double v, unsigned int epoch) {
+  const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(v));
+  const unsigned int lo = static_cast<unsigned int>(bits), hi = static_cast<unsigned int>(bits >> 32);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(slot), "r"(lo), "r"(epoch), "r"(hi),
+               "r"(epoch)
+               : "memory");
 }
-__device__ __forceinline__ unsigned int ld_relaxed_sys(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
+__device__ __forceinline__ bool ld_tagged(const double* slot, unsigned int epoch, double& v) {
+  unsigned int lo, t0, hi, t1;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(lo), "=r"(t0), "=r"(hi), "=r"(t1)
+               : "l"(slot)
+               : "memory");
+  v = __longlong_as_double(static_cast<long long>((static_cast<unsigned long long>(hi) << 32) | lo));
+  return t0 == epoch && t1 == epoch;
 }
 __device__ __forceinline__ long long global_ns() {
   unsigned long long t;
@@ -761,10 +767,10 @@ constexpr long long kPeerSpinNs = 4000000000LL;   // give up after 4 s: a peer d
 // 144 loads of the block are the expensive part -- and everything else is recomputed per lane in the
 // order of k_term, so the two kernels give identical bits):
 //   [kTermFused, kTermPeer] raw = sum of the camera's item partials (k_reduce_items);
-//   [kTermPeer] the all-reduce over the landmark shards, fused: the block stores its 16 cameras' sums
-//       into every rank's receive buffer (NVLink peer stores), raises its flag on every rank, waits
-//       for the same block of every peer and adds the ranks' sums in rank order -- every rank gets the
-//       same bits, no NCCL launch, no separate reduction kernel;
+//   [kTermPeer] the all-reduce over the landmark shards, fused: every lane stores its camera sum, tagged
+//       with the exchange number, into every rank's receive buffer (NVLink peer stores), then polls its
+//       own buffer for the peers' values and adds them in rank order -- every rank gets the same bits,
+//       no NCCL launch, no separate reduction kernel, no fence;
 //   tmp = B^-1 reduced(raw);  accum += tmp;  y = y(tmp);  per-camera norms;  then the LAST block to
 //   finish applies the convergence test of k_series_decide.  Block = 256 threads = 16 cameras.
 template <bool JOINT, int MODE>
@@ -792,41 +798,37 @@ k_term16(int C, const double* __restrict__ raw_in, const int* __restrict__ cam_i
       for (int it = cam_item_ptr[c]; it < ie; ++it) mine += item_part[static_cast<size_t>(it) * 12 + lane16];
     }
     if (MODE == kTermPeer) {
+      // slots are 16 bytes (2 doubles wide): [parity][source rank][C*12]
       const int par = static_cast<int>(px.epoch & 1u);
       const size_t vec = static_cast<size_t>(C) * 12;
-      const size_t slot = (static_cast<size_t>(par) * px.world + px.rank) * vec + 12 * static_cast<size_t>(c) + lane16;
+      const size_t mine_at = 2 * ((static_cast<size_t>(par) * px.world + px.rank) * vec + 12 * static_cast<size_t>(c) + lane16);
       if (live && lane16 < 12) {
-        for (int r = 0; r < px.world; ++r) px.recv[r][slot] = mine;
+        for (int r = 0; r < px.world; ++r) st_tagged(px.recv[r] + mine_at, mine, px.epoch);
       }
-      // the flag store below is a release at system scope; it covers the block's data stores through
-      // the barrier (causality order), so the other threads need no fence of their own
-      __syncthreads();
-      if (static_cast<int>(threadIdx.x) < px.world) {
-        const int r = threadIdx.x;
-        st_release_sys(px.flags[r] + (static_cast<size_t>(par) * px.world + px.rank) * px.nblk + blockIdx.x, px.epoch);
-        // wait for rank r's block of the same index (flags only grow; a peer is at most one exchange ahead,
-        // and that one uses the other parity)
-        const unsigned int* f = px.flags[px.rank] + (static_cast<size_t>(par) * px.world + r) * px.nblk + blockIdx.x;
+      // add the ranks' sums in rank order (the same bits on every rank), each as soon as it has arrived
+      double sum = 0.0;
+      if (live && lane16 < 12) {
+        const double* rb = px.recv[px.rank] + 2 * (static_cast<size_t>(par) * px.world * vec + 12 * static_cast<size_t>(c) + lane16);
         long long t0 = 0;
         unsigned int spins = 0;
-        while (static_cast<int>(ld_relaxed_sys(f) - px.epoch) < 0) {
-          if ((++spins & 1023u) == 0) {
-            const long long now = global_ns();
-            if (t0 == 0) t0 = now;
-            if (now - t0 > kPeerSpinNs) {
-              atomicExch(&ctl->peer_timeout, 1);
-              break;
+        for (int r = 0; r < px.world; ++r) {
+          double v;
+          while (!ld_tagged(rb + 2 * r * vec, px.epoch, v)) {
+            if ((++spins & 1023u) == 0) {
+              const long long now = global_ns();
+              if (t0 == 0) t0 = now;
+              if (now - t0 > kPeerSpinNs) {
+                atomicExch(&ctl->peer_timeout, 1);
+                v = 0.0;
+                break;
+              }
             }
           }
+          sum += v;
         }
-        (void)ld_acquire_sys(f);
       }
-      __syncthreads();
-      mine = 0.0;
-      if (lane16 < 12) {
-        const double* rb = px.recv[px.rank] + static_cast<size_t>(par) * px.world * vec + 12 * static_cast<size_t>(c) + lane16;
-        for (int r = 0; r < px.world; ++r) mine += __ldcg(rb + r * vec);   // L2: the peers' stores land there
-      }
+      __syncwarp();
+      mine = sum;
     }
 #pragma unroll
     for (int k = 0; k < 12; ++k) raw[k] = __shfl_sync(kFullMask, mine, base + k);

@@ -67,14 +67,13 @@ struct SeriesCtl {
 
 // Peer-memory exchange of the per-term camera sums when landmarks are sharded over several GPUs
 // (engine.cu Engine::setup_peer_exchange, kernels_camera.cu k_term16<.., kTermPeer>).  Every rank owns
-// a receive buffer [2 parities][world][C*12] and a flag array [2][world][blocks]; recv[r] / flags[r] are
-// rank r's arrays as mapped into this process (CUDA IPC over NVLink; recv[rank] is the local one).
+// a receive buffer [2 parities][world][C*12] of 16-byte slots {lo, epoch, hi, epoch}; recv[r] is rank r's
+// buffer as mapped into this process (CUDA IPC over NVLink; recv[rank] is the local one).
 constexpr int kMaxPeers = 8;
 struct PeerExchange {
   double* recv[kMaxPeers];
-  unsigned int* flags[kMaxPeers];
-  int rank, world, nblk;
-  unsigned int epoch;   // number of this exchange; parity = epoch & 1
+  int rank, world;
+  unsigned int epoch;   // number of this exchange (> 0); parity = epoch & 1
 };
 // where k_term16 takes the reduced camera sums from
 enum TermMode { kTermRaw = 0, kTermFused = 1, kTermPeer = 2 };

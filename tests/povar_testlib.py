@@ -25,12 +25,25 @@ def traces():
     return _traces
 
 
+_traces_large = None
+
+
+def traces_large():
+    """Traces of the reference on BASELINE.json's larger configurations (tools/make_golden_large.py)."""
+    global _traces_large
+    if _traces_large is None:
+        with open(os.path.join(GOLD, "traces_large.json")) as f:
+            _traces_large = json.load(f)
+    return _traces_large
+
+
 def golden_file(shape: str) -> str:
     """Path of the data_custom file of a golden shape.  Small ones are committed; larger ones are
     regenerated from the seeded generator and checked against the recorded sha256."""
     if shape in _files:
         return _files[shape]
-    meta = traces()["files"][shape]
+    files = traces()["files"]
+    meta = files[shape] if shape in files else traces_large()["files"][shape]
     if meta["committed"]:
         path = os.path.join(GOLD, f"{shape}.txt")
     else:
