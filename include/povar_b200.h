@@ -139,6 +139,13 @@ typedef struct povar_bal_data {
 int povar_bal_read(const char* path, povar_bal_data* out, char* err, size_t err_len);
 void povar_bal_free(povar_bal_data* data);
 
+/* --create-dataset (BalProblem::load_bal_varproj_space_matrix_write, bal/bal_problem.cpp:306-471): turns an
+ * original BAL file (9 parameters per camera) into the 15-parameter file povar_bal_read loads -- same
+ * observations, the first two rows of every camera matrix drawn from N(0,1), third row 0 0 0 1, f k1 k2
+ * and the landmark block copied through, in the reference's text layout.  seed < 0 seeds from
+ * std::random_device like the reference; seed >= 0 makes the output reproducible. */
+int povar_bal_create_dataset(const char* input, const char* output, int64_t seed, char* err, size_t err_len);
+
 /* canonical order of an unordered observation list: fills perm[num_obs] (indices into the
  * input, landmark-major, camera ascending) and lm_ptr[num_lms+1]; returns POVAR_ERR_INVALID on
  * a duplicate pair or an index out of range. */

@@ -136,6 +136,7 @@ SIGNATURES = {
     "povar_bench_power_terms": (C.c_int, [_H, C.c_int32, C.c_int32, _DP]),
     "povar_bench_power_kernels": (C.c_int, [_H, C.c_int32, C.c_int32, _DP]),
     "povar_launch_count": (C.c_int64, [_H]),
+    "povar_bal_create_dataset": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int64, C.c_char_p, C.c_size_t]),
     "povar_peer_exchange_active": (C.c_int, [_H]),
     "povar_cuda_stream": (C.c_void_p, [_H]),
 }
@@ -409,6 +410,15 @@ class Solver:
 
     def launch_count(self) -> int:
         return int(self.lib.povar_launch_count(self.h))
+
+
+def create_dataset(src: str, dst: str, seed: int = -1) -> None:
+    """--create-dataset of the reference (bal_problem.cpp:306-471): BAL file -> 15-parameter file."""
+    lib = load()
+    err = C.create_string_buffer(512)
+    rc = lib.povar_bal_create_dataset(src.encode(), dst.encode(), seed, err, 512)
+    if rc != OK:
+        raise PovarError(rc, err.value.decode() or "povar_bal_create_dataset failed")
 
 
 def unique_id() -> bytes:

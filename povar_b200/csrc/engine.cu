@@ -356,7 +356,7 @@ int Engine::create(const povar_problem_desc* desc, const povar_options* opt,
     }
   }
   if (rc == POVAR_OK) rc = e->upload(desc);
-  if (rc == POVAR_OK && e->world_ > 1) rc = e->setup_peer_exchange();
+  if (rc == POVAR_OK) rc = e->setup_peer_exchange();
   if (rc != POVAR_OK) {
     if (err) *err = e->err_;
     delete e;
@@ -371,6 +371,10 @@ Engine::~Engine() {
   if (stream_) cudaStreamSynchronize(stream_);
   // the communicator belongs to the process-wide cache (povar_comm_finalize releases it)
   if (cusolver_) destroy_cusolver(cusolver_);
+  if (peer_owned_ && peer_) {
+    peer_->release();
+    delete peer_;
+  }
   for (void* p : allocs_) cudaFreeAsync(p, stream_);
   if (stream_) cudaStreamSynchronize(stream_);
   for (auto& ev : ev_) {
@@ -526,11 +530,26 @@ int Engine::setup_peer_exchange() {
   const char* env = getenv("POVAR_PEER_EXCHANGE");
   if (env != nullptr && std::strcmp(env, "0") == 0) return POVAR_OK;
   if (world_ > kMaxPeers || C_ <= 0) return POVAR_OK;
-  const int nblk = (C_ + 15) / 16;
-  // the whole grid of the term kernel has to be resident (blocks wait for their peers); C and the GPUs
-  // are the same on every rank, so this test needs no agreement round
-  const int cap = std::min(series_term_peer_capacity(false), series_term_peer_capacity(true));
-  if (nblk > cap) return POVAR_OK;
+  if (world_ == 1) {
+    // POVAR_PEER_EXCHANGE=self: a single GPU runs the exchange protocol against its own buffer (tests on a
+    // one-GPU box; isolates the protocol's cost from the NVLink hop)
+    if (env == nullptr || std::strcmp(env, "self") != 0) return POVAR_OK;
+    PeerShared* ps = new PeerShared();
+    const size_t bytes = 16 * 2 * static_cast<size_t>(C_) * 12;
+    if (cudaMalloc(&ps->mem, bytes) != cudaSuccess || cudaMemset(ps->mem, 0, bytes) != cudaSuccess) {
+      delete ps;
+      return fail(POVAR_ERR_CUDA, "cudaMalloc failed for the self exchange buffer");
+    }
+    ps->px.recv[0] = static_cast<double*>(ps->mem);
+    ps->px.rank = 0;
+    ps->px.world = 1;
+    ps->ok = true;
+    peer_ = ps;
+    peer_owned_ = true;
+    peer_ok_ = true;
+    return POVAR_OK;
+  }
+  if (env != nullptr && std::strcmp(env, "self") == 0) env = nullptr;
   const std::string key = comm_key_ + ":" + std::to_string(C_);
   std::lock_guard<std::mutex> lock(comm_cache_mutex());
   auto& cache = peer_cache();

@@ -54,7 +54,7 @@ class Engine {
   int upload(const povar_problem_desc* desc);
   int allreduce(double* buf, size_t n);
   int setup_peer_exchange();
-  TermMode term_mode() const { return world_ == 1 ? kTermFused : (peer_ok_ ? kTermPeer : kTermRaw); }
+  TermMode term_mode() const { return peer_ok_ ? kTermPeer : (world_ == 1 ? kTermFused : kTermRaw); }
   const PeerExchange* next_exchange();   // one epoch per term launch, on every rank alike
   void set_model(bool joint, double alpha);
   int solve_power(bool joint, double lambda);
@@ -98,6 +98,7 @@ class Engine {
   PeerShared* peer_ = nullptr;
   std::string comm_key_;
   bool peer_ok_ = false;
+  bool peer_owned_ = false;       // POVAR_PEER_EXCHANGE=self: a private buffer, not the communicator's
   // host mirrors
   int C_ = 0, L_ = 0;
   long long nnz_ = 0;

@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <random>
 #include <string>
 #include <vector>
 
@@ -192,5 +193,100 @@ extern "C" int povar_bal_read(const char* path, povar_bal_data* out, char* err, 
   out->num_cams = static_cast<int32_t>(C);
   out->num_lms = static_cast<int32_t>(L);
   out->num_obs = N;
+  return POVAR_OK;
+}
+
+// --create-dataset: BalProblem::load_bal_varproj_space_matrix_write (bal_problem.cpp:306-471).  Reads an
+// original BAL file (C L N / N x (cam lm x y) / C x 9 / L x 3) and writes the 15-parameter file the
+// solver loads: same header and observation lines (`%d %d %lf %lf`, i.e. six decimals), per camera the
+// first two rows of the 3x4 matrix drawn from N(0,1) and the third row `0 0 0 1`, then f k1 k2 of the
+// input, then the landmark block copied through; one number per line, like the reference's fprintf
+// sequence.  The reference seeds std::mt19937 from std::random_device (seed < 0 here); with a seed the
+// output is reproducible.  Like the reference it draws 15 variates per camera from a fresh
+// std::normal_distribution and uses the first 8.
+extern "C" int povar_bal_create_dataset(const char* input, const char* output, int64_t seed, char* err,
+                                        size_t err_len) {
+  if (!input || !output) return POVAR_ERR_INVALID;
+  FILE* f = std::fopen(input, "rb");
+  if (!f) {
+    set_err(err, err_len, std::string("Could not open '") + input + "'");
+    return POVAR_ERR_IO;
+  }
+  std::fseek(f, 0, SEEK_END);
+  const long size = std::ftell(f);
+  std::fseek(f, 0, SEEK_SET);
+  std::vector<char> buf(static_cast<size_t>(size) + 1);
+  const size_t got = std::fread(buf.data(), 1, static_cast<size_t>(size), f);
+  std::fclose(f);
+  buf[got] = '\0';
+  Cursor cur{buf.data(), buf.data() + got};
+  long long C = 0, L = 0, N = 0;
+  if (!cur.next_int(&C) || !cur.next_int(&L) || !cur.next_int(&N) || C <= 0 || L <= 0 || N <= 0) {
+    set_err(err, err_len, std::string("Failed to parse header of '") + input + "'");
+    return POVAR_ERR_IO;
+  }
+  FILE* out = std::fopen(output, "w");
+  if (!out) {
+    set_err(err, err_len, std::string("Could not open '") + output + "' for writing");
+    return POVAR_ERR_IO;
+  }
+  std::vector<char> obuf(1 << 22);
+  std::setvbuf(out, obuf.data(), _IOFBF, obuf.size());
+  auto bail = [&](const std::string& msg, int code) {
+    std::fclose(out);
+    set_err(err, err_len, msg);
+    return code;
+  };
+  std::fprintf(out, "%lld %lld %lld", C, L, N);
+  // duplicate (cam, lm) pairs are fatal in the reference (CHECK(inserted), bal_problem.cpp:366)
+  std::vector<int32_t> cams(static_cast<size_t>(N)), lms(static_cast<size_t>(N));
+  for (long long i = 0; i < N; ++i) {
+    long long c = 0, l = 0;
+    double x = 0, y = 0;
+    if (!cur.next_int(&c) || !cur.next_int(&l) || !cur.next_double(&x) || !cur.next_double(&y)) {
+      return bail(std::string("Failed to parse observations of '") + input + "'", POVAR_ERR_IO);
+    }
+    if (c < 0 || c >= C || l < 0 || l >= L) {
+      return bail(std::string("Index out of range in '") + input + "'", POVAR_ERR_INVALID);
+    }
+    cams[i] = static_cast<int32_t>(c);
+    lms[i] = static_cast<int32_t>(l);
+    std::fprintf(out, "\n%lld %lld %lf %lf", c, l, x, y);
+  }
+  {
+    std::vector<int64_t> perm(static_cast<size_t>(N)), lm_ptr(static_cast<size_t>(L) + 1);
+    if (povar_canonical_order(static_cast<int32_t>(C), static_cast<int32_t>(L), N, cams.data(), lms.data(),
+                              perm.data(), lm_ptr.data()) != POVAR_OK) {
+      return bail(std::string("Invalid file '") + input + "' (duplicate observation)", POVAR_ERR_INVALID);
+    }
+  }
+  std::mt19937 gen;
+  if (seed < 0) {
+    std::random_device rd;
+    gen.seed(rd());
+  } else {
+    gen.seed(static_cast<std::mt19937::result_type>(seed));
+  }
+  for (long long i = 0; i < C; ++i) {
+    double p9[9];
+    for (double& v : p9) {
+      if (!cur.next_double(&v)) return bail(std::string("Failed to parse cameras of '") + input + "'", POVAR_ERR_IO);
+    }
+    std::normal_distribution<double> d(0, 1);
+    double draw[15];
+    for (double& v : draw) v = d(gen);
+    for (int m = 0; m < 8; ++m) std::fprintf(out, "\n%lf", draw[m]);
+    std::fprintf(out, "\n%lf\n%lf\n%lf\n%lf", 0.0, 0.0, 0.0, 1.0);
+    for (int m = 6; m < 9; ++m) std::fprintf(out, "\n%lf", p9[m]);
+  }
+  for (long long i = 0; i < 3 * L; ++i) {
+    double v;
+    if (!cur.next_double(&v)) return bail(std::string("Failed to parse landmarks of '") + input + "'", POVAR_ERR_IO);
+    std::fprintf(out, "\n%lf", v);
+  }
+  if (std::fclose(out) != 0) {
+    set_err(err, err_len, std::string("Failed to write '") + output + "'");
+    return POVAR_ERR_IO;
+  }
   return POVAR_OK;
 }

@@ -18,6 +18,8 @@
 #include <string>
 #include <vector>
 
+#include <sys/stat.h>
+
 #include "../../../include/povar_b200.h"
 
 namespace {
@@ -27,6 +29,7 @@ struct AppOptions {
   std::string log_path = "ba_log.json";
   int num_gpus = 1;
   bool create_dataset = false;
+  long long dataset_seed = -1;   // < 0: std::random_device, like the reference
   povar_options solver;
 };
 
@@ -44,7 +47,8 @@ int parse_enum(const std::string& flag, const std::string& v, const std::map<std
 void usage() {
   std::printf(
       "Solve BAL problem with solver determined by config (B200 build).\n\n"
-      "  --input <STR>\n  --create-dataset (not supported: use the reference or povar_b200.synthetic)\n"
+      "  --input <STR>\n  --create-dataset  write data_custom/<name> with randomised camera matrices and exit\n"
+      "  --create-dataset-seed <INT> (default: std::random_device, like the reference)\n"
       "  --num-gpus <INT>\n  --num-threads <INT> (ignored)\n"
       "  --solver-type-step-1 {POWER_VARPROJ,POWER_SCHUR_COMPLEMENT,POWER_BUNDLE_ADJUSTMENT,PCG,CHOLESKY}\n"
       "  --solver-type-step-2 {RIPOBA,RIPCG}\n  --power-sc-iterations <INT>\n"
@@ -83,6 +87,7 @@ AppOptions parse(int argc, char** argv) {
     } else if (f == "--input") o.input = val();
     else if (f == "--create-dataset") o.create_dataset = true;
     else if (f == "--no-create-dataset") o.create_dataset = false;
+    else if (f == "--create-dataset-seed") o.dataset_seed = std::atoll(val().c_str());
     else if (f == "--num-gpus") o.num_gpus = std::atoi(val().c_str());
     else if (f == "--num-threads") val();
     else if (f == "--solver-type-step-1") o.solver.solver_type_step_1 = parse_enum(f, val(), step1);
@@ -201,8 +206,14 @@ void write_log(const AppOptions& o, const povar_bal_data& data, const std::vecto
 int main(int argc, char** argv) {
   AppOptions o = parse(argc, argv);
   if (o.create_dataset) {
-    die("--create-dataset is outside the accelerated path: generate the data_custom file with the "
-        "reference or with `python -m povar_b200.synthetic` (SURVEY 8f)");
+    // bal_problem.cpp:306-319, 899-903: data_custom/<basename of the input>, then exit(0)
+    mkdir("data_custom", 0777);
+    const size_t slash = o.input.find_last_of('/');
+    const std::string out = "data_custom/" + (slash == std::string::npos ? o.input : o.input.substr(slash + 1));
+    char cerr[512] = {0};
+    if (povar_bal_create_dataset(o.input.c_str(), out.c_str(), o.dataset_seed, cerr, sizeof(cerr)) != POVAR_OK) die(cerr);
+    if (o.solver.verbosity_level >= 1) std::printf("Wrote '%s'\n", out.c_str());
+    return 0;
   }
 
   // fork the other ranks BEFORE any CUDA / NCCL call

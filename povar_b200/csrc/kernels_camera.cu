@@ -787,9 +787,37 @@ k_term16(int C, const double* __restrict__ raw_in, const int* __restrict__ cam_i
   __shared__ int is_last;
   const int lane16 = threadIdx.x & 15;
   const int base = (threadIdx.x & 31) & ~15;   // first lane of this half-warp
-  const int c_raw = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+  // Peer mode: a block waits for the sums its cameras get from the other ranks, i.e. for the peers'
+  // block with the same number.  Numbers are handed out in dispatch order (a counter, as in a
+  // decoupled look-back scan), so on every rank the lowest-numbered unfinished block is running and
+  // has already sent: the exchange makes progress even when the grid is larger than one wave.
+  unsigned int bid = blockIdx.x;
+  if (MODE == kTermPeer) {
+    __shared__ unsigned int s_bid;
+    if (threadIdx.x == 0) s_bid = atomicAdd(&ctl->next_block, 1u);
+    __syncthreads();
+    bid = s_bid;
+  }
+  const int c_raw = static_cast<int>((bid * blockDim.x + threadIdx.x) >> 4);
   const bool live = c_raw < C;
   const int c = live ? c_raw : C - 1;          // idle half-warps shadow the last camera (no stores)
+  // Everything that does not depend on the camera sums is requested first: these loads are in flight
+  // while the item partials are added and (sharded) while the peers' sums travel.
+  const double* s = pose_scale + 12 * static_cast<size_t>(c);
+  const double* Pc = P + 12 * static_cast<size_t>(c);
+  double sreg[12], preg[12], brow[12], aold[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) {
+    sreg[k] = s[k];
+    preg[k] = JOINT ? Pc[k] : 0.0;
+  }
+  {
+    const double* bi = Binv + 144 * static_cast<size_t>(c) + (lane16 < D ? lane16 : 0) * D;
+#pragma unroll
+    for (int j = 0; j < D; ++j) brow[j] = bi[j];
+#pragma unroll
+    for (int i = 0; i < D; ++i) aold[i] = acc[static_cast<size_t>(c) * D + i];
+  }
   double raw[12];
   if (MODE != kTermRaw) {
     double mine = 0.0;
@@ -803,28 +831,45 @@ k_term16(int C, const double* __restrict__ raw_in, const int* __restrict__ cam_i
       const size_t vec = static_cast<size_t>(C) * 12;
       const size_t mine_at = 2 * ((static_cast<size_t>(par) * px.world + px.rank) * vec + 12 * static_cast<size_t>(c) + lane16);
       if (live && lane16 < 12) {
-        for (int r = 0; r < px.world; ++r) st_tagged(px.recv[r] + mine_at, mine, px.epoch);
+#pragma unroll
+        for (int r = 0; r < kMaxPeers; ++r) {
+          if (r < px.world) st_tagged(px.recv[r] + mine_at, mine, px.epoch);
+        }
       }
-      // add the ranks' sums in rank order (the same bits on every rank), each as soon as it has arrived
+      // collect the ranks' sums (all polls of a round are in flight together), then add them in rank
+      // order: the same bits on every rank
       double sum = 0.0;
       if (live && lane16 < 12) {
         const double* rb = px.recv[px.rank] + 2 * (static_cast<size_t>(par) * px.world * vec + 12 * static_cast<size_t>(c) + lane16);
+        double v[kMaxPeers];
+        unsigned int pending = (1u << px.world) - 1u;
         long long t0 = 0;
         unsigned int spins = 0;
-        for (int r = 0; r < px.world; ++r) {
-          double v;
-          while (!ld_tagged(rb + 2 * r * vec, px.epoch, v)) {
-            if ((++spins & 1023u) == 0) {
-              const long long now = global_ns();
-              if (t0 == 0) t0 = now;
-              if (now - t0 > kPeerSpinNs) {
-                atomicExch(&ctl->peer_timeout, 1);
-                v = 0.0;
-                break;
+#pragma unroll
+        for (int r = 0; r < kMaxPeers; ++r) v[r] = 0.0;
+        while (pending != 0u) {
+#pragma unroll
+          for (int r = 0; r < kMaxPeers; ++r) {
+            if ((pending >> r) & 1u) {
+              double got;
+              if (ld_tagged(rb + 2 * r * vec, px.epoch, got)) {
+                v[r] = got;
+                pending &= ~(1u << r);
               }
             }
           }
-          sum += v;
+          if ((++spins & 1023u) == 0) {
+            const long long now = global_ns();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > kPeerSpinNs) {
+              atomicExch(&ctl->peer_timeout, 1);
+              break;
+            }
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < kMaxPeers; ++r) {
+          if (r < px.world) sum += v[r];
         }
       }
       __syncwarp();
@@ -836,31 +881,33 @@ k_term16(int C, const double* __restrict__ raw_in, const int* __restrict__ cam_i
 #pragma unroll
     for (int k = 0; k < 12; ++k) raw[k] = raw_in[12 * static_cast<size_t>(c) + k];
   }
-  const double* s = pose_scale + 12 * static_cast<size_t>(c);
-  const double* Pc = P + 12 * static_cast<size_t>(c);
   double e[12];
-  raw_to_reduced<JOINT>(raw, s, Pc, e);
+  raw_to_reduced<JOINT>(raw, sreg, preg, e);
   double ti = 0.0;
   if (lane16 < D) {
-    const double* bi = Binv + 144 * static_cast<size_t>(c) + lane16 * D;
-    for (int j = 0; j < D; ++j) ti += bi[j] * e[j];
+#pragma unroll
+    for (int j = 0; j < D; ++j) ti += brow[j] * e[j];
   }
   double t[12];
   double nt = 0.0, na = 0.0;
 #pragma unroll
   for (int i = 0; i < 12; ++i) t[i] = __shfl_sync(kFullMask, ti, base + i);
+#pragma unroll
   for (int i = 0; i < D; ++i) {
     nt += t[i] * t[i];
-    const double a = acc[static_cast<size_t>(c) * D + i] + t[i];
+    const double a = aold[i] + t[i];
     na += a * a;
   }
   __syncwarp();   // every lane has read accum before lane i overwrites entry i
   if (live && lane16 < D) {
-    acc[static_cast<size_t>(c) * D + lane16] += ti;
+    double mine_old = 0.0;
+#pragma unroll
+    for (int i = 0; i < D; ++i) mine_old = (i == lane16) ? aold[i] : mine_old;
+    acc[static_cast<size_t>(c) * D + lane16] = mine_old + ti;
     tmp[static_cast<size_t>(c) * D + lane16] = ti;
   }
   double yv[12];
-  reduced_to_y_values<JOINT>(t, s, Pc, yv);
+  reduced_to_y_values<JOINT>(t, sreg, preg, yv);
   if (live && lane16 < 12) {
     double mine = 0.0;
 #pragma unroll
@@ -886,6 +933,7 @@ k_term16(int C, const double* __restrict__ raw_in, const int* __restrict__ cam_i
   sum_norm_parts(C, norm_part, smem, s0, s1);
   if (threadIdx.x == 0) {
     ctl->ticket = 0;
+    ctl->next_block = 0;
     series_decide(s0, s1, term, eta, r_tolerance, ctl);
   }
 }
@@ -1125,17 +1173,6 @@ void launch_series_term(const DeviceState& d, bool joint, int term, double eta, 
   }
 #undef POVAR_TERM
   count(lc);
-}
-
-int series_term_peer_capacity(bool joint) {
-  int dev = 0, sms = 0, per_sm = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
-  const cudaError_t e = joint
-      ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_term16<true, kTermPeer>, kBlock, 0)
-      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_term16<false, kTermPeer>, kBlock, 0);
-  if (e != cudaSuccess) return 0;
-  return sms * per_sm;
 }
 
 void launch_e0_finish(const DeviceState& d, bool joint, double* out, const LaunchCfg& lc) {

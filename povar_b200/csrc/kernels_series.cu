@@ -371,13 +371,12 @@ k_e0_landmark_sell(DeviceIndex ix, const double* __restrict__ X, const double* _
 // completed with one exchange, and each lane accumulates its six entries of m (x) X.  The
 // landmark indices of the next trip are loaded before the records of this one are used.
 // ------------------------------------------------------------------------------------------
-template <bool JOINT, bool HASW>
-__global__ void __launch_bounds__(kBlock, 3)
+template <bool JOINT, bool HASW, int kSteps, int kOcc = (kSteps <= 2 ? 3 : 2)>
+__global__ void __launch_bounds__(kBlock, kOcc)
 k_passB_e0_v2(DeviceIndex ix, const double* __restrict__ P, const double* __restrict__ lm_rec,
               const double* __restrict__ csc_d, const double* __restrict__ csc_w, double c1, double c2,
               double* __restrict__ item_part, const SeriesCtl* __restrict__ ctl) {
   if (ctl != nullptr && ctl->done) return;
-  constexpr int kSteps = 2;   // steps in flight per trip
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= ix.num_items) return;
@@ -488,11 +487,14 @@ void launch_landmark_half(const DeviceState& d, const ModelParams& mp, const Ser
                           const LaunchCfg& lc) {
   if (d.ix.num_slices == 0 && d.ix.num_long == 0) return;
   // one wave of persistent-style blocks for the slices: 148 SMs x 4 resident blocks x 8 warps,
-  // contiguous slice ranges per warp (small problems: one range of 16 slices per warp); in front of
-  // them one warp per long landmark
+  // contiguous slice ranges per warp; in front of them one warp per long landmark.  Small problems and
+  // small shards (a venice-1778 shard on 8 GPUs has 15 k slices) keep the wave full with short ranges:
+  // a warp walks its rows one dependent gather after the other, so the launch lasts as long as the
+  // longest range (64 us for 16 slices, whatever the problem size).
   const long long full = 148LL * 4 * kWarps;
   long long per_warp = (d.ix.num_slices + full - 1) / full;
-  if (per_warp < 16) per_warp = 16;
+  static const int min_per_warp = getenv("POVAR_SELL_MIN_SLICES") ? atoi(getenv("POVAR_SELL_MIN_SLICES")) : 2;
+  if (per_warp < min_per_warp) per_warp = min_per_warp;
   const long long warps = (d.ix.num_slices + per_warp - 1) / per_warp;
   int blocks = static_cast<int>((warps + kWarps - 1) / kWarps);
   if (blocks > 148) blocks = (blocks + 147) / 148 * 148;   // whole multiples of 148: see the chunk map
@@ -542,16 +544,32 @@ void launch_passB_e0_v2(const DeviceState& d, const ModelParams& mp, bool joint,
   const int blocks = (d.ix.num_items + kWarps - 1) / kWarps;
   const SeriesCtl* ctl = in_series ? d.ctl : nullptr;
   const bool hasw = !joint && mp.robust_norm == NORM_HUBER;
-  if (joint) {
-    k_passB_e0_v2<true, false><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.lm_rec, d.csc_d, nullptr,
-                                                                 mp.c1, mp.c2, d.item_part, ctl);
+  // steps (of sixteen entries) a warp keeps in flight per trip: the pass is bound by the number of
+  // landmark records in flight (Little's law), registers permitting
+  static const int steps = getenv("POVAR_PASSB_STEPS") ? atoi(getenv("POVAR_PASSB_STEPS")) : 2;
+#define POVAR_PASSB(J, W, S, CD, CW)                                                                   \
+  k_passB_e0_v2<J, W, S><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.lm_rec, CD, CW, mp.c1, mp.c2, \
+                                                           d.item_part, ctl)
+  if (steps == 12) {   // two steps, four blocks per SM (64 registers)
+    if (joint) {
+      k_passB_e0_v2<true, false, 2, 4><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.lm_rec, d.csc_d, nullptr, mp.c1,
+                                                                         mp.c2, d.item_part, ctl);
+    } else {
+      k_passB_e0_v2<false, false, 2, 4><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.lm_rec, nullptr, nullptr,
+                                                                          mp.c1, mp.c2, d.item_part, ctl);
+    }
+  } else if (joint) {
+    if (steps >= 4) POVAR_PASSB(true, false, 4, d.csc_d, nullptr);
+    else if (steps == 3) POVAR_PASSB(true, false, 3, d.csc_d, nullptr);
+    else POVAR_PASSB(true, false, 2, d.csc_d, nullptr);
   } else if (hasw) {
-    k_passB_e0_v2<false, true><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.lm_rec, nullptr, d.csc_w,
-                                                                 mp.c1, mp.c2, d.item_part, ctl);
+    POVAR_PASSB(false, true, 2, nullptr, d.csc_w);
   } else {
-    k_passB_e0_v2<false, false><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.lm_rec, nullptr, nullptr,
-                                                                  mp.c1, mp.c2, d.item_part, ctl);
+    if (steps >= 4) POVAR_PASSB(false, false, 4, nullptr, nullptr);
+    else if (steps == 3) POVAR_PASSB(false, false, 3, nullptr, nullptr);
+    else POVAR_PASSB(false, false, 2, nullptr, nullptr);
   }
+#undef POVAR_PASSB
   count(lc);
 }
 

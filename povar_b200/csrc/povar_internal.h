@@ -62,7 +62,7 @@ struct SeriesCtl {
   double last_tmp_norm;
   double last_acc_norm;
   unsigned int ticket; // last-block election
-  unsigned int pad2;
+  unsigned int next_block;  // peer mode: logical block numbers in dispatch order
 };
 
 // Peer-memory exchange of the per-term camera sums when landmarks are sharded over several GPUs
@@ -192,9 +192,7 @@ void launch_series_start(const DeviceState& d, double r_tolerance, int max_terms
 // the NCCL all-reduce)
 void launch_series_term(const DeviceState& d, bool joint, int term, double eta, double r_tolerance,
                         TermMode mode, const PeerExchange* px, const LaunchCfg& lc);
-// most blocks of the peer-mode term kernel that can be resident at once on the current device (every
-// block waits for its peers' block of the same index, so the whole grid has to be resident)
-int series_term_peer_capacity(bool joint);
+
 void launch_finish_b(const DeviceState& d, bool joint, const LaunchCfg& lc);
 void launch_e0_finish(const DeviceState& d, bool joint, double* out, const LaunchCfg& lc);
 void launch_make_y(const DeviceState& d, bool joint, const double* x, double* y, const LaunchCfg& lc);

@@ -204,3 +204,19 @@ def test_full_size_short_solve_decreases_cost_and_is_reproducible(venice):
     assert all(b <= a for a, b in zip(runs[0][:k2], runs[0][1:k2]))      # logged cost is monotone per step
     assert all(b <= a for a, b in zip(runs[0][k2:], runs[0][k2 + 1:]))
     assert summary.power_terms > 0 and summary.power_series_time > 0
+
+
+def test_peer_exchange_protocol_on_one_gpu(monkeypatch):
+    """POVAR_PEER_EXCHANGE=self: the term kernel runs the peer-memory exchange (tagged 16-byte stores,
+    polling, dispatch-order block numbers) against its own buffer.  With one rank the sum has one term,
+    so the trace must be bit-identical to the plain single-GPU run."""
+    plain = _gpu_trace("small_povar")[1]
+    monkeypatch.setenv("POVAR_PEER_EXCHANGE", "self")
+    hp = capi.HostProblem.read(common.golden_file("small"))
+    meta = common.traces()["traces"]["small_povar"]
+    s = capi.Solver(hp, capi.default_options(verbosity_level=0, **common.flags_to_options(meta["flags"])))
+    assert s.peer_exchange_active()
+    its, _ = s.bundle_adjust()
+    s.close()
+    assert [e.cost for e in its] == [e.cost for e in plain]
+    assert [e.linear_solver_iterations for e in its] == [e.linear_solver_iterations for e in plain]

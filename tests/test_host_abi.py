@@ -152,3 +152,72 @@ def test_bal_binary_refuses_to_run_without_a_gpu():
                          capture_output=True, text=True)
     assert res.returncode != 0
     assert "no CUDA device" in res.stderr
+
+
+# ---------------------------------------------------------------------------------------------
+# --create-dataset: BAL file (9 parameters per camera) -> the 15-parameter file the solver loads
+# (bal/bal_problem.cpp:306-471), compared with the reference program's own output
+# ---------------------------------------------------------------------------------------------
+def _write_bal9(path, sp, rng):
+    with open(path, "w") as f:
+        f.write(f"{sp.num_cams} {sp.num_lms} {sp.num_obs}\n")
+        for c, l, (x, y) in zip(sp.obs_cam, sp.obs_lm, sp.obs_xy):
+            f.write(f"{c} {l}     {x:.10e} {y:.10e}\n")
+        cams = rng.normal(size=(sp.num_cams, 9))
+        cams[:, 6] = 1000.0 + rng.normal(size=sp.num_cams)
+        cams[:, 7:] *= 1e-7
+        for v in cams.reshape(-1):
+            f.write(f"{v:.16e}\n")
+        for v in sp.points.reshape(-1):
+            f.write(f"{v:.16e}\n")
+    return cams
+
+
+def test_create_dataset_writes_the_reference_format(tmp_path):
+    import subprocess
+    from povar_b200 import build, synthetic
+    rng = np.random.default_rng(7)
+    sp = synthetic.generate_named("small")
+    src = tmp_path / "problem-16-400-pre.txt"
+    cams9 = _write_bal9(src, sp, rng)
+    ours = tmp_path / "ours"
+    ours.mkdir()
+    res = subprocess.run([build.BAL, "--input", str(src), "--create-dataset", "--create-dataset-seed", "11"],
+                         cwd=ours, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    out = ours / "data_custom" / src.name
+    tok = out.read_text().split()
+    C, L, N = sp.num_cams, sp.num_lms, sp.num_obs
+    assert [int(t) for t in tok[:3]] == [C, L, N]
+    assert len(tok) == 3 + 4 * N + 15 * C + 3 * L
+    obs = np.array(tok[3:3 + 4 * N], dtype=np.float64).reshape(N, 4)
+    assert np.array_equal(obs[:, 0], sp.obs_cam) and np.array_equal(obs[:, 1], sp.obs_lm)
+    assert np.allclose(obs[:, 2:], sp.obs_xy, rtol=0, atol=5.1e-7)          # %lf: six decimals
+    cam = np.array(tok[3 + 4 * N:3 + 4 * N + 15 * C], dtype=np.float64).reshape(C, 15)
+    assert np.array_equal(cam[:, 8:12], np.tile([0.0, 0.0, 0.0, 1.0], (C, 1)))
+    assert np.allclose(cam[:, 12:], cams9[:, 6:], rtol=0, atol=5.1e-7)
+    draws = cam[:, :8].reshape(-1)
+    assert abs(draws.mean()) < 0.2 and 0.8 < draws.std() < 1.2              # N(0, 1)
+    # reproducible with a seed, and loadable by the solver's reader
+    again = tmp_path / "again.txt"
+    capi.create_dataset(str(src), str(again), seed=11)
+    assert again.read_bytes() == out.read_bytes()
+    hp = capi.HostProblem.read(str(out))
+    assert (hp.num_cams, hp.num_lms, hp.num_obs) == (C, L, N)
+    # the reference program on the same input: identical text except for the random draws
+    ref_bin = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "bal_ref")
+    if not os.path.exists(ref_bin):
+        pytest.skip("oracle/_ref/bal_ref not built")
+    theirs = tmp_path / "theirs"
+    theirs.mkdir()
+    res = subprocess.run([ref_bin, "--input", str(src), "--create-dataset"], cwd=theirs, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-500:]
+    a = out.read_text().split("\n")
+    b = (theirs / "data_custom" / src.name).read_text().split("\n")
+    assert len(a) == len(b) or (len(a) == len(b) + 1 and a[-1] == "") or (len(b) == len(a) + 1 and b[-1] == "")
+    first_cam = 1 + N
+    for i in range(min(len(a), len(b))):
+        k = i - first_cam
+        if 0 <= k < 15 * C and k % 15 < 8:
+            continue                                                         # a random matrix entry
+        assert a[i] == b[i], (i, a[i], b[i])
