@@ -281,6 +281,13 @@ int povar_bench_power_kernels(povar_handle* h, int32_t which, int32_t reps, doub
 /* kernels launched by this handle since creation (bench.py's gpu_launches) */
 int64_t povar_launch_count(const povar_handle* h);
 
+/* host-side sliced-ELL order of the landmark half of the E0 product, exposed for the CPU tests:
+ * call with NULL outputs to get sizes = {len(slice_ptr), len(sell_lm), len(long_lms)}, then again with buffers.
+ * `threads` > 0 fixes the number of host threads (the result must not depend on it), 0 = automatic. */
+int povar_debug_sell_layout(int32_t num_cams, int32_t num_lms, const int64_t* lm_ptr, const int32_t* obs_cam,
+                            int32_t threads, int32_t* slice_ptr, int32_t* sell_lm, int32_t* long_lms,
+                            int64_t sizes[3]);
+
 /* 1 if this handle exchanges the per-term camera sums over peer memory (CUDA IPC + NVLink stores fused
  * into the term kernel), 0 if it uses ncclAllReduce per term (single GPU: 0).  POVAR_PEER_EXCHANGE=0 in
  * the environment forces NCCL, =1 makes povar_create fail instead of falling back. */

@@ -138,6 +138,9 @@ SIGNATURES = {
     "povar_launch_count": (C.c_int64, [_H]),
     "povar_bal_create_dataset": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int64, C.c_char_p, C.c_size_t]),
     "povar_peer_exchange_active": (C.c_int, [_H]),
+    "povar_debug_sell_layout": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.c_int32,
+                                          C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                          C.POINTER(C.c_int64)]),
     "povar_cuda_stream": (C.c_void_p, [_H]),
 }
 
@@ -410,6 +413,24 @@ class Solver:
 
     def launch_count(self) -> int:
         return int(self.lib.povar_launch_count(self.h))
+
+
+def sell_layout(hp: "HostProblem", threads: int = 0):
+    """(slice_ptr, sell_lm, long_lms) of the sliced-ELL landmark order povar_create builds for `hp`."""
+    lib = load()
+    sizes = (C.c_int64 * 3)()
+    lp = np.ascontiguousarray(hp.lm_ptr, dtype=np.int64)
+    oc = np.ascontiguousarray(hp.obs_cam, dtype=np.int32)
+    args = (hp.num_cams, hp.num_lms, lp.ctypes.data_as(C.POINTER(C.c_int64)), oc.ctypes.data_as(C.POINTER(C.c_int32)),
+            threads)
+    rc = lib.povar_debug_sell_layout(*args, None, None, None, sizes)
+    if rc != OK:
+        raise PovarError(rc, "povar_debug_sell_layout failed")
+    out = [np.zeros(max(int(n), 1), dtype=np.int32) for n in sizes]
+    rc = lib.povar_debug_sell_layout(*args, *[a.ctypes.data_as(C.POINTER(C.c_int32)) for a in out], sizes)
+    if rc != OK:
+        raise PovarError(rc, "povar_debug_sell_layout failed")
+    return tuple(a[:int(n)] for a, n in zip(out, sizes))
 
 
 def create_dataset(src: str, dst: str, seed: int = -1) -> None:

@@ -2,6 +2,9 @@
 #include <cstring>
 #include <string>
 
+#include <algorithm>
+#include <vector>
+
 #include "engine.h"
 
 namespace povar {
@@ -187,6 +190,25 @@ int povar_bench_power_kernels(povar_handle* h, int32_t which, int32_t reps, doub
 int64_t povar_launch_count(const povar_handle* h) {
   if (!h || !h->engine) return 0;
   return h->engine->launches();
+}
+
+int povar_debug_sell_layout(int32_t num_cams, int32_t num_lms, const int64_t* lm_ptr, const int32_t* obs_cam,
+                            int32_t threads, int32_t* slice_ptr, int32_t* sell_lm, int32_t* long_lms,
+                            int64_t sizes[3]) {
+  if (num_cams <= 0 || num_lms < 0 || !lm_ptr || !sizes) return POVAR_ERR_INVALID;
+  std::vector<int> lp(static_cast<size_t>(num_lms) + 1);
+  for (int32_t l = 0; l <= num_lms; ++l) lp[l] = static_cast<int>(lm_ptr[l]);
+  povar::SellLayout sell;
+  povar::set_host_threads_override(threads);
+  povar::build_sell(lp, obs_cam, num_cams, povar::kSellWindow, &sell);
+  povar::set_host_threads_override(0);
+  sizes[0] = static_cast<int64_t>(sell.slice_ptr.size());
+  sizes[1] = static_cast<int64_t>(sell.sell_lm.size());
+  sizes[2] = static_cast<int64_t>(sell.long_lms.size());
+  if (slice_ptr) std::copy(sell.slice_ptr.begin(), sell.slice_ptr.end(), slice_ptr);
+  if (sell_lm) std::copy(sell.sell_lm.begin(), sell.sell_lm.end(), sell_lm);
+  if (long_lms) std::copy(sell.long_lms.begin(), sell.long_lms.end(), long_lms);
+  return POVAR_OK;
 }
 
 int povar_peer_exchange_active(const povar_handle* h) {

@@ -18,6 +18,7 @@
 #include <map>
 #include <mutex>
 #include <numeric>
+#include <thread>
 
 namespace povar {
 
@@ -128,6 +129,32 @@ int nccl_unique_id(uint8_t id[128], std::string* err) {
 // ---------------------------------------------------------------------------------------------
 // host-side index construction
 // ---------------------------------------------------------------------------------------------
+// Static chunking over a few host threads: povar_create walks the observation list a handful of times
+// (validation, per-camera counts, sliced-ELL order) and at 5e6 observations a single thread spends more
+// on that than the GPU on ten LM iterations.  Results never depend on the thread count.
+static int g_host_threads_override = 0;   // povar_debug_sell_layout: tests compare thread counts
+void set_host_threads_override(int n) { g_host_threads_override = n; }
+static int host_threads(long long work) {
+  static const int forced = getenv("POVAR_HOST_THREADS") ? atoi(getenv("POVAR_HOST_THREADS")) : 0;
+  if (g_host_threads_override > 0) return g_host_threads_override;
+  if (forced > 0) return forced;
+  if (work < (1 << 18)) return 1;
+  const unsigned hw = std::thread::hardware_concurrency();
+  return static_cast<int>(std::min<unsigned>(hw == 0 ? 1 : hw, 16));
+}
+template <typename F>
+static void parallel_chunks(int chunks, F&& body) {   // body(chunk index)
+  if (chunks <= 1) {
+    body(0);
+    return;
+  }
+  std::vector<std::thread> pool;
+  pool.reserve(chunks - 1);
+  for (int t = 1; t < chunks; ++t) pool.emplace_back([&body, t] { body(t); });
+  body(0);
+  for (auto& th : pool) th.join();
+}
+
 // Tiles of the landmark-sorted observation array: runs of whole landmarks with <= 32
 // observations together, or a single landmark with more than 32.
 void build_tiles(const std::vector<int>& lm_ptr, std::vector<int>* tile_ptr) {
@@ -170,45 +197,72 @@ void build_sell(const std::vector<int>& lm_ptr, const int* obs_cam, int num_cams
   out->slice_ptr.assign(1, 0);
   out->sell_lm.clear();
   out->long_lms.clear();
-  // landmarks with 1..32 observations by median camera
-  std::vector<int> by_cam;
-  {
-    std::vector<int> bucket(static_cast<size_t>(num_cams) + 1, 0);
-    auto key = [&](int l) { return obs_cam[(lm_ptr[l] + lm_ptr[l + 1]) / 2]; };
-    for (int l = 0; l < L; ++l) {
+  out->rows = 0;
+  if (L <= 0) return;
+  const int T = host_threads(L);
+  auto chunk_begin = [&](int t) { return static_cast<int>(static_cast<long long>(L) * t / T); };
+  auto key = [&](int l) { return obs_cam[(lm_ptr[l] + lm_ptr[l + 1]) / 2]; };
+  // landmarks with 1..32 observations by median camera: stable counting sort, one histogram per chunk
+  // (chunk t's landmarks of a camera go after those of the chunks before it)
+  std::vector<std::vector<int>> hist(T, std::vector<int>(static_cast<size_t>(num_cams), 0));
+  std::vector<std::vector<int>> longs(T);
+  parallel_chunks(T, [&](int t) {
+    std::vector<int>& h = hist[t];
+    for (int l = chunk_begin(t); l < chunk_begin(t + 1); ++l) {
       const int deg = lm_ptr[l + 1] - lm_ptr[l];
-      if (deg > 32) out->long_lms.push_back(l);
-      else if (deg > 0) bucket[key(l) + 1]++;
+      if (deg > 32) longs[t].push_back(l);
+      else if (deg > 0) h[key(l)]++;
     }
-    for (int c = 0; c < num_cams; ++c) bucket[c + 1] += bucket[c];
-    by_cam.resize(bucket[num_cams]);
-    for (int l = 0; l < L; ++l) {
-      const int deg = lm_ptr[l + 1] - lm_ptr[l];
-      if (deg > 0 && deg <= 32) by_cam[bucket[key(l)]++] = l;
+  });
+  for (int t = 0; t < T; ++t) out->long_lms.insert(out->long_lms.end(), longs[t].begin(), longs[t].end());
+  int n = 0;
+  for (int c = 0; c < num_cams; ++c) {
+    for (int t = 0; t < T; ++t) {
+      const int cnt = hist[t][c];
+      hist[t][c] = n;   // first position of chunk t's landmarks with median camera c
+      n += cnt;
     }
   }
-  const int n = static_cast<int>(by_cam.size());
-  out->sell_lm.reserve(static_cast<size_t>(n) + 8);
-  int rows = 0;
-  int head[34];
-  std::vector<int> order(window);
-  for (int w0 = 0; w0 < n; w0 += window) {
-    const int w1 = std::min(n, w0 + window);
-    // stable counting sort by descending degree
-    for (int k = 0; k < 34; ++k) head[k] = 0;
-    for (int i = w0; i < w1; ++i) head[32 - (lm_ptr[by_cam[i] + 1] - lm_ptr[by_cam[i]]) + 1]++;
-    for (int k = 0; k < 33; ++k) head[k + 1] += head[k];
-    for (int i = w0; i < w1; ++i) order[head[32 - (lm_ptr[by_cam[i] + 1] - lm_ptr[by_cam[i]])]++] = by_cam[i];
-    const int cnt = w1 - w0;
-    for (int i = 0; i < cnt; i += 8) {
-      const int len = lm_ptr[order[i] + 1] - lm_ptr[order[i]];
-      for (int g = 0; g < 8; ++g) {
-        const int l = i + g < cnt ? order[i + g] : -1;
-        out->sell_lm.push_back(l);
-      }
-      rows += len;
-      out->slice_ptr.push_back(rows);
+  std::vector<int> by_cam(static_cast<size_t>(n));
+  parallel_chunks(T, [&](int t) {
+    std::vector<int>& h = hist[t];
+    for (int l = chunk_begin(t); l < chunk_begin(t + 1); ++l) {
+      const int deg = lm_ptr[l + 1] - lm_ptr[l];
+      if (deg > 0 && deg <= 32) by_cam[h[key(l)]++] = l;
     }
+  });
+  // windows of `window` landmarks of that order, each sorted (stably) by descending degree and cut into
+  // slices of eight: the windows are independent, and where a window's slices go is known up front
+  const int num_windows = (n + window - 1) / window;
+  const int slices_per_full = (window + 7) / 8;
+  const int last_cnt = n - (num_windows - 1) * window;
+  const int num_slices = num_windows == 0 ? 0 : (num_windows - 1) * slices_per_full + (last_cnt + 7) / 8;
+  out->sell_lm.assign(static_cast<size_t>(num_slices) * 8, -1);
+  std::vector<int> slice_len(static_cast<size_t>(num_slices), 0);
+  parallel_chunks(T, [&](int t) {
+    int head[34];
+    std::vector<int> order(window);
+    const int wb = static_cast<int>(static_cast<long long>(num_windows) * t / T);
+    const int we = static_cast<int>(static_cast<long long>(num_windows) * (t + 1) / T);
+    for (int w = wb; w < we; ++w) {
+      const int w0 = w * window, w1 = std::min(n, w0 + window);
+      for (int k = 0; k < 34; ++k) head[k] = 0;
+      for (int i = w0; i < w1; ++i) head[32 - (lm_ptr[by_cam[i] + 1] - lm_ptr[by_cam[i]]) + 1]++;
+      for (int k = 0; k < 33; ++k) head[k + 1] += head[k];
+      for (int i = w0; i < w1; ++i) order[head[32 - (lm_ptr[by_cam[i] + 1] - lm_ptr[by_cam[i]])]++] = by_cam[i];
+      const int cnt = w1 - w0;
+      int sl = w * slices_per_full;
+      for (int i = 0; i < cnt; i += 8, ++sl) {
+        slice_len[sl] = lm_ptr[order[i] + 1] - lm_ptr[order[i]];   // the largest degree of the slice
+        for (int g = 0; g < 8 && i + g < cnt; ++g) out->sell_lm[static_cast<size_t>(sl) * 8 + g] = order[i + g];
+      }
+    }
+  });
+  out->slice_ptr.resize(static_cast<size_t>(num_slices) + 1);
+  int rows = 0;
+  for (int sl = 0; sl < num_slices; ++sl) {
+    rows += slice_len[sl];
+    out->slice_ptr[sl + 1] = rows;
   }
   out->rows = rows;
 }
@@ -391,26 +445,60 @@ int Engine::upload(const povar_problem_desc* desc) {
   nnz_ = nnz;
   // ---- host: validation, per-camera counts and the small tables (one pass over the observations);
   // everything per observation is built on the device (kernels_index.cu)
+  static const bool trace = getenv("POVAR_TRACE_CREATE") != nullptr;   // phase times of povar_create on stderr
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!trace) return;
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "povar_create: %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+    t_prev = now;
+  };
   std::vector<int> lm_ptr(L + 1), cam_ptr(C + 1, 0);
   if (desc->lm_ptr[0] != 0 || desc->lm_ptr[L] != nnz) return fail(POVAR_ERR_INVALID, "lm_ptr does not span the observations");
-  for (int l = 0; l < L; ++l) {
-    const int64_t b = desc->lm_ptr[l], e = desc->lm_ptr[l + 1];
-    if (e < b) return fail(POVAR_ERR_INVALID, "lm_ptr is not monotone");
-    lm_ptr[l] = static_cast<int>(b);
-    for (int64_t o = b; o < e; ++o) {
-      const int c = desc->obs_cam[o];
-      if (c < 0 || c >= C) return fail(POVAR_ERR_INVALID, "camera index out of range");
-      if (o > b && desc->obs_cam[o - 1] >= c) return fail(POVAR_ERR_INVALID, "observations of a landmark must have strictly ascending camera indices");
-      cam_ptr[c + 1]++;
+  {
+    const int T = host_threads(nnz);
+    std::vector<std::vector<int>> counts(T, std::vector<int>(static_cast<size_t>(C), 0));
+    std::vector<const char*> bad(T, nullptr);
+    parallel_chunks(T, [&](int t) {
+      std::vector<int>& cnt = counts[t];
+      const int l0 = static_cast<int>(static_cast<long long>(L) * t / T);
+      const int l1 = static_cast<int>(static_cast<long long>(L) * (t + 1) / T);
+      for (int l = l0; l < l1; ++l) {
+        const int64_t b = desc->lm_ptr[l], e = desc->lm_ptr[l + 1];
+        if (e < b || b < 0 || e > nnz) {
+          bad[t] = "lm_ptr is not monotone";
+          return;
+        }
+        lm_ptr[l] = static_cast<int>(b);
+        for (int64_t o = b; o < e; ++o) {
+          const int c = desc->obs_cam[o];
+          if (c < 0 || c >= C) {
+            bad[t] = "camera index out of range";
+            return;
+          }
+          if (o > b && desc->obs_cam[o - 1] >= c) {
+            bad[t] = "observations of a landmark must have strictly ascending camera indices";
+            return;
+          }
+          cnt[c]++;
+        }
+      }
+    });
+    for (int t = 0; t < T; ++t) {
+      if (bad[t]) return fail(POVAR_ERR_INVALID, bad[t]);
+      for (int c = 0; c < C; ++c) cam_ptr[c + 1] += counts[t][c];
     }
   }
   lm_ptr[L] = nnz;
   for (int c = 0; c < C; ++c) cam_ptr[c + 1] += cam_ptr[c];
+  lap("validate + camera counts");
   std::vector<int> tile_ptr, item_ptr, item_cam, cam_item_ptr;
   build_tiles(lm_ptr, &tile_ptr);
   build_items(cam_ptr, choose_item_len(nnz), &item_ptr, &item_cam, &cam_item_ptr);
+  lap("tiles + items");
   SellLayout sell;
   build_sell(lm_ptr, desc->obs_cam, C, kSellWindow, &sell);
+  lap("sliced-ELL order");
   if (static_cast<long long>(sell.rows) * 8 >= (1LL << 31)) {
     return fail(POVAR_ERR_UNSUPPORTED, "sliced-ELL layout exceeds 2^31 slots in one shard");
   }
@@ -515,8 +603,10 @@ int Engine::upload(const povar_problem_desc* desc) {
   PV_ALLOC(d_.ctl, 1);
   PV_UP(d_.P, desc->cam_P, sizeof(double) * C12);
 #undef PV_UP
+  lap("allocate + enqueue uploads");
   // the host tables above live on this stack frame
   PV_CUDA(cudaStreamSynchronize(stream_));
+  lap("device index build + sync");
   return POVAR_OK;
 }
 
@@ -1153,15 +1243,14 @@ int Engine::get_state(int which, double* cam_P, double* lms) {
   PV_CUDA(cudaSetDevice(device_));
   PV_CUDA(cudaStreamSynchronize(stream_));
   if (cam_P) PV_CUDA(cudaMemcpy(cam_P, d_.P, sizeof(double) * static_cast<size_t>(C_) * 12, cudaMemcpyDeviceToHost));
-  if (lms) {
-    std::vector<double> h(static_cast<size_t>(L_) * 4);
-    PV_CUDA(cudaMemcpy(h.data(), d_.X, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
+  if (lms && L_ > 0) {
+    // straight into the caller's buffer (no staging vector: its page faults cost more than the copy);
+    // step-1 landmarks are [x y z 1] on the device and [x y z] for the caller: a pitched copy drops w
     if (which == POVAR_STATE_JOINT) {
-      std::memcpy(lms, h.data(), sizeof(double) * h.size());
+      PV_CUDA(cudaMemcpy(lms, d_.X, sizeof(double) * 4 * static_cast<size_t>(L_), cudaMemcpyDeviceToHost));
     } else {
-      for (int l = 0; l < L_; ++l) {
-        for (int k = 0; k < 3; ++k) lms[3 * static_cast<size_t>(l) + k] = h[4 * static_cast<size_t>(l) + k];
-      }
+      PV_CUDA(cudaMemcpy2D(lms, 3 * sizeof(double), d_.X, 4 * sizeof(double), 3 * sizeof(double),
+                           static_cast<size_t>(L_), cudaMemcpyDeviceToHost));
     }
   }
   return POVAR_OK;

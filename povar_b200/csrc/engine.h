@@ -110,6 +110,7 @@ struct SellLayout {
   std::vector<int> long_lms;    // landmarks with more than 32 observations
   int rows = 0;
 };
+void set_host_threads_override(int n);   // 0 = automatic
 void build_sell(const std::vector<int>& lm_ptr, const int* obs_cam, int num_cams, int window,
                 SellLayout* out);
 

@@ -221,3 +221,33 @@ def test_create_dataset_writes_the_reference_format(tmp_path):
         if 0 <= k < 15 * C and k % 15 < 8:
             continue                                                         # a random matrix entry
         assert a[i] == b[i], (i, a[i], b[i])
+
+
+def _sell_reference(hp, window=128):
+    """The sliced-ELL rule restated with numpy sorts (engine.cu build_sell): landmarks with 1..32 observations
+    in the order of their median camera (stable), windows of `window`, inside a window stable by descending
+    degree, eight landmarks per slice, slice length = the largest degree in it."""
+    deg = np.diff(hp.lm_ptr)
+    ok = np.nonzero((deg > 0) & (deg <= 32))[0]
+    med = hp.obs_cam[(hp.lm_ptr[ok] + hp.lm_ptr[ok + 1]) // 2]
+    by_cam = ok[np.argsort(med, kind="stable")]
+    slice_ptr, sell_lm = [0], []
+    for w0 in range(0, len(by_cam), window):
+        win = by_cam[w0:w0 + window]
+        order = win[np.argsort(-deg[win], kind="stable")]
+        for i in range(0, len(order), 8):
+            grp = list(order[i:i + 8])
+            sell_lm += grp + [-1] * (8 - len(grp))
+            slice_ptr.append(slice_ptr[-1] + int(deg[order[i]]))
+    return np.array(slice_ptr), np.array(sell_lm), np.nonzero(deg > 32)[0]
+
+
+@pytest.mark.parametrize("shape", ["small", "ladybug49", "trafalgar257"])
+def test_sliced_ell_order_matches_its_rule_for_any_thread_count(shape):
+    sp = synthetic.generate_named(shape)
+    hp = capi.HostProblem.from_unordered(sp.num_cams, sp.num_lms, sp.obs_cam, sp.obs_lm, sp.obs_xy, sp.cam_params)
+    ref = _sell_reference(hp)
+    for threads in (1, 3, 8):
+        got = capi.sell_layout(hp, threads)
+        for a, b in zip(got, ref):
+            assert np.array_equal(a, b), (shape, threads)
