@@ -265,11 +265,17 @@ def main():
     trials = 0
     terms = 0
     series_t = 0.0
+    phase_keys = ("residual_evaluation_time", "jacobian_evaluation_time", "prepare_time",
+                  "solve_reduced_system_time", "back_substitution_time", "iteration_time")
+    phases = dict.fromkeys(phase_keys, 0.0)
     for _ in range(args.steps):
         its, summ = resident_step()
         trials += len(its)
         terms += summ.power_terms
         series_t += summ.power_series_time
+        for e in its:
+            for k in phase_keys:
+                phases[k] += getattr(e, k)
     ev1.record(hstream)
     barrier()
     t_res_host = time.perf_counter() - t0
@@ -394,6 +400,8 @@ def main():
         "step1_lm_iterations": step1_trials, "final_cost": final_cost,
         "power_terms_per_solve": terms / args.steps,
         "power_series_ms_per_term": 1e3 * series_t / max(terms, 1),
+        # device time of the phases of a solve (CUDA events inside the library, rank 0), like the reference's log
+        "phase_ms_per_solve": {k.replace("_time", ""): 1e3 * v / args.steps for k, v in phases.items()},
         "e2e": {"value": e2e_trials / t_e2e, "unit": "LM iterations/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "solve_s": t_e2e / args.steps},
         "gpu_launches": int(launches),

@@ -63,8 +63,11 @@ def _run(cmd, verbose):
     return res
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, defines=(), suffix: str = "") -> str:
+    """`defines` / `suffix`: tuning builds (-D... into lib/libpovar_b200<suffix>.so, selected with POVAR_LIB)."""
     nvcc = _nvcc()
+    if suffix:
+        return _build_variant(nvcc, list(defines), suffix, verbose)
     os.makedirs(OBJ, exist_ok=True)
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
     os.makedirs(os.path.dirname(BAL), exist_ok=True)
@@ -92,6 +95,24 @@ def build(force: bool = False, verbose: bool = False) -> str:
                                       "-lpovar_b200", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../lib"],
              verbose)
     return LIB
+
+
+def _build_variant(nvcc, defines, suffix, verbose):
+    obj_dir = OBJ + suffix
+    os.makedirs(obj_dir, exist_ok=True)
+    lib = LIB.replace(".so", suffix + ".so")
+    sources = [s for s in LIB_SOURCES if os.path.exists(os.path.join(CSRC, s))]
+
+    def compile_one(src):
+        obj = os.path.join(obj_dir, src.replace("/", "_") + ".o")
+        _run([nvcc] + ARCH + COMMON + ["-D" + d for d in defines] + ["-x", "cu", "-Xptxas", "-warn-spills", "-c",
+                                                                    os.path.join(CSRC, src), "-o", obj], verbose)
+        return obj
+
+    with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(sources))) as ex:
+        objs = list(ex.map(compile_one, sources))
+    _run([nvcc] + ARCH + ["-shared", "-o", lib] + objs + ["-ldl"], verbose)
+    return lib
 
 
 if __name__ == "__main__":

@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpovar_b200.so")
+# POVAR_LIB: a tuning build of the same library (povar_b200.build.build(defines=..., suffix=...))
+LIB_PATH = os.environ.get("POVAR_LIB") or os.path.join(_HERE, "lib", "libpovar_b200.so")
 
 # status codes / enums (include/povar_b200.h)
 OK = 0

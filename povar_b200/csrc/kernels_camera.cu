@@ -55,7 +55,12 @@ __device__ __forceinline__ void load_rec(const double* __restrict__ rec, int lm,
 // KIND 1 (KRON_SDIAG): E_i = W^2 K_i^T N_i K_i,  N_i = Jl_i Hll^-1 Jl_i^T (scaled, tangent-projected
 //                      in step 2)                  -> diagonal blocks of sum_l Hpl Hll^-1 Hlp
 template <bool JOINT, int KIND>
-__global__ void __launch_bounds__(kBlock)
+#ifdef POVAR_OCC_KRON
+#define POVAR_BOUNDS_KRON __launch_bounds__(kBlock, POVAR_OCC_KRON)
+#else
+#define POVAR_BOUNDS_KRON __launch_bounds__(kBlock)
+#endif
+__global__ void POVAR_BOUNDS_KRON
 k_kron(DeviceIndex ix, const double* __restrict__ P, const double* __restrict__ X, double c1,
        double c2, Robust rb, const double* __restrict__ lm_scale, const double* __restrict__ hll_inv,
        double* __restrict__ item_kron, double* __restrict__ csc_d, double* __restrict__ csc_w) {

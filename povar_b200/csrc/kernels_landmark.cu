@@ -23,6 +23,18 @@ namespace povar {
 namespace {
 
 constexpr int kBlock = 256;
+// minimum resident blocks per SM the register allocator has to leave room for (tuning knobs; the
+// defaults are the measured optimum on B200, profiles/)
+#ifdef POVAR_OCC_LIN
+#define POVAR_BOUNDS_LIN __launch_bounds__(kBlock, POVAR_OCC_LIN)
+#else
+#define POVAR_BOUNDS_LIN __launch_bounds__(kBlock)
+#endif
+#ifdef POVAR_OCC_BACKSUB
+#define POVAR_BOUNDS_BACKSUB __launch_bounds__(kBlock, POVAR_OCC_BACKSUB)
+#else
+#define POVAR_BOUNDS_BACKSUB __launch_bounds__(kBlock)
+#endif
 
 __device__ __forceinline__ void load_lm4(const double* __restrict__ X, int lm, double (&x)[4]) {
   load4(X + 4 * static_cast<size_t>(lm), x);
@@ -211,7 +223,7 @@ k_scalar_final(int nblocks, const double* __restrict__ part, double* out) {
 // linearisation, landmark side: sum_i w Jl_raw^T Jl_raw, sum_i w Jl_raw^T r, column scales
 // ------------------------------------------------------------------------------------------
 template <bool JOINT>
-__global__ void __launch_bounds__(kBlock)
+__global__ void POVAR_BOUNDS_LIN
 k_lin_landmark(DeviceIndex ix, const double* __restrict__ P, const double* __restrict__ X,
                double c1, double c2, Robust rb, double eps, int scale_jl,
                double* __restrict__ lm_hraw, double* __restrict__ lm_graw,
@@ -556,7 +568,7 @@ k_e0_landmark(DeviceIndex ix, const double* __restrict__ P, const double* __rest
 // VarPro (landmark_block.hpp:670-707): cameras are ALREADY updated (P), P_old is the backup.
 // Fresh raw Jp/Jl/res at (P, X_old); stored scaled Jl and r are those of the linearisation
 // (P_old, X_old, weights, lm_scale).  `inc` is the scaled-space pose increment.
-__global__ void __launch_bounds__(kBlock)
+__global__ void POVAR_BOUNDS_BACKSUB
 k_backsub_varpro(DeviceIndex ix, const double* __restrict__ P, const double* __restrict__ P_old,
                  double* __restrict__ X, const double* __restrict__ inc, double c1, double c2,
                  Robust rb, const double* __restrict__ lm_scale, double* __restrict__ scalar_part) {
@@ -734,7 +746,7 @@ k_backsub_poba(DeviceIndex ix, const double* __restrict__ P, double* __restrict_
 }
 
 // joint (landmark_block.hpp:574-623): y = pose_scale o (Pi_c inc11)
-__global__ void __launch_bounds__(kBlock)
+__global__ void POVAR_BOUNDS_BACKSUB
 k_backsub_joint(DeviceIndex ix, const double* __restrict__ P, double* __restrict__ X,
                 const double* __restrict__ y, Robust rb, const double* __restrict__ lm_scale,
                 const double* __restrict__ hll_inv, double* __restrict__ scalar_part) {
