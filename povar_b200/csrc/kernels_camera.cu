@@ -54,6 +54,128 @@ __device__ __forceinline__ void load_rec(const double* __restrict__ rec, int lm,
 // KIND 0 (KRON_HPP):   E_i = W K_i^T K_i            -> Jp^T Jp
 // KIND 1 (KRON_SDIAG): E_i = W^2 K_i^T N_i K_i,  N_i = Jl_i Hll^-1 Jl_i^T (scaled, tangent-projected
 //                      in step 2)                  -> diagonal blocks of sum_l Hpl Hll^-1 Hlp
+// factors of one camera-major entry e: E[6] (packed symmetric 3x3) and Y[10] = packed X X^T
+template <bool JOINT, int KIND>
+__device__ __forceinline__ void kron_factors(const DeviceIndex& ix, int e, const Cam3x4& cam,
+                                             const double* __restrict__ X, double c1, double c2, const Robust& rb,
+                                             const double* __restrict__ lm_scale,
+                                             const double* __restrict__ hll_inv, double* __restrict__ csc_d,
+                                             double* __restrict__ csc_w, double (&E)[6], double (&Y)[10]) {
+  const int lm = __ldg(ix.csc_lm + e);
+  const double2 uv = ix.csc_uv[e];
+  double x[4];
+  load4(X + 4 * static_cast<size_t>(lm), x);
+  if (KIND == KRON_SDIAG) {
+    double sl[4], inv[6];
+    load4(lm_scale + 4 * static_cast<size_t>(lm), sl);
+    {
+      const double* hi = hll_inv + 6 * static_cast<size_t>(lm);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) inv[k] = hi[k];
+    }
+    if (JOINT) {
+      JointObs ob;
+      ob.eval(cam, uv.x, uv.y, x, rb);
+      double j0[4], j1[4];
+      ob.jl_rows(cam, j0, j1);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        j0[k] *= sl[k];
+        j1[k] *= sl[k];
+      }
+      Reflector<4> pi;
+      pi.make(x);
+      double t0[3], t1[3], v0[3], v1[3];
+      pi.apply_t(j0, t0);             // rows of Jl_t = (Jl_raw o scale) Pi_l
+      pi.apply_t(j1, t1);
+      sym3_mul(inv, t0, v0);
+      sym3_mul(inv, t1, v1);
+      const double n00 = t0[0] * v0[0] + t0[1] * v0[1] + t0[2] * v0[2];
+      const double n01 = t0[0] * v1[0] + t0[1] * v1[1] + t0[2] * v1[2];
+      const double n11 = t1[0] * v1[0] + t1[1] * v1[1] + t1[2] * v1[2];
+      const double w2 = ob.sw * ob.sw * ob.sw * ob.sw;
+      // E = w^2 d^T N d with d = [[iz 0 d02],[0 iz d12]]
+      const double a0 = n00 * ob.d02 + n01 * ob.d12, a1 = n01 * ob.d02 + n11 * ob.d12;
+      E[0] = w2 * ob.iz * ob.iz * n00;
+      E[1] = w2 * ob.iz * ob.iz * n01;
+      E[2] = w2 * ob.iz * a0;
+      E[3] = w2 * ob.iz * ob.iz * n11;
+      E[4] = w2 * ob.iz * a1;
+      E[5] = w2 * (ob.d02 * a0 + ob.d12 * a1);
+    } else {
+      PoseObs ob;
+      ob.eval(cam, uv.x, uv.y, x, c1, c2, rb);
+      double Z[4][3], V[4][3], N[4][4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) Z[q][k] = ob.T[q][k] * sl[k];
+        sym3_mul(inv, Z[q], V[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) N[q][r] = Z[q][0] * V[r][0] + Z[q][1] * V[r][1] + Z[q][2] * V[r][2];
+      }
+      // K rows: c1 (1 0 -u), c1 (0 1 -v), c2 (1 0 0), c2 (0 1 0);  E = w^2 K^T N K
+      const double K[4][3] = {{c1, 0.0, -c1 * uv.x}, {0.0, c1, -c1 * uv.y}, {c2, 0.0, 0.0}, {0.0, c2, 0.0}};
+      double G[4][3];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          G[q][k] = N[q][0] * K[0][k] + N[q][1] * K[1][k] + N[q][2] * K[2][k] + N[q][3] * K[3][k];
+        }
+      }
+      const double w2 = ob.sw * ob.sw * ob.sw * ob.sw;
+      int n = 0;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int b2 = a; b2 < 3; ++b2) {
+          E[n++] = w2 * (K[0][a] * G[0][b2] + K[1][a] * G[1][b2] + K[2][a] * G[2][b2] + K[3][a] * G[3][b2]);
+        }
+      }
+    }
+  } else if (JOINT) {
+    JointObs ob;
+    ob.eval(cam, uv.x, uv.y, x, rb);
+    const double w = ob.sw * ob.sw;
+    if (csc_d != nullptr) {
+      double* dp = csc_d + 3 * static_cast<size_t>(e);
+      dp[0] = ob.sw * ob.iz;
+      dp[1] = ob.sw * ob.d02;
+      dp[2] = ob.sw * ob.d12;
+    }
+    E[0] = w * ob.iz * ob.iz;
+    E[1] = 0.0;
+    E[2] = w * ob.iz * ob.d02;
+    E[3] = E[0];
+    E[4] = w * ob.iz * ob.d12;
+    E[5] = w * (ob.d02 * ob.d02 + ob.d12 * ob.d12);
+  } else {
+    PoseObs ob;
+    ob.eval(cam, uv.x, uv.y, x, c1, c2, rb);
+    const double w = ob.sw * ob.sw;
+    if (csc_w != nullptr) csc_w[e] = w;
+    const double a = c1 * c1, bq = c2 * c2;
+    E[0] = w * (a + bq);
+    E[1] = 0.0;
+    E[2] = -w * a * uv.x;
+    E[3] = E[0];
+    E[4] = -w * a * uv.y;
+    E[5] = w * a * (uv.x * uv.x + uv.y * uv.y);
+  }
+  {
+    int n = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int j = i; j < 4; ++j) Y[n++] = x[i] * x[j];
+    }
+  }
+}
+
 template <bool JOINT, int KIND>
 #ifdef POVAR_OCC_KRON
 #define POVAR_BOUNDS_KRON __launch_bounds__(kBlock, POVAR_OCC_KRON)
@@ -75,121 +197,8 @@ k_kron(DeviceIndex ix, const double* __restrict__ P, const double* __restrict__ 
 #pragma unroll
   for (int k = 0; k < kKron; ++k) acc[k] = 0.0;
   for (int e = eb + lane; e < ee; e += 32) {
-    const int lm = __ldg(ix.csc_lm + e);
-    const double2 uv = ix.csc_uv[e];
-    double x[4];
-    load4(X + 4 * static_cast<size_t>(lm), x);
-    double E[6];
-    if (KIND == KRON_SDIAG) {
-      double sl[4], inv[6];
-      load4(lm_scale + 4 * static_cast<size_t>(lm), sl);
-      {
-        const double* hi = hll_inv + 6 * static_cast<size_t>(lm);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) inv[k] = hi[k];
-      }
-      if (JOINT) {
-        JointObs ob;
-        ob.eval(cam, uv.x, uv.y, x, rb);
-        double j0[4], j1[4];
-        ob.jl_rows(cam, j0, j1);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          j0[k] *= sl[k];
-          j1[k] *= sl[k];
-        }
-        Reflector<4> pi;
-        pi.make(x);
-        double t0[3], t1[3], v0[3], v1[3];
-        pi.apply_t(j0, t0);             // rows of Jl_t = (Jl_raw o scale) Pi_l
-        pi.apply_t(j1, t1);
-        sym3_mul(inv, t0, v0);
-        sym3_mul(inv, t1, v1);
-        const double n00 = t0[0] * v0[0] + t0[1] * v0[1] + t0[2] * v0[2];
-        const double n01 = t0[0] * v1[0] + t0[1] * v1[1] + t0[2] * v1[2];
-        const double n11 = t1[0] * v1[0] + t1[1] * v1[1] + t1[2] * v1[2];
-        const double w2 = ob.sw * ob.sw * ob.sw * ob.sw;
-        // E = w^2 d^T N d with d = [[iz 0 d02],[0 iz d12]]
-        const double a0 = n00 * ob.d02 + n01 * ob.d12, a1 = n01 * ob.d02 + n11 * ob.d12;
-        E[0] = w2 * ob.iz * ob.iz * n00;
-        E[1] = w2 * ob.iz * ob.iz * n01;
-        E[2] = w2 * ob.iz * a0;
-        E[3] = w2 * ob.iz * ob.iz * n11;
-        E[4] = w2 * ob.iz * a1;
-        E[5] = w2 * (ob.d02 * a0 + ob.d12 * a1);
-      } else {
-        PoseObs ob;
-        ob.eval(cam, uv.x, uv.y, x, c1, c2, rb);
-        double Z[4][3], V[4][3], N[4][4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-#pragma unroll
-          for (int k = 0; k < 3; ++k) Z[q][k] = ob.T[q][k] * sl[k];
-          sym3_mul(inv, Z[q], V[q]);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-#pragma unroll
-          for (int r = 0; r < 4; ++r) N[q][r] = Z[q][0] * V[r][0] + Z[q][1] * V[r][1] + Z[q][2] * V[r][2];
-        }
-        // K rows: c1 (1 0 -u), c1 (0 1 -v), c2 (1 0 0), c2 (0 1 0);  E = w^2 K^T N K
-        const double K[4][3] = {{c1, 0.0, -c1 * uv.x}, {0.0, c1, -c1 * uv.y}, {c2, 0.0, 0.0}, {0.0, c2, 0.0}};
-        double G[4][3];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-#pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            G[q][k] = N[q][0] * K[0][k] + N[q][1] * K[1][k] + N[q][2] * K[2][k] + N[q][3] * K[3][k];
-          }
-        }
-        const double w2 = ob.sw * ob.sw * ob.sw * ob.sw;
-        int n = 0;
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-#pragma unroll
-          for (int b2 = a; b2 < 3; ++b2) {
-            E[n++] = w2 * (K[0][a] * G[0][b2] + K[1][a] * G[1][b2] + K[2][a] * G[2][b2] + K[3][a] * G[3][b2]);
-          }
-        }
-      }
-    } else if (JOINT) {
-      JointObs ob;
-      ob.eval(cam, uv.x, uv.y, x, rb);
-      const double w = ob.sw * ob.sw;
-      if (csc_d != nullptr) {
-        double* dp = csc_d + 3 * static_cast<size_t>(e);
-        dp[0] = ob.sw * ob.iz;
-        dp[1] = ob.sw * ob.d02;
-        dp[2] = ob.sw * ob.d12;
-      }
-      E[0] = w * ob.iz * ob.iz;
-      E[1] = 0.0;
-      E[2] = w * ob.iz * ob.d02;
-      E[3] = E[0];
-      E[4] = w * ob.iz * ob.d12;
-      E[5] = w * (ob.d02 * ob.d02 + ob.d12 * ob.d12);
-    } else {
-      PoseObs ob;
-      ob.eval(cam, uv.x, uv.y, x, c1, c2, rb);
-      const double w = ob.sw * ob.sw;
-      if (csc_w != nullptr) csc_w[e] = w;
-      const double a = c1 * c1, bq = c2 * c2;
-      E[0] = w * (a + bq);
-      E[1] = 0.0;
-      E[2] = -w * a * uv.x;
-      E[3] = E[0];
-      E[4] = -w * a * uv.y;
-      E[5] = w * a * (uv.x * uv.x + uv.y * uv.y);
-    }
-    double Y[10];
-    {
-      int n = 0;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-#pragma unroll
-        for (int j = i; j < 4; ++j) Y[n++] = x[i] * x[j];
-      }
-    }
+    double E[6], Y[10];
+    kron_factors<JOINT, KIND>(ix, e, cam, X, c1, c2, rb, lm_scale, hll_inv, csc_d, csc_w, E, Y);
 #pragma unroll
     for (int a = 0; a < 6; ++a) {
 #pragma unroll
@@ -201,6 +210,80 @@ k_kron(DeviceIndex ix, const double* __restrict__ P, const double* __restrict__ 
     double* out = item_kron + kKron * static_cast<size_t>(warp);
 #pragma unroll
     for (int k = 0; k < kKron; ++k) out[k] = acc[k];
+  }
+}
+
+// The same sums on the FP64 tensor cores.  Per camera the 6 x 10 block is a contraction over the
+// observations, sum_i E_i (x) Y_i = [E_1 .. E_n] [Y_1 .. Y_n]^T: each lane makes the factors of one entry,
+// the warp transposes them through shared memory into DMMA fragments (m8n8k4: A = E^T, 8 x 4 entries with
+// rows 6..7 zero; B = Y, 4 entries x 8, two column tiles for the 10 entries of X X^T) and eight k-steps
+// consume the 32 entries.  Four accumulator registers per lane instead of 60 (the one-lane-one-entry
+// kernel above runs at one block per SM), and no 60-value warp reduction at the end.
+__device__ __forceinline__ void dmma_m8n8k4(double (&d)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(d[0]), "+d"(d[1])
+               : "d"(a), "d"(b));
+}
+
+constexpr int kKronWarps = 4;   // warps per block of k_kron_mma: 6 KB of staging each
+
+template <bool JOINT, int KIND>
+__global__ void __launch_bounds__(32 * kKronWarps)
+k_kron_mma(DeviceIndex ix, const double* __restrict__ P, const double* __restrict__ X, double c1,
+           double c2, Robust rb, const double* __restrict__ lm_scale, const double* __restrict__ hll_inv,
+           double* __restrict__ item_kron, double* __restrict__ csc_d, double* __restrict__ csc_w) {
+  __shared__ __align__(16) double stage[kKronWarps][3][32][8];   // [E | Y 0..7 | Y 8..9] per entry
+  const int wib = threadIdx.x >> 5;
+  const int warp = blockIdx.x * kKronWarps + wib;
+  const int lane = threadIdx.x & 31;
+  if (warp >= ix.num_items) return;
+  const int c = __ldg(ix.item_cam + warp);
+  const int eb = __ldg(ix.item_ptr + warp), ee = __ldg(ix.item_ptr + warp + 1);
+  Cam3x4 cam;
+  load_cam(P, c, cam);
+  double (*sE)[8] = stage[wib][0];
+  double (*sY0)[8] = stage[wib][1];
+  double (*sY1)[8] = stage[wib][2];
+  // the padding never changes
+  sE[lane][6] = sE[lane][7] = 0.0;
+#pragma unroll
+  for (int k = 2; k < 8; ++k) sY1[lane][k] = 0.0;
+  double d0[2] = {0.0, 0.0}, d1[2] = {0.0, 0.0};
+  const int fr = lane >> 2, fk = lane & 3;   // fragment row (A) / column (B), k index inside a step
+  for (int e0 = eb; e0 < ee; e0 += 32) {
+    const int e = e0 + lane;
+    double E[6], Y[10];
+    if (e < ee) {
+      kron_factors<JOINT, KIND>(ix, e, cam, X, c1, c2, rb, lm_scale, hll_inv, csc_d, csc_w, E, Y);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) E[k] = 0.0;
+#pragma unroll
+      for (int k = 0; k < 10; ++k) Y[k] = 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k += 2) *reinterpret_cast<double2*>(&sE[lane][k]) = make_double2(E[k], E[k + 1]);
+#pragma unroll
+    for (int k = 0; k < 8; k += 2) *reinterpret_cast<double2*>(&sY0[lane][k]) = make_double2(Y[k], Y[k + 1]);
+    *reinterpret_cast<double2*>(&sY1[lane][0]) = make_double2(Y[8], Y[9]);
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const double a = sE[4 * j + fk][fr];
+      dmma_m8n8k4(d0, a, sY0[4 * j + fk][fr]);
+      dmma_m8n8k4(d1, a, sY1[4 * j + fk][fr]);
+    }
+    __syncwarp();
+  }
+  // C fragment: row fr = entry of E, columns 2 fk, 2 fk + 1 of the tile
+  if (fr < 6) {
+    double* out = item_kron + kKron * static_cast<size_t>(warp) + 10 * fr;
+    out[2 * fk] = d0[0];
+    out[2 * fk + 1] = d0[1];
+    if (fk == 0) {
+      out[8] = d1[0];
+      out[9] = d1[1];
+    }
   }
 }
 
@@ -1038,25 +1121,34 @@ k_block_matvec(int C, int D, const double* __restrict__ blocks, const double* __
 void launch_kron(const DeviceState& d, const ModelParams& mp, bool joint, KronKind kind,
                  const LaunchCfg& lc) {
   const Robust rb = {mp.robust_norm, mp.huber};
-  const int blocks = item_grid(d);
-  if (kind == KRON_HPP) {
-    if (joint) {
-      k_kron<true, KRON_HPP><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.X, mp.c1, mp.c2, rb, d.lm_scale,
-                                                               d.hll_inv, d.item_kron, d.csc_d, nullptr);
+  // POVAR_KRON=v1: one entry per lane with 60 accumulators (A/B runs); default: FP64 tensor cores
+  static const bool v1 = getenv("POVAR_KRON") != nullptr && std::strcmp(getenv("POVAR_KRON"), "v1") == 0;
+  const int blocks = v1 ? item_grid(d) : (d.ix.num_items + kKronWarps - 1) / kKronWarps;
+  const int threads = v1 ? kBlock : 32 * kKronWarps;
+  if (blocks == 0) return;
+  double* cw = (!joint && kind == KRON_HPP && mp.robust_norm == NORM_HUBER) ? d.csc_w : nullptr;
+  double* cd = (joint && kind == KRON_HPP) ? d.csc_d : nullptr;
+#define POVAR_KRON_LAUNCH(K, J, KIND)                                                                     \
+  K<J, KIND><<<blocks, threads, 0, lc.stream>>>(d.ix, d.P, d.X, mp.c1, mp.c2, rb, d.lm_scale, d.hll_inv, \
+                                                d.item_kron, cd, cw)
+  if (v1) {
+    if (kind == KRON_HPP) {
+      if (joint) POVAR_KRON_LAUNCH(k_kron, true, KRON_HPP);
+      else POVAR_KRON_LAUNCH(k_kron, false, KRON_HPP);
     } else {
-      k_kron<false, KRON_HPP><<<blocks, kBlock, 0, lc.stream>>>(
-          d.ix, d.P, d.X, mp.c1, mp.c2, rb, d.lm_scale, d.hll_inv, d.item_kron, nullptr,
-          mp.robust_norm == NORM_HUBER ? d.csc_w : nullptr);
+      if (joint) POVAR_KRON_LAUNCH(k_kron, true, KRON_SDIAG);
+      else POVAR_KRON_LAUNCH(k_kron, false, KRON_SDIAG);
     }
   } else {
-    if (joint) {
-      k_kron<true, KRON_SDIAG><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.X, mp.c1, mp.c2, rb, d.lm_scale,
-                                                                 d.hll_inv, d.item_kron, nullptr, nullptr);
+    if (kind == KRON_HPP) {
+      if (joint) POVAR_KRON_LAUNCH(k_kron_mma, true, KRON_HPP);
+      else POVAR_KRON_LAUNCH(k_kron_mma, false, KRON_HPP);
     } else {
-      k_kron<false, KRON_SDIAG><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.X, mp.c1, mp.c2, rb, d.lm_scale,
-                                                                  d.hll_inv, d.item_kron, nullptr, nullptr);
+      if (joint) POVAR_KRON_LAUNCH(k_kron_mma, true, KRON_SDIAG);
+      else POVAR_KRON_LAUNCH(k_kron_mma, false, KRON_SDIAG);
     }
   }
+#undef POVAR_KRON_LAUNCH
   count(lc);
 }
 
