@@ -33,5 +33,6 @@ else:
         s.solve_joint(1e-4)
         which = capi.STATE_JOINT
     k = s.bench_power_kernels(which, reps)
-    print("kernel us:", [round(1e6 * v, 1) for v in k])
+    print("kernel us:", [round(1e6 * float(v), 1) for v in k], "| term in sequence us:",
+          round(1e6 * s.bench_power_terms(which, 2 * reps), 1))
 s.close()
