@@ -64,3 +64,27 @@ def test_two_gpu_shards_reproduce_single_gpu_trace(name, exchange, tmp_path):
     for i in range(min(n, k2 + 6)):
         assert abs(its[i].cost - r0["cost"][i]) <= 1e-9 * abs(its[i].cost)
     assert r0["lm_end"] == r1["lm_begin"] and r1["lm_end"] == hp.num_lms
+
+
+def test_bal_binary_with_two_gpus(tmp_path):
+    """`bal --num-gpus 2` (forked ranks, NCCL id through pipes, peer exchange between the two processes) writes the
+    same trace as the single-GPU binary, up to summation order."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import json
+    import subprocess
+    from povar_b200 import build
+    meta = common.traces()["traces"]["small_povar"]
+    logs = []
+    for n in (1, 2):
+        log = tmp_path / f"ba_log_{n}.json"
+        res = subprocess.run([build.BAL, "--input", common.golden_file("small"), "--alpha", "0.1",
+                              "--power-sc-iterations", "20", "--num-gpus", str(n), "--verbosity-level", "0",
+                              "--log-log-path", str(log)], capture_output=True, text=True, timeout=300)
+        assert res.returncode == 0, res.stderr[-2000:]
+        logs.append(json.loads(log.read_text()))
+    common.assert_trace_close(meta, logs[1]["cost"], logs[1]["step_is_successful"],
+                              logs[1]["linear_solver_iterations"], label="bal x2")
+    k2 = common.step2_start(meta["threads1"]["iteration"])
+    for i in range(min(k2 + 6, len(logs[0]["cost"]), len(logs[1]["cost"]))):
+        assert abs(logs[0]["cost"][i] - logs[1]["cost"][i]) <= 1e-9 * abs(logs[0]["cost"][i])
