@@ -644,6 +644,11 @@ int Engine::setup_peer_exchange() {
   const char* env = getenv("POVAR_PEER_EXCHANGE");
   if (env != nullptr && std::strcmp(env, "0") == 0) return POVAR_OK;
   if (world_ > kMaxPeers || C_ <= 0) return POVAR_OK;
+  {
+    // POVAR_PEER_ALLREDUCE=0: only the per-term exchange uses the peer buffers, the other reductions NCCL
+    const char* small = getenv("POVAR_PEER_ALLREDUCE");
+    peer_small_ = !(small != nullptr && std::strcmp(small, "0") == 0);
+  }
   if (world_ == 1) {
     // POVAR_PEER_EXCHANGE=self: a single GPU runs the exchange protocol against its own buffer (tests on a
     // one-GPU box; isolates the protocol's cost from the NVLink hop)
@@ -657,6 +662,7 @@ int Engine::setup_peer_exchange() {
     ps->px.recv[0] = static_cast<double*>(ps->mem);
     ps->px.rank = 0;
     ps->px.world = 1;
+    ps->px.stride = static_cast<unsigned long long>(C_) * 12;
     ps->ok = true;
     peer_ = ps;
     peer_owned_ = true;
@@ -679,8 +685,9 @@ int Engine::setup_peer_exchange() {
   PeerShared* ps = new PeerShared();
   cache[key] = ps;
   peer_ = ps;
-  // 16-byte tagged slots, [2 parities][world][C*12]; zero = "exchange 0", never waited for
-  const size_t recv_pad = 16 * 2 * static_cast<size_t>(world_) * C_ * 12;
+  // 16-byte tagged slots, [2 parities][world][60*C]; zero = "exchange 0", never waited for
+  const size_t stride = static_cast<size_t>(C_) * kKron;
+  const size_t recv_pad = 16 * 2 * static_cast<size_t>(world_) * stride;
   const size_t flag_bytes = 0;
   unsigned int ok = 1;
   cudaIpcMemHandle_t mine{};
@@ -747,6 +754,7 @@ int Engine::setup_peer_exchange() {
   }
   ps->px.rank = rank_;
   ps->px.world = world_;
+  ps->px.stride = stride;
   ps->ok = true;
   peer_ok_ = true;
   return POVAR_OK;
@@ -760,6 +768,10 @@ const PeerExchange* Engine::next_exchange() {
 
 int Engine::allreduce(double* buf, size_t n) {
   if (world_ <= 1) return POVAR_OK;
+  if (peer_ok_ && n <= peer_->px.stride && peer_small_) {
+    launch_peer_allreduce(d_, buf, n, *next_exchange(), lc());
+    return POVAR_OK;
+  }
   // ncclDouble = 8, ncclSum = 0
   const int rc = nccl_->AllReduce(buf, buf, n, 8, 0, nccl_comm_, stream_);
   if (rc != 0) return fail(POVAR_ERR_NCCL, "ncclAllReduce failed");

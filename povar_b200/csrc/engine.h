@@ -98,6 +98,7 @@ class Engine {
   PeerShared* peer_ = nullptr;
   std::string comm_key_;
   bool peer_ok_ = false;
+  bool peer_small_ = true;        // cost scalars, b, Kronecker sums ... also go over the peer buffers
   bool peer_owned_ = false;       // POVAR_PEER_EXCHANGE=self: a private buffer, not the communicator's
   // host mirrors
   int C_ = 0, L_ = 0;

@@ -914,9 +914,9 @@ k_term16(int C, const double* __restrict__ raw_in, const int* __restrict__ cam_i
       for (int it = cam_item_ptr[c]; it < ie; ++it) mine += item_part[static_cast<size_t>(it) * 12 + lane16];
     }
     if (MODE == kTermPeer) {
-      // slots are 16 bytes (2 doubles wide): [parity][source rank][C*12]
+      // slots are 16 bytes (2 doubles wide): [parity][source rank][stride], the first 12*C of a rank used here
       const int par = static_cast<int>(px.epoch & 1u);
-      const size_t vec = static_cast<size_t>(C) * 12;
+      const size_t vec = static_cast<size_t>(px.stride);
       const size_t mine_at = 2 * ((static_cast<size_t>(par) * px.world + px.rank) * vec + 12 * static_cast<size_t>(c) + lane16);
       if (live && lane16 < 12) {
 #pragma unroll
@@ -1036,7 +1036,6 @@ k_series_start(int C, const double* __restrict__ norm_part, double r_tolerance, 
     ctl->done = max_terms > 0 ? 0 : 1;
     ctl->iterations = max_terms > 0 ? max_terms : 0;   // "Maximum number of iterations reached."
     ctl->nonfinite = isfinite(s1) ? 0 : 1;
-    ctl->peer_timeout = 0;
     ctl->norm0 = r_tolerance > 0 ? sqrt(s0) : 0.0;
     ctl->last_tmp_norm = sqrt(s0);
     ctl->last_acc_norm = sqrt(s1);
@@ -1246,6 +1245,68 @@ void launch_finish_b(const DeviceState& d, bool joint, const LaunchCfg& lc) {
 
 void launch_series_start(const DeviceState& d, double r_tolerance, int max_terms, const LaunchCfg& lc) {
   k_series_start<<<1, kBlock, 0, lc.stream>>>(d.ix.C, d.norm_part, r_tolerance, max_terms, d.ctl);
+  count(lc);
+}
+
+// The same exchange for any vector of up to px.stride doubles (cost scalars, l_diff, flags, b, the Kronecker
+// sums): element i is pushed to every rank and collected from every rank by one thread; a thread only waits
+// for the thread with the same index on the other ranks, which pushes before it polls, so the one-wave
+// grid-stride launch cannot deadlock.
+__global__ void __launch_bounds__(kBlock)
+k_peer_allreduce(double* __restrict__ buf, size_t n, PeerExchange px, SeriesCtl* ctl) {
+  const int par = static_cast<int>(px.epoch & 1u);
+  const size_t stride = static_cast<size_t>(px.stride);
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const double mine = buf[i];
+    const size_t at = 2 * ((static_cast<size_t>(par) * px.world + px.rank) * stride + i);
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r) {
+      if (r < px.world) st_tagged(px.recv[r] + at, mine, px.epoch);
+    }
+    const double* rb = px.recv[px.rank] + 2 * (static_cast<size_t>(par) * px.world * stride + i);
+    double v[kMaxPeers];
+    unsigned int pending = (1u << px.world) - 1u;
+    long long t0 = 0;
+    unsigned int spins = 0;
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r) v[r] = 0.0;
+    while (pending != 0u) {
+#pragma unroll
+      for (int r = 0; r < kMaxPeers; ++r) {
+        if ((pending >> r) & 1u) {
+          double got;
+          if (ld_tagged(rb + 2 * r * stride, px.epoch, got)) {
+            v[r] = got;
+            pending &= ~(1u << r);
+          }
+        }
+      }
+      if ((++spins & 1023u) == 0) {
+        const long long now = global_ns();
+        if (t0 == 0) t0 = now;
+        if (now - t0 > kPeerSpinNs) {
+          atomicExch(&ctl->peer_timeout, 1);
+          break;
+        }
+      }
+    }
+    double sum = 0.0;
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r) {
+      if (r < px.world) sum += v[r];
+    }
+    // a peer that never answered: poison the result so that the caller's finiteness checks trip
+    buf[i] = pending != 0u ? __longlong_as_double(0x7ff8000000000000LL) : sum;
+  }
+}
+
+void launch_peer_allreduce(const DeviceState& d, double* buf, size_t n, const PeerExchange& px,
+                           const LaunchCfg& lc) {
+  if (n == 0) return;
+  size_t blocks = (n + kBlock - 1) / kBlock;
+  if (blocks > 148 * 2) blocks = 148 * 2;   // one wave, always resident
+  k_peer_allreduce<<<static_cast<int>(blocks), kBlock, 0, lc.stream>>>(buf, n, px, d.ctl);
   count(lc);
 }
 

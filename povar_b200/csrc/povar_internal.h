@@ -67,13 +67,17 @@ struct SeriesCtl {
 
 // Peer-memory exchange of the per-term camera sums when landmarks are sharded over several GPUs
 // (engine.cu Engine::setup_peer_exchange, kernels_camera.cu k_term16<.., kTermPeer>).  Every rank owns
-// a receive buffer [2 parities][world][C*12] of 16-byte slots {lo, epoch, hi, epoch}; recv[r] is rank r's
-// buffer as mapped into this process (CUDA IPC over NVLink; recv[rank] is the local one).
+// a receive buffer [2 parities][world][stride] of 16-byte slots {lo, epoch, hi, epoch}; recv[r] is rank r's
+// buffer as mapped into this process (CUDA IPC over NVLink; recv[rank] is the local one).  stride = 60*C
+// slots: the largest camera-sized vector that is reduced (the Kronecker sums); the per-term exchange uses the
+// first 12*C of them, scalar reductions the first few.
 constexpr int kMaxPeers = 8;
 struct PeerExchange {
   double* recv[kMaxPeers];
   int rank, world;
   unsigned int epoch;   // number of this exchange (> 0); parity = epoch & 1
+  unsigned int pad;
+  unsigned long long stride;
 };
 // where k_term16 takes the reduced camera sums from
 enum TermMode { kTermRaw = 0, kTermFused = 1, kTermPeer = 2 };
@@ -193,6 +197,9 @@ void launch_series_start(const DeviceState& d, double r_tolerance, int max_terms
 void launch_series_term(const DeviceState& d, bool joint, int term, double eta, double r_tolerance,
                         TermMode mode, const PeerExchange* px, const LaunchCfg& lc);
 
+// buf[0..n) += the other ranks' buf, over the peer buffers (n <= px.stride): what ncclAllReduce(sum) would do,
+// every rank adding in rank order
+void launch_peer_allreduce(const DeviceState& d, double* buf, size_t n, const PeerExchange& px, const LaunchCfg& lc);
 void launch_finish_b(const DeviceState& d, bool joint, const LaunchCfg& lc);
 void launch_e0_finish(const DeviceState& d, bool joint, double* out, const LaunchCfg& lc);
 void launch_make_y(const DeviceState& d, bool joint, const double* x, double* y, const LaunchCfg& lc);
