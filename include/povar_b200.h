@@ -256,6 +256,21 @@ typedef struct povar_solve_summary {
 int povar_bundle_adjust(povar_handle* h, const povar_options* opt, povar_iteration* iterations,
                         int32_t max_iterations, povar_solve_summary* summary);
 
+/* ba_log.json with the reference's complete key set (bal/ba_log.hpp:85-245, bal/ba_log_utils.cpp:100-175), so that
+ * the reference's python/rootba tooling loads it unchanged; what `bal --log-log-path` writes.  lm_ptr may be NULL
+ * (then per_lm_obs is zero).  Host only. */
+typedef struct povar_ba_log_info {
+  const char* input_path;
+  int32_t num_cams;
+  int32_t num_lms;
+  int64_t num_obs;
+  const int64_t* lm_ptr;     /* [num_lms+1] of the whole problem, or NULL */
+  double load_time;          /* seconds, timing.load */
+  int32_t num_gpus;
+} povar_ba_log_info;
+int povar_write_ba_log(const char* path, const povar_ba_log_info* info, const povar_options* opt,
+                       const povar_iteration* iterations, int32_t num_iterations, const povar_solve_summary* summary);
+
 /* ---------- instrumentation ------------------------------------------------------------ */
 
 /* copy an internal device array to the host for parity tests.  Names: "pose_scale" [C*12],

@@ -89,6 +89,11 @@ class Iteration(C.Structure):
     ]
 
 
+class BaLogInfo(C.Structure):
+    _fields_ = [("input_path", C.c_char_p), ("num_cams", C.c_int32), ("num_lms", C.c_int32), ("num_obs", C.c_int64),
+                ("lm_ptr", C.POINTER(C.c_int64)), ("load_time", C.c_double), ("num_gpus", C.c_int32)]
+
+
 class SolveSummary(C.Structure):
     _fields_ = [
         ("num_iterations", C.c_int32), ("termination_type_step_1", C.c_int32),
@@ -139,6 +144,7 @@ SIGNATURES = {
     "povar_launch_count": (C.c_int64, [_H]),
     "povar_bal_create_dataset": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int64, C.c_char_p, C.c_size_t]),
     "povar_peer_exchange_active": (C.c_int, [_H]),
+    "povar_write_ba_log": (C.c_int, [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "povar_debug_sell_layout": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.c_int32,
                                           C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                           C.POINTER(C.c_int64)]),
@@ -414,6 +420,19 @@ class Solver:
 
     def launch_count(self) -> int:
         return int(self.lib.povar_launch_count(self.h))
+
+
+def write_ba_log(path: str, hp: "HostProblem", options, iterations, summary, input_path: str = "", load_time=0.0,
+                 num_gpus: int = 1) -> None:
+    """ba_log.json with the reference's key set (what `bal --log-log-path` writes) from a solve's records."""
+    lib = load()
+    lp = np.ascontiguousarray(hp.lm_ptr, dtype=np.int64)
+    info = BaLogInfo(input_path.encode(), hp.num_cams, hp.num_lms, hp.num_obs,
+                     lp.ctypes.data_as(C.POINTER(C.c_int64)), load_time, num_gpus)
+    arr = (Iteration * max(len(iterations), 1))(*iterations)
+    rc = lib.povar_write_ba_log(path.encode(), C.byref(info), C.byref(options), arr, len(iterations), C.byref(summary))
+    if rc != OK:
+        raise PovarError(rc, "povar_write_ba_log failed")
 
 
 def sell_layout(hp: "HostProblem", threads: int = 0):

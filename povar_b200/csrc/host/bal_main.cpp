@@ -128,77 +128,20 @@ AppOptions parse(int argc, char** argv) {
   return o;
 }
 
-const char* step1_name(int t) {
-  switch (t) {   // finish_solve, bal_bundle_adjustment.cpp:98-113
-    case POVAR_PCG: return "bal_pcg";
-    case POVAR_POWER_SCHUR_COMPLEMENT: return "bal_power_sc";
-    case POVAR_POWER_VARPROJ: return "power_variable_projection";
-    default: return "variable_projection";
-  }
-}
-
-template <typename F>
-void json_array(FILE* f, const char* key, const std::vector<povar_iteration>& its, F get, const char* fmt,
-                bool last = false) {
-  std::fprintf(f, "    \"%s\": [", key);
-  for (size_t i = 0; i < its.size(); ++i) {
-    std::fprintf(f, fmt, get(its[i]));
-    if (i + 1 < its.size()) std::fprintf(f, ", ");
-  }
-  std::fprintf(f, "]%s\n", last ? "" : ",");
-}
-
-void json_number(FILE* f, double v) {
-  if (std::isfinite(v)) std::fprintf(f, "%.17g", v);
-  else std::fprintf(f, "null");
-}
-
 void write_log(const AppOptions& o, const povar_bal_data& data, const std::vector<povar_iteration>& its,
                const povar_solve_summary& s, double load_time) {
-  FILE* f = std::fopen(o.log_path.c_str(), "w");
-  if (!f) {
+  povar_ba_log_info info;
+  info.input_path = o.input.c_str();
+  info.num_cams = data.num_cams;
+  info.num_lms = data.num_lms;
+  info.num_obs = data.num_obs;
+  info.lm_ptr = data.lm_ptr;
+  info.load_time = load_time;
+  info.num_gpus = o.num_gpus;
+  if (povar_write_ba_log(o.log_path.c_str(), &info, &o.solver, its.data(), static_cast<int32_t>(its.size()), &s) !=
+      POVAR_OK) {
     std::fprintf(stderr, "bal: Could not save BA log to %s.\n", o.log_path.c_str());
-    return;
   }
-  std::fprintf(f, "{\n");
-  std::fprintf(f, "    \"_type\": \"rootba_povar\",\n");
-  std::fprintf(f, "    \"_static\": {\n");
-  std::fprintf(f, "        \"problem_info\": {\"type\": \"bal\", \"input_path\": \"%s\", \"num_cameras\": %d, "
-                  "\"num_landmarks\": %d, \"num_observations\": %lld},\n",
-               o.input.c_str(), data.num_cams, data.num_lms, static_cast<long long>(data.num_obs));
-  std::fprintf(f, "        \"timing\": {\"load\": %.9g, \"preprocess\": 0.0, \"optimize\": %.9g, \"postprocess\": 0.0, \"total\": %.9g},\n",
-               load_time, s.total_time, load_time + s.total_time);
-  std::fprintf(f, "        \"solver\": {\"solver_type\": \"%s\", \"termination_type\": %d, \"termination_type_step_1\": %d, "
-                  "\"message\": \"%s\", \"num_successful_steps\": %d, \"num_unsuccessful_steps\": %d, "
-                  "\"total_time_in_seconds\": %.9g, \"step_1_time_in_seconds\": %.9g, \"step_2_time_in_seconds\": %.9g, "
-                  "\"power_series_terms\": %lld, \"power_series_time_in_seconds\": %.9g, \"num_gpus\": %d, ",
-               step1_name(o.solver.solver_type_step_1), s.termination_type_step_2, s.termination_type_step_1,
-               s.message, s.num_successful_steps, s.num_unsuccessful_steps, s.total_time, s.step1_time,
-               s.step2_time, static_cast<long long>(s.power_terms), s.power_series_time, o.num_gpus);
-  std::fprintf(f, "\"initial_cost\": ");
-  json_number(f, s.initial_cost);
-  std::fprintf(f, ", \"final_cost\": ");
-  json_number(f, s.final_cost);
-  std::fprintf(f, "}\n    },\n");
-  json_array(f, "iteration", its, [](const povar_iteration& e) { return e.iteration; }, "%d");
-  json_array(f, "step", its, [](const povar_iteration& e) { return e.step; }, "%d");
-  json_array(f, "step_is_valid", its, [](const povar_iteration& e) { return e.step_is_valid ? "true" : "false"; }, "%s");
-  json_array(f, "step_is_successful", its, [](const povar_iteration& e) { return e.step_is_successful ? "true" : "false"; }, "%s");
-  json_array(f, "cost", its, [](const povar_iteration& e) { return e.cost; }, "%.17g");
-  json_array(f, "cost_valid", its, [](const povar_iteration& e) { return e.cost_valid; }, "%.17g");
-  json_array(f, "num_obs_valid", its, [](const povar_iteration& e) { return static_cast<long long>(e.num_obs_valid); }, "%lld");
-  json_array(f, "relative_decrease", its, [](const povar_iteration& e) { return std::isfinite(e.relative_decrease) ? e.relative_decrease : 0.0; }, "%.17g");
-  json_array(f, "trust_region_radius", its, [](const povar_iteration& e) { return e.trust_region_radius; }, "%.17g");
-  json_array(f, "linear_solver_iterations", its, [](const povar_iteration& e) { return e.linear_solver_iterations; }, "%d");
-  json_array(f, "iteration_time", its, [](const povar_iteration& e) { return e.iteration_time; }, "%.9g");
-  json_array(f, "cumulative_time", its, [](const povar_iteration& e) { return e.cumulative_time; }, "%.9g");
-  json_array(f, "residual_evaluation_time", its, [](const povar_iteration& e) { return e.residual_evaluation_time; }, "%.9g");
-  json_array(f, "jacobian_evaluation_time", its, [](const povar_iteration& e) { return e.jacobian_evaluation_time; }, "%.9g");
-  json_array(f, "prepare_time", its, [](const povar_iteration& e) { return e.prepare_time; }, "%.9g");
-  json_array(f, "solve_reduced_system_time", its, [](const povar_iteration& e) { return e.solve_reduced_system_time; }, "%.9g");
-  json_array(f, "back_substitution_time", its, [](const povar_iteration& e) { return e.back_substitution_time; }, "%.9g", true);
-  std::fprintf(f, "}\n");
-  std::fclose(f);
 }
 
 }  // namespace

@@ -251,3 +251,70 @@ def test_sliced_ell_order_matches_its_rule_for_any_thread_count(shape):
         got = capi.sell_layout(hp, threads)
         for a, b in zip(got, ref):
             assert np.array_equal(a, b), (shape, threads)
+
+
+def test_ba_log_has_every_key_of_the_reference_log(tmp_path):
+    """povar_write_ba_log (what `bal --log-log-path` writes) against the key set of the reference program's own
+    ba_log.json, plus the derived columns of bal/ba_log_utils.cpp:100-175 on a hand-made trace."""
+    import json
+    hp = capi.HostProblem.read(common.golden_file("tiny"))
+    opt = capi.default_options(solver_type_step_1=capi.POWER_VARPROJ)
+    rows = [  # step, iteration, valid, successful, cost, cost_valid, trial_cost, n_valid
+        (1, 0, 1, 1, 100.0, 100.0, 100.0, 131),
+        (1, 1, 1, 1, 60.0, 60.0, 60.0, 131),
+        (1, 2, 1, 0, 60.0, 60.0, 75.0, 131),      # rejected: the log repeats the previous cost
+        (1, 3, 1, 1, 50.0, 50.0, 50.0, 131),
+        (2, 0, 1, 1, 40.0, 39.0, 40.0, 130),      # step 2 starts again at iteration 0
+        (2, 1, 1, 1, 30.0, 29.0, 30.0, 129),
+    ]
+    its = []
+    for k, (step, it, valid, succ, cost, cv, trial, nv) in enumerate(rows):
+        e = capi.Iteration()
+        e.step, e.iteration, e.step_is_valid, e.step_is_successful = step, it, valid, succ
+        e.cost, e.cost_valid, e.trial_cost, e.num_obs_valid = cost, cv, trial, nv
+        e.relative_decrease, e.trust_region_radius, e.linear_solver_iterations = 0.5, 1e4 / (k + 1), (7 if it else 0)
+        e.iteration_time, e.cumulative_time = 0.01, 0.01 * (k + 1)
+        e.residual_evaluation_time, e.jacobian_evaluation_time = 1e-3, (2e-3 if it else 0.0)
+        e.prepare_time, e.solve_reduced_system_time, e.back_substitution_time = 3e-3, 4e-3, 5e-3
+        its.append(e)
+    summ = capi.SolveSummary()
+    summ.num_iterations, summ.num_successful_steps, summ.num_unsuccessful_steps = len(its), 4, 1
+    summ.initial_cost, summ.final_cost, summ.total_time = 100.0, 30.0, 0.06
+    summ.message = b'Solver did not converge after maximum number of 2 iterations "quoted"'
+    path = tmp_path / "ba_log.json"
+    capi.write_ba_log(str(path), hp, opt, its, summ, input_path="data_custom/tiny.txt", load_time=0.5)
+    data = json.loads(path.read_text())
+
+    def keys(x, p=""):
+        out = []
+        for k, v in x.items():
+            out.append(p + k)
+            if isinstance(v, dict):
+                out += keys(v, p + k + ".")
+        return out
+    with open(os.path.join(common.GOLD, "ba_log_keys.json")) as f:
+        want = json.load(f)["keys"]
+    have = set(keys(data))
+    assert [k for k in want if k not in have] == []
+    n = len(its)
+    for k, v in data.items():
+        if not k.startswith("_"):
+            assert isinstance(v, list) and len(v) == n, k
+    assert data["_type"] == "rootba_povar"
+    assert data["cost"] == [100.0, 60.0, 60.0, 50.0, 40.0, 30.0]
+    # previous - current, only for successful trials with iteration > 0; after a rejected trial the previous
+    # summary's own cost is its trial cost (bal_bundle_adjustment.cpp:74-78)
+    assert data["cost_change"] == [0.0, 40.0, 0.0, 25.0, 0.0, 10.0]
+    assert data["num_obs_valid_change"] == [0, 0, 0, 0, 0, 1]
+    assert data["linear_solver_type"] == ["", "bal_power_sc", "bal_power_sc", "bal_power_sc", "", "bal_power_sc"]
+    assert data["num_obs"] == [131] * n and data["step_is_nonmonotonic"] == [False] * n
+    assert abs(data["cost_avg_valid"][4] - 39.0 / 130) < 1e-15
+    st = data["_static"]
+    assert st["problem_info"]["num_observations"] == hp.num_obs and st["problem_info"]["input_path"] == "data_custom/tiny.txt"
+    deg = np.diff(hp.lm_ptr)
+    assert st["problem_info"]["per_lm_obs"]["max"] == deg.max() and abs(st["problem_info"]["per_lm_obs"]["mean"] - deg.mean()) < 1e-12
+    assert st["solver"]["solver_type"] == "power_variable_projection"
+    assert st["solver"]["message"].endswith('"quoted"')
+    assert st["solver"]["num_linear_solves"] == 4 and st["solver"]["num_jacobian_evaluations"] == 4
+    assert abs(st["solver"]["linear_solver_time_in_seconds"] - n * 12e-3) < 1e-12
+    assert abs(st["timing"]["total"] - 0.56) < 1e-12

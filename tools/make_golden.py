@@ -110,6 +110,27 @@ def make_kernel_cod():
     print("kernel_cod.npz written")
 
 
+def make_ba_log_keys():
+    """Key set of the reference's own ba_log.json (tests/test_host_abi.py checks povar_write_ba_log against it)."""
+    def keys(x, p=""):
+        out = []
+        for k, v in x.items():
+            out.append(p + k)
+            if isinstance(v, dict):
+                out += keys(v, p + k + ".")
+        return out
+    with tempfile.TemporaryDirectory() as tmp:
+        subprocess.run([BAL_REF, "--input", os.path.join(GOLD, "tiny.txt"), "--alpha", "0.1", "--power-sc-iterations", "20",
+                        "--num-threads", "1", "--max-num-iterations-step-1", "3", "--max-num-iterations-step-2", "2"],
+                       cwd=tmp, capture_output=True, check=True)
+        with open(os.path.join(tmp, "ba_log.json")) as f:
+            data = json.load(f)
+    with open(os.path.join(GOLD, "ba_log_keys.json"), "w") as f:
+        json.dump({"_comment": "every key of the ba_log.json the reference program (oracle/_ref/bal_ref) writes; "
+                               "made by tools/make_golden.py", "keys": sorted(keys(data))}, f, indent=1)
+    print("ba_log_keys.json written")
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     make_kernel_cod()
@@ -134,6 +155,7 @@ def main():
                   f"final cost {one['cost'][-1]:.6e}")
     for v in files.values():
         v.pop("path")
+    make_ba_log_keys()
     with open(os.path.join(GOLD, "traces.json"), "w") as f:
         json.dump({"files": files, "traces": traces,
                    "reference_flags": "--alpha 0.1 --power-sc-iterations 20 (+ per-config flags)"}, f, indent=1)
