@@ -13,7 +13,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <string>
 #include <vector>
@@ -47,6 +49,8 @@ int parse_enum(const std::string& flag, const std::string& v, const std::map<std
 void usage() {
   std::printf(
       "Solve BAL problem with solver determined by config (B200 build).\n\n"
+      "  -C, --directory <DIR>  change to DIR first\n  --config <PATH>  config file (default rootba_config.toml)\n"
+      "  --dump-config  print the effective config and exit\n"
       "  --input <STR>\n  --create-dataset  write data_custom/<name> with randomised camera matrices and exit\n"
       "  --create-dataset-seed <INT> (default: std::random_device, like the reference)\n"
       "  --num-gpus <INT>\n  --num-threads <INT> (ignored)\n"
@@ -62,9 +66,8 @@ void usage() {
       "  --verbosity-level <INT>\n  --log-log-path <STR>\n");
 }
 
-AppOptions parse(int argc, char** argv) {
-  AppOptions o;
-  povar_options_default(&o.solver);
+// one option, by its command-line name; `val` yields its value.  false: not an option of this program
+bool apply_option(AppOptions& o, const std::string& f, const std::function<std::string()>& val) {
   const std::map<std::string, int> step1 = {{"PCG", POVAR_PCG},
                                             {"POWER_SCHUR_COMPLEMENT", POVAR_POWER_SCHUR_COMPLEMENT},
                                             // README name; the reference's own enum rejects it
@@ -75,16 +78,8 @@ AppOptions parse(int argc, char** argv) {
   const std::map<std::string, int> norm = {{"NONE", POVAR_NORM_NONE}, {"HUBER", POVAR_NORM_HUBER}, {"CAUCHY", POVAR_NORM_CAUCHY}};
   const std::map<std::string, int> oc = {{"ERROR", POVAR_COST_ERROR}, {"ERROR_VALID", POVAR_COST_ERROR_VALID},
                                          {"ERROR_VALID_AVG", POVAR_COST_ERROR_VALID_AVG}};
-  for (int i = 1; i < argc; ++i) {
-    const std::string f = argv[i];
-    auto val = [&]() -> std::string {
-      if (i + 1 >= argc) die("missing value for " + f);
-      return argv[++i];
-    };
-    if (f == "--help" || f == "-h") {
-      usage();
-      std::exit(0);
-    } else if (f == "--input") o.input = val();
+  {
+    if (f == "--input") o.input = val();
     else if (f == "--create-dataset") o.create_dataset = true;
     else if (f == "--no-create-dataset") o.create_dataset = false;
     else if (f == "--create-dataset-seed") o.dataset_seed = std::atoll(val().c_str());
@@ -120,8 +115,150 @@ AppOptions parse(int argc, char** argv) {
              f == "--debug" || f == "--no-debug") {
       // accepted for command-line compatibility; no effect on this path
     } else {
-      die("unknown argument " + f);
+      return false;
     }
+  }
+  return true;
+}
+
+// rootba_config.toml (options/options_interface.cpp:255-302, cli/bal_cli_utils.cpp:105-115): the sections
+// [dataset], [solver], [solver.residual], [solver.log] hold the same options as the command line
+// (--<key>, --residual-<key>, --log-<key>, '_' -> '-'); the file is read first, the command line overrides it,
+// a missing file means defaults.  The subset of TOML the reference's own --dump-config writes is understood:
+// tables, `key = "string" | number | true | false`, arrays (skipped), comments.
+void load_config(AppOptions& o, const std::string& path, bool verbose) {
+  FILE* f = std::fopen(path.c_str(), "r");
+  if (!f) {
+    if (verbose) std::printf("Config file %s doesn't exist. Loading defaults.\n", path.c_str());
+    return;
+  }
+  std::string section;
+  char line[4096];
+  int loaded = 0, depth = 0;
+  while (std::fgets(line, sizeof(line), f)) {
+    std::string t(line);
+    // strip comments outside strings
+    bool in_str = false;
+    for (size_t i = 0; i < t.size(); ++i) {
+      if (t[i] == '"') in_str = !in_str;
+      if (t[i] == '#' && !in_str) {
+        t.erase(i);
+        break;
+      }
+    }
+    auto trim = [](std::string v) {
+      const size_t b = v.find_first_not_of(" \t\r\n");
+      if (b == std::string::npos) return std::string();
+      return v.substr(b, v.find_last_not_of(" \t\r\n") - b + 1);
+    };
+    t = trim(t);
+    if (t.empty()) continue;
+    if (depth > 0) {   // inside a multi-line array
+      for (char ch : t) depth += (ch == '[') - (ch == ']');
+      continue;
+    }
+    if (t.front() == '[') {
+      section = trim(t.substr(1, t.find(']') - 1));
+      continue;
+    }
+    const size_t eq = t.find('=');
+    if (eq == std::string::npos) continue;
+    const std::string key = trim(t.substr(0, eq));
+    std::string value = trim(t.substr(eq + 1));
+    if (!value.empty() && value.front() == '[') {
+      for (char ch : value) depth += (ch == '[') - (ch == ']');
+      continue;   // arrays (save_log_flags): nothing this program uses
+    }
+    if (value.size() >= 2 && value.front() == '"' && value.back() == '"') value = value.substr(1, value.size() - 2);
+    std::string prefix;
+    if (section == "solver.residual") prefix = "residual-";
+    else if (section == "solver.log") prefix = "log-";
+    else if (section != "solver" && section != "dataset") continue;   // /batch_run, /slurm, ...
+    std::string name = key;
+    std::replace(name.begin(), name.end(), '_', '-');
+    bool known;
+    if (value == "true" || value == "false") {
+      known = apply_option(o, (value == "true" ? "--" : "--no-") + prefix + name, [] { return std::string(); });
+    } else {
+      known = apply_option(o, "--" + prefix + name, [&] { return value; });
+    }
+    if (known) ++loaded;
+  }
+  std::fclose(f);
+  if (verbose) std::printf("Loaded %d items from config file %s\n", loaded, path.c_str());
+}
+
+const char* enum_name(const std::map<std::string, int>& table, int v) {
+  for (const auto& kv : table) {
+    if (kv.second == v && kv.first != "POWER_BUNDLE_ADJUSTMENT") return kv.first.c_str();
+  }
+  return "?";
+}
+
+// --dump-config: the effective options in the reference's layout (only keys both programs know)
+void dump_config(const AppOptions& o) {
+  const std::map<std::string, int> step1 = {{"PCG", POVAR_PCG}, {"POWER_SCHUR_COMPLEMENT", POVAR_POWER_SCHUR_COMPLEMENT},
+                                            {"POWER_VARPROJ", POVAR_POWER_VARPROJ}, {"CHOLESKY", POVAR_CHOLESKY}};
+  const std::map<std::string, int> step2 = {{"RIPOBA", POVAR_RIPOBA}, {"RIPCG", POVAR_RIPCG}};
+  const std::map<std::string, int> norm = {{"NONE", POVAR_NORM_NONE}, {"HUBER", POVAR_NORM_HUBER}, {"CAUCHY", POVAR_NORM_CAUCHY}};
+  const std::map<std::string, int> oc = {{"ERROR", POVAR_COST_ERROR}, {"ERROR_VALID", POVAR_COST_ERROR_VALID},
+                                         {"ERROR_VALID_AVG", POVAR_COST_ERROR_VALID_AVG}};
+  const povar_options& s = o.solver;
+  std::printf("\n[dataset]\ninput = \"%s\"\ncreate_dataset = %s\n", o.input.c_str(), o.create_dataset ? "true" : "false");
+  std::printf("\n[solver]\nsolver_type_step_1 = \"%s\"\nsolver_type_step_2 = \"%s\"\nverbosity_level = %d\n",
+              enum_name(step1, s.solver_type_step_1), enum_name(step2, s.solver_type_step_2), s.verbosity_level);
+  std::printf("alpha = %.17g\noptimized_cost = \"%s\"\nmax_num_iterations_step_1 = %d\nmax_num_iterations_step_2 = %d\n",
+              s.alpha, enum_name(oc, s.optimized_cost), s.max_num_iterations_step_1, s.max_num_iterations_step_2);
+  std::printf("min_relative_decrease = %.17g\ninitial_trust_region_radius = %.17g\nmin_trust_region_radius = %.17g\n"
+              "max_trust_region_radius = %.17g\n",
+              s.min_relative_decrease, s.initial_trust_region_radius, s.min_trust_region_radius,
+              s.max_trust_region_radius);
+  std::printf("min_linear_solver_iterations = %d\nmax_linear_solver_iterations = %d\neta = %.17g\nr_tolerance = %.17g\n",
+              s.min_linear_solver_iterations, s.max_linear_solver_iterations, s.eta, s.r_tolerance);
+  std::printf("jacobi_scaling_epsilon = %.17g\npreconditioner_type = \"SCHUR_JACOBI\"\nfunction_tolerance = %.17g\n"
+              "power_sc_iterations = %d\ninitial_vee = %.17g\nvee_factor = %.17g\n",
+              s.jacobi_scaling_epsilon, s.function_tolerance, s.power_sc_iterations, s.initial_vee, s.vee_factor);
+  std::printf("\n[solver.residual]\nrobust_norm = \"%s\"\nhuber_parameter = %.17g\n", enum_name(norm, s.robust_norm),
+              s.huber_parameter);
+  std::printf("\n[solver.log]\nlog_path = \"%s\"\n", o.log_path.c_str());
+}
+
+AppOptions parse(int argc, char** argv) {
+  AppOptions o;
+  povar_options_default(&o.solver);
+  // -C / --config / --dump-config first: the config file is read before the other arguments (bal_cli_utils.cpp:96-115)
+  std::string config_path = "rootba_config.toml", working_dir;
+  bool dump = false, quiet_cli = false;
+  for (int i = 1; i < argc; ++i) {
+    const std::string f = argv[i];
+    if ((f == "--config" || f == "-C" || f == "--directory") && i + 1 >= argc) die("missing value for " + f);
+    if (f == "--config") config_path = argv[++i];
+    else if (f == "-C" || f == "--directory") working_dir = argv[++i];
+    else if (f == "--dump-config") dump = true;
+    else if (f == "--verbosity-level" && i + 1 < argc) quiet_cli = std::atoi(argv[i + 1]) == 0;
+    else if (f == "--help" || f == "-h") {
+      usage();
+      std::exit(0);
+    }
+  }
+  if (!working_dir.empty() && chdir(working_dir.c_str()) != 0) die("cannot change to directory " + working_dir);
+  load_config(o, config_path, !quiet_cli && !dump);
+  for (int i = 1; i < argc; ++i) {
+    const std::string f = argv[i];
+    if (f == "--config" || f == "-C" || f == "--directory") {
+      ++i;
+      continue;
+    }
+    if (f == "--dump-config") continue;
+    auto val = [&]() -> std::string {
+      if (i + 1 >= argc) die("missing value for " + f);
+      return argv[++i];
+    };
+    if (!apply_option(o, f, val)) die("unknown argument " + f);
+  }
+  if (dump) {
+    dump_config(o);
+    std::exit(1);   // like the reference: parse_bal_app_arguments returns false after printing (app/bal.cpp:53-57)
   }
   if (o.input.empty()) die("--input is required");
   if (o.num_gpus < 1) die("--num-gpus must be >= 1");

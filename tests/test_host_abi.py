@@ -318,3 +318,66 @@ def test_ba_log_has_every_key_of_the_reference_log(tmp_path):
     assert st["solver"]["num_linear_solves"] == 4 and st["solver"]["num_jacobian_evaluations"] == 4
     assert abs(st["solver"]["linear_solver_time_in_seconds"] - n * 12e-3) < 1e-12
     assert abs(st["timing"]["total"] - 0.56) < 1e-12
+
+
+def _parse_dump(text):
+    """{section.key: value} of a --dump-config print-out (the subset of TOML both programs write)."""
+    out, section = {}, ""
+    for line in text.splitlines():
+        line = line.strip()
+        if line.startswith("[") and line.endswith("]") and "=" not in line:
+            section = line[1:-1]
+        elif "=" in line and section:
+            k, v = [t.strip() for t in line.split("=", 1)]
+            out[f"{section}.{k}"] = v
+    return out
+
+
+def test_config_file_and_dump_config_follow_the_reference(tmp_path):
+    """rootba_config.toml is read first, the command line overrides it, --dump-config prints the effective
+    options in the reference's layout (cli/bal_cli_utils.cpp:96-122); defaults equal the reference's own."""
+    import subprocess
+    from povar_b200 import build
+    # defaults: every key we print has the reference's default value
+    ours = _parse_dump(subprocess.run([build.BAL, "--dump-config", "--input", "x"], cwd=tmp_path, capture_output=True,
+                                      text=True).stdout)
+    assert ours["solver.alpha"] == "0.01" and ours["solver.power_sc_iterations"] == "10"
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "bal_ref")
+    if os.path.exists(ref_bin):
+        theirs = _parse_dump(subprocess.run([ref_bin, "--dump-config", "--input", "x"], cwd=tmp_path,
+                                            capture_output=True, text=True).stdout)
+        assert set(ours) <= set(theirs), sorted(set(ours) - set(theirs))
+        for k, v in ours.items():
+            a, b = v.strip('"'), theirs[k].strip('"')
+            try:
+                assert float(a) == float(b), (k, a, b)
+            except ValueError:
+                assert a == b, (k, a, b)
+    # a config file, partly overridden on the command line
+    (tmp_path / "rootba_config.toml").write_text(
+        '# comment\n[dataset]\ninput = "data_custom/p.txt"   # trailing comment\n\n[solver]\nalpha = 0.1\n'
+        'solver_type_step_1 = "PCG"\nsolver_type_step_2 = "RIPCG"\npower_sc_iterations = 20\nnum_threads = 4\n'
+        'max_num_iterations_step_2 = 7\n\n[solver.residual]\nrobust_norm = "CAUCHY"\nhuber_parameter = 3.5\n\n'
+        '[solver.log]\nlog_path = "out/ba_log.json"\nsave_log_flags = [\n"JSON",\n]\n\n[batch_run]\nsomething = 1\n')
+    res = subprocess.run([build.BAL, "--dump-config", "--alpha", "0.25", "--residual-huber-parameter", "2"],
+                         cwd=tmp_path, capture_output=True, text=True)
+    got = _parse_dump(res.stdout)
+    assert got["dataset.input"] == '"data_custom/p.txt"'
+    assert got["solver.alpha"] == "0.25"                        # command line wins
+    assert got["solver.solver_type_step_1"] == '"PCG"' and got["solver.solver_type_step_2"] == '"RIPCG"'
+    assert got["solver.power_sc_iterations"] == "20" and got["solver.max_num_iterations_step_2"] == "7"
+    assert got["solver.residual.robust_norm"] == '"CAUCHY"' and float(got["solver.residual.huber_parameter"]) == 2.0
+    assert got["solver.log.log_path"] == '"out/ba_log.json"'
+    # --config names another file; -C changes the directory first; a missing file means defaults
+    other = tmp_path / "sub"
+    other.mkdir()
+    (other / "alt.toml").write_text("[solver]\neta = 0.5\n")
+    got = _parse_dump(subprocess.run([build.BAL, "-C", str(other), "--config", "alt.toml", "--dump-config", "--input", "x"],
+                                     capture_output=True, text=True).stdout)
+    assert float(got["solver.eta"]) == 0.5 and got["solver.alpha"] == "0.01"
+    # the reference reads what we dump
+    if os.path.exists(ref_bin):
+        (other / "rootba_config.toml").write_text(res.stdout)
+        back = _parse_dump(subprocess.run([ref_bin, "--dump-config"], cwd=other, capture_output=True, text=True).stdout)
+        assert float(back["solver.alpha"]) == 0.25 and back["solver.solver_type_step_1"] == '"PCG"'
+        assert back["solver.residual.robust_norm"] == '"CAUCHY"' and back["solver.log.log_path"] == '"out/ba_log.json"'
