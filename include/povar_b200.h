@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define POVAR_ABI_VERSION 1
+#define POVAR_ABI_VERSION 2
 
 /* status codes */
 enum {
@@ -121,6 +121,10 @@ typedef struct povar_handle povar_handle;
 /* ---------- host-side, no GPU needed ------------------------------------------------ */
 
 int povar_abi_version(void);
+/* sizeof of the public structs as this library was compiled, for bindings that mirror them (ctypes, cgo ...):
+ * 0 povar_options, 1 povar_problem_desc, 2 povar_comm_desc, 3 povar_residual_info, 4 povar_iteration,
+ * 5 povar_solve_summary, 6 povar_bal_data, 7 povar_ba_log_info; -1 for anything else */
+int64_t povar_abi_sizeof(int32_t which);
 
 /* BAL text reader for the 15-parameter format written by --create-dataset:
  * replaces BalProblem::load_bal_eccv (bal/bal_problem.cpp:182-303) up to and including
@@ -232,6 +236,10 @@ typedef struct povar_iteration {
   double prepare_time;                /* solve: everything before the reduced solve */
   double solve_reduced_system_time;   /* power series / PCG / Cholesky */
   double back_substitution_time;      /* apply_* */
+  /* mean |r| per observation, all / valid, as logged (repeated for failed trials): residual_block_mean and
+   * residual_block_valid_mean of the reference's log (bal/ba_log_utils.cpp:116-117) */
+  double residual_mean;
+  double residual_valid_mean;
 } povar_iteration;
 
 typedef struct povar_solve_summary {

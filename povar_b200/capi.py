@@ -86,6 +86,7 @@ class Iteration(C.Structure):
         ("residual_evaluation_time", C.c_double), ("jacobian_evaluation_time", C.c_double),
         ("prepare_time", C.c_double), ("solve_reduced_system_time", C.c_double),
         ("back_substitution_time", C.c_double),
+        ("residual_mean", C.c_double), ("residual_valid_mean", C.c_double),
     ]
 
 
@@ -109,6 +110,7 @@ _H = C.c_void_p
 _DP = C.POINTER(C.c_double)
 SIGNATURES = {
     "povar_abi_version": (C.c_int, []),
+    "povar_abi_sizeof": (C.c_int64, [C.c_int32]),
     "povar_options_default": (None, [C.POINTER(Options)]),
     "povar_bal_read": (C.c_int, [C.c_char_p, C.POINTER(BalData), C.c_char_p, C.c_size_t]),
     "povar_bal_free": (None, [C.POINTER(BalData)]),

@@ -23,6 +23,20 @@ extern "C" {
 
 int povar_abi_version(void) { return POVAR_ABI_VERSION; }
 
+int64_t povar_abi_sizeof(int32_t which) {
+  switch (which) {
+    case 0: return sizeof(povar_options);
+    case 1: return sizeof(povar_problem_desc);
+    case 2: return sizeof(povar_comm_desc);
+    case 3: return sizeof(povar_residual_info);
+    case 4: return sizeof(povar_iteration);
+    case 5: return sizeof(povar_solve_summary);
+    case 6: return sizeof(povar_bal_data);
+    case 7: return sizeof(povar_ba_log_info);
+    default: return -1;
+  }
+}
+
 void povar_options_default(povar_options* o) {
   if (!o) return;
   // code defaults of bal/solver_options.hpp:88-307 and bal_residual_options.hpp:52-60

@@ -6,9 +6,7 @@
 //   solver/bal_bundle_adjustment.cpp:61-150 (finish_iteration / finish_solve: derived sums).
 // No CUDA in this file.  Columns the GPU path has no counterpart for are written as the reference writes
 // them when it does not compute them (0 / false / ""): gradient norms, step_norm, logging_time,
-// perform_qr_time, compute_gradient_time, compute_preconditioner_time, grouping / merge fields;
-// residual_block_mean and residual_block_valid_mean (mean |r| per observation) are not carried by
-// povar_iteration and are written as 0 too.
+// perform_qr_time, compute_gradient_time, compute_preconditioner_time, grouping / merge fields.
 #include <sys/resource.h>
 
 #include <algorithm>
@@ -204,8 +202,8 @@ extern "C" int povar_write_ba_log(const char* path, const povar_ba_log_info* inf
   c.doubles("cost_valid_change", [&](int i) { return changes(i) ? its[i - 1].cost_valid - its[i].cost_valid : 0.0; });
   c.doubles("cost_avg_valid", avg_valid);
   c.doubles("cost_avg_valid_change", [&](int i) { return changes(i) ? avg_valid(i - 1) - avg_valid(i) : 0.0; });
-  c.doubles("residual_block_mean", [&](int) { return 0.0; });
-  c.doubles("residual_block_valid_mean", [&](int) { return 0.0; });
+  c.doubles("residual_block_mean", [&](int i) { return its[i].residual_mean; });
+  c.doubles("residual_block_valid_mean", [&](int i) { return its[i].residual_valid_mean; });
   c.doubles("grad_max_norm", [&](int) { return 0.0; });
   c.doubles("grad_norm", [&](int) { return 0.0; });
   c.doubles("grad_projected_max_norm", [&](int) { return 0.0; });

@@ -40,6 +40,7 @@ struct Log {
   double back_cost = 0.0;
   // last logged values (for failed trials the log repeats them, ba_log_utils.cpp:128-147)
   double logged_cost = 0.0, logged_cost_valid = 0.0;
+  double logged_res_mean = 0.0, logged_res_valid_mean = 0.0;
   int64_t logged_valid = 0;
 
   void push(povar_handle* h, int step, int it, bool valid, bool successful, double trial_cost,
@@ -50,6 +51,9 @@ struct Log {
         logged_cost = ri->error_all;
         logged_cost_valid = ri->error_valid;
         logged_valid = ri->num_obs_valid;
+        logged_res_mean = ri->num_obs_all > 0 ? ri->residual_sum_all / static_cast<double>(ri->num_obs_all) : 0.0;
+        logged_res_valid_mean =
+            ri->num_obs_valid > 0 ? ri->residual_sum_valid / static_cast<double>(ri->num_obs_valid) : 0.0;
       }
     }
     back_cost = ri ? ri->error_all : 0.0;   // an "Invalid" trial leaves a default-constructed cost
@@ -74,6 +78,8 @@ struct Log {
       e.prepare_time = t.prepare;
       e.solve_reduced_system_time = t.reduced_solve;
       e.back_substitution_time = t.back_substitution;
+      e.residual_mean = logged_res_mean;
+      e.residual_valid_mean = logged_res_valid_mean;
     }
     ++count;
     povar::handle_reset_times(h);

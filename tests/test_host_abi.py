@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/povar_b200.h but not exported"
     assert set(names) == set(capi.SIGNATURES), set(names) ^ set(capi.SIGNATURES)
-    assert lib.povar_abi_version() == 1
+    assert lib.povar_abi_version() == 2
 
 
 def test_option_defaults_are_the_reference_code_defaults():
@@ -272,6 +272,7 @@ def test_ba_log_has_every_key_of_the_reference_log(tmp_path):
         e = capi.Iteration()
         e.step, e.iteration, e.step_is_valid, e.step_is_successful = step, it, valid, succ
         e.cost, e.cost_valid, e.trial_cost, e.num_obs_valid = cost, cv, trial, nv
+        e.residual_mean, e.residual_valid_mean = 2.0 + k, 1.0 + k
         e.relative_decrease, e.trust_region_radius, e.linear_solver_iterations = 0.5, 1e4 / (k + 1), (7 if it else 0)
         e.iteration_time, e.cumulative_time = 0.01, 0.01 * (k + 1)
         e.residual_evaluation_time, e.jacobian_evaluation_time = 1e-3, (2e-3 if it else 0.0)
@@ -309,6 +310,8 @@ def test_ba_log_has_every_key_of_the_reference_log(tmp_path):
     assert data["linear_solver_type"] == ["", "bal_power_sc", "bal_power_sc", "bal_power_sc", "", "bal_power_sc"]
     assert data["num_obs"] == [131] * n and data["step_is_nonmonotonic"] == [False] * n
     assert abs(data["cost_avg_valid"][4] - 39.0 / 130) < 1e-15
+    assert data["residual_block_mean"] == [2.0 + k for k in range(n)]
+    assert data["residual_block_valid_mean"] == [1.0 + k for k in range(n)]
     st = data["_static"]
     assert st["problem_info"]["num_observations"] == hp.num_obs and st["problem_info"]["input_path"] == "data_custom/tiny.txt"
     deg = np.diff(hp.lm_ptr)
@@ -381,3 +384,13 @@ def test_config_file_and_dump_config_follow_the_reference(tmp_path):
         back = _parse_dump(subprocess.run([ref_bin, "--dump-config"], cwd=other, capture_output=True, text=True).stdout)
         assert float(back["solver.alpha"]) == 0.25 and back["solver.solver_type_step_1"] == '"PCG"'
         assert back["solver.residual.robust_norm"] == '"CAUCHY"' and back["solver.log.log_path"] == '"out/ba_log.json"'
+
+
+def test_ctypes_structs_have_the_library_s_layout():
+    """capi.py mirrors the public structs by hand; a size mismatch would corrupt memory in povar_bundle_adjust."""
+    lib = capi.load()
+    mirrors = [capi.Options, capi.ProblemDesc, capi.CommDesc, capi.ResidualInfo, capi.Iteration, capi.SolveSummary,
+               capi.BalData, capi.BaLogInfo]
+    for which, cls in enumerate(mirrors):
+        assert lib.povar_abi_sizeof(which) == ctypes.sizeof(cls), cls.__name__
+    assert lib.povar_abi_sizeof(99) == -1
