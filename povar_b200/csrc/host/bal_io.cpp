@@ -11,11 +11,14 @@
 // not reproduced: iteration 0 of step 1 overwrites all landmarks.
 #include <algorithm>
 #include <cerrno>
+#include <charconv>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <random>
 #include <string>
+#include <system_error>
+#include <thread>
 #include <vector>
 
 #include "../../../include/povar_b200.h"
@@ -116,6 +119,40 @@ extern "C" void povar_bal_free(povar_bal_data* data) {
   std::memset(data, 0, sizeof(*data));
 }
 
+// Number parsing: std::from_chars is correctly rounded like strtod (the values must be the ones the
+// reference's fscanf("%lf") reads, bit for bit) and several times faster; anything it does not accept
+// (a leading '+', "inf", hex floats) goes through strtod.
+static inline bool is_ws(char c) { return c == ' ' || c == '\n' || c == '\t' || c == '\r' || c == '\f' || c == '\v'; }
+
+static bool token_to_double(const char* b, const char* e, double* out) {
+  const auto r = std::from_chars(b, e, *out);
+  if (r.ec == std::errc() && r.ptr == e) return true;
+  std::string tmp(b, e);
+  char* q = nullptr;
+  errno = 0;
+  const double v = std::strtod(tmp.c_str(), &q);
+  if (q == tmp.c_str() || *q != '\0') return false;
+  *out = v;
+  return true;
+}
+
+static bool token_to_int(const char* b, const char* e, long long* out) {
+  if (b < e && *b == '+') ++b;
+  const auto r = std::from_chars(b, e, *out);
+  return r.ec == std::errc() && r.ptr == e;
+}
+
+static int reader_threads(size_t bytes) {
+  static const int forced = getenv("POVAR_HOST_THREADS") ? atoi(getenv("POVAR_HOST_THREADS")) : 0;
+  if (forced > 0) return forced;
+  if (bytes < (1u << 20)) return 1;
+  const unsigned hw = std::thread::hardware_concurrency();
+  return static_cast<int>(std::min<unsigned>(hw == 0 ? 1 : hw, 16));
+}
+
+// The file is a flat list of whitespace-separated tokens: 3 header, 4 N observation, 15 C camera, 3 L landmark.
+// Two parallel passes over chunks cut at whitespace: count the tokens of each chunk, then (their global numbers
+// known by a prefix sum) convert every token straight into its destination.
 extern "C" int povar_bal_read(const char* path, povar_bal_data* out, char* err, size_t err_len) {
   if (!path || !out) return POVAR_ERR_INVALID;
   std::memset(out, 0, sizeof(*out));
@@ -131,47 +168,113 @@ extern "C" int povar_bal_read(const char* path, povar_bal_data* out, char* err, 
   const size_t got = std::fread(buf.data(), 1, static_cast<size_t>(size), f);
   std::fclose(f);
   buf[got] = '\0';
-  Cursor cur{buf.data(), buf.data() + got};
+  const char* base = buf.data();
+  const char* end = base + got;
+  Cursor cur{base, end};
 
   long long C = 0, L = 0, N = 0;
   if (!cur.next_int(&C) || !cur.next_int(&L) || !cur.next_int(&N) || C <= 0 || L <= 0 || N <= 0) {
     set_err(err, err_len, std::string("Failed to parse header of '") + path + "'");
     return POVAR_ERR_IO;
   }
+  const long long n_obs_tok = 4 * N, n_cam_tok = 15 * C, n_lm_tok = 3 * L;
   std::vector<int32_t> cam(static_cast<size_t>(N)), lm(static_cast<size_t>(N));
   std::vector<double> xy(2 * static_cast<size_t>(N));
-  for (long long i = 0; i < N; ++i) {
-    long long c = 0, l = 0;
-    double x = 0, y = 0;
-    if (!cur.next_int(&c) || !cur.next_int(&l) || !cur.next_double(&x) || !cur.next_double(&y)) {
-      set_err(err, err_len, std::string("Failed to parse observations of '") + path + "'");
-      return POVAR_ERR_IO;
-    }
-    if (c < 0 || c >= C || l < 0 || l >= L) {
-      set_err(err, err_len, std::string("Index out of range in '") + path + "'");
-      return POVAR_ERR_INVALID;
-    }
-    cam[i] = static_cast<int32_t>(c);
-    lm[i] = static_cast<int32_t>(l);
-    xy[2 * i] = x;
-    xy[2 * i + 1] = -y;  // invert y axis, bal_problem.cpp:240
-  }
   out->cam_params = static_cast<double*>(std::malloc(sizeof(double) * 15 * static_cast<size_t>(C)));
-  for (long long i = 0; i < 15 * C; ++i) {
-    if (!cur.next_double(&out->cam_params[i])) {
-      set_err(err, err_len, std::string("Failed to parse cameras of '") + path + "'");
-      povar_bal_free(out);
-      return POVAR_ERR_IO;
-    }
+
+  // chunks of the remainder, each starting at the beginning of a token
+  const char* body = cur.p;
+  const int T = reader_threads(static_cast<size_t>(end - body));
+  std::vector<const char*> cut(T + 1);
+  cut[0] = body;
+  cut[T] = end;
+  for (int t = 1; t < T; ++t) {
+    const char* p = body + (end - body) * t / T;
+    while (p < end && !is_ws(*p)) ++p;   // finish the token the cut fell into
+    cut[t] = p;
   }
-  // the L x 3 landmark block must be present (the reference's loader reads it) but is not used
-  for (long long i = 0; i < 3 * L; ++i) {
-    double v;
-    if (!cur.next_double(&v)) {
-      set_err(err, err_len, std::string("Failed to parse landmarks of '") + path + "'");
-      povar_bal_free(out);
-      return POVAR_ERR_IO;
+  std::vector<long long> first(T + 1, 0);
+  std::vector<std::thread> pool;
+  auto run = [&](auto&& fn) {
+    pool.clear();
+    for (int t = 1; t < T; ++t) pool.emplace_back(fn, t);
+    fn(0);
+    for (auto& th : pool) th.join();
+  };
+  run([&](int t) {
+    long long n = 0;
+    const char* p = cut[t];
+    const char* e = cut[t + 1];
+    while (p < e) {
+      while (p < e && is_ws(*p)) ++p;
+      if (p >= e) break;
+      ++n;
+      while (p < e && !is_ws(*p)) ++p;
     }
+    first[t + 1] = n;
+  });
+  for (int t = 0; t < T; ++t) first[t + 1] += first[t];
+  const long long total = first[T];
+  // 0 ok, 1 bad observation token, 2 index out of range, 3 bad camera token, 4 bad landmark token
+  std::vector<int> status(T, 0);
+  run([&](int t) {
+    long long k = first[t];
+    const char* p = cut[t];
+    const char* e = cut[t + 1];
+    while (p < e) {
+      while (p < e && is_ws(*p)) ++p;
+      if (p >= e) break;
+      const char* b = p;
+      while (p < e && !is_ws(*p)) ++p;
+      if (k < n_obs_tok) {
+        const long long i = k >> 2;
+        const int field = static_cast<int>(k & 3);
+        if (field < 2) {
+          long long v = 0;
+          if (!token_to_int(b, p, &v)) {
+            status[t] = 1;
+            return;
+          }
+          if (v < 0 || v >= (field == 0 ? C : L)) {
+            status[t] = 2;
+            return;
+          }
+          (field == 0 ? cam : lm)[i] = static_cast<int32_t>(v);
+        } else {
+          double v = 0;
+          if (!token_to_double(b, p, &v)) {
+            status[t] = 1;
+            return;
+          }
+          xy[2 * i + (field - 2)] = field == 3 ? -v : v;   // invert y axis, bal_problem.cpp:240
+        }
+      } else if (k < n_obs_tok + n_cam_tok) {
+        if (!token_to_double(b, p, &out->cam_params[k - n_obs_tok])) {
+          status[t] = 3;
+          return;
+        }
+      } else if (k < n_obs_tok + n_cam_tok + n_lm_tok) {
+        // the L x 3 landmark block must be present and numeric (the reference's loader reads it) but is not used
+        double v;
+        if (!token_to_double(b, p, &v)) {
+          status[t] = 4;
+          return;
+        }
+      }
+      ++k;
+    }
+  });
+  int bad = 0;
+  for (int t = 0; t < T && bad == 0; ++t) bad = status[t];
+  if (bad == 0 && total < n_obs_tok) bad = 1;
+  else if (bad == 0 && total < n_obs_tok + n_cam_tok) bad = 3;
+  else if (bad == 0 && total < n_obs_tok + n_cam_tok + n_lm_tok) bad = 4;
+  if (bad != 0) {
+    const char* what = bad == 1 ? "Failed to parse observations of '" : bad == 2 ? "Index out of range in '"
+                       : bad == 3 ? "Failed to parse cameras of '" : "Failed to parse landmarks of '";
+    set_err(err, err_len, std::string(what) + path + "'");
+    povar_bal_free(out);
+    return bad == 2 ? POVAR_ERR_INVALID : POVAR_ERR_IO;
   }
   std::vector<int64_t> perm(static_cast<size_t>(N));
   out->lm_ptr = static_cast<int64_t*>(std::malloc(sizeof(int64_t) * (static_cast<size_t>(L) + 1)));

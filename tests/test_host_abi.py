@@ -394,3 +394,50 @@ def test_ctypes_structs_have_the_library_s_layout():
     for which, cls in enumerate(mirrors):
         assert lib.povar_abi_sizeof(which) == ctypes.sizeof(cls), cls.__name__
     assert lib.povar_abi_sizeof(99) == -1
+
+
+def test_bal_reader_parses_numbers_like_strtod_on_many_threads(tmp_path):
+    """The reader converts tokens with std::from_chars on several threads: every value must be the correctly
+    rounded double (what the reference's fscanf("%lf") and Python's float() give), whatever the notation, and the
+    multi-threaded path (files above 1 MB) must agree with a token-by-token Python parse."""
+    rng = np.random.default_rng(3)
+    C, L = 7, 60000
+    deg = rng.integers(2, 5, L)
+    cams = np.concatenate([np.sort(rng.choice(C, d, replace=False)) for d in deg])
+    lms = np.repeat(np.arange(L), deg)
+    N = len(cams)
+    order = rng.permutation(N)
+    fmts = ["%.6f", "%.17g", "%.3e", "%+.10e", "%.1f", "%d"]
+    toks = []
+    for k in order:
+        x, y = rng.normal(0, 300, 2)
+        f = fmts[k % len(fmts)]
+        toks.append(f"{cams[k]} {lms[k]}   {f % (x if f != '%d' else int(x))}\t{fmts[(k + 1) % len(fmts)] % (y if fmts[(k + 1) % len(fmts)] != '%d' else int(y))}")
+    camtok = ["%.17g" % v for v in rng.normal(size=15 * C)]
+    camtok[3] = "1e-320"          # subnormal
+    camtok[4] = "0.1"
+    camtok[5] = "123456789012345678901234567890"
+    camtok[6] = "-0.0"
+    lmtok = ["%.6e" % v for v in rng.normal(size=3 * L)]
+    path = tmp_path / "numbers.txt"
+    path.write_text(f"{C} {L} {N}\n" + "\n".join(toks) + "\n" + " ".join(camtok) + "\n" + "\n".join(lmtok) + "\n")
+    assert path.stat().st_size > (1 << 20)
+    hp = capi.HostProblem.read(str(path))
+    assert (hp.num_cams, hp.num_lms, hp.num_obs) == (C, L, N)
+    # Python parse of the same tokens
+    flat = path.read_text().split()
+    obs = flat[3:3 + 4 * N]
+    pc = np.array([int(t) for t in obs[0::4]])
+    pl = np.array([int(t) for t in obs[1::4]])
+    px = np.array([float(t) for t in obs[2::4]])
+    py = -np.array([float(t) for t in obs[3::4]])
+    perm = np.lexsort((pc, pl))
+    assert np.array_equal(hp.obs_cam, pc[perm])
+    assert np.array_equal(hp.obs_uv[:, 0], px[perm]) and np.array_equal(hp.obs_uv[:, 1], py[perm])
+    want = np.array([float(t) for t in camtok]).reshape(C, 15)
+    assert np.array_equal(hp.cam_params.view(np.uint64), want.view(np.uint64))      # bit for bit, -0.0 and subnormals too
+    # a malformed token anywhere is an error, not a silently shifted parse
+    bad = tmp_path / "bad.txt"
+    bad.write_text(path.read_text().replace(lmtok[-5], "abc", 1))
+    with pytest.raises(capi.PovarError):
+        capi.HostProblem.read(str(bad))
