@@ -1,0 +1,195 @@
+// LinearizorB200: the reference's own `Linearizor<Scalar>` interface
+// (/root/reference/src/rootba_povar/solver/linearizor.hpp:47-82) implemented on libpovar_b200.so.
+//
+// This is the reference-side binding of INTEGRATION.md 2, as real code: with this header and
+// linearizor_factory_b200.cpp in place of solver/linearizor.cpp, the reference's UNMODIFIED driver
+// (bundle_adjust_manual, solver/bal_bundle_adjustment.cpp:252-876) runs both LM loops on the GPU library.
+// `make -C oracle plugin` builds that program (oracle/_ref/bal_ref_b200) from the reference's sources.
+//
+// The reference's caller owns BalProblem and mutates it between calls (backup_* / restore_*, the step-2
+// normalisation, create_homogeneous_landmark), so the host copy is pushed to the device before every cost
+// evaluation and linearisation and pulled back after every apply.  A driver that uses povar_backup /
+// povar_restore / povar_normalize_joint instead (host/lm_driver.cpp) needs none of these copies.
+#pragma once
+
+#include <povar_b200.h>
+
+#include <cstdint>
+#include <vector>
+
+#include <glog/logging.h>
+
+#include "rootba_povar/solver/linearizor.hpp"
+
+namespace rootba_povar {
+
+template <class Scalar_>   // instantiated for double only: the device path is FP64 like the reference
+class LinearizorB200 : public Linearizor<Scalar_> {
+ public:
+  using Scalar = Scalar_;
+  using VecX = Eigen::Matrix<Scalar, Eigen::Dynamic, 1>;
+
+  LinearizorB200(BalProblem<Scalar>& problem, const SolverOptions& o, SolverSummary* /*summary*/, bool joint)
+      : problem_(problem), joint_(joint), alpha_(o.alpha) {
+    static_assert(sizeof(Scalar) == sizeof(double), "libpovar_b200 computes in FP64");
+    // canonical order = landmark index, then the std::map<cam, obs> order (bal_problem.hpp:226)
+    std::vector<int64_t> lm_ptr{0};
+    std::vector<int32_t> obs_cam;
+    std::vector<double> obs_uv;
+    for (const auto& lm : problem_.landmarks()) {
+      for (const auto& [cam, obs] : lm.obs) {
+        obs_cam.push_back(static_cast<int32_t>(cam));
+        obs_uv.push_back(obs.pos.x());
+        obs_uv.push_back(obs.pos.y());          // already y-flipped by load_bal_eccv (bal_problem.cpp:240)
+      }
+      lm_ptr.push_back(static_cast<int64_t>(obs_cam.size()));
+    }
+    std::vector<double> cam_P;
+    pack_cameras(cam_P);
+    povar_options po;
+    povar_options_default(&po);
+    po.solver_type_step_1 = static_cast<int>(o.solver_type_step_1);   // same enumerators, same order
+    po.solver_type_step_2 = static_cast<int>(o.solver_type_step_2);   // (solver_options.hpp:56-75)
+    po.robust_norm = static_cast<int>(o.residual.robust_norm);
+    po.huber_parameter = o.residual.huber_parameter;
+    po.alpha = o.alpha;
+    po.eta = o.eta;
+    po.r_tolerance = o.r_tolerance;
+    po.power_sc_iterations = o.power_sc_iterations;
+    po.jacobi_scaling_epsilon = o.jacobi_scaling_epsilon;
+    po.min_linear_solver_iterations = o.min_linear_solver_iterations;
+    po.max_linear_solver_iterations = o.max_linear_solver_iterations;
+    po.verbosity_level = 0;
+    povar_problem_desc d;
+    d.num_cams = static_cast<int32_t>(problem_.cameras().size());
+    d.num_lms = static_cast<int32_t>(problem_.landmarks().size());
+    d.num_obs = static_cast<int64_t>(obs_cam.size());
+    d.lm_ptr = lm_ptr.data();
+    d.obs_cam = obs_cam.data();
+    d.obs_uv = obs_uv.data();
+    d.cam_P = cam_P.data();
+    CHECK_EQ(povar_create(&d, &po, /*comm=*/nullptr, &h_), POVAR_OK) << povar_last_error(nullptr);
+  }
+  ~LinearizorB200() override { povar_destroy(h_); }
+
+  void start_iteration(IterationSummary* it_summary = nullptr) override { it_ = it_summary; }
+  void finish_iteration() override { it_ = nullptr; }
+
+  void initialize_varproj_lm_pOSE(Scalar alpha, bool initialization_varproj) override {
+    if (!initialization_varproj) return;
+    push_state(POVAR_STATE_POSE, /*landmarks=*/false);
+    CHECK_EQ(povar_init_varproj(h_, alpha), POVAR_OK) << povar_last_error(h_);
+    pull_state(POVAR_STATE_POSE);
+  }
+  void compute_error_pOSE(ResidualInfo& ri, bool /*initialization_varproj*/) override {
+    push_state(POVAR_STATE_POSE, true);
+    povar_residual_info r;
+    CHECK_EQ(povar_cost_pose(h_, alpha_, &r), POVAR_OK) << povar_last_error(h_);
+    fill(ri, r);
+  }
+  void compute_error_homogeneous(ResidualInfo& ri, bool /*initialization_varproj*/) override {
+    push_state(POVAR_STATE_JOINT, true);
+    povar_residual_info r;
+    CHECK_EQ(povar_cost_homogeneous(h_, &r), POVAR_OK) << povar_last_error(h_);
+    fill(ri, r);
+  }
+  void linearize_pOSE(Scalar alpha) override {
+    push_state(POVAR_STATE_POSE, true);
+    CHECK_EQ(povar_linearize_pose(h_, alpha), POVAR_OK) << "did not expect numerical failure during linearization";
+  }
+  void linearize_projective_space_homogeneous() override {
+    push_state(POVAR_STATE_JOINT, true);
+    CHECK_EQ(povar_linearize_homogeneous(h_), POVAR_OK) << "did not expect numerical failure during linearization";
+  }
+  VecX solve(const SolverOptions& /*solver_options*/, Scalar lambda, Scalar /*relative_error_change*/) override {
+    return solve_impl(lambda, false, 12);
+  }
+  VecX solve_joint(Scalar lambda, Scalar /*relative_error_change*/) override { return solve_impl(lambda, true, 11); }
+  Scalar apply(const SolverOptions& /*solver_options*/, Scalar alpha, VecX&& /*inc*/) override {
+    double l_diff = 0;   // the increment stayed on the device
+    CHECK_EQ(povar_apply_pose(h_, alpha, &l_diff), POVAR_OK) << povar_last_error(h_);
+    pull_state(POVAR_STATE_POSE);
+    return l_diff;
+  }
+  Scalar apply_joint(VecX&& /*inc*/) override {
+    double l_diff = 0;
+    CHECK_EQ(povar_apply_joint(h_, &l_diff), POVAR_OK) << povar_last_error(h_);
+    pull_state(POVAR_STATE_JOINT);
+    return l_diff;
+  }
+
+ private:
+  VecX solve_impl(Scalar lambda, bool joint, int dim) {
+    VecX inc(dim * static_cast<int>(problem_.cameras().size()));
+    int32_t its = 0;
+    const int rc = joint ? povar_solve_joint(h_, lambda, inc.data(), &its) : povar_solve_pose(h_, lambda, inc.data(), &its);
+    // rc == POVAR_NUM_NONFINITE_INC: inc has NaNs, the caller rejects the step (bal_bundle_adjustment.cpp:362-401)
+    CHECK_GE(rc, 0) << povar_last_error(h_);
+    if (it_ != nullptr) {
+      it_->linear_solver_iterations = its;
+      it_->linear_solver_type = "bal_power_sc";
+    }
+    return inc;
+  }
+  static void fill(ResidualInfo& ri, const povar_residual_info& r) {
+    ri.all.num_obs = static_cast<int>(r.num_obs_all);
+    ri.all.error = r.error_all;
+    ri.all.residual_sum = r.residual_sum_all;
+    ri.valid.num_obs = static_cast<int>(r.num_obs_valid);
+    ri.valid.error = r.error_valid;
+    ri.valid.residual_sum = r.residual_sum_valid;
+    ri.is_numerically_valid = r.is_numerically_valid != 0;
+  }
+  void pack_cameras(std::vector<double>& cam_P) const {
+    const auto& cams = problem_.cameras();
+    cam_P.resize(12 * cams.size());
+    for (size_t c = 0; c < cams.size(); ++c) {
+      for (int r = 0; r < 3; ++r) {
+        for (int k = 0; k < 4; ++k) cam_P[12 * c + 4 * r + k] = cams[c].space_matrix(r, k);
+      }
+    }
+  }
+  // host BalProblem -> device
+  void push_state(int which, bool landmarks) {
+    std::vector<double> cam_P, X;
+    pack_cameras(cam_P);
+    if (landmarks) {
+      const auto& lms = problem_.landmarks();
+      const int w = which == POVAR_STATE_JOINT ? 4 : 3;
+      X.resize(static_cast<size_t>(w) * lms.size());
+      for (size_t l = 0; l < lms.size(); ++l) {
+        for (int k = 0; k < w; ++k) {
+          X[w * l + k] = which == POVAR_STATE_JOINT ? lms[l].p_w_homogeneous(k) : lms[l].p_w(k);
+        }
+      }
+    }
+    CHECK_EQ(povar_set_state(h_, which, cam_P.data(), landmarks ? X.data() : nullptr), POVAR_OK) << povar_last_error(h_);
+  }
+  // device -> host BalProblem
+  void pull_state(int which) {
+    auto& cams = problem_.cameras();
+    auto& lms = problem_.landmarks();
+    const int w = which == POVAR_STATE_JOINT ? 4 : 3;
+    std::vector<double> cam_P(12 * cams.size()), X(static_cast<size_t>(w) * lms.size());
+    CHECK_EQ(povar_get_state(h_, which, cam_P.data(), X.data()), POVAR_OK) << povar_last_error(h_);
+    for (size_t c = 0; c < cams.size(); ++c) {
+      for (int r = 0; r < 3; ++r) {
+        for (int k = 0; k < 4; ++k) cams[c].space_matrix(r, k) = cam_P[12 * c + 4 * r + k];
+      }
+    }
+    for (size_t l = 0; l < lms.size(); ++l) {
+      for (int k = 0; k < w; ++k) {
+        if (which == POVAR_STATE_JOINT) lms[l].p_w_homogeneous(k) = X[w * l + k];
+        else lms[l].p_w(k) = X[w * l + k];
+      }
+    }
+  }
+
+  BalProblem<Scalar>& problem_;
+  povar_handle* h_ = nullptr;
+  IterationSummary* it_ = nullptr;
+  bool joint_;
+  double alpha_;
+};
+
+}  // namespace rootba_povar
