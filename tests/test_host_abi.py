@@ -441,3 +441,20 @@ def test_bal_reader_parses_numbers_like_strtod_on_many_threads(tmp_path):
     bad.write_text(path.read_text().replace(lmtok[-5], "abc", 1))
     with pytest.raises(capi.PovarError):
         capi.HostProblem.read(str(bad))
+
+
+def test_reference_driver_with_the_plugin_links_and_fails_loudly_without_a_gpu(tmp_path):
+    """oracle/_ref/bal_ref_b200 = the reference's own driver with LinearizorB200 (integration/) behind its Linearizor
+    interface: it must exist after build(), load libpovar_b200.so, get as far as povar_create and stop there."""
+    import subprocess
+    import torch
+    plugin = os.path.join(ROOT, "oracle", "_ref", "bal_ref_b200")
+    if not os.path.exists(plugin):
+        pytest.skip("oracle/_ref/bal_ref_b200 not built (needs /root/reference: make -C oracle plugin)")
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    res = subprocess.run([plugin, "--input", common.golden_file("tiny"), "--alpha", "0.1", "--power-sc-iterations", "20"],
+                         cwd=tmp_path, capture_output=True, text=True)
+    assert res.returncode != 0
+    assert "no CUDA device (this library has no CPU fallback)" in res.stderr
+    assert "linearizor_b200.hpp" in res.stderr          # the CHECK in the plug-in's constructor, not a crash elsewhere
