@@ -8,7 +8,7 @@
 //
 // The reference's caller owns BalProblem and mutates it between calls (backup_* / restore_*, the step-2
 // normalisation, create_homogeneous_landmark), so the host copy is pushed to the device before every cost
-// evaluation and linearisation and pulled back after every apply.  A driver that uses povar_backup /
+// evaluation, linearisation and solve and pulled back after every apply.  A driver that uses povar_backup /
 // povar_restore / povar_normalize_joint instead (host/lm_driver.cpp) needs none of these copies.
 #pragma once
 
@@ -120,6 +120,10 @@ class LinearizorB200 : public Linearizor<Scalar_> {
 
  private:
   VecX solve_impl(Scalar lambda, bool joint, int dim) {
+    // After a rejected trial the caller restores BalProblem and solves again with a larger damping WITHOUT
+    // linearising again (bal_bundle_adjustment.cpp:340-350, 508): the device still holds the trial state, and the
+    // matrix-free products rebuild their Jacobian blocks from the state, so the restored host state goes up first.
+    push_state(joint ? POVAR_STATE_JOINT : POVAR_STATE_POSE, true);
     VecX inc(dim * static_cast<int>(problem_.cameras().size()));
     int32_t its = 0;
     const int rc = joint ? povar_solve_joint(h_, lambda, inc.data(), &its) : povar_solve_pose(h_, lambda, inc.data(), &its);
