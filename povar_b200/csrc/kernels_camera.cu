@@ -860,7 +860,7 @@ constexpr long long kPeerSpinNs = 4000000000LL;   // give up after 4 s: a peer d
 //       own buffer for the peers' values and adds them in rank order -- every rank gets the same bits,
 //       no NCCL launch, no separate reduction kernel, no fence;
 //   tmp = B^-1 reduced(raw);  accum += tmp;  y = y(tmp);  per-camera norms;  then the LAST block to
-//   finish applies the convergence test of k_series_decide.  Block = 256 threads = 16 cameras.
+//   finish applies the convergence test (series_decide).  Block = 256 threads = 16 cameras.
 template <bool JOINT, int MODE>
 __global__ void __launch_bounds__(kBlock)
 k_term16(int C, const double* __restrict__ raw_in, const int* __restrict__ cam_item_ptr,
@@ -1040,17 +1040,6 @@ k_series_start(int C, const double* __restrict__ norm_part, double r_tolerance, 
     ctl->last_tmp_norm = sqrt(s0);
     ctl->last_acc_norm = sqrt(s1);
   }
-}
-
-// convergence test after term i (linearization_power_varproj.hpp:205-229)
-__global__ void __launch_bounds__(kBlock)
-k_series_decide(int C, const double* __restrict__ norm_part, int term, double eta,
-                double r_tolerance, SeriesCtl* ctl) {
-  if (ctl->done) return;
-  __shared__ double smem[2 * (kBlock / 32)];
-  double s0, s1;
-  sum_norm_parts(C, norm_part, smem, s0, s1);
-  if (threadIdx.x == 0) series_decide(s0, s1, term, eta, r_tolerance, ctl);
 }
 
 // out = reduced(raw)   (E0 x for callers outside the series: tests, PCG)
