@@ -9,7 +9,7 @@ What can be asked at these sizes is set by the reference itself: its own 8-threa
 (1e-8 with PCG / CHOLESKY), drifts apart exponentially in step 2 (RIPOBA at small damping is chaotic on these
 scenes, none of which converges within the 50 iterations), takes a different accept/reject decision somewhere
 between trial 38 and 90, and ends 1-5 % away on trafalgar-257.  So:
-  (a) step 1: every trial within max(1e-9, 5 x the reference's own running deviation, the reference's own worst
+  (a) step 1: every trial within max(1e-9, 5 x the reference's own running deviation, 5 x the reference's own worst
       step-1 deviation), identical accept/reject decisions and linear-solver iteration counts (the last term only
       matters for PCG / CHOLESKY, where the reference reproduces itself to 3e-8 / 5e-8 and our dense-S assembly
       uses atomics like the reference's own scatter-adds);
@@ -52,7 +52,7 @@ def compare_with_reference_runs(name, meta, cost, succ, lin):
         drift = max(drift, dev(ref8["cost"], i))
         d = dev(cost, i)
         worst1 = max(worst1, d)
-        assert d <= max(1e-9, 5.0 * drift, step1_ref), \
+        assert d <= max(1e-9, 5.0 * drift, 5.0 * step1_ref), \
             f"{name} step-1 trial {i}: rel {d:.2e} (reference's own drift {drift:.1e}, over step 1 {step1_ref:.1e})"
         assert bool(succ[i]) == bool(ref["step_is_successful"][i]), f"{name} step-1 trial {i}: accept/reject differs"
         assert int(lin[i]) == int(ref["linear_solver_iterations"][i]), f"{name} step-1 trial {i}: linear iterations"
