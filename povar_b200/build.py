@@ -32,7 +32,7 @@ LIB_SOURCES = [
     "engine.cu",
     "capi.cpp",
     "host/bal_io.cpp",
-    "host/ba_log.cpp",
+    "host/ba_log_writer.cpp",
     "host/lm_driver.cpp",
 ]
 HEADERS = ["device_math.cuh", "povar_internal.h", "engine.h", "../../include/povar_b200.h"]
