@@ -36,12 +36,16 @@ struct Log {
   povar_iteration* out;
   int32_t capacity;
   int32_t count = 0;
-  // cost of summary.iterations.back() as the reference's finish_iteration sees it
-  double back_cost = 0.0;
+  // cost (all / valid) of summary.iterations.back() as the reference's finish_iteration sees it
+  // (bal_bundle_adjustment.cpp:75-78): cost_change of a trial is measured against the previous LIST entry
+  double back_cost = 0.0, back_cost_valid = 0.0;
   // last logged values (for failed trials the log repeats them, ba_log_utils.cpp:128-147)
   double logged_cost = 0.0, logged_cost_valid = 0.0;
   double logged_res_mean = 0.0, logged_res_valid_mean = 0.0;
   int64_t logged_valid = 0;
+  // finish_solve (:97-159), kept here so that they do not depend on the caller's optional buffer
+  int32_t num_successful = 0, num_unsuccessful = 0;
+  double initial_cost = 0.0, final_cost = 0.0;
 
   void push(povar_handle* h, int step, int it, bool valid, bool successful, double trial_cost,
             const povar_residual_info* ri, double rel, double radius, int lin_it, double it_time,
@@ -57,6 +61,14 @@ struct Log {
       }
     }
     back_cost = ri ? ri->error_all : 0.0;   // an "Invalid" trial leaves a default-constructed cost
+    back_cost_valid = ri ? ri->error_valid : 0.0;
+    if (count == 0) initial_cost = logged_cost;
+    if (successful) {
+      ++num_successful;
+      final_cost = logged_cost;
+    } else {
+      ++num_unsuccessful;
+    }
     const povar::PhaseTimes& t = povar::handle_times(h);
     if (count < capacity && out) {
       povar_iteration& e = out[count];
@@ -235,7 +247,7 @@ StepResult run_step(povar_handle* h, const povar_options& opt, bool joint, Log& 
         lambda *= std::max(1.0 / 3, 1 - std::pow(2 * rho - 1, 3));   // :461-463
         lambda = std::max(min_lambda, lambda);
         vee = opt.initial_vee;
-        const double prev_cost = log.back_cost;
+        const double prev_cost = log.back_cost, prev_cost_valid = log.back_cost_valid;
         log.push(h, step, it, true, true, ri2.error_all, &ri2, rho, 1.0 / lambda, lin_it,
                  seconds_since(t_it), seconds_since(t_total));
         ++it;
@@ -246,7 +258,7 @@ StepResult run_step(povar_handle* h, const povar_options& opt, bool joint, Log& 
           change = std::fabs(prev_cost - ri2.error_all);
         } else {
           cost_now = ri2.error_valid;
-          change = std::fabs(prev_cost - ri2.error_valid);
+          change = std::fabs(prev_cost_valid - ri2.error_valid);   // |cost_change.valid.error|, :190-194
         }
         if (change <= opt.function_tolerance * cost_now) {
           terminated = true;
@@ -328,21 +340,11 @@ extern "C" int povar_bundle_adjust(povar_handle* h, const povar_options* opt_in,
     summary->step2_time = t_all - t_step1;
     summary->power_terms = power_terms;
     summary->power_series_time = power_time;
-    // finish_solve (:97-159): iteration 0 entries count as successful and are subtracted once
-    int succ = -1, fail = 0;
-    double final_cost = 0.0;
-    for (int i = 0; i < summary->num_iterations; ++i) {
-      if (iterations[i].step_is_successful) {
-        ++succ;
-        final_cost = iterations[i].cost;
-      } else {
-        ++fail;
-      }
-    }
-    summary->num_successful_steps = succ;
-    summary->num_unsuccessful_steps = fail;
-    summary->initial_cost = summary->num_iterations > 0 ? iterations[0].cost : 0.0;
-    summary->final_cost = final_cost;
+    // finish_solve (:97-159): iteration 0 entries count as successful; the reference subtracts one
+    summary->num_successful_steps = log.num_successful - 1;
+    summary->num_unsuccessful_steps = log.num_unsuccessful;
+    summary->initial_cost = log.initial_cost;
+    summary->final_cost = log.final_cost;
     const std::string& msg = (s1.rc != POVAR_OK) ? s1.message : s2.message;
     std::snprintf(summary->message, sizeof(summary->message), "%s", msg.c_str());
   }

@@ -76,6 +76,12 @@ def flags_to_options(flags):
             kw["power_sc_iterations"] = int(v)
         elif k == "--alpha":
             kw["alpha"] = float(v)
+        elif k == "--optimized-cost":
+            kw["optimized_cost"] = {"ERROR": 0, "ERROR_VALID": 1, "ERROR_VALID_AVG": 2}[v]
+        elif k == "--max-num-iterations-step-1":
+            kw["max_num_iterations_step_1"] = int(v)
+        elif k == "--max-num-iterations-step-2":
+            kw["max_num_iterations_step_2"] = int(v)
         else:
             raise KeyError(k)
     return kw

@@ -57,7 +57,8 @@ def _gpu_trace(name, **override):
 
 @pytest.mark.parametrize("name", ["tiny_povar", "small_povar", "small_poba", "small_cauchy", "small_huber", "small_m5",
                                   "ladybug49_povar", "ladybug49_poba", "ladybug49_cauchy",
-                                  "small_pcg_ripcg", "small_cholesky", "ladybug49_pcg_ripcg"])
+                                  "small_pcg_ripcg", "small_cholesky", "ladybug49_pcg_ripcg",
+                                  "small_error_valid", "small_error_valid_avg", "ladybug49_error_valid_avg"])
 def test_two_step_trace_matches_reference_golden(name):
     meta, its, summary = _gpu_trace(name)
     worst = common.assert_trace_close(meta, [e.cost for e in its], [e.step_is_successful for e in its],
@@ -79,6 +80,30 @@ def test_two_step_trace_matches_reference_golden(name):
     for i in range(min(len(its), k2)):
         assert its[i].iteration == ref["iteration"][i]
         assert abs(its[i].trust_region_radius - ref["trust_region_radius"][i]) <= 1e-6 * ref["trust_region_radius"][i]
+
+
+@pytest.mark.parametrize("key", ["tiny", "small_shuffle11", "ladybug49_shuffle5"])
+def test_device_index_matches_the_reference_structures(key, tmp_path):
+    """The landmark-major index in HBM (lm_ptr, obs_cam) and its camera-major transpose against the reference's own
+    pose_idx_ (tests/golden/index.npz, dumped from the compiled reference by oracle/index_probe.cpp)."""
+    g = np.load(os.path.join(common.GOLD, "index.npz"))
+    deg, cam = g[key + "/deg"], g[key + "/cam"]
+    shape, _, shuffle = key.partition("_shuffle")
+    path = tmp_path / "p.txt"
+    synthetic.write_bal(synthetic.generate_named(shape), str(path), shuffle_seed=int(shuffle) if shuffle else None)
+    hp = capi.HostProblem.read(str(path))
+    s = capi.Solver(hp, capi.default_options(verbosity_level=0))
+    lm_ptr = np.concatenate([[0], np.cumsum(deg)])
+    assert np.array_equal(s.debug_read("lm_ptr").astype(np.int64), lm_ptr)
+    assert np.array_equal(s.debug_read("obs_cam").astype(np.int64), cam)
+    obs_lm = np.repeat(np.arange(deg.shape[0]), deg)
+    assert np.array_equal(s.debug_read("obs_lm").astype(np.int64), obs_lm)
+    # camera-major transpose: stable in the landmark index
+    order = np.argsort(cam, kind="stable")
+    assert np.array_equal(s.debug_read("csc_lm").astype(np.int64), obs_lm[order])
+    assert np.array_equal(s.debug_read("cam_ptr").astype(np.int64),
+                          np.concatenate([[0], np.cumsum(np.bincount(cam, minlength=hp.num_cams))]))
+    s.close()
 
 
 def test_runs_are_bit_reproducible():

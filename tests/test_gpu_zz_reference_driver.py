@@ -3,8 +3,7 @@ unmodified sources with integration/linearizor_factory_b200.cpp in place of its 
 `bundle_adjust_manual` (both LM loops, backup / restore, step-2 normalisation on the host BalProblem) calling
 libpovar_b200.so through its `Linearizor` interface.  Its trace must match the reference's own.
 
-Built and linked in the authoring container (`make -C oracle plugin`, no GPU there); round 1 ended without GPU
-minutes to run it, hence the non-strict xfail: a pass shows up as XPASS, a failure does not hide the other tests."""
+Built and linked in the authoring container (`make -C oracle plugin`, no GPU there)."""
 import json
 import os
 import subprocess
@@ -19,7 +18,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PLUGIN = os.path.join(ROOT, "oracle", "_ref", "bal_ref_b200")
 
 
-@pytest.mark.xfail(strict=False, reason="first GPU run of the reference-side plug-in happens after round 1")
 @pytest.mark.parametrize("name", ["tiny_povar", "small_povar", "small_poba"])
 def test_reference_driver_runs_on_the_gpu_library(name, tmp_path):
     if not os.path.exists(PLUGIN):

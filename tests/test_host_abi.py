@@ -63,6 +63,36 @@ def test_bal_reader_matches_oracle_loader_bit_exactly(shape, tmp_path):
     assert np.array_equal(hs.obs_uv, hp.obs_uv)
 
 
+@pytest.mark.parametrize("key", ["tiny", "tiny_shuffle3", "small", "small_shuffle11", "ladybug49_shuffle5"])
+def test_reader_indexing_matches_the_reference_structures_bit_exactly(key, tmp_path):
+    """tests/golden/index.npz holds what the reference ITSELF keeps after loading the file: `pose_idx_` of every
+    LandmarkBlockSC (sc/landmark_block.hpp:104-108), the observation stored per (landmark, camera) pair
+    (Landmark::obs, bal/bal_problem.hpp:226, after the loader's y flip) and the camera matrices -- dumped by
+    oracle/index_probe.cpp from the compiled reference (tools/make_golden.py).  povar_bal_read, the numpy oracle's
+    loader and povar_canonical_order must reproduce them bit for bit, whatever the order of the file's lines."""
+    g = np.load(os.path.join(common.GOLD, "index.npz"))
+    deg, cam, uv, P = g[key + "/deg"], g[key + "/cam"], g[key + "/uv"], g[key + "/P"]
+    shape, _, shuffle = key.partition("_shuffle")
+    prob = synthetic.generate_named(shape)
+    path = tmp_path / "p.txt"
+    synthetic.write_bal(prob, str(path), shuffle_seed=int(shuffle) if shuffle else None)
+    lm_ptr = np.concatenate([[0], np.cumsum(deg)])
+    hp = capi.HostProblem.read(str(path))
+    assert (hp.num_cams, hp.num_lms, hp.num_obs) == (P.shape[0], deg.shape[0], cam.shape[0])
+    assert np.array_equal(hp.lm_ptr, lm_ptr) and np.array_equal(hp.obs_cam, cam)
+    assert np.array_equal(hp.obs_uv.reshape(-1, 2), uv)
+    assert np.array_equal(hp.cam_P.reshape(-1, 12), P)
+    op = O.load_bal(str(path))
+    assert np.array_equal(op.lm_ptr, lm_ptr) and np.array_equal(op.obs_cam, cam) and np.array_equal(op.uv, uv)
+    assert np.array_equal(op.P.reshape(-1, 12), P)
+    rng = np.random.default_rng(1)
+    perm = rng.permutation(prob.num_obs)
+    hu = capi.HostProblem.from_unordered(prob.num_cams, prob.num_lms, prob.obs_cam[perm], prob.obs_lm[perm],
+                                         prob.obs_xy[perm], prob.cam_params)
+    assert np.array_equal(hu.lm_ptr, lm_ptr) and np.array_equal(hu.obs_cam, cam)
+    assert np.array_equal(hu.obs_uv.reshape(-1, 2), uv)
+
+
 def test_bal_reader_errors(tmp_path):
     with pytest.raises(capi.PovarError) as e:
         capi.HostProblem.read(str(tmp_path / "missing.txt"))

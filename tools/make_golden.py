@@ -5,6 +5,10 @@ that the GPU box, which has no /root/reference, can check against them.
 
   tests/golden/kernel_cod.npz      row vectors and the kernels returned by the reference's own
                                    BalBundleAdjustmentHelper::kernel_COD (oracle/cod_probe.cpp)
+  tests/golden/index.npz           what the reference itself holds after loading a data_custom file: pose_idx_
+                                   of every LandmarkBlockSC (sc/landmark_block.hpp:104-108), the observation
+                                   stored for each (landmark, camera) pair and the camera matrices
+                                   (oracle/index_probe.cpp), for tiny / small and shuffled copies of them
   tests/golden/<shape>.txt         data_custom-format problem files (povar_b200.synthetic), small ones only
   tests/golden/traces.json         per-configuration ba_log.json columns of `bal_ref --num-threads 1`
                                    (cost, step_is_successful, trust_region_radius,
@@ -31,6 +35,7 @@ from povar_b200 import synthetic  # noqa: E402
 GOLD = os.path.join(ROOT, "tests", "golden")
 BAL_REF = os.path.join(ROOT, "oracle", "_ref", "bal_ref")
 COD_PROBE = os.path.join(ROOT, "oracle", "_ref", "cod_probe")
+INDEX_PROBE = os.path.join(ROOT, "oracle", "_ref", "index_probe")
 
 # (name, shape, extra reference flags).  --alpha / --power-sc-iterations are always explicit.
 CONFIGS = [
@@ -46,6 +51,11 @@ CONFIGS = [
     ("ladybug49_poba", "ladybug49", ["--solver-type-step-1", "POWER_SCHUR_COMPLEMENT"]),
     ("ladybug49_pcg_ripcg", "ladybug49", ["--solver-type-step-1", "PCG", "--solver-type-step-2", "RIPCG"]),
     ("ladybug49_cauchy", "ladybug49", ["--residual-robust-norm", "CAUCHY"]),
+    # --optimized-cost (bal/solver_options.hpp:48-57, solver/bal_bundle_adjustment.cpp:163-205): the accept test,
+    # rho (ERROR_VALID_AVG divides l_diff by the valid count) and the function-tolerance test use the valid sums
+    ("small_error_valid", "small", ["--optimized-cost", "ERROR_VALID"]),
+    ("small_error_valid_avg", "small", ["--optimized-cost", "ERROR_VALID_AVG"]),
+    ("ladybug49_error_valid_avg", "ladybug49", ["--optimized-cost", "ERROR_VALID_AVG"]),
 ]
 COMMITTED_FILES = {"tiny", "small"}
 KEYS = ["iteration", "cost", "cost_valid", "num_obs_valid", "step_is_valid", "step_is_successful",
@@ -110,6 +120,42 @@ def make_kernel_cod():
     print("kernel_cod.npz written")
 
 
+def run_index_probe(path):
+    """degrees [L], cameras [N], uv [N, 2], P [C, 12] exactly as the reference's own structures hold them"""
+    res = subprocess.run([INDEX_PROBE, path], capture_output=True, text=True, check=True)
+    lines = res.stdout.split("\n")
+    C, L, N = (int(v) for v in lines[0].split())
+    deg = np.empty(L, dtype=np.int32)
+    cams = np.empty(N, dtype=np.int32)
+    p = 0
+    for l in range(L):
+        tok = lines[1 + l].split()
+        deg[l] = int(tok[0])
+        cams[p:p + deg[l]] = [int(t) for t in tok[1:]]
+        p += deg[l]
+    assert p == N
+    uv = np.array([[float(t) for t in lines[1 + L + i].split()] for i in range(N)], dtype=np.float64).reshape(N, 2)
+    P = np.array([[float(t) for t in lines[1 + L + N + c].split()] for c in range(C)], dtype=np.float64)
+    return deg, cams, uv, P
+
+
+def make_index_fixture():
+    """tests/golden/index.npz: the reference's own pose_idx_ / Landmark::obs for committed and shuffled files."""
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for shape, shuffle in (("tiny", None), ("tiny", 3), ("small", None), ("small", 11), ("ladybug49", 5)):
+            prob = synthetic.generate_named(shape)
+            path = os.path.join(tmp, "p.txt")
+            synthetic.write_bal(prob, path, shuffle_seed=shuffle)
+            if shuffle is None:
+                assert sha256(path) == sha256(os.path.join(GOLD, f"{shape}.txt"))
+            deg, cams, uv, P = run_index_probe(path)
+            key = shape if shuffle is None else f"{shape}_shuffle{shuffle}"
+            out[key + "/deg"], out[key + "/cam"], out[key + "/uv"], out[key + "/P"] = deg, cams, uv, P
+    np.savez_compressed(os.path.join(GOLD, "index.npz"), **out)
+    print("index.npz written:", sorted({k.split("/")[0] for k in out}))
+
+
 def make_ba_log_keys():
     """Key set of the reference's own ba_log.json (tests/test_host_abi.py checks povar_write_ba_log against it)."""
     def keys(x, p=""):
@@ -132,33 +178,45 @@ def make_ba_log_keys():
 
 
 def main():
+    """python tools/make_golden.py            everything (kernel_COD vectors, index fixture, all traces)
+    python tools/make_golden.py NAME ...   only these configurations / "index" / "cod" / "keys", merged into the
+                                           existing traces.json"""
     os.makedirs(GOLD, exist_ok=True)
-    make_kernel_cod()
-    traces = {}
-    files = {}
+    want = set(sys.argv[1:])
+    out_path = os.path.join(GOLD, "traces.json")
+    doc = {"files": {}, "traces": {}, "reference_flags": "--alpha 0.1 --power-sc-iterations 20 (+ per-config flags)"}
+    if want and os.path.exists(out_path):
+        with open(out_path) as f:
+            doc = json.load(f)
+    if not want or "cod" in want:
+        make_kernel_cod()
+    if not want or "index" in want:
+        make_index_fixture()
+    if not want or "keys" in want:
+        make_ba_log_keys()
+    configs = [c for c in CONFIGS if not want or c[0] in want]
+    paths = {}
     with tempfile.TemporaryDirectory() as tmp:
-        for shape in sorted({c[1] for c in CONFIGS}):
+        for shape in sorted({c[1] for c in configs}):
             prob = synthetic.generate_named(shape)
             path = os.path.join(GOLD if shape in COMMITTED_FILES else tmp, f"{shape}.txt")
-            synthetic.write_bal(prob, path)
-            files[shape] = {"path": path, "sha256": sha256(path), "num_cams": prob.num_cams,
-                            "num_lms": prob.num_lms, "num_obs": prob.num_obs,
-                            "committed": shape in COMMITTED_FILES}
-        for name, shape, flags in CONFIGS:
-            one = run_ref(files[shape]["path"], flags, 1, tmp)
-            many = run_ref(files[shape]["path"], flags, 8, tmp)
-            traces[name] = {"shape": shape, "flags": flags, "threads1": one,
-                            "threads8": {"cost": many["cost"], "step_is_successful": many["step_is_successful"],
-                                         "iteration": many["iteration"]}}
+            if not (shape in COMMITTED_FILES and os.path.exists(path)):
+                synthetic.write_bal(prob, path)
+            paths[shape] = path
+            doc["files"][shape] = {"sha256": sha256(path), "num_cams": prob.num_cams,
+                                   "num_lms": prob.num_lms, "num_obs": prob.num_obs,
+                                   "committed": shape in COMMITTED_FILES}
+        for name, shape, flags in configs:
+            one = run_ref(paths[shape], flags, 1, tmp)
+            many = run_ref(paths[shape], flags, 8, tmp)
+            doc["traces"][name] = {"shape": shape, "flags": flags, "threads1": one,
+                                   "threads8": {"cost": many["cost"], "step_is_successful": many["step_is_successful"],
+                                                "iteration": many["iteration"]}}
             k2 = [i for i in range(1, len(one["iteration"])) if one["iteration"][i] == 0]
             print(f"{name}: {len(one['cost'])} trials, step 2 starts at {k2[0] if k2 else None}, "
                   f"final cost {one['cost'][-1]:.6e}")
-    for v in files.values():
-        v.pop("path")
-    make_ba_log_keys()
-    with open(os.path.join(GOLD, "traces.json"), "w") as f:
-        json.dump({"files": files, "traces": traces,
-                   "reference_flags": "--alpha 0.1 --power-sc-iterations 20 (+ per-config flags)"}, f, indent=1)
+    with open(out_path, "w") as f:
+        json.dump(doc, f, indent=1)
     print("traces.json written")
 
 
