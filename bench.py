@@ -141,6 +141,8 @@ def reference_arm(args, sp, path, workdir):
               f"(same data_custom file, same flags), {steps} step(s)")
     return {
         "value": value, "ms_per_step": 1e3 * t / steps, "cores": threads, "sample": sample,
+        "sample_lm_iterations": [it1, it2], "sample_trials_logged": trials / steps,
+        "sample_final_cost": runs[-1]["final_cost"],
         "spmv_ref_layout_gbs": (ref_layout_bytes(nnz, L, C) * terms / t_series / 1e9) if t_series > 0 else None,
         "s_per_power_term": (t_series / terms) if terms else None, "trials_per_step": trials / steps,
         "load_s": runs[0]["load_s"],
@@ -192,7 +194,9 @@ def main():
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config,
             "cpu_baseline": {"value": r["value"], "unit": "LM iterations/s", "cores": r["cores"], "kind": "reference",
-                             "sample": r["sample"], "spmv_ref_layout_gbs": r["spmv_ref_layout_gbs"],
+                             "sample": r["sample"], "sample_lm_iterations": r["sample_lm_iterations"],
+                             "sample_trials_logged": r["sample_trials_logged"],
+                             "full_workload": False, "spmv_ref_layout_gbs": r["spmv_ref_layout_gbs"],
                              "s_per_power_term": r["s_per_power_term"]},
             "e2e": {"value": r["value"], "unit": "LM iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
@@ -241,9 +245,9 @@ def main():
     # ---- resident: one handle, state reset between steps
     solver = capi.Solver(hp, opt, comm)
     P0 = hp.cam_P.copy()
-    config["series_exchange"] = ("none (1 GPU)" if world == 1 else
-                                 "peer-memory stores fused into the term kernel (CUDA IPC over NVLink)"
-                                 if solver.peer_exchange_active() else "ncclAllReduce per term")
+    series_exchange = ("none (1 GPU)" if world == 1 else
+                       "peer-memory stores fused into the term kernel (CUDA IPC over NVLink)"
+                       if solver.peer_exchange_active() else "ncclAllReduce per term")
 
     def resident_step():
         solver.set_state(capi.STATE_POSE, P0, None)
@@ -284,6 +288,20 @@ def main():
     clocks = sampler.stop() if sampler else None
     final_cost = its[-1].cost
     step1_trials = sum(1 for e in its if e.step == 1)
+    # what the solve produced, so that runs at different GPU counts can be compared from their bench lines: the
+    # sharded result may differ from the 1-GPU one by summation order only
+    import hashlib
+    solve_result = {
+        "final_cost": summ.final_cost, "initial_cost": summ.initial_cost,
+        "accepted_steps": int(summ.num_successful_steps), "rejected_steps": int(summ.num_unsuccessful_steps),
+        "lm_trials": len(its), "step1_trials": step1_trials, "power_terms": int(summ.power_terms),
+        "cost_first5": [e.cost for e in its[:5]],
+        "cost_step2_first": next((e.cost for e in its if e.step == 2), None),
+        # sha256 over the logged costs printed with 7 significant digits and the accept/reject and term-count
+        # columns: equal across GPU counts unless a cost sits within ~1e-9 of a rounding boundary
+        "trace_digest_7digits": hashlib.sha256(";".join(
+            f"{e.cost:.6e},{int(e.step_is_successful)},{e.linear_solver_iterations}" for e in its).encode()).hexdigest()[:16],
+    }
 
     # ---- roofline of the dominant kernel (CUDA events on the handle's stream)
     solver.set_state(capi.STATE_POSE, P0, None)
@@ -321,6 +339,11 @@ def main():
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
         "traffic": traffic,
+        "traffic_source": ("profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full "
+                           "capture of this kernel on this workload (static, not re-measured in this run)"
+                           if traffic is not None else None),
+        "series_exchange": series_exchange,
+        "solve_result": solve_result,
         "bytes_per_launch": dom_bytes, "kernel_us": 1e6 * ksec[dom],
         "term_kernels_us": {"landmark_pass": 1e6 * ksec[0], "camera_pass": 1e6 * ksec[1],
                             "item_reduce_multi_gpu_only": 1e6 * ksec[2], "binv_norms_test": 1e6 * ksec[3]},
@@ -387,7 +410,9 @@ def main():
             sub.steps = 1
             r = reference_arm(sub, sp, path, tmp)
         cpu = {"value": r["value"], "unit": "LM iterations/s", "cores": r["cores"], "kind": "reference",
-               "sample": r["sample"], "ms_per_lm_iteration": 1e3 / r["value"],
+               "sample": r["sample"], "sample_lm_iterations": r["sample_lm_iterations"],
+               "sample_trials_logged": r["sample_trials_logged"], "full_workload": False,
+               "ms_per_lm_iteration": 1e3 / r["value"],
                "spmv_ref_layout_gbs": r["spmv_ref_layout_gbs"], "s_per_power_term": r["s_per_power_term"],
                "load_s": r["load_s"]}
 

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define POVAR_ABI_VERSION 2
+#define POVAR_ABI_VERSION 3
 
 /* status codes */
 enum {
@@ -123,7 +123,7 @@ typedef struct povar_handle povar_handle;
 int povar_abi_version(void);
 /* sizeof of the public structs as this library was compiled, for bindings that mirror them (ctypes, cgo ...):
  * 0 povar_options, 1 povar_problem_desc, 2 povar_comm_desc, 3 povar_residual_info, 4 povar_iteration,
- * 5 povar_solve_summary, 6 povar_bal_data, 7 povar_ba_log_info; -1 for anything else */
+ * 5 povar_solve_summary, 6 povar_bal_data, 7 povar_ba_log_info, 8 povar_phase_times; -1 for anything else */
 int64_t povar_abi_sizeof(int32_t which);
 
 /* BAL text reader for the 15-parameter format written by --create-dataset:
@@ -163,6 +163,13 @@ int povar_partition_landmarks(int32_t num_lms, const int64_t* lm_ptr, int32_t wo
 /* ---------- life cycle ---------------------------------------------------------------- */
 
 int povar_comm_unique_id(uint8_t id[128]);
+/* An id for ranks on ONE host that need no NCCL communicator: the handles swap their CUDA IPC handles through a
+ * POSIX shared-memory rendezvous named by the id, and every reduction of the path (camera sums per power-series
+ * term, cost scalars, Kronecker sums ...) goes over the peer-mapped buffers.  Unlike NCCL this allows several
+ * ranks on the same device (povar_comm_desc.device may repeat), so the sharded arithmetic can be exercised on a
+ * one-GPU box; povar_create fails if CUDA IPC / peer access is unavailable (there is nothing to fall back to).
+ * Broadcast the id to the other ranks like an NCCL id.  The reference has no counterpart (single process). */
+int povar_comm_host_id(uint8_t id[128]);
 /* The NCCL communicator of a (nccl_id, rank) pair is made by the first povar_create that names it and
  * shared by every later handle of this process with the same descriptor (the reference makes a step-1
  * and a step-2 linearizor per solve, solver/linearizor.cpp:47-79; both ride on one communicator).
@@ -280,6 +287,19 @@ int povar_write_ba_log(const char* path, const povar_ba_log_info* info, const po
                        const povar_iteration* iterations, int32_t num_iterations, const povar_solve_summary* summary);
 
 /* ---------- instrumentation ------------------------------------------------------------ */
+
+/* Phase times of the Linearizor methods, seconds, from CUDA events on the handle's stream, accumulated since the
+ * last povar_reset_timings: what the reference's linearizors write into IterationSummary through IF_SET(it_summary_)
+ * (solver/linearizor_power_varproj.cpp:16-17; fields of solver/solver_summary.hpp:172-212). */
+typedef struct povar_phase_times {
+  double residual_evaluation_time;     /* compute_error_* */
+  double jacobian_evaluation_time;     /* linearize_*: Jacobians, Jp^T Jp, Jacobi scalings */
+  double prepare_time;                 /* solve: Hll^-1, B^-1, b (the reference's stage2 / prepare columns) */
+  double solve_reduced_system_time;    /* power series / PCG / Cholesky */
+  double back_substitution_time;       /* apply_* */
+} povar_phase_times;
+int povar_get_timings(const povar_handle* h, povar_phase_times* out);
+int povar_reset_timings(povar_handle* h);
 
 /* copy an internal device array to the host for parity tests.  Names: "pose_scale" [C*12],
  * "lm_scale" [L*4], "hll_inv" [L*6], "b_inv" [C*D*D], "b" [C*D], "inc" [C*D], "lm_ptr", ...

@@ -105,6 +105,12 @@ class SolveSummary(C.Structure):
     ]
 
 
+class PhaseTimes(C.Structure):
+    _fields_ = [("residual_evaluation_time", C.c_double), ("jacobian_evaluation_time", C.c_double),
+                ("prepare_time", C.c_double), ("solve_reduced_system_time", C.c_double),
+                ("back_substitution_time", C.c_double)]
+
+
 # every symbol include/povar_b200.h declares: (restype, argtypes)
 _H = C.c_void_p
 _DP = C.POINTER(C.c_double)
@@ -118,6 +124,9 @@ SIGNATURES = {
                                         C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "povar_partition_landmarks": (C.c_int, [C.c_int32, C.POINTER(C.c_int64), C.c_int32, C.POINTER(C.c_int32)]),
     "povar_comm_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
+    "povar_comm_host_id": (C.c_int, [C.POINTER(C.c_uint8)]),
+    "povar_get_timings": (C.c_int, [_H, C.POINTER(PhaseTimes)]),
+    "povar_reset_timings": (C.c_int, [_H]),
     "povar_create": (C.c_int, [C.POINTER(ProblemDesc), C.POINTER(Options), C.POINTER(CommDesc), C.POINTER(_H)]),
     "povar_destroy": (None, [_H]),
     "povar_last_error": (C.c_char_p, [_H]),
@@ -423,6 +432,15 @@ class Solver:
     def launch_count(self) -> int:
         return int(self.lib.povar_launch_count(self.h))
 
+    def timings(self) -> PhaseTimes:
+        """CUDA-event phase times accumulated since the last reset_timings (povar_get_timings)"""
+        t = PhaseTimes()
+        self._check(self.lib.povar_get_timings(self.h, C.byref(t)))
+        return t
+
+    def reset_timings(self) -> None:
+        self._check(self.lib.povar_reset_timings(self.h))
+
 
 def write_ba_log(path: str, hp: "HostProblem", options, iterations, summary, input_path: str = "", load_time=0.0,
                  num_gpus: int = 1) -> None:
@@ -470,6 +488,16 @@ def unique_id() -> bytes:
     rc = lib.povar_comm_unique_id(buf)
     if rc != OK:
         raise PovarError(rc, lib.povar_last_error(None).decode())
+    return bytes(buf)
+
+
+def host_id() -> bytes:
+    """id of a host (shared-memory) rendezvous: no NCCL, ranks may share a device (povar_comm_host_id)"""
+    lib = load()
+    buf = (C.c_uint8 * 128)()
+    rc = lib.povar_comm_host_id(buf)
+    if rc != OK:
+        raise PovarError(rc, "povar_comm_host_id failed")
     return bytes(buf)
 
 

@@ -10,6 +10,7 @@
 namespace povar {
 int nccl_unique_id(uint8_t id[128], std::string* err);
 int nccl_finalize();
+int host_unique_id(uint8_t id[128]);
 }
 
 struct povar_handle {
@@ -33,6 +34,7 @@ int64_t povar_abi_sizeof(int32_t which) {
     case 5: return sizeof(povar_solve_summary);
     case 6: return sizeof(povar_bal_data);
     case 7: return sizeof(povar_ba_log_info);
+    case 8: return sizeof(povar_phase_times);
     default: return -1;
   }
 }
@@ -69,6 +71,11 @@ int povar_comm_unique_id(uint8_t id[128]) {
   const int rc = povar::nccl_unique_id(id, &err);
   if (rc != POVAR_OK) g_last_global_error = err;
   return rc;
+}
+
+int povar_comm_host_id(uint8_t id[128]) {
+  if (!id) return POVAR_ERR_INVALID;
+  return povar::host_unique_id(id);
 }
 
 int povar_comm_finalize(void) { return povar::nccl_finalize(); }
@@ -199,6 +206,23 @@ int povar_bench_power_terms(povar_handle* h, int32_t which, int32_t terms, doubl
 int povar_bench_power_kernels(povar_handle* h, int32_t which, int32_t reps, double seconds[4]) {
   PV_ENGINE(h);
   return e.bench_power_kernels(which == POVAR_STATE_JOINT, reps, seconds);
+}
+
+int povar_get_timings(const povar_handle* h, povar_phase_times* out) {
+  if (!h || !h->engine || !out) return POVAR_ERR_INVALID;
+  const povar::PhaseTimes& t = h->engine->last_times();
+  out->residual_evaluation_time = t.residual;
+  out->jacobian_evaluation_time = t.linearize;
+  out->prepare_time = t.prepare;
+  out->solve_reduced_system_time = t.reduced_solve;
+  out->back_substitution_time = t.back_substitution;
+  return POVAR_OK;
+}
+
+int povar_reset_timings(povar_handle* h) {
+  PV_ENGINE(h);
+  e.reset_times();
+  return POVAR_OK;
 }
 
 int64_t povar_launch_count(const povar_handle* h) {

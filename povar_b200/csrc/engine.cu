@@ -9,8 +9,13 @@
 #include "engine.h"
 
 #include <dlfcn.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -78,7 +83,6 @@ struct PeerShared {
   void* mem = nullptr;            // this rank's receive buffer + flags (cudaMalloc, IPC-exported)
   std::vector<void*> opened;      // the peers' buffers as mapped here
   PeerExchange px{};
-  unsigned int epoch = 0;
   bool ok = false;
   void release() {
     ok = false;
@@ -99,6 +103,8 @@ static std::string comm_key(const povar_comm_desc& c) {
   return key;
 }
 
+static void release_rendezvous();   // host rendezvous segments (below)
+
 // destroys every cached communicator; handles made with them must have been destroyed before
 int nccl_finalize() {
   std::lock_guard<std::mutex> lock(comm_cache_mutex());
@@ -108,6 +114,7 @@ int nccl_finalize() {
     delete kv.second;
   }
   peer_cache().clear();
+  release_rendezvous();
   for (auto& kv : comm_cache()) {
     if (api && kv.second) api->CommDestroy(kv.second);
   }
@@ -124,6 +131,90 @@ int nccl_unique_id(uint8_t id[128], std::string* err) {
     return POVAR_ERR_NCCL;
   }
   return POVAR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host rendezvous: a POSIX shared-memory segment instead of an NCCL communicator for the ONE thing the
+// communicator is needed for when the peer buffers carry every reduction -- swapping the CUDA IPC handles at
+// set-up.  Selected by a communicator id that starts with kHostIdMagic (povar_comm_host_id).  It is what lets
+// several ranks share one device (NCCL refuses two ranks on the same GPU): the sharded arithmetic, the IPC
+// mapping and the tagged peer stores are then exactly those of a multi-GPU run, on a one-GPU box.
+// ---------------------------------------------------------------------------------------------
+static const char kHostIdMagic[] = "POVAR-SHM:";
+constexpr int kRdvRounds = 64;       // rendezvous per id (one per distinct camera count)
+constexpr int kRdvSlotWords = 160;   // >= kMaxPeers * 17 words
+struct RdvRegion {
+  std::atomic<unsigned int> arrived[kRdvRounds][2];
+  unsigned int payload[kRdvRounds][2][kMaxPeers][kRdvSlotWords];
+};
+struct HostRendezvous {
+  RdvRegion* region = nullptr;
+  int next_round = 0;
+  std::string name;
+};
+static std::map<std::string, HostRendezvous>& rdv_cache() {
+  static std::map<std::string, HostRendezvous> cache;
+  return cache;
+}
+static void release_rendezvous() {
+  for (auto& kv : rdv_cache()) {
+    if (kv.second.region) munmap(kv.second.region, sizeof(RdvRegion));
+    shm_unlink(kv.first.c_str());
+  }
+  rdv_cache().clear();
+}
+static bool is_host_id(const uint8_t* id) { return std::memcmp(id, kHostIdMagic, sizeof(kHostIdMagic) - 1) == 0; }
+
+int host_unique_id(uint8_t id[128]) {
+  static std::atomic<unsigned int> counter{0};
+  std::memset(id, 0, 128);
+  const auto now = std::chrono::steady_clock::now().time_since_epoch().count();
+  std::snprintf(reinterpret_cast<char*>(id), 128, "%s/povar_%d_%u_%llx", kHostIdMagic, static_cast<int>(getpid()),
+                counter.fetch_add(1), static_cast<unsigned long long>(now));
+  return POVAR_OK;
+}
+
+// comm_cache_mutex() held by the caller
+static HostRendezvous* open_rendezvous(const uint8_t* id, std::string* err) {
+  const std::string name(reinterpret_cast<const char*>(id) + sizeof(kHostIdMagic) - 1);
+  auto& cache = rdv_cache();
+  auto it = cache.find(name);
+  if (it != cache.end()) return &it->second;
+  const int fd = shm_open(name.c_str(), O_CREAT | O_RDWR, 0600);
+  if (fd < 0 || ftruncate(fd, sizeof(RdvRegion)) != 0) {   // a new segment reads as zeros; same size on every rank
+    if (fd >= 0) close(fd);
+    if (err) *err = "host rendezvous: shm_open(" + name + ") failed";
+    return nullptr;
+  }
+  void* p = mmap(nullptr, sizeof(RdvRegion), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (p == MAP_FAILED) {
+    if (err) *err = "host rendezvous: mmap failed";
+    return nullptr;
+  }
+  HostRendezvous& r = cache[name];
+  r.region = static_cast<RdvRegion*>(p);
+  r.name = name;
+  return &r;
+}
+
+// element-wise sum over the ranks of `words` unsigned ints (what the set-up does with ncclAllReduce otherwise)
+static bool rendezvous_sum(HostRendezvous* r, int round, int phase, int rank, int world, unsigned int* data,
+                           int words) {
+  if (round >= kRdvRounds || words > kRdvSlotWords) return false;
+  RdvRegion* g = r->region;
+  std::memcpy(g->payload[round][phase][rank], data, sizeof(unsigned int) * words);
+  g->arrived[round][phase].fetch_add(1, std::memory_order_acq_rel);
+  const auto t0 = std::chrono::steady_clock::now();
+  while (g->arrived[round][phase].load(std::memory_order_acquire) < static_cast<unsigned int>(world)) {
+    if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(120)) return false;   // a rank never came
+    std::this_thread::sleep_for(std::chrono::microseconds(50));
+  }
+  for (int w = 0; w < words; ++w) data[w] = 0;
+  for (int q = 0; q < world; ++q) {
+    for (int w = 0; w < words; ++w) data[w] += g->payload[round][phase][q][w];
+  }
+  return true;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -381,7 +472,18 @@ int Engine::create(const povar_problem_desc* desc, const povar_options* opt,
   }
   if (rc == POVAR_OK) rc = e->check(cudaStreamCreateWithFlags(&e->stream_, cudaStreamNonBlocking), "cudaStreamCreate");
   for (int i = 0; i < 4 && rc == POVAR_OK; ++i) rc = e->check(cudaEventCreate(&e->ev_[i]), "cudaEventCreate");
-  if (rc == POVAR_OK && e->world_ > 1) {
+  if (rc == POVAR_OK && e->world_ > 1 && opt->solver_type_step_1 == POVAR_CHOLESKY) {
+    // the direct solver's reduced camera system is not sharded (solver/linearizor_sc.cpp:121-128 is serial too)
+    rc = e->fail(POVAR_ERR_UNSUPPORTED, "CHOLESKY is single-GPU: create the handle without a communicator");
+  }
+  if (rc == POVAR_OK && e->world_ > 1 && is_host_id(comm->nccl_id)) {
+    // host rendezvous (povar_comm_host_id): no NCCL communicator at all, every reduction over the peer buffers
+    e->comm_key_ = comm_key(*comm);
+    std::lock_guard<std::mutex> lock(comm_cache_mutex());
+    std::string herr;
+    e->rdv_ = open_rendezvous(comm->nccl_id, &herr);
+    if (!e->rdv_) rc = e->fail(POVAR_ERR_NCCL, herr);
+  } else if (rc == POVAR_OK && e->world_ > 1) {
     std::string nerr;
     e->nccl_ = load_nccl(&nerr);
     if (!e->nccl_) {
@@ -634,28 +736,59 @@ int Engine::upload(const povar_problem_desc* desc) {
   return POVAR_OK;
 }
 
-// Peer-memory exchange for the per-term camera sums: one cudaMalloc per rank (receive buffer + flags),
-// exported with CUDA IPC, handles swapped through the NCCL communicator, mapped with peer access over
-// NVLink.  Every rank takes the same decisions (the inputs of each decision are all-reduced), because a
-// rank that fell back to NCCL alone would deadlock the others.  The mapping is made once per
-// (communicator, camera count) and process -- like the communicator itself -- and shared by later
+// Peer-memory exchange for the per-term camera sums: one cudaMalloc per rank (receive buffer + exchange
+// counter), exported with CUDA IPC, handles swapped through the NCCL communicator (or the host rendezvous),
+// mapped with peer access over NVLink.  Every rank takes the same decisions (the inputs of each decision are
+// all-reduced), because a rank that fell back to NCCL alone would deadlock the others.  The mapping is made
+// once per (communicator, camera count) and process -- like the communicator itself -- and shared by later
 // handles: ranks create their handles in the same order, so cache hits are symmetric.
+//
+// The number of an exchange -- its tag and the parity of the slots it uses -- is a DEVICE-side counter that
+// lives next to the receive buffer and is advanced by the kernel that performed the exchange (k_term16,
+// k_peer_allreduce): terms that are enqueued but skipped after the series converged do not count, every rank
+// performs the same sequence of exchanges, and the count survives the handle (the slots keep their tags).
+static constexpr size_t kPeerCounterBytes = 256;
+int Engine::sum_setup_words(unsigned int* host, int words, int phase, int round) {
+  if (rdv_) {
+    if (!rendezvous_sum(rdv_, round, phase, rank_, world_, host, words)) {
+      return fail(POVAR_ERR_NCCL, "host rendezvous: a rank did not arrive (peer exchange setup)");
+    }
+    return POVAR_OK;
+  }
+  unsigned int* dev = nullptr;
+  PV_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&dev), sizeof(unsigned int) * words, stream_));
+  PV_CUDA(cudaMemcpyAsync(dev, host, sizeof(unsigned int) * words, cudaMemcpyHostToDevice, stream_));
+  if (nccl_->AllReduce(dev, dev, words, /*ncclUint32*/ 3, /*ncclSum*/ 0, nccl_comm_, stream_) != 0) {
+    return fail(POVAR_ERR_NCCL, "ncclAllReduce failed (peer exchange setup)");
+  }
+  PV_CUDA(cudaMemcpyAsync(host, dev, sizeof(unsigned int) * words, cudaMemcpyDeviceToHost, stream_));
+  PV_CUDA(cudaStreamSynchronize(stream_));
+  PV_CUDA(cudaFreeAsync(dev, stream_));
+  return POVAR_OK;
+}
+
 int Engine::setup_peer_exchange() {
   const char* env = getenv("POVAR_PEER_EXCHANGE");
-  if (env != nullptr && std::strcmp(env, "0") == 0) return POVAR_OK;
-  if (world_ > kMaxPeers || C_ <= 0) return POVAR_OK;
+  const bool forbid = env != nullptr && std::strcmp(env, "0") == 0;
+  if (forbid && rdv_) return fail(POVAR_ERR_NCCL, "the host rendezvous needs the peer exchange (POVAR_PEER_EXCHANGE=0 set)");
+  if (forbid) return POVAR_OK;
+  if (world_ > kMaxPeers || C_ <= 0) {
+    if (rdv_) return fail(POVAR_ERR_UNSUPPORTED, "host rendezvous: more ranks than the peer exchange supports");
+    return POVAR_OK;
+  }
   {
     // POVAR_PEER_ALLREDUCE=0: only the per-term exchange uses the peer buffers, the other reductions NCCL
     const char* small = getenv("POVAR_PEER_ALLREDUCE");
-    peer_small_ = !(small != nullptr && std::strcmp(small, "0") == 0);
+    peer_small_ = rdv_ != nullptr || !(small != nullptr && std::strcmp(small, "0") == 0);
   }
   if (world_ == 1) {
-    // POVAR_PEER_EXCHANGE=self: a single GPU runs the exchange protocol against its own buffer (tests on a
-    // one-GPU box; isolates the protocol's cost from the NVLink hop)
+    // POVAR_PEER_EXCHANGE=self: a single GPU runs the exchange protocol against its own buffer (isolates the
+    // protocol's cost from the NVLink hop)
     if (env == nullptr || std::strcmp(env, "self") != 0) return POVAR_OK;
     PeerShared* ps = new PeerShared();
     const size_t bytes = 16 * 2 * static_cast<size_t>(C_) * 12;
-    if (cudaMalloc(&ps->mem, bytes) != cudaSuccess || cudaMemset(ps->mem, 0, bytes) != cudaSuccess) {
+    if (cudaMalloc(&ps->mem, bytes + kPeerCounterBytes) != cudaSuccess ||
+        cudaMemset(ps->mem, 0, bytes + kPeerCounterBytes) != cudaSuccess) {
       delete ps;
       return fail(POVAR_ERR_CUDA, "cudaMalloc failed for the self exchange buffer");
     }
@@ -663,6 +796,7 @@ int Engine::setup_peer_exchange() {
     ps->px.rank = 0;
     ps->px.world = 1;
     ps->px.stride = static_cast<unsigned long long>(C_) * 12;
+    ps->px.count = reinterpret_cast<unsigned int*>(static_cast<char*>(ps->mem) + bytes);
     ps->ok = true;
     peer_ = ps;
     peer_owned_ = true;
@@ -670,6 +804,7 @@ int Engine::setup_peer_exchange() {
     return POVAR_OK;
   }
   if (env != nullptr && std::strcmp(env, "self") == 0) env = nullptr;
+  const bool must = env != nullptr || rdv_ != nullptr;   // asked for explicitly, or no NCCL to fall back to
   const std::string key = comm_key_ + ":" + std::to_string(C_);
   std::lock_guard<std::mutex> lock(comm_cache_mutex());
   auto& cache = peer_cache();
@@ -677,7 +812,7 @@ int Engine::setup_peer_exchange() {
   if (it != cache.end()) {
     peer_ = it->second;
     peer_ok_ = peer_->ok;
-    if (!peer_ok_ && env != nullptr) {
+    if (!peer_ok_ && must) {
       return fail(POVAR_ERR_NCCL, "peer exchange requested but CUDA IPC / peer access is unavailable");
     }
     return POVAR_OK;
@@ -685,17 +820,18 @@ int Engine::setup_peer_exchange() {
   PeerShared* ps = new PeerShared();
   cache[key] = ps;
   peer_ = ps;
+  const int round = rdv_ ? rdv_->next_round++ : 0;
   // 16-byte tagged slots, [2 parities][world][60*C]; zero = "exchange 0", never waited for
   const size_t stride = static_cast<size_t>(C_) * kKron;
   const size_t recv_pad = 16 * 2 * static_cast<size_t>(world_) * stride;
-  const size_t flag_bytes = 0;
   unsigned int ok = 1;
   cudaIpcMemHandle_t mine{};
-  if (cudaMalloc(&ps->mem, recv_pad + flag_bytes) != cudaSuccess) {
+  if (cudaMalloc(&ps->mem, recv_pad + kPeerCounterBytes) != cudaSuccess) {
     ps->mem = nullptr;
     ok = 0;
   }
-  if (ok && cudaMemsetAsync(ps->mem, 0, recv_pad + flag_bytes, stream_) != cudaSuccess) ok = 0;
+  if (ok && cudaMemsetAsync(ps->mem, 0, recv_pad + kPeerCounterBytes, stream_) != cudaSuccess) ok = 0;
+  if (ok && cudaStreamSynchronize(stream_) != cudaSuccess) ok = 0;   // zeroed before any peer can store into it
   if (ok && cudaIpcGetMemHandle(&mine, ps->mem) != cudaSuccess) ok = 0;
   cudaGetLastError();
   // swap: [world][16 words of handle] + [world] ok flags, summed as uint32 (everything else is zero)
@@ -704,14 +840,10 @@ int Engine::setup_peer_exchange() {
   std::vector<unsigned int> host(words, 0u);
   if (ok) std::memcpy(host.data() + 16 * rank_, &mine, 64);
   host[16 * world_ + rank_] = ok;
-  unsigned int* dev = nullptr;
-  PV_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&dev), sizeof(unsigned int) * words, stream_));
-  PV_CUDA(cudaMemcpyAsync(dev, host.data(), sizeof(unsigned int) * words, cudaMemcpyHostToDevice, stream_));
-  if (nccl_->AllReduce(dev, dev, words, /*ncclUint32*/ 3, /*ncclSum*/ 0, nccl_comm_, stream_) != 0) {
-    return fail(POVAR_ERR_NCCL, "ncclAllReduce failed (peer exchange setup)");
+  {
+    const int rc = sum_setup_words(host.data(), words, 0, round);
+    if (rc != POVAR_OK) return rc;
   }
-  PV_CUDA(cudaMemcpyAsync(host.data(), dev, sizeof(unsigned int) * words, cudaMemcpyDeviceToHost, stream_));
-  PV_CUDA(cudaStreamSynchronize(stream_));
   unsigned int all_ok = 1;
   for (int r = 0; r < world_; ++r) all_ok &= host[16 * world_ + r];
   std::vector<void*> base(world_, nullptr);
@@ -735,16 +867,13 @@ int Engine::setup_peer_exchange() {
   }
   // second round: did everybody map everybody?
   unsigned int mapped = all_ok;
-  PV_CUDA(cudaMemcpyAsync(dev, &mapped, sizeof(unsigned int), cudaMemcpyHostToDevice, stream_));
-  if (nccl_->AllReduce(dev, dev, 1, 3, 0, nccl_comm_, stream_) != 0) {
-    return fail(POVAR_ERR_NCCL, "ncclAllReduce failed (peer exchange setup)");
+  {
+    const int rc = sum_setup_words(&mapped, 1, 1, round);
+    if (rc != POVAR_OK) return rc;
   }
-  PV_CUDA(cudaMemcpyAsync(&mapped, dev, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream_));
-  PV_CUDA(cudaStreamSynchronize(stream_));
-  PV_CUDA(cudaFreeAsync(dev, stream_));
   if (mapped != static_cast<unsigned int>(world_)) {
     ps->release();   // the entry stays, marked unavailable: later handles do not try again
-    if (env != nullptr) {   // asked for explicitly: do not hide it
+    if (must) {   // asked for explicitly: do not hide it
       return fail(POVAR_ERR_NCCL, "peer exchange requested but CUDA IPC / peer access is unavailable");
     }
     return POVAR_OK;   // ncclAllReduce per term instead
@@ -755,23 +884,21 @@ int Engine::setup_peer_exchange() {
   ps->px.rank = rank_;
   ps->px.world = world_;
   ps->px.stride = stride;
+  ps->px.count = reinterpret_cast<unsigned int*>(static_cast<char*>(ps->mem) + recv_pad);
   ps->ok = true;
   peer_ok_ = true;
   return POVAR_OK;
 }
 
-const PeerExchange* Engine::next_exchange() {
-  if (!peer_ok_) return nullptr;
-  peer_->px.epoch = ++peer_->epoch;
-  return &peer_->px;
-}
+const PeerExchange* Engine::exchange() const { return peer_ok_ ? &peer_->px : nullptr; }
 
 int Engine::allreduce(double* buf, size_t n) {
   if (world_ <= 1) return POVAR_OK;
   if (peer_ok_ && n <= peer_->px.stride && peer_small_) {
-    launch_peer_allreduce(d_, buf, n, *next_exchange(), lc());
+    launch_peer_allreduce(d_, buf, n, peer_->px, lc());
     return POVAR_OK;
   }
+  if (!nccl_comm_) return fail(POVAR_ERR_NCCL, "reduction needs an NCCL communicator (host rendezvous handle)");
   // ncclDouble = 8, ncclSum = 0
   const int rc = nccl_->AllReduce(buf, buf, n, 8, 0, nccl_comm_, stream_);
   if (rc != 0) return fail(POVAR_ERR_NCCL, "ncclAllReduce failed");
@@ -892,7 +1019,7 @@ int Engine::linearize(bool joint, double alpha) {
 }
 
 // raw_c = sum over the observations of camera c of the camera half of E0 (or of b), all ranks
-void Engine::e0_product(bool joint, const double* y, bool in_series) {
+int Engine::e0_product(bool joint, const double* y, bool in_series) {
   if (e0_v1_) {
     launch_e0_landmark(d_, mp_, joint, y, in_series, lc());
     launch_passB(d_, mp_, joint, PASSB_E0, in_series, lc());
@@ -901,9 +1028,9 @@ void Engine::e0_product(bool joint, const double* y, bool in_series) {
     launch_passB_e0_v2(d_, mp_, joint, in_series, lc());
   }
   // the term kernel adds the item partials itself (and, sharded, exchanges them over peer memory)
-  if (in_series && term_mode() != kTermRaw) return;
+  if (in_series && term_mode() != kTermRaw) return POVAR_OK;
   launch_reduce_items(d_, d_.item_part, 12, d_.cam_raw, in_series, lc());
-  allreduce(d_.cam_raw, static_cast<size_t>(C_) * 12);
+  return allreduce(d_.cam_raw, static_cast<size_t>(C_) * 12);
 }
 
 int Engine::solve_power(bool joint, double lambda) {
@@ -925,8 +1052,9 @@ int Engine::solve_power(bool joint, double lambda) {
   const int m = opt_.power_sc_iterations;
   launch_series_start(d_, opt_.r_tolerance, m, lc());
   for (int i = 1; i <= m; ++i) {
-    e0_product(joint, d_.vec_y, true);
-    launch_series_term(d_, joint, i, opt_.eta, opt_.r_tolerance, term_mode(), next_exchange(), lc());
+    const int rc = e0_product(joint, d_.vec_y, true);
+    if (rc != POVAR_OK) return rc;
+    launch_series_term(d_, joint, i, opt_.eta, opt_.r_tolerance, term_mode(), exchange(), lc());
   }
   PV_CUDA(cudaEventRecord(ev_[2], stream_));
   PV_CUDA(cudaGetLastError());
@@ -996,13 +1124,15 @@ int Engine::read_scalars(double* out, int n) {
 }
 
 // out = S p = B p - E0 p   (the reduced camera system applied implicitly)
-void Engine::schur_product(bool joint, const double* p, double* out) {
+int Engine::schur_product(bool joint, const double* p, double* out) {
   const int n = C_ * (joint ? 11 : 12);
   launch_make_y(d_, joint, p, d_.vec_y, lc());
-  e0_product(joint, d_.vec_y, false);
+  const int rc = e0_product(joint, d_.vec_y, false);
+  if (rc != POVAR_OK) return rc;
   launch_e0_finish(d_, joint, d_.vec_x, lc());
   launch_block_matvec(d_, joint ? 11 : 12, d_.Bmat, p, out, lc());
   launch_axpby(d_, n, 1.0, out, -1.0, d_.vec_x, out, lc());
+  return POVAR_OK;
 }
 
 // ConjugateGradientsSolver::solve / solve_joint (cg/conjugate_gradient.hpp:114-489) with the block-Jacobi
@@ -1054,7 +1184,8 @@ int Engine::solve_pcg(bool joint, double lambda) {
         if (beta == 0.0 || std::isinf(beta)) break;
         launch_axpby(d_, n, 1.0, z, beta, p, p, lc());
       }
-      schur_product(joint, p, q);
+      rc = schur_product(joint, p, q);
+      if (rc != POVAR_OK) return rc;
       launch_dot(d_, n, p, q, 0, lc());
       rc = read_scalars(s, 1);
       if (rc != POVAR_OK) return rc;
@@ -1064,7 +1195,8 @@ int Engine::solve_pcg(bool joint, double lambda) {
       if (std::isinf(alpha)) break;
       launch_axpby(d_, n, 1.0, x, alpha, p, x, lc());
       if (iterations % 10 == 0) {                             // residual_reset_period
-        schur_product(joint, x, tmp);
+        rc = schur_product(joint, x, tmp);
+        if (rc != POVAR_OK) return rc;
         launch_axpby(d_, n, 1.0, b, -1.0, tmp, r, lc());
       } else {
         launch_axpby(d_, n, 1.0, r, -alpha, q, r, lc());
@@ -1154,10 +1286,6 @@ int Engine::solve_cholesky(double lambda) {
   if (!d_.dense_S) PV_ALLOC(d_.dense_S, static_cast<size_t>(n) * n);
   PV_CUDA(cudaMemsetAsync(d_.dense_S, 0, sizeof(double) * static_cast<size_t>(n) * n, stream_));
   launch_dense_schur(d_, mp_, d_.dense_S, lc());
-  if (world_ > 1) {
-    // the diagonal blocks were added on every rank: undo on all but rank 0 before the sum
-    return fail(POVAR_ERR_UNSUPPORTED, "CHOLESKY is single-GPU (the dense reduced system is not sharded)");
-  }
   PV_CUDA(cudaEventRecord(ev_[1], stream_));
   launch_axpby(d_, static_cast<int>(n), -1.0, d_.b, 0.0, nullptr, d_.vec_acc, lc());
   if (!cusolver_) {
@@ -1374,7 +1502,10 @@ int Engine::right_mul_e0(bool joint, const double* x, double* out) {
   const size_t n = static_cast<size_t>(C_) * (joint ? 11 : 12);
   PV_CUDA(cudaMemcpyAsync(d_.vec_x, x, sizeof(double) * n, cudaMemcpyHostToDevice, stream_));
   launch_make_y(d_, joint, d_.vec_x, d_.vec_y, lc());
-  e0_product(joint, d_.vec_y, false);
+  {
+    const int rc = e0_product(joint, d_.vec_y, false);
+    if (rc != POVAR_OK) return rc;
+  }
   launch_e0_finish(d_, joint, d_.vec_x, lc());
   PV_CUDA(cudaGetLastError());
   PV_CUDA(cudaMemcpyAsync(out, d_.vec_x, sizeof(double) * n, cudaMemcpyDeviceToHost, stream_));
@@ -1394,8 +1525,9 @@ int Engine::bench_power_terms(bool joint, int terms, double* seconds_per_term) {
   launch_series_start(d_, -1.0, terms, lc());
   PV_CUDA(cudaEventRecord(ev_[0], stream_));
   for (int i = 1; i <= terms; ++i) {
-    e0_product(joint, d_.vec_y, true);
-    launch_series_term(d_, joint, i, /*eta=*/-1.0, /*r_tolerance=*/-1.0, term_mode(), next_exchange(), lc());
+    const int rc = e0_product(joint, d_.vec_y, true);
+    if (rc != POVAR_OK) return rc;
+    launch_series_term(d_, joint, i, /*eta=*/-1.0, /*r_tolerance=*/-1.0, term_mode(), exchange(), lc());
   }
   PV_CUDA(cudaEventRecord(ev_[1], stream_));
   PV_CUDA(cudaGetLastError());
@@ -1427,7 +1559,7 @@ int Engine::bench_power_kernels(bool joint, int reps, double* seconds) {
           else launch_passB_e0_v2(d_, mp_, joint, true, lc());
           break;
         case 2: launch_reduce_items(d_, d_.item_part, 12, d_.cam_raw, true, lc()); break;
-        default: launch_series_term(d_, joint, i + 1, -1.0, -1.0, term_mode(), next_exchange(), lc()); break;
+        default: launch_series_term(d_, joint, i + 1, -1.0, -1.0, term_mode(), exchange(), lc()); break;
       }
     }
     PV_CUDA(cudaEventRecord(ev_[1], stream_));

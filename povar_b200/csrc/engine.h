@@ -10,6 +10,7 @@ namespace povar {
 
 struct NcclApi;  // dlopen'ed entry points (engine.cu)
 struct PeerShared;
+struct HostRendezvous;
 
 struct PhaseTimes {
   double residual = 0, linearize = 0, prepare = 0, reduced_solve = 0, back_substitution = 0;
@@ -55,15 +56,16 @@ class Engine {
   int allreduce(double* buf, size_t n);
   int setup_peer_exchange();
   TermMode term_mode() const { return peer_ok_ ? kTermPeer : (world_ == 1 ? kTermFused : kTermRaw); }
-  const PeerExchange* next_exchange();   // one epoch per term launch, on every rank alike
+  const PeerExchange* exchange() const;
+  int sum_setup_words(unsigned int* host, int words, int phase, int round);
   void set_model(bool joint, double alpha);
   int solve_power(bool joint, double lambda);
   int solve_pcg(bool joint, double lambda);
   int solve_cholesky(double lambda);
   int prepare_reduced_system(bool joint, double lambda, double lambda_lm);
   int read_scalars(double* out, int n);
-  void schur_product(bool joint, const double* p, double* out);
-  void e0_product(bool joint, const double* y, bool in_series);
+  int schur_product(bool joint, const double* p, double* out);
+  int e0_product(bool joint, const double* y, bool in_series);
   int finish_solve(bool joint, double* inc, int32_t* iterations);
   LaunchCfg lc() { return LaunchCfg{stream_, &launches_}; }
   double elapsed(cudaEvent_t a, cudaEvent_t b);
@@ -91,6 +93,7 @@ class Engine {
   int rank_ = 0, world_ = 1, device_ = 0;
   void* nccl_comm_ = nullptr;
   NcclApi* nccl_ = nullptr;
+  HostRendezvous* rdv_ = nullptr;   // povar_comm_host_id: shared-memory rendezvous instead of a communicator
   // peer-memory exchange of the per-term camera sums (world_ > 1; falls back to ncclAllReduce when
   // CUDA IPC / peer access is not available or the term grid would not be resident)
   // The mapping belongs to a process-wide cache next to the communicator (one per communicator and

@@ -30,6 +30,7 @@ struct AppOptions {
   std::string input;
   std::string log_path = "ba_log.json";
   int num_gpus = 1;
+  std::vector<int> devices;      // --devices: CUDA ordinal of every rank (default: rank r on device r)
   bool create_dataset = false;
   long long dataset_seed = -1;   // < 0: std::random_device, like the reference
   povar_options solver;
@@ -53,7 +54,10 @@ void usage() {
       "  --dump-config  print the effective config and exit\n"
       "  --input <STR>\n  --create-dataset  write data_custom/<name> with randomised camera matrices and exit\n"
       "  --create-dataset-seed <INT> (default: std::random_device, like the reference)\n"
-      "  --num-gpus <INT>\n  --num-threads <INT> (ignored)\n"
+      "  --num-gpus <INT>  ranks (one forked process each; landmarks sharded, cameras replicated)\n"
+      "  --devices <a,b,...>  CUDA ordinal of each rank (default 0,1,...); a repeated ordinal puts several\n"
+      "                       ranks on one GPU and swaps the peer handles through shared memory instead of NCCL\n"
+      "  --num-threads <INT> (ignored)\n"
       "  --solver-type-step-1 {POWER_VARPROJ,POWER_SCHUR_COMPLEMENT,POWER_BUNDLE_ADJUSTMENT,PCG,CHOLESKY}\n"
       "  --solver-type-step-2 {RIPOBA,RIPCG}\n  --power-sc-iterations <INT>\n"
       "  --residual-robust-norm {NONE,HUBER,CAUCHY}\n  --residual-huber-parameter <FLOAT>\n  --alpha <FLOAT>\n"
@@ -84,6 +88,16 @@ bool apply_option(AppOptions& o, const std::string& f, const std::function<std::
     else if (f == "--no-create-dataset") o.create_dataset = false;
     else if (f == "--create-dataset-seed") o.dataset_seed = std::atoll(val().c_str());
     else if (f == "--num-gpus") o.num_gpus = std::atoi(val().c_str());
+    else if (f == "--devices") {
+      o.devices.clear();
+      const std::string v = val();
+      for (size_t p = 0; p < v.size();) {
+        const size_t q = v.find(',', p);
+        o.devices.push_back(std::atoi(v.substr(p, q == std::string::npos ? std::string::npos : q - p).c_str()));
+        if (q == std::string::npos) break;
+        p = q + 1;
+      }
+    }
     else if (f == "--num-threads") val();
     else if (f == "--solver-type-step-1") o.solver.solver_type_step_1 = parse_enum(f, val(), step1);
     else if (f == "--solver-type-step-2") o.solver.solver_type_step_2 = parse_enum(f, val(), step2);
@@ -262,6 +276,7 @@ AppOptions parse(int argc, char** argv) {
   }
   if (o.input.empty()) die("--input is required");
   if (o.num_gpus < 1) die("--num-gpus must be >= 1");
+  if (!o.devices.empty() && static_cast<int>(o.devices.size()) != o.num_gpus) die("--devices needs one ordinal per rank");
   return o;
 }
 
@@ -335,10 +350,14 @@ int main(int argc, char** argv) {
   std::memset(&comm, 0, sizeof(comm));
   comm.rank = rank;
   comm.world_size = o.num_gpus;
-  comm.device = rank;
+  comm.device = o.devices.empty() ? rank : o.devices[rank];
   if (o.num_gpus > 1) {
     if (rank == 0) {
-      rc = povar_comm_unique_id(comm.nccl_id);
+      // ranks that share a device cannot form an NCCL communicator: host rendezvous (povar_comm_host_id)
+      std::vector<int> sorted = o.devices;
+      std::sort(sorted.begin(), sorted.end());
+      const bool shared_device = std::adjacent_find(sorted.begin(), sorted.end()) != sorted.end();
+      rc = shared_device ? povar_comm_host_id(comm.nccl_id) : povar_comm_unique_id(comm.nccl_id);
       if (rc != POVAR_OK) die(std::string("NCCL: ") + povar_last_error(nullptr));
       for (int w : write_fds) {
         if (write(w, comm.nccl_id, 128) != 128) die("pipe write failed");

@@ -824,25 +824,28 @@ __device__ __forceinline__ void series_decide(double s0, double s1, int term, do
   }
 }
 
-// Peer exchange, low-latency protocol: a double travels as ONE 16-byte store {lo, epoch, hi, epoch};
-// the receiver polls the slot until both tags carry the epoch it waits for (each 8-byte half is written
-// atomically, so a torn line is recognised and re-read).  No fence, no separate flag: the latency of an
-// exchange is one NVLink store.
+// Peer exchange, low-latency protocol: a double travels as ONE 16-byte store of two 8-byte words
+// {lo | number << 32, hi | number << 32}; the receiver polls the slot until both words carry the number of the
+// exchange it waits for.  PTX guarantees single-copy atomicity per ELEMENT of a vector access, so each
+// {value half, tag} pair is one 64-bit element: a reader sees a half either with its own tag or not at all,
+// and a slot whose two tags match holds one value.  No fence, no separate flag: the latency of an exchange is
+// one NVLink store.
 __device__ __forceinline__ void st_tagged(double* slot, double v, unsigned int epoch) {
   const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(v));
-  const unsigned int lo = static_cast<unsigned int>(bits), hi = static_cast<unsigned int>(bits >> 32);
-  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(slot), "r"(lo), "r"(epoch), "r"(hi),
-               "r"(epoch)
-               : "memory");
+  const unsigned long long tag = static_cast<unsigned long long>(epoch) << 32;
+  const unsigned long long a = (bits & 0xffffffffULL) | tag, b = (bits >> 32) | tag;
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(a), "l"(b) : "memory");
 }
 __device__ __forceinline__ bool ld_tagged(const double* slot, unsigned int epoch, double& v) {
-  unsigned int lo, t0, hi, t1;
-  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(lo), "=r"(t0), "=r"(hi), "=r"(t1)
-               : "l"(slot)
-               : "memory");
-  v = __longlong_as_double(static_cast<long long>((static_cast<unsigned long long>(hi) << 32) | lo));
-  return t0 == epoch && t1 == epoch;
+  unsigned long long a, b;
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(slot) : "memory");
+  v = __longlong_as_double(static_cast<long long>((b << 32) | (a & 0xffffffffULL)));
+  return static_cast<unsigned int>(a >> 32) == epoch && static_cast<unsigned int>(b >> 32) == epoch;
+}
+// number of the exchange a kernel is about to perform: one more than the buffer has seen (written by the last
+// block of the previous exchanging kernel on this stream)
+__device__ __forceinline__ unsigned int next_exchange_number(const PeerExchange& px) {
+  return *reinterpret_cast<volatile const unsigned int*>(px.count) + 1u;
 }
 __device__ __forceinline__ long long global_ns() {
   unsigned long long t;
@@ -880,7 +883,9 @@ k_term16(int C, const double* __restrict__ raw_in, const int* __restrict__ cam_i
   // decoupled look-back scan), so on every rank the lowest-numbered unfinished block is running and
   // has already sent: the exchange makes progress even when the grid is larger than one wave.
   unsigned int bid = blockIdx.x;
+  unsigned int epoch = 0;
   if (MODE == kTermPeer) {
+    epoch = next_exchange_number(px);   // before this block's ticket: the last block advances the count
     __shared__ unsigned int s_bid;
     if (threadIdx.x == 0) s_bid = atomicAdd(&ctl->next_block, 1u);
     __syncthreads();
@@ -915,13 +920,13 @@ k_term16(int C, const double* __restrict__ raw_in, const int* __restrict__ cam_i
     }
     if (MODE == kTermPeer) {
       // slots are 16 bytes (2 doubles wide): [parity][source rank][stride], the first 12*C of a rank used here
-      const int par = static_cast<int>(px.epoch & 1u);
+      const int par = static_cast<int>(epoch & 1u);
       const size_t vec = static_cast<size_t>(px.stride);
       const size_t mine_at = 2 * ((static_cast<size_t>(par) * px.world + px.rank) * vec + 12 * static_cast<size_t>(c) + lane16);
       if (live && lane16 < 12) {
 #pragma unroll
         for (int r = 0; r < kMaxPeers; ++r) {
-          if (r < px.world) st_tagged(px.recv[r] + mine_at, mine, px.epoch);
+          if (r < px.world) st_tagged(px.recv[r] + mine_at, mine, epoch);
         }
       }
       // collect the ranks' sums (all polls of a round are in flight together), then add them in rank
@@ -940,7 +945,7 @@ k_term16(int C, const double* __restrict__ raw_in, const int* __restrict__ cam_i
           for (int r = 0; r < kMaxPeers; ++r) {
             if ((pending >> r) & 1u) {
               double got;
-              if (ld_tagged(rb + 2 * r * vec, px.epoch, got)) {
+              if (ld_tagged(rb + 2 * r * vec, epoch, got)) {
                 v[r] = got;
                 pending &= ~(1u << r);
               }
@@ -1022,6 +1027,7 @@ k_term16(int C, const double* __restrict__ raw_in, const int* __restrict__ cam_i
   if (threadIdx.x == 0) {
     ctl->ticket = 0;
     ctl->next_block = 0;
+    if (MODE == kTermPeer) *px.count = epoch;   // this exchange happened (skipped terms never get here)
     series_decide(s0, s1, term, eta, r_tolerance, ctl);
   }
 }
@@ -1243,7 +1249,8 @@ void launch_series_start(const DeviceState& d, double r_tolerance, int max_terms
 // grid-stride launch cannot deadlock.
 __global__ void __launch_bounds__(kBlock)
 k_peer_allreduce(double* __restrict__ buf, size_t n, PeerExchange px, SeriesCtl* ctl) {
-  const int par = static_cast<int>(px.epoch & 1u);
+  const unsigned int epoch = next_exchange_number(px);
+  const int par = static_cast<int>(epoch & 1u);
   const size_t stride = static_cast<size_t>(px.stride);
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -1251,7 +1258,7 @@ k_peer_allreduce(double* __restrict__ buf, size_t n, PeerExchange px, SeriesCtl*
     const size_t at = 2 * ((static_cast<size_t>(par) * px.world + px.rank) * stride + i);
 #pragma unroll
     for (int r = 0; r < kMaxPeers; ++r) {
-      if (r < px.world) st_tagged(px.recv[r] + at, mine, px.epoch);
+      if (r < px.world) st_tagged(px.recv[r] + at, mine, epoch);
     }
     const double* rb = px.recv[px.rank] + 2 * (static_cast<size_t>(par) * px.world * stride + i);
     double v[kMaxPeers];
@@ -1265,7 +1272,7 @@ k_peer_allreduce(double* __restrict__ buf, size_t n, PeerExchange px, SeriesCtl*
       for (int r = 0; r < kMaxPeers; ++r) {
         if ((pending >> r) & 1u) {
           double got;
-          if (ld_tagged(rb + 2 * r * stride, px.epoch, got)) {
+          if (ld_tagged(rb + 2 * r * stride, epoch, got)) {
             v[r] = got;
             pending &= ~(1u << r);
           }
@@ -1287,6 +1294,16 @@ k_peer_allreduce(double* __restrict__ buf, size_t n, PeerExchange px, SeriesCtl*
     }
     // a peer that never answered: poison the result so that the caller's finiteness checks trip
     buf[i] = pending != 0u ? __longlong_as_double(0x7ff8000000000000LL) : sum;
+  }
+  // the last block to finish advances the exchange count (every block has read it by then)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int prev = atomicAdd(px.count + 1, 1u);
+    if (prev == gridDim.x - 1) {
+      px.count[1] = 0;
+      px.count[0] = epoch;
+    }
   }
 }
 

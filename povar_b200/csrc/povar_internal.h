@@ -75,8 +75,10 @@ constexpr int kMaxPeers = 8;
 struct PeerExchange {
   double* recv[kMaxPeers];
   int rank, world;
-  unsigned int epoch;   // number of this exchange (> 0); parity = epoch & 1
-  unsigned int pad;
+  // count[0]: exchanges performed so far on this buffer (device memory, local); the next exchange has number
+  // count[0] + 1 (its tag; parity = number & 1) and the kernel that performs it stores the new count.
+  // count[1]: block ticket of k_peer_allreduce.
+  unsigned int* count;
   unsigned long long stride;
 };
 // where k_term16 takes the reduced camera sums from

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/povar_b200.h but not exported"
     assert set(names) == set(capi.SIGNATURES), set(names) ^ set(capi.SIGNATURES)
-    assert lib.povar_abi_version() == 2
+    assert lib.povar_abi_version() == 3
 
 
 def test_option_defaults_are_the_reference_code_defaults():
@@ -420,7 +420,7 @@ def test_ctypes_structs_have_the_library_s_layout():
     """capi.py mirrors the public structs by hand; a size mismatch would corrupt memory in povar_bundle_adjust."""
     lib = capi.load()
     mirrors = [capi.Options, capi.ProblemDesc, capi.CommDesc, capi.ResidualInfo, capi.Iteration, capi.SolveSummary,
-               capi.BalData, capi.BaLogInfo]
+               capi.BalData, capi.BaLogInfo, capi.PhaseTimes]
     for which, cls in enumerate(mirrors):
         assert lib.povar_abi_sizeof(which) == ctypes.sizeof(cls), cls.__name__
     assert lib.povar_abi_sizeof(99) == -1
