@@ -295,20 +295,17 @@ struct Reflector {
 };
 
 // ---- per-camera record gathered by the landmark-major half of E0 (kernels_series.cu) -----------
-// Four lanes share one observation; lane `sub` reads 16-byte chunk 4 p + sub in its p-th load, so
-// each load of a group covers 64 aligned bytes (two whole sectors) instead of one line per lane.
-// 24 doubles = 192 bytes per camera, both models:
-//   lanes 0..2:  (y_sub[0], y_sub[1]) | (y_sub[2], y_sub[3]) | (M[0][sub], M[1][sub])
-//   lane 3:      (M[2][0], M[2][1])   | (M[2][2], M[2][3])   | (M[0][3], M[1][3])
-// y = the vector the product is applied to (three 4-blocks), M = P (step 1 uses M[:, 0:3] only and
-// keeps zeros in column 3).
+// One lane handles one observation and reads the whole record of its camera from shared memory in 16-byte
+// units: y (the vector the product is applied to, three 4-blocks, 12 doubles), then M = P[:, 0:3] row-major
+// (step 1, 9 doubles + 1 pad) or M = P (step 2, 12 doubles + 2 pad).  The stride is an ODD number of units
+// (11 resp. 13): unit j of camera c falls into bank group (stride * c + j) mod 8, so the eight lanes of a
+// shared-memory wavefront -- eight different cameras, same j -- spread over the bank groups like their camera
+// numbers mod 8 instead of all landing on one.
 struct CamRec {
-  static constexpr int kStride = 24;   // doubles per camera
-  __host__ __device__ static constexpr int y_index(int k, int j) {
-    return 2 * (4 * (j >> 1) + k) + (j & 1);
-  }
-  __host__ __device__ static constexpr int m_index(int r, int n) {
-    return r < 2 ? (n < 3 ? 16 + 2 * n + r : 22 + r) : (n < 2 ? 6 + n : 12 + n);
+  __host__ __device__ static constexpr int stride(bool joint) { return joint ? 26 : 22; }   // doubles
+  __host__ __device__ static constexpr int y_index(int k, int j) { return 4 * k + j; }
+  __host__ __device__ static constexpr int m_index(bool joint, int r, int n) {
+    return joint ? 12 + 4 * r + n : 12 + 3 * r + n;
   }
 };
 

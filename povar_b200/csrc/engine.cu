@@ -274,19 +274,20 @@ void build_tiles(const std::vector<int>& lm_ptr, std::vector<int>* tile_ptr) {
   if (tile_ptr->size() == 1 && L >= 0 && lm_ptr[L] == 0) tile_ptr->clear(), tile_ptr->push_back(0);
 }
 
-// Sliced ELL order of the landmarks with 1..32 observations (the landmark half of E0 gives a group of
-// four lanes to each landmark and walks its observations serially, so the eight landmarks of a slice
-// should have the same degree).  Landmarks are first put in the order of their MEDIAN camera (stable
+// Sliced ELL order of the landmarks with 1..32 observations (the landmark half of E0 gives a lane
+// to each landmark and walks its observations serially, so the 32 landmarks of a slice should have the
+// same degree).  Landmarks are first put in the order of their MEDIAN camera (stable
 // counting sort): neighbouring slices then gather from neighbouring camera records, which is what lets
 // the per-camera table stay in L1 (the slices of one SM come from one stretch of this order,
 // kernels_series.cu).  Inside windows of `window` landmarks of that order: stable sort by descending
-// degree, eight landmarks per slice, slice length = largest degree in it.  The order of the
+// degree, kSellWidth landmarks per slice, slice length = largest degree in it.  The order of the
 // observations INSIDE a landmark is untouched (camera ascending), so every H_l keeps its bits.
 void build_sell(const std::vector<int>& lm_ptr, const int* obs_cam, int num_cams, int window,
                 SellLayout* out) {
   const int L = static_cast<int>(lm_ptr.size()) - 1;
   out->slice_ptr.assign(1, 0);
   out->sell_lm.clear();
+  out->slice_cam.clear();
   out->long_lms.clear();
   out->rows = 0;
   if (L <= 0) return;
@@ -325,10 +326,12 @@ void build_sell(const std::vector<int>& lm_ptr, const int* obs_cam, int num_cams
   // windows of `window` landmarks of that order, each sorted (stably) by descending degree and cut into
   // slices of eight: the windows are independent, and where a window's slices go is known up front
   const int num_windows = (n + window - 1) / window;
-  const int slices_per_full = (window + 7) / 8;
+  const int W = kSellWidth;
+  const int slices_per_full = (window + W - 1) / W;
   const int last_cnt = n - (num_windows - 1) * window;
-  const int num_slices = num_windows == 0 ? 0 : (num_windows - 1) * slices_per_full + (last_cnt + 7) / 8;
-  out->sell_lm.assign(static_cast<size_t>(num_slices) * 8, -1);
+  const int num_slices = num_windows == 0 ? 0 : (num_windows - 1) * slices_per_full + (last_cnt + W - 1) / W;
+  out->sell_lm.assign(static_cast<size_t>(num_slices) * W, -1);
+  out->slice_cam.assign(static_cast<size_t>(num_slices), 0);
   std::vector<int> slice_len(static_cast<size_t>(num_slices), 0);
   parallel_chunks(T, [&](int t) {
     int head[34];
@@ -343,9 +346,10 @@ void build_sell(const std::vector<int>& lm_ptr, const int* obs_cam, int num_cams
       for (int i = w0; i < w1; ++i) order[head[32 - (lm_ptr[by_cam[i] + 1] - lm_ptr[by_cam[i]])]++] = by_cam[i];
       const int cnt = w1 - w0;
       int sl = w * slices_per_full;
-      for (int i = 0; i < cnt; i += 8, ++sl) {
+      for (int i = 0; i < cnt; i += W, ++sl) {
         slice_len[sl] = lm_ptr[order[i] + 1] - lm_ptr[order[i]];   // the largest degree of the slice
-        for (int g = 0; g < 8 && i + g < cnt; ++g) out->sell_lm[static_cast<size_t>(sl) * 8 + g] = order[i + g];
+        out->slice_cam[sl] = key(by_cam[w0]);                      // the window's smallest median camera
+        for (int g = 0; g < W && i + g < cnt; ++g) out->sell_lm[static_cast<size_t>(sl) * W + g] = order[i + g];
       }
     }
   });
@@ -601,7 +605,7 @@ int Engine::upload(const povar_problem_desc* desc) {
   SellLayout sell;
   build_sell(lm_ptr, desc->obs_cam, C, kSellWindow, &sell);
   lap("sliced-ELL order");
-  if (static_cast<long long>(sell.rows) * 8 >= (1LL << 31)) {
+  if (static_cast<long long>(sell.rows) * kSellWidth >= (1LL << 31)) {
     return fail(POVAR_ERR_UNSUPPORTED, "sliced-ELL layout exceeds 2^31 slots in one shard");
   }
 
@@ -612,7 +616,7 @@ int Engine::upload(const povar_problem_desc* desc) {
   ix.num_tiles = static_cast<int>(tile_ptr.size()) - 1;
   ix.num_items = static_cast<int>(item_cam.size());
   ix.num_slices = static_cast<int>(sell.slice_ptr.size()) - 1;
-  ix.sell_slots = 8LL * sell.rows;
+  ix.sell_slots = static_cast<long long>(kSellWidth) * sell.rows;
   ix.num_long = static_cast<int>(sell.long_lms.size());
   const size_t slots = static_cast<size_t>(ix.sell_slots);
   PV_ALLOC(ix.lm_ptr, L + 1);
@@ -628,6 +632,7 @@ int Engine::upload(const povar_problem_desc* desc) {
   PV_ALLOC(ix.cam_item_ptr, C + 1);
   PV_ALLOC(ix.slice_ptr, sell.slice_ptr.size());
   PV_ALLOC(ix.sell_lm, sell.sell_lm.size());
+  PV_ALLOC(ix.slice_cam, sell.slice_cam.size());
   PV_ALLOC(ix.sell_cam, slots);
   PV_ALLOC(ix.sell_uv, slots);
   PV_ALLOC(ix.obs_slot, nnz);
@@ -642,6 +647,7 @@ int Engine::upload(const povar_problem_desc* desc) {
   PV_UP(ix.tile_ptr, tile_ptr.data(), sizeof(int) * tile_ptr.size());
   PV_UP(ix.slice_ptr, sell.slice_ptr.data(), sizeof(int) * sell.slice_ptr.size());
   if (!sell.sell_lm.empty()) PV_UP(ix.sell_lm, sell.sell_lm.data(), sizeof(int) * sell.sell_lm.size());
+  if (!sell.slice_cam.empty()) PV_UP(ix.slice_cam, sell.slice_cam.data(), sizeof(int) * sell.slice_cam.size());
   if (ix.num_long > 0) PV_UP(ix.long_lm, sell.long_lms.data(), sizeof(int) * sell.long_lms.size());
   PV_UP(ix.cam_ptr, cam_ptr.data(), sizeof(int) * (C + 1));
   PV_UP(ix.item_ptr, item_ptr.data(), sizeof(int) * item_ptr.size());
@@ -677,7 +683,9 @@ int Engine::upload(const povar_problem_desc* desc) {
   PV_ALLOC(d_.hll_inv, static_cast<size_t>(L) * 6);
   PV_ALLOC(d_.lm_rec, static_cast<size_t>(L) * kLmRec);
   PV_ALLOC(d_.lm_fold, static_cast<size_t>(L) * 10);
-  PV_ALLOC(d_.cam_rec, static_cast<size_t>(C) * 28);
+  PV_ALLOC(d_.cam_rec, static_cast<size_t>(C) * kCamRecStride);
+  PV_ALLOC(d_.sell_x, static_cast<size_t>(ix.num_slices) * 4 * kSellWidth);
+  PV_ALLOC(d_.sell_fold, static_cast<size_t>(ix.num_slices) * 10 * kSellWidth);
   PV_ALLOC(d_.kron, static_cast<size_t>(C) * kKron);
   PV_ALLOC(d_.kron2, static_cast<size_t>(C) * kKron);
   PV_ALLOC(d_.item_kron, static_cast<size_t>(ix.num_items) * kKron);
@@ -1039,6 +1047,7 @@ int Engine::solve_power(bool joint, double lambda) {
   PV_CUDA(cudaEventRecord(ev_[0], stream_));
   // prepare_Hb_*: Hll^-1 and Hll^-1 Jl^T r per landmark; B^-1 per camera; b
   launch_prep_landmark(d_, joint, lambda_lm, lc());
+  launch_sell_pack(d_, joint, lc());
   launch_cam_binv(d_, joint, lambda, lc());
   launch_passB(d_, mp_, joint, PASSB_B, false, lc());
   launch_reduce_items(d_, d_.item_part, 12, d_.cam_raw, false, lc());
@@ -1108,6 +1117,7 @@ int Engine::solve(bool joint, double lambda, double* inc, int32_t* iterations) {
 // b (and B, B^-1) exactly as the power solvers build them; shared by PCG / RIPCG / CHOLESKY
 int Engine::prepare_reduced_system(bool joint, double lambda, double lambda_lm) {
   launch_prep_landmark(d_, joint, lambda_lm, lc());
+  launch_sell_pack(d_, joint, lc());
   launch_cam_binv(d_, joint, lambda, lc());
   launch_passB(d_, mp_, joint, PASSB_B, false, lc());
   launch_reduce_items(d_, d_.item_part, 12, d_.cam_raw, false, lc());
@@ -1471,7 +1481,7 @@ int64_t Engine::debug_read(const char* name, double* out, int64_t capacity) {
   else if (n == "item_ptr") isrc = d_.ix.item_ptr, count = d_.ix.num_items + 1;
   else if (n == "item_cam") isrc = d_.ix.item_cam, count = d_.ix.num_items;
   else if (n == "slice_ptr") isrc = d_.ix.slice_ptr, count = d_.ix.num_slices + 1;
-  else if (n == "sell_lm") isrc = d_.ix.sell_lm, count = 8LL * d_.ix.num_slices;
+  else if (n == "sell_lm") isrc = d_.ix.sell_lm, count = static_cast<int64_t>(kSellWidth) * d_.ix.num_slices;
   else if (n == "sell_cam") isrc = d_.ix.sell_cam, count = d_.ix.sell_slots;
   else if (n == "obs_slot") isrc = d_.ix.obs_slot, count = nnz_;
   else {

@@ -111,6 +111,7 @@ class Engine {
 struct SellLayout {
   std::vector<int> slice_ptr;   // [num_slices+1] rows
   std::vector<int> sell_lm;     // [8*num_slices]
+  std::vector<int> slice_cam;   // [num_slices] median camera of the slice's first landmark (non-decreasing)
   std::vector<int> long_lms;    // landmarks with more than 32 observations
   int rows = 0;
 };

@@ -753,7 +753,7 @@ k_finish_b(int C, const double* __restrict__ raw, const double* __restrict__ pos
     acc[static_cast<size_t>(c) * D + i] = v;
   }
   reduced_to_y<JOINT>(x0, s, Pc, y + 12 * static_cast<size_t>(c),
-                      cam_rec + CamRec::kStride * static_cast<size_t>(c));
+                      cam_rec + CamRec::stride(JOINT) * static_cast<size_t>(c));
   norm_part[2 * c] = n2;
   norm_part[2 * c + 1] = n2;
 }
@@ -787,7 +787,7 @@ k_term(int C, const double* __restrict__ raw, const double* __restrict__ pose_sc
     tmp[static_cast<size_t>(c) * D + i] = v;
   }
   reduced_to_y<JOINT>(t, s, Pc, y + 12 * static_cast<size_t>(c),
-                      cam_rec + CamRec::kStride * static_cast<size_t>(c));
+                      cam_rec + CamRec::stride(JOINT) * static_cast<size_t>(c));
   norm_part[2 * c] = nt;
   norm_part[2 * c + 1] = na;
 }
@@ -1006,7 +1006,7 @@ k_term16(int C, const double* __restrict__ raw_in, const int* __restrict__ cam_i
 #pragma unroll
     for (int i = 0; i < 12; ++i) mine = (i == lane16) ? yv[i] : mine;
     y[12 * static_cast<size_t>(c) + lane16] = mine;
-    cam_rec[CamRec::kStride * static_cast<size_t>(c) + CamRec::y_index(lane16 >> 2, lane16 & 3)] = mine;
+    cam_rec[CamRec::stride(JOINT) * static_cast<size_t>(c) + CamRec::y_index(lane16 >> 2, lane16 & 3)] = mine;
   }
   if (live && lane16 == 0) {
     norm_part[2 * c] = nt;
@@ -1073,7 +1073,7 @@ k_make_y(int C, const double* __restrict__ x, const double* __restrict__ pose_sc
   for (int i = 0; i < D; ++i) xv[i] = x[static_cast<size_t>(c) * D + i];
   reduced_to_y<JOINT>(xv, pose_scale + 12 * static_cast<size_t>(c), P + 12 * static_cast<size_t>(c),
                       y + 12 * static_cast<size_t>(c),
-                      cam_rec + CamRec::kStride * static_cast<size_t>(c));
+                      cam_rec + CamRec::stride(JOINT) * static_cast<size_t>(c));
 }
 
 // P += reshape(v)   (Camera::inc_pose_pOSE / inc_pose_projective_space, bal_problem.hpp:132-163)

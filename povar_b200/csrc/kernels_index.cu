@@ -50,7 +50,7 @@ k_lm_slot(int groups, const int* __restrict__ slice_ptr, const int* __restrict__
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= groups) return;
   const int lm = sell_lm[i];
-  if (lm >= 0) lm_slot[lm] = 8 * slice_ptr[i >> 3] + (i & 7);
+  if (lm >= 0) lm_slot[lm] = kSellWidth * slice_ptr[i / kSellWidth] + (i % kSellWidth);
 }
 
 __global__ void __launch_bounds__(kBlock)
@@ -64,7 +64,7 @@ k_sell_fill(int nnz, const int* __restrict__ lm_ptr, const int* __restrict__ obs
   const int base = lm_slot[l];
   int slot = -1;
   if (base >= 0) {
-    slot = base + 8 * (o - lm_ptr[l]);
+    slot = base + kSellWidth * (o - lm_ptr[l]);
     sell_cam[slot] = obs_cam[o];
     sell_uv[slot] = obs_uv[o];
   }
@@ -105,7 +105,7 @@ cudaError_t build_device_index(const DeviceIndex& ix, int* iota, int* keys_out, 
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(ix.sell_cam, 0xFF, sizeof(int) * static_cast<size_t>(ix.sell_slots), st);
     if (e != cudaSuccess) return e;
-    const int groups = 8 * ix.num_slices;
+    const int groups = kSellWidth * ix.num_slices;
     if (groups > 0) {
       k_lm_slot<<<(groups + kBlock - 1) / kBlock, kBlock, 0, st>>>(groups, ix.slice_ptr, ix.sell_lm, lm_slot);
       ++launches;

@@ -264,10 +264,11 @@ k_lin_landmark(DeviceIndex ix, const double* __restrict__ P, const double* __res
           dp[2] = d2;
           const int slot = __ldg(ix.obs_slot + o);
           if (slot >= 0) {
-            double* sp = sell_d + 3 * static_cast<size_t>(slot);
+            // [row][coefficient][lane]: what a warp of the landmark half reads is one line per coefficient
+            double* sp = sell_d + 3 * static_cast<size_t>(slot - (slot % kSellWidth)) + (slot % kSellWidth);
             sp[0] = d0;
-            sp[1] = d1;
-            sp[2] = d2;
+            sp[kSellWidth] = d1;
+            sp[2 * kSellWidth] = d2;
           }
         }
         int n = 0;

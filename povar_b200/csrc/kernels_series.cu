@@ -1,15 +1,6 @@
-// The two halves of one power-series term,  raw_c = sum_l Jp^T Jl Hll^-1 Jl^T Jp y,  in the
-// lane-group layout.  Replaces right_mul_e0_pOSE / right_mul_e0_joint
+// The two halves of one power-series term,  raw_c = sum_l Jp^T Jl Hll^-1 Jl^T Jp y.  Replaces
+// right_mul_e0_pOSE / right_mul_e0_joint
 // (/root/reference/src/rootba_povar/sc/linearization_power_varproj.hpp:364-453).
-//
-// Why not one observation per lane (kernels_landmark.cu k_e0_landmark, kernels_camera.cu k_passB):
-// every observation needs ~170 bytes of its camera (landmark half) or 64 bytes of its landmark
-// (camera half) from a table that lives in L1/L2.  With one observation per lane each LDG.128
-// touches 32 different cache lines; L1TEX, not HBM, bounded those kernels (tools/ubench_gather.cu,
-// profiles/).  Here a small group of lanes shares an observation and reads consecutive 16-byte
-// chunks of the record (whole sectors), the arithmetic is split along the same lines (each lane
-// owns one row / column of the 3x4 blocks), and the only cross-lane traffic is a 3-value exchange
-// per observation.
 //
 // Both observation models have  Jp_raw = K (x) X^T  and  Jl_raw = K M  with a small K that depends on
 // the observation only (step 1: K_i(u, v, c1, c2) 4x3, M = P[:, 0:3]; step 2: K_i = d_i 2x3, M = P), so
@@ -17,6 +8,16 @@
 //   camera half:    raw_c = sum_i ((K^T W K) (M H_l)) (x) X_l
 // where Y_c is y_c as a 3x4 matrix and fold_l = S (Pi) Hll^-1 (Pi^T) S is made once per solve
 // (k_prep_landmark).  Step 2 streams sqrt(w) d_i, stored at the linearisation point.
+//
+// Landmark half: one LANE per landmark (sliced ELL, 32 landmarks of nearly equal degree per slice, the k-th
+// observations of the 32 landmarks in one row), the camera records in shared memory.  History, because it
+// explains the shape: with one observation per lane and the records in global memory every LDG.128 touched
+// 32 cache lines (round 1, v1); four lanes per observation reading 64-byte chunks fixed the gathers but spent
+// 4x the instructions on redundant arithmetic and a 3-value exchange per observation -- that kernel ran at
+// half the issue rate of its 32 warps per SM and scaled with nothing but the warp count (this round's
+// profiles).  From shared memory a whole 176-byte record per lane is cheap (eleven LDS.128, conflicts limited
+// by the odd record stride), nothing is computed twice and nothing is exchanged.
+// Camera half: two lanes per entry, the landmark records gathered from L2.
 #include <cuda_runtime.h>
 
 #include <cstdlib>
@@ -62,124 +63,151 @@ __device__ __forceinline__ void joint_normal_coef(double q0, double q1, double q
   m[2] = d02 * a0 + d12 * a1;
 }
 
-// One observation of the landmark half, seen from one lane of its 4-lane group.  L0..L2 are the
-// lane's three chunks of the camera record (CamRec): lanes 0..2 make q_sub = y_sub . X, everybody
-// receives q, and the products with M are accumulated where the entries of M live:
-//   lanes 0..2:  acc[0] += M[0][sub] m0 + M[1][sub] m1
-//   lane 3:      acc[n] += M[2][n] m2  (n = 0..3),  acc[3] += M[0][3] m0 + M[1][3] m1
-// (combined once per landmark by group_totals).
 struct ObsCoef {
   double a, b, c;   // step 1: u, v, w;  step 2: sqrt(w) (1/z, -x/z^2, -y/z^2)
 };
 
-template <bool JOINT>
-__device__ __forceinline__ void landmark_obs(const double2& L0, const double2& L1, const double2& L2,
-                                             const double (&x)[4], const ObsCoef& k, double c1,
-                                             double c2, int sub, int gb, bool act, double (&acc)[4]) {
-  const double q = L0.x * x[0] + L0.y * x[1] + L1.x * x[2] + L1.y * x[3];
-  const double q0 = __shfl_sync(kFullMask, q, gb);
-  const double q1 = __shfl_sync(kFullMask, q, gb + 1);
-  const double q2 = __shfl_sync(kFullMask, q, gb + 2);
-  double m[3];
-  if (JOINT) {
-    joint_normal_coef(q0, q1, q2, k.a, k.b, k.c, m);
-  } else {
-    pose_normal_coef(q0, q1, q2, k.a, k.b, k.c, c1, c2, m);
-  }
-  if (act) {
-    const double e0 = L2.x * m[0] + L2.y * m[1];
-    acc[0] += sub < 3 ? e0 : L0.x * m[2];
-    acc[1] += L0.y * m[2];
-    acc[2] += L1.x * m[2];
-    acc[3] += L1.y * m[2] + e0;
-  }
-}
-
-// G_l on every lane of the group from the per-lane accumulators above
-template <bool JOINT>
-__device__ __forceinline__ void group_totals(const double (&acc)[4], int gb, double (&G)[4]) {
-  G[0] = __shfl_sync(kFullMask, acc[0], gb) + __shfl_sync(kFullMask, acc[0], gb + 3);
-  G[1] = __shfl_sync(kFullMask, acc[0], gb + 1) + __shfl_sync(kFullMask, acc[1], gb + 3);
-  G[2] = __shfl_sync(kFullMask, acc[0], gb + 2) + __shfl_sync(kFullMask, acc[2], gb + 3);
-  G[3] = JOINT ? __shfl_sync(kFullMask, acc[3], gb + 3) : 0.0;
-}
-
-// H[sub] = row `sub` of fold_l times G  (fold packed symmetric: 3x3 in step 1, 4x4 in step 2)
-template <bool JOINT>
-__device__ __forceinline__ double fold_row(const double* __restrict__ f, int sub, const double (&G)[4]) {
-  if (JOINT) {
-    double F[10];
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-      const double2 t = ldg2(f + 2 * k);
-      F[2 * k] = t.x;
-      F[2 * k + 1] = t.y;
-    }
-    const double r0 = sub == 0 ? F[0] : (sub == 1 ? F[1] : (sub == 2 ? F[2] : F[3]));
-    const double r1 = sub == 0 ? F[1] : (sub == 1 ? F[4] : (sub == 2 ? F[5] : F[6]));
-    const double r2 = sub == 0 ? F[2] : (sub == 1 ? F[5] : (sub == 2 ? F[7] : F[8]));
-    const double r3 = sub == 0 ? F[3] : (sub == 1 ? F[6] : (sub == 2 ? F[8] : F[9]));
-    return r0 * G[0] + r1 * G[1] + r2 * G[2] + r3 * G[3];
-  }
-  double F[6];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const double2 t = ldg2(f + 2 * k);
-    F[2 * k] = t.x;
-    F[2 * k + 1] = t.y;
-  }
-  const double r0 = sub == 0 ? F[0] : (sub == 1 ? F[1] : F[2]);
-  const double r1 = sub == 0 ? F[1] : (sub == 1 ? F[3] : F[4]);
-  const double r2 = sub == 0 ? F[2] : (sub == 1 ? F[4] : F[5]);
-  return sub < 3 ? r0 * G[0] + r1 * G[1] + r2 * G[2] : 0.0;
-}
-
 // ------------------------------------------------------------------------------------------
-// landmark half, sliced-ELL order (DeviceIndex::slice_ptr ...): a warp walks a contiguous range of
-// slices; a slice is eight landmarks of (nearly) equal degree, four lanes per landmark.  The group
-// visits the observations of its landmark in camera order and keeps its part of G_l in registers:
-// no tile table, no shared memory, no segmented reduction.
+// landmark half, sliced-ELL order (DeviceIndex::slice_ptr ...): a warp walks a contiguous range of slices;
+// a slice is 32 landmarks of (nearly) equal degree, one per lane; the lane visits the observations of its
+// landmark in camera order and keeps G_l in registers: no tile table, no reduction, no exchange.
 //
-// Software pipeline: the rows of a warp's range are contiguous and every slice has an even number
-// of rows, so rows alternate between two register sets A / B regardless of slice boundaries; the
-// record of row r + 1 is requested before row r is computed, camera indices run two rows ahead, and
-// the observation stream is pulled into L2 kStreamAhead rows ahead.
+// Where the camera records come from.  The landmarks are ordered by median camera, so the slices of one block
+// meet a WINDOW of cameras: the block stages the records of that window in shared memory with bulk-async
+// copies (cp.async.bulk + mbarrier, the TMA unit; the copy overlaps the index loads of the prologue) and every
+// lane reads the record of its observation's camera with LDS.128.  A camera outside the window (rare by
+// construction of the order; never for C <= window) is read from global memory, so the result does not depend
+// on the window.  Large problems run one block of 32 warps per SM around a window of 228 KB (1,300 cameras in
+// step 1, 1,100 in step 2); a table of up to 48 KB fits four times per SM and the blocks stay small (short
+// launches on small shards).
+//
+// The per-slice landmark data (X, fold) are read from lane-major copies packed once per solve (k_sell_pack):
+// one coalesced line per component instead of 32 scattered records.  What is fetched ahead is the stream from
+// HBM: camera index and observation coefficients of the next kAhead rows (coalesced, 32 lanes wide).
 // ------------------------------------------------------------------------------------------
-struct RowData {
-  double2 L0, L1, L2;
-  ObsCoef k;
-  bool act;
+constexpr int kWinBytes = 228800;     // records staged by a big block (one per SM)
+constexpr int kWinSmallBytes = 49152; // whole table: four blocks of 256 threads per SM
+constexpr int kBigBlock = 1024;
+
+struct CamWindow {
+  const double* smem;   // records of cameras lo .. lo + n - 1
+  int lo, n;
 };
 
-template <bool JOINT, bool HASW>
-__device__ __forceinline__ void load_row(const DeviceIndex& ix, const double* __restrict__ cam_rec,
-                                         const double* __restrict__ sell_d,
-                                         const double* __restrict__ sell_w, int row, int c, int grp,
-                                         int sub, RowData& d) {
-  const size_t slot = 8 * static_cast<size_t>(row) + grp;
-  d.act = c >= 0;
-  const double* r = cam_rec + CamRec::kStride * static_cast<size_t>(d.act ? c : 0) + 2 * sub;
-  d.L0 = ldg2(r);
-  d.L1 = ldg2(r + 8);
-  d.L2 = ldg2(r + 16);
-  if (JOINT) {
-    const double* dp = sell_d + 3 * slot;
-    d.k.a = __ldcs(dp);
-    d.k.b = __ldcs(dp + 1);
-    d.k.c = __ldcs(dp + 2);
-  } else {
-    const double2 uv = __ldcs(ix.sell_uv + slot);
-    d.k.a = uv.x;
-    d.k.b = uv.y;
-    d.k.c = HASW ? __ldcs(sell_w + slot) : 1.0;
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+  return static_cast<unsigned>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
+  unsigned done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(phase)
+        : "memory");
   }
 }
 
-// landmarks with more than 32 observations (outside the sliced-ELL set): one warp per landmark (the
-// first blocks of the grid of k_e0_landmark_sell, so that they overlap with the slices),
-// group g takes observations g, g + 8, ... of the CSR list, fixed-tree sum over the groups
+// G += M^T (K^T W K) (Y x) for one observation whose camera record is `rec` (shared or global memory)
+template <bool JOINT>
+__device__ __forceinline__ void landmark_obs(const double2* __restrict__ rec, const double (&x)[4], const ObsCoef& k,
+                                             double c1, double c2, double (&G)[4]) {
+  double q[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const double2 a = rec[2 * r], b = rec[2 * r + 1];
+    q[r] = a.x * x[0] + a.y * x[1] + b.x * x[2] + b.y * x[3];
+  }
+  double m[3];
+  if (JOINT) {
+    joint_normal_coef(q[0], q[1], q[2], k.a, k.b, k.c, m);
+    // M = P, row-major 3 x 4, units 6..11
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const double2 a = rec[6 + 2 * r], b = rec[7 + 2 * r];
+      G[0] += a.x * m[r];
+      G[1] += a.y * m[r];
+      G[2] += b.x * m[r];
+      G[3] += b.y * m[r];
+    }
+  } else {
+    pose_normal_coef(q[0], q[1], q[2], k.a, k.b, k.c, c1, c2, m);
+    // M = P[:, 0:3], row-major 3 x 3 (+ pad), units 6..10:  (M00 M01) (M02 M10) (M11 M12) (M20 M21) (M22 -)
+    const double2 u0 = rec[6], u1 = rec[7], u2 = rec[8], u3 = rec[9], u4 = rec[10];
+    G[0] += u0.x * m[0] + u1.y * m[1] + u3.x * m[2];
+    G[1] += u0.y * m[0] + u2.x * m[1] + u3.y * m[2];
+    G[2] += u1.x * m[0] + u2.y * m[1] + u4.x * m[2];
+  }
+}
+
+// the record of camera c (c >= 0): from the window if it is there, else from global memory
+template <bool JOINT>
+__device__ __forceinline__ void landmark_obs_at(const CamWindow& w, const double* __restrict__ cam_rec, int c,
+                                                const double (&x)[4], const ObsCoef& k, double c1, double c2,
+                                                double (&G)[4]) {
+  constexpr int kStride = CamRec::stride(JOINT);
+  const unsigned rel = static_cast<unsigned>(c - w.lo);
+  if (rel < static_cast<unsigned>(w.n)) {
+    landmark_obs<JOINT>(reinterpret_cast<const double2*>(w.smem + kStride * static_cast<size_t>(rel)), x, k, c1, c2, G);
+  } else {
+    landmark_obs<JOINT>(reinterpret_cast<const double2*>(cam_rec + kStride * static_cast<size_t>(c)), x, k, c1, c2, G);
+  }
+}
+
+// H = fold G  (fold packed symmetric: 3x3 in step 1, 4x4 in step 2)
+template <bool JOINT>
+__device__ __forceinline__ void fold_apply(const double (&F)[10], const double (&G)[4], double (&H)[4]) {
+  if (JOINT) {
+    H[0] = F[0] * G[0] + F[1] * G[1] + F[2] * G[2] + F[3] * G[3];
+    H[1] = F[1] * G[0] + F[4] * G[1] + F[5] * G[2] + F[6] * G[3];
+    H[2] = F[2] * G[0] + F[5] * G[1] + F[7] * G[2] + F[8] * G[3];
+    H[3] = F[3] * G[0] + F[6] * G[1] + F[8] * G[2] + F[9] * G[3];
+  } else {
+    H[0] = F[0] * G[0] + F[1] * G[1] + F[2] * G[2];
+    H[1] = F[1] * G[0] + F[3] * G[1] + F[4] * G[2];
+    H[2] = F[2] * G[0] + F[4] * G[1] + F[5] * G[2];
+    H[3] = 0.0;
+  }
+}
+
+// the streamed part of one observation slot: camera index and the coefficients of the observation model
 template <bool JOINT, bool HASW>
-__device__ __forceinline__ void long_landmark_warp(const DeviceIndex& ix, int warp,
+__device__ __forceinline__ void load_stream(const DeviceIndex& ix, const double* __restrict__ sell_d,
+                                            const double* __restrict__ sell_w, int row, int lane, int& c,
+                                            ObsCoef& k) {
+  const size_t slot = kSellWidth * static_cast<size_t>(row) + lane;
+  c = __ldcs(ix.sell_cam + slot);
+  if (JOINT) {
+    const double* dp = sell_d + 3 * kSellWidth * static_cast<size_t>(row) + lane;
+    k.a = __ldcs(dp);
+    k.b = __ldcs(dp + kSellWidth);
+    k.c = __ldcs(dp + 2 * kSellWidth);
+  } else {
+    const double2 uv = __ldcs(ix.sell_uv + slot);
+    k.a = uv.x;
+    k.b = uv.y;
+    k.c = HASW ? __ldcs(sell_w + slot) : 1.0;
+  }
+}
+
+// landmarks with more than 32 observations (outside the sliced-ELL set): one warp per landmark, taken by
+// the warps of the same blocks after their slices; lane g takes observations g, g + 32, ... of the CSR list,
+// fixed-tree sum over the lanes
+template <bool JOINT, bool HASW>
+__device__ __forceinline__ void long_landmark_warp(const DeviceIndex& ix, const CamWindow& win, int which,
                                                    const double* __restrict__ X,
                                                    const double* __restrict__ cam_rec,
                                                    const double* __restrict__ obs_d,
@@ -187,19 +215,13 @@ __device__ __forceinline__ void long_landmark_warp(const DeviceIndex& ix, int wa
                                                    const double* __restrict__ lm_fold,
                                                    double* __restrict__ lm_rec) {
   const int lane = threadIdx.x & 31;
-  const int grp = lane >> 2, sub = lane & 3, gb = lane & ~3;
-  if (warp >= ix.num_long) return;
-  const int lm = __ldg(ix.long_lm + warp);
+  const int lm = __ldg(ix.long_lm + which);
   const int ob = __ldg(ix.lm_ptr + lm), oe = __ldg(ix.lm_ptr + lm + 1);
   double x[4];
   load4(X + 4 * static_cast<size_t>(lm), x);
-  double acc[4] = {0.0, 0.0, 0.0, 0.0};
-  for (int base = ob; base < oe; base += 8) {
-    const bool act = base + grp < oe;
-    const int o = act ? base + grp : ob;
+  double G[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int o = ob + lane; o < oe; o += 32) {
     const int c = __ldg(ix.obs_cam + o);
-    const double* r = cam_rec + CamRec::kStride * static_cast<size_t>(c) + 2 * sub;
-    const double2 A0 = ldg2(r), A1 = ldg2(r + 8), A2 = ldg2(r + 16);
     ObsCoef k;
     if (JOINT) {
       const double* dp = obs_d + 3 * static_cast<size_t>(o);
@@ -212,156 +234,168 @@ __device__ __forceinline__ void long_landmark_warp(const DeviceIndex& ix, int wa
       k.b = uv.y;
       k.c = HASW ? __ldg(obs_w + o) : 1.0;
     }
-    landmark_obs<JOINT>(A0, A1, A2, x, k, c1, c2, sub, gb, act, acc);
+    landmark_obs_at<JOINT>(win, cam_rec, c, x, k, c1, c2, G);
   }
+  warp_allreduce<4>(G);
+  double F[10], H[4];
 #pragma unroll
-  for (int off = 4; off < 32; off <<= 1) {
-#pragma unroll
-    for (int n = 0; n < 4; ++n) acc[n] += __shfl_xor_sync(kFullMask, acc[n], off);
-  }
-  double G[4];
-  group_totals<JOINT>(acc, gb, G);
-  const double H = fold_row<JOINT>(lm_fold + 10 * static_cast<size_t>(lm), sub, G);
-  if (grp == 0) lm_rec[kLmRec * static_cast<size_t>(lm) + 4 + sub] = H;
+  for (int i = 0; i < 10; ++i) F[i] = (JOINT || i < 6) ? __ldg(lm_fold + 10 * static_cast<size_t>(lm) + i) : 0.0;
+  fold_apply<JOINT>(F, G, H);
+  if (lane < 4) lm_rec[kLmRec * static_cast<size_t>(lm) + 4 + lane] = lane == 0 ? H[0] : (lane == 1 ? H[1] : (lane == 2 ? H[2] : H[3]));
 }
 
-constexpr int kStreamAhead = 24;   // rows
+constexpr int kStreamAhead = 16;   // rows the L2 prefetch runs ahead of the loads
 
-// per-warp state of the slice being accumulated
-template <bool JOINT>
-struct SliceState {
-  int lm, row1;        // landmark of this group (-1: none), first row after the slice
-  int lm_n, row1_n;    // the same for the next slice (loaded one slice ahead)
-  double x[4];
-  double fr[4];        // row `sub` of fold_l
-  double acc[4];
-};
-
-template <bool JOINT, bool HASW, int NR>
-__global__ void __launch_bounds__(kBlock, NR == 1 ? 4 : 3)
+template <bool JOINT, bool HASW, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, BLOCK > 256 ? 1 : 4)
 k_e0_landmark_sell(DeviceIndex ix, const double* __restrict__ X, const double* __restrict__ cam_rec,
                    const double* __restrict__ sell_d, const double* __restrict__ sell_w, double c1,
-                   double c2, const double* __restrict__ lm_fold, double* __restrict__ lm_rec,
+                   double c2, const double* __restrict__ lm_fold, const double* __restrict__ sell_x,
+                   const double* __restrict__ sell_fold, double* __restrict__ lm_rec,
                    const double* __restrict__ obs_d, const double* __restrict__ obs_w,
-                   const SeriesCtl* __restrict__ ctl, int slices_per_warp, int stream_ahead, int long_blocks) {
+                   const SeriesCtl* __restrict__ ctl, int slices_per_warp, int win_cams) {
+  extern __shared__ __align__(128) double win_smem[];
+  __shared__ unsigned long long win_bar;
   if (ctl != nullptr && ctl->done) return;
-  if (static_cast<int>(blockIdx.x) < long_blocks) {
-    long_landmark_warp<JOINT, HASW>(ix, blockIdx.x * kWarps + (threadIdx.x >> 5), X, cam_rec, obs_d, obs_w,
-                                    c1, c2, lm_fold, lm_rec);
-    return;
-  }
+  constexpr int kW = BLOCK / 32;
+  constexpr int kStride = CamRec::stride(JOINT);
   const int lane = threadIdx.x & 31;
-  const int grp = lane >> 2, sub = lane & 3, gb = lane & ~3;
-  // Blocks that share an SM should work on neighbouring slices (same stretch of the camera table in
-  // L1).  With a grid of 148 k blocks, all resident, blocks b, b + 148, ... land on the same SM.
-  const int bid = static_cast<int>(blockIdx.x) - long_blocks, nblk = static_cast<int>(gridDim.x) - long_blocks;
-  const int per_sm = nblk / 148;
-  const int chunk = (per_sm * 148 == nblk) ? (bid % 148) * per_sm + bid / 148 : bid;
-  const int warp = chunk * kWarps + (threadIdx.x >> 5);
+  const int warp = static_cast<int>(blockIdx.x) * kW + (threadIdx.x >> 5);
+  // ---- the window of this block: centred on the median cameras of its slices; staged by the TMA unit
+  CamWindow win;
+  win.smem = win_smem;
+  win.n = min(win_cams, ix.C);
+  {
+    const int bs0 = min(static_cast<int>(blockIdx.x) * kW * slices_per_warp, ix.num_slices);
+    const int bs1 = min(bs0 + kW * slices_per_warp, ix.num_slices);
+    const int centre = bs1 > bs0 ? (__ldg(ix.slice_cam + bs0) + __ldg(ix.slice_cam + bs1 - 1)) / 2 : ix.C / 2;
+    win.lo = max(0, min(centre - win.n / 2, ix.C - win.n));
+  }
+  if (threadIdx.x == 0) mbar_init(&win_bar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned bytes = static_cast<unsigned>(win.n) * (kStride * 8);
+    mbar_expect_tx(&win_bar, bytes);
+    const char* src = reinterpret_cast<const char*>(cam_rec + kStride * static_cast<size_t>(win.lo));
+    char* dst = reinterpret_cast<char*>(win_smem);
+    for (unsigned off = 0; off < bytes; off += 32768u) {
+      bulk_copy_g2s(dst + off, src + off, min(32768u, bytes - off), &win_bar);
+    }
+  }
   const int s0 = warp * slices_per_warp;
-  if (s0 >= ix.num_slices) return;
-  const int s1 = min(s0 + slices_per_warp, ix.num_slices);
-  const int row_first = __ldg(ix.slice_ptr + s0);
-  const int row_end = __ldg(ix.slice_ptr + s1);        // one past the last row of this warp
-  const int row_last = row_end - 1;
-  // indices of the packed symmetric fold matrix that make up row `sub`
-  const int f0 = sub;
-  const int f1 = JOINT ? (sub == 0 ? 1 : sub + 3) : (sub == 0 ? 1 : sub + 2);
-  const int f2 = JOINT ? (sub == 0 ? 2 : (sub == 1 ? 5 : sub + 5)) : (sub == 0 ? 2 : sub + 3);
-  const int f3 = sub == 0 ? 3 : (sub == 1 ? 6 : sub + 6);
+  if (s0 < ix.num_slices) {
+    const int s1 = min(s0 + slices_per_warp, ix.num_slices);
+    const int row_first = __ldg(ix.slice_ptr + s0);
+    const int row_end = __ldg(ix.slice_ptr + s1);        // one past the last row of this warp
+    const int row_last = row_end - 1;
+    // first rows after the slices of this warp, 32 at a time: lane j keeps the one of slice hdr_base + j
+    int hdr_base = s0;
+    int hdr = __ldg(ix.slice_ptr + min(s0 + lane, s1 - 1) + 1);
+    int sl = s0, row1 = 0, lm = -1;
+    double x[4], G[4];
+    auto open_slice = [&]() {
+      if (sl - hdr_base >= 32) {
+        hdr_base = sl;
+        hdr = __ldg(ix.slice_ptr + min(sl + lane, s1 - 1) + 1);
+      }
+      row1 = __shfl_sync(kFullMask, hdr, sl - hdr_base);
+      lm = __ldcs(ix.sell_lm + kSellWidth * static_cast<size_t>(sl) + lane);
+      const double* xp = sell_x + 4 * kSellWidth * static_cast<size_t>(sl) + lane;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        x[k] = __ldcs(xp + k * kSellWidth);
+        G[k] = 0.0;
+      }
+      if (sl + 1 < s1 && lane < 4) prefetch_l2(sell_x + 4 * kSellWidth * static_cast<size_t>(sl + 1) + 16 * lane);
+    };
+    auto close_slice = [&]() {
+      double F[10], H[4];
+      const double* fp = sell_fold + 10 * kSellWidth * static_cast<size_t>(sl) + lane;
+#pragma unroll
+      for (int i = 0; i < 10; ++i) F[i] = (JOINT || i < 6) ? __ldcs(fp + i * kSellWidth) : 0.0;
+      fold_apply<JOINT>(F, G, H);
+      if (lm >= 0) {
+        double2* out = reinterpret_cast<double2*>(lm_rec + kLmRec * static_cast<size_t>(lm) + 4);
+        __stcs(out, make_double2(H[0], H[1]));
+        __stcs(out + 1, make_double2(H[2], H[3]));
+      }
+      ++sl;
+    };
 
-  SliceState<JOINT> st;
-  int sl = s0;
-  auto open_slice = [&]() {
-    // st.lm / st.row1 are set; fetch this slice's landmark data and the header of the next slice
-    const int sn = min(sl + 1, s1 - 1);
-    st.lm_n = __ldg(ix.sell_lm + 8 * sn + grp);
-    st.row1_n = __ldg(ix.slice_ptr + sn + 1);
+    constexpr int kAhead = 2;
+    int camq[kAhead];
+    ObsCoef kq[kAhead];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) st.x[k] = st.fr[k] = st.acc[k] = 0.0;
-    if (st.lm >= 0) {
-      // streamed once per term: keep them from displacing the camera records in L1
-      const double2* xp = reinterpret_cast<const double2*>(X + 4 * static_cast<size_t>(st.lm));
-      const double2 xa = __ldcs(xp), xb = __ldcs(xp + 1);
-      st.x[0] = xa.x;
-      st.x[1] = xa.y;
-      st.x[2] = xb.x;
-      st.x[3] = xb.y;
-      const double* f = lm_fold + 10 * static_cast<size_t>(st.lm);
-      if (JOINT || sub < 3) {
-        st.fr[0] = __ldcs(f + f0);
-        st.fr[1] = __ldcs(f + f1);
-        st.fr[2] = __ldcs(f + f2);
-        if (JOINT) st.fr[3] = __ldcs(f + f3);
+    for (int j = 0; j < kAhead; ++j) {
+      load_stream<JOINT, HASW>(ix, sell_d, sell_w, min(row_first + j, row_last), lane, camq[j], kq[j]);
+    }
+    open_slice();
+    mbar_wait(&win_bar, 0);                   // the window is in shared memory
+    for (int row = row_first; row < row_end; row += kAhead) {
+      // pull the stream towards L2 ahead of the loads: per row 128 B of camera indices, 512 B of uv (768 B of d)
+      if (lane < (JOINT ? 7 : 5) * kAhead) {
+        const int per = JOINT ? 7 : 5;
+        const int rp = row + kStreamAhead + lane / per, part = lane % per;
+        if (rp <= row_last) {
+          if (part == 0) prefetch_l2(ix.sell_cam + kSellWidth * static_cast<size_t>(rp));
+          else if (JOINT) prefetch_l2(sell_d + 3 * kSellWidth * static_cast<size_t>(rp) + 16 * (part - 1));
+          else prefetch_l2(ix.sell_uv + kSellWidth * static_cast<size_t>(rp) + 8 * (part - 1));
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < kAhead; ++i) {
+        const int r = row + i;
+        if (r < row_end) {           // warp-uniform
+          if (r == row1) {           // warp-uniform: the previous slice is complete
+            close_slice();
+            open_slice();
+          }
+          const int c = camq[i];
+          const ObsCoef k = kq[i];
+          load_stream<JOINT, HASW>(ix, sell_d, sell_w, min(r + kAhead, row_last), lane, camq[i], kq[i]);
+          if (c >= 0) landmark_obs_at<JOINT>(win, cam_rec, c, x, k, c1, c2, G);
+        }
       }
     }
-    if (st.lm_n >= 0 && sub == 0) {
-      prefetch_l2(X + 4 * static_cast<size_t>(st.lm_n));
-      prefetch_l2(lm_fold + 10 * static_cast<size_t>(st.lm_n));
-    }
-  };
-  auto close_slice = [&]() {
-    double G[4];
-    group_totals<JOINT>(st.acc, gb, G);
-    if (st.lm >= 0) {
-      const double H = st.fr[0] * G[0] + st.fr[1] * G[1] + st.fr[2] * G[2] + st.fr[3] * G[3];
-      __stcs(lm_rec + kLmRec * static_cast<size_t>(st.lm) + 4 + sub, H);
-    }
-    ++sl;
-    st.lm = st.lm_n;
-    st.row1 = st.row1_n;
-  };
+    close_slice();
+  } else {
+    mbar_wait(&win_bar, 0);   // nobody leaves while the copy is in flight
+  }
+  // ---- long landmarks, spread over all warps of the grid
+  const int total_warps = static_cast<int>(gridDim.x) * kW;
+  for (int k = warp; k < ix.num_long; k += total_warps) {
+    long_landmark_warp<JOINT, HASW>(ix, win, k, X, cam_rec, obs_d, obs_w, c1, c2, lm_fold, lm_rec);
+  }
+}
 
-  st.lm = __ldg(ix.sell_lm + 8 * s0 + grp);
-  st.row1 = __ldg(ix.slice_ptr + s0 + 1);
-  // ring of NR rows in flight; camera indices run kCamAhead rows ahead of the records
-  constexpr int kCamAhead = 4;
-  constexpr int kUnroll = NR * kCamAhead;   // both rings keep static indices
-  RowData ring[NR];
-  int camq[kCamAhead];                      // camq[j]: camera index of row (next record row) + j
+// X and fold of the landmarks of every slice in lane-major planes ([slice][component][lane]); once per solve
+__global__ void __launch_bounds__(kBlock)
+k_sell_pack(int groups, const int* __restrict__ sell_lm, const double* __restrict__ X,
+            const double* __restrict__ lm_fold, double* __restrict__ sell_x, double* __restrict__ sell_fold) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= groups) return;
+  const int sl = i / kSellWidth, lane = i % kSellWidth;
+  const int lm = sell_lm[i];
+  double* xp = sell_x + 4 * kSellWidth * static_cast<size_t>(sl) + lane;
+  double* fp = sell_fold + 10 * kSellWidth * static_cast<size_t>(sl) + lane;
+  if (lm >= 0) {
+    double x[4];
+    load4(X + 4 * static_cast<size_t>(lm), x);
 #pragma unroll
-  for (int i = 0; i < NR; ++i) {
-    const int r = min(row_first + i, row_last);
-    const int c = __ldcs(ix.sell_cam + 8 * static_cast<size_t>(r) + grp);
-    load_row<JOINT, HASW>(ix, cam_rec, sell_d, sell_w, r, c, grp, sub, ring[i]);
-  }
+    for (int k = 0; k < 4; ++k) xp[k * kSellWidth] = x[k];
+    const double2* f = reinterpret_cast<const double2*>(lm_fold + 10 * static_cast<size_t>(lm));
 #pragma unroll
-  for (int j = 0; j < kCamAhead; ++j) {
-    camq[j] = __ldcs(ix.sell_cam + 8 * static_cast<size_t>(min(row_first + NR + j, row_last)) + grp);
-  }
-  open_slice();
-  for (int row = row_first; row < row_end; row += kUnroll) {
-    // pull the observation stream towards L2 ahead of the loads (one 128-byte line of uv per row)
-    if (stream_ahead > 0 && lane < kUnroll) {
-      const int rp = row + stream_ahead + lane;
-      if (rp <= row_last) {
-        if (JOINT) {
-          prefetch_l2(sell_d + 24 * static_cast<size_t>(rp));
-          prefetch_l2(sell_d + 24 * static_cast<size_t>(rp) + 16);
-        } else {
-          prefetch_l2(ix.sell_uv + 8 * static_cast<size_t>(rp));
-        }
-        if ((lane & 3) == 0) prefetch_l2(ix.sell_cam + 8 * static_cast<size_t>(rp));
-      }
+    for (int k = 0; k < 5; ++k) {
+      const double2 t = __ldg(f + k);
+      fp[(2 * k) * kSellWidth] = t.x;
+      fp[(2 * k + 1) * kSellWidth] = t.y;
     }
+  } else {
 #pragma unroll
-    for (int i = 0; i < kUnroll; ++i) {
-      const int r = row + i;
-      if (r < row_end) {           // warp-uniform
-        if (r == st.row1) {        // warp-uniform: the previous slice is complete
-          close_slice();
-          open_slice();
-        }
-        RowData& cur = ring[i % NR];
-        landmark_obs<JOINT>(cur.L0, cur.L1, cur.L2, st.x, cur.k, c1, c2, sub, gb, cur.act, st.acc);
-        load_row<JOINT, HASW>(ix, cam_rec, sell_d, sell_w, min(r + NR, row_last), camq[i % kCamAhead],
-                              grp, sub, cur);
-        camq[i % kCamAhead] =
-            __ldcs(ix.sell_cam + 8 * static_cast<size_t>(min(r + NR + kCamAhead, row_last)) + grp);
-      }
-    }
+    for (int k = 0; k < 4; ++k) xp[k * kSellWidth] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) fp[k * kSellWidth] = 0.0;
   }
-  close_slice();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -475,45 +509,52 @@ k_cam_rec_static(int C, const double* __restrict__ P, double* __restrict__ cam_r
   if (idx >= C * 4) return;
   const int c = idx >> 2, n = idx & 3;
   const double* p = P + 12 * static_cast<size_t>(c);
-  double* r = cam_rec + CamRec::kStride * static_cast<size_t>(c);
-  const bool used = JOINT || n < 3;
-  r[CamRec::m_index(0, n)] = used ? p[n] : 0.0;
-  r[CamRec::m_index(1, n)] = used ? p[4 + n] : 0.0;
-  r[CamRec::m_index(2, n)] = used ? p[8 + n] : 0.0;
+  double* r = cam_rec + CamRec::stride(JOINT) * static_cast<size_t>(c);
+  if (JOINT || n < 3) {
+    r[CamRec::m_index(JOINT, 0, n)] = p[n];
+    r[CamRec::m_index(JOINT, 1, n)] = p[4 + n];
+    r[CamRec::m_index(JOINT, 2, n)] = p[8 + n];
+  } else {
+    r[CamRec::stride(JOINT) - 1] = 0.0;   // the pad of the step-1 record
+  }
+  if (JOINT && n == 0) r[24] = r[25] = 0.0;
+}
+
+template <bool JOINT, bool HASW, int BLOCK>
+void launch_landmark_block(const DeviceState& d, const ModelParams& mp, const SeriesCtl* ctl, int blocks,
+                           int per_warp, int win_cams, const LaunchCfg& lc) {
+  const size_t smem = static_cast<size_t>(win_cams) * CamRec::stride(JOINT) * 8;
+  static const cudaError_t attr = cudaFuncSetAttribute(k_e0_landmark_sell<JOINT, HASW, BLOCK>,
+                                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                       BLOCK > 256 ? kWinBytes : kWinSmallBytes);
+  (void)attr;
+  k_e0_landmark_sell<JOINT, HASW, BLOCK><<<blocks, BLOCK, smem, lc.stream>>>(
+      d.ix, d.X, d.cam_rec, d.sell_d, d.sell_w, mp.c1, mp.c2, d.lm_fold, d.sell_x, d.sell_fold, d.lm_rec, d.obs_d,
+      d.obs_w, ctl, per_warp, win_cams);
 }
 
 template <bool JOINT, bool HASW>
 void launch_landmark_half(const DeviceState& d, const ModelParams& mp, const SeriesCtl* ctl,
                           const LaunchCfg& lc) {
   if (d.ix.num_slices == 0 && d.ix.num_long == 0) return;
-  // one wave of persistent-style blocks for the slices: 148 SMs x 4 resident blocks x 8 warps,
-  // contiguous slice ranges per warp; in front of them one warp per long landmark.  Small problems and
-  // small shards (a venice-1778 shard on 8 GPUs has 15 k slices) keep the wave full with short ranges:
-  // a warp walks its rows one dependent gather after the other, so the launch lasts as long as the
-  // longest range (64 us for 16 slices, whatever the problem size).
-  const long long full = 148LL * 4 * kWarps;
+  // one wave of persistent-style blocks: SMs x 32 warps, contiguous slice ranges per warp.  Small problems and
+  // small shards keep the wave full with short ranges: a warp walks its rows one after the other, so the
+  // launch lasts as long as the longest range.
+  const int rec_bytes = CamRec::stride(JOINT) * 8;
+  const bool small_table = d.ix.C * rec_bytes <= kWinSmallBytes;
+  const long long full = static_cast<long long>(sm_count()) * 32;
   long long per_warp = (d.ix.num_slices + full - 1) / full;
-  static const int min_per_warp = getenv("POVAR_SELL_MIN_SLICES") ? atoi(getenv("POVAR_SELL_MIN_SLICES")) : 2;
-  if (per_warp < min_per_warp) per_warp = min_per_warp;
-  const long long warps = (d.ix.num_slices + per_warp - 1) / per_warp;
-  int blocks = static_cast<int>((warps + kWarps - 1) / kWarps);
-  if (blocks > 148) blocks = (blocks + 147) / 148 * 148;   // whole multiples of 148: see the chunk map
-  const int long_blocks = (d.ix.num_long + kWarps - 1) / kWarps;
-  static const int nr = getenv("POVAR_SELL_NR") ? atoi(getenv("POVAR_SELL_NR")) : 1;
-  static const int ahead = getenv("POVAR_SELL_AHEAD") ? atoi(getenv("POVAR_SELL_AHEAD")) : kStreamAhead;
-#define POVAR_SELL_LAUNCH(NRV)                                                                     \
-  {                                                                                                \
-    static const cudaError_t carve_##NRV = cudaFuncSetAttribute(                                   \
-        k_e0_landmark_sell<JOINT, HASW, NRV>, cudaFuncAttributePreferredSharedMemoryCarveout,      \
-        cudaSharedmemCarveoutMaxL1); /* no shared memory: all of it to L1 (the camera table) */    \
-    (void)carve_##NRV;                                                                             \
-    k_e0_landmark_sell<JOINT, HASW, NRV><<<blocks + long_blocks, kBlock, 0, lc.stream>>>(          \
-        d.ix, d.X, d.cam_rec, d.sell_d, d.sell_w, mp.c1, mp.c2, d.lm_fold, d.lm_rec, d.obs_d,      \
-        d.obs_w, ctl, static_cast<int>(per_warp), ahead, long_blocks);                             \
+  if (per_warp < 1) per_warp = 1;
+  long long warps = (d.ix.num_slices + per_warp - 1) / per_warp;
+  if (warps < 1) warps = 1;   // long landmarks only
+  if (small_table) {
+    launch_landmark_block<JOINT, HASW, 256>(d, mp, ctl, static_cast<int>((warps + 7) / 8), static_cast<int>(per_warp),
+                                            d.ix.C, lc);
+  } else {
+    const int win = kWinBytes / rec_bytes;
+    launch_landmark_block<JOINT, HASW, kBigBlock>(d, mp, ctl, static_cast<int>((warps + kBigBlock / 32 - 1) / (kBigBlock / 32)),
+                                                  static_cast<int>(per_warp), d.ix.C < win ? d.ix.C : win, lc);
   }
-  if (nr == 2) POVAR_SELL_LAUNCH(2)
-  else POVAR_SELL_LAUNCH(1)
-#undef POVAR_SELL_LAUNCH
   count(lc);
 }
 
@@ -526,6 +567,15 @@ void launch_cam_rec_static(const DeviceState& d, bool joint, const LaunchCfg& lc
   } else {
     k_cam_rec_static<false><<<blocks, kBlock, 0, lc.stream>>>(d.ix.C, d.P, d.cam_rec);
   }
+  count(lc);
+}
+
+void launch_sell_pack(const DeviceState& d, bool joint, const LaunchCfg& lc) {
+  (void)joint;
+  const int groups = kSellWidth * d.ix.num_slices;
+  if (groups == 0) return;
+  k_sell_pack<<<(groups + kBlock - 1) / kBlock, kBlock, 0, lc.stream>>>(groups, d.ix.sell_lm, d.X, d.lm_fold, d.sell_x,
+                                                                       d.sell_fold);
   count(lc);
 }
 

@@ -26,15 +26,17 @@ struct DeviceIndex {
                               //   (<= 32 obs together) or one long landmark
   int num_tiles = 0;
   // landmark-major, sliced ELL for the landmark half of E0 (kernels_series.cu): landmarks with 1..32
-  // observations, sorted by degree inside windows of kSellWindow landmarks, eight per slice; slot
-  // 8 * row + g holds the row-th observation of the g-th landmark of the slice (camera -1 = padding)
+  // observations, sorted by degree inside windows of kSellWindow landmarks, kSellWidth (32) per slice; slot
+  // 32 * row + g holds the row-th observation of the g-th landmark of the slice (camera -1 = padding)
   int num_slices = 0;
   int* slice_ptr = nullptr;   // [num_slices+1] first row of the slice
-  int* sell_lm = nullptr;     // [8*num_slices] landmark of group g, -1 = none
-  int* sell_cam = nullptr;    // [8*rows]
-  double2* sell_uv = nullptr; // [8*rows]
+  int* sell_lm = nullptr;     // [32*num_slices] landmark of lane g, -1 = none
+  int* slice_cam = nullptr;   // [num_slices] median camera of the slice's first landmark: where a block of
+                              //   slices centres the window of camera records it stages in shared memory
+  int* sell_cam = nullptr;    // [32*rows]
+  double2* sell_uv = nullptr; // [32*rows]
   int* obs_slot = nullptr;    // [nnz] slot of the observation, -1 for landmarks outside the SELL set
-  long long sell_slots = 0;   // 8 * rows
+  long long sell_slots = 0;   // 32 * rows
   int num_long = 0;           // landmarks with more than 32 observations: one warp each, CSR arrays
   int* long_lm = nullptr;     // [num_long]
   // camera-major
@@ -49,7 +51,9 @@ struct DeviceIndex {
 
 constexpr double kEpsSqrtHost = 1e-5;  // Sophus::Constants<double>::epsilonSqrt()
 constexpr int kKron = 60;     // unique entries of sum_i E_i (x) (X X^T): 6 x 10
-constexpr int kSellWindow = 128;    // sorting window of the sliced-ELL landmark order
+constexpr int kSellWidth = 32;      // landmarks per slice of the sliced-ELL order: one per lane of a warp
+constexpr int kSellWindow = 512;    // sorting window of the sliced-ELL landmark order
+constexpr int kCamRecStride = 26;   // doubles per camera record, the larger of the two models (CamRec::stride)
 constexpr int kLmRec = 8;     // per-landmark record read by the camera-major pass: [X(4) | H(4)]
 
 // series control block, lives in device memory
@@ -107,11 +111,13 @@ struct DeviceState {
   double* hll_inv = nullptr;     // [L*6]
   double* lm_rec = nullptr;      // [L*8]  [X | H] for the camera-major pass
   double* lm_fold = nullptr;     // [L*10] S (Pi) Hll^-1 (Pi^T) S, packed symmetric: H_l = fold_l G_l
-  double* cam_rec = nullptr;     // [C*28] per-camera record of the landmark-major E0 pass (CamRec<>)
+  double* cam_rec = nullptr;     // [C*32] per-camera record of the landmark-major E0 pass (CamRec<>)
   double* obs_d = nullptr;       // [nnz*3] step 2: sqrt(w) (1/z, -x/z^2, -y/z^2) at the linearisation point
   double* csc_d = nullptr;       // [nnz*3] the same, camera-major
   double* obs_w = nullptr;       // [nnz]   step 1, HUBER only: robust weight at the linearisation point
-  double* sell_d = nullptr;      // [slots*3] obs_d in SELL order
+  double* sell_d = nullptr;      // [rows][3][32] obs_d in SELL order, one plane per coefficient and row
+  double* sell_x = nullptr;      // [slices][4][32]  X of the slices' landmarks (packed once per solve)
+  double* sell_fold = nullptr;   // [slices][10][32] lm_fold of the slices' landmarks
   double* sell_w = nullptr;      // [slots]   obs_w in SELL order
   double* csc_w = nullptr;       // [nnz]   the same, camera-major
   double* kron = nullptr;        // [C*60]
@@ -141,6 +147,21 @@ struct DeviceState {
   SeriesCtl* ctl = nullptr;
   double* dense_S = nullptr;     // CHOLESKY: [12C x 12C]
 };
+
+// streaming multiprocessors of the current device (grids are sized in multiples of it)
+inline int sm_count() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) {
+      cached = n;
+    } else {
+      cached = 148;   // B200
+    }
+  }
+  return cached;
+}
 
 struct LaunchCfg {
   cudaStream_t stream = nullptr;
@@ -207,6 +228,8 @@ void launch_e0_finish(const DeviceState& d, bool joint, double* out, const Launc
 void launch_make_y(const DeviceState& d, bool joint, const double* x, double* y, const LaunchCfg& lc);
 // cam_rec: matrix part (after a linearisation) -- the y part is written by whoever makes y
 void launch_cam_rec_static(const DeviceState& d, bool joint, const LaunchCfg& lc);
+// X and lm_fold of the landmarks of every slice, lane-major (after launch_prep_landmark, before any E0 product)
+void launch_sell_pack(const DeviceState& d, bool joint, const LaunchCfg& lc);
 // ---- power-series term kernels, lane-group layout (kernels_series.cu) ----
 void launch_e0_landmark_v2(const DeviceState& d, const ModelParams& mp, bool joint, bool in_series,
                            const LaunchCfg& lc);

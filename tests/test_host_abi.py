@@ -253,10 +253,10 @@ def test_create_dataset_writes_the_reference_format(tmp_path):
         assert a[i] == b[i], (i, a[i], b[i])
 
 
-def _sell_reference(hp, window=128):
+def _sell_reference(hp, window=512, width=32):
     """The sliced-ELL rule restated with numpy sorts (engine.cu build_sell): landmarks with 1..32 observations
     in the order of their median camera (stable), windows of `window`, inside a window stable by descending
-    degree, eight landmarks per slice, slice length = the largest degree in it."""
+    degree, 32 landmarks (one per lane) per slice, slice length = the largest degree in it."""
     deg = np.diff(hp.lm_ptr)
     ok = np.nonzero((deg > 0) & (deg <= 32))[0]
     med = hp.obs_cam[(hp.lm_ptr[ok] + hp.lm_ptr[ok + 1]) // 2]
@@ -265,9 +265,9 @@ def _sell_reference(hp, window=128):
     for w0 in range(0, len(by_cam), window):
         win = by_cam[w0:w0 + window]
         order = win[np.argsort(-deg[win], kind="stable")]
-        for i in range(0, len(order), 8):
-            grp = list(order[i:i + 8])
-            sell_lm += grp + [-1] * (8 - len(grp))
+        for i in range(0, len(order), width):
+            grp = list(order[i:i + width])
+            sell_lm += grp + [-1] * (width - len(grp))
             slice_ptr.append(slice_ptr[-1] + int(deg[order[i]]))
     return np.array(slice_ptr), np.array(sell_lm), np.nonzero(deg > 32)[0]
 

@@ -27,12 +27,25 @@ from povar_b200 import synthetic  # noqa: E402
 import make_golden as mg  # noqa: E402
 
 OUT = os.path.join(mg.GOLD, "traces_large.json")
+# Step 2 (RIPOBA at small damping) is chaotic on these non-converged scenes: rounding-level differences grow by a
+# constant factor per trial, and the reference's own 8-thread run (scatter order only) leaves its
+# 1-thread run after a while (measured on the uncapped runs: trafalgar-257 PoVar 3e-9 at step-2 trial 12 and 1e-6
+# at 13, PoBA 1e-8 at 11; venice-89 2e-8 at trial 41, 2e-6 at 47; venice-1778 stays at 1e-9 to the end).  Each
+# configuration therefore runs step 2 only as far as the reference reproduces itself to ~1e-8
+# (--max-num-iterations-step-2), so that the comparison can use BASELINE.json's literal bars to the last trial.
+# PCG / CHOLESKY on trafalgar-257 are the exception: their step-1 solves are ill-conditioned at small damping, the
+# reference's two runs differ by 3e-8 / 5e-8 inside step 1 and by 7e-7 / 6e-5 at the first cost of step 2, whatever
+# the cap (tests/test_gpu_parity_large.py states what is asserted there).
 CONFIGS = [
-    ("trafalgar257_povar", "trafalgar257", []),
-    ("trafalgar257_poba", "trafalgar257", ["--solver-type-step-1", "POWER_SCHUR_COMPLEMENT"]),
-    ("trafalgar257_pcg", "trafalgar257", ["--solver-type-step-1", "PCG"]),
-    ("trafalgar257_cholesky", "trafalgar257", ["--solver-type-step-1", "CHOLESKY"]),
-    ("venice89_poba", "venice89", ["--solver-type-step-1", "POWER_SCHUR_COMPLEMENT"]),
+    ("trafalgar257_povar", "trafalgar257", ["--max-num-iterations-step-2", "10"]),
+    ("trafalgar257_poba", "trafalgar257", ["--solver-type-step-1", "POWER_SCHUR_COMPLEMENT",
+                                           "--max-num-iterations-step-2", "8"]),
+    ("trafalgar257_pcg", "trafalgar257", ["--solver-type-step-1", "PCG", "--max-num-iterations-step-2", "4"]),
+    ("trafalgar257_cholesky", "trafalgar257", ["--solver-type-step-1", "CHOLESKY", "--max-num-iterations-step-2", "4"]),
+    ("trafalgar257_huber", "trafalgar257", ["--residual-robust-norm", "HUBER", "--residual-huber-parameter", "10",
+                                            "--max-num-iterations-step-2", "8"]),
+    ("venice89_poba", "venice89", ["--solver-type-step-1", "POWER_SCHUR_COMPLEMENT",
+                                   "--max-num-iterations-step-2", "36"]),
     ("venice1778_povar_cauchy", "venice1778", ["--residual-robust-norm", "CAUCHY"]),
 ]
 
