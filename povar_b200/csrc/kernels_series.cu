@@ -350,10 +350,11 @@ k_e0_landmark_sell(DeviceIndex ix, const double* __restrict__ X, const double* _
             close_slice();
             open_slice();
           }
-          const int c = camq[i];
-          const ObsCoef k = kq[i];
+          if (camq[i] >= 0) landmark_obs_at<JOINT>(win, cam_rec, camq[i], x, kq[i], c1, c2, G);
+          // refill the slot only now: issued before the use, the compiler loads into a scratch register and
+          // copies it into the slot at once -- a stall on the load in every row (seen in the SASS); a row of
+          // a warp lasts thousands of cycles, so kAhead - 1 rows of distance cover any latency
           load_stream<JOINT, HASW>(ix, sell_d, sell_w, min(r + kAhead, row_last), lane, camq[i], kq[i]);
-          if (c >= 0) landmark_obs_at<JOINT>(win, cam_rec, c, x, k, c1, c2, G);
         }
       }
     }
