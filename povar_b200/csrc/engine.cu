@@ -363,8 +363,8 @@ void build_sell(const std::vector<int>& lm_ptr, const int* obs_cam, int num_cams
 }
 
 int choose_item_len(long long nnz) {
-  // enough items to fill 148 SMs x 64 warps a couple of times, at most 256 entries per item
-  long long len = nnz / (148LL * 64 * 2);
+  // enough items to fill every SM with 64 warps a couple of times, at most 256 entries per item
+  long long len = nnz / (static_cast<long long>(sm_count()) * 64 * 2);
   len = (len + 31) / 32 * 32;
   if (len < 32) len = 32;
   if (len > 256) len = 256;
@@ -456,11 +456,6 @@ int Engine::create(const povar_problem_desc* desc, const povar_options* opt,
   e->rank_ = comm ? comm->rank : 0;
   e->world_ = comm ? comm->world_size : 1;
   e->device_ = comm ? comm->device : 0;
-  {
-    // POVAR_E0_IMPL=v1 selects the one-observation-per-lane term kernels (A/B timing, debugging)
-    const char* impl = getenv("POVAR_E0_IMPL");
-    e->e0_v1_ = impl != nullptr && std::strcmp(impl, "v1") == 0;
-  }
   if (e->device_ < 0 || e->device_ >= ndev) {
     if (err) *err = "povar_create: device ordinal out of range";
     delete e;
@@ -713,30 +708,6 @@ int Engine::upload(const povar_problem_desc* desc) {
   PV_ALLOC(d_.ctl, 1);
   PV_UP(d_.P, desc->cam_P, sizeof(double) * C12);
 #undef PV_UP
-  {
-    // POVAR_L2_PERSIST=1: keep the per-landmark records of the camera half ([X | H], written by the landmark
-    // half of every term, gathered by the camera half) resident in L2 -- between the two the landmark half
-    // streams ~4x their size through the cache.  Off by default: measured on venice-1778 it is worth 1 % of a
-    // step-1 term (239.4 vs 242.3 us) and nothing in step 2 (281.1 vs 280.4 us).
-    const char* env = getenv("POVAR_L2_PERSIST");
-    int max_persist = 0, max_window = 0;
-    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device_);
-    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device_);
-    const size_t bytes = sizeof(double) * kLmRec * static_cast<size_t>(L);
-    if (env != nullptr && std::strcmp(env, "1") == 0 && max_persist > 0 && max_window > 0 && bytes > 0) {
-      const size_t persist = std::min<size_t>(static_cast<size_t>(max_persist), bytes);
-      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist);
-      cudaStreamAttrValue attr{};
-      attr.accessPolicyWindow.base_ptr = d_.lm_rec;
-      attr.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, static_cast<size_t>(max_window));
-      attr.accessPolicyWindow.hitRatio =
-          static_cast<float>(std::min(1.0, static_cast<double>(persist) / static_cast<double>(attr.accessPolicyWindow.num_bytes)));
-      attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-      attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-      cudaStreamSetAttribute(stream_, cudaStreamAttributeAccessPolicyWindow, &attr);
-      cudaGetLastError();
-    }
-  }
   lap("allocate + enqueue uploads");
   // the host tables above live on this stack frame
   PV_CUDA(cudaStreamSynchronize(stream_));
@@ -783,11 +754,6 @@ int Engine::setup_peer_exchange() {
   if (world_ > kMaxPeers || C_ <= 0) {
     if (rdv_) return fail(POVAR_ERR_UNSUPPORTED, "host rendezvous: more ranks than the peer exchange supports");
     return POVAR_OK;
-  }
-  {
-    // POVAR_PEER_ALLREDUCE=0: only the per-term exchange uses the peer buffers, the other reductions NCCL
-    const char* small = getenv("POVAR_PEER_ALLREDUCE");
-    peer_small_ = rdv_ != nullptr || !(small != nullptr && std::strcmp(small, "0") == 0);
   }
   if (world_ == 1) {
     // POVAR_PEER_EXCHANGE=self: a single GPU runs the exchange protocol against its own buffer (isolates the
@@ -1028,13 +994,9 @@ int Engine::linearize(bool joint, double alpha) {
 
 // raw_c = sum over the observations of camera c of the camera half of E0 (or of b), all ranks
 int Engine::e0_product(bool joint, const double* y, bool in_series) {
-  if (e0_v1_) {
-    launch_e0_landmark(d_, mp_, joint, y, in_series, lc());
-    launch_passB(d_, mp_, joint, PASSB_E0, in_series, lc());
-  } else {
-    launch_e0_landmark_v2(d_, mp_, joint, in_series, lc());
-    launch_passB_e0_v2(d_, mp_, joint, in_series, lc());
-  }
+  (void)y;   // the passes gather y from the camera records (cam_rec), written by whoever made y
+  launch_e0_landmark_v2(d_, mp_, joint, in_series, lc());
+  launch_passB_e0_v2(d_, mp_, joint, in_series, lc());
   // the term kernel adds the item partials itself (and, sharded, exchanges them over peer memory)
   if (in_series && term_mode() != kTermRaw) return POVAR_OK;
   launch_reduce_items(d_, d_.item_part, 12, d_.cam_raw, in_series, lc());
@@ -1049,7 +1011,7 @@ int Engine::solve_power(bool joint, double lambda) {
   launch_prep_landmark(d_, joint, lambda_lm, lc());
   launch_sell_pack(d_, joint, lc());
   launch_cam_binv(d_, joint, lambda, lc());
-  launch_passB(d_, mp_, joint, PASSB_B, false, lc());
+  launch_passB(d_, mp_, joint, lc());
   launch_reduce_items(d_, d_.item_part, 12, d_.cam_raw, false, lc());
   {
     const int rc = allreduce(d_.cam_raw, static_cast<size_t>(C_) * 12);
@@ -1119,7 +1081,7 @@ int Engine::prepare_reduced_system(bool joint, double lambda, double lambda_lm) 
   launch_prep_landmark(d_, joint, lambda_lm, lc());
   launch_sell_pack(d_, joint, lc());
   launch_cam_binv(d_, joint, lambda, lc());
-  launch_passB(d_, mp_, joint, PASSB_B, false, lc());
+  launch_passB(d_, mp_, joint, lc());
   launch_reduce_items(d_, d_.item_part, 12, d_.cam_raw, false, lc());
   const int rc = allreduce(d_.cam_raw, static_cast<size_t>(C_) * 12);
   if (rc != POVAR_OK) return rc;
@@ -1561,12 +1523,10 @@ int Engine::bench_power_kernels(bool joint, int reps, double* seconds) {
     for (int i = 0; i < reps; ++i) {
       switch (k) {
         case 0:
-          if (e0_v1_) launch_e0_landmark(d_, mp_, joint, d_.vec_y, true, lc());
-          else launch_e0_landmark_v2(d_, mp_, joint, true, lc());
+          launch_e0_landmark_v2(d_, mp_, joint, true, lc());
           break;
         case 1:
-          if (e0_v1_) launch_passB(d_, mp_, joint, PASSB_E0, true, lc());
-          else launch_passB_e0_v2(d_, mp_, joint, true, lc());
+          launch_passB_e0_v2(d_, mp_, joint, true, lc());
           break;
         case 2: launch_reduce_items(d_, d_.item_part, 12, d_.cam_raw, true, lc()); break;
         default: launch_series_term(d_, joint, i + 1, -1.0, -1.0, term_mode(), exchange(), lc()); break;

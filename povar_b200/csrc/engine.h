@@ -84,7 +84,6 @@ class Engine {
   bool have_solve_ = false;       // a solve ran on the current linearisation (apply needs its increment)
   double lambda_ = 0.0;           // damping of the last solve (landmark damping of apply)
   int dim_ = 12;
-  bool e0_v1_ = false;            // POVAR_E0_IMPL=v1: old term kernels (kernels_landmark.cu / kernels_camera.cu)
   double* P_prev_ = nullptr;      // cameras of the linearisation point during a VarPro apply
   void* cusolver_ = nullptr;      // cusolverDnHandle_t (CHOLESKY only)
   double* chol_work_ = nullptr;
@@ -101,7 +100,7 @@ class Engine {
   PeerShared* peer_ = nullptr;
   std::string comm_key_;
   bool peer_ok_ = false;
-  bool peer_small_ = true;        // cost scalars, b, Kronecker sums ... also go over the peer buffers
+  bool peer_small_ = true;        // cost scalars, b, Kronecker sums ... also go over the peer buffers (always)
   bool peer_owned_ = false;       // POVAR_PEER_EXCHANGE=self: a private buffer, not the communicator's
   // host mirrors
   int C_ = 0, L_ = 0;

@@ -176,49 +176,12 @@ __device__ __forceinline__ void kron_factors(const DeviceIndex& ix, int e, const
   }
 }
 
-template <bool JOINT, int KIND>
-#ifdef POVAR_OCC_KRON
-#define POVAR_BOUNDS_KRON __launch_bounds__(kBlock, POVAR_OCC_KRON)
-#else
-#define POVAR_BOUNDS_KRON __launch_bounds__(kBlock)
-#endif
-__global__ void POVAR_BOUNDS_KRON
-k_kron(DeviceIndex ix, const double* __restrict__ P, const double* __restrict__ X, double c1,
-       double c2, Robust rb, const double* __restrict__ lm_scale, const double* __restrict__ hll_inv,
-       double* __restrict__ item_kron, double* __restrict__ csc_d, double* __restrict__ csc_w) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= ix.num_items) return;
-  const int c = __ldg(ix.item_cam + warp);
-  const int eb = __ldg(ix.item_ptr + warp), ee = __ldg(ix.item_ptr + warp + 1);
-  Cam3x4 cam;
-  load_cam(P, c, cam);
-  double acc[kKron];
-#pragma unroll
-  for (int k = 0; k < kKron; ++k) acc[k] = 0.0;
-  for (int e = eb + lane; e < ee; e += 32) {
-    double E[6], Y[10];
-    kron_factors<JOINT, KIND>(ix, e, cam, X, c1, c2, rb, lm_scale, hll_inv, csc_d, csc_w, E, Y);
-#pragma unroll
-    for (int a = 0; a < 6; ++a) {
-#pragma unroll
-      for (int k = 0; k < 10; ++k) acc[a * 10 + k] += E[a] * Y[k];
-    }
-  }
-  warp_allreduce<kKron>(acc);
-  if (lane == 0) {
-    double* out = item_kron + kKron * static_cast<size_t>(warp);
-#pragma unroll
-    for (int k = 0; k < kKron; ++k) out[k] = acc[k];
-  }
-}
-
-// The same sums on the FP64 tensor cores.  Per camera the 6 x 10 block is a contraction over the
+// The sums on the FP64 tensor cores.  Per camera the 6 x 10 block is a contraction over the
 // observations, sum_i E_i (x) Y_i = [E_1 .. E_n] [Y_1 .. Y_n]^T: each lane makes the factors of one entry,
 // the warp transposes them through shared memory into DMMA fragments (m8n8k4: A = E^T, 8 x 4 entries with
 // rows 6..7 zero; B = Y, 4 entries x 8, two column tiles for the 10 entries of X X^T) and eight k-steps
-// consume the 32 entries.  Four accumulator registers per lane instead of 60 (the one-lane-one-entry
-// kernel above runs at one block per SM), and no 60-value warp reduction at the end.
+// consume the 32 entries.  Four accumulator registers per lane instead of 60 (a one-lane-one-entry
+// kernel ran at one block per SM), and no 60-value warp reduction at the end.
 __device__ __forceinline__ void dmma_m8n8k4(double (&d)[2], double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
                : "+d"(d[0]), "+d"(d[1])
@@ -380,6 +343,10 @@ __device__ __forceinline__ bool chol_inverse(double (&A)[D][D], double (&Inv)[D]
 // during assembly and factorisation, lane c solves column c of the inverse.  Every entry is produced by
 // the same sequence of operations as in the one-thread version below (k_cam_binv, kept for A/B runs
 // with POVAR_CAM_BINV=v1), including Eigen's stop-at-the-first-bad-pivot behaviour.
+// MODE 0: R = proj((s s^T) o kron) + lambda I -> Bmat, R^-1 -> Binv           (prepare_Hb_*)
+// MODE 1: R = Bmat - proj((s s^T) o kron)               , R^-1 -> Binv(=Mprec) (block-Jacobi
+//         preconditioner of the reduced camera system, cg/preconditioner.hpp:78-124; kron then holds
+//         the diagonal blocks of sum_l Hpl Hll^-1 Hlp)
 template <bool JOINT, int MODE>
 __global__ void __launch_bounds__(kBlock)
 k_cam_binv16(int C, const double* __restrict__ P, const double* __restrict__ kron,
@@ -511,81 +478,6 @@ k_cam_binv16(int C, const double* __restrict__ P, const double* __restrict__ kro
 #pragma unroll
       for (int r = 0; r < D; ++r) bi[r * D + cc] = x[r];
     }
-  }
-}
-
-// MODE 0: R = proj((s s^T) o kron) + lambda I -> Bmat, R^-1 -> Binv           (prepare_Hb_*)
-// MODE 1: R = Bmat - proj((s s^T) o kron)               , R^-1 -> Binv(=Mprec) (block-Jacobi
-//         preconditioner of the reduced camera system, cg/preconditioner.hpp:78-124; kron then holds
-//         the diagonal blocks of sum_l Hpl Hll^-1 Hlp)
-template <bool JOINT, int MODE>
-__global__ void __launch_bounds__(128)
-k_cam_binv(int C, const double* __restrict__ P, const double* __restrict__ kron,
-           const double* __restrict__ pose_scale, double lambda, double* __restrict__ Bmat,
-           double* __restrict__ Binv) {
-  constexpr int D = JOINT ? 11 : 12;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const double* kr = kron + kKron * static_cast<size_t>(c);
-  const double* s = pose_scale + 12 * static_cast<size_t>(c);
-  double A12[12][12];
-  for (int i = 0; i < 12; ++i) {
-    for (int j = 0; j < 12; ++j) A12[i][j] = s[i] * s[j] * kron_entry(kr, i, j);
-  }
-  double A[D][D], Inv[D][D];
-  if (JOINT) {
-    // Pi^T A Pi = (H S A S H)[1:,1:]  with S the 0<->p exchange and H = I - tau w w^T
-    double pv[12];
-    for (int i = 0; i < 12; ++i) pv[i] = P[12 * static_cast<size_t>(c) + i];
-    Reflector<12> pi;
-    pi.make(pv);
-    const int p = pi.p;
-    if (p != 0) {
-      for (int j = 0; j < 12; ++j) {
-        const double t = A12[0][j];
-        A12[0][j] = A12[p][j];
-        A12[p][j] = t;
-      }
-      for (int i = 0; i < 12; ++i) {
-        const double t = A12[i][0];
-        A12[i][0] = A12[i][p];
-        A12[i][p] = t;
-      }
-    }
-    double u[12], alpha = 0.0;
-    for (int i = 0; i < 12; ++i) {
-      double v = 0.0;
-      for (int j = 0; j < 12; ++j) v += A12[i][j] * pi.w[j];
-      u[i] = v;
-    }
-    for (int i = 0; i < 12; ++i) alpha += pi.w[i] * u[i];
-    const double tau = pi.tau;
-    for (int i = 1; i < 12; ++i) {
-      for (int j = 1; j < 12; ++j) {
-        A[i - 1][j - 1] = A12[i][j] - tau * (pi.w[i] * u[j] + u[i] * pi.w[j]) +
-                          tau * tau * alpha * pi.w[i] * pi.w[j];
-      }
-    }
-  } else {
-    for (int i = 0; i < 12; ++i) {
-      for (int j = 0; j < 12; ++j) A[i][j] = A12[i][j];
-    }
-  }
-  double* bm = Bmat + 144 * static_cast<size_t>(c);
-  if (MODE == 0) {
-    for (int i = 0; i < D; ++i) A[i][i] += lambda;
-    for (int i = 0; i < D; ++i) {
-      for (int j = 0; j < D; ++j) bm[i * D + j] = A[i][j];
-    }
-  } else {
-    for (int i = 0; i < D; ++i) {
-      for (int j = 0; j < D; ++j) A[i][j] = bm[i * D + j] - A[i][j];
-    }
-  }
-  chol_inverse<D>(A, Inv);
-  double* bi = Binv + 144 * static_cast<size_t>(c);
-  for (int i = 0; i < D; ++i) {
-    for (int j = 0; j < D; ++j) bi[i * D + j] = Inv[i][j];
   }
 }
 
@@ -1115,32 +1007,20 @@ k_block_matvec(int C, int D, const double* __restrict__ blocks, const double* __
 void launch_kron(const DeviceState& d, const ModelParams& mp, bool joint, KronKind kind,
                  const LaunchCfg& lc) {
   const Robust rb = {mp.robust_norm, mp.huber};
-  // POVAR_KRON=v1: one entry per lane with 60 accumulators (A/B runs); default: FP64 tensor cores
-  static const bool v1 = getenv("POVAR_KRON") != nullptr && std::strcmp(getenv("POVAR_KRON"), "v1") == 0;
-  const int blocks = v1 ? item_grid(d) : (d.ix.num_items + kKronWarps - 1) / kKronWarps;
-  const int threads = v1 ? kBlock : 32 * kKronWarps;
+  const int blocks = (d.ix.num_items + kKronWarps - 1) / kKronWarps;
+  const int threads = 32 * kKronWarps;
   if (blocks == 0) return;
   double* cw = (!joint && kind == KRON_HPP && mp.robust_norm == NORM_HUBER) ? d.csc_w : nullptr;
   double* cd = (joint && kind == KRON_HPP) ? d.csc_d : nullptr;
 #define POVAR_KRON_LAUNCH(K, J, KIND)                                                                     \
   K<J, KIND><<<blocks, threads, 0, lc.stream>>>(d.ix, d.P, d.X, mp.c1, mp.c2, rb, d.lm_scale, d.hll_inv, \
                                                 d.item_kron, cd, cw)
-  if (v1) {
-    if (kind == KRON_HPP) {
-      if (joint) POVAR_KRON_LAUNCH(k_kron, true, KRON_HPP);
-      else POVAR_KRON_LAUNCH(k_kron, false, KRON_HPP);
-    } else {
-      if (joint) POVAR_KRON_LAUNCH(k_kron, true, KRON_SDIAG);
-      else POVAR_KRON_LAUNCH(k_kron, false, KRON_SDIAG);
-    }
+  if (kind == KRON_HPP) {
+    if (joint) POVAR_KRON_LAUNCH(k_kron_mma, true, KRON_HPP);
+    else POVAR_KRON_LAUNCH(k_kron_mma, false, KRON_HPP);
   } else {
-    if (kind == KRON_HPP) {
-      if (joint) POVAR_KRON_LAUNCH(k_kron_mma, true, KRON_HPP);
-      else POVAR_KRON_LAUNCH(k_kron_mma, false, KRON_HPP);
-    } else {
-      if (joint) POVAR_KRON_LAUNCH(k_kron_mma, true, KRON_SDIAG);
-      else POVAR_KRON_LAUNCH(k_kron_mma, false, KRON_SDIAG);
-    }
+    if (joint) POVAR_KRON_LAUNCH(k_kron_mma, true, KRON_SDIAG);
+    else POVAR_KRON_LAUNCH(k_kron_mma, false, KRON_SDIAG);
   }
 #undef POVAR_KRON_LAUNCH
   count(lc);
@@ -1161,67 +1041,35 @@ void launch_cam_scale(const DeviceState& d, const ModelParams& mp, const LaunchC
   count(lc);
 }
 
-static bool cam_binv_v1() {
-  static const bool v1 = getenv("POVAR_CAM_BINV") != nullptr && std::strcmp(getenv("POVAR_CAM_BINV"), "v1") == 0;
-  return v1;
-}
-
 void launch_cam_binv(const DeviceState& d, bool joint, double lambda, const LaunchCfg& lc) {
-  const int blocks = (d.ix.C + 127) / 128;
   const int blocks16 = (d.ix.C + kBlock / 16 - 1) / (kBlock / 16);
-  if (!cam_binv_v1()) {
-    if (joint) {
-      k_cam_binv16<true, 0><<<blocks16, kBlock, 0, lc.stream>>>(d.ix.C, d.P, d.kron, d.pose_scale, lambda, d.Bmat, d.Binv);
-    } else {
-      k_cam_binv16<false, 0><<<blocks16, kBlock, 0, lc.stream>>>(d.ix.C, d.P, d.kron, d.pose_scale, lambda, d.Bmat, d.Binv);
-    }
-  } else if (joint) {
-    k_cam_binv<true, 0><<<blocks, 128, 0, lc.stream>>>(d.ix.C, d.P, d.kron, d.pose_scale, lambda, d.Bmat, d.Binv);
+  if (joint) {
+    k_cam_binv16<true, 0><<<blocks16, kBlock, 0, lc.stream>>>(d.ix.C, d.P, d.kron, d.pose_scale, lambda, d.Bmat, d.Binv);
   } else {
-    k_cam_binv<false, 0><<<blocks, 128, 0, lc.stream>>>(d.ix.C, d.P, d.kron, d.pose_scale, lambda, d.Bmat, d.Binv);
+    k_cam_binv16<false, 0><<<blocks16, kBlock, 0, lc.stream>>>(d.ix.C, d.P, d.kron, d.pose_scale, lambda, d.Bmat, d.Binv);
   }
   count(lc);
 }
 
-// block-Jacobi preconditioner: Mprec = (Bmat - proj((s s^T) o kron_sdiag))^-1
 void launch_cam_precond(const DeviceState& d, bool joint, const double* kron_sdiag, const LaunchCfg& lc) {
-  const int blocks = (d.ix.C + 127) / 128;
   const int blocks16 = (d.ix.C + kBlock / 16 - 1) / (kBlock / 16);
-  if (!cam_binv_v1()) {
-    if (joint) {
-      k_cam_binv16<true, 1><<<blocks16, kBlock, 0, lc.stream>>>(d.ix.C, d.P, kron_sdiag, d.pose_scale, 0.0, d.Bmat, d.Mprec);
-    } else {
-      k_cam_binv16<false, 1><<<blocks16, kBlock, 0, lc.stream>>>(d.ix.C, d.P, kron_sdiag, d.pose_scale, 0.0, d.Bmat, d.Mprec);
-    }
-  } else if (joint) {
-    k_cam_binv<true, 1><<<blocks, 128, 0, lc.stream>>>(d.ix.C, d.P, kron_sdiag, d.pose_scale, 0.0, d.Bmat, d.Mprec);
+  if (joint) {
+    k_cam_binv16<true, 1><<<blocks16, kBlock, 0, lc.stream>>>(d.ix.C, d.P, kron_sdiag, d.pose_scale, 0.0, d.Bmat, d.Mprec);
   } else {
-    k_cam_binv<false, 1><<<blocks, 128, 0, lc.stream>>>(d.ix.C, d.P, kron_sdiag, d.pose_scale, 0.0, d.Bmat, d.Mprec);
+    k_cam_binv16<false, 1><<<blocks16, kBlock, 0, lc.stream>>>(d.ix.C, d.P, kron_sdiag, d.pose_scale, 0.0, d.Bmat, d.Mprec);
   }
   count(lc);
 }
 
-void launch_passB(const DeviceState& d, const ModelParams& mp, bool joint, PassBMode mode,
-                  bool in_series, const LaunchCfg& lc) {
+// b: the camera-major pass with r_i - Jl_i H_l per observation (prepare_Hb_*); the E0 products use
+// k_passB_e0_v2 (kernels_series.cu)
+void launch_passB(const DeviceState& d, const ModelParams& mp, bool joint, const LaunchCfg& lc) {
   const Robust rb = {mp.robust_norm, mp.huber};
   const int blocks = item_grid(d);
-  const SeriesCtl* ctl = in_series ? d.ctl : nullptr;
   if (joint) {
-    if (mode == PASSB_E0) {
-      k_passB<true, PASSB_E0><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.lm_rec, mp.c1, mp.c2, rb,
-                                                                d.item_part, ctl);
-    } else {
-      k_passB<true, PASSB_B><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.lm_rec, mp.c1, mp.c2, rb,
-                                                               d.item_part, ctl);
-    }
+    k_passB<true, PASSB_B><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.lm_rec, mp.c1, mp.c2, rb, d.item_part, nullptr);
   } else {
-    if (mode == PASSB_E0) {
-      k_passB<false, PASSB_E0><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.lm_rec, mp.c1, mp.c2, rb,
-                                                                 d.item_part, ctl);
-    } else {
-      k_passB<false, PASSB_B><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.lm_rec, mp.c1, mp.c2, rb,
-                                                                d.item_part, ctl);
-    }
+    k_passB<false, PASSB_B><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.lm_rec, mp.c1, mp.c2, rb, d.item_part, nullptr);
   }
   count(lc);
 }
@@ -1311,7 +1159,7 @@ void launch_peer_allreduce(const DeviceState& d, double* buf, size_t n, const Pe
                            const LaunchCfg& lc) {
   if (n == 0) return;
   size_t blocks = (n + kBlock - 1) / kBlock;
-  if (blocks > 148 * 2) blocks = 148 * 2;   // one wave, always resident
+  if (blocks > static_cast<size_t>(sm_count()) * 2) blocks = static_cast<size_t>(sm_count()) * 2;   // one wave, always resident
   k_peer_allreduce<<<static_cast<int>(blocks), kBlock, 0, lc.stream>>>(buf, n, px, d.ctl);
   count(lc);
 }

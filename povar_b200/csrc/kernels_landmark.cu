@@ -11,7 +11,6 @@
 //   k_cost              helper.cpp:116-196, bal/residual_info.cpp:97-117
 //   k_lin_landmark      sc/landmark_block.hpp:135-225 (Jl part), 284-309 (scale_Jl_cols_*)
 //   k_prep_landmark     sc/landmark_block.hpp:474-572 (Hll^-1, Hll^-1 Jl^T r)
-//   k_e0_landmark       sc/linearization_power_varproj.hpp:364-453, first half (Jl^T Jp x, Hll^-1)
 //   k_backsub_*         sc/landmark_block.hpp:574-707
 #include <cuda_runtime.h>
 
@@ -492,78 +491,6 @@ __device__ __forceinline__ void landmark_solve(const double* acc, const double (
 }
 
 // ------------------------------------------------------------------------------------------
-// E0 product, landmark half:  H_l = scale o (Pi) Hll^-1 (Pi^T) scale o sum_i Jl_raw^T (w Jp_raw y)
-// ------------------------------------------------------------------------------------------
-template <bool JOINT>
-__global__ void __launch_bounds__(kBlock)
-k_e0_landmark(DeviceIndex ix, const double* __restrict__ P, const double* __restrict__ X,
-              const double* __restrict__ y, double c1, double c2, Robust rb,
-              const double* __restrict__ lm_scale, const double* __restrict__ hll_inv,
-              double* __restrict__ lm_rec, const SeriesCtl* __restrict__ ctl) {
-  if (ctl != nullptr && ctl->done) return;
-  constexpr int NV = JOINT ? 4 : 3;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (int tile = warp; tile < ix.num_tiles; tile += nwarps) {
-    const TileLane t(ix.tile_ptr, tile);
-    double acc[NV];
-#pragma unroll
-    for (int k = 0; k < NV; ++k) acc[k] = 0.0;
-    int lm = __ldg(ix.obs_lm + t.tb), o_first = -1;
-    bool has_obs = false;
-    double x[4] = {0, 0, 0, 0};
-    for (int o = t.tb + t.lane; o < t.te; o += 32) {
-      has_obs = true;
-      if (o_first < 0) o_first = o;
-      lm = __ldg(ix.obs_lm + o);
-      const int c = __ldg(ix.obs_cam + o);
-      Cam3x4 cam;
-      load_cam(P, c, cam);
-      load_lm4(X, lm, x);
-      const double2 uv = ix.obs_uv[o];
-      double y0[4], y1[4], y2[4];
-      const double* yc = y + 12 * static_cast<size_t>(c);
-      load4(yc, y0);
-      load4(yc + 4, y1);
-      load4(yc + 8, y2);
-      if (JOINT) {
-        JointObs ob;
-        ob.eval(cam, uv.x, uv.y, x, rb);
-        double a[2], j0[4], j1[4];
-        ob.jp_mul(x, y0, y1, y2, a);
-        ob.jl_rows(cam, j0, j1);
-        const double w = ob.sw * ob.sw;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) acc[k] += w * (j0[k] * a[0] + j1[k] * a[1]);
-      } else {
-        PoseObs ob;
-        ob.eval(cam, uv.x, uv.y, x, c1, c2, rb);
-        double a[4];
-        pose_jp_mul(x, uv.x, uv.y, c1, c2, y0, y1, y2, a);
-        const double w = ob.sw * ob.sw;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          acc[k] += w * (ob.T[0][k] * a[0] + ob.T[1][k] * a[1] + ob.T[2][k] * a[2] + ob.T[3][k] * a[3]);
-        }
-      }
-    }
-    tile_allreduce<NV>(acc, t, has_obs, lm, ix.lm_ptr);
-    if (is_head(t, has_obs, lm, ix.lm_ptr, o_first)) {
-      double s[4], inv[6], H[4];
-      load_lm4(X, lm, x);
-      load_lm4(lm_scale, lm, s);
-      const double* hi = hll_inv + 6 * static_cast<size_t>(lm);
-#pragma unroll
-      for (int k = 0; k < 6; ++k) inv[k] = hi[k];
-      landmark_solve<JOINT>(acc, x, s, inv, H);
-      double* rec = lm_rec + kLmRec * static_cast<size_t>(lm) + 4;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) rec[k] = H[k];
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
 // back-substitutions.  l_diff partial sums go to scalar_part[block]; k_scalar_final adds them.
 // ------------------------------------------------------------------------------------------
 // VarPro (landmark_block.hpp:670-707): cameras are ALREADY updated (P), P_old is the backup.
@@ -864,7 +791,7 @@ __global__ void k_normalize_lms(int L, double* __restrict__ X) {
 inline int tile_grid(const DeviceState& d) {
   const int warps_per_block = kBlock / 32;
   long long blocks = (static_cast<long long>(d.ix.num_tiles) + warps_per_block - 1) / warps_per_block;
-  const long long cap = 148LL * 8 * 4;   // a few waves of 148 SMs x 8 resident blocks
+  const long long cap = static_cast<long long>(sm_count()) * 8 * 4;   // a few waves of 8 resident blocks per SM
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return static_cast<int>(blocks);
@@ -878,7 +805,7 @@ inline void count(const LaunchCfg& lc, int n = 1) {
 
 int cost_blocks(const DeviceState& d) {
   long long blocks = (static_cast<long long>(d.ix.nnz) + kBlock - 1) / kBlock;
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
   if (blocks < 1) blocks = 1;
   return static_cast<int>(blocks);
 }
@@ -934,21 +861,6 @@ void launch_prep_landmark(const DeviceState& d, bool joint, double lambda_lm, co
   } else {
     k_prep_landmark<false><<<blocks, kBlock, 0, lc.stream>>>(d.ix.L, d.X, d.lm_hraw, d.lm_graw, d.lm_scale,
                                                              lambda_lm, d.hll_inv, d.lm_rec, d.lm_fold);
-  }
-  count(lc);
-}
-
-void launch_e0_landmark(const DeviceState& d, const ModelParams& mp, bool joint, const double* y,
-                        bool in_series, const LaunchCfg& lc) {
-  const Robust rb = {mp.robust_norm, mp.huber};
-  const int blocks = tile_grid(d);
-  const SeriesCtl* ctl = in_series ? d.ctl : nullptr;
-  if (joint) {
-    k_e0_landmark<true><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.X, y, mp.c1, mp.c2, rb, d.lm_scale,
-                                                          d.hll_inv, d.lm_rec, ctl);
-  } else {
-    k_e0_landmark<false><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.X, y, mp.c1, mp.c2, rb, d.lm_scale,
-                                                           d.hll_inv, d.lm_rec, ctl);
   }
   count(lc);
 }

@@ -171,7 +171,7 @@ void launch_dot(const DeviceState& d, int n, const double* x, const double* y, i
 
 void launch_finite_check(const DeviceState& d, int n, const double* x, const LaunchCfg& lc) {
   int blocks = (n + kBlock - 1) / kBlock;
-  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks > sm_count() * 4) blocks = sm_count() * 4;
   k_finite_check<<<blocks, kBlock, 0, lc.stream>>>(n, x, d.ctl);
   count(lc);
 }
@@ -180,7 +180,7 @@ void launch_dense_schur(const DeviceState& d, const ModelParams& mp, double* S, 
   const Robust rb = {mp.robust_norm, mp.huber};
   const long long ld = 12LL * d.ix.C;
   long long blocks = (static_cast<long long>(d.ix.L) + (kBlock / 32) - 1) / (kBlock / 32);
-  if (blocks > 148LL * 8 * 4) blocks = 148LL * 8 * 4;
+  if (blocks > static_cast<long long>(sm_count()) * 8 * 4) blocks = static_cast<long long>(sm_count()) * 8 * 4;
   if (blocks < 1) blocks = 1;
   k_dense_schur<<<static_cast<int>(blocks), kBlock, 0, lc.stream>>>(d.ix, d.P, d.X, mp.c1, mp.c2, rb, d.lm_scale,
                                                                     d.hll_inv, d.pose_scale, S, ld);

@@ -595,31 +595,13 @@ void launch_passB_e0_v2(const DeviceState& d, const ModelParams& mp, bool joint,
   const int blocks = (d.ix.num_items + kWarps - 1) / kWarps;
   const SeriesCtl* ctl = in_series ? d.ctl : nullptr;
   const bool hasw = !joint && mp.robust_norm == NORM_HUBER;
-  // steps (of sixteen entries) a warp keeps in flight per trip: the pass is bound by the number of
-  // landmark records in flight (Little's law), registers permitting
-  static const int steps = getenv("POVAR_PASSB_STEPS") ? atoi(getenv("POVAR_PASSB_STEPS")) : 2;
+  // two steps of sixteen entries in flight per trip (more was measured slower: registers, profiles/r1_summary.md)
 #define POVAR_PASSB(J, W, S, CD, CW)                                                                   \
   k_passB_e0_v2<J, W, S><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.lm_rec, CD, CW, mp.c1, mp.c2, \
                                                            d.item_part, ctl)
-  if (steps == 12) {   // two steps, four blocks per SM (64 registers)
-    if (joint) {
-      k_passB_e0_v2<true, false, 2, 4><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.lm_rec, d.csc_d, nullptr, mp.c1,
-                                                                         mp.c2, d.item_part, ctl);
-    } else {
-      k_passB_e0_v2<false, false, 2, 4><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.lm_rec, nullptr, nullptr,
-                                                                          mp.c1, mp.c2, d.item_part, ctl);
-    }
-  } else if (joint) {
-    if (steps >= 4) POVAR_PASSB(true, false, 4, d.csc_d, nullptr);
-    else if (steps == 3) POVAR_PASSB(true, false, 3, d.csc_d, nullptr);
-    else POVAR_PASSB(true, false, 2, d.csc_d, nullptr);
-  } else if (hasw) {
-    POVAR_PASSB(false, true, 2, nullptr, d.csc_w);
-  } else {
-    if (steps >= 4) POVAR_PASSB(false, false, 4, nullptr, nullptr);
-    else if (steps == 3) POVAR_PASSB(false, false, 3, nullptr, nullptr);
-    else POVAR_PASSB(false, false, 2, nullptr, nullptr);
-  }
+  if (joint) POVAR_PASSB(true, false, 2, d.csc_d, nullptr);
+  else if (hasw) POVAR_PASSB(false, true, 2, nullptr, d.csc_w);
+  else POVAR_PASSB(false, false, 2, nullptr, nullptr);
 #undef POVAR_PASSB
   count(lc);
 }

@@ -186,8 +186,6 @@ void launch_cost(const DeviceState& d, const ModelParams& mp, bool joint, const 
 void launch_lin_landmark(const DeviceState& d, const ModelParams& mp, bool joint, bool scale_jl,
                          const LaunchCfg& lc);
 void launch_prep_landmark(const DeviceState& d, bool joint, double lambda_lm, const LaunchCfg& lc);
-void launch_e0_landmark(const DeviceState& d, const ModelParams& mp, bool joint, const double* y,
-                        bool in_series, const LaunchCfg& lc);
 void launch_backsub_varpro(const DeviceState& d, const ModelParams& mp, const double* inc,
                            const LaunchCfg& lc);
 void launch_backsub_poba(const DeviceState& d, const ModelParams& mp, const double* y,
@@ -209,8 +207,7 @@ void launch_cam_scale(const DeviceState& d, const ModelParams& mp, const LaunchC
 void launch_cam_binv(const DeviceState& d, bool joint, double lambda, const LaunchCfg& lc);
 void launch_cam_precond(const DeviceState& d, bool joint, const double* kron_sdiag, const LaunchCfg& lc);
 enum PassBMode { PASSB_E0 = 0, PASSB_B = 1 };
-void launch_passB(const DeviceState& d, const ModelParams& mp, bool joint, PassBMode mode,
-                  bool in_series, const LaunchCfg& lc);
+void launch_passB(const DeviceState& d, const ModelParams& mp, bool joint, const LaunchCfg& lc);
 // series bookkeeping
 void launch_series_start(const DeviceState& d, double r_tolerance, int max_terms, const LaunchCfg& lc);
 // mode kTermFused: the term kernel adds the item partials of the camera half itself (single GPU);

@@ -42,8 +42,10 @@ CONFIGS = [
                                            "--max-num-iterations-step-2", "8"]),
     ("trafalgar257_pcg", "trafalgar257", ["--solver-type-step-1", "PCG", "--max-num-iterations-step-2", "4"]),
     ("trafalgar257_cholesky", "trafalgar257", ["--solver-type-step-1", "CHOLESKY", "--max-num-iterations-step-2", "4"]),
+    # HUBER re-weighting makes step 2 chaotic at once (reference vs itself: 6e-7 at its first cost, 5e-4 after one
+    # iteration): the IRLS path is pinned through all of step 1 and the conversion to step 2
     ("trafalgar257_huber", "trafalgar257", ["--residual-robust-norm", "HUBER", "--residual-huber-parameter", "10",
-                                            "--max-num-iterations-step-2", "8"]),
+                                            "--max-num-iterations-step-2", "0"]),
     ("venice89_poba", "venice89", ["--solver-type-step-1", "POWER_SCHUR_COMPLEMENT",
                                    "--max-num-iterations-step-2", "36"]),
     ("venice1778_povar_cauchy", "venice1778", ["--residual-robust-norm", "CAUCHY"]),
