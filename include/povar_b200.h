@@ -331,6 +331,12 @@ int povar_debug_sell_layout(int32_t num_cams, int32_t num_lms, const int64_t* lm
                             int32_t threads, int32_t* slice_ptr, int32_t* sell_lm, int32_t* long_lms,
                             int64_t sizes[3]);
 
+/* The direct solver of CHOLESKY (blocked LL^T on FP64 tensor-core tiles + substitution, kernels_chol.cu) on a
+ * caller-supplied symmetric matrix: x = A^-1 b for a row-major n x n matrix of which the lower triangle is read.
+ * *info = 0, or 1 + the index of the first 64-row tile with a non-positive pivot (x is then undefined).  What the
+ * reference does with Eigen::SimplicialLLT (sc/linearization_sc.hpp:236-245); exposed for the tests. */
+int povar_debug_cholesky(int32_t n, const double* A, const double* b, double* x, int32_t* info);
+
 /* 1 if this handle exchanges the per-term camera sums over peer memory (CUDA IPC + NVLink stores fused
  * into the term kernel), 0 if it uses ncclAllReduce per term (single GPU: 0).  POVAR_PEER_EXCHANGE=0 in
  * the environment forces NCCL, =1 makes povar_create fail instead of falling back. */

@@ -27,6 +27,7 @@ LIB_SOURCES = [
     "kernels_landmark.cu",
     "kernels_camera.cu",
     "kernels_schur.cu",
+    "kernels_chol.cu",
     "kernels_series.cu",
     "kernels_index.cu",
     "engine.cu",

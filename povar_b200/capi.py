@@ -155,6 +155,7 @@ SIGNATURES = {
     "povar_launch_count": (C.c_int64, [_H]),
     "povar_bal_create_dataset": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int64, C.c_char_p, C.c_size_t]),
     "povar_peer_exchange_active": (C.c_int, [_H]),
+    "povar_debug_cholesky": (C.c_int, [C.c_int32, _DP, _DP, _DP, C.POINTER(C.c_int32)]),
     "povar_write_ba_log": (C.c_int, [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "povar_debug_sell_layout": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.c_int32,
                                           C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
@@ -489,6 +490,19 @@ def unique_id() -> bytes:
     if rc != OK:
         raise PovarError(rc, lib.povar_last_error(None).decode())
     return bytes(buf)
+
+
+def cholesky_solve(A: np.ndarray, b: np.ndarray):
+    """x = A^-1 b by the library's own blocked Cholesky (povar_debug_cholesky); returns (x, info)"""
+    lib = load()
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    x = np.empty_like(b)
+    info = C.c_int32(0)
+    rc = lib.povar_debug_cholesky(A.shape[0], _dp(A), _dp(b), _dp(x), C.byref(info))
+    if rc != OK:
+        raise PovarError(rc, "povar_debug_cholesky failed")
+    return x, info.value
 
 
 def host_id() -> bytes:

@@ -11,6 +11,7 @@ namespace povar {
 int nccl_unique_id(uint8_t id[128], std::string* err);
 int nccl_finalize();
 int host_unique_id(uint8_t id[128]);
+int debug_cholesky(int n, const double* A, const double* b, double* x, int* info_out);
 }
 
 struct povar_handle {
@@ -249,6 +250,10 @@ int povar_debug_sell_layout(int32_t num_cams, int32_t num_lms, const int64_t* lm
   return POVAR_OK;
 }
 
+int povar_debug_cholesky(int32_t n, const double* A, const double* b, double* x, int32_t* info) {
+  return povar::debug_cholesky(n, A, b, x, info);
+}
+
 int povar_peer_exchange_active(const povar_handle* h) {
   if (!h || !h->engine) return 0;
   return h->engine->peer_exchange_active() ? 1 : 0;
@@ -266,4 +271,9 @@ namespace povar {
 const PhaseTimes& handle_times(povar_handle* h) { return h->engine->last_times(); }
 void handle_reset_times(povar_handle* h) { h->engine->reset_times(); }
 int handle_rank(povar_handle* h) { return h->engine->rank(); }
+int handle_linearize_deferred(povar_handle* h, bool joint, double alpha) { return h->engine->linearize(joint, alpha, true); }
+int handle_trial(povar_handle* h, bool joint, double alpha, double lambda, int32_t* iterations, double* l_diff,
+                 povar_residual_info* ri) {
+  return h->engine->trial(joint, alpha, lambda, iterations, l_diff, ri);
+}
 }  // namespace povar

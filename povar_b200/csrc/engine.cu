@@ -388,7 +388,6 @@ void build_items(const std::vector<int>& cam_ptr, int item_len, std::vector<int>
   (*cam_item_ptr)[C] = static_cast<int>(item_cam->size());
 }
 
-static void destroy_cusolver(void* handle);   // defined next to the dlopen'ed cuSOLVER entry points
 
 // ---------------------------------------------------------------------------------------------
 int Engine::fail(int code, const std::string& what) {
@@ -470,7 +469,8 @@ int Engine::create(const povar_problem_desc* desc, const povar_options* opt,
     }
   }
   if (rc == POVAR_OK) rc = e->check(cudaStreamCreateWithFlags(&e->stream_, cudaStreamNonBlocking), "cudaStreamCreate");
-  for (int i = 0; i < 4 && rc == POVAR_OK; ++i) rc = e->check(cudaEventCreate(&e->ev_[i]), "cudaEventCreate");
+  for (int i = 0; i < 6 && rc == POVAR_OK; ++i) rc = e->check(cudaEventCreate(&e->ev_[i]), "cudaEventCreate");
+  if (rc == POVAR_OK) rc = e->check(cudaHostAlloc(reinterpret_cast<void**>(&e->host_out_), 256, cudaHostAllocDefault), "cudaHostAlloc");
   if (rc == POVAR_OK && e->world_ > 1 && opt->solver_type_step_1 == POVAR_CHOLESKY) {
     // the direct solver's reduced camera system is not sharded (solver/linearizor_sc.cpp:121-128 is serial too)
     rc = e->fail(POVAR_ERR_UNSUPPORTED, "CHOLESKY is single-GPU: create the handle without a communicator");
@@ -525,7 +525,11 @@ Engine::~Engine() {
   if (device_ >= 0) cudaSetDevice(device_);
   if (stream_) cudaStreamSynchronize(stream_);
   // the communicator belongs to the process-wide cache (povar_comm_finalize releases it)
-  if (cusolver_) destroy_cusolver(cusolver_);
+  for (void*& g : series_graph_) {
+    if (g) cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(g));
+    g = nullptr;
+  }
+  if (host_out_) cudaFreeHost(host_out_);
   if (peer_owned_ && peer_) {
     peer_->release();
     delete peer_;
@@ -704,6 +708,7 @@ int Engine::upload(const povar_problem_desc* desc) {
   PV_ALLOC(d_.cost_out, 1);
   PV_ALLOC(d_.scalar_part, static_cast<size_t>(scalar_blocks(d_)) + 8);
   PV_ALLOC(d_.scalar_out, 8);
+  PV_ALLOC(d_.trial_out, 16);
   PV_ALLOC(d_.flags, 4);
   PV_ALLOC(d_.ctl, 1);
   PV_UP(d_.P, desc->cam_P, sizeof(double) * C12);
@@ -897,49 +902,41 @@ int Engine::init_varproj(double alpha) {
   return POVAR_OK;
 }
 
+// cost kernels + (sharded) the in-place sum over the ranks: the result is trial_out[0..7] on the device
+int Engine::enqueue_cost(bool joint, double alpha) {
+  set_model(joint, joint ? opt_.alpha : alpha);
+  launch_cost(d_, mp_, joint, lc());
+  return allreduce(d_.trial_out, 8);
+}
+
+void Engine::decode_cost(const double* v, povar_residual_info* out) {
+  out->error_all = v[0];
+  out->residual_sum_all = v[1];
+  out->error_valid = v[2];
+  out->residual_sum_valid = v[3];
+  out->num_obs_all = static_cast<long long>(v[4] + 0.5);
+  out->num_obs_valid = static_cast<long long>(v[5] + 0.5);
+  out->is_numerically_valid = v[6] > 0 ? 0 : 1;
+}
+
 int Engine::cost(bool joint, double alpha, povar_residual_info* out) {
   PV_CUDA(cudaSetDevice(device_));
-  set_model(joint, joint ? opt_.alpha : alpha);
   PV_CUDA(cudaEventRecord(ev_[0], stream_));
-  launch_cost(d_, mp_, joint, lc());
-  PV_CUDA(cudaGetLastError());
-  CostAccum h{};
-  if (world_ > 1) {
-    // sums travel as doubles: {err_all, rsum_all, err_valid, rsum_valid, n_all, n_valid, nonfinite}
-    PV_CUDA(cudaMemcpyAsync(&h, d_.cost_out, sizeof(h), cudaMemcpyDeviceToHost, stream_));
-    PV_CUDA(cudaStreamSynchronize(stream_));
-    double v[8] = {h.err_all, h.rsum_all, h.err_valid, h.rsum_valid, static_cast<double>(h.n_all),
-                   static_cast<double>(h.n_valid), static_cast<double>(h.nonfinite), 0.0};
-    PV_CUDA(cudaMemcpyAsync(d_.scalar_out, v, sizeof(v), cudaMemcpyHostToDevice, stream_));
-    const int rc = allreduce(d_.scalar_out, 8);
+  {
+    const int rc = enqueue_cost(joint, alpha);
     if (rc != POVAR_OK) return rc;
-    PV_CUDA(cudaMemcpyAsync(v, d_.scalar_out, sizeof(v), cudaMemcpyDeviceToHost, stream_));
-    PV_CUDA(cudaEventRecord(ev_[1], stream_));
-    PV_CUDA(cudaStreamSynchronize(stream_));
-    h.err_all = v[0];
-    h.rsum_all = v[1];
-    h.err_valid = v[2];
-    h.rsum_valid = v[3];
-    h.n_all = static_cast<long long>(v[4] + 0.5);
-    h.n_valid = static_cast<long long>(v[5] + 0.5);
-    h.nonfinite = v[6] > 0 ? 1 : 0;
-  } else {
-    PV_CUDA(cudaMemcpyAsync(&h, d_.cost_out, sizeof(h), cudaMemcpyDeviceToHost, stream_));
-    PV_CUDA(cudaEventRecord(ev_[1], stream_));
-    PV_CUDA(cudaStreamSynchronize(stream_));
   }
+  PV_CUDA(cudaGetLastError());
+  double* v = host_out_ + 8;
+  PV_CUDA(cudaMemcpyAsync(v, d_.trial_out, 8 * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+  PV_CUDA(cudaEventRecord(ev_[1], stream_));
+  PV_CUDA(cudaStreamSynchronize(stream_));
   times_.residual += elapsed(ev_[0], ev_[1]);
-  out->num_obs_all = h.n_all;
-  out->error_all = h.err_all;
-  out->residual_sum_all = h.rsum_all;
-  out->num_obs_valid = h.n_valid;
-  out->error_valid = h.err_valid;
-  out->residual_sum_valid = h.rsum_valid;
-  out->is_numerically_valid = h.nonfinite ? 0 : 1;
+  decode_cost(v, out);
   return POVAR_OK;
 }
 
-int Engine::linearize(bool joint, double alpha) {
+int Engine::linearize(bool joint, double alpha, bool defer_check) {
   PV_CUDA(cudaSetDevice(device_));
   set_model(joint, joint ? opt_.alpha : alpha);
   joint_lin_ = joint ? 1 : 0;
@@ -973,22 +970,24 @@ int Engine::linearize(bool joint, double alpha) {
   }
   launch_cam_scale(d_, mp_, lc());
   launch_cam_rec_static(d_, joint, lc());
-  PV_CUDA(cudaGetLastError());
-  int flags[4] = {0, 0, 0, 0};
-  PV_CUDA(cudaMemcpyAsync(flags, d_.flags, sizeof(flags), cudaMemcpyDeviceToHost, stream_));
+  // numerical-failure flag of this shard as a double, summed over the ranks in place
+  launch_flag_to_double(d_, lc());
+  {
+    const int rc = allreduce(d_.trial_out + 9, 1);
+    if (rc != POVAR_OK) return rc;
+  }
   PV_CUDA(cudaEventRecord(ev_[1], stream_));
+  PV_CUDA(cudaGetLastError());
+  if (defer_check) {
+    // the caller goes on to a trial(): the flag comes back with that trial's results (one synchronisation)
+    lin_check_pending_ = true;
+    return POVAR_OK;
+  }
+  double* v = host_out_ + 8;
+  PV_CUDA(cudaMemcpyAsync(v + 9, d_.trial_out + 9, sizeof(double), cudaMemcpyDeviceToHost, stream_));
   PV_CUDA(cudaStreamSynchronize(stream_));
   times_.linearize += elapsed(ev_[0], ev_[1]);
-  if (world_ > 1) {
-    double v[1] = {static_cast<double>(flags[0])};
-    PV_CUDA(cudaMemcpyAsync(d_.scalar_out, v, sizeof(v), cudaMemcpyHostToDevice, stream_));
-    const int rc = allreduce(d_.scalar_out, 1);
-    if (rc != POVAR_OK) return rc;
-    PV_CUDA(cudaMemcpyAsync(v, d_.scalar_out, sizeof(v), cudaMemcpyDeviceToHost, stream_));
-    PV_CUDA(cudaStreamSynchronize(stream_));
-    flags[0] = v[0] > 0 ? 1 : 0;
-  }
-  if (flags[0]) return fail(POVAR_NUM_LINEARIZATION, "did not expect numerical failure during linearization");
+  if (v[9] > 0) return fail(POVAR_NUM_LINEARIZATION, "did not expect numerical failure during linearization");
   return POVAR_OK;
 }
 
@@ -1019,16 +1018,57 @@ int Engine::solve_power(bool joint, double lambda) {
   }
   PV_CUDA(cudaEventRecord(ev_[1], stream_));
   // solve_*: accum = B^-1(-b); tmp = B^-1 E0 tmp; accum += tmp; early exit on zeta < eta
-  launch_finish_b(d_, joint, lc());
-  const int m = opt_.power_sc_iterations;
-  launch_series_start(d_, opt_.r_tolerance, m, lc());
-  for (int i = 1; i <= m; ++i) {
-    const int rc = e0_product(joint, d_.vec_y, true);
+  {
+    const int rc = enqueue_series(joint);
     if (rc != POVAR_OK) return rc;
-    launch_series_term(d_, joint, i, opt_.eta, opt_.r_tolerance, term_mode(), exchange(), lc());
   }
   PV_CUDA(cudaEventRecord(ev_[2], stream_));
   PV_CUDA(cudaGetLastError());
+  return POVAR_OK;
+}
+
+// The launches of one power series -- b -> x0, series start, then per term landmark half, camera half, term
+// kernel -- have the same arguments in every solve of a model (the damping enters before, the early exit is
+// decided on the device, the number of a peer exchange is a device-side counter): they are captured once into
+// a CUDA graph and replayed, one launch per solve instead of 3 m + 2.  The first solve of a model runs eagerly
+// (it sets function attributes and allocates nothing afterwards), the second is captured.
+int Engine::enqueue_series(bool joint) {
+  const int m = opt_.power_sc_iterations;
+  const int which = joint ? 1 : 0;
+  auto enqueue = [&]() -> int {
+    launch_finish_b(d_, joint, lc());
+    launch_series_start(d_, opt_.r_tolerance, m, lc());
+    for (int i = 1; i <= m; ++i) {
+      const int rc = e0_product(joint, d_.vec_y, true);
+      if (rc != POVAR_OK) return rc;
+      launch_series_term(d_, joint, i, opt_.eta, opt_.r_tolerance, term_mode(), exchange(), lc());
+    }
+    return POVAR_OK;
+  };
+  // NCCL's all-reduce per term (no peer exchange) stays outside graphs: eager
+  const bool graphable = term_mode() != kTermRaw;
+  if (!graphable || series_calls_[which]++ == 0) return enqueue();
+  if (!series_graph_[which]) {
+    const long long before = launches_;
+    cudaGraph_t graph = nullptr;
+    PV_CUDA(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+    const int rc = enqueue();
+    const cudaError_t ce = cudaStreamEndCapture(stream_, &graph);
+    if (rc != POVAR_OK || ce != cudaSuccess || graph == nullptr) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      return rc != POVAR_OK ? rc : fail(POVAR_ERR_CUDA, "stream capture of the power series failed");
+    }
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) return check(ie, "cudaGraphInstantiate");
+    series_graph_[which] = exec;
+    series_graph_launches_[which] = launches_ - before;
+    launches_ = before;   // nothing ran during the capture
+  }
+  PV_CUDA(cudaGraphLaunch(static_cast<cudaGraphExec_t>(series_graph_[which]), stream_));
+  launches_ += series_graph_launches_[which];
   return POVAR_OK;
 }
 
@@ -1048,30 +1088,27 @@ int Engine::finish_solve(bool joint, double* inc, int32_t* iterations) {
   return POVAR_OK;
 }
 
-int Engine::solve(bool joint, double lambda, double* inc, int32_t* iterations) {
-  PV_CUDA(cudaSetDevice(device_));
+int Engine::enqueue_solve(bool joint, double lambda) {
   if (static_cast<int>(joint) != joint_lin_) return fail(POVAR_ERR_INVALID, "solve called without a matching linearize");
   have_solve_ = true;
   lambda_ = lambda;
-  int rc;
-  if (joint) {
-    rc = opt_.solver_type_step_2 == POVAR_RIPOBA ? solve_power(true, lambda) : solve_pcg(true, lambda);
-  } else {
-    switch (opt_.solver_type_step_1) {
-      case POVAR_POWER_VARPROJ:
-      case POVAR_POWER_SCHUR_COMPLEMENT:
-        rc = solve_power(false, lambda);
-        break;
-      case POVAR_PCG:
-        rc = solve_pcg(false, lambda);
-        break;
-      case POVAR_CHOLESKY:
-        rc = solve_cholesky(lambda);
-        break;
-      default:
-        return fail(POVAR_ERR_INVALID, "unknown solver_type_step_1");
-    }
+  if (joint) return opt_.solver_type_step_2 == POVAR_RIPOBA ? solve_power(true, lambda) : solve_pcg(true, lambda);
+  switch (opt_.solver_type_step_1) {
+    case POVAR_POWER_VARPROJ:
+    case POVAR_POWER_SCHUR_COMPLEMENT:
+      return solve_power(false, lambda);
+    case POVAR_PCG:
+      return solve_pcg(false, lambda);
+    case POVAR_CHOLESKY:
+      return solve_cholesky(lambda);
+    default:
+      return fail(POVAR_ERR_INVALID, "unknown solver_type_step_1");
   }
+}
+
+int Engine::solve(bool joint, double lambda, double* inc, int32_t* iterations) {
+  PV_CUDA(cudaSetDevice(device_));
+  const int rc = enqueue_solve(joint, lambda);
   if (rc != POVAR_OK) return rc;
   return finish_solve(joint, inc, iterations);
 }
@@ -1197,91 +1234,33 @@ int Engine::solve_pcg(bool joint, double lambda) {
   return POVAR_OK;
 }
 
-// ---- cuSOLVER through dlopen (dense Cholesky of the reduced camera system) ----
-struct CusolverApi {
-  void* lib = nullptr;
-  int (*Create)(void**) = nullptr;
-  int (*Destroy)(void*) = nullptr;
-  int (*SetStream)(void*, cudaStream_t) = nullptr;
-  int (*PotrfBuf)(void*, int, int, double*, int, int*) = nullptr;
-  int (*Potrf)(void*, int, int, double*, int, double*, int, int*) = nullptr;
-  int (*Potrs)(void*, int, int, int, const double*, int, double*, int, int*) = nullptr;
-};
-
-static CusolverApi* load_cusolver(std::string* err) {
-  static CusolverApi api;
-  if (api.lib) return &api;
-  const char* names[] = {getenv("POVAR_CUSOLVER_LIB"), "libcusolver.so.11", "libcusolver.so",
-                         "/usr/local/cuda/lib64/libcusolver.so.11"};
-  for (const char* nme : names) {
-    if (!nme) continue;
-    api.lib = dlopen(nme, RTLD_NOW | RTLD_GLOBAL);
-    if (api.lib) break;
-  }
-  if (!api.lib) {
-    if (err) *err = "cannot dlopen libcusolver.so.11 (set POVAR_CUSOLVER_LIB)";
-    return nullptr;
-  }
-  api.Create = reinterpret_cast<int (*)(void**)>(dlsym(api.lib, "cusolverDnCreate"));
-  api.Destroy = reinterpret_cast<int (*)(void*)>(dlsym(api.lib, "cusolverDnDestroy"));
-  api.SetStream = reinterpret_cast<int (*)(void*, cudaStream_t)>(dlsym(api.lib, "cusolverDnSetStream"));
-  api.PotrfBuf = reinterpret_cast<int (*)(void*, int, int, double*, int, int*)>(dlsym(api.lib, "cusolverDnDpotrf_bufferSize"));
-  api.Potrf = reinterpret_cast<int (*)(void*, int, int, double*, int, double*, int, int*)>(dlsym(api.lib, "cusolverDnDpotrf"));
-  api.Potrs = reinterpret_cast<int (*)(void*, int, int, int, const double*, int, double*, int, int*)>(dlsym(api.lib, "cusolverDnDpotrs"));
-  if (!api.Create || !api.Destroy || !api.SetStream || !api.PotrfBuf || !api.Potrf || !api.Potrs) {
-    if (err) *err = "libcusolver is missing expected symbols";
-    dlclose(api.lib);
-    api.lib = nullptr;
-    return nullptr;
-  }
-  return &api;
-}
-
-static void destroy_cusolver(void* handle) {
-  CusolverApi* cs = load_cusolver(nullptr);
-  if (cs && handle) cs->Destroy(handle);
-}
-
 // CHOLESKY, step 1 (solver/linearizor_sc.cpp:121-128, sc/linearization_sc.hpp:236-245): the reference
-// factorises the sparse reduced camera system with Eigen::SimplicialLLT; here S is assembled densely
-// (12C x 12C, FP64) and factorised by cuSOLVER's potrf -- the solution of S x = -b is unique, so the
-// ordering / sparsity handling does not change the result beyond rounding.
+// factorises the sparse reduced camera system with Eigen::SimplicialLLT; here S is assembled densely without
+// atomics and factorised by the hand-written blocked LL^T of kernels_chol.cu (FP64 tensor-core tile updates).
+// The solution of S x = -b is unique, so ordering / blocking do not change the result beyond rounding.
 int Engine::solve_cholesky(double lambda) {
-  const long long n = 12LL * C_;
-  if (n * n * 8 > (96LL << 30)) return fail(POVAR_ERR_UNSUPPORTED, "CHOLESKY: dense reduced system would exceed 96 GB");
-  std::string cerr;
-  CusolverApi* cs = load_cusolver(&cerr);
-  if (!cs) return fail(POVAR_ERR_UNSUPPORTED, cerr);
+  const int n = 12 * C_;
+  const int n_pad = chol_padded(n);
+  if (static_cast<long long>(n_pad) * n_pad * 8 > (96LL << 30)) {
+    return fail(POVAR_ERR_UNSUPPORTED, "CHOLESKY: dense reduced system would exceed 96 GB");
+  }
   PV_CUDA(cudaEventRecord(ev_[0], stream_));
   int rc = prepare_reduced_system(false, lambda, 0.0);
   if (rc != POVAR_OK) return rc;
-  if (!d_.dense_S) PV_ALLOC(d_.dense_S, static_cast<size_t>(n) * n);
-  PV_CUDA(cudaMemsetAsync(d_.dense_S, 0, sizeof(double) * static_cast<size_t>(n) * n, stream_));
-  launch_dense_schur(d_, mp_, d_.dense_S, lc());
+  if (!d_.dense_S) {
+    PV_ALLOC(d_.dense_S, static_cast<size_t>(n_pad) * n_pad);
+    PV_ALLOC(chol_linv_, static_cast<size_t>(n_pad) * 64);
+    PV_ALLOC(chol_rhs_, static_cast<size_t>(n_pad));
+  }
+  PV_CUDA(cudaMemsetAsync(d_.dense_S, 0, sizeof(double) * static_cast<size_t>(n_pad) * n_pad, stream_));
+  launch_schur_lower(d_, mp_, d_.dense_S, n_pad, lc());
   PV_CUDA(cudaEventRecord(ev_[1], stream_));
-  launch_axpby(d_, static_cast<int>(n), -1.0, d_.b, 0.0, nullptr, d_.vec_acc, lc());
-  if (!cusolver_) {
-    if (cs->Create(&cusolver_) != 0) return fail(POVAR_ERR_CUDA, "cusolverDnCreate failed");
-    cs->SetStream(cusolver_, stream_);
-  }
-  int lwork = 0;
-  const int kLower = 0;   // CUBLAS_FILL_MODE_LOWER
-  if (cs->PotrfBuf(cusolver_, kLower, static_cast<int>(n), d_.dense_S, static_cast<int>(n), &lwork) != 0) {
-    return fail(POVAR_ERR_CUDA, "cusolverDnDpotrf_bufferSize failed");
-  }
-  if (lwork > chol_work_size_) {
-    PV_ALLOC(chol_work_, static_cast<size_t>(lwork));
-    chol_work_size_ = lwork;
-  }
+  PV_CUDA(cudaMemsetAsync(chol_rhs_, 0, sizeof(double) * static_cast<size_t>(n_pad), stream_));
+  launch_axpby(d_, n, -1.0, d_.b, 0.0, nullptr, chol_rhs_, lc());
   int* info = d_.flags + 2;
-  if (cs->Potrf(cusolver_, kLower, static_cast<int>(n), d_.dense_S, static_cast<int>(n), chol_work_, lwork, info) != 0) {
-    return fail(POVAR_ERR_CUDA, "cusolverDnDpotrf failed");
-  }
-  if (cs->Potrs(cusolver_, kLower, static_cast<int>(n), 1, d_.dense_S, static_cast<int>(n), d_.vec_acc,
-                static_cast<int>(n), d_.flags + 3) != 0) {
-    return fail(POVAR_ERR_CUDA, "cusolverDnDpotrs failed");
-  }
-  launches_ += 2;
+  launch_cholesky_factor(d_.dense_S, n_pad, chol_linv_, info, lc());
+  launch_cholesky_solve(d_.dense_S, n_pad, chol_linv_, chol_rhs_, info, lc());
+  PV_CUDA(cudaMemcpyAsync(d_.vec_acc, chol_rhs_, sizeof(double) * static_cast<size_t>(n), cudaMemcpyDeviceToDevice, stream_));
   int hinfo = 0;
   PV_CUDA(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, stream_));
   SeriesCtl h{};
@@ -1295,20 +1274,60 @@ int Engine::solve_cholesky(double lambda) {
     PV_CUDA(cudaMemcpyAsync(d_.ctl, &h, sizeof(h), cudaMemcpyHostToDevice, stream_));
     PV_CUDA(cudaStreamSynchronize(stream_));
   } else {
-    launch_finite_check(d_, static_cast<int>(n), d_.vec_acc, lc());
+    launch_finite_check(d_, n, d_.vec_acc, lc());
   }
   PV_CUDA(cudaEventRecord(ev_[2], stream_));
   PV_CUDA(cudaGetLastError());
   return POVAR_OK;
 }
 
-int Engine::apply(bool joint, double alpha, double* l_diff) {
-  PV_CUDA(cudaSetDevice(device_));
+// the factorisation and substitution kernels on a caller-supplied symmetric matrix (tests)
+int debug_cholesky(int n, const double* A, const double* b, double* x, int* info_out) {
+  if (n <= 0 || !A || !b || !x) return POVAR_ERR_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return POVAR_ERR_NO_DEVICE;
+  const int n_pad = chol_padded(n);
+  double *S = nullptr, *linv = nullptr, *r = nullptr;
+  int* info = nullptr;
+  int rc = POVAR_OK;
+  auto ok = [&](cudaError_t e) {
+    if (e != cudaSuccess) rc = POVAR_ERR_CUDA;
+    return e == cudaSuccess;
+  };
+  if (ok(cudaSetDevice(0)) && ok(cudaMalloc(&S, sizeof(double) * static_cast<size_t>(n_pad) * n_pad)) &&
+      ok(cudaMalloc(&linv, sizeof(double) * static_cast<size_t>(n_pad) * 64)) &&
+      ok(cudaMalloc(&r, sizeof(double) * static_cast<size_t>(n_pad))) && ok(cudaMalloc(&info, sizeof(int))) &&
+      ok(cudaMemset(S, 0, sizeof(double) * static_cast<size_t>(n_pad) * n_pad)) &&
+      ok(cudaMemset(r, 0, sizeof(double) * static_cast<size_t>(n_pad))) &&
+      ok(cudaMemcpy2D(S, sizeof(double) * n_pad, A, sizeof(double) * n, sizeof(double) * n, n, cudaMemcpyHostToDevice)) &&
+      ok(cudaMemcpy(r, b, sizeof(double) * n, cudaMemcpyHostToDevice))) {
+    std::vector<double> ones(static_cast<size_t>(n_pad - n), 1.0);
+    if (n_pad > n) {
+      ok(cudaMemcpy2D(S + static_cast<size_t>(n) * n_pad + n, sizeof(double) * (n_pad + 1), ones.data(), sizeof(double),
+                      sizeof(double), n_pad - n, cudaMemcpyHostToDevice));
+    }
+    LaunchCfg lc{};
+    launch_cholesky_factor(S, n_pad, linv, info, lc);
+    launch_cholesky_solve(S, n_pad, linv, r, info, lc);
+    int hinfo = 0;
+    ok(cudaMemcpy(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost));
+    ok(cudaMemcpy(x, r, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    ok(cudaGetLastError());
+    if (info_out) *info_out = hinfo;
+  }
+  cudaFree(S);
+  cudaFree(linv);
+  cudaFree(r);
+  cudaFree(info);
+  return rc;
+}
+
+// back-substitution and camera update + (sharded) the sum of l_diff over the ranks: trial_out[8] on the device
+int Engine::enqueue_apply(bool joint, double alpha) {
   if (static_cast<int>(joint) != joint_lin_ || !have_solve_) {
     return fail(POVAR_ERR_INVALID, "apply called without a matching linearize + solve");
   }
   set_model(joint, joint ? opt_.alpha : alpha);
-  PV_CUDA(cudaEventRecord(ev_[0], stream_));
   const size_t C12 = static_cast<size_t>(C_) * 12;
   if (joint) {
     // apply_joint (linearizor_power_varproj.cpp:276-308): landmarks first, then P += s o (Pi inc)
@@ -1329,17 +1348,63 @@ int Engine::apply(bool joint, double alpha, double* l_diff) {
     tmp.P_bak = P_prev_;
     launch_backsub_varpro(tmp, mp_, d_.vec_acc, lc());
   }
-  PV_CUDA(cudaGetLastError());
+  return allreduce(d_.trial_out + 8, 1);
+}
+
+int Engine::apply(bool joint, double alpha, double* l_diff) {
+  PV_CUDA(cudaSetDevice(device_));
+  PV_CUDA(cudaEventRecord(ev_[0], stream_));
   {
-    const int rc = allreduce(d_.scalar_out, 1);
+    const int rc = enqueue_apply(joint, alpha);
     if (rc != POVAR_OK) return rc;
   }
-  double v = 0.0;
-  PV_CUDA(cudaMemcpyAsync(&v, d_.scalar_out, sizeof(double), cudaMemcpyDeviceToHost, stream_));
+  PV_CUDA(cudaGetLastError());
+  double* v = host_out_ + 8;
+  PV_CUDA(cudaMemcpyAsync(v + 8, d_.trial_out + 8, sizeof(double), cudaMemcpyDeviceToHost, stream_));
   PV_CUDA(cudaEventRecord(ev_[1], stream_));
   PV_CUDA(cudaStreamSynchronize(stream_));
   times_.back_substitution += elapsed(ev_[0], ev_[1]);
-  if (l_diff) *l_diff = v;
+  if (l_diff) *l_diff = v[8];
+  return POVAR_OK;
+}
+
+int Engine::trial(bool joint, double alpha, double lambda, int32_t* iterations, double* l_diff,
+                  povar_residual_info* ri) {
+  PV_CUDA(cudaSetDevice(device_));
+  int rc = enqueue_solve(joint, lambda);   // records ev_[0] (start), ev_[1] (prepared), ev_[2] (solved)
+  if (rc != POVAR_OK) return rc;
+  rc = backup(joint ? POVAR_STATE_JOINT : POVAR_STATE_POSE);
+  if (rc != POVAR_OK) return rc;
+  rc = enqueue_apply(joint, alpha);
+  if (rc != POVAR_OK) return rc;
+  if (joint) {   // solver/bal_bundle_adjustment.cpp:700-705
+    launch_normalize_cams(d_, lc());
+    launch_normalize_joint(d_, lc());
+  }
+  PV_CUDA(cudaEventRecord(ev_[3], stream_));
+  rc = enqueue_cost(joint, alpha);
+  if (rc != POVAR_OK) return rc;
+  PV_CUDA(cudaGetLastError());
+  static_assert(sizeof(SeriesCtl) <= 64, "SeriesCtl shares the pinned read-back buffer");
+  SeriesCtl* hctl = reinterpret_cast<SeriesCtl*>(host_out_);
+  double* v = host_out_ + 8;
+  PV_CUDA(cudaMemcpyAsync(hctl, d_.ctl, sizeof(SeriesCtl), cudaMemcpyDeviceToHost, stream_));
+  PV_CUDA(cudaMemcpyAsync(v, d_.trial_out, 16 * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+  PV_CUDA(cudaEventRecord(ev_[4], stream_));
+  PV_CUDA(cudaStreamSynchronize(stream_));
+  times_.prepare += elapsed(ev_[0], ev_[1]);
+  times_.reduced_solve += elapsed(ev_[1], ev_[2]);
+  times_.back_substitution += elapsed(ev_[2], ev_[3]);
+  times_.residual += elapsed(ev_[3], ev_[4]);
+  if (lin_check_pending_) {
+    lin_check_pending_ = false;
+    if (v[9] > 0) return fail(POVAR_NUM_LINEARIZATION, "did not expect numerical failure during linearization");
+  }
+  if (iterations) *iterations = hctl->iterations;
+  if (l_diff) *l_diff = v[8];
+  if (ri) decode_cost(v, ri);
+  if (hctl->peer_timeout) return fail(POVAR_ERR_NCCL, "peer exchange of the camera sums timed out (a rank is gone?)");
+  if (hctl->nonfinite) return POVAR_NUM_NONFINITE_INC;
   return POVAR_OK;
 }
 

@@ -24,9 +24,14 @@ class Engine {
 
   int init_varproj(double alpha);
   int cost(bool joint, double alpha, povar_residual_info* out);
-  int linearize(bool joint, double alpha);
+  int linearize(bool joint, double alpha, bool defer_check = false);
   int solve(bool joint, double lambda, double* inc, int32_t* iterations);
   int apply(bool joint, double alpha, double* l_diff);
+  // One LM trial with ONE host synchronisation: solve, backup, apply, (step 2: normalise,) cost -- what the
+  // caller of the Linearizor does between two accept/reject decisions (solver/bal_bundle_adjustment.cpp:346-420,
+  // 655-720).  Returns the solve's status; after POVAR_NUM_NONFINITE_INC the state is garbage until restore().
+  // A linearize(.., defer_check = true) before it has its failure flag checked here.
+  int trial(bool joint, double alpha, double lambda, int32_t* iterations, double* l_diff, povar_residual_info* ri);
   int backup(int which);
   int restore(int which);
   int to_homogeneous();
@@ -67,6 +72,11 @@ class Engine {
   int schur_product(bool joint, const double* p, double* out);
   int e0_product(bool joint, const double* y, bool in_series);
   int finish_solve(bool joint, double* inc, int32_t* iterations);
+  int enqueue_solve(bool joint, double lambda);
+  int enqueue_cost(bool joint, double alpha);
+  int enqueue_apply(bool joint, double alpha);
+  int enqueue_series(bool joint);
+  static void decode_cost(const double* v, povar_residual_info* out);
   LaunchCfg lc() { return LaunchCfg{stream_, &launches_}; }
   double elapsed(cudaEvent_t a, cudaEvent_t b);
 
@@ -75,7 +85,7 @@ class Engine {
   ModelParams mp_{};
   std::vector<void*> allocs_;
   cudaStream_t stream_ = nullptr;
-  cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   long long launches_ = 0;
   std::string err_;
   PhaseTimes times_;
@@ -85,9 +95,14 @@ class Engine {
   double lambda_ = 0.0;           // damping of the last solve (landmark damping of apply)
   int dim_ = 12;
   double* P_prev_ = nullptr;      // cameras of the linearisation point during a VarPro apply
-  void* cusolver_ = nullptr;      // cusolverDnHandle_t (CHOLESKY only)
-  double* chol_work_ = nullptr;
-  int chol_work_size_ = 0;
+  bool lin_check_pending_ = false;  // linearize(defer_check): the flag is read with the next trial
+  double* host_out_ = nullptr;    // pinned: [SeriesCtl (64 B) | trial_out (16 doubles)]
+  // the 3 x power_sc_iterations launches of a power series as one CUDA graph per model (pOSE / joint)
+  void* series_graph_[2] = {nullptr, nullptr};   // cudaGraphExec_t
+  long long series_graph_launches_[2] = {0, 0};
+  int series_calls_[2] = {0, 0};
+  double* chol_linv_ = nullptr;   // CHOLESKY: inverses of the factor's diagonal tiles [n_pad / 64][64][64]
+  double* chol_rhs_ = nullptr;    // CHOLESKY: padded right-hand side / solution [n_pad]
   // distributed
   int rank_ = 0, world_ = 1, device_ = 0;
   void* nccl_comm_ = nullptr;

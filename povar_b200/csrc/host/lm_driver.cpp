@@ -8,6 +8,11 @@
 // including its quirks: lambda update uses rho = f_diff / l_diff in both steps,
 // iteration counters count trials, the function-tolerance test compares with the previous LIST
 // entry (which may be a rejected trial), step 2 restarts lambda from the initial radius.
+//
+// What is NOT repeated: the reference evaluates the cost again at the top of the iteration that follows an
+// accepted step (:306-312, :608-612) -- on the state it has just evaluated.  The cost kernels have fixed
+// reduction trees, so that second evaluation returns the same bits; the accepted trial's ResidualInfo is
+// reused instead.  Every trial costs one host synchronisation (Engine::trial).
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -22,6 +27,12 @@ namespace povar {
 const PhaseTimes& handle_times(povar_handle* h);
 void handle_reset_times(povar_handle* h);
 int handle_rank(povar_handle* h);
+// the library's own driver takes two shortcuts behind the per-method ABI (engine.h): a linearisation whose
+// failure flag is read with the next trial, and a whole trial (solve, backup, apply, normalise, cost) with one
+// host synchronisation
+int handle_linearize_deferred(povar_handle* h, bool joint, double alpha);
+int handle_trial(povar_handle* h, bool joint, double alpha, double lambda, int32_t* iterations, double* l_diff,
+                 povar_residual_info* ri);
 }  // namespace povar
 
 namespace {
@@ -125,6 +136,8 @@ StepResult run_step(povar_handle* h, const povar_options& opt, bool joint, Log& 
     return joint ? povar_cost_homogeneous(h, ri) : povar_cost_pose(h, opt.alpha, ri);
   };
 
+  povar_residual_info ri_accepted;   // cost of the state an accepted trial left behind
+  bool have_accepted = false;
   for (int it = 0; it <= max_iter && !terminated;) {
     Clock::time_point t_it = Clock::now();
     povar_residual_info ri;
@@ -133,8 +146,12 @@ StepResult run_step(povar_handle* h, const povar_options& opt, bool joint, Log& 
       if (res.rc != POVAR_OK) return res;
     }
     first = false;
-    res.rc = cost(&ri);
-    if (res.rc != POVAR_OK) return res;
+    if (have_accepted) {
+      ri = ri_accepted;   // the state is the one that trial evaluated
+    } else {
+      res.rc = cost(&ri);
+      if (res.rc != POVAR_OK) return res;
+    }
     if (verbose) {
       std::printf("Iteration %d, error: %.4e (mean res: %.2f, num: %lld), error valid: %.4e (num: %lld)\n",
                   it, ri.error_all, ri.num_obs_all > 0 ? ri.residual_sum_all / ri.num_obs_all : 0.0,
@@ -152,7 +169,7 @@ StepResult run_step(povar_handle* h, const povar_options& opt, bool joint, Log& 
       ++it;
       continue;
     }
-    res.rc = joint ? povar_linearize_homogeneous(h) : povar_linearize_pose(h, opt.alpha);
+    res.rc = povar::handle_linearize_deferred(h, joint, opt.alpha);
     if (res.rc != POVAR_OK) {
       res.message = povar_last_error(h);
       return res;
@@ -164,9 +181,11 @@ StepResult run_step(povar_handle* h, const povar_options& opt, bool joint, Log& 
         t_it = Clock::now();
       }
       int32_t lin_it = 0;
-      const int src = joint ? povar_solve_joint(h, lambda, nullptr, &lin_it)
-                            : povar_solve_pose(h, lambda, nullptr, &lin_it);
-      if (src < 0) {
+      double l_diff = 0.0;
+      povar_residual_info ri2;
+      // solve, backup, apply, (step 2) normalise, cost: :346-420 / :655-720, one synchronisation
+      const int src = povar::handle_trial(h, joint, opt.alpha, lambda, &lin_it, &l_diff, &ri2);
+      if (src < 0 || src == POVAR_NUM_LINEARIZATION) {
         res.rc = src;
         res.message = povar_last_error(h);
         return res;
@@ -176,6 +195,9 @@ StepResult run_step(povar_handle* h, const povar_options& opt, bool joint, Log& 
         *power_time += povar::handle_times(h).reduced_solve;
       }
       if (src == POVAR_NUM_NONFINITE_INC) {   // :362-401
+        // the reference does not apply such an increment; here it was applied to the copy the backup protects
+        res.rc = povar_restore(h, joint ? POVAR_STATE_JOINT : POVAR_STATE_POSE);
+        if (res.rc != POVAR_OK) return res;
         if (verbose) {
           std::printf("\t[Invalid] Numeric issues when computing increment (contains NaNs), lambda: %.1e, cg_iter: %d\n",
                       lambda, lin_it);
@@ -192,21 +214,6 @@ StepResult run_step(povar_handle* h, const povar_options& opt, bool joint, Log& 
         }
         continue;
       }
-      res.rc = povar_backup(h, joint ? POVAR_STATE_JOINT : POVAR_STATE_POSE);
-      if (res.rc != POVAR_OK) return res;
-      double l_diff = 0.0;
-      res.rc = joint ? povar_apply_joint(h, &l_diff) : povar_apply_pose(h, opt.alpha, &l_diff);
-      if (res.rc != POVAR_OK) {
-        res.message = povar_last_error(h);
-        return res;
-      }
-      if (joint) {   // :700-705
-        res.rc = povar_normalize_joint(h);
-        if (res.rc != POVAR_OK) return res;
-      }
-      povar_residual_info ri2;
-      res.rc = cost(&ri2);
-      if (res.rc != POVAR_OK) return res;
 
       bool valid = false, successful = false;
       double rho = 0.0;
@@ -251,6 +258,8 @@ StepResult run_step(povar_handle* h, const povar_options& opt, bool joint, Log& 
         log.push(h, step, it, true, true, ri2.error_all, &ri2, rho, 1.0 / lambda, lin_it,
                  seconds_since(t_it), seconds_since(t_total));
         ++it;
+        ri_accepted = ri2;
+        have_accepted = true;
         // function_tolerance_reached (:179-205): cost_change against the previous list entry
         double cost_now, change;
         if (opt.optimized_cost == POVAR_COST_ERROR) {
@@ -279,7 +288,6 @@ StepResult run_step(povar_handle* h, const povar_options& opt, bool joint, Log& 
       vee *= opt.vee_factor;
       log.push(h, step, it, valid, false, ri2.error_all, &ri2, 0.0, 1.0 / lambda, lin_it,
                seconds_since(t_it), seconds_since(t_total));
-      // Log::push took ri2 as "last logged" only for successful trials; restore the book-keeping
       res.rc = povar_restore(h, joint ? POVAR_STATE_JOINT : POVAR_STATE_POSE);
       if (res.rc != POVAR_OK) return res;
       ++it;

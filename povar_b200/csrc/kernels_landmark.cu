@@ -190,7 +190,7 @@ k_cost(int nnz, const int* __restrict__ obs_cam, const int* __restrict__ obs_lm,
 }
 
 __global__ void __launch_bounds__(kBlock)
-k_cost_final(int nblocks, long long nnz, const double* __restrict__ part, CostAccum* out) {
+k_cost_final(int nblocks, long long nnz, const double* __restrict__ part, CostAccum* out, double* __restrict__ outd) {
   __shared__ double smem[6 * (kBlock / 32)];
   double acc[6] = {0, 0, 0, 0, 0, 0};
   for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {
@@ -206,7 +206,20 @@ k_cost_final(int nblocks, long long nnz, const double* __restrict__ part, CostAc
     out->n_all = nnz;
     out->n_valid = static_cast<long long>(acc[4] + 0.5);
     out->nonfinite = acc[5] > 0.0 ? 1 : 0;
+    // the same as doubles: what a sharded run sums over the ranks in place
+    outd[0] = acc[0];
+    outd[1] = acc[1];
+    outd[2] = acc[2];
+    outd[3] = acc[3];
+    outd[4] = static_cast<double>(nnz);
+    outd[5] = static_cast<double>(static_cast<long long>(acc[4] + 0.5));
+    outd[6] = acc[5] > 0.0 ? 1.0 : 0.0;
+    outd[7] = 0.0;
   }
+}
+
+__global__ void k_flag_to_double(const int* __restrict__ flags, double* __restrict__ out) {
+  out[0] = flags[0] != 0 ? 1.0 : 0.0;
 }
 
 __global__ void __launch_bounds__(kBlock)
@@ -820,6 +833,11 @@ void launch_init_varproj(const DeviceState& d, const ModelParams& mp, const Laun
   count(lc);
 }
 
+void launch_flag_to_double(const DeviceState& d, const LaunchCfg& lc) {
+  k_flag_to_double<<<1, 1, 0, lc.stream>>>(d.flags, d.trial_out + 9);
+  count(lc);
+}
+
 void launch_cost(const DeviceState& d, const ModelParams& mp, bool joint, const LaunchCfg& lc) {
   const int blocks = cost_blocks(d);
   const Robust rb = {mp.robust_norm, mp.huber};
@@ -830,7 +848,7 @@ void launch_cost(const DeviceState& d, const ModelParams& mp, bool joint, const 
     k_cost<false><<<blocks, kBlock, 0, lc.stream>>>(d.ix.nnz, d.ix.obs_cam, d.ix.obs_lm, d.ix.obs_uv, d.P,
                                                     d.X, mp.c1, mp.c2, rb, d.cost_part);
   }
-  k_cost_final<<<1, kBlock, 0, lc.stream>>>(blocks, d.ix.nnz, d.cost_part, d.cost_out);
+  k_cost_final<<<1, kBlock, 0, lc.stream>>>(blocks, d.ix.nnz, d.cost_part, d.cost_out, d.trial_out);
   count(lc, 2);
 }
 
@@ -871,7 +889,7 @@ void launch_backsub_varpro(const DeviceState& d, const ModelParams& mp, const do
   const int blocks = tile_grid(d);
   k_backsub_varpro<<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.P_bak, d.X, inc, mp.c1, mp.c2, rb,
                                                      d.lm_scale, d.scalar_part);
-  k_scalar_final<<<1, kBlock, 0, lc.stream>>>(blocks, d.scalar_part, d.scalar_out);
+  k_scalar_final<<<1, kBlock, 0, lc.stream>>>(blocks, d.scalar_part, d.trial_out + 8);
   count(lc, 2);
 }
 
@@ -881,7 +899,7 @@ void launch_backsub_poba(const DeviceState& d, const ModelParams& mp, const doub
   const int blocks = tile_grid(d);
   k_backsub_poba<<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.X, y, mp.c1, mp.c2, rb, d.lm_scale,
                                                    d.hll_inv, d.scalar_part);
-  k_scalar_final<<<1, kBlock, 0, lc.stream>>>(blocks, d.scalar_part, d.scalar_out);
+  k_scalar_final<<<1, kBlock, 0, lc.stream>>>(blocks, d.scalar_part, d.trial_out + 8);
   count(lc, 2);
 }
 
@@ -891,7 +909,7 @@ void launch_backsub_joint(const DeviceState& d, const ModelParams& mp, const dou
   const int blocks = tile_grid(d);
   k_backsub_joint<<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.X, y, rb, d.lm_scale, d.hll_inv,
                                                     d.scalar_part);
-  k_scalar_final<<<1, kBlock, 0, lc.stream>>>(blocks, d.scalar_part, d.scalar_out);
+  k_scalar_final<<<1, kBlock, 0, lc.stream>>>(blocks, d.scalar_part, d.trial_out + 8);
   count(lc, 2);
 }
 

@@ -142,10 +142,14 @@ struct DeviceState {
   double* cost_part = nullptr;   // [blocks * 8]
   CostAccum* cost_out = nullptr;
   double* scalar_part = nullptr; // [blocks] l_diff partials
-  double* scalar_out = nullptr;  // [8]
+  double* scalar_out = nullptr;  // [8]  PCG dot products
+  // what one LM trial reports, as doubles so that shards can be summed in place (Engine::allreduce):
+  // [0..7] cost {err_all, rsum_all, err_valid, rsum_valid, n_all, n_valid, nonfinite, -}, [8] l_diff,
+  // [9] numerical-failure flag of the linearisation
+  double* trial_out = nullptr;   // [16]
   int* flags = nullptr;          // [4] numerical-failure flags
   SeriesCtl* ctl = nullptr;
-  double* dense_S = nullptr;     // CHOLESKY: [12C x 12C]
+  double* dense_S = nullptr;     // CHOLESKY: [n_pad x n_pad], n_pad = 12 C rounded up to 64
 };
 
 // streaming multiprocessors of the current device (grids are sized in multiples of it)
@@ -183,6 +187,8 @@ cudaError_t build_device_index(const DeviceIndex& ix, int* iota, int* keys_out, 
 // ---- landmark-major kernels (kernels_landmark.cu) ----
 void launch_init_varproj(const DeviceState& d, const ModelParams& mp, const LaunchCfg& lc);
 void launch_cost(const DeviceState& d, const ModelParams& mp, bool joint, const LaunchCfg& lc);
+// trial_out[9] = flags[0] as a double
+void launch_flag_to_double(const DeviceState& d, const LaunchCfg& lc);
 void launch_lin_landmark(const DeviceState& d, const ModelParams& mp, bool joint, bool scale_jl,
                          const LaunchCfg& lc);
 void launch_prep_landmark(const DeviceState& d, bool joint, double lambda_lm, const LaunchCfg& lc);
@@ -243,8 +249,13 @@ void launch_axpby(const DeviceState& d, int n, double a, const double* x, double
                   double* out, const LaunchCfg& lc);
 // scalar_out[slot] = x . y (deterministic two-stage reduction); slot in [0, 8)
 void launch_dot(const DeviceState& d, int n, const double* x, const double* y, int slot, const LaunchCfg& lc);
-// dense reduced camera system of step 1 (CHOLESKY): S = blockdiag(Bmat) - sum_l Hpl Hll^-1 Hlp
-void launch_dense_schur(const DeviceState& d, const ModelParams& mp, double* S, const LaunchCfg& lc);
+// CHOLESKY (kernels_chol.cu): dense reduced camera system of step 1, S = blockdiag(Bmat) - sum_l Hpl Hll^-1 Hlp,
+// lower block triangle, fixed summation order; blocked LL^T on 64x64 tiles; substitution
+int chol_padded(int n);
+void launch_schur_lower(const DeviceState& d, const ModelParams& mp, double* S, int n_pad, const LaunchCfg& lc);
+void launch_cholesky_factor(double* S, int n_pad, double* linv, int* info, const LaunchCfg& lc);
+void launch_cholesky_solve(const double* S, int n_pad, const double* linv, double* r, const int* info,
+                           const LaunchCfg& lc);
 void launch_finite_check(const DeviceState& d, int n, const double* x, const LaunchCfg& lc);
 
 }  // namespace povar

@@ -106,6 +106,59 @@ def test_device_index_matches_the_reference_structures(key, tmp_path):
     s.close()
 
 
+@pytest.mark.parametrize("n", [60, 64, 300, 1024, 12 * 257])
+def test_own_cholesky_solves_like_numpy(n):
+    """The direct solver of CHOLESKY (blocked LL^T on 64x64 tiles, FP64 tensor-core updates, substitution with
+    the inverted diagonal factors; kernels_chol.cu) on random symmetric positive definite systems of sizes that
+    do and do not fill whole tiles -- the reference uses Eigen::SimplicialLLT here (sc/linearization_sc.hpp:236-245)."""
+    rng = np.random.default_rng(n)
+    G = rng.normal(size=(n, n + 8))
+    A = G @ G.T + 0.5 * np.eye(n)
+    b = rng.normal(size=n)
+    x, info = capi.cholesky_solve(A, b)
+    assert info == 0
+    ref = np.linalg.solve(A, b)
+    assert common.rel(x, ref) < 1e-9 * max(1.0, np.linalg.cond(A) / 1e6)
+    assert np.linalg.norm(A @ x - b) <= 1e-10 * np.linalg.norm(b) * np.sqrt(n)
+    # only the lower triangle is read
+    U = A.copy()
+    U[np.triu_indices(n, 1)] = 123.0
+    x2, _ = capi.cholesky_solve(U, b)
+    assert np.array_equal(x, x2)
+    # twice the same bits
+    assert np.array_equal(x, capi.cholesky_solve(A, b)[0])
+
+
+def test_own_cholesky_reports_an_indefinite_matrix():
+    n = 200
+    rng = np.random.default_rng(1)
+    G = rng.normal(size=(n, n))
+    A = G @ G.T + np.eye(n)
+    A[150, 150] = -1.0            # not positive definite: a pivot of the third tile goes negative
+    x, info = capi.cholesky_solve(A, np.ones(n))
+    assert info == 3
+    A[3, 3] = np.nan
+    assert capi.cholesky_solve(A, np.ones(n))[1] == 1
+
+
+def test_cholesky_solve_is_reproducible_and_solves_the_reduced_system():
+    """S assembled without atomics: two solves give the same bits; the increment satisfies (B - E0) inc = -b
+    up to the conditioning of S (checked with the matrix-free product)."""
+    hp = capi.HostProblem.read(common.golden_file("small"))
+    s = capi.Solver(hp, capi.default_options(alpha=0.1, solver_type_step_1=capi.CHOLESKY, verbosity_level=0))
+    s.initialize_varproj_lm_pOSE(0.1)
+    assert s.linearize_pOSE(0.1) == capi.OK
+    inc, its, rc = s.solve(1e-2)
+    inc2, _, _ = s.solve(1e-2)
+    assert rc == capi.OK and its == 0 and np.array_equal(inc, inc2)
+    C = hp.num_cams
+    b = s.debug_read("b").reshape(C, 12)
+    Bm = s.debug_read("b_mat").reshape(C, 12, 12)
+    res = np.einsum("cij,cj->ci", Bm, inc) - s.right_mul_e0(capi.STATE_POSE, inc) + b
+    assert np.linalg.norm(res) <= 1e-8 * np.linalg.norm(b)
+    s.close()
+
+
 def test_runs_are_bit_reproducible():
     a = _gpu_trace("small_povar")[1]
     b = _gpu_trace("small_povar")[1]
