@@ -711,6 +711,7 @@ int Engine::upload(const povar_problem_desc* desc) {
   PV_ALLOC(d_.trial_out, 16);
   PV_ALLOC(d_.flags, 4);
   PV_ALLOC(d_.ctl, 1);
+  PV_ALLOC(d_.cg, 1);
   PV_UP(d_.P, desc->cam_P, sizeof(double) * C12);
 #undef PV_UP
   lap("allocate + enqueue uploads");
@@ -871,10 +872,10 @@ int Engine::setup_peer_exchange() {
 
 const PeerExchange* Engine::exchange() const { return peer_ok_ ? &peer_->px : nullptr; }
 
-int Engine::allreduce(double* buf, size_t n) {
+int Engine::allreduce(double* buf, size_t n, bool skip_when_done) {
   if (world_ <= 1) return POVAR_OK;
   if (peer_ok_ && n <= peer_->px.stride && peer_small_) {
-    launch_peer_allreduce(d_, buf, n, peer_->px, lc());
+    launch_peer_allreduce(d_, buf, n, peer_->px, lc(), skip_when_done);
     return POVAR_OK;
   }
   if (!nccl_comm_) return fail(POVAR_ERR_NCCL, "reduction needs an NCCL communicator (host rendezvous handle)");
@@ -991,15 +992,16 @@ int Engine::linearize(bool joint, double alpha, bool defer_check) {
   return POVAR_OK;
 }
 
-// raw_c = sum over the observations of camera c of the camera half of E0 (or of b), all ranks
-int Engine::e0_product(bool joint, const double* y, bool in_series) {
-  (void)y;   // the passes gather y from the camera records (cam_rec), written by whoever made y
-  launch_e0_landmark_v2(d_, mp_, joint, in_series, lc());
-  launch_passB_e0_v2(d_, mp_, joint, in_series, lc());
-  // the term kernel adds the item partials itself (and, sharded, exchanges them over peer memory)
-  if (in_series && term_mode() != kTermRaw) return POVAR_OK;
-  launch_reduce_items(d_, d_.item_part, 12, d_.cam_raw, in_series, lc());
-  return allreduce(d_.cam_raw, static_cast<size_t>(C_) * 12);
+// raw_c = sum over the observations of camera c of the camera half of E0 (or of b), all ranks.
+// skip_when_done: the launches return at once when ctl->done is set (inside a power series or a CG solve).
+// fused_reduce: the caller's term kernel adds the item partials (and exchanges them) itself.
+int Engine::e0_product(bool joint, bool skip_when_done, bool fused_reduce) {
+  // the passes gather y from the camera records (cam_rec), written by whoever made y
+  launch_e0_landmark_v2(d_, mp_, joint, skip_when_done, lc());
+  launch_passB_e0_v2(d_, mp_, joint, skip_when_done, lc());
+  if (fused_reduce) return POVAR_OK;
+  launch_reduce_items(d_, d_.item_part, 12, d_.cam_raw, skip_when_done, lc());
+  return allreduce(d_.cam_raw, static_cast<size_t>(C_) * 12, skip_when_done);
 }
 
 int Engine::solve_power(bool joint, double lambda) {
@@ -1039,7 +1041,7 @@ int Engine::enqueue_series(bool joint) {
     launch_finish_b(d_, joint, lc());
     launch_series_start(d_, opt_.r_tolerance, m, lc());
     for (int i = 1; i <= m; ++i) {
-      const int rc = e0_product(joint, d_.vec_y, true);
+      const int rc = e0_product(joint, true, term_mode() != kTermRaw);
       if (rc != POVAR_OK) return rc;
       launch_series_term(d_, joint, i, opt_.eta, opt_.r_tolerance, term_mode(), exchange(), lc());
     }
@@ -1126,17 +1128,11 @@ int Engine::prepare_reduced_system(bool joint, double lambda, double lambda_lm) 
   return POVAR_OK;
 }
 
-int Engine::read_scalars(double* out, int n) {
-  PV_CUDA(cudaMemcpyAsync(out, d_.scalar_out, sizeof(double) * n, cudaMemcpyDeviceToHost, stream_));
-  PV_CUDA(cudaStreamSynchronize(stream_));
-  return POVAR_OK;
-}
-
 // out = S p = B p - E0 p   (the reduced camera system applied implicitly)
-int Engine::schur_product(bool joint, const double* p, double* out) {
+int Engine::schur_product(bool joint, const double* p, double* out, bool skip_when_done) {
   const int n = C_ * (joint ? 11 : 12);
   launch_make_y(d_, joint, p, d_.vec_y, lc());
-  const int rc = e0_product(joint, d_.vec_y, false);
+  const int rc = e0_product(joint, skip_when_done, false);
   if (rc != POVAR_OK) return rc;
   launch_e0_finish(d_, joint, d_.vec_x, lc());
   launch_block_matvec(d_, joint ? 11 : 12, d_.Bmat, p, out, lc());
@@ -1146,8 +1142,10 @@ int Engine::schur_product(bool joint, const double* p, double* out) {
 
 // ConjugateGradientsSolver::solve / solve_joint (cg/conjugate_gradient.hpp:114-489) with the block-Jacobi
 // preconditioner (cg/preconditioner.hpp:70-144), x0 = 0, r_tolerance = -1, then x = -x
-// (solver/linearizor_base.cpp:102-147).  Scalars (rho, p'q, Q) are reduced on the device with fixed trees
-// and read back; the control flow is the reference's, including its NaN behaviour.
+// (solver/linearizor_base.cpp:102-147).  The scalars (rho, beta, alpha, Q) and every termination test of the
+// reference's loop -- its NaN behaviour included -- live on the device (k_cg_scalar): the host enqueues
+// iterations a few at a time and reads the control block once per batch; after termination the remaining
+// launches of a batch return at once.
 int Engine::solve_pcg(bool joint, double lambda) {
   const int D = joint ? 11 : 12;
   const int n = C_ * D;
@@ -1165,69 +1163,41 @@ int Engine::solve_pcg(bool joint, double lambda) {
 
   const double* b = d_.b;
   double *x = d_.cg_x, *r = d_.cg_r, *p = d_.cg_p, *z = d_.cg_z, *q = d_.cg_q, *tmp = d_.vec_tmp;
-  int iterations = 0;
-  double s[4];
+  const int min_it = opt_.min_linear_solver_iterations, max_it = opt_.max_linear_solver_iterations;
   PV_CUDA(cudaMemsetAsync(x, 0, bytes, stream_));
-  launch_dot(d_, n, b, b, 0, lc());
-  rc = read_scalars(s, 1);
-  if (rc != POVAR_OK) return rc;
-  const double norm_b = std::sqrt(s[0]);
-  if (norm_b != 0.0) {
-    const double tol_r = opt_.r_tolerance < 0 ? -1.0 * norm_b : -1.0 * norm_b;   // pso.r_tolerance = -1
-    PV_CUDA(cudaMemcpyAsync(r, b, bytes, cudaMemcpyDeviceToDevice, stream_));   // r = b - S*0
-    (void)tol_r;
-    double rho = 1.0, q0 = 0.0;   // q0 = -x.(b + r) = 0
-    const int min_it = opt_.min_linear_solver_iterations, max_it = opt_.max_linear_solver_iterations;
-    for (iterations = 1;; ++iterations) {
-      launch_block_matvec(d_, D, d_.Mprec, r, z, lc());
-      const double last_rho = rho;
-      launch_dot(d_, n, r, z, 0, lc());
-      rc = read_scalars(s, 1);
+  PV_CUDA(cudaMemsetAsync(p, 0, bytes, stream_));
+  PV_CUDA(cudaMemcpyAsync(r, b, bytes, cudaMemcpyDeviceToDevice, stream_));   // r = b - S*0
+  launch_dot_partials(d_, n, b, b, lc());
+  launch_cg_scalar(d_, CG_BEGIN, 0, opt_.eta, min_it, max_it, lc());          // |b| = 0: done at once
+  SeriesCtl* hctl = reinterpret_cast<SeriesCtl*>(host_out_);
+  constexpr int kBatch = 4;
+  for (int it = 1; it <= max_it;) {
+    for (int k = 0; k < kBatch && it <= max_it; ++k, ++it) {
+      launch_block_matvec(d_, D, d_.Mprec, r, z, lc());                       // z = M^-1 r
+      launch_dot_partials(d_, n, r, z, lc());
+      launch_cg_scalar(d_, CG_RHO, it, opt_.eta, min_it, max_it, lc());
+      launch_cg_update(d_, CG_UPDATE_P, n, it, z, p, lc());                   // p = z + beta p
+      rc = schur_product(joint, p, q, true);                                  // q = S p
       if (rc != POVAR_OK) return rc;
-      rho = s[0];
-      if (rho == 0.0 || std::isinf(rho)) break;               // LINEAR_SOLVER_FAILURE
-      if (iterations == 1) {
-        PV_CUDA(cudaMemcpyAsync(p, z, bytes, cudaMemcpyDeviceToDevice, stream_));
-      } else {
-        const double beta = rho / last_rho;
-        if (beta == 0.0 || std::isinf(beta)) break;
-        launch_axpby(d_, n, 1.0, z, beta, p, p, lc());
-      }
-      rc = schur_product(joint, p, q);
-      if (rc != POVAR_OK) return rc;
-      launch_dot(d_, n, p, q, 0, lc());
-      rc = read_scalars(s, 1);
-      if (rc != POVAR_OK) return rc;
-      const double pq = s[0];
-      if (pq <= 0 || std::isinf(pq)) break;                   // "Matrix is indefinite"
-      const double alpha = rho / pq;
-      if (std::isinf(alpha)) break;
-      launch_axpby(d_, n, 1.0, x, alpha, p, x, lc());
-      if (iterations % 10 == 0) {                             // residual_reset_period
-        rc = schur_product(joint, x, tmp);
+      launch_dot_partials(d_, n, p, q, lc());
+      launch_cg_scalar(d_, CG_PQ, it, opt_.eta, min_it, max_it, lc());
+      launch_cg_update(d_, CG_UPDATE_X, n, it, p, x, lc());                   // x += alpha p
+      if (it % 10 == 0) {                                                     // residual_reset_period
+        rc = schur_product(joint, x, tmp, true);
         if (rc != POVAR_OK) return rc;
-        launch_axpby(d_, n, 1.0, b, -1.0, tmp, r, lc());
+        launch_axpby(d_, n, 1.0, b, -1.0, tmp, r, lc());                      // r = b - S x
       } else {
-        launch_axpby(d_, n, 1.0, r, -alpha, q, r, lc());
+        launch_cg_update(d_, CG_UPDATE_R, n, it, q, r, lc());                 // r -= alpha q
       }
       launch_axpby(d_, n, 1.0, b, 1.0, r, tmp, lc());
-      launch_dot(d_, n, x, tmp, 0, lc());
-      rc = read_scalars(s, 1);
-      if (rc != POVAR_OK) return rc;
-      const double q1 = -1.0 * s[0];
-      const double zeta = iterations * (q1 - q0) / q1;
-      if (zeta < opt_.eta && iterations >= min_it) break;     // LINEAR_SOLVER_SUCCESS
-      q0 = q1;
-      // residual-based termination never fires: tol_r = r_tolerance * |b| < 0
-      if (iterations >= max_it) break;
+      launch_dot_partials(d_, n, x, tmp, lc());
+      launch_cg_scalar(d_, CG_ZETA, it, opt_.eta, min_it, max_it, lc());      // Q, zeta < eta, max iterations
     }
+    PV_CUDA(cudaMemcpyAsync(hctl, d_.ctl, sizeof(SeriesCtl), cudaMemcpyDeviceToHost, stream_));
+    PV_CUDA(cudaStreamSynchronize(stream_));
+    if (hctl->done) break;
   }
   launch_axpby(d_, n, -1.0, x, 0.0, nullptr, d_.vec_acc, lc());   // "negate the pose increment"
-  SeriesCtl h{};
-  h.done = 1;
-  h.iterations = iterations;
-  PV_CUDA(cudaMemcpyAsync(d_.ctl, &h, sizeof(h), cudaMemcpyHostToDevice, stream_));
-  PV_CUDA(cudaStreamSynchronize(stream_));   // h lives on this stack frame
   launch_finite_check(d_, n, d_.vec_acc, lc());
   PV_CUDA(cudaEventRecord(ev_[2], stream_));
   PV_CUDA(cudaGetLastError());
@@ -1540,7 +1510,7 @@ int Engine::right_mul_e0(bool joint, const double* x, double* out) {
   PV_CUDA(cudaMemcpyAsync(d_.vec_x, x, sizeof(double) * n, cudaMemcpyHostToDevice, stream_));
   launch_make_y(d_, joint, d_.vec_x, d_.vec_y, lc());
   {
-    const int rc = e0_product(joint, d_.vec_y, false);
+    const int rc = e0_product(joint, false, false);
     if (rc != POVAR_OK) return rc;
   }
   launch_e0_finish(d_, joint, d_.vec_x, lc());
@@ -1562,7 +1532,7 @@ int Engine::bench_power_terms(bool joint, int terms, double* seconds_per_term) {
   launch_series_start(d_, -1.0, terms, lc());
   PV_CUDA(cudaEventRecord(ev_[0], stream_));
   for (int i = 1; i <= terms; ++i) {
-    const int rc = e0_product(joint, d_.vec_y, true);
+    const int rc = e0_product(joint, true, term_mode() != kTermRaw);
     if (rc != POVAR_OK) return rc;
     launch_series_term(d_, joint, i, /*eta=*/-1.0, /*r_tolerance=*/-1.0, term_mode(), exchange(), lc());
   }

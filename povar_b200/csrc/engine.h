@@ -58,7 +58,7 @@ class Engine {
   int fail(int code, const std::string& what);
   int check(cudaError_t e, const char* what);
   int upload(const povar_problem_desc* desc);
-  int allreduce(double* buf, size_t n);
+  int allreduce(double* buf, size_t n, bool skip_when_done = false);
   int setup_peer_exchange();
   TermMode term_mode() const { return peer_ok_ ? kTermPeer : (world_ == 1 ? kTermFused : kTermRaw); }
   const PeerExchange* exchange() const;
@@ -68,9 +68,8 @@ class Engine {
   int solve_pcg(bool joint, double lambda);
   int solve_cholesky(double lambda);
   int prepare_reduced_system(bool joint, double lambda, double lambda_lm);
-  int read_scalars(double* out, int n);
-  int schur_product(bool joint, const double* p, double* out);
-  int e0_product(bool joint, const double* y, bool in_series);
+  int schur_product(bool joint, const double* p, double* out, bool skip_when_done);
+  int e0_product(bool joint, bool skip_when_done, bool fused_reduce);
   int finish_solve(bool joint, double* inc, int32_t* iterations);
   int enqueue_solve(bool joint, double lambda);
   int enqueue_cost(bool joint, double alpha);

@@ -1096,7 +1096,8 @@ void launch_series_start(const DeviceState& d, double r_tolerance, int max_terms
 // for the thread with the same index on the other ranks, which pushes before it polls, so the one-wave
 // grid-stride launch cannot deadlock.
 __global__ void __launch_bounds__(kBlock)
-k_peer_allreduce(double* __restrict__ buf, size_t n, PeerExchange px, SeriesCtl* ctl) {
+k_peer_allreduce(double* __restrict__ buf, size_t n, PeerExchange px, SeriesCtl* ctl, int skip_when_done) {
+  if (skip_when_done && ctl->done) return;   // every rank holds the same flag: nobody exchanges
   const unsigned int epoch = next_exchange_number(px);
   const int par = static_cast<int>(epoch & 1u);
   const size_t stride = static_cast<size_t>(px.stride);
@@ -1156,11 +1157,11 @@ k_peer_allreduce(double* __restrict__ buf, size_t n, PeerExchange px, SeriesCtl*
 }
 
 void launch_peer_allreduce(const DeviceState& d, double* buf, size_t n, const PeerExchange& px,
-                           const LaunchCfg& lc) {
+                           const LaunchCfg& lc, bool skip_when_done) {
   if (n == 0) return;
   size_t blocks = (n + kBlock - 1) / kBlock;
   if (blocks > static_cast<size_t>(sm_count()) * 2) blocks = static_cast<size_t>(sm_count()) * 2;   // one wave, always resident
-  k_peer_allreduce<<<static_cast<int>(blocks), kBlock, 0, lc.stream>>>(buf, n, px, d.ctl);
+  k_peer_allreduce<<<static_cast<int>(blocks), kBlock, 0, lc.stream>>>(buf, n, px, d.ctl, skip_when_done ? 1 : 0);
   count(lc);
 }
 

@@ -47,6 +47,84 @@ k_dot_final(int nblocks, const double* __restrict__ part, double* out) {
   if (threadIdx.x == 0) out[0] = acc[0];
 }
 
+// ---- conjugate gradients on the device (cg/conjugate_gradient.hpp:114-489): the scalar recurrences and every
+// termination test of the reference's loop, one thread, after the ordered sum of the dot-product partials
+__global__ void __launch_bounds__(kBlock)
+k_cg_scalar(int nblocks, const double* __restrict__ part, int stage, int it, double eta, int min_it, int max_it,
+            CgState* cg, SeriesCtl* ctl) {
+  if (stage != CG_BEGIN && ctl->done) return;
+  __shared__ double smem[kBlock / 32];
+  double acc[1] = {0.0};
+  for (int b = threadIdx.x; b < nblocks; b += blockDim.x) acc[0] += part[b];
+  block_reduce<1>(acc, smem);
+  if (threadIdx.x != 0) return;
+  const double v = acc[0];
+  auto stop = [&]() {
+    ctl->done = 1;
+    ctl->iterations = it;
+  };
+  if (stage == CG_BEGIN) {            // |b|; x0 = 0, r = b, Q0 = -x.(b + r) = 0
+    cg->norm_b = sqrt(v);
+    cg->rho = 1.0;
+    cg->last_rho = 1.0;
+    cg->alpha = 0.0;
+    cg->beta = 0.0;
+    cg->q0 = 0.0;
+    ctl->nonfinite = 0;
+    ctl->peer_timeout = 0;
+    ctl->iterations = 0;
+    ctl->done = cg->norm_b == 0.0 ? 1 : 0;
+  } else if (stage == CG_RHO) {       // rho = r.z; beta = rho / last_rho
+    cg->last_rho = cg->rho;
+    cg->rho = v;
+    if (v == 0.0 || isinf(v)) {       // LINEAR_SOLVER_FAILURE
+      stop();
+      return;
+    }
+    if (it == 1) {
+      cg->beta = 0.0;
+    } else {
+      const double beta = v / cg->last_rho;
+      cg->beta = beta;
+      if (beta == 0.0 || isinf(beta)) stop();
+    }
+  } else if (stage == CG_PQ) {        // alpha = rho / p.q
+    if (v <= 0 || isinf(v)) {         // "Matrix is indefinite"
+      stop();
+      return;
+    }
+    const double alpha = cg->rho / v;
+    cg->alpha = alpha;
+    if (isinf(alpha)) stop();
+  } else {                            // Q1 = -x.(b + r); zeta = it (Q1 - Q0) / Q1
+    const double q1 = -1.0 * v;
+    const double zeta = it * (q1 - cg->q0) / q1;
+    if (zeta < eta && it >= min_it) { // LINEAR_SOLVER_SUCCESS
+      stop();
+      return;
+    }
+    cg->q0 = q1;
+    // the residual-based test never fires: tol_r = r_tolerance * |b| < 0 (pso.r_tolerance = -1)
+    if (it >= max_it) stop();
+  }
+}
+
+// p = z (+ beta p);  x += alpha p;  r -= alpha q  -- with the device's scalars, nothing after termination
+__global__ void __launch_bounds__(kBlock)
+k_cg_update(int n, int what, int it, const double* __restrict__ src, double* __restrict__ dst,
+            const CgState* __restrict__ cg, const SeriesCtl* __restrict__ ctl) {
+  if (ctl->done) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (what == CG_UPDATE_P) {
+    dst[i] = it == 1 ? src[i] : 1.0 * src[i] + cg->beta * dst[i];
+  } else if (what == CG_UPDATE_X) {
+    dst[i] = 1.0 * dst[i] + cg->alpha * src[i];
+  } else {
+    dst[i] = 1.0 * dst[i] + (-cg->alpha) * src[i];
+  }
+}
+
 __global__ void __launch_bounds__(kBlock)
 k_finite_check(int n, const double* __restrict__ x, SeriesCtl* ctl) {
   bool bad = false;
@@ -73,6 +151,31 @@ void launch_dot(const DeviceState& d, int n, const double* x, const double* y, i
   k_dot_part<<<blocks, kBlock, 0, lc.stream>>>(n, x, y, d.scalar_part);
   k_dot_final<<<1, kBlock, 0, lc.stream>>>(blocks, d.scalar_part, d.scalar_out + slot);
   count(lc, 2);
+}
+
+void launch_dot_partials(const DeviceState& d, int n, const double* x, const double* y, const LaunchCfg& lc) {
+  int blocks = (n + kBlock - 1) / kBlock;
+  const int cap = scalar_blocks(d);
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  k_dot_part<<<blocks, kBlock, 0, lc.stream>>>(n, x, y, d.scalar_part);
+  count(lc);
+}
+
+void launch_cg_scalar(const DeviceState& d, CgStage stage, int it, double eta, int min_it, int max_it,
+                      const LaunchCfg& lc) {
+  int blocks = (d.ix.C * 12 + kBlock - 1) / kBlock;   // as launch_dot_partials for a camera-sized vector
+  const int cap = scalar_blocks(d);
+  if (blocks > cap) blocks = cap;
+  k_cg_scalar<<<1, kBlock, 0, lc.stream>>>(blocks, d.scalar_part, static_cast<int>(stage), it, eta, min_it, max_it, d.cg,
+                                           d.ctl);
+  count(lc);
+}
+
+void launch_cg_update(const DeviceState& d, CgUpdate what, int n, int it, const double* src, double* dst,
+                      const LaunchCfg& lc) {
+  k_cg_update<<<(n + kBlock - 1) / kBlock, kBlock, 0, lc.stream>>>(n, static_cast<int>(what), it, src, dst, d.cg, d.ctl);
+  count(lc);
 }
 
 void launch_finite_check(const DeviceState& d, int n, const double* x, const LaunchCfg& lc) {

@@ -69,6 +69,11 @@ struct SeriesCtl {
   unsigned int next_block;  // peer mode: logical block numbers in dispatch order
 };
 
+// scalars of the preconditioned conjugate gradients (PCG / RIPCG), kept on the device: the iteration decides there
+struct CgState {
+  double rho, last_rho, alpha, beta, q0, norm_b;
+};
+
 // Peer-memory exchange of the per-term camera sums when landmarks are sharded over several GPUs
 // (engine.cu Engine::setup_peer_exchange, kernels_camera.cu k_term16<.., kTermPeer>).  Every rank owns
 // a receive buffer [2 parities][world][stride] of 16-byte slots {lo, epoch, hi, epoch}; recv[r] is rank r's
@@ -149,6 +154,7 @@ struct DeviceState {
   double* trial_out = nullptr;   // [16]
   int* flags = nullptr;          // [4] numerical-failure flags
   SeriesCtl* ctl = nullptr;
+  CgState* cg = nullptr;
   double* dense_S = nullptr;     // CHOLESKY: [n_pad x n_pad], n_pad = 12 C rounded up to 64
 };
 
@@ -225,7 +231,8 @@ void launch_series_term(const DeviceState& d, bool joint, int term, double eta, 
 
 // buf[0..n) += the other ranks' buf, over the peer buffers (n <= px.stride): what ncclAllReduce(sum) would do,
 // every rank adding in rank order
-void launch_peer_allreduce(const DeviceState& d, double* buf, size_t n, const PeerExchange& px, const LaunchCfg& lc);
+void launch_peer_allreduce(const DeviceState& d, double* buf, size_t n, const PeerExchange& px, const LaunchCfg& lc,
+                           bool skip_when_done = false);
 void launch_finish_b(const DeviceState& d, bool joint, const LaunchCfg& lc);
 void launch_e0_finish(const DeviceState& d, bool joint, double* out, const LaunchCfg& lc);
 void launch_make_y(const DeviceState& d, bool joint, const double* x, double* y, const LaunchCfg& lc);
@@ -257,5 +264,13 @@ void launch_cholesky_factor(double* S, int n_pad, double* linv, int* info, const
 void launch_cholesky_solve(const double* S, int n_pad, const double* linv, double* r, const int* info,
                            const LaunchCfg& lc);
 void launch_finite_check(const DeviceState& d, int n, const double* x, const LaunchCfg& lc);
+// PCG / RIPCG with the scalars and the termination tests on the device (kernels_schur.cu); every kernel returns
+// at once when ctl->done is set
+enum CgStage { CG_BEGIN = 0, CG_RHO = 1, CG_PQ = 2, CG_ZETA = 3 };
+// reduces the partials of the preceding launch_dot_partials and applies stage `stage` of iteration `it`
+void launch_cg_scalar(const DeviceState& d, CgStage stage, int it, double eta, int min_it, int max_it, const LaunchCfg& lc);
+void launch_dot_partials(const DeviceState& d, int n, const double* x, const double* y, const LaunchCfg& lc);
+enum CgUpdate { CG_UPDATE_P = 0, CG_UPDATE_X = 1, CG_UPDATE_R = 2 };
+void launch_cg_update(const DeviceState& d, CgUpdate what, int n, int it, const double* src, double* dst, const LaunchCfg& lc);
 
 }  // namespace povar
