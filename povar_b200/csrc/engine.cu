@@ -469,7 +469,7 @@ int Engine::create(const povar_problem_desc* desc, const povar_options* opt,
     }
   }
   if (rc == POVAR_OK) rc = e->check(cudaStreamCreateWithFlags(&e->stream_, cudaStreamNonBlocking), "cudaStreamCreate");
-  for (int i = 0; i < 6 && rc == POVAR_OK; ++i) rc = e->check(cudaEventCreate(&e->ev_[i]), "cudaEventCreate");
+  for (int i = 0; i < 8 && rc == POVAR_OK; ++i) rc = e->check(cudaEventCreate(&e->ev_[i]), "cudaEventCreate");
   if (rc == POVAR_OK) rc = e->check(cudaHostAlloc(reinterpret_cast<void**>(&e->host_out_), 256, cudaHostAllocDefault), "cudaHostAlloc");
   if (rc == POVAR_OK && e->world_ > 1 && opt->solver_type_step_1 == POVAR_CHOLESKY) {
     // the direct solver's reduced camera system is not sharded (solver/linearizor_sc.cpp:121-128 is serial too)
@@ -957,7 +957,7 @@ int Engine::linearize(bool joint, double alpha, bool defer_check) {
     PV_ALLOC(d_.csc_w, static_cast<size_t>(nnz_));
     PV_ALLOC(d_.sell_w, static_cast<size_t>(d_.ix.sell_slots));
   }
-  PV_CUDA(cudaEventRecord(ev_[0], stream_));
+  PV_CUDA(cudaEventRecord(ev_[6], stream_));
   PV_CUDA(cudaMemsetAsync(d_.flags, 0, 4 * sizeof(int), stream_));
   // landmark side: Jl^T Jl, Jl^T r, column scales (LinearizorSC step 1 does not scale Jl:
   // solver/linearizor_sc.cpp:174-203)
@@ -977,7 +977,7 @@ int Engine::linearize(bool joint, double alpha, bool defer_check) {
     const int rc = allreduce(d_.trial_out + 9, 1);
     if (rc != POVAR_OK) return rc;
   }
-  PV_CUDA(cudaEventRecord(ev_[1], stream_));
+  PV_CUDA(cudaEventRecord(ev_[7], stream_));
   PV_CUDA(cudaGetLastError());
   if (defer_check) {
     // the caller goes on to a trial(): the flag comes back with that trial's results (one synchronisation)
@@ -987,7 +987,7 @@ int Engine::linearize(bool joint, double alpha, bool defer_check) {
   double* v = host_out_ + 8;
   PV_CUDA(cudaMemcpyAsync(v + 9, d_.trial_out + 9, sizeof(double), cudaMemcpyDeviceToHost, stream_));
   PV_CUDA(cudaStreamSynchronize(stream_));
-  times_.linearize += elapsed(ev_[0], ev_[1]);
+  times_.linearize += elapsed(ev_[6], ev_[7]);
   if (v[9] > 0) return fail(POVAR_NUM_LINEARIZATION, "did not expect numerical failure during linearization");
   return POVAR_OK;
 }
@@ -1368,6 +1368,7 @@ int Engine::trial(bool joint, double alpha, double lambda, int32_t* iterations, 
   times_.residual += elapsed(ev_[3], ev_[4]);
   if (lin_check_pending_) {
     lin_check_pending_ = false;
+    times_.linearize += elapsed(ev_[6], ev_[7]);
     if (v[9] > 0) return fail(POVAR_NUM_LINEARIZATION, "did not expect numerical failure during linearization");
   }
   if (iterations) *iterations = hctl->iterations;

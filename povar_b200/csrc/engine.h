@@ -84,7 +84,7 @@ class Engine {
   ModelParams mp_{};
   std::vector<void*> allocs_;
   cudaStream_t stream_ = nullptr;
-  cudaEvent_t ev_[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [6], [7]: linearize
   long long launches_ = 0;
   std::string err_;
   PhaseTimes times_;
