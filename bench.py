@@ -162,6 +162,9 @@ def main():
                     help="LM iterations of step 1 / step 2 in each CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--max-iters", type=int, nargs=2, default=[50, 50])
+    ap.add_argument("--trace-out", default=None,
+                    help="write the logged trace of the last timed solve (cost, accept/reject, term counts) as json: "
+                         "what runs at different GPU counts are compared by (tools/compare_traces.py)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -358,6 +361,13 @@ def main():
                 "bytes than the reference layout; frac is against the bytes THIS layout must move",
     }
     solver.close()
+    if args.trace_out and rank == 0:
+        with open(args.trace_out, "w") as f:
+            json.dump({"workload": args.workload, "n_gpus": world, "max_iters": args.max_iters,
+                       "step": [e.step for e in its], "iteration": [e.iteration for e in its],
+                       "cost": [e.cost for e in its], "step_is_successful": [int(e.step_is_successful) for e in its],
+                       "linear_solver_iterations": [e.linear_solver_iterations for e in its],
+                       "trust_region_radius": [e.trust_region_radius for e in its]}, f)
 
     # ---- end to end from host buffers: create (H2D) + solve + read back (D2H) + destroy
     # inputs are page-locked once, outside the timed region (the contract: H2D from pinned host memory);

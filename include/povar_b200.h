@@ -337,6 +337,11 @@ int povar_debug_sell_layout(int32_t num_cams, int32_t num_lms, const int64_t* lm
  * reference does with Eigen::SimplicialLLT (sc/linearization_sc.hpp:236-245); exposed for the tests. */
 int povar_debug_cholesky(int32_t n, const double* A, const double* b, double* x, int32_t* info);
 
+/* Caps the number of camera records the landmark half of a power-series term stages in shared memory (0 = as many
+ * as fit).  The result must not depend on it: cameras outside the staged window are read from global memory.  Tests
+ * use it to exercise that path on problems whose whole camera table would fit. */
+int povar_debug_set_window(povar_handle* h, int32_t cams);
+
 /* 1 if this handle exchanges the per-term camera sums over peer memory (CUDA IPC + NVLink stores fused
  * into the term kernel), 0 if it uses ncclAllReduce per term (single GPU: 0).  POVAR_PEER_EXCHANGE=0 in
  * the environment forces NCCL, =1 makes povar_create fail instead of falling back. */

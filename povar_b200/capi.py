@@ -155,6 +155,7 @@ SIGNATURES = {
     "povar_launch_count": (C.c_int64, [_H]),
     "povar_bal_create_dataset": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int64, C.c_char_p, C.c_size_t]),
     "povar_peer_exchange_active": (C.c_int, [_H]),
+    "povar_debug_set_window": (C.c_int, [_H, C.c_int32]),
     "povar_debug_cholesky": (C.c_int, [C.c_int32, _DP, _DP, _DP, C.POINTER(C.c_int32)]),
     "povar_write_ba_log": (C.c_int, [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "povar_debug_sell_layout": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.c_int32,
@@ -429,6 +430,9 @@ class Solver:
 
     def peer_exchange_active(self) -> bool:
         return bool(self.lib.povar_peer_exchange_active(self.h))
+
+    def debug_set_window(self, cams: int) -> None:
+        self._check(self.lib.povar_debug_set_window(self.h, cams))
 
     def launch_count(self) -> int:
         return int(self.lib.povar_launch_count(self.h))

@@ -254,6 +254,12 @@ int povar_debug_cholesky(int32_t n, const double* A, const double* b, double* x,
   return povar::debug_cholesky(n, A, b, x, info);
 }
 
+int povar_debug_set_window(povar_handle* h, int32_t cams) {
+  PV_ENGINE(h);
+  e.debug_set_window(cams);
+  return POVAR_OK;
+}
+
 int povar_peer_exchange_active(const povar_handle* h) {
   if (!h || !h->engine) return 0;
   return h->engine->peer_exchange_active() ? 1 : 0;

@@ -51,6 +51,7 @@ class Engine {
   void reset_times() { times_ = PhaseTimes(); }
   int world_size() const { return world_; }
   bool peer_exchange_active() const { return peer_ok_; }
+  void debug_set_window(int cams) { d_.debug_window_cams = cams; }
   int rank() const { return rank_; }
 
  private:

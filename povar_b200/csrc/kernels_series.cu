@@ -548,11 +548,13 @@ void launch_landmark_half(const DeviceState& d, const ModelParams& mp, const Ser
   if (per_warp < 1) per_warp = 1;
   long long warps = (d.ix.num_slices + per_warp - 1) / per_warp;
   if (warps < 1) warps = 1;   // long landmarks only
+  // tests force a small window so that the global-memory path for cameras outside it is exercised
+  const int cap = d.debug_window_cams > 0 ? d.debug_window_cams : (1 << 30);
   if (small_table) {
     launch_landmark_block<JOINT, HASW, 256>(d, mp, ctl, static_cast<int>((warps + 7) / 8), static_cast<int>(per_warp),
-                                            d.ix.C, lc);
+                                            d.ix.C < cap ? d.ix.C : cap, lc);
   } else {
-    const int win = kWinBytes / rec_bytes;
+    const int win = kWinBytes / rec_bytes < cap ? kWinBytes / rec_bytes : cap;
     launch_landmark_block<JOINT, HASW, kBigBlock>(d, mp, ctl, static_cast<int>((warps + kBigBlock / 32 - 1) / (kBigBlock / 32)),
                                                   static_cast<int>(per_warp), d.ix.C < win ? d.ix.C : win, lc);
   }

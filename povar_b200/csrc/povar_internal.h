@@ -155,6 +155,7 @@ struct DeviceState {
   int* flags = nullptr;          // [4] numerical-failure flags
   SeriesCtl* ctl = nullptr;
   CgState* cg = nullptr;
+  int debug_window_cams = 0;     // > 0: cap on the cameras the landmark half stages (povar_debug_set_window)
   double* dense_S = nullptr;     // CHOLESKY: [n_pad x n_pad], n_pad = 12 C rounded up to 64
 };
 

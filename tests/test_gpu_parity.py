@@ -159,6 +159,40 @@ def test_cholesky_solve_is_reproducible_and_solves_the_reduced_system():
     s.close()
 
 
+@pytest.mark.parametrize("shape,window", [("small", 3), ("ladybug49", 8), ("trafalgar257", 40)])
+def test_term_product_does_not_depend_on_the_staged_camera_window(shape, window):
+    """The landmark half of a term stages a window of camera records in shared memory and reads the cameras outside
+    it from global memory (kernels_series.cu).  With the window forced far below the camera count most observations
+    take the global path: E0 x must come out bit-identical in both steps, and so must a short solve."""
+    sp = synthetic.generate_named(shape)
+    hp = capi.HostProblem.from_unordered(sp.num_cams, sp.num_lms, sp.obs_cam, sp.obs_lm, sp.obs_xy, sp.cam_params)
+    opt = capi.default_options(alpha=0.1, power_sc_iterations=20, verbosity_level=0,
+                               max_num_iterations_step_1=3, max_num_iterations_step_2=2)
+    out = []
+    for cams in (0, window):
+        s = capi.Solver(hp, opt)
+        s.debug_set_window(cams)
+        s.initialize_varproj_lm_pOSE(0.1)
+        assert s.linearize_pOSE(0.1) == capi.OK
+        s.solve(1e-4)
+        x = np.random.default_rng(3).normal(size=(hp.num_cams, 12))
+        e1 = s.right_mul_e0(capi.STATE_POSE, x)
+        s.backup(capi.STATE_POSE)
+        s.apply(0.1)
+        s.to_homogeneous()
+        assert s.linearize_projective_space_homogeneous() == capi.OK
+        s.solve_joint(1e-2)
+        e2 = s.right_mul_e0(capi.STATE_JOINT, np.random.default_rng(4).normal(size=(hp.num_cams, 11)))
+        s.close()
+        s = capi.Solver(hp, opt)
+        s.debug_set_window(cams)
+        its, _ = s.bundle_adjust()
+        s.close()
+        out.append((e1, e2, [e.cost for e in its]))
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    assert out[0][2] == out[1][2]
+
+
 def test_runs_are_bit_reproducible():
     a = _gpu_trace("small_povar")[1]
     b = _gpu_trace("small_povar")[1]
