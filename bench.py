@@ -47,9 +47,11 @@ def ref_layout_bytes(nnz, L, C, joint=False):
 # bytes the matrix-free kernels have to move per launch (DESIGN.md "kernels"): index + observation
 # streams, per-landmark records, per-camera vectors, each counted once
 def own_bytes_landmark_pass(slots, slices, L, C):
-    # sliced-ELL landmark half (k_e0_landmark_sell<pose>): camera index + uv per slot (padding included: it is
-    # streamed), slice header, X + fold record read and H written per landmark, camera records once
-    return 20 * slots + 36 * slices + (32 + 80 + 32) * L + 224 * C
+    # sliced-ELL landmark half (k_e0_landmark_sell<pose>), 32 landmarks per slice: camera index + uv per slot
+    # (padding included: it is streamed), slice header (32 landmark ids + row pointer), per landmark the packed X
+    # (32 B) and fold (6 x 8 B in step 1) read and H written (32 B), camera records once (176 B each; the blocks
+    # stage them from L2)
+    return 20 * slots + 132 * slices + (32 + 48 + 32) * L + 176 * C
 
 
 def own_bytes_camera_pass(nnz, L, C, items):
