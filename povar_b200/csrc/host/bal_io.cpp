@@ -12,9 +12,12 @@
 #include <algorithm>
 #include <cerrno>
 #include <charconv>
+#include <climits>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <random>
 #include <string>
 #include <system_error>
@@ -142,6 +145,18 @@ static bool token_to_int(const char* b, const char* e, long long* out) {
   return r.ec == std::errc() && r.ptr == e;
 }
 
+// whole file into memory (+ a terminating NUL); false on any I/O error (ftell can fail on pipes, fread can be short)
+static bool slurp(FILE* f, std::vector<char>* buf) {
+  if (std::fseek(f, 0, SEEK_END) != 0) return false;
+  const long size = std::ftell(f);
+  if (size < 0 || std::fseek(f, 0, SEEK_SET) != 0) return false;
+  buf->resize(static_cast<size_t>(size) + 1);
+  const size_t got = std::fread(buf->data(), 1, static_cast<size_t>(size), f);
+  if (got != static_cast<size_t>(size) || std::ferror(f)) return false;
+  (*buf)[got] = '\0';
+  return true;
+}
+
 static int reader_threads(size_t bytes) {
   static const int forced = getenv("POVAR_HOST_THREADS") ? atoi(getenv("POVAR_HOST_THREADS")) : 0;
   if (forced > 0) return forced;
@@ -153,7 +168,7 @@ static int reader_threads(size_t bytes) {
 // The file is a flat list of whitespace-separated tokens: 3 header, 4 N observation, 15 C camera, 3 L landmark.
 // Two parallel passes over chunks cut at whitespace: count the tokens of each chunk, then (their global numbers
 // known by a prefix sum) convert every token straight into its destination.
-extern "C" int povar_bal_read(const char* path, povar_bal_data* out, char* err, size_t err_len) {
+static int bal_read_impl(const char* path, povar_bal_data* out, char* err, size_t err_len) {
   if (!path || !out) return POVAR_ERR_INVALID;
   std::memset(out, 0, sizeof(*out));
   FILE* f = std::fopen(path, "rb");
@@ -161,13 +176,14 @@ extern "C" int povar_bal_read(const char* path, povar_bal_data* out, char* err, 
     set_err(err, err_len, std::string("Could not open '") + path + "'");
     return POVAR_ERR_IO;
   }
-  std::fseek(f, 0, SEEK_END);
-  const long size = std::ftell(f);
-  std::fseek(f, 0, SEEK_SET);
-  std::vector<char> buf(static_cast<size_t>(size) + 1);
-  const size_t got = std::fread(buf.data(), 1, static_cast<size_t>(size), f);
+  std::vector<char> buf;
+  if (!slurp(f, &buf)) {
+    std::fclose(f);
+    set_err(err, err_len, std::string("Could not read '") + path + "'");
+    return POVAR_ERR_IO;
+  }
   std::fclose(f);
-  buf[got] = '\0';
+  const size_t got = buf.size() - 1;
   const char* base = buf.data();
   const char* end = base + got;
   Cursor cur{base, end};
@@ -175,6 +191,16 @@ extern "C" int povar_bal_read(const char* path, povar_bal_data* out, char* err, 
   long long C = 0, L = 0, N = 0;
   if (!cur.next_int(&C) || !cur.next_int(&L) || !cur.next_int(&N) || C <= 0 || L <= 0 || N <= 0) {
     set_err(err, err_len, std::string("Failed to parse header of '") + path + "'");
+    return POVAR_ERR_IO;
+  }
+  // the header is untrusted: indices are int32 on the device, and a file with N observations, C cameras and L
+  // landmarks has at least 4 N + 15 C + 3 L tokens of at least two bytes each -- checked before anything is
+  // allocated from these numbers
+  if (C > INT32_MAX || L > INT32_MAX || N > INT32_MAX ||
+      2 * (4 * N + 15 * C + 3 * L) > static_cast<long long>(got) + 1) {
+    set_err(err, err_len, std::string("Header of '") + path + "' does not fit the file (" + std::to_string(C) +
+                              " cameras, " + std::to_string(L) + " landmarks, " + std::to_string(N) +
+                              " observations in " + std::to_string(got) + " bytes)");
     return POVAR_ERR_IO;
   }
   const long long n_obs_tok = 4 * N, n_cam_tok = 15 * C, n_lm_tok = 3 * L;
@@ -307,21 +333,43 @@ extern "C" int povar_bal_read(const char* path, povar_bal_data* out, char* err, 
 // sequence.  The reference seeds std::mt19937 from std::random_device (seed < 0 here); with a seed the
 // output is reproducible.  Like the reference it draws 15 variates per camera from a fresh
 // std::normal_distribution and uses the first 8.
+// no exception crosses the C ABI: allocation failures on hostile sizes come back as POVAR_ERR_IO
+extern "C" int povar_bal_read(const char* path, povar_bal_data* out, char* err, size_t err_len) {
+  try {
+    return bal_read_impl(path, out, err, err_len);
+  } catch (const std::exception& e) {
+    set_err(err, err_len, std::string("Could not load '") + (path ? path : "") + "': " + e.what());
+    if (out) povar_bal_free(out);
+    return POVAR_ERR_IO;
+  }
+}
+
+static int create_dataset_impl(const char* input, const char* output, int64_t seed, char* err, size_t err_len);
 extern "C" int povar_bal_create_dataset(const char* input, const char* output, int64_t seed, char* err,
                                         size_t err_len) {
+  try {
+    return create_dataset_impl(input, output, seed, err, err_len);
+  } catch (const std::exception& e) {
+    set_err(err, err_len, std::string("--create-dataset failed: ") + e.what());
+    return POVAR_ERR_IO;
+  }
+}
+
+static int create_dataset_impl(const char* input, const char* output, int64_t seed, char* err, size_t err_len) {
   if (!input || !output) return POVAR_ERR_INVALID;
   FILE* f = std::fopen(input, "rb");
   if (!f) {
     set_err(err, err_len, std::string("Could not open '") + input + "'");
     return POVAR_ERR_IO;
   }
-  std::fseek(f, 0, SEEK_END);
-  const long size = std::ftell(f);
-  std::fseek(f, 0, SEEK_SET);
-  std::vector<char> buf(static_cast<size_t>(size) + 1);
-  const size_t got = std::fread(buf.data(), 1, static_cast<size_t>(size), f);
+  std::vector<char> buf;
+  if (!slurp(f, &buf)) {
+    std::fclose(f);
+    set_err(err, err_len, std::string("Could not read '") + input + "'");
+    return POVAR_ERR_IO;
+  }
   std::fclose(f);
-  buf[got] = '\0';
+  const size_t got = buf.size() - 1;
   Cursor cur{buf.data(), buf.data() + got};
   long long C = 0, L = 0, N = 0;
   if (!cur.next_int(&C) || !cur.next_int(&L) || !cur.next_int(&N) || C <= 0 || L <= 0 || N <= 0) {

@@ -110,6 +110,16 @@ def test_bal_reader_errors(tmp_path):
     oob.write_text("2 1 1\n5 0 1.0 2.0\n" + "\n".join(["0"] * 30) + "\n0 0 0\n")
     with pytest.raises(capi.PovarError):
         capi.HostProblem.read(str(oob))
+    # hostile headers: sizes the file cannot hold are refused before anything is allocated from them
+    for k, header in enumerate(["2000000000 2000000000 2000000000", "3000000000 1 1", "1 1 9223372036854775807"]):
+        bad = tmp_path / f"hostile{k}.txt"
+        bad.write_text(header + "\n0 0 1.0 2.0\n")
+        with pytest.raises(capi.PovarError) as e:
+            capi.HostProblem.read(str(bad))
+        assert e.value.code == capi.ERR_IO
+    with pytest.raises(capi.PovarError) as e:                    # a directory: fopen works, ftell / fread do not
+        capi.HostProblem.read(str(tmp_path))
+    assert e.value.code == capi.ERR_IO
 
 
 def test_canonical_order_from_generator_arrays():
