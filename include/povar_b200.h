@@ -331,6 +331,14 @@ int povar_debug_sell_layout(int32_t num_cams, int32_t num_lms, const int64_t* lm
                             int32_t threads, int32_t* slice_ptr, int32_t* sell_lm, int32_t* long_lms,
                             int64_t sizes[3]);
 
+/* host-side plan of the landmark half for that order: which slices every warp walks and which
+ * cameras every block stages in shared memory.  model: 0 step 1, 1 step 2, 2 step 1 with HUBER weights;
+ * sms: streaming multiprocessors to plan for.  info = {warps per block, ring stages, blocks per SM, blocks,
+ * ranges, cameras per window, 1 if every block's window holds every camera its slices meet, bytes of shared
+ * memory per block}.  range_slice [ranges + 1] and blk_lo [blocks] may be NULL (sizes come back in info). */
+int povar_debug_landmark_plan(int32_t num_cams, int32_t num_lms, const int64_t* lm_ptr, const int32_t* obs_cam,
+                              int32_t model, int32_t sms, int64_t info[8], int32_t* range_slice, int32_t* blk_lo);
+
 /* The direct solver of CHOLESKY (blocked LL^T on FP64 tensor-core tiles + substitution, kernels_chol.cu) on a
  * caller-supplied symmetric matrix: x = A^-1 b for a row-major n x n matrix of which the lower triangle is read.
  * *info = 0, or 1 + the index of the first 64-row tile with a non-positive pivot (x is then undefined).  What the

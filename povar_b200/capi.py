@@ -161,6 +161,9 @@ SIGNATURES = {
     "povar_debug_sell_layout": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.c_int32,
                                           C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                           C.POINTER(C.c_int64)]),
+    "povar_debug_landmark_plan": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.c_int32,
+                                            C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int32),
+                                            C.POINTER(C.c_int32)]),
     "povar_cuda_stream": (C.c_void_p, [_H]),
 }
 
@@ -476,6 +479,27 @@ def sell_layout(hp: "HostProblem", threads: int = 0):
     if rc != OK:
         raise PovarError(rc, "povar_debug_sell_layout failed")
     return tuple(a[:int(n)] for a, n in zip(out, sizes))
+
+
+def landmark_plan(hp: "HostProblem", model: int = 0, sms: int = 148):
+    """Plan of the landmark half (engine.cu plan_landmark_half) for `hp`: (info dict, range_slice, blk_lo)."""
+    lib = load()
+    info = (C.c_int64 * 8)()
+    lp = np.ascontiguousarray(hp.lm_ptr, dtype=np.int64)
+    oc = np.ascontiguousarray(hp.obs_cam, dtype=np.int32)
+    args = (hp.num_cams, hp.num_lms, lp.ctypes.data_as(C.POINTER(C.c_int64)), oc.ctypes.data_as(C.POINTER(C.c_int32)),
+            model, sms, info)
+    rc = lib.povar_debug_landmark_plan(*args, None, None)
+    if rc != OK:
+        raise PovarError(rc, "povar_debug_landmark_plan failed")
+    rs = np.zeros(int(info[4]) + 1, dtype=np.int32)
+    bl = np.zeros(max(int(info[3]), 1), dtype=np.int32)
+    rc = lib.povar_debug_landmark_plan(*args, rs.ctypes.data_as(C.POINTER(C.c_int32)),
+                                       bl.ctypes.data_as(C.POINTER(C.c_int32)))
+    if rc != OK:
+        raise PovarError(rc, "povar_debug_landmark_plan failed")
+    names = ("warps", "stages", "blocks_per_sm", "blocks", "ranges", "win_cams", "covered", "smem_bytes")
+    return {k: int(v) for k, v in zip(names, info)}, rs, bl[:int(info[3])]
 
 
 def create_dataset(src: str, dst: str, seed: int = -1) -> None:

@@ -250,6 +250,30 @@ int povar_debug_sell_layout(int32_t num_cams, int32_t num_lms, const int64_t* lm
   return POVAR_OK;
 }
 
+int povar_debug_landmark_plan(int32_t num_cams, int32_t num_lms, const int64_t* lm_ptr, const int32_t* obs_cam,
+                              int32_t model, int32_t sms, int64_t info[8], int32_t* range_slice, int32_t* blk_lo) {
+  if (num_cams <= 0 || num_lms < 0 || !lm_ptr || !info || model < 0 || model > 2 || sms <= 0) return POVAR_ERR_INVALID;
+  std::vector<int> lp(static_cast<size_t>(num_lms) + 1);
+  for (int32_t l = 0; l <= num_lms; ++l) lp[l] = static_cast<int>(lm_ptr[l]);
+  povar::SellLayout sell;
+  povar::build_sell(lp, obs_cam, num_cams, povar::kSellWindow, &sell);
+  const int rec_bytes = 8 * (model == 1 ? povar::kCamRecJoint : povar::kCamRecPose);
+  const int stage_bytes = model == 0 ? povar::kStagePose : povar::kStageWide;
+  const povar::LmPlanHost h = povar::plan_landmark_half(sell, num_cams, static_cast<int>(sell.long_lms.size()),
+                                                        rec_bytes, stage_bytes, sms);
+  info[0] = h.p.warps;
+  info[1] = h.p.stages;
+  info[2] = h.p.blocks_per_sm;
+  info[3] = h.p.blocks;
+  info[4] = h.p.ranges;
+  info[5] = h.p.win_cams;
+  info[6] = h.p.covered;
+  info[7] = static_cast<int64_t>(h.smem_bytes);
+  if (range_slice) std::copy(h.range_slice.begin(), h.range_slice.end(), range_slice);
+  if (blk_lo) std::copy(h.blk_lo.begin(), h.blk_lo.begin() + h.p.blocks, blk_lo);
+  return POVAR_OK;
+}
+
 int povar_debug_cholesky(int32_t n, const double* A, const double* b, double* x, int32_t* info) {
   return povar::debug_cholesky(n, A, b, x, info);
 }

@@ -276,25 +276,48 @@ void build_tiles(const std::vector<int>& lm_ptr, std::vector<int>* tile_ptr) {
 
 // Sliced ELL order of the landmarks with 1..32 observations (the landmark half of E0 gives a lane
 // to each landmark and walks its observations serially, so the 32 landmarks of a slice should have the
-// same degree).  Landmarks are first put in the order of their MEDIAN camera (stable
-// counting sort): neighbouring slices then gather from neighbouring camera records, which is what lets
-// the per-camera table stay in L1 (the slices of one SM come from one stretch of this order,
-// kernels_series.cu).  Inside windows of `window` landmarks of that order: stable sort by descending
-// degree, kSellWidth landmarks per slice, slice length = largest degree in it.  The order of the
-// observations INSIDE a landmark is untouched (camera ascending), so every H_l keeps its bits.
-void build_sell(const std::vector<int>& lm_ptr, const int* obs_cam, int num_cams, int window,
+// same degree).  Landmarks are first put in the order of their KEY camera (stable counting sort): the centre
+// of the stretch of kSellKeySpan cameras that holds most of the landmark's observations (the first such
+// stretch; for a landmark whose cameras span less than that, the middle between its first and its last
+// camera).  Neighbouring slices then gather from one stretch of the camera table, as short as the tracks
+// allow -- a block of the landmark half stages exactly that stretch in shared memory (kernels_series.cu); with
+// the median camera as key the stretch was twice as long on banded scenes.  Inside windows of `window`
+// landmarks of that order: stable sort by descending degree, kSellWidth landmarks per slice, slice length =
+// largest degree in it.  The order of the observations INSIDE a landmark is untouched (camera ascending), so
+// every H_l keeps its bits.
+int sell_key(const int* cams, int deg, int span) {
+  int best_i = 0, best_j = 0;
+  for (int i = 0, j = 0; i < deg; ++i) {
+    if (j < i) j = i;
+    while (j + 1 < deg && cams[j + 1] - cams[i] < span) ++j;
+    if (j - i > best_j - best_i) {
+      best_i = i;
+      best_j = j;
+    }
+  }
+  return (cams[best_i] + cams[best_j]) / 2;
+}
+
+int sell_window(int landmarks, int max_window) {
+  int w = max_window;
+  while (w > 512 && static_cast<long long>(w) * 128 > landmarks) w /= 2;
+  return w;
+}
+
+void build_sell(const std::vector<int>& lm_ptr, const int* obs_cam, int num_cams, int max_window,
                 SellLayout* out) {
   const int L = static_cast<int>(lm_ptr.size()) - 1;
   out->slice_ptr.assign(1, 0);
   out->sell_lm.clear();
-  out->slice_cam.clear();
+  out->slice_lo.clear();
+  out->slice_hi.clear();
   out->long_lms.clear();
   out->rows = 0;
   if (L <= 0) return;
   const int T = host_threads(L);
   auto chunk_begin = [&](int t) { return static_cast<int>(static_cast<long long>(L) * t / T); };
-  auto key = [&](int l) { return obs_cam[(lm_ptr[l] + lm_ptr[l + 1]) / 2]; };
-  // landmarks with 1..32 observations by median camera: stable counting sort, one histogram per chunk
+  auto key = [&](int l) { return sell_key(obs_cam + lm_ptr[l], lm_ptr[l + 1] - lm_ptr[l], kSellKeySpan); };
+  // landmarks with 1..32 observations by key camera: stable counting sort, one histogram per chunk
   // (chunk t's landmarks of a camera go after those of the chunks before it)
   std::vector<std::vector<int>> hist(T, std::vector<int>(static_cast<size_t>(num_cams), 0));
   std::vector<std::vector<int>> longs(T);
@@ -324,14 +347,20 @@ void build_sell(const std::vector<int>& lm_ptr, const int* obs_cam, int num_cams
     }
   });
   // windows of `window` landmarks of that order, each sorted (stably) by descending degree and cut into
-  // slices of eight: the windows are independent, and where a window's slices go is known up front
+  // slices: the windows are independent, and where a window's slices go is known up front.  A long window
+  // means little padding (2.6 % at 4,096 on venice-1778, 16 % at 512) but its slices mix the keys of the whole
+  // window; a shard with few landmarks per camera takes a shorter one, so that the cameras a block of the
+  // landmark half meets stay one stretch of the table: `max_window`, halved while there are fewer than 128
+  // windows, not below 512.
+  const int window = sell_window(n, max_window);
   const int num_windows = (n + window - 1) / window;
   const int W = kSellWidth;
   const int slices_per_full = (window + W - 1) / W;
   const int last_cnt = n - (num_windows - 1) * window;
   const int num_slices = num_windows == 0 ? 0 : (num_windows - 1) * slices_per_full + (last_cnt + W - 1) / W;
   out->sell_lm.assign(static_cast<size_t>(num_slices) * W, -1);
-  out->slice_cam.assign(static_cast<size_t>(num_slices), 0);
+  out->slice_lo.assign(static_cast<size_t>(num_slices), 0);
+  out->slice_hi.assign(static_cast<size_t>(num_slices), 0);
   std::vector<int> slice_len(static_cast<size_t>(num_slices), 0);
   parallel_chunks(T, [&](int t) {
     int head[34];
@@ -348,8 +377,15 @@ void build_sell(const std::vector<int>& lm_ptr, const int* obs_cam, int num_cams
       int sl = w * slices_per_full;
       for (int i = 0; i < cnt; i += W, ++sl) {
         slice_len[sl] = lm_ptr[order[i] + 1] - lm_ptr[order[i]];   // the largest degree of the slice
-        out->slice_cam[sl] = key(by_cam[w0]);                      // the window's smallest median camera
-        for (int g = 0; g < W && i + g < cnt; ++g) out->sell_lm[static_cast<size_t>(sl) * W + g] = order[i + g];
+        int lo = num_cams, hi = -1;
+        for (int g = 0; g < W && i + g < cnt; ++g) {
+          const int l = order[i + g];
+          out->sell_lm[static_cast<size_t>(sl) * W + g] = l;
+          lo = std::min(lo, obs_cam[lm_ptr[l]]);            // cameras ascend inside a landmark
+          hi = std::max(hi, obs_cam[lm_ptr[l + 1] - 1]);
+        }
+        out->slice_lo[sl] = lo;
+        out->slice_hi[sl] = hi;
       }
     }
   });
@@ -360,6 +396,84 @@ void build_sell(const std::vector<int>& lm_ptr, const int* obs_cam, int num_cams
     out->slice_ptr[sl + 1] = rows;
   }
   out->rows = rows;
+}
+
+// ---- plan of the landmark half (LmPlan, povar_internal.h) ----
+// Shared memory of one block: [mbarriers][warps x stages x stage_bytes of stream ring][window].
+size_t landmark_half_smem(int warps, int stages, int stage_bytes, int win_cams, int rec_bytes) {
+  return lm_bar_bytes(warps, stages) + static_cast<size_t>(warps) * stages * stage_bytes +
+         static_cast<size_t>(win_cams) * rec_bytes;
+}
+
+LmPlanHost plan_landmark_half(const SellLayout& sell, int num_cams, int num_long, int rec_bytes, int stage_bytes,
+                              int sms) {
+  const int S = static_cast<int>(sell.slice_ptr.size()) - 1;
+  constexpr size_t kSmemPerSm = 228 * 1024;   // sm_100: 228 KB per SM, 1 KB of it reserved per resident block
+  struct Cand {
+    int warps, stages, bps;
+  };
+  // preference: small blocks while the table still fits beside the rings (short launches on small shards,
+  // less tail), then one block per SM with the deepest ring, then fewer warps around a larger window
+  const Cand cands[] = {{8, 3, 4}, {16, 3, 2}, {32, 3, 1}, {32, 2, 1}, {24, 2, 1}, {16, 2, 1}};
+  LmPlanHost best;
+  int best_win = -1;
+  for (const Cand& cd : cands) {
+    LmPlanHost h;
+    LmPlan& p = h.p;
+    p.warps = cd.warps;
+    p.stages = cd.stages;
+    p.blocks_per_sm = cd.bps;
+    const long long resident = static_cast<long long>(sms) * cd.bps * cd.warps;   // warps of one wave
+    p.ranges = static_cast<int>(std::min<long long>(resident, S));
+    // ranges of (nearly) equal rows: range w starts at the first slice at or after row w * rows / ranges
+    h.range_slice.assign(static_cast<size_t>(p.ranges) + 1, S);
+    {
+      const long long rows = S > 0 ? sell.slice_ptr[S] : 0;
+      int sl = 0;
+      for (int w = 0; w < p.ranges; ++w) {
+        const long long target = rows * w / p.ranges;
+        while (sl < S && sell.slice_ptr[sl] < target) ++sl;
+        h.range_slice[w] = sl;
+      }
+    }
+    const int slice_blocks = (p.ranges + cd.warps - 1) / cd.warps;
+    const int long_blocks = static_cast<int>(std::min<long long>(static_cast<long long>(sms) * cd.bps,
+                                                                 (num_long + cd.warps - 1) / cd.warps));
+    p.blocks = std::max(slice_blocks, long_blocks);
+    // cameras every block meets
+    std::vector<int> lo(static_cast<size_t>(std::max(p.blocks, 1)), num_cams), hi(lo.size(), -1);
+    int need = 1;
+    for (int b = 0; b < slice_blocks; ++b) {
+      const int s0 = h.range_slice[static_cast<size_t>(b) * cd.warps];
+      const int s1 = h.range_slice[std::min<size_t>(static_cast<size_t>(b + 1) * cd.warps, p.ranges)];
+      for (int sl = s0; sl < s1; ++sl) {
+        lo[b] = std::min(lo[b], sell.slice_lo[sl]);
+        hi[b] = std::max(hi[b], sell.slice_hi[sl]);
+      }
+      if (hi[b] >= lo[b]) need = std::max(need, hi[b] - lo[b] + 1);
+    }
+    const size_t budget = kSmemPerSm / cd.bps - 1024;
+    const size_t fixed = landmark_half_smem(cd.warps, cd.stages, stage_bytes, 0, rec_bytes);
+    const int fit = budget > fixed ? static_cast<int>((budget - fixed) / rec_bytes) : 0;
+    p.win_cams = std::min(num_cams, std::min(need, fit));
+    p.covered = fit >= std::min(need, num_cams) ? 1 : 0;
+    h.blk_lo.assign(static_cast<size_t>(std::max(p.blocks, 1)), 0);
+    for (int b = 0; b < p.blocks; ++b) {
+      int start = 0;
+      if (hi[b] >= lo[b]) {
+        const int span = hi[b] - lo[b] + 1;
+        start = span <= p.win_cams ? lo[b] : lo[b] + (span - p.win_cams) / 2;   // not covered: the middle
+      }
+      h.blk_lo[b] = std::max(0, std::min(start, num_cams - p.win_cams));
+    }
+    h.smem_bytes = landmark_half_smem(cd.warps, cd.stages, stage_bytes, p.win_cams, rec_bytes);
+    if (p.covered) return h;
+    if (p.win_cams > best_win) {
+      best_win = p.win_cams;
+      best = std::move(h);
+    }
+  }
+  return best;
 }
 
 int choose_item_len(long long nnz) {
@@ -631,7 +745,6 @@ int Engine::upload(const povar_problem_desc* desc) {
   PV_ALLOC(ix.cam_item_ptr, C + 1);
   PV_ALLOC(ix.slice_ptr, sell.slice_ptr.size());
   PV_ALLOC(ix.sell_lm, sell.sell_lm.size());
-  PV_ALLOC(ix.slice_cam, sell.slice_cam.size());
   PV_ALLOC(ix.sell_cam, slots);
   PV_ALLOC(ix.sell_uv, slots);
   PV_ALLOC(ix.obs_slot, nnz);
@@ -646,7 +759,19 @@ int Engine::upload(const povar_problem_desc* desc) {
   PV_UP(ix.tile_ptr, tile_ptr.data(), sizeof(int) * tile_ptr.size());
   PV_UP(ix.slice_ptr, sell.slice_ptr.data(), sizeof(int) * sell.slice_ptr.size());
   if (!sell.sell_lm.empty()) PV_UP(ix.sell_lm, sell.sell_lm.data(), sizeof(int) * sell.sell_lm.size());
-  if (!sell.slice_cam.empty()) PV_UP(ix.slice_cam, sell.slice_cam.data(), sizeof(int) * sell.slice_cam.size());
+  // landmark half: ranges of slices per warp, windows of cameras per block (kernels_series.cu), per model
+  LmPlanHost lm_plans[3];   // alive until the synchronisation at the end of this function
+  for (int m = 0; m < 3; ++m) {
+    const int rec_bytes = 8 * (m == 1 ? kCamRecJoint : kCamRecPose);
+    const int stage_bytes = m == 0 ? kStagePose : kStageWide;
+    lm_plans[m] = plan_landmark_half(sell, C, ix.num_long, rec_bytes, stage_bytes, sm_count());
+    const LmPlanHost& h = lm_plans[m];
+    d_.plan[m] = h.p;
+    PV_ALLOC(d_.plan[m].range_slice, h.range_slice.size());
+    PV_ALLOC(d_.plan[m].blk_lo, h.blk_lo.size());
+    PV_UP(d_.plan[m].range_slice, h.range_slice.data(), sizeof(int) * h.range_slice.size());
+    PV_UP(d_.plan[m].blk_lo, h.blk_lo.data(), sizeof(int) * h.blk_lo.size());
+  }
   if (ix.num_long > 0) PV_UP(ix.long_lm, sell.long_lms.data(), sizeof(int) * sell.long_lms.size());
   PV_UP(ix.cam_ptr, cam_ptr.data(), sizeof(int) * (C + 1));
   PV_UP(ix.item_ptr, item_ptr.data(), sizeof(int) * item_ptr.size());

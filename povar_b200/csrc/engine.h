@@ -125,13 +125,27 @@ class Engine {
 struct SellLayout {
   std::vector<int> slice_ptr;   // [num_slices+1] rows
   std::vector<int> sell_lm;     // [8*num_slices]
-  std::vector<int> slice_cam;   // [num_slices] median camera of the slice's first landmark (non-decreasing)
+  std::vector<int> slice_lo;    // [num_slices] smallest camera the slice's landmarks observe
+  std::vector<int> slice_hi;    // [num_slices] largest
   std::vector<int> long_lms;    // landmarks with more than 32 observations
   int rows = 0;
 };
 void set_host_threads_override(int n);   // 0 = automatic
-void build_sell(const std::vector<int>& lm_ptr, const int* obs_cam, int num_cams, int window,
+void build_sell(const std::vector<int>& lm_ptr, const int* obs_cam, int num_cams, int max_window,
                 SellLayout* out);
+int sell_window(int landmarks, int max_window);
+int sell_key(const int* cams, int deg, int span);
+
+// plan of the landmark half for records of rec_bytes per camera and ring stages of stage_bytes per row
+// (LmPlan without the device arrays; range_slice / blk_lo come back as host vectors)
+struct LmPlanHost {
+  LmPlan p;
+  std::vector<int> range_slice, blk_lo;
+  size_t smem_bytes = 0;
+};
+LmPlanHost plan_landmark_half(const SellLayout& sell, int num_cams, int num_long, int rec_bytes, int stage_bytes,
+                              int sms);
+size_t landmark_half_smem(int warps, int stages, int stage_bytes, int win_cams, int rec_bytes);
 
 // host-side index construction (engine.cu), exposed for the CPU tests through the C ABI
 void build_tiles(const std::vector<int>& lm_ptr, std::vector<int>* tile_ptr);

@@ -72,23 +72,23 @@ struct ObsCoef {
 // a slice is 32 landmarks of (nearly) equal degree, one per lane; the lane visits the observations of its
 // landmark in camera order and keeps G_l in registers: no tile table, no reduction, no exchange.
 //
-// Where the camera records come from.  The landmarks are ordered by median camera, so the slices of one block
-// meet a WINDOW of cameras: the block stages the records of that window in shared memory with bulk-async
-// copies (cp.async.bulk + mbarrier, the TMA unit; the copy overlaps the index loads of the prologue) and every
-// lane reads the record of its observation's camera with LDS.128.  A camera outside the window (rare by
-// construction of the order; never for C <= window) is read from global memory, so the result does not depend
-// on the window.  Large problems run one block of 32 warps per SM around a window of 228 KB (1,300 cameras in
-// step 1, 1,100 in step 2); a table of up to 48 KB fits four times per SM and the blocks stay small (short
-// launches on small shards).
-//
-// The per-slice landmark data (X, fold) are read from lane-major copies packed once per solve (k_sell_pack):
-// one coalesced line per component instead of 32 scattered records.  What is fetched ahead is the stream from
-// HBM: camera index and observation coefficients of the next kAhead rows (coalesced, 32 lanes wide).
+// Everything the inner loop reads comes from shared memory, put there by the TMA unit (cp.async.bulk +
+// mbarrier: no registers and no scoreboards are tied up while the data travels):
+//   * the camera records.  The landmarks are ordered by the centre of their cameras, so the slices of one
+//     block meet a WINDOW of cameras (LmPlan::blk_lo, made on the host from the exact camera ranges of the
+//     block's slices); the block stages the records of that window once, and every lane reads the record of
+//     its observation's camera with LDS.128.  A camera outside the window (only when the window a block
+//     needs does not fit; never for a small C) is read from global memory, so the result does not depend on
+//     the window;
+//   * the observation stream (camera index and model coefficients, 640 or 896 bytes per row of 32 slots): every
+//     warp owns a ring of `stages` rows; one lane refills the stage of row r with row r + stages as soon as the
+//     warp has used it.  Round 2's first version kept the next rows in registers: the compiler placed the
+//     scoreboard waits of those loads at the head of the loop, so the latency of the stream was exposed in
+//     every iteration (54 % of the stall samples, profiles/r2_summary.md).
+// The ranges have equal numbers of ROWS (LmPlan::range_slice), one wave of warps: every block carries the
+// same load.  The per-slice landmark data (X, fold) are read from lane-major copies packed once per solve
+// (k_sell_pack): one coalesced line per component; they are pulled into L2 one slice ahead.
 // ------------------------------------------------------------------------------------------
-constexpr int kWinBytes = 228800;     // records staged by a big block (one per SM)
-constexpr int kWinSmallBytes = 49152; // whole table: four blocks of 256 threads per SM
-constexpr int kBigBlock = 1024;
-
 struct CamWindow {
   const double* smem;   // records of cameras lo .. lo + n - 1
   int lo, n;
@@ -183,26 +183,6 @@ __device__ __forceinline__ void fold_apply(const double (&F)[10], const double (
   }
 }
 
-// the streamed part of one observation slot: camera index and the coefficients of the observation model
-template <bool JOINT, bool HASW>
-__device__ __forceinline__ void load_stream(const DeviceIndex& ix, const double* __restrict__ sell_d,
-                                            const double* __restrict__ sell_w, int row, int lane, int& c,
-                                            ObsCoef& k) {
-  const size_t slot = kSellWidth * static_cast<size_t>(row) + lane;
-  c = __ldcs(ix.sell_cam + slot);
-  if (JOINT) {
-    const double* dp = sell_d + 3 * kSellWidth * static_cast<size_t>(row) + lane;
-    k.a = __ldcs(dp);
-    k.b = __ldcs(dp + kSellWidth);
-    k.c = __ldcs(dp + 2 * kSellWidth);
-  } else {
-    const double2 uv = __ldcs(ix.sell_uv + slot);
-    k.a = uv.x;
-    k.b = uv.y;
-    k.c = HASW ? __ldcs(sell_w + slot) : 1.0;
-  }
-}
-
 // landmarks with more than 32 observations (outside the sliced-ELL set): one warp per landmark, taken by
 // the warps of the same blocks after their slices; lane g takes observations g, g + 32, ... of the CSR list,
 // fixed-tree sum over the lanes
@@ -244,50 +224,79 @@ __device__ __forceinline__ void long_landmark_warp(const DeviceIndex& ix, const 
   if (lane < 4) lm_rec[kLmRec * static_cast<size_t>(lm) + 4 + lane] = lane == 0 ? H[0] : (lane == 1 ? H[1] : (lane == 2 ? H[2] : H[3]));
 }
 
-constexpr int kStreamAhead = 16;   // rows the L2 prefetch runs ahead of the loads
-
-template <bool JOINT, bool HASW, int BLOCK>
-__global__ void __launch_bounds__(BLOCK, BLOCK > 256 ? 1 : 4)
-k_e0_landmark_sell(DeviceIndex ix, const double* __restrict__ X, const double* __restrict__ cam_rec,
-                   const double* __restrict__ sell_d, const double* __restrict__ sell_w, double c1,
-                   double c2, const double* __restrict__ lm_fold, const double* __restrict__ sell_x,
-                   const double* __restrict__ sell_fold, double* __restrict__ lm_rec,
-                   const double* __restrict__ obs_d, const double* __restrict__ obs_w,
-                   const SeriesCtl* __restrict__ ctl, int slices_per_warp, int win_cams) {
-  extern __shared__ __align__(128) double win_smem[];
-  __shared__ unsigned long long win_bar;
-  if (ctl != nullptr && ctl->done) return;
-  constexpr int kW = BLOCK / 32;
-  constexpr int kStride = CamRec::stride(JOINT);
-  const int lane = threadIdx.x & 31;
-  const int warp = static_cast<int>(blockIdx.x) * kW + (threadIdx.x >> 5);
-  // ---- the window of this block: centred on the median cameras of its slices; staged by the TMA unit
-  CamWindow win;
-  win.smem = win_smem;
-  win.n = min(win_cams, ix.C);
-  {
-    const int bs0 = min(static_cast<int>(blockIdx.x) * kW * slices_per_warp, ix.num_slices);
-    const int bs1 = min(bs0 + kW * slices_per_warp, ix.num_slices);
-    const int centre = bs1 > bs0 ? (__ldg(ix.slice_cam + bs0) + __ldg(ix.slice_cam + bs1 - 1)) / 2 : ix.C / 2;
-    win.lo = max(0, min(centre - win.n / 2, ix.C - win.n));
+// one row of the observation stream into a stage of the warp's ring (called by one lane)
+template <bool JOINT, bool HASW>
+__device__ __forceinline__ void issue_stage(const DeviceIndex& ix, const double* __restrict__ sell_d,
+                                            const double* __restrict__ sell_w, int row, unsigned char* stage,
+                                            unsigned long long* bar) {
+  constexpr unsigned kStage = (JOINT || HASW) ? kStageWide : kStagePose;
+  const size_t slot = kSellWidth * static_cast<size_t>(row);
+  mbar_expect_tx(bar, kStage);
+  bulk_copy_g2s(stage, ix.sell_cam + slot, 128u, bar);
+  if (JOINT) {
+    bulk_copy_g2s(stage + 128, sell_d + 3 * slot, 768u, bar);
+  } else {
+    bulk_copy_g2s(stage + 128, ix.sell_uv + slot, 512u, bar);
+    if (HASW) bulk_copy_g2s(stage + 640, sell_w + slot, 256u, bar);
   }
-  if (threadIdx.x == 0) mbar_init(&win_bar, 1);
+}
+
+template <bool JOINT, bool HASW, int W, int D, int BPS>
+__global__ void __launch_bounds__(32 * W, BPS)
+k_e0_landmark_sell(DeviceIndex ix, LmPlan plan, int win_cams, const double* __restrict__ X,
+                   const double* __restrict__ cam_rec, const double* __restrict__ sell_d,
+                   const double* __restrict__ sell_w, double c1, double c2, const double* __restrict__ lm_fold,
+                   const double* __restrict__ sell_x, const double* __restrict__ sell_fold,
+                   double* __restrict__ lm_rec, const double* __restrict__ obs_d,
+                   const double* __restrict__ obs_w, const SeriesCtl* __restrict__ ctl) {
+  extern __shared__ __align__(128) unsigned char lm_smem[];
+  if (ctl != nullptr && ctl->done) return;
+  constexpr int kStage = (JOINT || HASW) ? kStageWide : kStagePose;
+  constexpr int kStride = CamRec::stride(JOINT);
+  static_assert(kStride == (JOINT ? kCamRecJoint : kCamRecPose), "plan_landmark_half sizes the window with these");
+  constexpr int kBars = lm_bar_bytes(W, D);
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int range = static_cast<int>(blockIdx.x) * W + wib;
+  // shared memory: [mbarriers: window, then D per warp][rings][window]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(lm_smem);
+  unsigned long long* my_bars = bars + 1 + wib * D;
+  unsigned char* my_ring = lm_smem + kBars + static_cast<size_t>(wib) * D * kStage;
+  CamWindow win;
+  win.smem = reinterpret_cast<const double*>(lm_smem + kBars + static_cast<size_t>(W) * D * kStage);
+  win.n = min(win_cams, ix.C);
+  win.lo = min(__ldg(plan.blk_lo + blockIdx.x), ix.C - win.n);
+  if (threadIdx.x == 0) mbar_init(&bars[0], 1);
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < D; ++s) mbar_init(&my_bars[s], 1);
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned bytes = static_cast<unsigned>(win.n) * (kStride * 8);
-    mbar_expect_tx(&win_bar, bytes);
+    mbar_expect_tx(&bars[0], bytes);
     const char* src = reinterpret_cast<const char*>(cam_rec + kStride * static_cast<size_t>(win.lo));
-    char* dst = reinterpret_cast<char*>(win_smem);
+    char* dst = reinterpret_cast<char*>(const_cast<double*>(win.smem));
     for (unsigned off = 0; off < bytes; off += 32768u) {
-      bulk_copy_g2s(dst + off, src + off, min(32768u, bytes - off), &win_bar);
+      bulk_copy_g2s(dst + off, src + off, min(32768u, bytes - off), &bars[0]);
     }
   }
-  const int s0 = warp * slices_per_warp;
-  if (s0 < ix.num_slices) {
-    const int s1 = min(s0 + slices_per_warp, ix.num_slices);
+  int s0 = 0, s1 = 0;
+  if (range < plan.ranges) {
+    s0 = __ldg(plan.range_slice + range);
+    s1 = __ldg(plan.range_slice + range + 1);
+  }
+  if (s0 < s1) {
     const int row_first = __ldg(ix.slice_ptr + s0);
     const int row_end = __ldg(ix.slice_ptr + s1);        // one past the last row of this warp
-    const int row_last = row_end - 1;
+    if (lane == 0) {
+#pragma unroll
+      for (int s = 0; s < D; ++s) {
+        if (row_first + s < row_end) {
+          issue_stage<JOINT, HASW>(ix, sell_d, sell_w, row_first + s, my_ring + s * kStage, &my_bars[s]);
+        }
+      }
+    }
     // first rows after the slices of this warp, 32 at a time: lane j keeps the one of slice hdr_base + j
     int hdr_base = s0;
     int hdr = __ldg(ix.slice_ptr + min(s0 + lane, s1 - 1) + 1);
@@ -306,7 +315,16 @@ k_e0_landmark_sell(DeviceIndex ix, const double* __restrict__ X, const double* _
         x[k] = __ldcs(xp + k * kSellWidth);
         G[k] = 0.0;
       }
-      if (sl + 1 < s1 && lane < 4) prefetch_l2(sell_x + 4 * kSellWidth * static_cast<size_t>(sl + 1) + 16 * lane);
+      // towards L2, one 128-byte line per lane: the fold of this slice (read when it closes) and the
+      // landmarks of the next one
+      constexpr int kFoldLines = JOINT ? 20 : 12;
+      if (lane < kFoldLines) {
+        prefetch_l2(sell_fold + 10 * kSellWidth * static_cast<size_t>(sl) + 16 * lane);
+      } else if (lane - kFoldLines < 8 && sl + 1 < s1) {
+        prefetch_l2(sell_x + 4 * kSellWidth * static_cast<size_t>(sl + 1) + 16 * (lane - kFoldLines));
+      } else if (lane == 31 && sl + 1 < s1) {
+        prefetch_l2(ix.sell_lm + kSellWidth * static_cast<size_t>(sl + 1));
+      }
     };
     auto close_slice = [&]() {
       double F[10], H[4];
@@ -322,49 +340,50 @@ k_e0_landmark_sell(DeviceIndex ix, const double* __restrict__ X, const double* _
       ++sl;
     };
 
-    constexpr int kAhead = 2;
-    int camq[kAhead];
-    ObsCoef kq[kAhead];
-#pragma unroll
-    for (int j = 0; j < kAhead; ++j) {
-      load_stream<JOINT, HASW>(ix, sell_d, sell_w, min(row_first + j, row_last), lane, camq[j], kq[j]);
-    }
     open_slice();
-    mbar_wait(&win_bar, 0);                   // the window is in shared memory
-    for (int row = row_first; row < row_end; row += kAhead) {
-      // pull the stream towards L2 ahead of the loads: per row 128 B of camera indices, 512 B of uv (768 B of d)
-      if (lane < (JOINT ? 7 : 5) * kAhead) {
-        const int per = JOINT ? 7 : 5;
-        const int rp = row + kStreamAhead + lane / per, part = lane % per;
-        if (rp <= row_last) {
-          if (part == 0) prefetch_l2(ix.sell_cam + kSellWidth * static_cast<size_t>(rp));
-          else if (JOINT) prefetch_l2(sell_d + 3 * kSellWidth * static_cast<size_t>(rp) + 16 * (part - 1));
-          else prefetch_l2(ix.sell_uv + kSellWidth * static_cast<size_t>(rp) + 8 * (part - 1));
-        }
-      }
+    mbar_wait(&bars[0], 0);                   // the window is in shared memory
+    unsigned phase = 0;
+    for (int row = row_first; row < row_end; row += D) {
 #pragma unroll
-      for (int i = 0; i < kAhead; ++i) {
+      for (int i = 0; i < D; ++i) {
         const int r = row + i;
         if (r < row_end) {           // warp-uniform
+          const unsigned char* st = my_ring + i * kStage;
+          mbar_wait(&my_bars[i], phase);
+          const int c = reinterpret_cast<const int*>(st)[lane];
+          ObsCoef k;
+          if (JOINT) {
+            const double* dp = reinterpret_cast<const double*>(st + 128) + lane;
+            k.a = dp[0];
+            k.b = dp[kSellWidth];
+            k.c = dp[2 * kSellWidth];
+          } else {
+            const double2 uv = reinterpret_cast<const double2*>(st + 128)[lane];
+            k.a = uv.x;
+            k.b = uv.y;
+            k.c = HASW ? reinterpret_cast<const double*>(st + 640)[lane] : 1.0;
+          }
           if (r == row1) {           // warp-uniform: the previous slice is complete
             close_slice();
             open_slice();
           }
-          if (camq[i] >= 0) landmark_obs_at<JOINT>(win, cam_rec, camq[i], x, kq[i], c1, c2, G);
-          // refill the slot only now: issued before the use, the compiler loads into a scratch register and
-          // copies it into the slot at once -- a stall on the load in every row (seen in the SASS); a row of
-          // a warp lasts thousands of cycles, so kAhead - 1 rows of distance cover any latency
-          load_stream<JOINT, HASW>(ix, sell_d, sell_w, min(r + kAhead, row_last), lane, camq[i], kq[i]);
+          if (c >= 0) landmark_obs_at<JOINT>(win, cam_rec, c, x, k, c1, c2, G);
+          // every lane holds its slot in registers: the stage can take row r + D
+          __syncwarp();
+          if (lane == 0 && r + D < row_end) {
+            issue_stage<JOINT, HASW>(ix, sell_d, sell_w, r + D, my_ring + i * kStage, &my_bars[i]);
+          }
         }
       }
+      phase ^= 1u;
     }
     close_slice();
   } else {
-    mbar_wait(&win_bar, 0);   // nobody leaves while the copy is in flight
+    mbar_wait(&bars[0], 0);   // nobody leaves while the copy is in flight
   }
   // ---- long landmarks, spread over all warps of the grid
-  const int total_warps = static_cast<int>(gridDim.x) * kW;
-  for (int k = warp; k < ix.num_long; k += total_warps) {
+  const int total_warps = static_cast<int>(gridDim.x) * W;
+  for (int k = static_cast<int>(blockIdx.x) * W + wib; k < ix.num_long; k += total_warps) {
     long_landmark_warp<JOINT, HASW>(ix, win, k, X, cam_rec, obs_d, obs_w, c1, c2, lm_fold, lm_rec);
   }
 }
@@ -521,43 +540,46 @@ k_cam_rec_static(int C, const double* __restrict__ P, double* __restrict__ cam_r
   if (JOINT && n == 0) r[24] = r[25] = 0.0;
 }
 
-template <bool JOINT, bool HASW, int BLOCK>
-void launch_landmark_block(const DeviceState& d, const ModelParams& mp, const SeriesCtl* ctl, int blocks,
-                           int per_warp, int win_cams, const LaunchCfg& lc) {
-  const size_t smem = static_cast<size_t>(win_cams) * CamRec::stride(JOINT) * 8;
-  static const cudaError_t attr = cudaFuncSetAttribute(k_e0_landmark_sell<JOINT, HASW, BLOCK>,
-                                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                       BLOCK > 256 ? kWinBytes : kWinSmallBytes);
+template <bool JOINT, bool HASW, int W, int D, int BPS>
+void launch_landmark_cfg(const DeviceState& d, const ModelParams& mp, const SeriesCtl* ctl, const LmPlan& plan,
+                         int win_cams, const LaunchCfg& lc) {
+  constexpr int kStage = (JOINT || HASW) ? kStageWide : kStagePose;
+  const size_t smem = lm_bar_bytes(W, D) + static_cast<size_t>(W) * D * kStage +
+                      static_cast<size_t>(win_cams) * CamRec::stride(JOINT) * 8;
+  auto kernel = k_e0_landmark_sell<JOINT, HASW, W, D, BPS>;
+  static const cudaError_t attr = [&]() {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) {
+      e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    }
+    return e;
+  }();
   (void)attr;
-  k_e0_landmark_sell<JOINT, HASW, BLOCK><<<blocks, BLOCK, smem, lc.stream>>>(
-      d.ix, d.X, d.cam_rec, d.sell_d, d.sell_w, mp.c1, mp.c2, d.lm_fold, d.sell_x, d.sell_fold, d.lm_rec, d.obs_d,
-      d.obs_w, ctl, per_warp, win_cams);
+  kernel<<<plan.blocks, 32 * W, smem, lc.stream>>>(d.ix, plan, win_cams, d.X, d.cam_rec, d.sell_d, d.sell_w, mp.c1,
+                                                   mp.c2, d.lm_fold, d.sell_x, d.sell_fold, d.lm_rec, d.obs_d,
+                                                   d.obs_w, ctl);
 }
 
 template <bool JOINT, bool HASW>
 void launch_landmark_half(const DeviceState& d, const ModelParams& mp, const SeriesCtl* ctl,
                           const LaunchCfg& lc) {
-  if (d.ix.num_slices == 0 && d.ix.num_long == 0) return;
-  // one wave of persistent-style blocks: SMs x 32 warps, contiguous slice ranges per warp.  Small problems and
-  // small shards keep the wave full with short ranges: a warp walks its rows one after the other, so the
-  // launch lasts as long as the longest range.
-  const int rec_bytes = CamRec::stride(JOINT) * 8;
-  const bool small_table = d.ix.C * rec_bytes <= kWinSmallBytes;
-  const long long full = static_cast<long long>(sm_count()) * 32;
-  long long per_warp = (d.ix.num_slices + full - 1) / full;
-  if (per_warp < 1) per_warp = 1;
-  long long warps = (d.ix.num_slices + per_warp - 1) / per_warp;
-  if (warps < 1) warps = 1;   // long landmarks only
-  // tests force a small window so that the global-memory path for cameras outside it is exercised
-  const int cap = d.debug_window_cams > 0 ? d.debug_window_cams : (1 << 30);
-  if (small_table) {
-    launch_landmark_block<JOINT, HASW, 256>(d, mp, ctl, static_cast<int>((warps + 7) / 8), static_cast<int>(per_warp),
-                                            d.ix.C < cap ? d.ix.C : cap, lc);
-  } else {
-    const int win = kWinBytes / rec_bytes < cap ? kWinBytes / rec_bytes : cap;
-    launch_landmark_block<JOINT, HASW, kBigBlock>(d, mp, ctl, static_cast<int>((warps + kBigBlock / 32 - 1) / (kBigBlock / 32)),
-                                                  static_cast<int>(per_warp), d.ix.C < win ? d.ix.C : win, lc);
+  const LmPlan& plan = d.plan[JOINT ? 1 : (HASW ? 2 : 0)];
+  if (plan.blocks == 0) return;   // no landmarks in this shard
+  // tests cap the window so that the global-memory path for cameras outside it is exercised
+  const int win = d.debug_window_cams > 0 && d.debug_window_cams < plan.win_cams ? d.debug_window_cams : plan.win_cams;
+#define POVAR_LM(W, D, BPS) \
+  if (plan.warps == W && plan.stages == D && plan.blocks_per_sm == BPS) { \
+    launch_landmark_cfg<JOINT, HASW, W, D, BPS>(d, mp, ctl, plan, win, lc); \
+  } else
+  POVAR_LM(8, 3, 4)
+  POVAR_LM(16, 3, 2)
+  POVAR_LM(32, 3, 1)
+  POVAR_LM(32, 2, 1)
+  POVAR_LM(24, 2, 1)
+  POVAR_LM(16, 2, 1) {
+    return;   // plan_landmark_half makes no other shape
   }
+#undef POVAR_LM
   count(lc);
 }
 

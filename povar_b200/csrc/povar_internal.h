@@ -26,13 +26,12 @@ struct DeviceIndex {
                               //   (<= 32 obs together) or one long landmark
   int num_tiles = 0;
   // landmark-major, sliced ELL for the landmark half of E0 (kernels_series.cu): landmarks with 1..32
-  // observations, sorted by degree inside windows of kSellWindow landmarks, kSellWidth (32) per slice; slot
+  // observations, ordered by the centre of their cameras, sorted by degree inside windows of kSellWindow
+  // landmarks of that order, kSellWidth (32) per slice; slot
   // 32 * row + g holds the row-th observation of the g-th landmark of the slice (camera -1 = padding)
   int num_slices = 0;
   int* slice_ptr = nullptr;   // [num_slices+1] first row of the slice
   int* sell_lm = nullptr;     // [32*num_slices] landmark of lane g, -1 = none
-  int* slice_cam = nullptr;   // [num_slices] median camera of the slice's first landmark: where a block of
-                              //   slices centres the window of camera records it stages in shared memory
   int* sell_cam = nullptr;    // [32*rows]
   double2* sell_uv = nullptr; // [32*rows]
   int* obs_slot = nullptr;    // [nnz] slot of the observation, -1 for landmarks outside the SELL set
@@ -52,8 +51,16 @@ struct DeviceIndex {
 constexpr double kEpsSqrtHost = 1e-5;  // Sophus::Constants<double>::epsilonSqrt()
 constexpr int kKron = 60;     // unique entries of sum_i E_i (x) (X X^T): 6 x 10
 constexpr int kSellWidth = 32;      // landmarks per slice of the sliced-ELL order: one per lane of a warp
-constexpr int kSellWindow = 512;    // sorting window of the sliced-ELL landmark order
+constexpr int kSellWindow = 4096;   // sorting window of the sliced-ELL landmark order
+constexpr int kSellKeySpan = 896;   // cameras the key of a landmark (build_sell) tries to centre
 constexpr int kCamRecStride = 26;   // doubles per camera record, the larger of the two models (CamRec::stride)
+constexpr int kCamRecPose = 22, kCamRecJoint = 26;   // CamRec::stride(false / true)
+// bytes of one row of the observation stream of the landmark half: 32 camera indices + 32 x (u, v) in step 1
+// (+ 32 robust weights with HUBER), 32 camera indices + 3 x 32 coefficients in step 2
+constexpr int kStagePose = 128 + 512, kStageWide = 128 + 768;
+// shared memory of a block of the landmark half ahead of the rings: one mbarrier for the window and one per
+// ring stage, rounded up to 128 bytes
+__host__ __device__ constexpr int lm_bar_bytes(int warps, int stages) { return ((1 + warps * stages) * 8 + 127) / 128 * 128; }
 constexpr int kLmRec = 8;     // per-landmark record read by the camera-major pass: [X(4) | H(4)]
 
 // series control block, lives in device memory
@@ -98,6 +105,22 @@ struct CostAccum {
   long long n_all, n_valid;
   int nonfinite;
   int pad;
+};
+
+// How the landmark half of a power-series term (kernels_series.cu) walks the sliced-ELL order: `ranges`
+// contiguous slice ranges with (nearly) equal numbers of rows, one per warp; a block of `warps` warps takes
+// consecutive ranges and stages the camera records [blk_lo[b], blk_lo[b] + win_cams) in shared memory.  Made
+// once per handle and model by plan_landmark_half (engine.cu) from what fits in shared memory.
+struct LmPlan {
+  int warps = 0;          // warps per block: 8, 16, 24 or 32
+  int stages = 0;         // depth of every warp's stream ring: 2 or 3 rows
+  int blocks_per_sm = 1;
+  int blocks = 0;
+  int ranges = 0;
+  int win_cams = 0;       // cameras staged per block (C if the whole table fits)
+  int covered = 0;        // 1: every block's window holds every camera its slices meet
+  int* range_slice = nullptr;   // [ranges + 1] first slice of every range
+  int* blk_lo = nullptr;        // [blocks] first camera of the block's window
 };
 
 // everything a kernel launcher needs
@@ -155,6 +178,7 @@ struct DeviceState {
   int* flags = nullptr;          // [4] numerical-failure flags
   SeriesCtl* ctl = nullptr;
   CgState* cg = nullptr;
+  LmPlan plan[3];                // landmark half: [0] step 1, [1] step 2, [2] step 1 with HUBER weights
   int debug_window_cams = 0;     // > 0: cap on the cameras the landmark half stages (povar_debug_set_window)
   double* dense_S = nullptr;     // CHOLESKY: [n_pad x n_pad], n_pad = 12 C rounded up to 64
 };

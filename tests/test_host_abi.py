@@ -263,14 +263,30 @@ def test_create_dataset_writes_the_reference_format(tmp_path):
         assert a[i] == b[i], (i, a[i], b[i])
 
 
-def _sell_reference(hp, window=512, width=32):
+def _sell_key(cams, span=896):
+    """Centre of the first stretch of `span` cameras that holds most of the landmark's observations."""
+    best = (0, 0)
+    j = 0
+    for i in range(len(cams)):
+        j = max(j, i)
+        while j + 1 < len(cams) and cams[j + 1] - cams[i] < span:
+            j += 1
+        if j - i > best[1] - best[0]:
+            best = (i, j)
+    return (int(cams[best[0]]) + int(cams[best[1]])) // 2
+
+
+def _sell_reference(hp, max_window=4096, width=32):
     """The sliced-ELL rule restated with numpy sorts (engine.cu build_sell): landmarks with 1..32 observations
-    in the order of their median camera (stable), windows of `window`, inside a window stable by descending
+    in the order of their key camera (stable), windows of `window`, inside a window stable by descending
     degree, 32 landmarks (one per lane) per slice, slice length = the largest degree in it."""
     deg = np.diff(hp.lm_ptr)
     ok = np.nonzero((deg > 0) & (deg <= 32))[0]
-    med = hp.obs_cam[(hp.lm_ptr[ok] + hp.lm_ptr[ok + 1]) // 2]
-    by_cam = ok[np.argsort(med, kind="stable")]
+    key = np.array([_sell_key(hp.obs_cam[hp.lm_ptr[l]:hp.lm_ptr[l + 1]]) for l in ok], dtype=np.int64)
+    by_cam = ok[np.argsort(key, kind="stable")]
+    window = max_window
+    while window > 512 and window * 128 > len(ok):
+        window //= 2
     slice_ptr, sell_lm = [0], []
     for w0 in range(0, len(by_cam), window):
         win = by_cam[w0:w0 + window]
@@ -282,6 +298,13 @@ def _sell_reference(hp, window=512, width=32):
     return np.array(slice_ptr), np.array(sell_lm), np.nonzero(deg > 32)[0]
 
 
+def test_sell_key_centres_the_cameras_it_can_cover():
+    assert _sell_key(np.array([10, 11, 12, 13, 1500])) == 11      # an outlier does not move the key
+    assert _sell_key(np.array([100, 400, 700])) == 400            # everything fits: the middle of first and last
+    assert _sell_key(np.array([5])) == 5
+    assert _sell_key(np.array([0, 1000, 1001, 1002])) == 1001
+
+
 @pytest.mark.parametrize("shape", ["small", "ladybug49", "trafalgar257"])
 def test_sliced_ell_order_matches_its_rule_for_any_thread_count(shape):
     sp = synthetic.generate_named(shape)
@@ -291,6 +314,41 @@ def test_sliced_ell_order_matches_its_rule_for_any_thread_count(shape):
         got = capi.sell_layout(hp, threads)
         for a, b in zip(got, ref):
             assert np.array_equal(a, b), (shape, threads)
+
+
+@pytest.mark.parametrize("shape,world", [("small", 1), ("trafalgar257", 1), ("venice89", 1), ("venice1778", 1),
+                                         ("venice1778", 8)])
+def test_landmark_half_plan_covers_the_slices_and_their_cameras(shape, world):
+    """plan_landmark_half (engine.cu): contiguous slice ranges with (nearly) equal rows, one per warp; per block a
+    window of the camera table that holds every camera its slices observe (on these shapes), inside what an SM
+    has of shared memory."""
+    sp = synthetic.generate_named(shape)
+    hp = capi.HostProblem.from_unordered(sp.num_cams, sp.num_lms, sp.obs_cam, sp.obs_lm, sp.obs_xy, sp.cam_params)
+    if world > 1:
+        hp = hp.shard(world - 1, world)
+    slice_ptr, sell_lm, _ = capi.sell_layout(hp)
+    S = len(slice_ptr) - 1
+    deg = np.diff(hp.lm_ptr)
+    for model, rec, stage in ((0, 176, 640), (1, 208, 896), (2, 176, 896)):
+        info, rs, lo = capi.landmark_plan(hp, model, sms=148)
+        W, D, bps = info["warps"], info["stages"], info["blocks_per_sm"]
+        assert (W, D, bps) in ((8, 3, 4), (16, 3, 2), (32, 3, 1), (32, 2, 1), (24, 2, 1), (16, 2, 1))
+        assert info["smem_bytes"] == ((1 + W * D) * 8 + 127) // 128 * 128 + W * D * stage + info["win_cams"] * rec
+        assert bps * (info["smem_bytes"] + 1024) <= 228 * 1024
+        assert info["ranges"] == min(148 * bps * W, S) and info["blocks"] >= -(-info["ranges"] // W)
+        assert rs[0] == 0 and rs[-1] == S and np.all(np.diff(rs) >= 0)
+        rows = np.diff(slice_ptr[rs])
+        longest = int(np.diff(slice_ptr).max())
+        assert rows.max() <= slice_ptr[-1] / info["ranges"] + longest + 1          # equal rows up to one slice
+        assert info["covered"] == 1
+        for b in range(-(-info["ranges"] // W)):
+            s0, s1 = rs[b * W], rs[min((b + 1) * W, info["ranges"])]
+            lms = sell_lm[32 * s0:32 * s1]
+            lms = lms[lms >= 0]
+            if len(lms) == 0:
+                continue
+            first, last = hp.obs_cam[hp.lm_ptr[lms]], hp.obs_cam[hp.lm_ptr[lms + 1] - 1]
+            assert lo[b] <= first.min() and last.max() < lo[b] + info["win_cams"] <= hp.num_cams, (shape, model, b)
 
 
 def test_ba_log_has_every_key_of_the_reference_log(tmp_path):

@@ -12,8 +12,11 @@ from povar_b200 import capi, synthetic  # noqa: E402
 workload = sys.argv[1] if len(sys.argv) > 1 else "venice1778"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 step = sys.argv[3] if len(sys.argv) > 3 else "pose"
+shard_of = int(sys.argv[4]) if len(sys.argv) > 4 else 1     # > 1: the first of that many landmark shards, alone
 sp = synthetic.generate_named(workload)
 hp = capi.HostProblem.from_unordered(sp.num_cams, sp.num_lms, sp.obs_cam, sp.obs_lm, sp.obs_xy, sp.cam_params)
+if shard_of > 1:
+    hp = hp.shard(0, shard_of)
 opt = capi.default_options(alpha=0.1, power_sc_iterations=20, verbosity_level=0, robust_norm=capi.NORM_CAUCHY,
                            max_num_iterations_step_1=3, max_num_iterations_step_2=2)
 s = capi.Solver(hp, opt)
