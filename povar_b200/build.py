@@ -36,7 +36,7 @@ LIB_SOURCES = [
     "host/ba_log_writer.cpp",
     "host/lm_driver.cpp",
 ]
-HEADERS = ["device_math.cuh", "povar_internal.h", "engine.h", "../../include/povar_b200.h"]
+HEADERS = ["device_math.cuh", "sell_walk.cuh", "povar_internal.h", "engine.h", "../../include/povar_b200.h"]
 
 
 def _nvcc() -> str:

@@ -406,7 +406,7 @@ size_t landmark_half_smem(int warps, int stages, int stage_bytes, int win_cams, 
 }
 
 LmPlanHost plan_landmark_half(const SellLayout& sell, int num_cams, int num_long, int rec_bytes, int stage_bytes,
-                              int sms) {
+                              int sms, int max_warps_per_sm, int reserve_bytes) {
   const int S = static_cast<int>(sell.slice_ptr.size()) - 1;
   constexpr size_t kSmemPerSm = 228 * 1024;   // sm_100: 228 KB per SM, 1 KB of it reserved per resident block
   struct Cand {
@@ -414,10 +414,13 @@ LmPlanHost plan_landmark_half(const SellLayout& sell, int num_cams, int num_long
   };
   // preference: small blocks while the table still fits beside the rings (short launches on small shards,
   // less tail), then one block per SM with the deepest ring, then fewer warps around a larger window
-  const Cand cands[] = {{8, 3, 4}, {16, 3, 2}, {32, 3, 1}, {32, 2, 1}, {24, 2, 1}, {16, 2, 1}};
+  // (operations with many registers per lane ask for at most 16 warps per SM: 128 registers per thread)
+  const Cand cands[] = {{8, 3, 4}, {16, 3, 2}, {32, 3, 1}, {32, 2, 1}, {24, 2, 1},
+                        {8, 3, 2}, {16, 3, 1}, {16, 2, 1}};
   LmPlanHost best;
   int best_win = -1;
   for (const Cand& cd : cands) {
+    if (cd.warps * cd.bps > max_warps_per_sm) continue;
     LmPlanHost h;
     LmPlan& p = h.p;
     p.warps = cd.warps;
@@ -452,7 +455,7 @@ LmPlanHost plan_landmark_half(const SellLayout& sell, int num_cams, int num_long
       }
       if (hi[b] >= lo[b]) need = std::max(need, hi[b] - lo[b] + 1);
     }
-    const size_t budget = kSmemPerSm / cd.bps - 1024;
+    const size_t budget = kSmemPerSm / cd.bps - 1024 - static_cast<size_t>(reserve_bytes);
     const size_t fixed = landmark_half_smem(cd.warps, cd.stages, stage_bytes, 0, rec_bytes);
     const int fit = budget > fixed ? static_cast<int>((budget - fixed) / rec_bytes) : 0;
     p.win_cams = std::min(num_cams, std::min(need, fit));
@@ -760,11 +763,14 @@ int Engine::upload(const povar_problem_desc* desc) {
   PV_UP(ix.slice_ptr, sell.slice_ptr.data(), sizeof(int) * sell.slice_ptr.size());
   if (!sell.sell_lm.empty()) PV_UP(ix.sell_lm, sell.sell_lm.data(), sizeof(int) * sell.sell_lm.size());
   // landmark half: ranges of slices per warp, windows of cameras per block (kernels_series.cu), per model
-  LmPlanHost lm_plans[3];   // alive until the synchronisation at the end of this function
-  for (int m = 0; m < 3; ++m) {
-    const int rec_bytes = 8 * (m == 1 ? kCamRecJoint : kCamRecPose);
-    const int stage_bytes = m == 0 ? kStagePose : kStageWide;
-    lm_plans[m] = plan_landmark_half(sell, C, ix.num_long, rec_bytes, stage_bytes, sm_count());
+  LmPlanHost lm_plans[5];   // alive until the synchronisation at the end of this function
+  for (int m = 0; m < 5; ++m) {
+    // [0..2] landmark half of a term (pOSE, joint, pOSE + HUBER); [3], [4] once-per-trial walks: more registers
+    // per lane (16 warps per SM), no long landmarks, 256 bytes of static shared memory for the block sums
+    const int rec_bytes = 8 * (m == 1 ? kCamRecJoint : m == 3 ? kCamTab1 : m == 4 ? kCamTab2 : kCamRecPose);
+    const int stage_bytes = (m == 1 || m == 2) ? kStageWide : kStagePose;
+    lm_plans[m] = m < 3 ? plan_landmark_half(sell, C, ix.num_long, rec_bytes, stage_bytes, sm_count(), 32, 0)
+                        : plan_landmark_half(sell, C, 0, rec_bytes, stage_bytes, sm_count(), 16, 256);
     const LmPlanHost& h = lm_plans[m];
     d_.plan[m] = h.p;
     PV_ALLOC(d_.plan[m].range_slice, h.range_slice.size());
@@ -808,6 +814,8 @@ int Engine::upload(const povar_problem_desc* desc) {
   PV_ALLOC(d_.lm_rec, static_cast<size_t>(L) * kLmRec);
   PV_ALLOC(d_.lm_fold, static_cast<size_t>(L) * 10);
   PV_ALLOC(d_.cam_rec, static_cast<size_t>(C) * kCamRecStride);
+  PV_ALLOC(d_.cam_tab, static_cast<size_t>(C) * kCamTab2);
+  PV_ALLOC(d_.lm_step, static_cast<size_t>(L) * 4);
   PV_ALLOC(d_.sell_x, static_cast<size_t>(ix.num_slices) * 4 * kSellWidth);
   PV_ALLOC(d_.sell_fold, static_cast<size_t>(ix.num_slices) * 10 * kSellWidth);
   PV_ALLOC(d_.kron, static_cast<size_t>(C) * kKron);

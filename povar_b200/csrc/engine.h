@@ -144,7 +144,7 @@ struct LmPlanHost {
   size_t smem_bytes = 0;
 };
 LmPlanHost plan_landmark_half(const SellLayout& sell, int num_cams, int num_long, int rec_bytes, int stage_bytes,
-                              int sms);
+                              int sms, int max_warps_per_sm = 32, int reserve_bytes = 0);
 size_t landmark_half_smem(int warps, int stages, int stage_bytes, int win_cams, int rec_bytes);
 
 // host-side index construction (engine.cu), exposed for the CPU tests through the C ABI

@@ -1,10 +1,10 @@
 // Landmark-major kernels: everything that reduces over the observations of one landmark.
 //
-// Work decomposition: one warp per TILE of the landmark-sorted observation array.  A tile is
-// either a run of whole landmarks with at most 32 observations together (one observation per
-// lane, segmented warp reductions between them) or one long landmark (> 32 observations, lanes
-// stride over it, full-warp reduction).  The tile table is built once on the host
-// (engine.cu: build_tiles).  All reductions use fixed trees => results are bit-reproducible.
+// Work decomposition of the passes over the observations (linearisation, back-substitution): landmarks with
+// 1..32 observations go through the sliced-ELL walk of sell_walk.cuh -- one lane per landmark, sums in
+// registers in camera order, the camera matrices staged in shared memory by the TMA unit; a landmark with more
+// than 32 observations gets a warp of the k_*_long kernels (lanes stride over it, fixed-tree warp sum).  All
+// reductions have a fixed order => results are bit-reproducible.
 //
 // Reference loops replaced (paths relative to /root/reference/src/rootba_povar/):
 //   k_init_varproj      bal/bal_bundle_adjustment_helper.cpp:75-99, 220-241
@@ -16,6 +16,7 @@
 
 #include "device_math.cuh"
 #include "povar_internal.h"
+#include "sell_walk.cuh"
 
 namespace povar {
 
@@ -39,39 +40,25 @@ __device__ __forceinline__ void load_lm4(const double* __restrict__ X, int lm, d
   load4(X + 4 * static_cast<size_t>(lm), x);
 }
 
+// one warp per landmark with more than 32 observations (DeviceIndex::long_lm)
 struct TileLane {
   int tb, te;
-  bool is_long;
   int lane;
-  __device__ __forceinline__ TileLane(const int* __restrict__ tile_ptr, int tile) {
-    tb = __ldg(tile_ptr + tile);
-    te = __ldg(tile_ptr + tile + 1);
-    is_long = (te - tb) > 32;
+  __device__ __forceinline__ TileLane(const DeviceIndex& ix, int which) {
+    const int lm = __ldg(ix.long_lm + which);
+    tb = __ldg(ix.lm_ptr + lm);
+    te = __ldg(ix.lm_ptr + lm + 1);
     lane = threadIdx.x & 31;
   }
 };
 
-// landmark totals of per-lane accumulators; seg bounds from the landmark of this lane
+// landmark totals of per-lane accumulators
 template <int NV>
-__device__ __forceinline__ void tile_allreduce(double (&acc)[NV], const TileLane& t, bool has_obs,
-                                               int lm, const int* __restrict__ lm_ptr) {
-  if (t.is_long) {
-    warp_allreduce<NV>(acc);
-  } else {
-    int first = t.lane, last = t.lane;
-    if (has_obs) {
-      first = __ldg(lm_ptr + lm) - t.tb;
-      last = __ldg(lm_ptr + lm + 1) - 1 - t.tb;
-    }
-    segment_allreduce<NV>(acc, t.lane, first, last);
-  }
+__device__ __forceinline__ void tile_allreduce(double (&acc)[NV], const TileLane&, bool, int, const int*) {
+  warp_allreduce<NV>(acc);
 }
 
-__device__ __forceinline__ bool is_head(const TileLane& t, bool has_obs, int lm,
-                                        const int* __restrict__ lm_ptr, int o) {
-  if (t.is_long) return t.lane == 0;
-  return has_obs && (o == __ldg(lm_ptr + lm));
-}
+__device__ __forceinline__ bool is_head(const TileLane& t, bool, int, const int*, int) { return t.lane == 0; }
 
 // ------------------------------------------------------------------------------------------
 // VarPro initialisation: X_l = argmin | G X - z | by Givens row updates of a 3x3 triangular
@@ -236,7 +223,7 @@ k_scalar_final(int nblocks, const double* __restrict__ part, double* out) {
 // ------------------------------------------------------------------------------------------
 template <bool JOINT>
 __global__ void POVAR_BOUNDS_LIN
-k_lin_landmark(DeviceIndex ix, const double* __restrict__ P, const double* __restrict__ X,
+k_lin_long(DeviceIndex ix, const double* __restrict__ P, const double* __restrict__ X,
                double c1, double c2, Robust rb, double eps, int scale_jl,
                double* __restrict__ lm_hraw, double* __restrict__ lm_graw,
                double* __restrict__ lm_scale, int* __restrict__ flags,
@@ -245,8 +232,8 @@ k_lin_landmark(DeviceIndex ix, const double* __restrict__ P, const double* __res
   constexpr int NV = JOINT ? 14 : 9;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (int tile = warp; tile < ix.num_tiles; tile += nwarps) {
-    const TileLane t(ix.tile_ptr, tile);
+  for (int tile = warp; tile < ix.num_long; tile += nwarps) {
+    const TileLane t(ix, tile);
     double acc[NV];
 #pragma unroll
     for (int k = 0; k < NV; ++k) acc[k] = 0.0;
@@ -510,7 +497,7 @@ __device__ __forceinline__ void landmark_solve(const double* acc, const double (
 // Fresh raw Jp/Jl/res at (P, X_old); stored scaled Jl and r are those of the linearisation
 // (P_old, X_old, weights, lm_scale).  `inc` is the scaled-space pose increment.
 __global__ void POVAR_BOUNDS_BACKSUB
-k_backsub_varpro(DeviceIndex ix, const double* __restrict__ P, const double* __restrict__ P_old,
+k_backsub_varpro_long(DeviceIndex ix, const double* __restrict__ P, const double* __restrict__ P_old,
                  double* __restrict__ X, const double* __restrict__ inc, double c1, double c2,
                  Robust rb, const double* __restrict__ lm_scale, double* __restrict__ scalar_part) {
   __shared__ double smem[kBlock / 32];
@@ -518,8 +505,8 @@ k_backsub_varpro(DeviceIndex ix, const double* __restrict__ P, const double* __r
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   double ld[1] = {0.0};
-  for (int tile = warp; tile < ix.num_tiles; tile += nwarps) {
-    const TileLane t(ix.tile_ptr, tile);
+  for (int tile = warp; tile < ix.num_long; tile += nwarps) {
+    const TileLane t(ix, tile);
     double acc[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) acc[k] = 0.0;
@@ -600,7 +587,7 @@ k_backsub_varpro(DeviceIndex ix, const double* __restrict__ P, const double* __r
 // PoBA (landmark_block.hpp:625-656): stored scaled Jp, Jl, r at the linearisation point, which is
 // the current state; y = pose_scale o inc.
 __global__ void __launch_bounds__(kBlock)
-k_backsub_poba(DeviceIndex ix, const double* __restrict__ P, double* __restrict__ X,
+k_backsub_poba_long(DeviceIndex ix, const double* __restrict__ P, double* __restrict__ X,
                const double* __restrict__ y, double c1, double c2, Robust rb,
                const double* __restrict__ lm_scale, const double* __restrict__ hll_inv,
                double* __restrict__ scalar_part) {
@@ -608,8 +595,8 @@ k_backsub_poba(DeviceIndex ix, const double* __restrict__ P, double* __restrict_
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   double ld[1] = {0.0};
-  for (int tile = warp; tile < ix.num_tiles; tile += nwarps) {
-    const TileLane t(ix.tile_ptr, tile);
+  for (int tile = warp; tile < ix.num_long; tile += nwarps) {
+    const TileLane t(ix, tile);
     double acc[3] = {0, 0, 0};
     int lm = __ldg(ix.obs_lm + t.tb), o_first = -1;
     bool has_obs = false;
@@ -688,15 +675,15 @@ k_backsub_poba(DeviceIndex ix, const double* __restrict__ P, double* __restrict_
 
 // joint (landmark_block.hpp:574-623): y = pose_scale o (Pi_c inc11)
 __global__ void POVAR_BOUNDS_BACKSUB
-k_backsub_joint(DeviceIndex ix, const double* __restrict__ P, double* __restrict__ X,
+k_backsub_joint_long(DeviceIndex ix, const double* __restrict__ P, double* __restrict__ X,
                 const double* __restrict__ y, Robust rb, const double* __restrict__ lm_scale,
                 const double* __restrict__ hll_inv, double* __restrict__ scalar_part) {
   __shared__ double smem[kBlock / 32];
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   double ld[1] = {0.0};
-  for (int tile = warp; tile < ix.num_tiles; tile += nwarps) {
-    const TileLane t(ix.tile_ptr, tile);
+  for (int tile = warp; tile < ix.num_long; tile += nwarps) {
+    const TileLane t(ix, tile);
     double acc[4] = {0, 0, 0, 0};
     int lm = __ldg(ix.obs_lm + t.tb), o_first = -1;
     bool has_obs = false;
@@ -724,12 +711,7 @@ k_backsub_joint(DeviceIndex ix, const double* __restrict__ P, double* __restrict
       for (int k = 0; k < 4; ++k) acc[k] += ob.sw * (j0[k] * e0 + j1[k] * e1);
     }
     tile_allreduce<4>(acc, t, has_obs, lm, ix.lm_ptr);
-    if (!t.is_long && !has_obs) {
-      // idle lane of a short tile: keep the reflector well defined
-      x[0] = 1.0;
-    } else if (t.is_long) {
-      load_lm4(X, lm, x);
-    }
+    load_lm4(X, lm, x);
     double s[4], inv[6];
     load_lm4(lm_scale, lm, s);
     {
@@ -782,6 +764,480 @@ k_backsub_joint(DeviceIndex ix, const double* __restrict__ P, double* __restrict
   if (threadIdx.x == 0) scalar_part[blockIdx.x] = ld[0];
 }
 
+// ------------------------------------------------------------------------------------------
+// The same passes for the landmarks of the sliced-ELL set (1..32 observations): operations of k_sell_walk.
+// A lane owns a landmark, meets its observations in camera order and keeps the sums in registers; the camera
+// data come from the staged table -- [P | pad] (kCamTab1 doubles) or [A | B | pad] (kCamTab2 doubles), packed
+// from the 12-vectors per camera right before the walk (k_pack_cam_tab).
+// The model decrease of a back-substitution, l_diff = -sum_i ji (ji / 2 + e_i) with ji = a_i + Jl_i dl, needs the
+// landmark increment dl, which is only known after the landmark's sums: the tile kernels walk the
+// observations twice.  Here the square is expanded,
+//   sum_i ji (ji / 2 + e_i) = sum_i (a_i^2 / 2 + a_i e_i) + dl^T sum_i Jl_i^T (a_i + e_i) + dl^T (sum_i Jl_i^T Jl_i) dl / 2,
+// the first two sums are made in the one walk and the third is the landmark's Jl^T Jl block of the
+// linearisation (lm_hraw): one walk, same value up to rounding.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void rec_cam(const double2* __restrict__ rec, Cam3x4& m) {
+  const double2 a0 = rec[0], a1 = rec[1], b0 = rec[2], b1 = rec[3], c0 = rec[4], c1 = rec[5];
+  m.r0[0] = a0.x; m.r0[1] = a0.y; m.r0[2] = a1.x; m.r0[3] = a1.y;
+  m.r1[0] = b0.x; m.r1[1] = b0.y; m.r1[2] = b1.x; m.r1[3] = b1.y;
+  m.r2[0] = c0.x; m.r2[1] = c0.y; m.r2[2] = c1.x; m.r2[3] = c1.y;
+}
+__device__ __forceinline__ void rec_vec12(const double2* __restrict__ rec, double (&y0)[4], double (&y1)[4],
+                                          double (&y2)[4]) {
+  const double2 a0 = rec[0], a1 = rec[1], b0 = rec[2], b1 = rec[3], c0 = rec[4], c1 = rec[5];
+  y0[0] = a0.x; y0[1] = a0.y; y0[2] = a1.x; y0[3] = a1.y;
+  y1[0] = b0.x; y1[1] = b0.y; y1[2] = b1.x; y1[3] = b1.y;
+  y2[0] = c0.x; y2[1] = c0.y; y2[2] = c1.x; y2[3] = c1.y;
+}
+
+// table[c] = [A_c (12) | pad]  or  [A_c (12) | B_c (12) | pad]
+__global__ void __launch_bounds__(kBlock)
+k_pack_cam_tab(int C, int stride, const double* __restrict__ A, const double* __restrict__ B,
+               double* __restrict__ table) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= C * 14) return;
+  const int c = idx / 14, k = idx % 14;
+  double* r = table + static_cast<size_t>(stride) * c;
+  if (k < 12) {
+    r[k] = A[12 * static_cast<size_t>(c) + k];
+    if (B != nullptr) r[12 + k] = B[12 * static_cast<size_t>(c) + k];
+  } else {
+    r[(B != nullptr ? 24 : 12) + (k - 12)] = 0.0;
+  }
+}
+
+// what every one of these walks shares: the stream, the landmark of the lane, the l_diff partial of the block
+struct WalkBase {
+  static constexpr int kStage = kStagePose;
+  static constexpr int kWarpsPerSm = 16;   // 100 - 128 registers per lane
+  __device__ __forceinline__ bool skip() const { return false; }
+  template <class Lane>
+  __device__ __forceinline__ void init(Lane& st) const {
+    st.lm1 = -2;   // nothing fetched yet
+  }
+  __device__ __forceinline__ void issue(const DeviceIndex& ix, int row, unsigned char* stage,
+                                        unsigned long long* bar) const {
+    issue_cam_uv(ix, row, stage, bar);
+  }
+  __device__ __forceinline__ static double2 uv_of(const unsigned char* stage, int lane) {
+    return reinterpret_cast<const double2*>(stage + 128)[lane];
+  }
+  // The landmark of this lane in slice `sl` and its coordinates (x0 for an idle lane).  The gather X[lm] is
+  // two dependent trips to memory per slice; it is taken off the critical path by running ahead: the index
+  // two slices ahead and the coordinates one slice ahead travel while the current slice is walked.
+  template <class Lane>
+  __device__ __forceinline__ static void open_landmark(Lane& st, const DeviceIndex& ix, const double* __restrict__ X,
+                                                       int sl, int lane, int last, double x0) {
+    const int* lmp = ix.sell_lm + kSellWidth * static_cast<size_t>(sl) + lane;
+    if (st.lm1 == -2) {   // first slice of the warp (every lane starts with -2)
+      st.lm1 = __ldcs(lmp);
+      st.lm2 = sl < last ? __ldcs(lmp + kSellWidth) : -1;
+      fetch(X, st.lm1, x0, st.x1);
+    }
+    st.lm = st.lm1;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) st.x[k] = st.x1[k];
+    st.lm1 = st.lm2;
+    fetch(X, st.lm1, x0, st.x1);
+    st.lm2 = sl + 2 <= last ? __ldcs(lmp + 2 * kSellWidth) : -1;
+  }
+  __device__ __forceinline__ static void fetch(const double* __restrict__ X, int lm, double x0, double (&x)[4]) {
+    if (lm >= 0) {
+      load_lm4(X, lm, x);
+    } else {
+      x[0] = x0;
+      x[1] = x[2] = x[3] = 0.0;
+    }
+  }
+  __device__ __forceinline__ static void block_sum_to(double v, double* __restrict__ out) {
+    __shared__ double smem[32];
+    double ld[1] = {v};
+    block_reduce<1>(ld, smem);
+    if (threadIdx.x == 0) out[blockIdx.x] = ld[0];
+  }
+};
+
+// k_lin_long for the sliced-ELL landmarks: sum_i w Jl_raw^T Jl_raw, sum_i w Jl_raw^T r, column scales
+template <bool JOINT>
+struct LinLandmarkOp : WalkBase {
+  static constexpr int kRec = kCamTab1;
+  static constexpr int NV = JOINT ? 14 : 9;
+  const double* X;
+  double c1, c2;
+  Robust rb;
+  double eps;
+  int scale_jl;
+  double* lm_hraw;
+  double* lm_graw;
+  double* lm_scale;
+  int* flags;
+  double* sell_d;   // step 2: what the term kernels stream, [row][3][32]
+  double* sell_w;   // step 1 with HUBER: [row][32]
+
+  struct Lane {
+    int lm, lm1, lm2;
+    bool bad;
+    double x[4], x1[4], acc[NV];
+  };
+
+  __device__ __forceinline__ void open(Lane& st, const DeviceIndex& ix, int sl, int lane, int last) const {
+    open_landmark(st, ix, X, sl, lane, last, 0.0);
+    st.bad = false;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) st.acc[k] = 0.0;
+  }
+
+  __device__ __forceinline__ void obs(Lane& st, const double2* __restrict__ rec, const unsigned char* stage, int lane,
+                                      int row) const {
+    Cam3x4 cam;
+    rec_cam(rec, cam);
+    const double2 uv = uv_of(stage, lane);
+    if (JOINT) {
+      JointObs ob;
+      ob.eval(cam, uv.x, uv.y, st.x, rb);
+      double j0[4], j1[4];
+      ob.jl_rows(cam, j0, j1);
+      const double w = ob.sw * ob.sw;
+      double* sp = sell_d + 3 * kSellWidth * static_cast<size_t>(row) + lane;
+      sp[0] = ob.sw * ob.iz;
+      sp[kSellWidth] = ob.sw * ob.d02;
+      sp[2 * kSellWidth] = ob.sw * ob.d12;
+      int n = 0;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+#pragma unroll
+        for (int b2 = a; b2 < 4; ++b2) st.acc[n++] += w * (j0[a] * j0[b2] + j1[a] * j1[b2]);
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a) st.acc[10 + a] += w * (j0[a] * ob.r[0] + j1[a] * ob.r[1]);
+      st.bad = st.bad || !(isfinite(ob.r[0]) && isfinite(ob.r[1]) && isfinite(ob.iz) && isfinite(ob.d02) &&
+                           isfinite(ob.d12));
+    } else {
+      PoseObs ob;
+      ob.eval(cam, uv.x, uv.y, st.x, c1, c2, rb);
+      const double w = ob.sw * ob.sw;
+      if (sell_w != nullptr) sell_w[kSellWidth * static_cast<size_t>(row) + lane] = w;
+      int n = 0;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int b2 = a; b2 < 3; ++b2) {
+          st.acc[n++] += w * (ob.T[0][a] * ob.T[0][b2] + ob.T[1][a] * ob.T[1][b2] + ob.T[2][a] * ob.T[2][b2] +
+                              ob.T[3][a] * ob.T[3][b2]);
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        st.acc[6 + a] += w * (ob.T[0][a] * ob.r[0] + ob.T[1][a] * ob.r[1] + ob.T[2][a] * ob.r[2] +
+                              ob.T[3][a] * ob.r[3]);
+      }
+      st.bad = st.bad || !(isfinite(ob.r[0]) && isfinite(ob.r[1]) && isfinite(ob.r[2]) && isfinite(ob.r[3]));
+    }
+  }
+
+  __device__ __forceinline__ void close(Lane& st, const DeviceIndex&, int, int) const {
+    if (st.lm < 0) return;
+    double* h = lm_hraw + 10 * static_cast<size_t>(st.lm);
+    double* g = lm_graw + 4 * static_cast<size_t>(st.lm);
+    double* s = lm_scale + 4 * static_cast<size_t>(st.lm);
+    if (JOINT) {
+#pragma unroll
+      for (int k = 0; k < 10; ++k) h[k] = st.acc[k];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) g[k] = st.acc[10 + k];
+      s[0] = 1.0 / (eps + sqrt(st.acc[0]));
+      s[1] = 1.0 / (eps + sqrt(st.acc[4]));
+      s[2] = 1.0 / (eps + sqrt(st.acc[7]));
+      s[3] = 1.0 / (eps + sqrt(st.acc[9]));
+    } else {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) h[k] = st.acc[k];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) g[k] = st.acc[6 + k];
+      g[3] = 0.0;
+      s[0] = scale_jl ? 1.0 / (eps + sqrt(st.acc[0])) : 1.0;
+      s[1] = scale_jl ? 1.0 / (eps + sqrt(st.acc[3])) : 1.0;
+      s[2] = scale_jl ? 1.0 / (eps + sqrt(st.acc[5])) : 1.0;
+      s[3] = 1.0;
+    }
+    bool fin = isfinite(st.x[0]) && isfinite(st.x[1]) && isfinite(st.x[2]) && isfinite(st.x[3]);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) fin = fin && isfinite(st.acc[k]);
+    if (st.bad || !fin) atomicOr(flags, 1);
+  }
+
+  __device__ __forceinline__ void finish(Lane&, const DeviceIndex&, const CamWindow&, const double*) const {}
+};
+
+// VarPro back-substitution, first walk (table [P_new]): the closed-form landmark step at the new cameras,
+//   il = -(sum_i T^T T)^-1 sum_i T^T r   (landmark_block.hpp:670-690, no robust weight, helper.cpp:382-454),
+// kept in lm_step; X is updated by the second walk, which still needs the old landmark
+struct BacksubVarproStepOp : WalkBase {
+  static constexpr int kRec = kCamTab1;
+  const double* X;
+  double c1, c2;
+  double* lm_step;   // [L*4]
+
+  struct Lane {
+    int lm, lm1, lm2;
+    double x[4], x1[4], acc[9];
+  };
+
+  __device__ __forceinline__ void open(Lane& st, const DeviceIndex& ix, int sl, int lane, int last) const {
+    open_landmark(st, ix, X, sl, lane, last, 0.0);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) st.acc[k] = 0.0;
+  }
+
+  __device__ __forceinline__ void obs(Lane& st, const double2* __restrict__ rec, const unsigned char* stage, int lane,
+                                      int) const {
+    Cam3x4 cam;
+    rec_cam(rec, cam);
+    const double2 uv = uv_of(stage, lane);
+    const Robust none = {NORM_NONE, 1.0};
+    PoseObs ob;
+    ob.eval(cam, uv.x, uv.y, st.x, c1, c2, none);
+    int n = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+      for (int b2 = a; b2 < 3; ++b2) {
+        st.acc[n++] += ob.T[0][a] * ob.T[0][b2] + ob.T[1][a] * ob.T[1][b2] + ob.T[2][a] * ob.T[2][b2] +
+                       ob.T[3][a] * ob.T[3][b2];
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      st.acc[6 + a] += ob.T[0][a] * ob.r[0] + ob.T[1][a] * ob.r[1] + ob.T[2][a] * ob.r[2] + ob.T[3][a] * ob.r[3];
+    }
+  }
+
+  __device__ __forceinline__ void close(Lane& st, const DeviceIndex&, int, int) const {
+    if (st.lm < 0) return;
+    double hll[6], inv[6], tmp[3], il[3];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) hll[k] = st.acc[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) tmp[k] = st.acc[6 + k];
+    inv3_sym(hll, inv);
+    sym3_mul(inv, tmp, il);
+    double2* out = reinterpret_cast<double2*>(lm_step + 4 * static_cast<size_t>(st.lm));
+    out[0] = make_double2(-il[0], -il[1]);
+    out[1] = make_double2(-il[2], 0.0);
+  }
+
+  __device__ __forceinline__ void finish(Lane&, const DeviceIndex&, const CamWindow&, const double*) const {}
+};
+
+// VarPro back-substitution, second walk (table [P_old | inc]): the model decrease with the Jacobians and
+// residuals of the linearisation point and the fresh Jp (landmark_block.hpp:691-707), then X += il
+struct BacksubVarproDiffOp : WalkBase {
+  static constexpr int kRec = kCamTab2;
+  double* X;
+  double c1, c2;
+  Robust rb;
+  const double* lm_scale;
+  const double* lm_hraw;
+  const double* lm_step;
+  double* scalar_part;
+
+  struct Lane {
+    int lm, lm1, lm2;
+    double ld;
+    double x[4], x1[4], A, B[3];
+  };
+
+  __device__ __forceinline__ void init(Lane& st) const {
+    WalkBase::init(st);
+    st.ld = 0.0;
+  }
+
+  __device__ __forceinline__ void open(Lane& st, const DeviceIndex& ix, int sl, int lane, int last) const {
+    open_landmark(st, ix, X, sl, lane, last, 0.0);
+    if (st.lm >= 0) {   // what close() gathers, towards L2
+      prefetch_l2(lm_scale + 4 * static_cast<size_t>(st.lm));
+      prefetch_l2(lm_step + 4 * static_cast<size_t>(st.lm));
+      prefetch_l2(lm_hraw + 10 * static_cast<size_t>(st.lm));
+    }
+    st.A = 0.0;
+    st.B[0] = st.B[1] = st.B[2] = 0.0;
+  }
+
+  __device__ __forceinline__ void obs(Lane& st, const double2* __restrict__ rec, const unsigned char* stage, int lane,
+                                      int) const {
+    Cam3x4 cam_old;
+    rec_cam(rec, cam_old);
+    double i0[4], i1[4], i2[4], jp[4];
+    rec_vec12(rec + 6, i0, i1, i2);
+    const double2 uv = uv_of(stage, lane);
+    pose_jp_mul(st.x, uv.x, uv.y, c1, c2, i0, i1, i2, jp);   // fresh, unscaled, unweighted Jp
+    PoseObs old;
+    old.eval(cam_old, uv.x, uv.y, st.x, c1, c2, rb);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const double e = old.sw * old.r[q];
+      st.A += jp[q] * (0.5 * jp[q] + e);
+      const double t = old.sw * (jp[q] + e);
+      st.B[0] += old.T[q][0] * t;
+      st.B[1] += old.T[q][1] * t;
+      st.B[2] += old.T[q][2] * t;
+    }
+  }
+
+  __device__ __forceinline__ void close(Lane& st, const DeviceIndex&, int, int) const {
+    if (st.lm < 0) return;
+    double s[4], il[4], d[3], hd[3];
+    load_lm4(lm_scale, st.lm, s);
+    load_lm4(lm_step, st.lm, il);
+    const double* h = lm_hraw + 10 * static_cast<size_t>(st.lm);
+    const double hs[6] = {h[0], h[1], h[2], h[3], h[4], h[5]};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) d[k] = s[k] * il[k];
+    sym3_mul(hs, d, hd);
+    st.ld -= st.A + (d[0] * st.B[0] + d[1] * st.B[1] + d[2] * st.B[2]) +
+             0.5 * (d[0] * hd[0] + d[1] * hd[1] + d[2] * hd[2]);
+    double2* xo = reinterpret_cast<double2*>(X + 4 * static_cast<size_t>(st.lm));
+    xo[0] = make_double2(st.x[0] + il[0], st.x[1] + il[1]);
+    xo[1] = make_double2(st.x[2] + il[2], st.x[3]);
+  }
+
+  __device__ __forceinline__ void finish(Lane& st, const DeviceIndex&, const CamWindow&, const double*) const {
+    block_sum_to(st.ld, scalar_part);
+  }
+};
+
+// PoBA (landmark_block.hpp:625-656) and joint (:574-623) back-substitution (table [P | y]): stored scaled
+// Jacobians and residuals at the linearisation point, which is the current state
+template <bool JOINT>
+struct BacksubLinPointOp : WalkBase {
+  static constexpr int kRec = kCamTab2;
+  static constexpr int NA = JOINT ? 4 : 3;
+  double* X;
+  double c1, c2;
+  Robust rb;
+  const double* lm_scale;
+  const double* hll_inv;
+  const double* lm_hraw;
+  double* scalar_part;
+
+  struct Lane {
+    int lm, lm1, lm2;
+    double ld;
+    double x[4], x1[4], S0, acc[NA];
+  };
+
+  __device__ __forceinline__ void init(Lane& st) const {
+    WalkBase::init(st);
+    st.ld = 0.0;
+  }
+
+  __device__ __forceinline__ void open(Lane& st, const DeviceIndex& ix, int sl, int lane, int last) const {
+    open_landmark(st, ix, X, sl, lane, last, 1.0);   // x0 = 1 keeps the reflector of an idle lane well defined
+    if (st.lm >= 0) {   // what close() gathers, towards L2
+      prefetch_l2(lm_scale + 4 * static_cast<size_t>(st.lm));
+      prefetch_l2(hll_inv + 6 * static_cast<size_t>(st.lm));
+      prefetch_l2(lm_hraw + 10 * static_cast<size_t>(st.lm));
+    }
+    st.S0 = 0.0;
+#pragma unroll
+    for (int k = 0; k < NA; ++k) st.acc[k] = 0.0;
+  }
+
+  __device__ __forceinline__ void obs(Lane& st, const double2* __restrict__ rec, const unsigned char* stage, int lane,
+                                      int) const {
+    Cam3x4 cam;
+    rec_cam(rec, cam);
+    double y0[4], y1[4], y2[4];
+    rec_vec12(rec + 6, y0, y1, y2);
+    const double2 uv = uv_of(stage, lane);
+    if (JOINT) {
+      JointObs ob;
+      ob.eval(cam, uv.x, uv.y, st.x, rb);
+      double a[2], j0[4], j1[4];
+      ob.jp_mul(st.x, y0, y1, y2, a);
+      ob.jl_rows(cam, j0, j1);
+      const double ea0 = ob.sw * a[0], ea1 = ob.sw * a[1], er0 = ob.sw * ob.r[0], er1 = ob.sw * ob.r[1];
+      st.S0 += ea0 * (0.5 * ea0 + er0) + ea1 * (0.5 * ea1 + er1);
+      const double e0 = er0 + ea0, e1 = er1 + ea1;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) st.acc[k] += ob.sw * (j0[k] * e0 + j1[k] * e1);
+    } else {
+      PoseObs ob;
+      ob.eval(cam, uv.x, uv.y, st.x, c1, c2, rb);
+      double a[4];
+      pose_jp_mul(st.x, uv.x, uv.y, c1, c2, y0, y1, y2, a);
+      double e[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const double ea = ob.sw * a[q], er = ob.sw * ob.r[q];
+        st.S0 += ea * (0.5 * ea + er);
+        e[q] = er + ea;
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        st.acc[k] += ob.sw * (ob.T[0][k] * e[0] + ob.T[1][k] * e[1] + ob.T[2][k] * e[2] + ob.T[3][k] * e[3]);
+      }
+    }
+  }
+
+  __device__ __forceinline__ void close(Lane& st, const DeviceIndex&, int, int) const {
+    if (st.lm < 0) return;
+    double s[4], inv[6];
+    load_lm4(lm_scale, st.lm, s);
+    {
+      const double* hi = hll_inv + 6 * static_cast<size_t>(st.lm);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) inv[k] = hi[k];
+    }
+    const double* h = lm_hraw + 10 * static_cast<size_t>(st.lm);
+    double dl[4];   // the landmark increment in raw coordinates
+    if (JOINT) {
+      Reflector<4> pi;
+      pi.make(st.x);
+      double sg[4], t3[3], i3[3], i4[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) sg[k] = s[k] * st.acc[k];
+      pi.apply_t(sg, t3);
+      sym3_mul(inv, t3, i3);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) i3[k] = -i3[k];
+      pi.apply(i3, i4);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) dl[k] = s[k] * i4[k];
+      // dl^T H dl with the packed symmetric 4x4 of the linearisation
+      double hd[4];
+      hd[0] = h[0] * dl[0] + h[1] * dl[1] + h[2] * dl[2] + h[3] * dl[3];
+      hd[1] = h[1] * dl[0] + h[4] * dl[1] + h[5] * dl[2] + h[6] * dl[3];
+      hd[2] = h[2] * dl[0] + h[5] * dl[1] + h[7] * dl[2] + h[8] * dl[3];
+      hd[3] = h[3] * dl[0] + h[6] * dl[1] + h[8] * dl[2] + h[9] * dl[3];
+      double da = 0.0;
+#pragma unroll
+      for (int k = 0; k < NA; ++k) da += dl[k] * st.acc[k];
+      st.ld -= st.S0 + da + 0.5 * dot4(dl, hd);
+    } else {
+      double sg[3], il[3], hd[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) sg[k] = s[k] * st.acc[k];
+      sym3_mul(inv, sg, il);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) dl[k] = -s[k] * il[k];
+      dl[3] = 0.0;
+      const double hs[6] = {h[0], h[1], h[2], h[3], h[4], h[5]};
+      const double d3[3] = {dl[0], dl[1], dl[2]};
+      sym3_mul(hs, d3, hd);
+      st.ld -= st.S0 + (dl[0] * st.acc[0] + dl[1] * st.acc[1] + dl[2] * st.acc[2]) +
+               0.5 * (dl[0] * hd[0] + dl[1] * hd[1] + dl[2] * hd[2]);
+    }
+    double2* xo = reinterpret_cast<double2*>(X + 4 * static_cast<size_t>(st.lm));
+    xo[0] = make_double2(st.x[0] + dl[0], st.x[1] + dl[1]);
+    xo[1] = make_double2(st.x[2] + dl[2], st.x[3] + dl[3]);
+  }
+
+  __device__ __forceinline__ void finish(Lane& st, const DeviceIndex&, const CamWindow&, const double*) const {
+    block_sum_to(st.ld, scalar_part);
+  }
+};
+
 // create_homogeneous_landmark, landmark part (bal_bundle_adjustment.cpp:546-549): the 4th entry is
 // already 1 in step-1 storage, written explicitly for clarity
 __global__ void k_to_homogeneous(int L, double* __restrict__ X) {
@@ -801,12 +1257,12 @@ __global__ void k_normalize_lms(int L, double* __restrict__ X) {
   x[3] = w / w;
 }
 
-inline int tile_grid(const DeviceState& d) {
+// blocks of the k_*_long kernels: one warp per landmark with more than 32 observations
+inline int long_grid(const DeviceState& d) {
   const int warps_per_block = kBlock / 32;
-  long long blocks = (static_cast<long long>(d.ix.num_tiles) + warps_per_block - 1) / warps_per_block;
-  const long long cap = static_cast<long long>(sm_count()) * 8 * 4;   // a few waves of 8 resident blocks per SM
+  long long blocks = (static_cast<long long>(d.ix.num_long) + warps_per_block - 1) / warps_per_block;
+  const long long cap = static_cast<long long>(sm_count()) * 8;
   if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
   return static_cast<int>(blocks);
 }
 
@@ -823,7 +1279,27 @@ int cost_blocks(const DeviceState& d) {
   return static_cast<int>(blocks);
 }
 
-int scalar_blocks(const DeviceState& d) { return tile_grid(d); }
+// l_diff partials: [blocks of the long kernel | blocks of the walk]
+int scalar_blocks(const DeviceState& d) { return long_grid(d) + d.plan[4].blocks + d.plan[3].blocks; }
+
+namespace {
+
+// table of a once-per-trial walk: [A | pad] (B == nullptr) or [A | B | pad] per camera
+void pack_cam_tab(const DeviceState& d, const double* A, const double* B, const LaunchCfg& lc) {
+  const int n = d.ix.C * 14;
+  k_pack_cam_tab<<<(n + kBlock - 1) / kBlock, kBlock, 0, lc.stream>>>(d.ix.C, B != nullptr ? kCamTab2 : kCamTab1, A, B,
+                                                                     d.cam_tab);
+  count(lc);
+}
+
+// sum of the l_diff partials of the long kernel (`long_blocks`) and of the walk (`walked`: it ran)
+void finish_l_diff(const DeviceState& d, int long_blocks, bool walked, const LaunchCfg& lc) {
+  const int walk_blocks = walked ? d.plan[4].blocks : 0;   // written behind the long kernel's partials
+  k_scalar_final<<<1, kBlock, 0, lc.stream>>>(long_blocks + walk_blocks, d.scalar_part, d.trial_out + 8);
+  count(lc);
+}
+
+}  // namespace
 
 void launch_init_varproj(const DeviceState& d, const ModelParams& mp, const LaunchCfg& lc) {
   const int blocks = (d.ix.L + kBlock - 1) / kBlock;
@@ -855,17 +1331,30 @@ void launch_cost(const DeviceState& d, const ModelParams& mp, bool joint, const 
 void launch_lin_landmark(const DeviceState& d, const ModelParams& mp, bool joint, bool scale_jl,
                          const LaunchCfg& lc) {
   const Robust rb = {mp.robust_norm, mp.huber};
-  const int blocks = tile_grid(d);
+  double* sw = mp.robust_norm == NORM_HUBER ? d.sell_w : nullptr;
+  if (d.plan[3].blocks > 0) {
+    pack_cam_tab(d, d.P, nullptr, lc);
+    if (joint) {
+      const LinLandmarkOp<true> op{{}, d.X, mp.c1, mp.c2, rb, mp.jacobi_eps, 1, d.lm_hraw, d.lm_graw, d.lm_scale,
+                                   d.flags, d.sell_d, nullptr};
+      if (launch_sell_walk(d.ix, d.plan[3], d.debug_window_cams, d.cam_tab, op, lc.stream)) count(lc);
+    } else {
+      const LinLandmarkOp<false> op{{}, d.X, mp.c1, mp.c2, rb, mp.jacobi_eps, scale_jl ? 1 : 0, d.lm_hraw, d.lm_graw,
+                                    d.lm_scale, d.flags, nullptr, sw};
+      if (launch_sell_walk(d.ix, d.plan[3], d.debug_window_cams, d.cam_tab, op, lc.stream)) count(lc);
+    }
+  }
+  const int blocks = long_grid(d);
+  if (blocks == 0) return;
   if (joint) {
-    k_lin_landmark<true><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.X, mp.c1, mp.c2, rb, mp.jacobi_eps, 1,
-                                                           d.lm_hraw, d.lm_graw, d.lm_scale, d.flags,
-                                                           d.obs_d, nullptr, d.sell_d, nullptr);
+    k_lin_long<true><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.X, mp.c1, mp.c2, rb, mp.jacobi_eps, 1, d.lm_hraw,
+                                                       d.lm_graw, d.lm_scale, d.flags, d.obs_d, nullptr, d.sell_d,
+                                                       nullptr);
   } else {
-    k_lin_landmark<false><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.X, mp.c1, mp.c2, rb, mp.jacobi_eps,
-                                                            scale_jl ? 1 : 0, d.lm_hraw, d.lm_graw,
-                                                            d.lm_scale, d.flags, nullptr,
-                                                            mp.robust_norm == NORM_HUBER ? d.obs_w : nullptr,
-                                                            nullptr, d.sell_w);
+    k_lin_long<false><<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.X, mp.c1, mp.c2, rb, mp.jacobi_eps,
+                                                        scale_jl ? 1 : 0, d.lm_hraw, d.lm_graw, d.lm_scale, d.flags,
+                                                        nullptr, mp.robust_norm == NORM_HUBER ? d.obs_w : nullptr,
+                                                        nullptr, d.sell_w);
   }
   count(lc);
 }
@@ -883,34 +1372,65 @@ void launch_prep_landmark(const DeviceState& d, bool joint, double lambda_lm, co
   count(lc);
 }
 
+// d.P: the updated cameras, d.P_bak: those of the linearisation point
 void launch_backsub_varpro(const DeviceState& d, const ModelParams& mp, const double* inc,
                            const LaunchCfg& lc) {
   const Robust rb = {mp.robust_norm, mp.huber};
-  const int blocks = tile_grid(d);
-  k_backsub_varpro<<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.P_bak, d.X, inc, mp.c1, mp.c2, rb,
-                                                     d.lm_scale, d.scalar_part);
-  k_scalar_final<<<1, kBlock, 0, lc.stream>>>(blocks, d.scalar_part, d.trial_out + 8);
-  count(lc, 2);
+  const int blocks = long_grid(d);
+  if (blocks > 0) {
+    k_backsub_varpro_long<<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.P_bak, d.X, inc, mp.c1, mp.c2, rb,
+                                                            d.lm_scale, d.scalar_part);
+    count(lc);
+  }
+  bool walked = false;
+  if (d.plan[3].blocks > 0) {
+    pack_cam_tab(d, d.P, nullptr, lc);
+    const BacksubVarproStepOp step{{}, d.X, mp.c1, mp.c2, d.lm_step};
+    if (launch_sell_walk(d.ix, d.plan[3], d.debug_window_cams, d.cam_tab, step, lc.stream)) count(lc);
+    pack_cam_tab(d, d.P_bak, inc, lc);
+    const BacksubVarproDiffOp diff{{}, d.X, mp.c1, mp.c2, rb, d.lm_scale, d.lm_hraw, d.lm_step, d.scalar_part + blocks};
+    walked = launch_sell_walk(d.ix, d.plan[4], d.debug_window_cams, d.cam_tab, diff, lc.stream);
+    if (walked) count(lc);
+  }
+  finish_l_diff(d, blocks, walked, lc);
 }
 
 void launch_backsub_poba(const DeviceState& d, const ModelParams& mp, const double* y,
                          const LaunchCfg& lc) {
   const Robust rb = {mp.robust_norm, mp.huber};
-  const int blocks = tile_grid(d);
-  k_backsub_poba<<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.X, y, mp.c1, mp.c2, rb, d.lm_scale,
-                                                   d.hll_inv, d.scalar_part);
-  k_scalar_final<<<1, kBlock, 0, lc.stream>>>(blocks, d.scalar_part, d.trial_out + 8);
-  count(lc, 2);
+  const int blocks = long_grid(d);
+  if (blocks > 0) {
+    k_backsub_poba_long<<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.X, y, mp.c1, mp.c2, rb, d.lm_scale, d.hll_inv,
+                                                          d.scalar_part);
+    count(lc);
+  }
+  bool walked = false;
+  if (d.plan[4].blocks > 0) {
+    pack_cam_tab(d, d.P, y, lc);
+    const BacksubLinPointOp<false> op{{}, d.X, mp.c1, mp.c2, rb, d.lm_scale, d.hll_inv, d.lm_hraw, d.scalar_part + blocks};
+    walked = launch_sell_walk(d.ix, d.plan[4], d.debug_window_cams, d.cam_tab, op, lc.stream);
+    if (walked) count(lc);
+  }
+  finish_l_diff(d, blocks, walked, lc);
 }
 
 void launch_backsub_joint(const DeviceState& d, const ModelParams& mp, const double* y,
                           const LaunchCfg& lc) {
   const Robust rb = {mp.robust_norm, mp.huber};
-  const int blocks = tile_grid(d);
-  k_backsub_joint<<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.X, y, rb, d.lm_scale, d.hll_inv,
-                                                    d.scalar_part);
-  k_scalar_final<<<1, kBlock, 0, lc.stream>>>(blocks, d.scalar_part, d.trial_out + 8);
-  count(lc, 2);
+  const int blocks = long_grid(d);
+  if (blocks > 0) {
+    k_backsub_joint_long<<<blocks, kBlock, 0, lc.stream>>>(d.ix, d.P, d.X, y, rb, d.lm_scale, d.hll_inv,
+                                                           d.scalar_part);
+    count(lc);
+  }
+  bool walked = false;
+  if (d.plan[4].blocks > 0) {
+    pack_cam_tab(d, d.P, y, lc);
+    const BacksubLinPointOp<true> op{{}, d.X, mp.c1, mp.c2, rb, d.lm_scale, d.hll_inv, d.lm_hraw, d.scalar_part + blocks};
+    walked = launch_sell_walk(d.ix, d.plan[4], d.debug_window_cams, d.cam_tab, op, lc.stream);
+    if (walked) count(lc);
+  }
+  finish_l_diff(d, blocks, walked, lc);
 }
 
 void launch_to_homogeneous(const DeviceState& d, const LaunchCfg& lc) {

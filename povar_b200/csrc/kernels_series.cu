@@ -24,6 +24,7 @@
 
 #include "device_math.cuh"
 #include "povar_internal.h"
+#include "sell_walk.cuh"
 
 namespace povar {
 
@@ -38,10 +39,6 @@ inline void count(const LaunchCfg& lc, int n = 1) {
 
 __device__ __forceinline__ double2 ldg2(const double* __restrict__ p) {
   return __ldg(reinterpret_cast<const double2*>(p));
-}
-
-__device__ __forceinline__ void prefetch_l2(const void* p) {
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
 // m = K^T W K q for the step-1 model (pose_jp_mul followed by pose_jpT_coef)
@@ -68,59 +65,11 @@ struct ObsCoef {
 };
 
 // ------------------------------------------------------------------------------------------
-// landmark half, sliced-ELL order (DeviceIndex::slice_ptr ...): a warp walks a contiguous range of slices;
-// a slice is 32 landmarks of (nearly) equal degree, one per lane; the lane visits the observations of its
-// landmark in camera order and keeps G_l in registers: no tile table, no reduction, no exchange.
-//
-// Everything the inner loop reads comes from shared memory, put there by the TMA unit (cp.async.bulk +
-// mbarrier: no registers and no scoreboards are tied up while the data travels):
-//   * the camera records.  The landmarks are ordered by the centre of their cameras, so the slices of one
-//     block meet a WINDOW of cameras (LmPlan::blk_lo, made on the host from the exact camera ranges of the
-//     block's slices); the block stages the records of that window once, and every lane reads the record of
-//     its observation's camera with LDS.128.  A camera outside the window (only when the window a block
-//     needs does not fit; never for a small C) is read from global memory, so the result does not depend on
-//     the window;
-//   * the observation stream (camera index and model coefficients, 640 or 896 bytes per row of 32 slots): every
-//     warp owns a ring of `stages` rows; one lane refills the stage of row r with row r + stages as soon as the
-//     warp has used it.  Round 2's first version kept the next rows in registers: the compiler placed the
-//     scoreboard waits of those loads at the head of the loop, so the latency of the stream was exposed in
-//     every iteration (54 % of the stall samples, profiles/r2_summary.md).
-// The ranges have equal numbers of ROWS (LmPlan::range_slice), one wave of warps: every block carries the
-// same load.  The per-slice landmark data (X, fold) are read from lane-major copies packed once per solve
-// (k_sell_pack): one coalesced line per component; they are pulled into L2 one slice ahead.
+// landmark half: the sliced-ELL walk of sell_walk.cuh with the camera records [y_c | M_c] (CamRec) staged per
+// block and the stream [camera index | (u, v) (| w)] resp. [camera index | d] in the per-warp rings.  The
+// per-slice landmark data (X, fold) are read from lane-major copies packed once per solve (k_sell_pack): one
+// coalesced line per component; they are pulled into L2 one slice ahead.
 // ------------------------------------------------------------------------------------------
-struct CamWindow {
-  const double* smem;   // records of cameras lo .. lo + n - 1
-  int lo, n;
-};
-
-__device__ __forceinline__ unsigned smem_u32(const void* p) {
-  return static_cast<unsigned>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
-  unsigned done = 0;
-  while (!done) {
-    asm volatile(
-        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(phase)
-        : "memory");
-  }
-}
-
 // G += M^T (K^T W K) (Y x) for one observation whose camera record is `rec` (shared or global memory)
 template <bool JOINT>
 __device__ __forceinline__ void landmark_obs(const double2* __restrict__ rec, const double (&x)[4], const ObsCoef& k,
@@ -224,169 +173,106 @@ __device__ __forceinline__ void long_landmark_warp(const DeviceIndex& ix, const 
   if (lane < 4) lm_rec[kLmRec * static_cast<size_t>(lm) + 4 + lane] = lane == 0 ? H[0] : (lane == 1 ? H[1] : (lane == 2 ? H[2] : H[3]));
 }
 
-// one row of the observation stream into a stage of the warp's ring (called by one lane)
 template <bool JOINT, bool HASW>
-__device__ __forceinline__ void issue_stage(const DeviceIndex& ix, const double* __restrict__ sell_d,
-                                            const double* __restrict__ sell_w, int row, unsigned char* stage,
-                                            unsigned long long* bar) {
-  constexpr unsigned kStage = (JOINT || HASW) ? kStageWide : kStagePose;
-  const size_t slot = kSellWidth * static_cast<size_t>(row);
-  mbar_expect_tx(bar, kStage);
-  bulk_copy_g2s(stage, ix.sell_cam + slot, 128u, bar);
-  if (JOINT) {
-    bulk_copy_g2s(stage + 128, sell_d + 3 * slot, 768u, bar);
-  } else {
-    bulk_copy_g2s(stage + 128, ix.sell_uv + slot, 512u, bar);
-    if (HASW) bulk_copy_g2s(stage + 640, sell_w + slot, 256u, bar);
-  }
-}
+struct E0LandmarkOp {
+  static constexpr int kRec = CamRec::stride(JOINT);
+  static constexpr int kStage = (JOINT || HASW) ? kStageWide : kStagePose;
+  static constexpr int kWarpsPerSm = 32;
+  static_assert(kRec == (JOINT ? kCamRecJoint : kCamRecPose), "plan_landmark_half sizes the window with these");
+  const double* X;
+  const double* sell_d;
+  const double* sell_w;
+  double c1, c2;
+  const double* lm_fold;
+  const double* sell_x;
+  const double* sell_fold;
+  double* lm_rec;
+  const double* obs_d;
+  const double* obs_w;
+  const SeriesCtl* ctl;
 
-template <bool JOINT, bool HASW, int W, int D, int BPS>
-__global__ void __launch_bounds__(32 * W, BPS)
-k_e0_landmark_sell(DeviceIndex ix, LmPlan plan, int win_cams, const double* __restrict__ X,
-                   const double* __restrict__ cam_rec, const double* __restrict__ sell_d,
-                   const double* __restrict__ sell_w, double c1, double c2, const double* __restrict__ lm_fold,
-                   const double* __restrict__ sell_x, const double* __restrict__ sell_fold,
-                   double* __restrict__ lm_rec, const double* __restrict__ obs_d,
-                   const double* __restrict__ obs_w, const SeriesCtl* __restrict__ ctl) {
-  extern __shared__ __align__(128) unsigned char lm_smem[];
-  if (ctl != nullptr && ctl->done) return;
-  constexpr int kStage = (JOINT || HASW) ? kStageWide : kStagePose;
-  constexpr int kStride = CamRec::stride(JOINT);
-  static_assert(kStride == (JOINT ? kCamRecJoint : kCamRecPose), "plan_landmark_half sizes the window with these");
-  constexpr int kBars = lm_bar_bytes(W, D);
-  const int lane = threadIdx.x & 31;
-  const int wib = threadIdx.x >> 5;
-  const int range = static_cast<int>(blockIdx.x) * W + wib;
-  // shared memory: [mbarriers: window, then D per warp][rings][window]
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(lm_smem);
-  unsigned long long* my_bars = bars + 1 + wib * D;
-  unsigned char* my_ring = lm_smem + kBars + static_cast<size_t>(wib) * D * kStage;
-  CamWindow win;
-  win.smem = reinterpret_cast<const double*>(lm_smem + kBars + static_cast<size_t>(W) * D * kStage);
-  win.n = min(win_cams, ix.C);
-  win.lo = min(__ldg(plan.blk_lo + blockIdx.x), ix.C - win.n);
-  if (threadIdx.x == 0) mbar_init(&bars[0], 1);
-  if (lane == 0) {
-#pragma unroll
-    for (int s = 0; s < D; ++s) mbar_init(&my_bars[s], 1);
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned bytes = static_cast<unsigned>(win.n) * (kStride * 8);
-    mbar_expect_tx(&bars[0], bytes);
-    const char* src = reinterpret_cast<const char*>(cam_rec + kStride * static_cast<size_t>(win.lo));
-    char* dst = reinterpret_cast<char*>(const_cast<double*>(win.smem));
-    for (unsigned off = 0; off < bytes; off += 32768u) {
-      bulk_copy_g2s(dst + off, src + off, min(32768u, bytes - off), &bars[0]);
-    }
-  }
-  int s0 = 0, s1 = 0;
-  if (range < plan.ranges) {
-    s0 = __ldg(plan.range_slice + range);
-    s1 = __ldg(plan.range_slice + range + 1);
-  }
-  if (s0 < s1) {
-    const int row_first = __ldg(ix.slice_ptr + s0);
-    const int row_end = __ldg(ix.slice_ptr + s1);        // one past the last row of this warp
-    if (lane == 0) {
-#pragma unroll
-      for (int s = 0; s < D; ++s) {
-        if (row_first + s < row_end) {
-          issue_stage<JOINT, HASW>(ix, sell_d, sell_w, row_first + s, my_ring + s * kStage, &my_bars[s]);
-        }
-      }
-    }
-    // first rows after the slices of this warp, 32 at a time: lane j keeps the one of slice hdr_base + j
-    int hdr_base = s0;
-    int hdr = __ldg(ix.slice_ptr + min(s0 + lane, s1 - 1) + 1);
-    int sl = s0, row1 = 0, lm = -1;
+  struct Lane {
+    int lm;
     double x[4], G[4];
-    auto open_slice = [&]() {
-      if (sl - hdr_base >= 32) {
-        hdr_base = sl;
-        hdr = __ldg(ix.slice_ptr + min(sl + lane, s1 - 1) + 1);
-      }
-      row1 = __shfl_sync(kFullMask, hdr, sl - hdr_base);
-      lm = __ldcs(ix.sell_lm + kSellWidth * static_cast<size_t>(sl) + lane);
-      const double* xp = sell_x + 4 * kSellWidth * static_cast<size_t>(sl) + lane;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        x[k] = __ldcs(xp + k * kSellWidth);
-        G[k] = 0.0;
-      }
-      // towards L2, one 128-byte line per lane: the fold of this slice (read when it closes) and the
-      // landmarks of the next one
-      constexpr int kFoldLines = JOINT ? 20 : 12;
-      if (lane < kFoldLines) {
-        prefetch_l2(sell_fold + 10 * kSellWidth * static_cast<size_t>(sl) + 16 * lane);
-      } else if (lane - kFoldLines < 8 && sl + 1 < s1) {
-        prefetch_l2(sell_x + 4 * kSellWidth * static_cast<size_t>(sl + 1) + 16 * (lane - kFoldLines));
-      } else if (lane == 31 && sl + 1 < s1) {
-        prefetch_l2(ix.sell_lm + kSellWidth * static_cast<size_t>(sl + 1));
-      }
-    };
-    auto close_slice = [&]() {
-      double F[10], H[4];
-      const double* fp = sell_fold + 10 * kSellWidth * static_cast<size_t>(sl) + lane;
-#pragma unroll
-      for (int i = 0; i < 10; ++i) F[i] = (JOINT || i < 6) ? __ldcs(fp + i * kSellWidth) : 0.0;
-      fold_apply<JOINT>(F, G, H);
-      if (lm >= 0) {
-        double2* out = reinterpret_cast<double2*>(lm_rec + kLmRec * static_cast<size_t>(lm) + 4);
-        __stcs(out, make_double2(H[0], H[1]));
-        __stcs(out + 1, make_double2(H[2], H[3]));
-      }
-      ++sl;
-    };
+  };
 
-    open_slice();
-    mbar_wait(&bars[0], 0);                   // the window is in shared memory
-    unsigned phase = 0;
-    for (int row = row_first; row < row_end; row += D) {
-#pragma unroll
-      for (int i = 0; i < D; ++i) {
-        const int r = row + i;
-        if (r < row_end) {           // warp-uniform
-          const unsigned char* st = my_ring + i * kStage;
-          mbar_wait(&my_bars[i], phase);
-          const int c = reinterpret_cast<const int*>(st)[lane];
-          ObsCoef k;
-          if (JOINT) {
-            const double* dp = reinterpret_cast<const double*>(st + 128) + lane;
-            k.a = dp[0];
-            k.b = dp[kSellWidth];
-            k.c = dp[2 * kSellWidth];
-          } else {
-            const double2 uv = reinterpret_cast<const double2*>(st + 128)[lane];
-            k.a = uv.x;
-            k.b = uv.y;
-            k.c = HASW ? reinterpret_cast<const double*>(st + 640)[lane] : 1.0;
-          }
-          if (r == row1) {           // warp-uniform: the previous slice is complete
-            close_slice();
-            open_slice();
-          }
-          if (c >= 0) landmark_obs_at<JOINT>(win, cam_rec, c, x, k, c1, c2, G);
-          // every lane holds its slot in registers: the stage can take row r + D
-          __syncwarp();
-          if (lane == 0 && r + D < row_end) {
-            issue_stage<JOINT, HASW>(ix, sell_d, sell_w, r + D, my_ring + i * kStage, &my_bars[i]);
-          }
-        }
-      }
-      phase ^= 1u;
+  __device__ __forceinline__ bool skip() const { return ctl != nullptr && ctl->done; }
+  __device__ __forceinline__ void init(Lane&) const {}
+
+  __device__ __forceinline__ void issue(const DeviceIndex& ix, int row, unsigned char* stage,
+                                        unsigned long long* bar) const {
+    const size_t slot = kSellWidth * static_cast<size_t>(row);
+    mbar_expect_tx(bar, kStage);
+    bulk_copy_g2s(stage, ix.sell_cam + slot, 128u, bar);
+    if (JOINT) {
+      bulk_copy_g2s(stage + 128, sell_d + 3 * slot, 768u, bar);
+    } else {
+      bulk_copy_g2s(stage + 128, ix.sell_uv + slot, 512u, bar);
+      if (HASW) bulk_copy_g2s(stage + 640, sell_w + slot, 256u, bar);
     }
-    close_slice();
-  } else {
-    mbar_wait(&bars[0], 0);   // nobody leaves while the copy is in flight
   }
-  // ---- long landmarks, spread over all warps of the grid
-  const int total_warps = static_cast<int>(gridDim.x) * W;
-  for (int k = static_cast<int>(blockIdx.x) * W + wib; k < ix.num_long; k += total_warps) {
-    long_landmark_warp<JOINT, HASW>(ix, win, k, X, cam_rec, obs_d, obs_w, c1, c2, lm_fold, lm_rec);
+
+  __device__ __forceinline__ void open(Lane& st, const DeviceIndex& ix, int sl, int lane, int last) const {
+    st.lm = __ldcs(ix.sell_lm + kSellWidth * static_cast<size_t>(sl) + lane);
+    const double* xp = sell_x + 4 * kSellWidth * static_cast<size_t>(sl) + lane;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      st.x[k] = __ldcs(xp + k * kSellWidth);
+      st.G[k] = 0.0;
+    }
+    // towards L2, one 128-byte line per lane: the fold of this slice (read when it closes) and the
+    // landmarks of the next one
+    constexpr int kFoldLines = JOINT ? 20 : 12;
+    if (lane < kFoldLines) {
+      prefetch_l2(sell_fold + 10 * kSellWidth * static_cast<size_t>(sl) + 16 * lane);
+    } else if (lane - kFoldLines < 8 && sl < last) {
+      prefetch_l2(sell_x + 4 * kSellWidth * static_cast<size_t>(sl + 1) + 16 * (lane - kFoldLines));
+    } else if (lane == 31 && sl < last) {
+      prefetch_l2(ix.sell_lm + kSellWidth * static_cast<size_t>(sl + 1));
+    }
   }
-}
+
+  __device__ __forceinline__ void obs(Lane& st, const double2* __restrict__ rec, const unsigned char* stage, int lane,
+                                      int /*row*/) const {
+    ObsCoef k;
+    if (JOINT) {
+      const double* dp = reinterpret_cast<const double*>(stage + 128) + lane;
+      k.a = dp[0];
+      k.b = dp[kSellWidth];
+      k.c = dp[2 * kSellWidth];
+    } else {
+      const double2 uv = reinterpret_cast<const double2*>(stage + 128)[lane];
+      k.a = uv.x;
+      k.b = uv.y;
+      k.c = HASW ? reinterpret_cast<const double*>(stage + 640)[lane] : 1.0;
+    }
+    landmark_obs<JOINT>(rec, st.x, k, c1, c2, st.G);
+  }
+
+  __device__ __forceinline__ void close(Lane& st, const DeviceIndex& /*ix*/, int sl, int lane) const {
+    double F[10], H[4];
+    const double* fp = sell_fold + 10 * kSellWidth * static_cast<size_t>(sl) + lane;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) F[i] = (JOINT || i < 6) ? __ldcs(fp + i * kSellWidth) : 0.0;
+    fold_apply<JOINT>(F, st.G, H);
+    if (st.lm >= 0) {
+      double2* out = reinterpret_cast<double2*>(lm_rec + kLmRec * static_cast<size_t>(st.lm) + 4);
+      __stcs(out, make_double2(H[0], H[1]));
+      __stcs(out + 1, make_double2(H[2], H[3]));
+    }
+  }
+
+  // long landmarks, spread over all warps of the grid
+  __device__ __forceinline__ void finish(Lane& /*st*/, const DeviceIndex& ix, const CamWindow& win,
+                                         const double* __restrict__ cam_rec) const {
+    const int warps = static_cast<int>(blockDim.x >> 5);
+    const int total_warps = static_cast<int>(gridDim.x) * warps;
+    for (int k = static_cast<int>(blockIdx.x) * warps + static_cast<int>(threadIdx.x >> 5); k < ix.num_long;
+         k += total_warps) {
+      long_landmark_warp<JOINT, HASW>(ix, win, k, X, cam_rec, obs_d, obs_w, c1, c2, lm_fold, lm_rec);
+    }
+  }
+};
 
 // X and fold of the landmarks of every slice in lane-major planes ([slice][component][lane]); once per solve
 __global__ void __launch_bounds__(kBlock)
@@ -540,47 +426,14 @@ k_cam_rec_static(int C, const double* __restrict__ P, double* __restrict__ cam_r
   if (JOINT && n == 0) r[24] = r[25] = 0.0;
 }
 
-template <bool JOINT, bool HASW, int W, int D, int BPS>
-void launch_landmark_cfg(const DeviceState& d, const ModelParams& mp, const SeriesCtl* ctl, const LmPlan& plan,
-                         int win_cams, const LaunchCfg& lc) {
-  constexpr int kStage = (JOINT || HASW) ? kStageWide : kStagePose;
-  const size_t smem = lm_bar_bytes(W, D) + static_cast<size_t>(W) * D * kStage +
-                      static_cast<size_t>(win_cams) * CamRec::stride(JOINT) * 8;
-  auto kernel = k_e0_landmark_sell<JOINT, HASW, W, D, BPS>;
-  static const cudaError_t attr = [&]() {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) {
-      e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    }
-    return e;
-  }();
-  (void)attr;
-  kernel<<<plan.blocks, 32 * W, smem, lc.stream>>>(d.ix, plan, win_cams, d.X, d.cam_rec, d.sell_d, d.sell_w, mp.c1,
-                                                   mp.c2, d.lm_fold, d.sell_x, d.sell_fold, d.lm_rec, d.obs_d,
-                                                   d.obs_w, ctl);
-}
-
 template <bool JOINT, bool HASW>
 void launch_landmark_half(const DeviceState& d, const ModelParams& mp, const SeriesCtl* ctl,
                           const LaunchCfg& lc) {
-  const LmPlan& plan = d.plan[JOINT ? 1 : (HASW ? 2 : 0)];
-  if (plan.blocks == 0) return;   // no landmarks in this shard
-  // tests cap the window so that the global-memory path for cameras outside it is exercised
-  const int win = d.debug_window_cams > 0 && d.debug_window_cams < plan.win_cams ? d.debug_window_cams : plan.win_cams;
-#define POVAR_LM(W, D, BPS) \
-  if (plan.warps == W && plan.stages == D && plan.blocks_per_sm == BPS) { \
-    launch_landmark_cfg<JOINT, HASW, W, D, BPS>(d, mp, ctl, plan, win, lc); \
-  } else
-  POVAR_LM(8, 3, 4)
-  POVAR_LM(16, 3, 2)
-  POVAR_LM(32, 3, 1)
-  POVAR_LM(32, 2, 1)
-  POVAR_LM(24, 2, 1)
-  POVAR_LM(16, 2, 1) {
-    return;   // plan_landmark_half makes no other shape
+  const E0LandmarkOp<JOINT, HASW> op{d.X,      d.sell_d,    d.sell_w, mp.c1,   mp.c2,   d.lm_fold,
+                                     d.sell_x, d.sell_fold, d.lm_rec, d.obs_d, d.obs_w, ctl};
+  if (launch_sell_walk(d.ix, d.plan[JOINT ? 1 : (HASW ? 2 : 0)], d.debug_window_cams, d.cam_rec, op, lc.stream)) {
+    count(lc);
   }
-#undef POVAR_LM
-  count(lc);
 }
 
 }  // namespace

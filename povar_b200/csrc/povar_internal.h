@@ -55,6 +55,8 @@ constexpr int kSellWindow = 4096;   // sorting window of the sliced-ELL landmark
 constexpr int kSellKeySpan = 896;   // cameras the key of a landmark (build_sell) tries to centre
 constexpr int kCamRecStride = 26;   // doubles per camera record, the larger of the two models (CamRec::stride)
 constexpr int kCamRecPose = 22, kCamRecJoint = 26;   // CamRec::stride(false / true)
+// per-camera tables of the once-per-trial landmark walks (kernels_landmark.cu): [P | pad], [A | B | pad]
+constexpr int kCamTab1 = 14, kCamTab2 = 26;
 // bytes of one row of the observation stream of the landmark half: 32 camera indices + 32 x (u, v) in step 1
 // (+ 32 robust weights with HUBER), 32 camera indices + 3 x 32 coefficients in step 2
 constexpr int kStagePose = 128 + 512, kStageWide = 128 + 768;
@@ -178,7 +180,11 @@ struct DeviceState {
   int* flags = nullptr;          // [4] numerical-failure flags
   SeriesCtl* ctl = nullptr;
   CgState* cg = nullptr;
-  LmPlan plan[3];                // landmark half: [0] step 1, [1] step 2, [2] step 1 with HUBER weights
+  // plans of the sliced-ELL walks: [0] landmark half of a term, step 1; [1] step 2; [2] step 1 with HUBER
+  // weights; [3] once-per-trial walks over [P]; [4] over [A | B]
+  LmPlan plan[5];
+  double* cam_tab = nullptr;     // [C*26] the table of the walks of plan 3 / 4, packed right before each
+  double* lm_step = nullptr;     // [L*4] VarPro back-substitution: the landmark step between its two walks
   int debug_window_cams = 0;     // > 0: cap on the cameras the landmark half stages (povar_debug_set_window)
   double* dense_S = nullptr;     // CHOLESKY: [n_pad x n_pad], n_pad = 12 C rounded up to 64
 };
