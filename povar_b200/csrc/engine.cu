@@ -815,7 +815,14 @@ int Engine::upload(const povar_problem_desc* desc) {
   PV_ALLOC(d_.lm_fold, static_cast<size_t>(L) * 10);
   PV_ALLOC(d_.cam_rec, static_cast<size_t>(C) * kCamRecStride);
   PV_ALLOC(d_.cam_tab, static_cast<size_t>(C) * kCamTab2);
-  PV_ALLOC(d_.lm_step, static_cast<size_t>(L) * 4);
+  {
+    const size_t plane = static_cast<size_t>(ix.num_slices) * kSellWidth;
+    PV_ALLOC(d_.sell_hraw, plane * 10);
+    PV_ALLOC(d_.sell_graw, plane * 4);
+    PV_ALLOC(d_.sell_scale, plane * 4);
+    PV_ALLOC(d_.sell_hinv, plane * 6);
+    PV_ALLOC(d_.sell_step, plane * 4);
+  }
   PV_ALLOC(d_.sell_x, static_cast<size_t>(ix.num_slices) * 4 * kSellWidth);
   PV_ALLOC(d_.sell_fold, static_cast<size_t>(ix.num_slices) * 10 * kSellWidth);
   PV_ALLOC(d_.kron, static_cast<size_t>(C) * kKron);
@@ -1143,7 +1150,6 @@ int Engine::solve_power(bool joint, double lambda) {
   PV_CUDA(cudaEventRecord(ev_[0], stream_));
   // prepare_Hb_*: Hll^-1 and Hll^-1 Jl^T r per landmark; B^-1 per camera; b
   launch_prep_landmark(d_, joint, lambda_lm, lc());
-  launch_sell_pack(d_, joint, lc());
   launch_cam_binv(d_, joint, lambda, lc());
   launch_passB(d_, mp_, joint, lc());
   launch_reduce_items(d_, d_.item_part, 12, d_.cam_raw, false, lc());
@@ -1251,7 +1257,6 @@ int Engine::solve(bool joint, double lambda, double* inc, int32_t* iterations) {
 // b (and B, B^-1) exactly as the power solvers build them; shared by PCG / RIPCG / CHOLESKY
 int Engine::prepare_reduced_system(bool joint, double lambda, double lambda_lm) {
   launch_prep_landmark(d_, joint, lambda_lm, lc());
-  launch_sell_pack(d_, joint, lc());
   launch_cam_binv(d_, joint, lambda, lc());
   launch_passB(d_, mp_, joint, lc());
   launch_reduce_items(d_, d_.item_part, 12, d_.cam_raw, false, lc());
@@ -1592,8 +1597,35 @@ int64_t Engine::debug_read(const char* name, double* out, int64_t capacity) {
   else if (n == "X") dsrc = d_.X, count = 4LL * L_;
   else if (n == "pose_scale") dsrc = d_.pose_scale, count = 12LL * C_;
   else if (n == "lm_scale") dsrc = d_.lm_scale, count = 4LL * L_;
-  else if (n == "lm_hraw") dsrc = d_.lm_hraw, count = 10LL * L_;
-  else if (n == "lm_graw") dsrc = d_.lm_graw, count = 4LL * L_;
+  else if (n == "lm_hraw" || n == "lm_graw") {
+    // by landmark for the caller: the landmarks of the sliced-ELL set keep these sums as lane-major planes
+    // [slice][component][32], the others (more than 32 observations) by landmark
+    const int K = n == "lm_hraw" ? 10 : 4;
+    count = static_cast<int64_t>(K) * L_;
+    if (!out) return count;
+    if (capacity < count) {
+      fail(POVAR_ERR_INVALID, "debug_read: buffer too small");
+      return POVAR_ERR_INVALID;
+    }
+    const double* by_lm = K == 10 ? d_.lm_hraw : d_.lm_graw;
+    const double* planes = K == 10 ? d_.sell_hraw : d_.sell_graw;
+    const size_t slots = static_cast<size_t>(kSellWidth) * d_.ix.num_slices;
+    std::vector<double> hp(slots * K);
+    std::vector<int> hlm(slots);
+    if (cudaMemcpy(out, by_lm, sizeof(double) * count, cudaMemcpyDeviceToHost) != cudaSuccess) return POVAR_ERR_CUDA;
+    if (slots > 0) {
+      if (cudaMemcpy(hp.data(), planes, sizeof(double) * hp.size(), cudaMemcpyDeviceToHost) != cudaSuccess ||
+          cudaMemcpy(hlm.data(), d_.ix.sell_lm, sizeof(int) * slots, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        return POVAR_ERR_CUDA;
+      }
+    }
+    for (size_t i = 0; i < slots; ++i) {
+      if (hlm[i] < 0) continue;
+      const size_t sl = i / kSellWidth, lane = i % kSellWidth;
+      for (int k = 0; k < K; ++k) out[static_cast<size_t>(hlm[i]) * K + k] = hp[(sl * K + k) * kSellWidth + lane];
+    }
+    return count;
+  }
   else if (n == "hll_inv") dsrc = d_.hll_inv, count = 6LL * L_;
   else if (n == "lm_rec") dsrc = d_.lm_rec, count = static_cast<int64_t>(kLmRec) * L_;
   else if (n == "kron") dsrc = d_.kron, count = static_cast<int64_t>(kKron) * C_;

@@ -346,20 +346,13 @@ k_lin_long(DeviceIndex ix, const double* __restrict__ P, const double* __restric
 // per solve, per landmark: Hll^-1 (with landmark damping), H_r = scale o (Pi) Hll^-1 Jl^T r,
 // and the [X | H] record the camera-major pass gathers
 // ------------------------------------------------------------------------------------------
+// x, s: landmark and column scales; h (10), g (4): the raw sums of the linearisation.  Out: inv = Hll^-1 (packed),
+// H = scale o (Pi) Hll^-1 (Pi^T) (scale o g), fold (10; 6 used in step 1)
 template <bool JOINT>
-__global__ void __launch_bounds__(kBlock)
-k_prep_landmark(int L, const double* __restrict__ X, const double* __restrict__ lm_hraw,
-                const double* __restrict__ lm_graw, const double* __restrict__ lm_scale,
-                double lambda_lm, double* __restrict__ hll_inv, double* __restrict__ lm_rec,
-                double* __restrict__ lm_fold) {
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
-  if (l >= L) return;
-  double x[4], s[4];
-  load_lm4(X, l, x);
-  load_lm4(lm_scale, l, s);
-  const double* h = lm_hraw + 10 * static_cast<size_t>(l);
-  const double* g = lm_graw + 4 * static_cast<size_t>(l);
-  double hll[6], inv[6], H[4] = {0, 0, 0, 0};
+__device__ __forceinline__ void prep_one(const double (&x)[4], const double (&s)[4], const double* h, const double* g,
+                                         double lambda_lm, double (&inv)[6], double (&H)[4], double (&fold)[10]) {
+  double hll[6];
+  H[0] = H[1] = H[2] = H[3] = 0.0;
   if (JOINT) {
     // A = (s s^T) o hraw (4x4), Hll = Pi^T A Pi + lambda I
     double A[4][4];
@@ -422,13 +415,12 @@ k_prep_landmark(int L, const double* __restrict__ X, const double* __restrict__ 
 #pragma unroll
       for (int a = 0; a < 4; ++a) F[a][nn] = s[a] * k4[a];
     }
-    double* fo = lm_fold + 10 * static_cast<size_t>(l);
     {
       int nn = 0;
 #pragma unroll
       for (int a = 0; a < 4; ++a) {
 #pragma unroll
-        for (int b2 = a; b2 < 4; ++b2) fo[nn++] = 0.5 * (F[a][b2] + F[b2][a]);
+        for (int b2 = a; b2 < 4; ++b2) fold[nn++] = 0.5 * (F[a][b2] + F[b2][a]);
       }
     }
   } else {
@@ -445,22 +437,98 @@ k_prep_landmark(int L, const double* __restrict__ X, const double* __restrict__ 
     sym3_mul(inv, sg, h3);
 #pragma unroll
     for (int a = 0; a < 3; ++a) H[a] = s[a] * h3[a];
-    double* fo = lm_fold + 10 * static_cast<size_t>(l);
-    fo[0] = s[0] * s[0] * inv[0];
-    fo[1] = s[0] * s[1] * inv[1];
-    fo[2] = s[0] * s[2] * inv[2];
-    fo[3] = s[1] * s[1] * inv[3];
-    fo[4] = s[1] * s[2] * inv[4];
-    fo[5] = s[2] * s[2] * inv[5];
+    fold[0] = s[0] * s[0] * inv[0];
+    fold[1] = s[0] * s[1] * inv[1];
+    fold[2] = s[0] * s[2] * inv[2];
+    fold[3] = s[1] * s[1] * inv[3];
+    fold[4] = s[1] * s[2] * inv[4];
+    fold[5] = s[2] * s[2] * inv[5];
+    fold[6] = fold[7] = fold[8] = fold[9] = 0.0;
   }
+}
+
+// landmarks with more than 32 observations: everything by landmark (k_*_long and long_landmark_warp read it there)
+template <bool JOINT>
+__global__ void __launch_bounds__(kBlock)
+k_prep_long(int num_long, const int* __restrict__ long_lm, const double* __restrict__ X,
+            const double* __restrict__ lm_hraw, const double* __restrict__ lm_graw,
+            const double* __restrict__ lm_scale, double lambda_lm, double* __restrict__ hll_inv,
+            double* __restrict__ lm_rec, double* __restrict__ lm_fold) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= num_long) return;
+  const int l = long_lm[i];
+  double x[4], s[4], inv[6], H[4], fold[10];
+  load_lm4(X, l, x);
+  load_lm4(lm_scale, l, s);
+  prep_one<JOINT>(x, s, lm_hraw + 10 * static_cast<size_t>(l), lm_graw + 4 * static_cast<size_t>(l), lambda_lm, inv,
+                  H, fold);
   double* hi = hll_inv + 6 * static_cast<size_t>(l);
 #pragma unroll
   for (int k = 0; k < 6; ++k) hi[k] = inv[k];
+  double* fo = lm_fold + 10 * static_cast<size_t>(l);
+#pragma unroll
+  for (int k = 0; k < 10; ++k) fo[k] = fold[k];
   double* rec = lm_rec + kLmRec * static_cast<size_t>(l);
 #pragma unroll
   for (int k = 0; k < 4; ++k) rec[k] = x[k];
 #pragma unroll
   for (int k = 0; k < 4; ++k) rec[4 + k] = H[k];
+}
+
+// the landmarks of the sliced-ELL set, one thread per slot: the sums of the linearisation come in and Hll^-1
+// and the fold go out as lane-major planes (one coalesced line per component and slice, what the walks read);
+// the [X | H] record of the camera-major passes and Hll^-1 for the camera-major kernels of PCG / CHOLESKY go
+// out by landmark
+template <bool JOINT>
+__global__ void __launch_bounds__(kBlock)
+k_prep_sell(int slots, const int* __restrict__ sell_lm, const double* __restrict__ sell_x,
+            const double* __restrict__ sell_hraw, const double* __restrict__ sell_graw,
+            const double* __restrict__ sell_scale, double lambda_lm, double* __restrict__ sell_hinv,
+            double* __restrict__ sell_fold, double* __restrict__ hll_inv, double* __restrict__ lm_rec) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= slots) return;
+  const int sl = i / kSellWidth, lane = i % kSellWidth;
+  const int lm = sell_lm[i];
+  double* ip = sell_hinv + 6 * kSellWidth * static_cast<size_t>(sl) + lane;
+  double* fp = sell_fold + 10 * kSellWidth * static_cast<size_t>(sl) + lane;
+  if (lm < 0) {   // padding of the last slice of a window: nothing reads it, keep it finite
+#pragma unroll
+    for (int k = 0; k < 6; ++k) ip[k * kSellWidth] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) fp[k * kSellWidth] = 0.0;
+    return;
+  }
+  double x[4], s[4], h[10], g[4], inv[6], H[4], fold[10];
+  {
+    const double* xp = sell_x + 4 * kSellWidth * static_cast<size_t>(sl) + lane;
+    const double* sp = sell_scale + 4 * kSellWidth * static_cast<size_t>(sl) + lane;
+    const double* gp = sell_graw + 4 * kSellWidth * static_cast<size_t>(sl) + lane;
+    const double* hp = sell_hraw + 10 * kSellWidth * static_cast<size_t>(sl) + lane;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      x[k] = xp[k * kSellWidth];
+      s[k] = sp[k * kSellWidth];
+      g[k] = gp[k * kSellWidth];
+    }
+#pragma unroll
+    for (int k = 0; k < 10; ++k) h[k] = (JOINT || k < 6) ? hp[k * kSellWidth] : 0.0;
+  }
+  prep_one<JOINT>(x, s, h, g, lambda_lm, inv, H, fold);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) ip[k * kSellWidth] = inv[k];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) {
+    if (JOINT || k < 6) fp[k * kSellWidth] = fold[k];
+  }
+  double2* hi = reinterpret_cast<double2*>(hll_inv + 6 * static_cast<size_t>(lm));
+  hi[0] = make_double2(inv[0], inv[1]);
+  hi[1] = make_double2(inv[2], inv[3]);
+  hi[2] = make_double2(inv[4], inv[5]);
+  double2* rec = reinterpret_cast<double2*>(lm_rec + kLmRec * static_cast<size_t>(lm));
+  rec[0] = make_double2(x[0], x[1]);
+  rec[1] = make_double2(x[2], x[3]);
+  rec[2] = make_double2(H[0], H[1]);
+  rec[3] = make_double2(H[2], H[3]);
 }
 
 // landmark-level tail shared by the E0 pass: G (sum of Jl_raw^T a over the landmark) -> H
@@ -867,9 +935,11 @@ struct LinLandmarkOp : WalkBase {
   Robust rb;
   double eps;
   int scale_jl;
-  double* lm_hraw;
-  double* lm_graw;
-  double* lm_scale;
+  double* sell_hraw;   // [slice][10][32] (6 planes used in step 1)
+  double* sell_graw;   // [slice][4][32]
+  double* sell_scale;  // [slice][4][32]
+  double* sell_x;      // [slice][4][32] the landmarks of the linearisation point, for the term kernels
+  double* lm_scale;    // the scales by landmark too: the camera-major kernels of PCG / CHOLESKY gather them
   int* flags;
   double* sell_d;   // step 2: what the term kernels stream, [row][3][32]
   double* sell_w;   // step 1 with HUBER: [row][32]
@@ -935,31 +1005,42 @@ struct LinLandmarkOp : WalkBase {
     }
   }
 
-  __device__ __forceinline__ void close(Lane& st, const DeviceIndex&, int, int) const {
-    if (st.lm < 0) return;
-    double* h = lm_hraw + 10 * static_cast<size_t>(st.lm);
-    double* g = lm_graw + 4 * static_cast<size_t>(st.lm);
-    double* s = lm_scale + 4 * static_cast<size_t>(st.lm);
+  // one coalesced line per component and slice (idle lanes write zeros: x = 0, sums = 0, scale = 1 / eps)
+  __device__ __forceinline__ void close(Lane& st, const DeviceIndex&, int sl, int lane) const {
+    double* h = sell_hraw + 10 * kSellWidth * static_cast<size_t>(sl) + lane;
+    double* g = sell_graw + 4 * kSellWidth * static_cast<size_t>(sl) + lane;
+    double* sp = sell_scale + 4 * kSellWidth * static_cast<size_t>(sl) + lane;
+    double* xp = sell_x + 4 * kSellWidth * static_cast<size_t>(sl) + lane;
+    double s[4];
     if (JOINT) {
 #pragma unroll
-      for (int k = 0; k < 10; ++k) h[k] = st.acc[k];
+      for (int k = 0; k < 10; ++k) h[k * kSellWidth] = st.acc[k];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) g[k] = st.acc[10 + k];
+      for (int k = 0; k < 4; ++k) g[k * kSellWidth] = st.acc[10 + k];
       s[0] = 1.0 / (eps + sqrt(st.acc[0]));
       s[1] = 1.0 / (eps + sqrt(st.acc[4]));
       s[2] = 1.0 / (eps + sqrt(st.acc[7]));
       s[3] = 1.0 / (eps + sqrt(st.acc[9]));
     } else {
 #pragma unroll
-      for (int k = 0; k < 6; ++k) h[k] = st.acc[k];
+      for (int k = 0; k < 6; ++k) h[k * kSellWidth] = st.acc[k];
 #pragma unroll
-      for (int k = 0; k < 3; ++k) g[k] = st.acc[6 + k];
-      g[3] = 0.0;
+      for (int k = 0; k < 3; ++k) g[k * kSellWidth] = st.acc[6 + k];
+      g[3 * kSellWidth] = 0.0;
       s[0] = scale_jl ? 1.0 / (eps + sqrt(st.acc[0])) : 1.0;
       s[1] = scale_jl ? 1.0 / (eps + sqrt(st.acc[3])) : 1.0;
       s[2] = scale_jl ? 1.0 / (eps + sqrt(st.acc[5])) : 1.0;
       s[3] = 1.0;
     }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      sp[k * kSellWidth] = s[k];
+      xp[k * kSellWidth] = st.x[k];
+    }
+    if (st.lm < 0) return;
+    double2* so = reinterpret_cast<double2*>(lm_scale + 4 * static_cast<size_t>(st.lm));
+    so[0] = make_double2(s[0], s[1]);
+    so[1] = make_double2(s[2], s[3]);
     bool fin = isfinite(st.x[0]) && isfinite(st.x[1]) && isfinite(st.x[2]) && isfinite(st.x[3]);
 #pragma unroll
     for (int k = 0; k < NV; ++k) fin = fin && isfinite(st.acc[k]);
@@ -976,7 +1057,7 @@ struct BacksubVarproStepOp : WalkBase {
   static constexpr int kRec = kCamTab1;
   const double* X;
   double c1, c2;
-  double* lm_step;   // [L*4]
+  double* sell_step;   // [slice][4][32]
 
   struct Lane {
     int lm, lm1, lm2;
@@ -1012,8 +1093,7 @@ struct BacksubVarproStepOp : WalkBase {
     }
   }
 
-  __device__ __forceinline__ void close(Lane& st, const DeviceIndex&, int, int) const {
-    if (st.lm < 0) return;
+  __device__ __forceinline__ void close(Lane& st, const DeviceIndex&, int sl, int lane) const {
     double hll[6], inv[6], tmp[3], il[3];
 #pragma unroll
     for (int k = 0; k < 6; ++k) hll[k] = st.acc[k];
@@ -1021,9 +1101,10 @@ struct BacksubVarproStepOp : WalkBase {
     for (int k = 0; k < 3; ++k) tmp[k] = st.acc[6 + k];
     inv3_sym(hll, inv);
     sym3_mul(inv, tmp, il);
-    double2* out = reinterpret_cast<double2*>(lm_step + 4 * static_cast<size_t>(st.lm));
-    out[0] = make_double2(-il[0], -il[1]);
-    out[1] = make_double2(-il[2], 0.0);
+    double* out = sell_step + 4 * kSellWidth * static_cast<size_t>(sl) + lane;   // (idle lanes: never read)
+    out[0] = -il[0];
+    out[kSellWidth] = -il[1];
+    out[2 * kSellWidth] = -il[2];
   }
 
   __device__ __forceinline__ void finish(Lane&, const DeviceIndex&, const CamWindow&, const double*) const {}
@@ -1036,9 +1117,9 @@ struct BacksubVarproDiffOp : WalkBase {
   double* X;
   double c1, c2;
   Robust rb;
-  const double* lm_scale;
-  const double* lm_hraw;
-  const double* lm_step;
+  const double* sell_scale;
+  const double* sell_hraw;
+  const double* sell_step;
   double* scalar_part;
 
   struct Lane {
@@ -1054,11 +1135,10 @@ struct BacksubVarproDiffOp : WalkBase {
 
   __device__ __forceinline__ void open(Lane& st, const DeviceIndex& ix, int sl, int lane, int last) const {
     open_landmark(st, ix, X, sl, lane, last, 0.0);
-    if (st.lm >= 0) {   // what close() gathers, towards L2
-      prefetch_l2(lm_scale + 4 * static_cast<size_t>(st.lm));
-      prefetch_l2(lm_step + 4 * static_cast<size_t>(st.lm));
-      prefetch_l2(lm_hraw + 10 * static_cast<size_t>(st.lm));
-    }
+    // what close() reads, towards L2: 6 + 3 + 3 planes of 256 bytes = 24 lines
+    if (lane < 12) prefetch_l2(sell_hraw + 10 * kSellWidth * static_cast<size_t>(sl) + 16 * lane);
+    else if (lane < 18) prefetch_l2(sell_scale + 4 * kSellWidth * static_cast<size_t>(sl) + 16 * (lane - 12));
+    else if (lane < 24) prefetch_l2(sell_step + 4 * kSellWidth * static_cast<size_t>(sl) + 16 * (lane - 18));
     st.A = 0.0;
     st.B[0] = st.B[1] = st.B[2] = 0.0;
   }
@@ -1084,15 +1164,19 @@ struct BacksubVarproDiffOp : WalkBase {
     }
   }
 
-  __device__ __forceinline__ void close(Lane& st, const DeviceIndex&, int, int) const {
+  __device__ __forceinline__ void close(Lane& st, const DeviceIndex&, int sl, int lane) const {
     if (st.lm < 0) return;
-    double s[4], il[4], d[3], hd[3];
-    load_lm4(lm_scale, st.lm, s);
-    load_lm4(lm_step, st.lm, il);
-    const double* h = lm_hraw + 10 * static_cast<size_t>(st.lm);
-    const double hs[6] = {h[0], h[1], h[2], h[3], h[4], h[5]};
+    double il[3], d[3], hd[3], hs[6];
+    const double* sp = sell_scale + 4 * kSellWidth * static_cast<size_t>(sl) + lane;
+    const double* ip = sell_step + 4 * kSellWidth * static_cast<size_t>(sl) + lane;
+    const double* hp = sell_hraw + 10 * kSellWidth * static_cast<size_t>(sl) + lane;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) d[k] = s[k] * il[k];
+    for (int k = 0; k < 6; ++k) hs[k] = __ldcs(hp + k * kSellWidth);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      il[k] = __ldcs(ip + k * kSellWidth);
+      d[k] = __ldcs(sp + k * kSellWidth) * il[k];
+    }
     sym3_mul(hs, d, hd);
     st.ld -= st.A + (d[0] * st.B[0] + d[1] * st.B[1] + d[2] * st.B[2]) +
              0.5 * (d[0] * hd[0] + d[1] * hd[1] + d[2] * hd[2]);
@@ -1115,9 +1199,9 @@ struct BacksubLinPointOp : WalkBase {
   double* X;
   double c1, c2;
   Robust rb;
-  const double* lm_scale;
-  const double* hll_inv;
-  const double* lm_hraw;
+  const double* sell_scale;
+  const double* sell_hinv;   // [slice][6][32] Hll^-1 of the last solve
+  const double* sell_hraw;
   double* scalar_part;
 
   struct Lane {
@@ -1133,10 +1217,12 @@ struct BacksubLinPointOp : WalkBase {
 
   __device__ __forceinline__ void open(Lane& st, const DeviceIndex& ix, int sl, int lane, int last) const {
     open_landmark(st, ix, X, sl, lane, last, 1.0);   // x0 = 1 keeps the reflector of an idle lane well defined
-    if (st.lm >= 0) {   // what close() gathers, towards L2
-      prefetch_l2(lm_scale + 4 * static_cast<size_t>(st.lm));
-      prefetch_l2(hll_inv + 6 * static_cast<size_t>(st.lm));
-      prefetch_l2(lm_hraw + 10 * static_cast<size_t>(st.lm));
+    // what close() reads, towards L2: 10 + 4 + 6 planes of 256 bytes = 40 lines, two per lane
+    {
+      const double* hp = sell_hraw + 10 * kSellWidth * static_cast<size_t>(sl);
+      if (lane < 20) prefetch_l2(hp + 16 * lane);
+      else if (lane < 28) prefetch_l2(sell_scale + 4 * kSellWidth * static_cast<size_t>(sl) + 16 * (lane - 20));
+      if (lane < 12) prefetch_l2(sell_hinv + 6 * kSellWidth * static_cast<size_t>(sl) + 16 * lane);
     }
     st.S0 = 0.0;
 #pragma unroll
@@ -1180,16 +1266,20 @@ struct BacksubLinPointOp : WalkBase {
     }
   }
 
-  __device__ __forceinline__ void close(Lane& st, const DeviceIndex&, int, int) const {
+  __device__ __forceinline__ void close(Lane& st, const DeviceIndex&, int sl, int lane) const {
     if (st.lm < 0) return;
-    double s[4], inv[6];
-    load_lm4(lm_scale, st.lm, s);
+    double s[4], inv[6], h[10];
     {
-      const double* hi = hll_inv + 6 * static_cast<size_t>(st.lm);
+      const double* sp = sell_scale + 4 * kSellWidth * static_cast<size_t>(sl) + lane;
+      const double* ip = sell_hinv + 6 * kSellWidth * static_cast<size_t>(sl) + lane;
+      const double* hp = sell_hraw + 10 * kSellWidth * static_cast<size_t>(sl) + lane;
 #pragma unroll
-      for (int k = 0; k < 6; ++k) inv[k] = hi[k];
+      for (int k = 0; k < 4; ++k) s[k] = __ldcs(sp + k * kSellWidth);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) inv[k] = __ldcs(ip + k * kSellWidth);
+#pragma unroll
+      for (int k = 0; k < 10; ++k) h[k] = (JOINT || k < 6) ? __ldcs(hp + k * kSellWidth) : 0.0;
     }
-    const double* h = lm_hraw + 10 * static_cast<size_t>(st.lm);
     double dl[4];   // the landmark increment in raw coordinates
     if (JOINT) {
       Reflector<4> pi;
@@ -1335,12 +1425,14 @@ void launch_lin_landmark(const DeviceState& d, const ModelParams& mp, bool joint
   if (d.plan[3].blocks > 0) {
     pack_cam_tab(d, d.P, nullptr, lc);
     if (joint) {
-      const LinLandmarkOp<true> op{{}, d.X, mp.c1, mp.c2, rb, mp.jacobi_eps, 1, d.lm_hraw, d.lm_graw, d.lm_scale,
-                                   d.flags, d.sell_d, nullptr};
+      const LinLandmarkOp<true> op{{},          d.X,         mp.c1,        mp.c2,    rb,         mp.jacobi_eps, 1,
+                                   d.sell_hraw, d.sell_graw, d.sell_scale, d.sell_x, d.lm_scale, d.flags,       d.sell_d,
+                                   nullptr};
       if (launch_sell_walk(d.ix, d.plan[3], d.debug_window_cams, d.cam_tab, op, lc.stream)) count(lc);
     } else {
-      const LinLandmarkOp<false> op{{}, d.X, mp.c1, mp.c2, rb, mp.jacobi_eps, scale_jl ? 1 : 0, d.lm_hraw, d.lm_graw,
-                                    d.lm_scale, d.flags, nullptr, sw};
+      const LinLandmarkOp<false> op{{},          d.X,         mp.c1,        mp.c2,    rb,         mp.jacobi_eps,
+                                    scale_jl ? 1 : 0, d.sell_hraw, d.sell_graw, d.sell_scale, d.sell_x, d.lm_scale,
+                                    d.flags,     nullptr,     sw};
       if (launch_sell_walk(d.ix, d.plan[3], d.debug_window_cams, d.cam_tab, op, lc.stream)) count(lc);
     }
   }
@@ -1360,16 +1452,31 @@ void launch_lin_landmark(const DeviceState& d, const ModelParams& mp, bool joint
 }
 
 void launch_prep_landmark(const DeviceState& d, bool joint, double lambda_lm, const LaunchCfg& lc) {
-  const int blocks = (d.ix.L + kBlock - 1) / kBlock;
-  if (blocks == 0) return;
-  if (joint) {
-    k_prep_landmark<true><<<blocks, kBlock, 0, lc.stream>>>(d.ix.L, d.X, d.lm_hraw, d.lm_graw, d.lm_scale,
-                                                            lambda_lm, d.hll_inv, d.lm_rec, d.lm_fold);
-  } else {
-    k_prep_landmark<false><<<blocks, kBlock, 0, lc.stream>>>(d.ix.L, d.X, d.lm_hraw, d.lm_graw, d.lm_scale,
-                                                             lambda_lm, d.hll_inv, d.lm_rec, d.lm_fold);
+  const int slots = kSellWidth * d.ix.num_slices;
+  if (slots > 0) {
+    const int blocks = (slots + kBlock - 1) / kBlock;
+    if (joint) {
+      k_prep_sell<true><<<blocks, kBlock, 0, lc.stream>>>(slots, d.ix.sell_lm, d.sell_x, d.sell_hraw, d.sell_graw,
+                                                          d.sell_scale, lambda_lm, d.sell_hinv, d.sell_fold, d.hll_inv,
+                                                          d.lm_rec);
+    } else {
+      k_prep_sell<false><<<blocks, kBlock, 0, lc.stream>>>(slots, d.ix.sell_lm, d.sell_x, d.sell_hraw, d.sell_graw,
+                                                           d.sell_scale, lambda_lm, d.sell_hinv, d.sell_fold, d.hll_inv,
+                                                           d.lm_rec);
+    }
+    count(lc);
   }
-  count(lc);
+  if (d.ix.num_long > 0) {
+    const int blocks = (d.ix.num_long + kBlock - 1) / kBlock;
+    if (joint) {
+      k_prep_long<true><<<blocks, kBlock, 0, lc.stream>>>(d.ix.num_long, d.ix.long_lm, d.X, d.lm_hraw, d.lm_graw,
+                                                          d.lm_scale, lambda_lm, d.hll_inv, d.lm_rec, d.lm_fold);
+    } else {
+      k_prep_long<false><<<blocks, kBlock, 0, lc.stream>>>(d.ix.num_long, d.ix.long_lm, d.X, d.lm_hraw, d.lm_graw,
+                                                           d.lm_scale, lambda_lm, d.hll_inv, d.lm_rec, d.lm_fold);
+    }
+    count(lc);
+  }
 }
 
 // d.P: the updated cameras, d.P_bak: those of the linearisation point
@@ -1385,10 +1492,10 @@ void launch_backsub_varpro(const DeviceState& d, const ModelParams& mp, const do
   bool walked = false;
   if (d.plan[3].blocks > 0) {
     pack_cam_tab(d, d.P, nullptr, lc);
-    const BacksubVarproStepOp step{{}, d.X, mp.c1, mp.c2, d.lm_step};
+    const BacksubVarproStepOp step{{}, d.X, mp.c1, mp.c2, d.sell_step};
     if (launch_sell_walk(d.ix, d.plan[3], d.debug_window_cams, d.cam_tab, step, lc.stream)) count(lc);
     pack_cam_tab(d, d.P_bak, inc, lc);
-    const BacksubVarproDiffOp diff{{}, d.X, mp.c1, mp.c2, rb, d.lm_scale, d.lm_hraw, d.lm_step, d.scalar_part + blocks};
+    const BacksubVarproDiffOp diff{{}, d.X, mp.c1, mp.c2, rb, d.sell_scale, d.sell_hraw, d.sell_step, d.scalar_part + blocks};
     walked = launch_sell_walk(d.ix, d.plan[4], d.debug_window_cams, d.cam_tab, diff, lc.stream);
     if (walked) count(lc);
   }
@@ -1407,7 +1514,7 @@ void launch_backsub_poba(const DeviceState& d, const ModelParams& mp, const doub
   bool walked = false;
   if (d.plan[4].blocks > 0) {
     pack_cam_tab(d, d.P, y, lc);
-    const BacksubLinPointOp<false> op{{}, d.X, mp.c1, mp.c2, rb, d.lm_scale, d.hll_inv, d.lm_hraw, d.scalar_part + blocks};
+    const BacksubLinPointOp<false> op{{}, d.X, mp.c1, mp.c2, rb, d.sell_scale, d.sell_hinv, d.sell_hraw, d.scalar_part + blocks};
     walked = launch_sell_walk(d.ix, d.plan[4], d.debug_window_cams, d.cam_tab, op, lc.stream);
     if (walked) count(lc);
   }
@@ -1426,7 +1533,7 @@ void launch_backsub_joint(const DeviceState& d, const ModelParams& mp, const dou
   bool walked = false;
   if (d.plan[4].blocks > 0) {
     pack_cam_tab(d, d.P, y, lc);
-    const BacksubLinPointOp<true> op{{}, d.X, mp.c1, mp.c2, rb, d.lm_scale, d.hll_inv, d.lm_hraw, d.scalar_part + blocks};
+    const BacksubLinPointOp<true> op{{}, d.X, mp.c1, mp.c2, rb, d.sell_scale, d.sell_hinv, d.sell_hraw, d.scalar_part + blocks};
     walked = launch_sell_walk(d.ix, d.plan[4], d.debug_window_cams, d.cam_tab, op, lc.stream);
     if (walked) count(lc);
   }

@@ -67,8 +67,8 @@ struct ObsCoef {
 // ------------------------------------------------------------------------------------------
 // landmark half: the sliced-ELL walk of sell_walk.cuh with the camera records [y_c | M_c] (CamRec) staged per
 // block and the stream [camera index | (u, v) (| w)] resp. [camera index | d] in the per-warp rings.  The
-// per-slice landmark data (X, fold) are read from lane-major copies packed once per solve (k_sell_pack): one
-// coalesced line per component; they are pulled into L2 one slice ahead.
+// per-slice landmark data (X, fold) are lane-major planes written by the linearisation walk and k_prep_sell
+// (kernels_landmark.cu): one coalesced line per component; they are pulled into L2 one slice ahead.
 // ------------------------------------------------------------------------------------------
 // G += M^T (K^T W K) (Y x) for one observation whose camera record is `rec` (shared or global memory)
 template <bool JOINT>
@@ -274,36 +274,6 @@ struct E0LandmarkOp {
   }
 };
 
-// X and fold of the landmarks of every slice in lane-major planes ([slice][component][lane]); once per solve
-__global__ void __launch_bounds__(kBlock)
-k_sell_pack(int groups, const int* __restrict__ sell_lm, const double* __restrict__ X,
-            const double* __restrict__ lm_fold, double* __restrict__ sell_x, double* __restrict__ sell_fold) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= groups) return;
-  const int sl = i / kSellWidth, lane = i % kSellWidth;
-  const int lm = sell_lm[i];
-  double* xp = sell_x + 4 * kSellWidth * static_cast<size_t>(sl) + lane;
-  double* fp = sell_fold + 10 * kSellWidth * static_cast<size_t>(sl) + lane;
-  if (lm >= 0) {
-    double x[4];
-    load4(X + 4 * static_cast<size_t>(lm), x);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) xp[k * kSellWidth] = x[k];
-    const double2* f = reinterpret_cast<const double2*>(lm_fold + 10 * static_cast<size_t>(lm));
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-      const double2 t = __ldg(f + k);
-      fp[(2 * k) * kSellWidth] = t.x;
-      fp[(2 * k + 1) * kSellWidth] = t.y;
-    }
-  } else {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) xp[k * kSellWidth] = 0.0;
-#pragma unroll
-    for (int k = 0; k < 10; ++k) fp[k * kSellWidth] = 0.0;
-  }
-}
-
 // ------------------------------------------------------------------------------------------
 // camera half.  One warp per work item (a run of CSC entries of one camera, kernels_camera.cu),
 // two lanes per entry, sixteen entries per step, two steps per trip.  Lane j owns X[2j..2j+1]
@@ -445,15 +415,6 @@ void launch_cam_rec_static(const DeviceState& d, bool joint, const LaunchCfg& lc
   } else {
     k_cam_rec_static<false><<<blocks, kBlock, 0, lc.stream>>>(d.ix.C, d.P, d.cam_rec);
   }
-  count(lc);
-}
-
-void launch_sell_pack(const DeviceState& d, bool joint, const LaunchCfg& lc) {
-  (void)joint;
-  const int groups = kSellWidth * d.ix.num_slices;
-  if (groups == 0) return;
-  k_sell_pack<<<(groups + kBlock - 1) / kBlock, kBlock, 0, lc.stream>>>(groups, d.ix.sell_lm, d.X, d.lm_fold, d.sell_x,
-                                                                       d.sell_fold);
   count(lc);
 }
 

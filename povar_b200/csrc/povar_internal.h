@@ -146,8 +146,16 @@ struct DeviceState {
   double* csc_d = nullptr;       // [nnz*3] the same, camera-major
   double* obs_w = nullptr;       // [nnz]   step 1, HUBER only: robust weight at the linearisation point
   double* sell_d = nullptr;      // [rows][3][32] obs_d in SELL order, one plane per coefficient and row
-  double* sell_x = nullptr;      // [slices][4][32]  X of the slices' landmarks (packed once per solve)
-  double* sell_fold = nullptr;   // [slices][10][32] lm_fold of the slices' landmarks
+  // per-landmark data of the sliced-ELL set as lane-major planes [slice][component][32]: what the walks read
+  // and write with one coalesced line per component (the landmarks with more than 32 observations use the
+  // by-landmark arrays above)
+  double* sell_x = nullptr;      // [slices][4][32]  X at the linearisation point
+  double* sell_hraw = nullptr;   // [slices][10][32]
+  double* sell_graw = nullptr;   // [slices][4][32]
+  double* sell_scale = nullptr;  // [slices][4][32]
+  double* sell_hinv = nullptr;   // [slices][6][32]  Hll^-1 of the last solve
+  double* sell_fold = nullptr;   // [slices][10][32]
+  double* sell_step = nullptr;   // [slices][4][32]  VarPro back-substitution: the landmark step between its walks
   double* sell_w = nullptr;      // [slots]   obs_w in SELL order
   double* csc_w = nullptr;       // [nnz]   the same, camera-major
   double* kron = nullptr;        // [C*60]
@@ -184,7 +192,6 @@ struct DeviceState {
   // weights; [3] once-per-trial walks over [P]; [4] over [A | B]
   LmPlan plan[5];
   double* cam_tab = nullptr;     // [C*26] the table of the walks of plan 3 / 4, packed right before each
-  double* lm_step = nullptr;     // [L*4] VarPro back-substitution: the landmark step between its two walks
   int debug_window_cams = 0;     // > 0: cap on the cameras the landmark half stages (povar_debug_set_window)
   double* dense_S = nullptr;     // CHOLESKY: [n_pad x n_pad], n_pad = 12 C rounded up to 64
 };
@@ -269,8 +276,6 @@ void launch_e0_finish(const DeviceState& d, bool joint, double* out, const Launc
 void launch_make_y(const DeviceState& d, bool joint, const double* x, double* y, const LaunchCfg& lc);
 // cam_rec: matrix part (after a linearisation) -- the y part is written by whoever makes y
 void launch_cam_rec_static(const DeviceState& d, bool joint, const LaunchCfg& lc);
-// X and lm_fold of the landmarks of every slice, lane-major (after launch_prep_landmark, before any E0 product)
-void launch_sell_pack(const DeviceState& d, bool joint, const LaunchCfg& lc);
 // ---- power-series term kernels, lane-group layout (kernels_series.cu) ----
 void launch_e0_landmark_v2(const DeviceState& d, const ModelParams& mp, bool joint, bool in_series,
                            const LaunchCfg& lc);
