@@ -47,7 +47,7 @@ def ref_layout_bytes(nnz, L, C, joint=False):
 # bytes the matrix-free kernels have to move per launch (DESIGN.md "kernels"): index + observation
 # streams, per-landmark records, per-camera vectors, each counted once
 def own_bytes_landmark_pass(slots, slices, L, C):
-    # sliced-ELL landmark half (k_e0_landmark_sell<pose>), 32 landmarks per slice: camera index + uv per slot
+    # sliced-ELL landmark half (k_sell_walk<E0LandmarkOp<pose>>), 32 landmarks per slice: camera index + uv per slot
     # (padding included: it is streamed), slice header (32 landmark ids + row pointer), per landmark the packed X
     # (32 B) and fold (6 x 8 B in step 1) read and H written (32 B), camera records once (176 B each; the blocks
     # stage them from L2)
@@ -329,7 +329,7 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     dom = 0 if ksec[0] >= ksec[1] else 1
     dom_bytes = own_a if dom == 0 else own_b
-    dom_name = "k_e0_landmark_sell<pose>" if dom == 0 else "k_passB_e0_v2<pose>"
+    dom_name = "k_sell_walk<E0LandmarkOp<pose>>" if dom == 0 else "k_passB_e0_v2<pose>"
     traffic = None
     try:   # measured DRAM bytes per launch of that kernel (one ncu --set full capture, committed)
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:

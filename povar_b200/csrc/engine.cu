@@ -316,7 +316,8 @@ void build_sell(const std::vector<int>& lm_ptr, const int* obs_cam, int num_cams
   if (L <= 0) return;
   const int T = host_threads(L);
   auto chunk_begin = [&](int t) { return static_cast<int>(static_cast<long long>(L) * t / T); };
-  auto key = [&](int l) { return sell_key(obs_cam + lm_ptr[l], lm_ptr[l + 1] - lm_ptr[l], kSellKeySpan); };
+  // key camera of every landmark (-1: not in the set), made once
+  std::vector<int> keys(static_cast<size_t>(L));
   // landmarks with 1..32 observations by key camera: stable counting sort, one histogram per chunk
   // (chunk t's landmarks of a camera go after those of the chunks before it)
   std::vector<std::vector<int>> hist(T, std::vector<int>(static_cast<size_t>(num_cams), 0));
@@ -325,8 +326,13 @@ void build_sell(const std::vector<int>& lm_ptr, const int* obs_cam, int num_cams
     std::vector<int>& h = hist[t];
     for (int l = chunk_begin(t); l < chunk_begin(t + 1); ++l) {
       const int deg = lm_ptr[l + 1] - lm_ptr[l];
-      if (deg > 32) longs[t].push_back(l);
-      else if (deg > 0) h[key(l)]++;
+      keys[l] = -1;
+      if (deg > 32) {
+        longs[t].push_back(l);
+      } else if (deg > 0) {
+        keys[l] = sell_key(obs_cam + lm_ptr[l], deg, kSellKeySpan);
+        h[keys[l]]++;
+      }
     }
   });
   for (int t = 0; t < T; ++t) out->long_lms.insert(out->long_lms.end(), longs[t].begin(), longs[t].end());
@@ -334,7 +340,7 @@ void build_sell(const std::vector<int>& lm_ptr, const int* obs_cam, int num_cams
   for (int c = 0; c < num_cams; ++c) {
     for (int t = 0; t < T; ++t) {
       const int cnt = hist[t][c];
-      hist[t][c] = n;   // first position of chunk t's landmarks with median camera c
+      hist[t][c] = n;   // first position of chunk t's landmarks with key camera c
       n += cnt;
     }
   }
@@ -342,8 +348,7 @@ void build_sell(const std::vector<int>& lm_ptr, const int* obs_cam, int num_cams
   parallel_chunks(T, [&](int t) {
     std::vector<int>& h = hist[t];
     for (int l = chunk_begin(t); l < chunk_begin(t + 1); ++l) {
-      const int deg = lm_ptr[l + 1] - lm_ptr[l];
-      if (deg > 0 && deg <= 32) by_cam[h[key(l)]++] = l;
+      if (keys[l] >= 0) by_cam[h[keys[l]]++] = l;
     }
   });
   // windows of `window` landmarks of that order, each sorted (stably) by descending degree and cut into
