@@ -352,7 +352,8 @@ def main():
         "bytes_per_launch": dom_bytes, "kernel_us": 1e6 * ksec[dom],
         "term_kernels_us": {"landmark_pass": 1e6 * ksec[0], "camera_pass": 1e6 * ksec[1],
                             "item_reduce_multi_gpu_only": 1e6 * ksec[2], "binv_norms_test": 1e6 * ksec[3]},
-        "sell_slots": slots, "sell_padding": slots / max(lnnz, 1) - 1.0,
+        "sell_slots": slots, "sell_slots_per_observation": slots / max(lnnz, 1),   # < 1: long landmarks stay in CSR
+
         "term_us": 1e6 * term_s,
         "term_own_bytes": own_a + own_b,
         "term_own_gbs": (own_a + own_b) / term_s / 1e9,
