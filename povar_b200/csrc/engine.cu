@@ -1173,15 +1173,19 @@ int Engine::solve_power(bool joint, double lambda) {
   return POVAR_OK;
 }
 
-// The launches of one power series -- b -> x0, series start, then per term landmark half, camera half, term
-// kernel -- have the same arguments in every solve of a model (the damping enters before, the early exit is
-// decided on the device, the number of a peer exchange is a device-side counter): they are captured once into
-// a CUDA graph and replayed, one launch per solve instead of 3 m + 2.  The first solve of a model runs eagerly
-// (it sets function attributes and allocates nothing afterwards), the second is captured.
+// One power series is b -> x0, series start, then per term landmark half, camera half, term kernel -- the same
+// arguments in every solve of a model (the damping enters before, the stopping rule is applied on the device, the
+// number of a peer exchange and of a term are device-side counters).  It is built once per model as a CUDA graph
+// with a conditional WHILE node whose body is one term: k_series_start and the last block of k_term16 set the
+// condition (cudaGraphSetConditional), so a solve is ONE launch that runs exactly the terms the reference's
+// stopping rule asks for.  (Until this round the graph held all m terms and the converged ones returned at once:
+// 430 skipped launches of 2-4 us per venice-1778 solve.)  The first solve of a model runs eagerly -- it sets
+// function attributes -- and so does a series whose exchange is ncclAllReduce (no peer memory).
 int Engine::enqueue_series(bool joint) {
   const int m = opt_.power_sc_iterations;
   const int which = joint ? 1 : 0;
-  auto enqueue = [&]() -> int {
+  const bool graphable = term_mode() != kTermRaw;
+  if (!graphable || series_calls_[which]++ == 0) {
     launch_finish_b(d_, joint, lc());
     launch_series_start(d_, opt_.r_tolerance, m, lc());
     for (int i = 1; i <= m; ++i) {
@@ -1189,32 +1193,75 @@ int Engine::enqueue_series(bool joint) {
       if (rc != POVAR_OK) return rc;
       launch_series_term(d_, joint, i, opt_.eta, opt_.r_tolerance, term_mode(), exchange(), lc());
     }
+    series_terms_counted_ = true;   // the launches above are in launches_ (skipped ones included)
     return POVAR_OK;
-  };
-  // NCCL's all-reduce per term (no peer exchange) stays outside graphs: eager
-  const bool graphable = term_mode() != kTermRaw;
-  if (!graphable || series_calls_[which]++ == 0) return enqueue();
+  }
   if (!series_graph_[which]) {
     const long long before = launches_;
     cudaGraph_t graph = nullptr;
-    PV_CUDA(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
-    const int rc = enqueue();
-    const cudaError_t ce = cudaStreamEndCapture(stream_, &graph);
-    if (rc != POVAR_OK || ce != cudaSuccess || graph == nullptr) {
-      if (graph) cudaGraphDestroy(graph);
+    cudaGraphConditionalHandle handle = 0;
+    PV_CUDA(cudaGraphCreate(&graph, 0));
+    auto bail = [&](cudaError_t e, const char* what) {
+      cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+      if (cudaStreamIsCapturing(stream_, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone) {
+        cudaGraph_t dummy = nullptr;
+        cudaStreamEndCapture(stream_, &dummy);
+      }
+      cudaGraphDestroy(graph);
       cudaGetLastError();
-      return rc != POVAR_OK ? rc : fail(POVAR_ERR_CUDA, "stream capture of the power series failed");
-    }
+      launches_ = before;
+      return e != cudaSuccess ? check(e, what) : fail(POVAR_ERR_CUDA, what);
+    };
+    cudaError_t e = cudaGraphConditionalHandleCreate(&handle, graph, 0, 0);   // set by k_series_start in every run
+    if (e != cudaSuccess) return bail(e, "cudaGraphConditionalHandleCreate");
+    SeriesLoop loop;
+    loop.handle = static_cast<unsigned long long>(handle);
+    loop.active = 1;
+    loop.max_terms = m;
+    // prefix: b -> x0, norms, loop condition
+    e = cudaStreamBeginCaptureToGraph(stream_, graph, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) return bail(e, "cudaStreamBeginCaptureToGraph");
+    launch_finish_b(d_, joint, lc());
+    launch_series_start(d_, opt_.r_tolerance, m, lc(), loop);
+    cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
+    const cudaGraphNode_t* deps = nullptr;
+    size_t num_deps = 0;
+    e = cudaStreamGetCaptureInfo(stream_, &status, nullptr, nullptr, &deps, &num_deps);
+    if (e != cudaSuccess || status != cudaStreamCaptureStatusActive) return bail(e, "cudaStreamGetCaptureInfo");
+    cudaGraphNodeParams params{};
+    params.type = cudaGraphNodeTypeConditional;
+    params.conditional.handle = handle;
+    params.conditional.type = cudaGraphCondTypeWhile;
+    params.conditional.size = 1;
+    cudaGraphNode_t loop_node = nullptr;
+    e = cudaGraphAddNode(&loop_node, graph, deps, num_deps, &params);
+    if (e != cudaSuccess) return bail(e, "cudaGraphAddNode(conditional)");
+    e = cudaStreamUpdateCaptureDependencies(stream_, &loop_node, 1, cudaStreamSetCaptureDependencies);
+    if (e != cudaSuccess) return bail(e, "cudaStreamUpdateCaptureDependencies");
+    cudaGraph_t same = nullptr;
+    e = cudaStreamEndCapture(stream_, &same);
+    if (e != cudaSuccess) return bail(e, "cudaStreamEndCapture");
+    // body: one term
+    cudaGraph_t body = params.conditional.phGraph_out[0];
+    e = cudaStreamBeginCaptureToGraph(stream_, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) return bail(e, "cudaStreamBeginCaptureToGraph(body)");
+    const int rc = e0_product(joint, true, true);
+    launch_series_term(d_, joint, 0, opt_.eta, opt_.r_tolerance, term_mode(), exchange(), lc(), loop);
+    e = cudaStreamEndCapture(stream_, &same);
+    if (rc != POVAR_OK || e != cudaSuccess) return bail(e, "stream capture of a power-series term failed");
     cudaGraphExec_t exec = nullptr;
-    const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+    e = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
-    if (ie != cudaSuccess) return check(ie, "cudaGraphInstantiate");
+    if (e != cudaSuccess) {
+      launches_ = before;
+      return check(e, "cudaGraphInstantiate");
+    }
     series_graph_[which] = exec;
-    series_graph_launches_[which] = launches_ - before;
     launches_ = before;   // nothing ran during the capture
   }
   PV_CUDA(cudaGraphLaunch(static_cast<cudaGraphExec_t>(series_graph_[which]), stream_));
-  launches_ += series_graph_launches_[which];
+  launches_ += 2;                  // b -> x0 and the series start; the terms are counted when the solve reports them
+  series_terms_counted_ = false;
   return POVAR_OK;
 }
 
@@ -1229,9 +1276,17 @@ int Engine::finish_solve(bool joint, double* inc, int32_t* iterations) {
   times_.prepare += elapsed(ev_[0], ev_[1]);
   times_.reduced_solve += elapsed(ev_[1], ev_[2]);
   if (iterations) *iterations = h.iterations;
+  count_series_terms(h.term);
   if (h.peer_timeout) return fail(POVAR_ERR_NCCL, "peer exchange of the camera sums timed out (a rank is gone?)");
   if (h.nonfinite) return POVAR_NUM_NONFINITE_INC;
   return POVAR_OK;
+}
+
+// kernels the loop of the series graph ran: three per term (the host learns the count with the solve's results)
+void Engine::count_series_terms(int terms) {
+  if (series_terms_counted_) return;
+  series_terms_counted_ = true;
+  launches_ += 3LL * terms;
 }
 
 int Engine::enqueue_solve(bool joint, double lambda) {
@@ -1515,6 +1570,7 @@ int Engine::trial(bool joint, double alpha, double lambda, int32_t* iterations, 
     if (v[9] > 0) return fail(POVAR_NUM_LINEARIZATION, "did not expect numerical failure during linearization");
   }
   if (iterations) *iterations = hctl->iterations;
+  count_series_terms(hctl->term);
   if (l_diff) *l_diff = v[8];
   if (ri) decode_cost(v, ri);
   if (hctl->peer_timeout) return fail(POVAR_ERR_NCCL, "peer exchange of the camera sums timed out (a rank is gone?)");

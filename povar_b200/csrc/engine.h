@@ -97,10 +97,11 @@ class Engine {
   double* P_prev_ = nullptr;      // cameras of the linearisation point during a VarPro apply
   bool lin_check_pending_ = false;  // linearize(defer_check): the flag is read with the next trial
   double* host_out_ = nullptr;    // pinned: [SeriesCtl (64 B) | trial_out (16 doubles)]
-  // the 3 x power_sc_iterations launches of a power series as one CUDA graph per model (pOSE / joint)
+  // a power series as one CUDA graph per model (pOSE / joint): prefix + WHILE node around one term
   void* series_graph_[2] = {nullptr, nullptr};   // cudaGraphExec_t
-  long long series_graph_launches_[2] = {0, 0};
   int series_calls_[2] = {0, 0};
+  bool series_terms_counted_ = true;             // the term launches of the last series are in launches_
+  void count_series_terms(int terms);
   double* chol_linv_ = nullptr;   // CHOLESKY: inverses of the factor's diagonal tiles [n_pad / 64][64][64]
   double* chol_rhs_ = nullptr;    // CHOLESKY: padded right-hand side / solution [n_pad]
   // distributed

@@ -763,8 +763,9 @@ k_term16(int C, const double* __restrict__ raw_in, const int* __restrict__ cam_i
          const double* __restrict__ P, const double* __restrict__ Binv, double* __restrict__ tmp,
          double* __restrict__ acc, double* __restrict__ y, double* __restrict__ cam_rec,
          double* __restrict__ norm_part, int term, double eta, double r_tolerance, SeriesCtl* ctl,
-         PeerExchange px) {
+         PeerExchange px, SeriesLoop loop) {
   if (ctl->done) return;
+  if (term <= 0) term = ctl->term + 1;   // inside the loop of the series graph (the last block advances the count)
   constexpr int D = JOINT ? 11 : 12;
   __shared__ double smem[2 * (kBlock / 32)];
   __shared__ int is_last;
@@ -919,14 +920,19 @@ k_term16(int C, const double* __restrict__ raw_in, const int* __restrict__ cam_i
   if (threadIdx.x == 0) {
     ctl->ticket = 0;
     ctl->next_block = 0;
+    ctl->term = term;
     if (MODE == kTermPeer) *px.count = epoch;   // this exchange happened (skipped terms never get here)
     series_decide(s0, s1, term, eta, r_tolerance, ctl);
+    if (loop.active) {
+      cudaGraphSetConditional(static_cast<cudaGraphConditionalHandle>(loop.handle),
+                              (ctl->done || term >= loop.max_terms) ? 0u : 1u);
+    }
   }
 }
 
 __global__ void __launch_bounds__(kBlock)
 k_series_start(int C, const double* __restrict__ norm_part, double r_tolerance, int max_terms,
-               SeriesCtl* ctl) {
+               SeriesCtl* ctl, SeriesLoop loop) {
   __shared__ double smem[2 * (kBlock / 32)];
   double s0, s1;
   sum_norm_parts(C, norm_part, smem, s0, s1);
@@ -937,6 +943,10 @@ k_series_start(int C, const double* __restrict__ norm_part, double r_tolerance, 
     ctl->norm0 = r_tolerance > 0 ? sqrt(s0) : 0.0;
     ctl->last_tmp_norm = sqrt(s0);
     ctl->last_acc_norm = sqrt(s1);
+    ctl->term = 0;
+    if (loop.active) {
+      cudaGraphSetConditional(static_cast<cudaGraphConditionalHandle>(loop.handle), max_terms > 0 ? 1u : 0u);
+    }
   }
 }
 
@@ -1086,8 +1096,9 @@ void launch_finish_b(const DeviceState& d, bool joint, const LaunchCfg& lc) {
   count(lc);
 }
 
-void launch_series_start(const DeviceState& d, double r_tolerance, int max_terms, const LaunchCfg& lc) {
-  k_series_start<<<1, kBlock, 0, lc.stream>>>(d.ix.C, d.norm_part, r_tolerance, max_terms, d.ctl);
+void launch_series_start(const DeviceState& d, double r_tolerance, int max_terms, const LaunchCfg& lc,
+                         const SeriesLoop& loop) {
+  k_series_start<<<1, kBlock, 0, lc.stream>>>(d.ix.C, d.norm_part, r_tolerance, max_terms, d.ctl, loop);
   count(lc);
 }
 
@@ -1166,7 +1177,7 @@ void launch_peer_allreduce(const DeviceState& d, double* buf, size_t n, const Pe
 }
 
 void launch_series_term(const DeviceState& d, bool joint, int term, double eta, double r_tolerance,
-                        TermMode mode, const PeerExchange* px, const LaunchCfg& lc) {
+                        TermMode mode, const PeerExchange* px, const LaunchCfg& lc, const SeriesLoop& loop) {
   const int blocks = (d.ix.C + 15) / 16;
   const PeerExchange none{};
   const PeerExchange& pe = (mode == kTermPeer && px != nullptr) ? *px : none;
@@ -1174,7 +1185,7 @@ void launch_series_term(const DeviceState& d, bool joint, int term, double eta, 
   k_term16<J, M><<<blocks, kBlock, 0, lc.stream>>>(d.ix.C, d.cam_raw, d.ix.cam_item_ptr, d.item_part,  \
                                                    d.pose_scale, d.P, d.Binv, d.vec_tmp, d.vec_acc,    \
                                                    d.vec_y, d.cam_rec, d.norm_part, term, eta,         \
-                                                   r_tolerance, d.ctl, pe)
+                                                   r_tolerance, d.ctl, pe, loop)
   if (joint) {
     if (mode == kTermPeer) POVAR_TERM(true, kTermPeer);
     else if (mode == kTermFused) POVAR_TERM(true, kTermFused);

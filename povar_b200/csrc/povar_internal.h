@@ -76,6 +76,16 @@ struct SeriesCtl {
   double last_acc_norm;
   unsigned int ticket; // last-block election
   unsigned int next_block;  // peer mode: logical block numbers in dispatch order
+  int term;            // terms of the running series that are complete (the loop of the series graph counts here)
+};
+
+// The series as a loop of the CUDA graph (Engine::enqueue_series): `handle` is the conditional handle of the WHILE
+// node whose body is one term; k_series_start and the last block of k_term16 set it (cudaGraphSetConditional), so
+// a series runs exactly the terms the reference's stopping rule asks for and nothing is enqueued to be skipped.
+struct SeriesLoop {
+  unsigned long long handle = 0;   // cudaGraphConditionalHandle
+  int active = 0;                  // 0: terms are enqueued one by one with their number (eager launches, benchmarks)
+  int max_terms = 0;
 };
 
 // scalars of the preconditioned conjugate gradients (PCG / RIPCG), kept on the device: the iteration decides there
@@ -259,13 +269,16 @@ void launch_cam_precond(const DeviceState& d, bool joint, const double* kron_sdi
 enum PassBMode { PASSB_E0 = 0, PASSB_B = 1 };
 void launch_passB(const DeviceState& d, const ModelParams& mp, bool joint, const LaunchCfg& lc);
 // series bookkeeping
-void launch_series_start(const DeviceState& d, double r_tolerance, int max_terms, const LaunchCfg& lc);
+void launch_series_start(const DeviceState& d, double r_tolerance, int max_terms, const LaunchCfg& lc,
+                         const SeriesLoop& loop = SeriesLoop());
 // mode kTermFused: the term kernel adds the item partials of the camera half itself (single GPU);
 // kTermPeer: it also pushes them to every rank's receive buffer and adds the ranks' sums in rank order
 // (px, with px->epoch set for this exchange); kTermRaw: it reads cam_raw (after launch_reduce_items and
 // the NCCL all-reduce)
+// term > 0: the number of the term; 0 (inside the loop of the series graph): one more than ctl->term
 void launch_series_term(const DeviceState& d, bool joint, int term, double eta, double r_tolerance,
-                        TermMode mode, const PeerExchange* px, const LaunchCfg& lc);
+                        TermMode mode, const PeerExchange* px, const LaunchCfg& lc,
+                        const SeriesLoop& loop = SeriesLoop());
 
 // buf[0..n) += the other ranks' buf, over the peer buffers (n <= px.stride): what ncclAllReduce(sum) would do,
 // every rank adding in rank order
