@@ -755,6 +755,9 @@ int Engine::upload(const povar_problem_desc* desc) {
   PV_ALLOC(ix.sell_lm, sell.sell_lm.size());
   PV_ALLOC(ix.sell_cam, slots);
   PV_ALLOC(ix.sell_uv, slots);
+  PV_ALLOC(ix.sell_cam_e0, slots);
+  PV_ALLOC(ix.sell_uv_e0, slots);
+  PV_ALLOC(ix.sell_row_e0, slots + 32);
   PV_ALLOC(ix.obs_slot, nnz);
   PV_ALLOC(ix.long_lm, sell.long_lms.size());
 #define PV_UP(dst, src, n) PV_CUDA(cudaMemcpyAsync((dst), (src), (n), cudaMemcpyHostToDevice, stream_))
@@ -773,7 +776,7 @@ int Engine::upload(const povar_problem_desc* desc) {
     // [0..2] landmark half of a term (pOSE, joint, pOSE + HUBER); [3], [4] once-per-trial walks: more registers
     // per lane (16 warps per SM), no long landmarks, 256 bytes of static shared memory for the block sums
     const int rec_bytes = 8 * (m == 1 ? kCamRecJoint : m == 3 ? kCamTab1 : m == 4 ? kCamTab2 : kCamRecPose);
-    const int stage_bytes = (m == 1 || m == 2) ? kStageWide : kStagePose;
+    const int stage_bytes = (m == 1 || m == 2) ? kStageWide : (m == 3 ? kStageLin : kStagePose);
     lm_plans[m] = m < 3 ? plan_landmark_half(sell, C, ix.num_long, rec_bytes, stage_bytes, sm_count(), 32, 0)
                         : plan_landmark_half(sell, C, 0, rec_bytes, stage_bytes, sm_count(), 16, 256);
     const LmPlanHost& h = lm_plans[m];
@@ -1707,6 +1710,7 @@ int64_t Engine::debug_read(const char* name, double* out, int64_t capacity) {
   else if (n == "slice_ptr") isrc = d_.ix.slice_ptr, count = d_.ix.num_slices + 1;
   else if (n == "sell_lm") isrc = d_.ix.sell_lm, count = static_cast<int64_t>(kSellWidth) * d_.ix.num_slices;
   else if (n == "sell_cam") isrc = d_.ix.sell_cam, count = d_.ix.sell_slots;
+  else if (n == "sell_cam_e0") isrc = d_.ix.sell_cam_e0, count = d_.ix.sell_slots;
   else if (n == "obs_slot") isrc = d_.ix.obs_slot, count = nnz_;
   else {
     fail(POVAR_ERR_INVALID, "debug_read: unknown array '" + n + "'");

@@ -1,6 +1,6 @@
 // Device-side construction of the per-observation index arrays from the canonical landmark-major
 // list (lm_ptr, obs_cam, obs_uv):  obs_lm, the camera-major copy (csc_lm, csc_uv) and the sliced-ELL
-// copy (sell_cam, sell_uv, obs_slot).  The host only derives the small tables (tiles, items, slice
+// copies (sell_cam, sell_uv, obs_slot; sell_cam_e0, sell_uv_e0, sell_row_e0).  The host only derives the small tables (tiles, items, slice
 // table) -- scattering 5 M observations into three orders is a few hundred milliseconds of cache
 // misses on one host core and well under a millisecond here.
 //
@@ -53,10 +53,60 @@ k_lm_slot(int groups, const int* __restrict__ slice_ptr, const int* __restrict__
   if (lm >= 0) lm_slot[lm] = kSellWidth * slice_ptr[i / kSellWidth] + (i % kSellWidth);
 }
 
+// Row of every observation inside its slice.  A lane of the landmark-major walks (sell_walk.cuh) reads the record
+// of its observation's camera from shared memory with LDS.128; the eight lanes of a quarter warp are served
+// together, and two of them collide when their records start in the same bank group, i.e. (records are an odd
+// number of 16-byte units) when their cameras are congruent mod 8.  With the k-th observation of every landmark in
+// row k the eight cameras of a quarter are as good as random: 2.55 wavefronts per quarter instead of 1, and the
+// walks are bound by exactly that.  The order of a landmark's observations is free -- it only fixes the order of
+// its sums -- so one thread per quarter warp places the observations of its eight landmarks greedily: each goes to
+// the free row (of this landmark) where the fewest earlier lanes of the quarter have a camera of the same class.
+// Deterministic (a function of the layout alone); rows beyond a landmark's degree are padding wherever they end up.
+__global__ void __launch_bounds__(128)
+k_sell_rows(int quarters, const int* __restrict__ slice_ptr, const int* __restrict__ sell_lm,
+            const int* __restrict__ lm_ptr, const int* __restrict__ obs_cam, unsigned char* __restrict__ obs_row) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= quarters) return;
+  const int sl = q >> 2;
+  const int len = slice_ptr[sl + 1] - slice_ptr[sl];   // 1..32 rows
+  unsigned int hist[32];                               // per row: eight 4-bit counters, one per camera class
+  for (int r = 0; r < 32; ++r) hist[r] = 0u;
+  for (int j = 0; j < 8; ++j) {
+    const int lm = sell_lm[kSellWidth * sl + 8 * (q & 3) + j];
+    if (lm < 0) continue;
+    unsigned int used = 0u;
+    const int ob = lm_ptr[lm], oe = lm_ptr[lm + 1];
+    for (int o = ob; o < oe; ++o) {
+      const int shift = 4 * (obs_cam[o] & 7);
+      int best = 0;
+      unsigned int best_cnt = 0xffu;
+      for (int r = 0; r < len; ++r) {
+        if ((used >> r) & 1u) continue;
+        const unsigned int cnt = (hist[r] >> shift) & 0xfu;
+        if (cnt < best_cnt) {
+          best_cnt = cnt;
+          best = r;
+        }
+      }
+      used |= 1u << best;
+      hist[best] += 1u << shift;
+      obs_row[o] = static_cast<unsigned char>(best);
+    }
+  }
+}
+
+// Two sliced-ELL copies of the observations: the NATURAL one (k-th observation of a landmark in row k: the
+// once-per-trial walks sum a landmark's observations in camera order, like the reference's loops -- the
+// ill-conditioned direct solve of CHOLESKY amplifies even the order of those sums to 1e-9 within five iterations)
+// and the one of the power-series term kernel with the rows of k_sell_rows.  sell_row_e0 [natural slot] = row
+// (inside the slice) of the same observation in the second copy: the linearisation writes the coefficients the
+// term kernel streams straight to where it reads them.
 __global__ void __launch_bounds__(kBlock)
 k_sell_fill(int nnz, const int* __restrict__ lm_ptr, const int* __restrict__ obs_lm,
             const int* __restrict__ obs_cam, const double2* __restrict__ obs_uv,
-            const int* __restrict__ lm_slot, int* __restrict__ sell_cam, double2* __restrict__ sell_uv,
+            const int* __restrict__ lm_slot, const unsigned char* __restrict__ obs_row,
+            int* __restrict__ sell_cam, double2* __restrict__ sell_uv, int* __restrict__ sell_cam_e0,
+            double2* __restrict__ sell_uv_e0, unsigned char* __restrict__ sell_row_e0,
             int* __restrict__ obs_slot) {
   const int o = blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= nnz) return;
@@ -65,8 +115,14 @@ k_sell_fill(int nnz, const int* __restrict__ lm_ptr, const int* __restrict__ obs
   int slot = -1;
   if (base >= 0) {
     slot = base + kSellWidth * (o - lm_ptr[l]);
-    sell_cam[slot] = obs_cam[o];
-    sell_uv[slot] = obs_uv[o];
+    const int slot_e0 = base + kSellWidth * obs_row[o];
+    const int c = obs_cam[o];
+    const double2 uv = obs_uv[o];
+    sell_cam[slot] = c;
+    sell_uv[slot] = uv;
+    sell_cam_e0[slot_e0] = c;
+    sell_uv_e0[slot_e0] = uv;
+    sell_row_e0[slot] = obs_row[o];
   }
   obs_slot[o] = slot;
 }
@@ -82,7 +138,8 @@ size_t index_sort_temp_bytes(int nnz, int num_cams) {
   return bytes;
 }
 
-// scratch: iota [nnz], keys_out [nnz], perm [nnz], lm_slot [L], cub temp
+// scratch: iota [nnz] (reused for the row numbers once the sort is done), keys_out [nnz], perm [nnz], lm_slot [L],
+// cub temp
 cudaError_t build_device_index(const DeviceIndex& ix, int* iota, int* keys_out, int* perm, int* lm_slot,
                                void* sort_temp, size_t sort_temp_bytes, const LaunchCfg& lc) {
   const int nnz = ix.nnz, L = ix.L;
@@ -105,13 +162,25 @@ cudaError_t build_device_index(const DeviceIndex& ix, int* iota, int* keys_out, 
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(ix.sell_cam, 0xFF, sizeof(int) * static_cast<size_t>(ix.sell_slots), st);
     if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(ix.sell_cam_e0, 0xFF, sizeof(int) * static_cast<size_t>(ix.sell_slots), st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(ix.sell_row_e0, 0, static_cast<size_t>(ix.sell_slots), st);
+    if (e != cudaSuccess) return e;
     const int groups = kSellWidth * ix.num_slices;
     if (groups > 0) {
       k_lm_slot<<<(groups + kBlock - 1) / kBlock, kBlock, 0, st>>>(groups, ix.slice_ptr, ix.sell_lm, lm_slot);
       ++launches;
     }
-    k_sell_fill<<<blocks, kBlock, 0, st>>>(nnz, ix.lm_ptr, ix.obs_lm, ix.obs_cam, ix.obs_uv, lm_slot,
-                                           ix.sell_cam, ix.sell_uv, ix.obs_slot);
+    unsigned char* obs_row = reinterpret_cast<unsigned char*>(iota);   // the sort has consumed iota
+    const int quarters = 4 * ix.num_slices;
+    if (quarters > 0) {
+      k_sell_rows<<<(quarters + 127) / 128, 128, 0, st>>>(quarters, ix.slice_ptr, ix.sell_lm, ix.lm_ptr, ix.obs_cam,
+                                                         obs_row);
+      ++launches;
+    }
+    k_sell_fill<<<blocks, kBlock, 0, st>>>(nnz, ix.lm_ptr, ix.obs_lm, ix.obs_cam, ix.obs_uv, lm_slot, obs_row,
+                                           ix.sell_cam, ix.sell_uv, ix.sell_cam_e0, ix.sell_uv_e0, ix.sell_row_e0,
+                                           ix.obs_slot);
     launches += 5;   // iota, radix sort (counted once), gather, fill
   }
   if (lc.launch_counter) *lc.launch_counter += launches;

@@ -929,6 +929,7 @@ struct WalkBase {
 template <bool JOINT>
 struct LinLandmarkOp : WalkBase {
   static constexpr int kRec = kCamTab1;
+  static constexpr int kStage = kStageLin;   // camera indices, (u, v), rows of the term kernel's copy
   static constexpr int NV = JOINT ? 14 : 9;
   const double* X;
   double c1, c2;
@@ -945,13 +946,23 @@ struct LinLandmarkOp : WalkBase {
   double* sell_w;   // step 1 with HUBER: [row][32]
 
   struct Lane {
-    int lm, lm1, lm2;
+    int lm, lm1, lm2, row0;
     bool bad;
     double x[4], x1[4], acc[NV];
   };
 
+  __device__ __forceinline__ void issue(const DeviceIndex& ix, int row, unsigned char* stage,
+                                        unsigned long long* bar) const {
+    const size_t slot = kSellWidth * static_cast<size_t>(row);
+    mbar_expect_tx(bar, kStageLin);
+    bulk_copy_g2s(stage, ix.sell_cam + slot, 128u, bar);
+    bulk_copy_g2s(stage + 128, ix.sell_uv + slot, 512u, bar);
+    bulk_copy_g2s(stage + 640, ix.sell_row_e0 + slot, 32u, bar);
+  }
+
   __device__ __forceinline__ void open(Lane& st, const DeviceIndex& ix, int sl, int lane, int last) const {
     open_landmark(st, ix, X, sl, lane, last, 0.0);
+    st.row0 = __ldg(ix.slice_ptr + sl);
     st.bad = false;
 #pragma unroll
     for (int k = 0; k < NV; ++k) st.acc[k] = 0.0;
@@ -968,7 +979,9 @@ struct LinLandmarkOp : WalkBase {
       double j0[4], j1[4];
       ob.jl_rows(cam, j0, j1);
       const double w = ob.sw * ob.sw;
-      double* sp = sell_d + 3 * kSellWidth * static_cast<size_t>(row) + lane;
+      // where the term kernel reads this observation (its copy has other rows inside a slice)
+      const int row_e0 = st.row0 + stage[640 + lane];
+      double* sp = sell_d + 3 * kSellWidth * static_cast<size_t>(row_e0) + lane;
       sp[0] = ob.sw * ob.iz;
       sp[kSellWidth] = ob.sw * ob.d02;
       sp[2 * kSellWidth] = ob.sw * ob.d12;
@@ -986,7 +999,7 @@ struct LinLandmarkOp : WalkBase {
       PoseObs ob;
       ob.eval(cam, uv.x, uv.y, st.x, c1, c2, rb);
       const double w = ob.sw * ob.sw;
-      if (sell_w != nullptr) sell_w[kSellWidth * static_cast<size_t>(row) + lane] = w;
+      if (sell_w != nullptr) sell_w[kSellWidth * static_cast<size_t>(st.row0 + stage[640 + lane]) + lane] = w;
       int n = 0;
 #pragma unroll
       for (int a = 0; a < 3; ++a) {

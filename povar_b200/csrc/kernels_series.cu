@@ -203,11 +203,11 @@ struct E0LandmarkOp {
                                         unsigned long long* bar) const {
     const size_t slot = kSellWidth * static_cast<size_t>(row);
     mbar_expect_tx(bar, kStage);
-    bulk_copy_g2s(stage, ix.sell_cam + slot, 128u, bar);
+    bulk_copy_g2s(stage, ix.sell_cam_e0 + slot, 128u, bar);
     if (JOINT) {
       bulk_copy_g2s(stage + 128, sell_d + 3 * slot, 768u, bar);
     } else {
-      bulk_copy_g2s(stage + 128, ix.sell_uv + slot, 512u, bar);
+      bulk_copy_g2s(stage + 128, ix.sell_uv_e0 + slot, 512u, bar);
       if (HASW) bulk_copy_g2s(stage + 640, sell_w + slot, 256u, bar);
     }
   }

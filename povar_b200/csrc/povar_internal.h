@@ -32,8 +32,13 @@ struct DeviceIndex {
   int num_slices = 0;
   int* slice_ptr = nullptr;   // [num_slices+1] first row of the slice
   int* sell_lm = nullptr;     // [32*num_slices] landmark of lane g, -1 = none
-  int* sell_cam = nullptr;    // [32*rows]
+  int* sell_cam = nullptr;    // [32*rows] k-th observation of a landmark in row k of its slice
   double2* sell_uv = nullptr; // [32*rows]
+  // the copy the power-series term kernel streams: inside a landmark the observations sit in the rows
+  // k_sell_rows chose (fewer shared-memory bank conflicts between the lanes of a quarter warp)
+  int* sell_cam_e0 = nullptr;           // [32*rows]
+  double2* sell_uv_e0 = nullptr;        // [32*rows]
+  unsigned char* sell_row_e0 = nullptr; // [32*rows] by slot of the first copy: row inside the slice in the second
   int* obs_slot = nullptr;    // [nnz] slot of the observation, -1 for landmarks outside the SELL set
   long long sell_slots = 0;   // 32 * rows
   int num_long = 0;           // landmarks with more than 32 observations: one warp each, CSR arrays
@@ -60,6 +65,8 @@ constexpr int kCamTab1 = 14, kCamTab2 = 26;
 // bytes of one row of the observation stream of the landmark half: 32 camera indices + 32 x (u, v) in step 1
 // (+ 32 robust weights with HUBER), 32 camera indices + 3 x 32 coefficients in step 2
 constexpr int kStagePose = 128 + 512, kStageWide = 128 + 768;
+// the linearisation walk also streams the 32 row numbers of sell_row_e0
+constexpr int kStageLin = kStagePose + 32;
 // shared memory of a block of the landmark half ahead of the rings: one mbarrier for the window and one per
 // ring stage, rounded up to 128 bytes
 __host__ __device__ constexpr int lm_bar_bytes(int warps, int stages) { return ((1 + warps * stages) * 8 + 127) / 128 * 128; }

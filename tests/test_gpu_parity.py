@@ -332,3 +332,48 @@ def test_peer_exchange_protocol_on_one_gpu(monkeypatch):
     s.close()
     assert [e.cost for e in its] == [e.cost for e in plain]
     assert [e.linear_solver_iterations for e in its] == [e.linear_solver_iterations for e in plain]
+
+
+@pytest.mark.parametrize("shape", ["small", "ladybug49", "trafalgar257"])
+def test_sliced_ell_copies_hold_every_observation_once_and_the_second_spreads_the_bank_groups(shape):
+    """The device-side sliced-ELL copies (kernels_index.cu).  First copy: the k-th observation of a landmark with
+    1..32 observations in row k of its slice, in the lane of its landmark (what the once-per-trial walks read:
+    sums in camera order).  Second copy (the term kernel's): the same observations, each landmark's in rows of its
+    own choosing inside the slice (k_sell_rows) -- and the choice does what it is for: fewer lanes of a quarter
+    warp with cameras congruent mod 8 (the shared-memory bank group of their records).  Everything else is
+    padding in both."""
+    sp = synthetic.generate_named(shape)
+    hp = capi.HostProblem.from_unordered(sp.num_cams, sp.num_lms, sp.obs_cam, sp.obs_lm, sp.obs_xy, sp.cam_params)
+    slice_ptr, sell_lm, long_lms = capi.sell_layout(hp)
+    s = capi.Solver(hp, capi.default_options(verbosity_level=0))
+    obs_slot = s.debug_read("obs_slot").astype(np.int64)
+    sell_cam = s.debug_read("sell_cam").astype(np.int64)
+    sell_cam_e0 = s.debug_read("sell_cam_e0").astype(np.int64)
+    s.close()
+    deg = np.diff(hp.lm_ptr)
+    lm_of_obs = np.repeat(np.arange(hp.num_lms), deg)
+    in_sell = deg[lm_of_obs] <= 32
+    where = np.full(hp.num_lms, -1, np.int64)
+    where[sell_lm[sell_lm >= 0]] = np.nonzero(sell_lm >= 0)[0]
+    sl, lane = where[lm_of_obs[in_sell]] // 32, where[lm_of_obs[in_sell]] % 32
+    k = (np.arange(hp.num_obs) - hp.lm_ptr[lm_of_obs])[in_sell]
+    natural = np.full(len(sell_cam), -1, np.int64)
+    natural[32 * (slice_ptr[sl] + k) + lane] = hp.obs_cam[in_sell]
+    assert np.array_equal(sell_cam, natural)
+    assert np.all(obs_slot[~in_sell] == -1)
+    assert np.array_equal(obs_slot[in_sell], 32 * (slice_ptr[sl] + k) + lane)
+    # second copy: per landmark (= per lane of a slice) the same cameras, in other rows of the same slice
+    assert len(sell_cam_e0) == len(natural)
+    for s_i in range(len(slice_ptr) - 1):
+        a = natural[32 * slice_ptr[s_i]:32 * slice_ptr[s_i + 1]].reshape(-1, 32)
+        b = sell_cam_e0[32 * slice_ptr[s_i]:32 * slice_ptr[s_i + 1]].reshape(-1, 32)
+        assert np.array_equal(np.sort(a, axis=0), np.sort(b, axis=0)), s_i
+
+    def quarter_wavefronts(cam_of_slot):
+        c = cam_of_slot.reshape(-1, 4, 8)                                       # [row][quarter][lane]
+        worst = np.zeros(c.shape[:2], np.int64)
+        for g in range(8):
+            worst = np.maximum(worst, ((c >= 0) & (c % 8 == g)).sum(axis=2))
+        return worst.sum()
+
+    assert quarter_wavefronts(sell_cam_e0) <= quarter_wavefronts(natural)
