@@ -457,4 +457,11 @@ def main():
 
 
 if __name__ == "__main__":
+    # stdout carries ONE JSON line: libraries that print there while they initialise (NCCL's version banner) go to
+    # stderr -- at the file-descriptor level, their writes do not pass through sys.stdout
+    sys.stdout.flush()
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(_real_stdout, "w")
     main()
+    sys.stdout.flush()
