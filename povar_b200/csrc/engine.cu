@@ -246,34 +246,6 @@ static void parallel_chunks(int chunks, F&& body) {   // body(chunk index)
   for (auto& th : pool) th.join();
 }
 
-// Tiles of the landmark-sorted observation array: runs of whole landmarks with <= 32
-// observations together, or a single landmark with more than 32.
-void build_tiles(const std::vector<int>& lm_ptr, std::vector<int>* tile_ptr) {
-  tile_ptr->clear();
-  const int L = static_cast<int>(lm_ptr.size()) - 1;
-  tile_ptr->push_back(0);
-  int cur = 0;  // observations in the open tile
-  for (int l = 0; l < L; ++l) {
-    const int deg = lm_ptr[l + 1] - lm_ptr[l];
-    if (deg == 0) continue;
-    if (deg > 32) {
-      if (cur > 0) {
-        tile_ptr->push_back(lm_ptr[l]);
-        cur = 0;
-      }
-      tile_ptr->push_back(lm_ptr[l + 1]);
-      continue;
-    }
-    if (cur + deg > 32) {
-      tile_ptr->push_back(lm_ptr[l]);
-      cur = 0;
-    }
-    cur += deg;
-  }
-  if (cur > 0) tile_ptr->push_back(lm_ptr[L]);
-  if (tile_ptr->size() == 1 && L >= 0 && lm_ptr[L] == 0) tile_ptr->clear(), tile_ptr->push_back(0);
-}
-
 // Sliced ELL order of the landmarks with 1..32 observations (the landmark half of E0 gives a lane
 // to each landmark and walks its observations serially, so the 32 landmarks of a slice should have the
 // same degree).  Landmarks are first put in the order of their KEY camera (stable counting sort): the centre
@@ -681,13 +653,18 @@ int Engine::upload(const povar_problem_desc* desc) {
     t_prev = now;
   };
   std::vector<int> lm_ptr(L + 1), cam_ptr(C + 1, 0);
+  SellLayout sell;    // sliced-ELL order: the long landmarks from the pass below, the slices from the device
+  int sell_n = 0;     // landmarks with 1..32 observations
   if (desc->lm_ptr[0] != 0 || desc->lm_ptr[L] != nnz) return fail(POVAR_ERR_INVALID, "lm_ptr does not span the observations");
   {
     const int T = host_threads(nnz);
     std::vector<std::vector<int>> counts(T, std::vector<int>(static_cast<size_t>(C), 0));
+    std::vector<std::vector<int>> longs(T);
+    std::vector<int> in_set(T, 0);
     std::vector<const char*> bad(T, nullptr);
     parallel_chunks(T, [&](int t) {
       std::vector<int>& cnt = counts[t];
+      int set_here = 0;   // (a local: the per-thread slots of in_set share a cache line)
       const int l0 = static_cast<int>(static_cast<long long>(L) * t / T);
       const int l1 = static_cast<int>(static_cast<long long>(L) * (t + 1) / T);
       for (int l = l0; l < l1; ++l) {
@@ -697,6 +674,8 @@ int Engine::upload(const povar_problem_desc* desc) {
           return;
         }
         lm_ptr[l] = static_cast<int>(b);
+        if (e - b > 32) longs[t].push_back(l);
+        else if (e > b) ++set_here;
         for (int64_t o = b; o < e; ++o) {
           const int c = desc->obs_cam[o];
           if (c < 0 || c >= C) {
@@ -710,41 +689,83 @@ int Engine::upload(const povar_problem_desc* desc) {
           cnt[c]++;
         }
       }
+      in_set[t] = set_here;
     });
     for (int t = 0; t < T; ++t) {
       if (bad[t]) return fail(POVAR_ERR_INVALID, bad[t]);
       for (int c = 0; c < C; ++c) cam_ptr[c + 1] += counts[t][c];
+      sell.long_lms.insert(sell.long_lms.end(), longs[t].begin(), longs[t].end());
+      sell_n += in_set[t];
     }
   }
   lm_ptr[L] = nnz;
   for (int c = 0; c < C; ++c) cam_ptr[c + 1] += cam_ptr[c];
   lap("validate + camera counts");
-  std::vector<int> tile_ptr, item_ptr, item_cam, cam_item_ptr;
-  build_tiles(lm_ptr, &tile_ptr);
+  // the observation list starts travelling now: the copies run while the host derives the work items and the
+  // sliced-ELL order below
+#define PV_UP(dst, src, n) PV_CUDA(cudaMemcpyAsync((dst), (src), (n), cudaMemcpyHostToDevice, stream_))
+  DeviceIndex& ix = d_.ix;
+  PV_ALLOC(ix.lm_ptr, L + 1);
+  PV_ALLOC(ix.obs_cam, nnz);
+  PV_ALLOC(ix.obs_lm, nnz);
+  PV_ALLOC(ix.obs_uv, nnz);
+  PV_UP(ix.lm_ptr, lm_ptr.data(), sizeof(int) * (L + 1));
+  if (nnz > 0) {
+    PV_UP(ix.obs_cam, desc->obs_cam, sizeof(int) * static_cast<size_t>(nnz));
+    PV_UP(ix.obs_uv, desc->obs_uv, sizeof(double) * 2 * static_cast<size_t>(nnz));
+  }
+  // the sliced-ELL order of the landmarks (rule: build_sell above, which the CPU tests check) on the device, as soon
+  // as the copies above have landed; the host derives the camera work items meanwhile
+  const int sell_slices = (sell_n + kSellWidth - 1) / kSellWidth;
+  const int window = sell_window(sell_n, kSellWindow);
+  std::vector<int> slice_len(static_cast<size_t>(sell_slices)), slice_lo(slice_len.size()), slice_hi(slice_len.size());
+  PV_ALLOC(ix.sell_lm, static_cast<size_t>(sell_slices) * kSellWidth);
+  if (sell_n > 0) {
+    int *keys_a = nullptr, *keys_b = nullptr, *ids_a = nullptr, *ids_b = nullptr, *d_len = nullptr, *d_lo = nullptr,
+        *d_hi = nullptr;
+    char* sort_temp = nullptr;
+    const size_t temp_bytes = sell_sort_temp_bytes(L, C, sell_n, window);
+    const size_t keep = allocs_.size();
+    PV_ALLOC(keys_a, L);
+    PV_ALLOC(keys_b, L);
+    PV_ALLOC(ids_a, L);
+    PV_ALLOC(ids_b, L);
+    PV_ALLOC(d_len, sell_slices);
+    PV_ALLOC(d_lo, sell_slices);
+    PV_ALLOC(d_hi, sell_slices);
+    PV_ALLOC(sort_temp, temp_bytes);
+    PV_CUDA(build_device_sell(L, C, sell_n, window, ix.lm_ptr, ix.obs_cam, keys_a, keys_b, ids_a, ids_b, sort_temp,
+                              temp_bytes, ix.sell_lm, d_len, d_lo, d_hi, lc()));
+    PV_CUDA(cudaMemcpyAsync(slice_len.data(), d_len, sizeof(int) * slice_len.size(), cudaMemcpyDeviceToHost, stream_));
+    PV_CUDA(cudaMemcpyAsync(slice_lo.data(), d_lo, sizeof(int) * slice_lo.size(), cudaMemcpyDeviceToHost, stream_));
+    PV_CUDA(cudaMemcpyAsync(slice_hi.data(), d_hi, sizeof(int) * slice_hi.size(), cudaMemcpyDeviceToHost, stream_));
+    while (allocs_.size() > keep) {
+      cudaFreeAsync(allocs_.back(), stream_);
+      allocs_.pop_back();
+    }
+  }
+  std::vector<int> item_ptr, item_cam, cam_item_ptr;
   build_items(cam_ptr, choose_item_len(nnz), &item_ptr, &item_cam, &cam_item_ptr);
-  lap("tiles + items");
-  SellLayout sell;
-  build_sell(lm_ptr, desc->obs_cam, C, kSellWindow, &sell);
-  lap("sliced-ELL order");
+  lap("items (+ device: sliced-ELL order)");
+  PV_CUDA(cudaStreamSynchronize(stream_));
+  sell.slice_ptr.assign(static_cast<size_t>(sell_slices) + 1, 0);
+  for (int sl = 0; sl < sell_slices; ++sl) sell.slice_ptr[sl + 1] = sell.slice_ptr[sl] + slice_len[sl];
+  sell.rows = sell.slice_ptr[sell_slices];
+  sell.slice_lo.swap(slice_lo);
+  sell.slice_hi.swap(slice_hi);
+  lap("wait for the order");
   if (static_cast<long long>(sell.rows) * kSellWidth >= (1LL << 31)) {
     return fail(POVAR_ERR_UNSUPPORTED, "sliced-ELL layout exceeds 2^31 slots in one shard");
   }
 
-  DeviceIndex& ix = d_.ix;
   ix.C = C;
   ix.L = L;
   ix.nnz = nnz;
-  ix.num_tiles = static_cast<int>(tile_ptr.size()) - 1;
   ix.num_items = static_cast<int>(item_cam.size());
   ix.num_slices = static_cast<int>(sell.slice_ptr.size()) - 1;
   ix.sell_slots = static_cast<long long>(kSellWidth) * sell.rows;
   ix.num_long = static_cast<int>(sell.long_lms.size());
   const size_t slots = static_cast<size_t>(ix.sell_slots);
-  PV_ALLOC(ix.lm_ptr, L + 1);
-  PV_ALLOC(ix.obs_cam, nnz);
-  PV_ALLOC(ix.obs_lm, nnz);
-  PV_ALLOC(ix.obs_uv, nnz);
-  PV_ALLOC(ix.tile_ptr, tile_ptr.size());
   PV_ALLOC(ix.cam_ptr, C + 1);
   PV_ALLOC(ix.csc_lm, nnz);
   PV_ALLOC(ix.csc_uv, nnz);
@@ -752,7 +773,6 @@ int Engine::upload(const povar_problem_desc* desc) {
   PV_ALLOC(ix.item_ptr, item_ptr.size());
   PV_ALLOC(ix.cam_item_ptr, C + 1);
   PV_ALLOC(ix.slice_ptr, sell.slice_ptr.size());
-  PV_ALLOC(ix.sell_lm, sell.sell_lm.size());
   PV_ALLOC(ix.sell_cam, slots);
   PV_ALLOC(ix.sell_uv, slots);
   PV_ALLOC(ix.sell_cam_e0, slots);
@@ -760,16 +780,8 @@ int Engine::upload(const povar_problem_desc* desc) {
   PV_ALLOC(ix.sell_row_e0, slots + 32);
   PV_ALLOC(ix.obs_slot, nnz);
   PV_ALLOC(ix.long_lm, sell.long_lms.size());
-#define PV_UP(dst, src, n) PV_CUDA(cudaMemcpyAsync((dst), (src), (n), cudaMemcpyHostToDevice, stream_))
-  PV_UP(ix.lm_ptr, lm_ptr.data(), sizeof(int) * (L + 1));
-  if (nnz > 0) {
-    PV_UP(ix.obs_cam, desc->obs_cam, sizeof(int) * static_cast<size_t>(nnz));
-    PV_UP(ix.obs_uv, desc->obs_uv, sizeof(double) * 2 * static_cast<size_t>(nnz));
-    PV_UP(ix.item_cam, item_cam.data(), sizeof(int) * item_cam.size());
-  }
-  PV_UP(ix.tile_ptr, tile_ptr.data(), sizeof(int) * tile_ptr.size());
+  if (nnz > 0) PV_UP(ix.item_cam, item_cam.data(), sizeof(int) * item_cam.size());
   PV_UP(ix.slice_ptr, sell.slice_ptr.data(), sizeof(int) * sell.slice_ptr.size());
-  if (!sell.sell_lm.empty()) PV_UP(ix.sell_lm, sell.sell_lm.data(), sizeof(int) * sell.sell_lm.size());
   // landmark half: ranges of slices per warp, windows of cameras per block (kernels_series.cu), per model
   LmPlanHost lm_plans[5];   // alive until the synchronisation at the end of this function
   for (int m = 0; m < 5; ++m) {
@@ -1702,7 +1714,6 @@ int64_t Engine::debug_read(const char* name, double* out, int64_t capacity) {
   else if (n == "lm_ptr") isrc = d_.ix.lm_ptr, count = L_ + 1;
   else if (n == "obs_cam") isrc = d_.ix.obs_cam, count = nnz_;
   else if (n == "obs_lm") isrc = d_.ix.obs_lm, count = nnz_;
-  else if (n == "tile_ptr") isrc = d_.ix.tile_ptr, count = d_.ix.num_tiles + 1;
   else if (n == "cam_ptr") isrc = d_.ix.cam_ptr, count = C_ + 1;
   else if (n == "csc_lm") isrc = d_.ix.csc_lm, count = nnz_;
   else if (n == "item_ptr") isrc = d_.ix.item_ptr, count = d_.ix.num_items + 1;

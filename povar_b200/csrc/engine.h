@@ -149,7 +149,6 @@ LmPlanHost plan_landmark_half(const SellLayout& sell, int num_cams, int num_long
 size_t landmark_half_smem(int warps, int stages, int stage_bytes, int win_cams, int rec_bytes);
 
 // host-side index construction (engine.cu), exposed for the CPU tests through the C ABI
-void build_tiles(const std::vector<int>& lm_ptr, std::vector<int>* tile_ptr);
 void build_items(const std::vector<int>& cam_ptr, int item_len, std::vector<int>* item_ptr,
                  std::vector<int>* item_cam, std::vector<int>* cam_item_ptr);
 int choose_item_len(long long nnz);

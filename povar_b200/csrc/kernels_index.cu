@@ -140,6 +140,74 @@ k_sell_fill(int nnz, const int* __restrict__ lm_ptr, const int* __restrict__ obs
   obs_slot[o] = slot;
 }
 
+// ---- the sliced-ELL order on the device (the rule of build_sell, engine.cu) -----------------------------------
+// sell_key of engine.cu: centre of the first stretch of `span` cameras that holds most of the observations
+__device__ __forceinline__ int sell_key_dev(const int* __restrict__ cams, int deg, int span) {
+  int best_i = 0, best_j = 0;
+  for (int i = 0, j = 0; i < deg; ++i) {
+    if (j < i) j = i;
+    while (j + 1 < deg && cams[j + 1] - cams[i] < span) ++j;
+    if (j - i > best_j - best_i) {
+      best_i = i;
+      best_j = j;
+    }
+  }
+  return (cams[best_i] + cams[best_j]) / 2;
+}
+
+// key of every landmark: its key camera, or num_cams (sorts last) for the landmarks outside the set
+__global__ void __launch_bounds__(kBlock)
+k_sell_keys(int L, int num_cams, int span, const int* __restrict__ lm_ptr, const int* __restrict__ obs_cam,
+            int* __restrict__ keys, int* __restrict__ ids) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= L) return;
+  const int b = lm_ptr[l], deg = lm_ptr[l + 1] - b;
+  keys[l] = (deg >= 1 && deg <= 32) ? sell_key_dev(obs_cam + b, deg, span) : num_cams;
+  ids[l] = l;
+}
+
+// second key of the n landmarks of the set, in key order: (window, 32 - degree)
+__global__ void __launch_bounds__(kBlock)
+k_sell_window_keys(int n, int window, const int* __restrict__ ids, const int* __restrict__ lm_ptr,
+                   int* __restrict__ keys) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int l = ids[i];
+  keys[i] = ((i / window) << 6) | (32 - (lm_ptr[l + 1] - lm_ptr[l]));
+}
+
+// one warp per slice: the landmarks of the slice (padding -1), its number of rows (= the degree of its first
+// landmark: the largest), the cameras it meets
+__global__ void __launch_bounds__(kBlock)
+k_sell_slices(int num_slices, int n, const int* __restrict__ ids, const int* __restrict__ lm_ptr,
+              const int* __restrict__ obs_cam, int* __restrict__ sell_lm, int* __restrict__ slice_len,
+              int* __restrict__ slice_lo, int* __restrict__ slice_hi) {
+  const int sl = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (sl >= num_slices) return;
+  const int i = kSellWidth * sl + lane;
+  int lm = -1, deg = 0, lo = 0x7fffffff, hi = -1;
+  if (i < n) {
+    lm = ids[i];
+    const int b = lm_ptr[lm], e = lm_ptr[lm + 1];
+    deg = e - b;
+    lo = obs_cam[b];
+    hi = obs_cam[e - 1];
+  }
+  sell_lm[i] = lm;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+  }
+  deg = __shfl_sync(0xffffffffu, deg, 0);
+  if (lane == 0) {
+    slice_len[sl] = deg;
+    slice_lo[sl] = lo;
+    slice_hi[sl] = hi;
+  }
+}
+
 }  // namespace
 
 size_t index_sort_temp_bytes(int nnz, int num_cams) {
@@ -197,6 +265,48 @@ cudaError_t build_device_index(const DeviceIndex& ix, int* iota, int* keys_out, 
     launches += 5;   // iota, radix sort (counted once), gather, fill
   }
   if (lc.launch_counter) *lc.launch_counter += launches;
+  return cudaGetLastError();
+}
+
+// The sliced-ELL order of the n landmarks with 1..32 observations, made on the device with the rule of
+// build_sell (engine.cu): stable radix sort by key camera, then by (window, descending degree).  Out: sell_lm
+// [32 * ceil(n / 32)], slice_len / slice_lo / slice_hi [ceil(n / 32)].  Scratch: keys_a, keys_b, ids_a, ids_b [L],
+// cub temp of sell_sort_temp_bytes.
+size_t sell_sort_temp_bytes(int L, int num_cams, int n, int window) {
+  size_t a = 0, b = 0;
+  int bits1 = 1;
+  while ((1 << bits1) <= num_cams) ++bits1;
+  int bits2 = 7;
+  while ((1LL << (bits2 - 6)) <= (n + window - 1) / window) ++bits2;
+  cub::DeviceRadixSort::SortPairs(nullptr, a, static_cast<const int*>(nullptr), static_cast<int*>(nullptr),
+                                  static_cast<const int*>(nullptr), static_cast<int*>(nullptr), L, 0, bits1);
+  cub::DeviceRadixSort::SortPairs(nullptr, b, static_cast<const int*>(nullptr), static_cast<int*>(nullptr),
+                                  static_cast<const int*>(nullptr), static_cast<int*>(nullptr), n > 0 ? n : 1, 0, bits2);
+  return a > b ? a : b;
+}
+
+cudaError_t build_device_sell(int L, int num_cams, int n, int window, const int* lm_ptr, const int* obs_cam,
+                              int* keys_a, int* keys_b, int* ids_a, int* ids_b, void* sort_temp,
+                              size_t sort_temp_bytes, int* sell_lm, int* slice_len, int* slice_lo, int* slice_hi,
+                              const LaunchCfg& lc) {
+  if (L <= 0 || n <= 0) return cudaSuccess;
+  cudaStream_t st = lc.stream;
+  int bits1 = 1;
+  while ((1 << bits1) <= num_cams) ++bits1;
+  int bits2 = 7;
+  while ((1LL << (bits2 - 6)) <= (n + window - 1) / window) ++bits2;
+  k_sell_keys<<<(L + kBlock - 1) / kBlock, kBlock, 0, st>>>(L, num_cams, kSellKeySpan, lm_ptr, obs_cam, keys_a, ids_a);
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(sort_temp, sort_temp_bytes, keys_a, keys_b, ids_a, ids_b, L, 0,
+                                                  bits1, st);
+  if (e != cudaSuccess) return e;
+  // the first n of ids_b are the landmarks of the set in key order
+  k_sell_window_keys<<<(n + kBlock - 1) / kBlock, kBlock, 0, st>>>(n, window, ids_b, lm_ptr, keys_a);
+  e = cub::DeviceRadixSort::SortPairs(sort_temp, sort_temp_bytes, keys_a, keys_b, ids_b, ids_a, n, 0, bits2, st);
+  if (e != cudaSuccess) return e;
+  const int num_slices = (n + kSellWidth - 1) / kSellWidth;
+  k_sell_slices<<<(num_slices * 32 + kBlock - 1) / kBlock, kBlock, 0, st>>>(num_slices, n, ids_a, lm_ptr, obs_cam,
+                                                                          sell_lm, slice_len, slice_lo, slice_hi);
+  if (lc.launch_counter) *lc.launch_counter += 5;
   return cudaGetLastError();
 }
 

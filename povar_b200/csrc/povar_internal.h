@@ -22,9 +22,6 @@ struct DeviceIndex {
   int* obs_cam = nullptr;     // [nnz]
   int* obs_lm = nullptr;      // [nnz]
   double2* obs_uv = nullptr;  // [nnz]
-  int* tile_ptr = nullptr;    // [num_tiles+1] observation ranges: whole short landmarks
-                              //   (<= 32 obs together) or one long landmark
-  int num_tiles = 0;
   // landmark-major, sliced ELL for the landmark half of E0 (kernels_series.cu): landmarks with 1..32
   // observations, ordered by the centre of their cameras, sorted by degree inside windows of kSellWindow
   // landmarks of that order, kSellWidth (32) per slice; slot
@@ -241,6 +238,11 @@ struct ModelParams {
 };
 
 // ---- device-side index construction (kernels_index.cu) ----
+size_t sell_sort_temp_bytes(int L, int num_cams, int n, int window);
+cudaError_t build_device_sell(int L, int num_cams, int n, int window, const int* lm_ptr, const int* obs_cam,
+                              int* keys_a, int* keys_b, int* ids_a, int* ids_b, void* sort_temp,
+                              size_t sort_temp_bytes, int* sell_lm, int* slice_len, int* slice_lo, int* slice_hi,
+                              const LaunchCfg& lc);
 size_t index_sort_temp_bytes(int nnz, int num_cams);
 cudaError_t build_device_index(const DeviceIndex& ix, int* iota, int* keys_out, int* perm, int* lm_slot,
                                void* sort_temp, size_t sort_temp_bytes, const LaunchCfg& lc);
