@@ -1064,10 +1064,10 @@ int Engine::init_varproj(double alpha) {
 }
 
 // cost kernels + (sharded) the in-place sum over the ranks: the result is trial_out[0..7] on the device
-int Engine::enqueue_cost(bool joint, double alpha) {
+int Engine::enqueue_cost(bool joint, double alpha, bool reduce) {
   set_model(joint, joint ? opt_.alpha : alpha);
   launch_cost(d_, mp_, joint, lc());
-  return allreduce(d_.trial_out, 8);
+  return reduce ? allreduce(d_.trial_out, 8) : POVAR_OK;
 }
 
 void Engine::decode_cost(const double* v, povar_residual_info* out) {
@@ -1506,7 +1506,7 @@ int debug_cholesky(int n, const double* A, const double* b, double* x, int* info
 }
 
 // back-substitution and camera update + (sharded) the sum of l_diff over the ranks: trial_out[8] on the device
-int Engine::enqueue_apply(bool joint, double alpha) {
+int Engine::enqueue_apply(bool joint, double alpha, bool reduce) {
   if (static_cast<int>(joint) != joint_lin_ || !have_solve_) {
     return fail(POVAR_ERR_INVALID, "apply called without a matching linearize + solve");
   }
@@ -1531,7 +1531,7 @@ int Engine::enqueue_apply(bool joint, double alpha) {
     tmp.P_bak = P_prev_;
     launch_backsub_varpro(tmp, mp_, d_.vec_acc, lc());
   }
-  return allreduce(d_.trial_out + 8, 1);
+  return reduce ? allreduce(d_.trial_out + 8, 1) : POVAR_OK;
 }
 
 int Engine::apply(bool joint, double alpha, double* l_diff) {
@@ -1558,14 +1558,17 @@ int Engine::trial(bool joint, double alpha, double lambda, int32_t* iterations, 
   if (rc != POVAR_OK) return rc;
   rc = backup(joint ? POVAR_STATE_JOINT : POVAR_STATE_POSE);
   if (rc != POVAR_OK) return rc;
-  rc = enqueue_apply(joint, alpha);
+  // sharded: the model decrease and the cost scalars of the trial travel together (trial_out[0..9), one exchange)
+  rc = enqueue_apply(joint, alpha, /*reduce=*/false);
   if (rc != POVAR_OK) return rc;
   if (joint) {   // solver/bal_bundle_adjustment.cpp:700-705
     launch_normalize_cams(d_, lc());
     launch_normalize_joint(d_, lc());
   }
   PV_CUDA(cudaEventRecord(ev_[3], stream_));
-  rc = enqueue_cost(joint, alpha);
+  rc = enqueue_cost(joint, alpha, /*reduce=*/false);
+  if (rc != POVAR_OK) return rc;
+  rc = allreduce(d_.trial_out, 9);
   if (rc != POVAR_OK) return rc;
   PV_CUDA(cudaGetLastError());
   static_assert(sizeof(SeriesCtl) <= 64, "SeriesCtl shares the pinned read-back buffer");

@@ -73,8 +73,8 @@ class Engine {
   int e0_product(bool joint, bool skip_when_done, bool fused_reduce);
   int finish_solve(bool joint, double* inc, int32_t* iterations);
   int enqueue_solve(bool joint, double lambda);
-  int enqueue_cost(bool joint, double alpha);
-  int enqueue_apply(bool joint, double alpha);
+  int enqueue_cost(bool joint, double alpha, bool reduce = true);
+  int enqueue_apply(bool joint, double alpha, bool reduce = true);
   int enqueue_series(bool joint);
   static void decode_cost(const double* v, povar_residual_info* out);
   LaunchCfg lc() { return LaunchCfg{stream_, &launches_}; }

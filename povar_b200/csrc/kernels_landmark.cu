@@ -93,12 +93,15 @@ __device__ __forceinline__ void givens_row(double (&R)[6], double (&d)[3], doubl
   }
 }
 
+// (one thread per landmark of `list`: the landmarks with more than 32 observations; the others go through the
+// walk, InitVarprojOp below)
 __global__ void __launch_bounds__(kBlock)
-k_init_varproj(int L, const int* __restrict__ lm_ptr, const int* __restrict__ obs_cam,
+k_init_varproj(int n, const int* __restrict__ list, const int* __restrict__ lm_ptr, const int* __restrict__ obs_cam,
                const double2* __restrict__ obs_uv, const double* __restrict__ P, double c1,
                double c2, double* __restrict__ X) {
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
-  if (l >= L) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int l = list[i];
   double R[6] = {0, 0, 0, 0, 0, 0};
   double d[3] = {0, 0, 0};
   const int e = lm_ptr[l + 1];
@@ -925,6 +928,51 @@ struct WalkBase {
   }
 };
 
+// VarPro initialisation (k_init_varproj) for the sliced-ELL landmarks: the same Givens row updates, in camera order
+struct InitVarprojOp : WalkBase {
+  static constexpr int kRec = kCamTab1;
+  double c1, c2;
+  double* X;
+
+  struct Lane {
+    int lm, lm1;   // (lm1: WalkBase::init's marker, unused: nothing is gathered per landmark)
+    double R[6], d[3];
+  };
+
+  __device__ __forceinline__ void open(Lane& st, const DeviceIndex& ix, int sl, int lane, int) const {
+    st.lm = __ldcs(ix.sell_lm + kSellWidth * static_cast<size_t>(sl) + lane);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) st.R[k] = 0.0;
+    st.d[0] = st.d[1] = st.d[2] = 0.0;
+  }
+
+  __device__ __forceinline__ void obs(Lane& st, const double2* __restrict__ rec, const unsigned char* stage, int lane,
+                                      int) const {
+    Cam3x4 cam;
+    rec_cam(rec, cam);
+    const double2 uv = uv_of(stage, lane);
+    // rows of G = T[:, 0:3], z = -(T[:,3]) + [0 0 c2 u c2 v]   (helper.cpp:224-237)
+    givens_row(st.R, st.d, c1 * (cam.r0[0] - cam.r2[0] * uv.x), c1 * (cam.r0[1] - cam.r2[1] * uv.x),
+               c1 * (cam.r0[2] - cam.r2[2] * uv.x), c1 * (cam.r2[3] * uv.x - cam.r0[3]));
+    givens_row(st.R, st.d, c1 * (cam.r1[0] - cam.r2[0] * uv.y), c1 * (cam.r1[1] - cam.r2[1] * uv.y),
+               c1 * (cam.r1[2] - cam.r2[2] * uv.y), c1 * (cam.r2[3] * uv.y - cam.r1[3]));
+    givens_row(st.R, st.d, c2 * cam.r0[0], c2 * cam.r0[1], c2 * cam.r0[2], c2 * (uv.x - cam.r0[3]));
+    givens_row(st.R, st.d, c2 * cam.r1[0], c2 * cam.r1[1], c2 * cam.r1[2], c2 * (uv.y - cam.r1[3]));
+  }
+
+  __device__ __forceinline__ void close(Lane& st, const DeviceIndex&, int, int) const {
+    if (st.lm < 0) return;
+    const double x2 = st.R[5] != 0.0 ? st.d[2] / st.R[5] : 0.0;
+    const double x1 = st.R[3] != 0.0 ? (st.d[1] - st.R[4] * x2) / st.R[3] : 0.0;
+    const double x0 = st.R[0] != 0.0 ? (st.d[0] - st.R[1] * x1 - st.R[2] * x2) / st.R[0] : 0.0;
+    double2* out = reinterpret_cast<double2*>(X + 4 * static_cast<size_t>(st.lm));
+    out[0] = make_double2(x0, x1);
+    out[1] = make_double2(x2, 1.0);
+  }
+
+  __device__ __forceinline__ void finish(Lane&, const DeviceIndex&, const CamWindow&, const double*) const {}
+};
+
 // k_lin_long for the sliced-ELL landmarks: sum_i w Jl_raw^T Jl_raw, sum_i w Jl_raw^T r, column scales
 template <bool JOINT>
 struct LinLandmarkOp : WalkBase {
@@ -1405,11 +1453,16 @@ void finish_l_diff(const DeviceState& d, int long_blocks, bool walked, const Lau
 }  // namespace
 
 void launch_init_varproj(const DeviceState& d, const ModelParams& mp, const LaunchCfg& lc) {
-  const int blocks = (d.ix.L + kBlock - 1) / kBlock;
-  if (blocks == 0) return;
-  k_init_varproj<<<blocks, kBlock, 0, lc.stream>>>(d.ix.L, d.ix.lm_ptr, d.ix.obs_cam, d.ix.obs_uv, d.P,
-                                                   mp.c1, mp.c2, d.X);
-  count(lc);
+  if (d.plan[3].blocks > 0) {
+    pack_cam_tab(d, d.P, nullptr, lc);
+    const InitVarprojOp op{{}, mp.c1, mp.c2, d.X};
+    if (launch_sell_walk(d.ix, d.plan[3], d.debug_window_cams, d.cam_tab, op, lc.stream)) count(lc);
+  }
+  if (d.ix.num_long > 0) {
+    k_init_varproj<<<(d.ix.num_long + kBlock - 1) / kBlock, kBlock, 0, lc.stream>>>(
+        d.ix.num_long, d.ix.long_lm, d.ix.lm_ptr, d.ix.obs_cam, d.ix.obs_uv, d.P, mp.c1, mp.c2, d.X);
+    count(lc);
+  }
 }
 
 void launch_flag_to_double(const DeviceState& d, const LaunchCfg& lc) {
