@@ -328,8 +328,11 @@ int64_t povar_launch_count(const povar_handle* h);
  * call with NULL outputs to get sizes = {len(slice_ptr), len(sell_lm), len(long_lms)}, then again with buffers.
  * `threads` > 0 fixes the number of host threads (the result must not depend on it), 0 = automatic. */
 int povar_debug_sell_layout(int32_t num_cams, int32_t num_lms, const int64_t* lm_ptr, const int32_t* obs_cam,
-                            int32_t threads, int32_t* slice_ptr, int32_t* sell_lm, int32_t* long_lms,
-                            int64_t sizes[3]);
+                            int32_t threads, int32_t max_deg, int32_t* slice_ptr, int32_t* sell_lm,
+                            int32_t* long_lms, int64_t sizes[3]);
+/* largest number of observations of a landmark of that order (`max_deg` above; 0 = 32) that povar_create uses for a
+ * shard of num_obs observations on a device with `sms` multiprocessors: 32, less on small shards */
+int povar_debug_sell_max_degree(int64_t num_obs, int32_t sms);
 
 /* host-side plan of the landmark half for that order: which slices every warp walks and which
  * cameras every block stages in shared memory.  model: 0 step 1, 1 step 2, 2 step 1 with HUBER weights;
@@ -337,7 +340,12 @@ int povar_debug_sell_layout(int32_t num_cams, int32_t num_lms, const int64_t* lm
  * ranges, cameras per window, 1 if every block's window holds every camera its slices meet, bytes of shared
  * memory per block}.  range_slice [ranges + 1] and blk_lo [blocks] may be NULL (sizes come back in info). */
 int povar_debug_landmark_plan(int32_t num_cams, int32_t num_lms, const int64_t* lm_ptr, const int32_t* obs_cam,
-                              int32_t model, int32_t sms, int64_t info[8], int32_t* range_slice, int32_t* blk_lo);
+                              int32_t model, int32_t sms, int32_t max_deg, int64_t info[8], int32_t* range_slice,
+                              int32_t* blk_lo);
+
+/* Tuning builds only (-DPOVAR_WALK_TRACE; POVAR_ERR_UNSUPPORTED otherwise): per block of the last landmark-half
+ * launches, four globaltimer stamps (entry, window staged, slices walked, done); reset on read. */
+int povar_debug_walk_trace(uint64_t* out, int32_t n);
 
 /* The direct solver of CHOLESKY (blocked LL^T on FP64 tensor-core tiles + substitution, kernels_chol.cu) on a
  * caller-supplied symmetric matrix: x = A^-1 b for a row-major n x n matrix of which the lower triangle is read.

@@ -159,11 +159,13 @@ SIGNATURES = {
     "povar_debug_cholesky": (C.c_int, [C.c_int32, _DP, _DP, _DP, C.POINTER(C.c_int32)]),
     "povar_write_ba_log": (C.c_int, [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "povar_debug_sell_layout": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.c_int32,
-                                          C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
-                                          C.POINTER(C.c_int64)]),
+                                          C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                          C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
+    "povar_debug_sell_max_degree": (C.c_int, [C.c_int64, C.c_int32]),
     "povar_debug_landmark_plan": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.c_int32,
-                                            C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int32),
+                                            C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int32),
                                             C.POINTER(C.c_int32)]),
+    "povar_debug_walk_trace": (C.c_int, [C.POINTER(C.c_uint64), C.c_int32]),
     "povar_cuda_stream": (C.c_void_p, [_H]),
 }
 
@@ -463,14 +465,20 @@ def write_ba_log(path: str, hp: "HostProblem", options, iterations, summary, inp
         raise PovarError(rc, "povar_write_ba_log failed")
 
 
-def sell_layout(hp: "HostProblem", threads: int = 0):
-    """(slice_ptr, sell_lm, long_lms) of the sliced-ELL landmark order povar_create builds for `hp`."""
+def sell_max_degree(num_obs: int, sms: int = 148) -> int:
+    """Largest degree of a landmark of the sliced-ELL set for a shard of num_obs observations."""
+    return int(load().povar_debug_sell_max_degree(num_obs, sms))
+
+
+def sell_layout(hp: "HostProblem", threads: int = 0, max_deg: int = 0):
+    """(slice_ptr, sell_lm, long_lms) of the sliced-ELL landmark order of `hp` (max_deg = 0: landmarks with up to 32
+    observations; povar_create uses sell_max_degree(hp.num_obs))."""
     lib = load()
     sizes = (C.c_int64 * 3)()
     lp = np.ascontiguousarray(hp.lm_ptr, dtype=np.int64)
     oc = np.ascontiguousarray(hp.obs_cam, dtype=np.int32)
     args = (hp.num_cams, hp.num_lms, lp.ctypes.data_as(C.POINTER(C.c_int64)), oc.ctypes.data_as(C.POINTER(C.c_int32)),
-            threads)
+            threads, max_deg)
     rc = lib.povar_debug_sell_layout(*args, None, None, None, sizes)
     if rc != OK:
         raise PovarError(rc, "povar_debug_sell_layout failed")
@@ -481,14 +489,14 @@ def sell_layout(hp: "HostProblem", threads: int = 0):
     return tuple(a[:int(n)] for a, n in zip(out, sizes))
 
 
-def landmark_plan(hp: "HostProblem", model: int = 0, sms: int = 148):
+def landmark_plan(hp: "HostProblem", model: int = 0, sms: int = 148, max_deg: int = 0):
     """Plan of the landmark half (engine.cu plan_landmark_half) for `hp`: (info dict, range_slice, blk_lo)."""
     lib = load()
     info = (C.c_int64 * 8)()
     lp = np.ascontiguousarray(hp.lm_ptr, dtype=np.int64)
     oc = np.ascontiguousarray(hp.obs_cam, dtype=np.int32)
     args = (hp.num_cams, hp.num_lms, lp.ctypes.data_as(C.POINTER(C.c_int64)), oc.ctypes.data_as(C.POINTER(C.c_int32)),
-            model, sms, info)
+            model, sms, max_deg, info)
     rc = lib.povar_debug_landmark_plan(*args, None, None)
     if rc != OK:
         raise PovarError(rc, "povar_debug_landmark_plan failed")

@@ -231,15 +231,19 @@ int64_t povar_launch_count(const povar_handle* h) {
   return h->engine->launches();
 }
 
+int povar_debug_sell_max_degree(int64_t num_obs, int32_t sms) {
+  return povar::sell_max_degree(num_obs, sms > 0 ? sms : 148);
+}
+
 int povar_debug_sell_layout(int32_t num_cams, int32_t num_lms, const int64_t* lm_ptr, const int32_t* obs_cam,
-                            int32_t threads, int32_t* slice_ptr, int32_t* sell_lm, int32_t* long_lms,
-                            int64_t sizes[3]) {
+                            int32_t threads, int32_t max_deg, int32_t* slice_ptr, int32_t* sell_lm,
+                            int32_t* long_lms, int64_t sizes[3]) {
   if (num_cams <= 0 || num_lms < 0 || !lm_ptr || !sizes) return POVAR_ERR_INVALID;
   std::vector<int> lp(static_cast<size_t>(num_lms) + 1);
   for (int32_t l = 0; l <= num_lms; ++l) lp[l] = static_cast<int>(lm_ptr[l]);
   povar::SellLayout sell;
   povar::set_host_threads_override(threads);
-  povar::build_sell(lp, obs_cam, num_cams, povar::kSellWindow, &sell);
+  povar::build_sell(lp, obs_cam, num_cams, povar::kSellWindow, &sell, max_deg > 0 ? max_deg : 32);
   povar::set_host_threads_override(0);
   sizes[0] = static_cast<int64_t>(sell.slice_ptr.size());
   sizes[1] = static_cast<int64_t>(sell.sell_lm.size());
@@ -251,12 +255,13 @@ int povar_debug_sell_layout(int32_t num_cams, int32_t num_lms, const int64_t* lm
 }
 
 int povar_debug_landmark_plan(int32_t num_cams, int32_t num_lms, const int64_t* lm_ptr, const int32_t* obs_cam,
-                              int32_t model, int32_t sms, int64_t info[8], int32_t* range_slice, int32_t* blk_lo) {
+                              int32_t model, int32_t sms, int32_t max_deg, int64_t info[8], int32_t* range_slice,
+                              int32_t* blk_lo) {
   if (num_cams <= 0 || num_lms < 0 || !lm_ptr || !info || model < 0 || model > 2 || sms <= 0) return POVAR_ERR_INVALID;
   std::vector<int> lp(static_cast<size_t>(num_lms) + 1);
   for (int32_t l = 0; l <= num_lms; ++l) lp[l] = static_cast<int>(lm_ptr[l]);
   povar::SellLayout sell;
-  povar::build_sell(lp, obs_cam, num_cams, povar::kSellWindow, &sell);
+  povar::build_sell(lp, obs_cam, num_cams, povar::kSellWindow, &sell, max_deg > 0 ? max_deg : 32);
   const int rec_bytes = 8 * (model == 1 ? povar::kCamRecJoint : povar::kCamRecPose);
   const int stage_bytes = model == 0 ? povar::kStagePose : povar::kStageWide;
   const povar::LmPlanHost h = povar::plan_landmark_half(sell, num_cams, static_cast<int>(sell.long_lms.size()),
@@ -272,6 +277,11 @@ int povar_debug_landmark_plan(int32_t num_cams, int32_t num_lms, const int64_t* 
   if (range_slice) std::copy(h.range_slice.begin(), h.range_slice.end(), range_slice);
   if (blk_lo) std::copy(h.blk_lo.begin(), h.blk_lo.begin() + h.p.blocks, blk_lo);
   return POVAR_OK;
+}
+
+int povar_debug_walk_trace(uint64_t* out, int32_t n) {
+  if (!out || n <= 0 || n > 4096) return POVAR_ERR_INVALID;
+  return povar::debug_walk_trace(reinterpret_cast<unsigned long long*>(out), n);
 }
 
 int povar_debug_cholesky(int32_t n, const double* A, const double* b, double* x, int32_t* info) {

@@ -276,8 +276,23 @@ int sell_window(int landmarks, int max_window) {
   return w;
 }
 
+// Largest degree of a landmark of the sliced-ELL set.  A slice is walked row by row by ONE warp, so a slice of 32
+// rows is a chain of 32 dependent steps (0.76 us each when the SM is not full); on a large shard every warp has
+// dozens of rows anyway, on a small one (a venice-1778 shard on 8 GPUs: one slice of ~5 rows per warp) the few
+// slices of 30 rows set the time of the whole launch (27 us where the median block needs 19).  There the
+// landmarks with more than about twice the rows a warp has anyway go to the warp-per-landmark kernels instead
+// (32 observations per step): 31 -> 22 us per launch with 12, measured on that shard.
+int sell_max_degree(long long nnz, int sms) {
+  const long long rows_per_warp = nnz / (32LL * 32 * sms);   // rows of one resident wave of warps
+  if (rows_per_warp >= 16) return 32;
+  long long t = (2 * rows_per_warp + 3) / 4 * 4;
+  if (t < 8) t = 8;
+  if (t > 32) t = 32;
+  return static_cast<int>(t);
+}
+
 void build_sell(const std::vector<int>& lm_ptr, const int* obs_cam, int num_cams, int max_window,
-                SellLayout* out) {
+                SellLayout* out, int max_deg) {
   const int L = static_cast<int>(lm_ptr.size()) - 1;
   out->slice_ptr.assign(1, 0);
   out->sell_lm.clear();
@@ -299,7 +314,7 @@ void build_sell(const std::vector<int>& lm_ptr, const int* obs_cam, int num_cams
     for (int l = chunk_begin(t); l < chunk_begin(t + 1); ++l) {
       const int deg = lm_ptr[l + 1] - lm_ptr[l];
       keys[l] = -1;
-      if (deg > 32) {
+      if (deg > max_deg) {
         longs[t].push_back(l);
       } else if (deg > 0) {
         keys[l] = sell_key(obs_cam + lm_ptr[l], deg, kSellKeySpan);
@@ -405,14 +420,16 @@ LmPlanHost plan_landmark_half(const SellLayout& sell, int num_cams, int num_long
     p.blocks_per_sm = cd.bps;
     const long long resident = static_cast<long long>(sms) * cd.bps * cd.warps;   // warps of one wave
     p.ranges = static_cast<int>(std::min<long long>(resident, S));
-    // ranges of (nearly) equal rows: range w starts at the first slice at or after row w * rows / ranges
+    // ranges of (nearly) equal cost -- rows plus kSliceCost per slice (opening and closing a slice: its landmarks
+    // in, its results out, about two rows' worth; blocks of many short slices were 20 % behind those of few
+    // long ones with rows alone): range w starts at the first slice at or after cost w * total / ranges
     h.range_slice.assign(static_cast<size_t>(p.ranges) + 1, S);
     {
-      const long long rows = S > 0 ? sell.slice_ptr[S] : 0;
+      const long long total = S > 0 ? sell.slice_ptr[S] + static_cast<long long>(kSliceCost) * S : 0;
       int sl = 0;
       for (int w = 0; w < p.ranges; ++w) {
-        const long long target = rows * w / p.ranges;
-        while (sl < S && sell.slice_ptr[sl] < target) ++sl;
+        const long long target = total * w / p.ranges;
+        while (sl < S && sell.slice_ptr[sl] + static_cast<long long>(kSliceCost) * sl < target) ++sl;
         h.range_slice[w] = sl;
       }
     }
@@ -654,7 +671,9 @@ int Engine::upload(const povar_problem_desc* desc) {
   };
   std::vector<int> lm_ptr(L + 1), cam_ptr(C + 1, 0);
   SellLayout sell;    // sliced-ELL order: the long landmarks from the pass below, the slices from the device
-  int sell_n = 0;     // landmarks with 1..32 observations
+  int sell_n = 0;     // landmarks with 1..sell_max_deg observations
+  const int sell_max_deg = sell_max_degree(nnz, sm_count());
+  d_.ix.sell_max_deg = sell_max_deg;
   if (desc->lm_ptr[0] != 0 || desc->lm_ptr[L] != nnz) return fail(POVAR_ERR_INVALID, "lm_ptr does not span the observations");
   {
     const int T = host_threads(nnz);
@@ -674,7 +693,7 @@ int Engine::upload(const povar_problem_desc* desc) {
           return;
         }
         lm_ptr[l] = static_cast<int>(b);
-        if (e - b > 32) longs[t].push_back(l);
+        if (e - b > sell_max_deg) longs[t].push_back(l);
         else if (e > b) ++set_here;
         for (int64_t o = b; o < e; ++o) {
           const int c = desc->obs_cam[o];
@@ -734,8 +753,8 @@ int Engine::upload(const povar_problem_desc* desc) {
     PV_ALLOC(d_lo, sell_slices);
     PV_ALLOC(d_hi, sell_slices);
     PV_ALLOC(sort_temp, temp_bytes);
-    PV_CUDA(build_device_sell(L, C, sell_n, window, ix.lm_ptr, ix.obs_cam, keys_a, keys_b, ids_a, ids_b, sort_temp,
-                              temp_bytes, ix.sell_lm, d_len, d_lo, d_hi, lc()));
+    PV_CUDA(build_device_sell(L, C, sell_n, window, sell_max_deg, ix.lm_ptr, ix.obs_cam, keys_a, keys_b, ids_a, ids_b,
+                              sort_temp, temp_bytes, ix.sell_lm, d_len, d_lo, d_hi, lc()));
     PV_CUDA(cudaMemcpyAsync(slice_len.data(), d_len, sizeof(int) * slice_len.size(), cudaMemcpyDeviceToHost, stream_));
     PV_CUDA(cudaMemcpyAsync(slice_lo.data(), d_lo, sizeof(int) * slice_lo.size(), cudaMemcpyDeviceToHost, stream_));
     PV_CUDA(cudaMemcpyAsync(slice_hi.data(), d_hi, sizeof(int) * slice_hi.size(), cudaMemcpyDeviceToHost, stream_));
@@ -1725,6 +1744,10 @@ int64_t Engine::debug_read(const char* name, double* out, int64_t capacity) {
   else if (n == "sell_lm") isrc = d_.ix.sell_lm, count = static_cast<int64_t>(kSellWidth) * d_.ix.num_slices;
   else if (n == "sell_cam") isrc = d_.ix.sell_cam, count = d_.ix.sell_slots;
   else if (n == "sell_cam_e0") isrc = d_.ix.sell_cam_e0, count = d_.ix.sell_slots;
+  else if (n == "sell_max_deg") {
+    if (out && capacity >= 1) out[0] = d_.ix.sell_max_deg;
+    return 1;
+  }
   else if (n == "obs_slot") isrc = d_.ix.obs_slot, count = nnz_;
   else {
     fail(POVAR_ERR_INVALID, "debug_read: unknown array '" + n + "'");

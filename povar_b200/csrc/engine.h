@@ -133,7 +133,8 @@ struct SellLayout {
 };
 void set_host_threads_override(int n);   // 0 = automatic
 void build_sell(const std::vector<int>& lm_ptr, const int* obs_cam, int num_cams, int max_window,
-                SellLayout* out);
+                SellLayout* out, int max_deg = 32);
+int sell_max_degree(long long nnz, int sms);
 int sell_window(int landmarks, int max_window);
 int sell_key(const int* cams, int deg, int span);
 

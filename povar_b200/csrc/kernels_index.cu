@@ -157,12 +157,12 @@ __device__ __forceinline__ int sell_key_dev(const int* __restrict__ cams, int de
 
 // key of every landmark: its key camera, or num_cams (sorts last) for the landmarks outside the set
 __global__ void __launch_bounds__(kBlock)
-k_sell_keys(int L, int num_cams, int span, const int* __restrict__ lm_ptr, const int* __restrict__ obs_cam,
+k_sell_keys(int L, int num_cams, int span, int max_deg, const int* __restrict__ lm_ptr, const int* __restrict__ obs_cam,
             int* __restrict__ keys, int* __restrict__ ids) {
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
   if (l >= L) return;
   const int b = lm_ptr[l], deg = lm_ptr[l + 1] - b;
-  keys[l] = (deg >= 1 && deg <= 32) ? sell_key_dev(obs_cam + b, deg, span) : num_cams;
+  keys[l] = (deg >= 1 && deg <= max_deg) ? sell_key_dev(obs_cam + b, deg, span) : num_cams;
   ids[l] = l;
 }
 
@@ -285,7 +285,7 @@ size_t sell_sort_temp_bytes(int L, int num_cams, int n, int window) {
   return a > b ? a : b;
 }
 
-cudaError_t build_device_sell(int L, int num_cams, int n, int window, const int* lm_ptr, const int* obs_cam,
+cudaError_t build_device_sell(int L, int num_cams, int n, int window, int max_deg, const int* lm_ptr, const int* obs_cam,
                               int* keys_a, int* keys_b, int* ids_a, int* ids_b, void* sort_temp,
                               size_t sort_temp_bytes, int* sell_lm, int* slice_len, int* slice_lo, int* slice_hi,
                               const LaunchCfg& lc) {
@@ -295,7 +295,8 @@ cudaError_t build_device_sell(int L, int num_cams, int n, int window, const int*
   while ((1 << bits1) <= num_cams) ++bits1;
   int bits2 = 7;
   while ((1LL << (bits2 - 6)) <= (n + window - 1) / window) ++bits2;
-  k_sell_keys<<<(L + kBlock - 1) / kBlock, kBlock, 0, st>>>(L, num_cams, kSellKeySpan, lm_ptr, obs_cam, keys_a, ids_a);
+  k_sell_keys<<<(L + kBlock - 1) / kBlock, kBlock, 0, st>>>(L, num_cams, kSellKeySpan, max_deg, lm_ptr, obs_cam, keys_a,
+                                                            ids_a);
   cudaError_t e = cub::DeviceRadixSort::SortPairs(sort_temp, sort_temp_bytes, keys_a, keys_b, ids_a, ids_b, L, 0,
                                                   bits1, st);
   if (e != cudaSuccess) return e;

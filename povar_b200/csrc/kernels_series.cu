@@ -408,6 +408,20 @@ void launch_landmark_half(const DeviceState& d, const ModelParams& mp, const Ser
 
 }  // namespace
 
+// tuning builds (-DPOVAR_WALK_TRACE): stamps of the last walk kernels of this translation unit, reset on read
+int debug_walk_trace(unsigned long long* out, int n) {
+#ifdef POVAR_WALK_TRACE
+  if (cudaMemcpyFromSymbol(out, g_walk_trace, sizeof(unsigned long long) * n) != cudaSuccess) return POVAR_ERR_CUDA;
+  static unsigned long long zeros[4 * 1024];
+  if (cudaMemcpyToSymbol(g_walk_trace, zeros, sizeof(zeros)) != cudaSuccess) return POVAR_ERR_CUDA;
+  return POVAR_OK;
+#else
+  (void)out;
+  (void)n;
+  return POVAR_ERR_UNSUPPORTED;
+#endif
+}
+
 void launch_cam_rec_static(const DeviceState& d, bool joint, const LaunchCfg& lc) {
   const int blocks = (d.ix.C * 4 + kBlock - 1) / kBlock;
   if (joint) {

@@ -27,6 +27,7 @@ struct DeviceIndex {
   // landmarks of that order, kSellWidth (32) per slice; slot
   // 32 * row + g holds the row-th observation of the g-th landmark of the slice (camera -1 = padding)
   int num_slices = 0;
+  int sell_max_deg = 32;      // landmarks with more observations than this are `long` (sell_max_degree, engine.cu)
   int* slice_ptr = nullptr;   // [num_slices+1] first row of the slice
   int* sell_lm = nullptr;     // [32*num_slices] landmark of lane g, -1 = none
   int* sell_cam = nullptr;    // [32*rows] k-th observation of a landmark in row k of its slice
@@ -54,6 +55,7 @@ constexpr double kEpsSqrtHost = 1e-5;  // Sophus::Constants<double>::epsilonSqrt
 constexpr int kKron = 60;     // unique entries of sum_i E_i (x) (X X^T): 6 x 10
 constexpr int kSellWidth = 32;      // landmarks per slice of the sliced-ELL order: one per lane of a warp
 constexpr int kSellWindow = 4096;   // sorting window of the sliced-ELL landmark order
+constexpr int kSliceCost = 2;        // rows a slice costs on top of its own when the walks are balanced
 constexpr int kSellKeySpan = 896;   // cameras the key of a landmark (build_sell) tries to centre
 constexpr int kCamRecStride = 26;   // doubles per camera record, the larger of the two models (CamRec::stride)
 constexpr int kCamRecPose = 22, kCamRecJoint = 26;   // CamRec::stride(false / true)
@@ -239,7 +241,7 @@ struct ModelParams {
 
 // ---- device-side index construction (kernels_index.cu) ----
 size_t sell_sort_temp_bytes(int L, int num_cams, int n, int window);
-cudaError_t build_device_sell(int L, int num_cams, int n, int window, const int* lm_ptr, const int* obs_cam,
+cudaError_t build_device_sell(int L, int num_cams, int n, int window, int max_deg, const int* lm_ptr, const int* obs_cam,
                               int* keys_a, int* keys_b, int* ids_a, int* ids_b, void* sort_temp,
                               size_t sort_temp_bytes, int* sell_lm, int* slice_len, int* slice_lo, int* slice_hi,
                               const LaunchCfg& lc);
@@ -298,6 +300,7 @@ void launch_e0_finish(const DeviceState& d, bool joint, double* out, const Launc
 void launch_make_y(const DeviceState& d, bool joint, const double* x, double* y, const LaunchCfg& lc);
 // cam_rec: matrix part (after a linearisation) -- the y part is written by whoever makes y
 void launch_cam_rec_static(const DeviceState& d, bool joint, const LaunchCfg& lc);
+int debug_walk_trace(unsigned long long* out, int n);   // tuning builds only, POVAR_ERR_UNSUPPORTED otherwise
 // ---- power-series term kernels, lane-group layout (kernels_series.cu) ----
 void launch_e0_landmark_v2(const DeviceState& d, const ModelParams& mp, bool joint, bool in_series,
                            const LaunchCfg& lc);

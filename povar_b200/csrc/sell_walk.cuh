@@ -86,11 +86,26 @@ __device__ __forceinline__ void issue_cam_uv(const DeviceIndex& ix, int row, uns
   bulk_copy_g2s(stage + 128, ix.sell_uv + slot, 512u, bar);
 }
 
+#ifdef POVAR_WALK_TRACE
+// tuning builds only (python -m povar_b200.build with -DPOVAR_WALK_TRACE): per block, the latest time any of its
+// warps passed [0] kernel entry, [1] window staged, [2] slices walked, [3] finish() done (globaltimer ns)
+__device__ unsigned long long g_walk_trace[4 * 1024];
+__device__ __forceinline__ void walk_stamp(int which) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  if ((threadIdx.x & 31) == 0 && blockIdx.x < 1024) atomicMax(&g_walk_trace[4 * blockIdx.x + which], t);
+}
+#define POVAR_WALK_STAMP(k) walk_stamp(k)
+#else
+#define POVAR_WALK_STAMP(k)
+#endif
+
 template <class Op, int W, int D, int BPS>
 __global__ void __launch_bounds__(32 * W, BPS)
 k_sell_walk(DeviceIndex ix, LmPlan plan, int win_cams, const double* __restrict__ table, Op op) {
   extern __shared__ __align__(128) unsigned char walk_smem[];
   if (op.skip()) return;
+  POVAR_WALK_STAMP(0);
   constexpr int kStage = Op::kStage;
   constexpr int kRec = Op::kRec;
   constexpr int kBars = lm_bar_bytes(W, D);
@@ -151,6 +166,7 @@ k_sell_walk(DeviceIndex ix, LmPlan plan, int win_cams, const double* __restrict_
     };
     open_slice();
     mbar_wait(&bars[0], 0);                   // the window is in shared memory
+    POVAR_WALK_STAMP(1);
     unsigned phase = 0;
     for (int row = row_first; row < row_end; row += D) {
 #pragma unroll
@@ -184,7 +200,9 @@ k_sell_walk(DeviceIndex ix, LmPlan plan, int win_cams, const double* __restrict_
   } else {
     mbar_wait(&bars[0], 0);   // nobody leaves while the copy is in flight
   }
+  POVAR_WALK_STAMP(2);
   op.finish(st, ix, win, table);
+  POVAR_WALK_STAMP(3);
 }
 
 // launch with the shape the plan chose (plan_landmark_half, engine.cu)

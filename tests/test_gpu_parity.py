@@ -344,15 +344,17 @@ def test_sliced_ell_copies_hold_every_observation_once_and_the_second_spreads_th
     padding in both."""
     sp = synthetic.generate_named(shape)
     hp = capi.HostProblem.from_unordered(sp.num_cams, sp.num_lms, sp.obs_cam, sp.obs_lm, sp.obs_xy, sp.cam_params)
-    slice_ptr, sell_lm, long_lms = capi.sell_layout(hp)
     s = capi.Solver(hp, capi.default_options(verbosity_level=0))
+    T = int(s.debug_read("sell_max_deg")[0])
+    assert T == capi.sell_max_degree(hp.num_obs)
+    slice_ptr, sell_lm, long_lms = capi.sell_layout(hp, 0, T)
     obs_slot = s.debug_read("obs_slot").astype(np.int64)
     sell_cam = s.debug_read("sell_cam").astype(np.int64)
     sell_cam_e0 = s.debug_read("sell_cam_e0").astype(np.int64)
     s.close()
     deg = np.diff(hp.lm_ptr)
     lm_of_obs = np.repeat(np.arange(hp.num_lms), deg)
-    in_sell = deg[lm_of_obs] <= 32
+    in_sell = deg[lm_of_obs] <= T
     where = np.full(hp.num_lms, -1, np.int64)
     where[sell_lm[sell_lm >= 0]] = np.nonzero(sell_lm >= 0)[0]
     sl, lane = where[lm_of_obs[in_sell]] // 32, where[lm_of_obs[in_sell]] % 32

@@ -276,12 +276,12 @@ def _sell_key(cams, span=896):
     return (int(cams[best[0]]) + int(cams[best[1]])) // 2
 
 
-def _sell_reference(hp, max_window=4096, width=32):
+def _sell_reference(hp, max_window=4096, width=32, max_deg=32):
     """The sliced-ELL rule restated with numpy sorts (engine.cu build_sell): landmarks with 1..32 observations
     in the order of their key camera (stable), windows of `window`, inside a window stable by descending
     degree, 32 landmarks (one per lane) per slice, slice length = the largest degree in it."""
     deg = np.diff(hp.lm_ptr)
-    ok = np.nonzero((deg > 0) & (deg <= 32))[0]
+    ok = np.nonzero((deg > 0) & (deg <= max_deg))[0]
     key = np.array([_sell_key(hp.obs_cam[hp.lm_ptr[l]:hp.lm_ptr[l + 1]]) for l in ok], dtype=np.int64)
     by_cam = ok[np.argsort(key, kind="stable")]
     window = max_window
@@ -295,7 +295,7 @@ def _sell_reference(hp, max_window=4096, width=32):
             grp = list(order[i:i + width])
             sell_lm += grp + [-1] * (width - len(grp))
             slice_ptr.append(slice_ptr[-1] + int(deg[order[i]]))
-    return np.array(slice_ptr), np.array(sell_lm), np.nonzero(deg > 32)[0]
+    return np.array(slice_ptr), np.array(sell_lm), np.nonzero(deg > max_deg)[0]
 
 
 def test_sell_key_centres_the_cameras_it_can_cover():
@@ -314,6 +314,18 @@ def test_sliced_ell_order_matches_its_rule_for_any_thread_count(shape):
         got = capi.sell_layout(hp, threads)
         for a, b in zip(got, ref):
             assert np.array_equal(a, b), (shape, threads)
+    # small shards keep only the landmarks with few observations in the set (sell_max_degree)
+    for a, b in zip(capi.sell_layout(hp, 2, 12), _sell_reference(hp, max_deg=12)):
+        assert np.array_equal(a, b), shape
+
+
+def test_sell_max_degree_shrinks_on_small_shards():
+    assert capi.sell_max_degree(4_999_019) == 32          # venice-1778 on one GPU: 33 rows per resident warp
+    assert capi.sell_max_degree(2_500_000) == 32
+    assert capi.sell_max_degree(1_250_000) == 16          # on four
+    assert capi.sell_max_degree(625_000) == 8             # on eight: one slice of ~5 rows per warp
+    assert capi.sell_max_degree(30_000) == 8
+    assert capi.sell_max_degree(50_000_000) == 32
 
 
 @pytest.mark.parametrize("shape,world", [("small", 1), ("trafalgar257", 1), ("venice89", 1), ("venice1778", 1),
@@ -326,20 +338,21 @@ def test_landmark_half_plan_covers_the_slices_and_their_cameras(shape, world):
     hp = capi.HostProblem.from_unordered(sp.num_cams, sp.num_lms, sp.obs_cam, sp.obs_lm, sp.obs_xy, sp.cam_params)
     if world > 1:
         hp = hp.shard(world - 1, world)
-    slice_ptr, sell_lm, _ = capi.sell_layout(hp)
+    T = capi.sell_max_degree(hp.num_obs)
+    slice_ptr, sell_lm, _ = capi.sell_layout(hp, 0, T)
     S = len(slice_ptr) - 1
     deg = np.diff(hp.lm_ptr)
     for model, rec, stage in ((0, 176, 640), (1, 208, 896), (2, 176, 896)):
-        info, rs, lo = capi.landmark_plan(hp, model, sms=148)
+        info, rs, lo = capi.landmark_plan(hp, model, sms=148, max_deg=T)
         W, D, bps = info["warps"], info["stages"], info["blocks_per_sm"]
         assert (W, D, bps) in ((8, 3, 4), (16, 3, 2), (32, 3, 1), (32, 2, 1), (24, 2, 1), (16, 2, 1))
         assert info["smem_bytes"] == ((1 + W * D) * 8 + 127) // 128 * 128 + W * D * stage + info["win_cams"] * rec
         assert bps * (info["smem_bytes"] + 1024) <= 228 * 1024
         assert info["ranges"] == min(148 * bps * W, S) and info["blocks"] >= -(-info["ranges"] // W)
         assert rs[0] == 0 and rs[-1] == S and np.all(np.diff(rs) >= 0)
-        rows = np.diff(slice_ptr[rs])
-        longest = int(np.diff(slice_ptr).max())
-        assert rows.max() <= slice_ptr[-1] / info["ranges"] + longest + 1          # equal rows up to one slice
+        cost = np.diff(slice_ptr[rs] + 2 * rs)                       # rows + 2 per slice
+        longest = int(np.diff(slice_ptr).max()) + 2
+        assert cost.max() <= (slice_ptr[-1] + 2 * S) / info["ranges"] + longest + 1   # equal cost up to one slice
         assert info["covered"] == 1
         for b in range(-(-info["ranges"] // W)):
             s0, s1 = rs[b * W], rs[min((b + 1) * W, info["ranges"])]
