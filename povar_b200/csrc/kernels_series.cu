@@ -190,6 +190,7 @@ struct E0LandmarkOp {
   const double* obs_d;
   const double* obs_w;
   const SeriesCtl* ctl;
+  SeriesCtl* queue;   // work queue of the long landmarks (nullptr: round robin)
 
   struct Lane {
     int lm;
@@ -262,14 +263,37 @@ struct E0LandmarkOp {
     }
   }
 
-  // long landmarks, spread over all warps of the grid
+  // Long landmarks (one warp each).  Inside a series they are handed out through a counter to the warps as they
+  // finish their slices, so the blocks that are done early take them (which warp makes a landmark's sum does not
+  // change it); outside a series (no control block) they are dealt round robin.
   __device__ __forceinline__ void finish(Lane& /*st*/, const DeviceIndex& ix, const CamWindow& win,
                                          const double* __restrict__ cam_rec) const {
-    const int warps = static_cast<int>(blockDim.x >> 5);
-    const int total_warps = static_cast<int>(gridDim.x) * warps;
-    for (int k = static_cast<int>(blockIdx.x) * warps + static_cast<int>(threadIdx.x >> 5); k < ix.num_long;
-         k += total_warps) {
-      long_landmark_warp<JOINT, HASW>(ix, win, k, X, cam_rec, obs_d, obs_w, c1, c2, lm_fold, lm_rec);
+    if (ix.num_long == 0) return;
+    if (queue == nullptr) {
+      const int warps = static_cast<int>(blockDim.x >> 5);
+      const int total_warps = static_cast<int>(gridDim.x) * warps;
+      for (int k = static_cast<int>(blockIdx.x) * warps + static_cast<int>(threadIdx.x >> 5); k < ix.num_long;
+           k += total_warps) {
+        long_landmark_warp<JOINT, HASW>(ix, win, k, X, cam_rec, obs_d, obs_w, c1, c2, lm_fold, lm_rec);
+      }
+      return;
+    }
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+      unsigned int k = 0;
+      if (lane == 0) k = atomicAdd(&queue->long_next, 1u);
+      k = __shfl_sync(kFullMask, k, 0);
+      if (k >= static_cast<unsigned int>(ix.num_long)) break;
+      long_landmark_warp<JOINT, HASW>(ix, win, static_cast<int>(k), X, cam_rec, obs_d, obs_w, c1, c2, lm_fold, lm_rec);
+    }
+    // the last block to leave puts the queue back for the next launch
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(&queue->long_left, 1u) == gridDim.x - 1) {
+        queue->long_next = 0u;
+        queue->long_left = 0u;
+      }
     }
   }
 };
@@ -399,8 +423,8 @@ k_cam_rec_static(int C, const double* __restrict__ P, double* __restrict__ cam_r
 template <bool JOINT, bool HASW>
 void launch_landmark_half(const DeviceState& d, const ModelParams& mp, const SeriesCtl* ctl,
                           const LaunchCfg& lc) {
-  const E0LandmarkOp<JOINT, HASW> op{d.X,      d.sell_d,    d.sell_w, mp.c1,   mp.c2,   d.lm_fold,
-                                     d.sell_x, d.sell_fold, d.lm_rec, d.obs_d, d.obs_w, ctl};
+  const E0LandmarkOp<JOINT, HASW> op{d.X,         d.sell_d, d.sell_w, mp.c1,   mp.c2, d.lm_fold, d.sell_x,
+                                     d.sell_fold, d.lm_rec, d.obs_d,  d.obs_w, ctl,   ctl != nullptr ? d.ctl : nullptr};
   if (launch_sell_walk(d.ix, d.plan[JOINT ? 1 : (HASW ? 2 : 0)], d.debug_window_cams, d.cam_rec, op, lc.stream)) {
     count(lc);
   }

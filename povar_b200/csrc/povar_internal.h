@@ -83,6 +83,9 @@ struct SeriesCtl {
   unsigned int ticket; // last-block election
   unsigned int next_block;  // peer mode: logical block numbers in dispatch order
   int term;            // terms of the running series that are complete (the loop of the series graph counts here)
+  // landmark half: the landmarks with many observations are handed out to the warps as they finish their slices
+  unsigned int long_next;   // next one to take
+  unsigned int long_left;   // blocks of the launch that have left the queue (the last one resets both)
 };
 
 // The series as a loop of the CUDA graph (Engine::enqueue_series): `handle` is the conditional handle of the WHILE
