@@ -67,11 +67,19 @@ __device__ __forceinline__ void load4(const double* __restrict__ p, double (&v)[
   v[3] = b.y;
 }
 
+// 32 bytes with one 256-bit load (LDG.E.256, sm_100): a gather of 32-byte pieces costs one L1 wavefront per piece
+// instead of the two of a pair of 128-bit loads.  p must be 32-byte aligned; read-only data path.
+__device__ __forceinline__ void load4_256(const double* __restrict__ p, double (&v)[4]) {
+  asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];"
+               : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3])
+               : "l"(p));
+}
+
 __device__ __forceinline__ void load_cam(const double* __restrict__ P, int c, Cam3x4& m) {
   const double* p = P + 12 * static_cast<size_t>(c);
-  load4(p, m.r0);
-  load4(p + 4, m.r1);
-  load4(p + 8, m.r2);
+  load4_256(p, m.r0);
+  load4_256(p + 4, m.r1);
+  load4_256(p + 8, m.r2);
 }
 
 __device__ __forceinline__ double dot4(const double (&a)[4], const double (&b)[4]) {

@@ -43,8 +43,11 @@ inline int item_grid(const DeviceState& d) {
 __device__ __forceinline__ void load_rec(const double* __restrict__ rec, int lm, double (&x)[4],
                                          double (&h)[4]) {
   const double* p = rec + kLmRec * static_cast<size_t>(lm);
-  load4(p, x);
-  load4(p + 4, h);
+  double a[4], b[4];   // [X0 X1 H0 H1], [X2 X3 H2 H3]
+  load4_256(p, a);
+  load4_256(p + 4, b);
+  x[0] = a[0], x[1] = a[1], x[2] = b[0], x[3] = b[1];
+  h[0] = a[2], h[1] = a[3], h[2] = b[2], h[3] = b[3];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -64,10 +67,10 @@ __device__ __forceinline__ void kron_factors(const DeviceIndex& ix, int e, const
   const int lm = __ldg(ix.csc_lm + e);
   const double2 uv = ix.csc_uv[e];
   double x[4];
-  load4(X + 4 * static_cast<size_t>(lm), x);
+  load4_256(X + 4 * static_cast<size_t>(lm), x);
   if (KIND == KRON_SDIAG) {
     double sl[4], inv[6];
-    load4(lm_scale + 4 * static_cast<size_t>(lm), sl);
+    load4_256(lm_scale + 4 * static_cast<size_t>(lm), sl);
     {
       const double* hi = hll_inv + 6 * static_cast<size_t>(lm);
 #pragma unroll
@@ -182,6 +185,11 @@ __device__ __forceinline__ void kron_factors(const DeviceIndex& ix, int e, const
 // rows 6..7 zero; B = Y, 4 entries x 8, two column tiles for the 10 entries of X X^T) and eight k-steps
 // consume the 32 entries.  Four accumulator registers per lane instead of 60 (a one-lane-one-entry
 // kernel ran at one block per SM), and no 60-value warp reduction at the end.
+// The staging rows are 64 bytes, so plain rows put the 16-byte stores of a quarter warp on two bank groups (4-way
+// conflict) and the 8-byte fragment reads of a half warp on half the banks (2-way): 290 shared-memory wavefronts
+// per 32 entries, which is what bounded the kernel (l1tex 95 %).  The four 16-byte chunks of row R are therefore
+// stored at chunk position q ^ swz(R), swz(R) = 2 * bit1(R) + bit2(R): stores and fragment reads are both
+// conflict-free (96 wavefronts).
 __device__ __forceinline__ void dmma_m8n8k4(double (&d)[2], double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
                : "+d"(d[0]), "+d"(d[1])
@@ -207,12 +215,15 @@ k_kron_mma(DeviceIndex ix, const double* __restrict__ P, const double* __restric
   double (*sE)[8] = stage[wib][0];
   double (*sY0)[8] = stage[wib][1];
   double (*sY1)[8] = stage[wib][2];
+  const int wz = 2 * ((lane >> 1) & 1) + ((lane >> 2) & 1);   // swz(row) of the row this lane writes
   // the padding never changes
-  sE[lane][6] = sE[lane][7] = 0.0;
+  *reinterpret_cast<double2*>(&sE[lane][2 * (3 ^ wz)]) = make_double2(0.0, 0.0);
 #pragma unroll
-  for (int k = 2; k < 8; ++k) sY1[lane][k] = 0.0;
+  for (int q = 1; q < 4; ++q) *reinterpret_cast<double2*>(&sY1[lane][2 * (q ^ wz)]) = make_double2(0.0, 0.0);
   double d0[2] = {0.0, 0.0}, d1[2] = {0.0, 0.0};
   const int fr = lane >> 2, fk = lane & 3;   // fragment row (A) / column (B), k index inside a step
+  // column fr of row 4 j + fk sits at chunk (fr >> 1) ^ swz(4 j + fk), swz(4 j + fk) = 2 * (fk >> 1) + (j & 1)
+  const int rq = (fr >> 1) ^ (2 * (fk >> 1)), ro = fr & 1;
   for (int e0 = eb; e0 < ee; e0 += 32) {
     const int e = e0 + lane;
     double E[6], Y[10];
@@ -225,16 +236,21 @@ k_kron_mma(DeviceIndex ix, const double* __restrict__ P, const double* __restric
       for (int k = 0; k < 10; ++k) Y[k] = 0.0;
     }
 #pragma unroll
-    for (int k = 0; k < 6; k += 2) *reinterpret_cast<double2*>(&sE[lane][k]) = make_double2(E[k], E[k + 1]);
+    for (int q = 0; q < 3; ++q) {
+      *reinterpret_cast<double2*>(&sE[lane][2 * (q ^ wz)]) = make_double2(E[2 * q], E[2 * q + 1]);
+    }
 #pragma unroll
-    for (int k = 0; k < 8; k += 2) *reinterpret_cast<double2*>(&sY0[lane][k]) = make_double2(Y[k], Y[k + 1]);
-    *reinterpret_cast<double2*>(&sY1[lane][0]) = make_double2(Y[8], Y[9]);
+    for (int q = 0; q < 4; ++q) {
+      *reinterpret_cast<double2*>(&sY0[lane][2 * (q ^ wz)]) = make_double2(Y[2 * q], Y[2 * q + 1]);
+    }
+    *reinterpret_cast<double2*>(&sY1[lane][2 * wz]) = make_double2(Y[8], Y[9]);
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const double a = sE[4 * j + fk][fr];
-      dmma_m8n8k4(d0, a, sY0[4 * j + fk][fr]);
-      dmma_m8n8k4(d1, a, sY1[4 * j + fk][fr]);
+      const int col = 2 * (rq ^ (j & 1)) + ro;
+      const double a = sE[4 * j + fk][col];
+      dmma_m8n8k4(d0, a, sY0[4 * j + fk][col]);
+      dmma_m8n8k4(d1, a, sY1[4 * j + fk][col]);
     }
     __syncwarp();
   }

@@ -37,7 +37,7 @@ constexpr int kBlock = 256;
 #endif
 
 __device__ __forceinline__ void load_lm4(const double* __restrict__ X, int lm, double (&x)[4]) {
-  load4(X + 4 * static_cast<size_t>(lm), x);
+  load4_256(X + 4 * static_cast<size_t>(lm), x);
 }
 
 // one warp per landmark with more than 32 observations (DeviceIndex::long_lm)
@@ -472,10 +472,8 @@ k_prep_long(int num_long, const int* __restrict__ long_lm, const double* __restr
 #pragma unroll
   for (int k = 0; k < 10; ++k) fo[k] = fold[k];
   double* rec = lm_rec + kLmRec * static_cast<size_t>(l);
-#pragma unroll
-  for (int k = 0; k < 4; ++k) rec[k] = x[k];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) rec[4 + k] = H[k];
+  rec[kLmRecX0] = x[0], rec[kLmRecX0 + 1] = x[1], rec[kLmRecX2] = x[2], rec[kLmRecX2 + 1] = x[3];
+  rec[kLmRecH0] = H[0], rec[kLmRecH0 + 1] = H[1], rec[kLmRecH2] = H[2], rec[kLmRecH2 + 1] = H[3];
 }
 
 // the landmarks of the sliced-ELL set, one thread per slot: the sums of the linearisation come in and Hll^-1
@@ -528,10 +526,10 @@ k_prep_sell(int slots, const int* __restrict__ sell_lm, const double* __restrict
   hi[1] = make_double2(inv[2], inv[3]);
   hi[2] = make_double2(inv[4], inv[5]);
   double2* rec = reinterpret_cast<double2*>(lm_rec + kLmRec * static_cast<size_t>(lm));
-  rec[0] = make_double2(x[0], x[1]);
-  rec[1] = make_double2(x[2], x[3]);
-  rec[2] = make_double2(H[0], H[1]);
-  rec[3] = make_double2(H[2], H[3]);
+  rec[kLmRecX0 / 2] = make_double2(x[0], x[1]);
+  rec[kLmRecH0 / 2] = make_double2(H[0], H[1]);
+  rec[kLmRecX2 / 2] = make_double2(x[2], x[3]);
+  rec[kLmRecH2 / 2] = make_double2(H[2], H[3]);
 }
 
 // landmark-level tail shared by the E0 pass: G (sum of Jl_raw^T a over the landmark) -> H

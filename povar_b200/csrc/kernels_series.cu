@@ -17,7 +17,7 @@
 // half the issue rate of its 32 warps per SM and scaled with nothing but the warp count (this round's
 // profiles).  From shared memory a whole 176-byte record per lane is cheap (eleven LDS.128, conflicts limited
 // by the odd record stride), nothing is computed twice and nothing is exchanged.
-// Camera half: two lanes per entry, the landmark records gathered from L2.
+// Camera half: two lanes per entry, the landmark records gathered from L2, one 256-bit load per lane.
 #include <cuda_runtime.h>
 
 #include <cstdlib>
@@ -170,7 +170,10 @@ __device__ __forceinline__ void long_landmark_warp(const DeviceIndex& ix, const 
 #pragma unroll
   for (int i = 0; i < 10; ++i) F[i] = (JOINT || i < 6) ? __ldg(lm_fold + 10 * static_cast<size_t>(lm) + i) : 0.0;
   fold_apply<JOINT>(F, G, H);
-  if (lane < 4) lm_rec[kLmRec * static_cast<size_t>(lm) + 4 + lane] = lane == 0 ? H[0] : (lane == 1 ? H[1] : (lane == 2 ? H[2] : H[3]));
+  if (lane < 4) {
+    lm_rec[kLmRec * static_cast<size_t>(lm) + (lane < 2 ? kLmRecH0 + lane : kLmRecH2 + lane - 2)] =
+        lane == 0 ? H[0] : (lane == 1 ? H[1] : (lane == 2 ? H[2] : H[3]));
+  }
 }
 
 template <bool JOINT, bool HASW>
@@ -257,9 +260,9 @@ struct E0LandmarkOp {
     for (int i = 0; i < 10; ++i) F[i] = (JOINT || i < 6) ? __ldcs(fp + i * kSellWidth) : 0.0;
     fold_apply<JOINT>(F, st.G, H);
     if (st.lm >= 0) {
-      double2* out = reinterpret_cast<double2*>(lm_rec + kLmRec * static_cast<size_t>(st.lm) + 4);
-      __stcs(out, make_double2(H[0], H[1]));
-      __stcs(out + 1, make_double2(H[2], H[3]));
+      double* out = lm_rec + kLmRec * static_cast<size_t>(st.lm);
+      __stcs(reinterpret_cast<double2*>(out + kLmRecH0), make_double2(H[0], H[1]));
+      __stcs(reinterpret_cast<double2*>(out + kLmRecH2), make_double2(H[2], H[3]));
     }
   }
 
@@ -301,9 +304,12 @@ struct E0LandmarkOp {
 // ------------------------------------------------------------------------------------------
 // camera half.  One warp per work item (a run of CSC entries of one camera, kernels_camera.cu),
 // two lanes per entry, sixteen entries per step, two steps per trip.  Lane j owns X[2j..2j+1]
-// and H[2j..2j+1] of the landmark record and the matching two columns of M; the 3-vector M H is
-// completed with one exchange, and each lane accumulates its six entries of m (x) X.  The
+// and H[2j..2j+1] of the landmark record (one 256-bit load, kLmRec) and the matching two columns of M; the
+// 3-vector M H is completed with one exchange, and each lane accumulates its six entries of m (x) X.  The
 // landmark indices of the next trip are loaded before the records of this one are used.
+// The kernel waits for the record gather (long_scoreboard; L2, half of it DRAM).  Measured and dropped: a ring
+// of register stages refilled right after use (ptxas puts the loads of all stages on one scoreboard, so every
+// step waits for the youngest load: 63 -> 118 us).
 // ------------------------------------------------------------------------------------------
 template <bool JOINT, bool HASW, int kSteps, int kOcc = (kSteps <= 2 ? 3 : 2)>
 __global__ void __launch_bounds__(kBlock, kOcc)
@@ -342,9 +348,10 @@ k_passB_e0_v2(DeviceIndex ix, const double* __restrict__ P, const double* __rest
       const int e = e0 + 16 * s + pr;
       act[s] = e < ee;
       const int ec = act[s] ? e : ee - 1;
-      const double* rp = lm_rec + kLmRec * static_cast<size_t>(lmn[s]) + 2 * j;
-      xe[s] = ldg2(rp);
-      he[s] = ldg2(rp + 4);
+      double t[4];   // this lane's half of the record: X[2j], X[2j+1], H[2j], H[2j+1]
+      load4_256(lm_rec + kLmRec * static_cast<size_t>(lmn[s]) + 4 * j, t);
+      xe[s] = make_double2(t[0], t[1]);
+      he[s] = make_double2(t[2], t[3]);
       if (JOINT) {
         const double* dp = csc_d + 3 * static_cast<size_t>(ec);
         kc[s].a = __ldg(dp);

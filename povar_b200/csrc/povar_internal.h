@@ -69,7 +69,11 @@ constexpr int kStageLin = kStagePose + 32;
 // shared memory of a block of the landmark half ahead of the rings: one mbarrier for the window and one per
 // ring stage, rounded up to 128 bytes
 __host__ __device__ constexpr int lm_bar_bytes(int warps, int stages) { return ((1 + warps * stages) * 8 + 127) / 128 * 128; }
-constexpr int kLmRec = 8;     // per-landmark record read by the camera-major pass: [X(4) | H(4)]
+// per-landmark record read by the camera-major passes: [X0 X1 H0 H1 | X2 X3 H2 H3].  The two 32-byte halves are what
+// the two lanes of an entry of the camera half need, so each takes its half with ONE 256-bit load (lm_rec_half,
+// device_math.cuh): the gather costs one L1 wavefront per entry instead of two
+constexpr int kLmRec = 8;
+constexpr int kLmRecX0 = 0, kLmRecH0 = 2, kLmRecX2 = 4, kLmRecH2 = 6;
 
 // series control block, lives in device memory
 struct SeriesCtl {
@@ -158,7 +162,7 @@ struct DeviceState {
   double* lm_hraw = nullptr;     // [L*10] sum_i w Jl_raw^T Jl_raw (packed symmetric; 6 used in step 1)
   double* lm_graw = nullptr;     // [L*4]  sum_i w Jl_raw^T r
   double* hll_inv = nullptr;     // [L*6]
-  double* lm_rec = nullptr;      // [L*8]  [X | H] for the camera-major pass
+  double* lm_rec = nullptr;      // [L*8]  X and H for the camera-major passes (kLmRec)
   double* lm_fold = nullptr;     // [L*10] S (Pi) Hll^-1 (Pi^T) S, packed symmetric: H_l = fold_l G_l
   double* cam_rec = nullptr;     // [C*32] per-camera record of the landmark-major E0 pass (CamRec<>)
   double* obs_d = nullptr;       // [nnz*3] step 2: sqrt(w) (1/z, -x/z^2, -y/z^2) at the linearisation point
