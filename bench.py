@@ -378,7 +378,9 @@ def main():
     # is that list plus the small host-built tables
     pinned = []
     rt = torch.cuda.cudart()
-    for arr in (hp.lm_ptr, hp.obs_cam, hp.obs_uv, hp.cam_P):
+    # the result is read back into the caller's own (page-locked) buffers, as a host application would keep them
+    out_P, out_X = np.zeros((hp.num_cams, 3, 4)), np.zeros((hp.num_lms, 4))
+    for arr in (hp.lm_ptr, hp.obs_cam, hp.obs_uv, hp.cam_P, out_P, out_X):
         if int(rt.cudaHostRegister(arr.ctypes.data, arr.nbytes, 0)) == 0:
             pinned.append(arr)
     h2d = (hp.lm_ptr.nbytes // 2 + hp.obs_cam.nbytes + hp.obs_uv.nbytes + hp.cam_P.nbytes)
@@ -387,7 +389,7 @@ def main():
     def e2e_step():
         s = capi.Solver(hp, opt, comm)
         its_, summ_ = s.bundle_adjust()
-        s.get_state(capi.STATE_JOINT)
+        s.get_state(capi.STATE_JOINT, out=(out_P, out_X))
         s.close()
         return len(its_)
 

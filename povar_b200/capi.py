@@ -375,9 +375,17 @@ class Solver:
     def normalize_joint(self):
         self._check(self.lib.povar_normalize_joint(self.h))
 
-    def get_state(self, which):
-        P = np.empty((self.problem.num_cams, 3, 4))
-        X = np.empty((self.problem.num_lms, 4 if which == STATE_JOINT else 3))
+    def get_state(self, which, out=None):
+        """`out`: (P, X) buffers of the caller (C-contiguous float64, e.g. page-locked) to read the state into."""
+        w = 4 if which == STATE_JOINT else 3
+        if out is not None:
+            P, X = out
+            if (P.dtype != np.float64 or X.dtype != np.float64 or not P.flags.c_contiguous or not X.flags.c_contiguous
+                    or P.size != self.problem.num_cams * 12 or X.size != self.problem.num_lms * w):
+                raise ValueError("get_state: out buffers must be C-contiguous float64 of the state's size")
+        else:
+            P = np.empty((self.problem.num_cams, 3, 4))
+            X = np.empty((self.problem.num_lms, w))
         self._check(self.lib.povar_get_state(self.h, which, _dp(P), _dp(X)))
         return P, X
 

@@ -75,6 +75,11 @@ __device__ __forceinline__ void load4_256(const double* __restrict__ p, double (
                : "l"(p));
 }
 
+// the matching store: one full 32-byte sector per lane instead of two half-written ones
+__device__ __forceinline__ void store4_256(double* p, double a, double b, double c, double d) {
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
 __device__ __forceinline__ void load_cam(const double* __restrict__ P, int c, Cam3x4& m) {
   const double* p = P + 12 * static_cast<size_t>(c);
   load4_256(p, m.r0);

@@ -659,8 +659,9 @@ int Engine::upload(const povar_problem_desc* desc) {
   C_ = C;
   L_ = L;
   nnz_ = nnz;
-  // ---- host: validation, per-camera counts and the small tables (one pass over the observations);
-  // everything per observation is built on the device (kernels_index.cu)
+  // ---- host: the landmark table (one pass over lm_ptr) and the small tables; everything per observation --
+  // the check of the camera indices and the per-camera counts included -- is made on the device
+  // (kernels_index.cu)
   static const bool trace = getenv("POVAR_TRACE_CREATE") != nullptr;   // phase times of povar_create on stderr
   auto t_prev = std::chrono::steady_clock::now();
   auto lap = [&](const char* what) {
@@ -675,53 +676,19 @@ int Engine::upload(const povar_problem_desc* desc) {
   const int sell_max_deg = sell_max_degree(nnz, sm_count());
   d_.ix.sell_max_deg = sell_max_deg;
   if (desc->lm_ptr[0] != 0 || desc->lm_ptr[L] != nnz) return fail(POVAR_ERR_INVALID, "lm_ptr does not span the observations");
-  {
-    const int T = host_threads(nnz);
-    std::vector<std::vector<int>> counts(T, std::vector<int>(static_cast<size_t>(C), 0));
-    std::vector<std::vector<int>> longs(T);
-    std::vector<int> in_set(T, 0);
-    std::vector<const char*> bad(T, nullptr);
-    parallel_chunks(T, [&](int t) {
-      std::vector<int>& cnt = counts[t];
-      int set_here = 0;   // (a local: the per-thread slots of in_set share a cache line)
-      const int l0 = static_cast<int>(static_cast<long long>(L) * t / T);
-      const int l1 = static_cast<int>(static_cast<long long>(L) * (t + 1) / T);
-      for (int l = l0; l < l1; ++l) {
-        const int64_t b = desc->lm_ptr[l], e = desc->lm_ptr[l + 1];
-        if (e < b || b < 0 || e > nnz) {
-          bad[t] = "lm_ptr is not monotone";
-          return;
-        }
-        lm_ptr[l] = static_cast<int>(b);
-        if (e - b > sell_max_deg) longs[t].push_back(l);
-        else if (e > b) ++set_here;
-        for (int64_t o = b; o < e; ++o) {
-          const int c = desc->obs_cam[o];
-          if (c < 0 || c >= C) {
-            bad[t] = "camera index out of range";
-            return;
-          }
-          if (o > b && desc->obs_cam[o - 1] >= c) {
-            bad[t] = "observations of a landmark must have strictly ascending camera indices";
-            return;
-          }
-          cnt[c]++;
-        }
-      }
-      in_set[t] = set_here;
-    });
-    for (int t = 0; t < T; ++t) {
-      if (bad[t]) return fail(POVAR_ERR_INVALID, bad[t]);
-      for (int c = 0; c < C; ++c) cam_ptr[c + 1] += counts[t][c];
-      sell.long_lms.insert(sell.long_lms.end(), longs[t].begin(), longs[t].end());
-      sell_n += in_set[t];
-    }
+  // (one thread: a million trivial iterations cost about a millisecond, less than starting threads does on a
+  // virtualised host -- the threaded version of this pass took 6 to 11 ms on the bench boxes)
+  for (int l = 0; l < L; ++l) {
+    const int64_t b = desc->lm_ptr[l], e = desc->lm_ptr[l + 1];
+    if (e < b || b < 0 || e > nnz) return fail(POVAR_ERR_INVALID, "lm_ptr is not monotone");
+    lm_ptr[l] = static_cast<int>(b);
+    if (e - b > sell_max_deg) sell.long_lms.push_back(l);
+    else if (e > b) ++sell_n;
   }
   lm_ptr[L] = nnz;
-  for (int c = 0; c < C; ++c) cam_ptr[c + 1] += cam_ptr[c];
-  lap("validate + camera counts");
-  // the observation list starts travelling now: the copies run while the host derives the work items and the
-  // sliced-ELL order below
+  lap("landmark table");
+  // the observation list starts travelling now: camera indices first (the device checks and counts them while
+  // the image coordinates follow), and the copies run while the host derives the work items below
 #define PV_UP(dst, src, n) PV_CUDA(cudaMemcpyAsync((dst), (src), (n), cudaMemcpyHostToDevice, stream_))
   DeviceIndex& ix = d_.ix;
   PV_ALLOC(ix.lm_ptr, L + 1);
@@ -729,10 +696,38 @@ int Engine::upload(const povar_problem_desc* desc) {
   PV_ALLOC(ix.obs_lm, nnz);
   PV_ALLOC(ix.obs_uv, nnz);
   PV_UP(ix.lm_ptr, lm_ptr.data(), sizeof(int) * (L + 1));
-  if (nnz > 0) {
-    PV_UP(ix.obs_cam, desc->obs_cam, sizeof(int) * static_cast<size_t>(nnz));
-    PV_UP(ix.obs_uv, desc->obs_uv, sizeof(double) * 2 * static_cast<size_t>(nnz));
+  if (nnz > 0) PV_UP(ix.obs_cam, desc->obs_cam, sizeof(int) * static_cast<size_t>(nnz));
+  {
+    int* d_count = nullptr;
+    const size_t keep = allocs_.size();
+    PV_ALLOC(d_count, static_cast<size_t>(C) + 1);
+    PV_CUDA(validate_obs(L, C, sm_count(), ix.lm_ptr, ix.obs_cam, d_count, lc()));
+    std::vector<int> count(static_cast<size_t>(C) + 1);
+    PV_CUDA(cudaMemcpyAsync(count.data(), d_count, sizeof(int) * count.size(), cudaMemcpyDeviceToHost, stream_));
+    cudaEvent_t counted = nullptr;
+    PV_CUDA(cudaEventCreateWithFlags(&counted, cudaEventDisableTiming));
+    cudaEventRecord(counted, stream_);
+    if (nnz > 0) {
+      const cudaError_t ce = cudaMemcpyAsync(ix.obs_uv, desc->obs_uv, sizeof(double) * 2 * static_cast<size_t>(nnz),
+                                             cudaMemcpyHostToDevice, stream_);
+      if (ce != cudaSuccess) {
+        cudaEventDestroy(counted);
+        return fail(POVAR_ERR_CUDA, cudaGetErrorString(ce));
+      }
+    }
+    const cudaError_t we = cudaEventSynchronize(counted);
+    cudaEventDestroy(counted);
+    if (we != cudaSuccess) return fail(POVAR_ERR_CUDA, cudaGetErrorString(we));
+    while (allocs_.size() > keep) {
+      cudaFreeAsync(allocs_.back(), stream_);
+      allocs_.pop_back();
+    }
+    if (count[C] & 1) return fail(POVAR_ERR_INVALID, "camera index out of range");
+    if (count[C] & 2) return fail(POVAR_ERR_INVALID, "observations of a landmark must have strictly ascending camera indices");
+    for (int c = 0; c < C; ++c) cam_ptr[c + 1] = cam_ptr[c] + count[c];
+    if (cam_ptr[C] != nnz) return fail(POVAR_ERR_INVALID, "camera counts do not add up to the observations");
   }
+  lap("camera check + counts (device)");
   // the sliced-ELL order of the landmarks (rule: build_sell above, which the CPU tests check) on the device, as soon
   // as the copies above have landed; the host derives the camera work items meanwhile
   const int sell_slices = (sell_n + kSellWidth - 1) / kSellWidth;
@@ -1188,7 +1183,7 @@ int Engine::solve_power(bool joint, double lambda) {
   const double lambda_lm = joint ? lambda : (poba ? lambda : 0.0);
   PV_CUDA(cudaEventRecord(ev_[0], stream_));
   // prepare_Hb_*: Hll^-1 and Hll^-1 Jl^T r per landmark; B^-1 per camera; b
-  launch_prep_landmark(d_, joint, lambda_lm, lc());
+  launch_prep_landmark(d_, joint, lambda_lm, false, lc());
   launch_cam_binv(d_, joint, lambda, lc());
   launch_passB(d_, mp_, joint, lc());
   launch_reduce_items(d_, d_.item_part, 12, d_.cam_raw, false, lc());
@@ -1350,7 +1345,7 @@ int Engine::solve(bool joint, double lambda, double* inc, int32_t* iterations) {
 
 // b (and B, B^-1) exactly as the power solvers build them; shared by PCG / RIPCG / CHOLESKY
 int Engine::prepare_reduced_system(bool joint, double lambda, double lambda_lm) {
-  launch_prep_landmark(d_, joint, lambda_lm, lc());
+  launch_prep_landmark(d_, joint, lambda_lm, true, lc());
   launch_cam_binv(d_, joint, lambda, lc());
   launch_passB(d_, mp_, joint, lc());
   launch_reduce_items(d_, d_.item_part, 12, d_.cam_raw, false, lc());
@@ -1695,18 +1690,18 @@ int64_t Engine::debug_read(const char* name, double* out, int64_t capacity) {
   else if (n == "X") dsrc = d_.X, count = 4LL * L_;
   else if (n == "pose_scale") dsrc = d_.pose_scale, count = 12LL * C_;
   else if (n == "lm_scale") dsrc = d_.lm_scale, count = 4LL * L_;
-  else if (n == "lm_hraw" || n == "lm_graw") {
-    // by landmark for the caller: the landmarks of the sliced-ELL set keep these sums as lane-major planes
+  else if (n == "lm_hraw" || n == "lm_graw" || n == "hll_inv") {
+    // by landmark for the caller: the landmarks of the sliced-ELL set keep these as lane-major planes
     // [slice][component][32], the others (more than 32 observations) by landmark
-    const int K = n == "lm_hraw" ? 10 : 4;
+    const int K = n == "lm_hraw" ? 10 : (n == "lm_graw" ? 4 : 6);
     count = static_cast<int64_t>(K) * L_;
     if (!out) return count;
     if (capacity < count) {
       fail(POVAR_ERR_INVALID, "debug_read: buffer too small");
       return POVAR_ERR_INVALID;
     }
-    const double* by_lm = K == 10 ? d_.lm_hraw : d_.lm_graw;
-    const double* planes = K == 10 ? d_.sell_hraw : d_.sell_graw;
+    const double* by_lm = K == 10 ? d_.lm_hraw : (K == 4 ? d_.lm_graw : d_.hll_inv);
+    const double* planes = K == 10 ? d_.sell_hraw : (K == 4 ? d_.sell_graw : d_.sell_hinv);
     const size_t slots = static_cast<size_t>(kSellWidth) * d_.ix.num_slices;
     std::vector<double> hp(slots * K);
     std::vector<int> hlm(slots);
@@ -1724,7 +1719,6 @@ int64_t Engine::debug_read(const char* name, double* out, int64_t capacity) {
     }
     return count;
   }
-  else if (n == "hll_inv") dsrc = d_.hll_inv, count = 6LL * L_;
   else if (n == "lm_rec") dsrc = d_.lm_rec, count = static_cast<int64_t>(kLmRec) * L_;
   else if (n == "kron") dsrc = d_.kron, count = static_cast<int64_t>(kKron) * C_;
   else if (n == "b_mat") dsrc = d_.Bmat, count = 144LL * C_;

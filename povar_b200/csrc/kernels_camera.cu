@@ -59,13 +59,11 @@ __device__ __forceinline__ void load_rec(const double* __restrict__ rec, int lm,
 //                      in step 2)                  -> diagonal blocks of sum_l Hpl Hll^-1 Hlp
 // factors of one camera-major entry e: E[6] (packed symmetric 3x3) and Y[10] = packed X X^T
 template <bool JOINT, int KIND>
-__device__ __forceinline__ void kron_factors(const DeviceIndex& ix, int e, const Cam3x4& cam,
+__device__ __forceinline__ void kron_factors(int e, int lm, double2 uv, const Cam3x4& cam,
                                              const double* __restrict__ X, double c1, double c2, const Robust& rb,
                                              const double* __restrict__ lm_scale,
                                              const double* __restrict__ hll_inv, double* __restrict__ csc_d,
                                              double* __restrict__ csc_w, double (&E)[6], double (&Y)[10]) {
-  const int lm = __ldg(ix.csc_lm + e);
-  const double2 uv = ix.csc_uv[e];
   double x[4];
   load4_256(X + 4 * static_cast<size_t>(lm), x);
   if (KIND == KRON_SDIAG) {
@@ -199,7 +197,7 @@ __device__ __forceinline__ void dmma_m8n8k4(double (&d)[2], double a, double b) 
 constexpr int kKronWarps = 4;   // warps per block of k_kron_mma: 6 KB of staging each
 
 template <bool JOINT, int KIND>
-__global__ void __launch_bounds__(32 * kKronWarps)
+__global__ void __launch_bounds__(32 * kKronWarps, KIND == KRON_HPP ? 5 : 4)
 k_kron_mma(DeviceIndex ix, const double* __restrict__ P, const double* __restrict__ X, double c1,
            double c2, Robust rb, const double* __restrict__ lm_scale, const double* __restrict__ hll_inv,
            double* __restrict__ item_kron, double* __restrict__ csc_d, double* __restrict__ csc_w) {
@@ -224,11 +222,20 @@ k_kron_mma(DeviceIndex ix, const double* __restrict__ P, const double* __restric
   const int fr = lane >> 2, fk = lane & 3;   // fragment row (A) / column (B), k index inside a step
   // column fr of row 4 j + fk sits at chunk (fr >> 1) ^ swz(4 j + fk), swz(4 j + fk) = 2 * (fk >> 1) + (j & 1)
   const int rq = (fr >> 1) ^ (2 * (fk >> 1)), ro = fr & 1;
+  // landmark index and image point of a lane's entry: loaded one trip ahead of the gather that needs them
+  int lm = eb + lane < ee ? __ldg(ix.csc_lm + eb + lane) : 0;
+  double2 uv = eb + lane < ee ? ix.csc_uv[eb + lane] : make_double2(0.0, 0.0);
   for (int e0 = eb; e0 < ee; e0 += 32) {
     const int e = e0 + lane;
     double E[6], Y[10];
+    const int lm_now = lm;
+    const double2 uv_now = uv;
+    if (e + 32 < ee) {
+      lm = __ldg(ix.csc_lm + e + 32);
+      uv = ix.csc_uv[e + 32];
+    }
     if (e < ee) {
-      kron_factors<JOINT, KIND>(ix, e, cam, X, c1, c2, rb, lm_scale, hll_inv, csc_d, csc_w, E, Y);
+      kron_factors<JOINT, KIND>(e, lm_now, uv_now, cam, X, c1, c2, rb, lm_scale, hll_inv, csc_d, csc_w, E, Y);
     } else {
 #pragma unroll
       for (int k = 0; k < 6; ++k) E[k] = 0.0;
@@ -502,7 +509,7 @@ k_cam_binv16(int C, const double* __restrict__ P, const double* __restrict__ kro
 // t_i = r_i - Jl_i H_l (b).  Output per item; k_reduce_items adds the items of a camera.
 // ------------------------------------------------------------------------------------------
 template <bool JOINT, int MODE>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, 2)
 k_passB(DeviceIndex ix, const double* __restrict__ P, const double* __restrict__ lm_rec, double c1,
         double c2, Robust rb, double* __restrict__ item_part, const SeriesCtl* __restrict__ ctl) {
   if (ctl != nullptr && ctl->done) return;
@@ -516,14 +523,22 @@ k_passB(DeviceIndex ix, const double* __restrict__ P, const double* __restrict__
   double acc[12];
 #pragma unroll
   for (int k = 0; k < 12; ++k) acc[k] = 0.0;
-  for (int e = eb + lane; e < ee; e += 32) {
-    const int lm = __ldg(ix.csc_lm + e);
-    const double2 uv = ix.csc_uv[e];
+  // the landmark index and the image point of the next entry are loaded before the record of this one is used:
+  // one memory latency per entry on the critical path instead of two (the kernel waits on the gather)
+  int e = eb + lane;
+  int lm = e < ee ? __ldg(ix.csc_lm + e) : 0;
+  double2 uv = e < ee ? ix.csc_uv[e] : make_double2(0.0, 0.0);
+  for (; e < ee; e += 32) {
     double x[4], H[4], m[3];
     load_rec(lm_rec, lm, x, H);
+    const double2 uv_now = uv;
+    if (e + 32 < ee) {
+      lm = __ldg(ix.csc_lm + e + 32);
+      uv = ix.csc_uv[e + 32];
+    }
     if (JOINT) {
       JointObs ob;
-      ob.eval(cam, uv.x, uv.y, x, rb);
+      ob.eval(cam, uv_now.x, uv_now.y, x, rb);
       double j0[4], j1[4], t[2];
       ob.jl_rows(cam, j0, j1);
       const double l0 = dot4(j0, H), l1 = dot4(j1, H);
@@ -538,7 +553,7 @@ k_passB(DeviceIndex ix, const double* __restrict__ P, const double* __restrict__
       ob.jpT_coef(t, m);
     } else {
       PoseObs ob;
-      ob.eval(cam, uv.x, uv.y, x, c1, c2, rb);
+      ob.eval(cam, uv_now.x, uv_now.y, x, c1, c2, rb);
       const double w = ob.sw * ob.sw;
       double t[4];
 #pragma unroll
@@ -546,7 +561,7 @@ k_passB(DeviceIndex ix, const double* __restrict__ P, const double* __restrict__
         const double l = ob.T[q][0] * H[0] + ob.T[q][1] * H[1] + ob.T[q][2] * H[2];
         t[q] = (MODE == PASSB_E0) ? w * l : w * (ob.r[q] - l);
       }
-      pose_jpT_coef(t, uv.x, uv.y, c1, c2, m);
+      pose_jpT_coef(t, uv_now.x, uv_now.y, c1, c2, m);
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {

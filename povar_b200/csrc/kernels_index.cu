@@ -9,6 +9,8 @@
 // sort of it by camera (landmarks ascending inside a camera), made with a stable LSD radix sort.
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include <cub/device/device_radix_sort.cuh>
 
 #include "povar_internal.h"
@@ -26,6 +28,43 @@ k_obs_lm(int L, const int* __restrict__ lm_ptr, int* __restrict__ obs_lm) {
   if (l >= L) return;
   const int e = lm_ptr[l + 1];
   for (int o = lm_ptr[l]; o < e; ++o) obs_lm[o] = l;
+}
+
+// Validation of the canonical list and the per-camera counts, one thread per landmark (povar_create used to spend
+// 9 of its 18 ms on this pass on the host).  out[0..C): observations per camera, out[C]: 1 = a camera index out
+// of range, 2 = the cameras of a landmark are not strictly ascending.  SMEM: the counts of a block's landmarks
+// go through a shared-memory histogram (integer sums: the result does not depend on the order).
+template <bool SMEM>
+__global__ void __launch_bounds__(kBlock)
+k_validate_obs(int L, int C, const int* __restrict__ lm_ptr, const int* __restrict__ obs_cam, int* __restrict__ out) {
+  extern __shared__ int hist[];
+  if (SMEM) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) hist[c] = 0;
+    __syncthreads();
+  }
+  int bad = 0;
+  for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < L; l += gridDim.x * blockDim.x) {
+    const int e = lm_ptr[l + 1];
+    int prev = -1;
+    for (int o = lm_ptr[l]; o < e; ++o) {
+      const int c = obs_cam[o];
+      if (static_cast<unsigned>(c) >= static_cast<unsigned>(C)) {
+        bad |= 1;
+        continue;
+      }
+      if (c <= prev) bad |= 2;
+      prev = c;
+      atomicAdd(SMEM ? &hist[c] : &out[c], 1);
+    }
+  }
+  if (bad) atomicOr(&out[C], bad);
+  if (SMEM) {
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const int n = hist[c];
+      if (n != 0) atomicAdd(&out[c], n);
+    }
+  }
 }
 
 __global__ void __launch_bounds__(kBlock) k_iota(int n, int* __restrict__ v) {
@@ -209,6 +248,25 @@ k_sell_slices(int num_slices, int n, const int* __restrict__ ids, const int* __r
 }
 
 }  // namespace
+
+// out: C + 1 zeroed ints (k_validate_obs); lm_ptr has been checked on the host (monotone, inside the list)
+cudaError_t validate_obs(int L, int C, int sms, const int* lm_ptr, const int* obs_cam, int* out, const LaunchCfg& lc) {
+  if (L <= 0) return cudaSuccess;
+  const size_t smem = sizeof(int) * static_cast<size_t>(C);
+  const int blocks = std::max(1, std::min((L + kBlock - 1) / kBlock, 4 * sms));
+  if (smem <= 200 * 1024) {
+    if (smem > 48 * 1024) {
+      const cudaError_t e = cudaFuncSetAttribute(k_validate_obs<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 static_cast<int>(smem));
+      if (e != cudaSuccess) return e;
+    }
+    k_validate_obs<true><<<blocks, kBlock, smem, lc.stream>>>(L, C, lm_ptr, obs_cam, out);
+  } else {
+    k_validate_obs<false><<<blocks, kBlock, 0, lc.stream>>>(L, C, lm_ptr, obs_cam, out);
+  }
+  if (lc.launch_counter) *lc.launch_counter += 1;
+  return cudaGetLastError();
+}
 
 size_t index_sort_temp_bytes(int nnz, int num_cams) {
   size_t bytes = 0;

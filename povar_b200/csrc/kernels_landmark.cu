@@ -521,15 +521,16 @@ k_prep_sell(int slots, const int* __restrict__ sell_lm, const double* __restrict
   for (int k = 0; k < 10; ++k) {
     if (JOINT || k < 6) fp[k * kSellWidth] = fold[k];
   }
-  double2* hi = reinterpret_cast<double2*>(hll_inv + 6 * static_cast<size_t>(lm));
-  hi[0] = make_double2(inv[0], inv[1]);
-  hi[1] = make_double2(inv[2], inv[3]);
-  hi[2] = make_double2(inv[4], inv[5]);
-  double2* rec = reinterpret_cast<double2*>(lm_rec + kLmRec * static_cast<size_t>(lm));
-  rec[kLmRecX0 / 2] = make_double2(x[0], x[1]);
-  rec[kLmRecH0 / 2] = make_double2(H[0], H[1]);
-  rec[kLmRecX2 / 2] = make_double2(x[2], x[3]);
-  rec[kLmRecH2 / 2] = make_double2(H[2], H[3]);
+  if (hll_inv != nullptr) {   // only the camera-major kernels of PCG / CHOLESKY read Hll^-1 by landmark
+    double2* hi = reinterpret_cast<double2*>(hll_inv + 6 * static_cast<size_t>(lm));
+    hi[0] = make_double2(inv[0], inv[1]);
+    hi[1] = make_double2(inv[2], inv[3]);
+    hi[2] = make_double2(inv[4], inv[5]);
+  }
+  static_assert(kLmRecX0 == 0 && kLmRecH0 == 2 && kLmRecX2 == 4 && kLmRecH2 == 6, "two sectors: [X0 X1 H0 H1] [X2 X3 H2 H3]");
+  double* rec = lm_rec + kLmRec * static_cast<size_t>(lm);
+  store4_256(rec, x[0], x[1], H[0], H[1]);
+  store4_256(rec + 4, x[2], x[3], H[2], H[3]);
 }
 
 // landmark-level tail shared by the E0 pass: G (sum of Jl_raw^T a over the landmark) -> H
@@ -1515,17 +1516,19 @@ void launch_lin_landmark(const DeviceState& d, const ModelParams& mp, bool joint
   count(lc);
 }
 
-void launch_prep_landmark(const DeviceState& d, bool joint, double lambda_lm, const LaunchCfg& lc) {
+void launch_prep_landmark(const DeviceState& d, bool joint, double lambda_lm, bool hinv_by_landmark,
+                          const LaunchCfg& lc) {
   const int slots = kSellWidth * d.ix.num_slices;
+  double* hinv_out = hinv_by_landmark ? d.hll_inv : nullptr;
   if (slots > 0) {
     const int blocks = (slots + kBlock - 1) / kBlock;
     if (joint) {
       k_prep_sell<true><<<blocks, kBlock, 0, lc.stream>>>(slots, d.ix.sell_lm, d.sell_x, d.sell_hraw, d.sell_graw,
-                                                          d.sell_scale, lambda_lm, d.sell_hinv, d.sell_fold, d.hll_inv,
+                                                          d.sell_scale, lambda_lm, d.sell_hinv, d.sell_fold, hinv_out,
                                                           d.lm_rec);
     } else {
       k_prep_sell<false><<<blocks, kBlock, 0, lc.stream>>>(slots, d.ix.sell_lm, d.sell_x, d.sell_hraw, d.sell_graw,
-                                                           d.sell_scale, lambda_lm, d.sell_hinv, d.sell_fold, d.hll_inv,
+                                                           d.sell_scale, lambda_lm, d.sell_hinv, d.sell_fold, hinv_out,
                                                            d.lm_rec);
     }
     count(lc);

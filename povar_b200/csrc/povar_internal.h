@@ -252,6 +252,8 @@ cudaError_t build_device_sell(int L, int num_cams, int n, int window, int max_de
                               int* keys_a, int* keys_b, int* ids_a, int* ids_b, void* sort_temp,
                               size_t sort_temp_bytes, int* sell_lm, int* slice_len, int* slice_lo, int* slice_hi,
                               const LaunchCfg& lc);
+// range / order check of the camera indices and the per-camera counts on the device: out[0..C) counts, out[C] flags
+cudaError_t validate_obs(int L, int C, int sms, const int* lm_ptr, const int* obs_cam, int* out, const LaunchCfg& lc);
 size_t index_sort_temp_bytes(int nnz, int num_cams);
 cudaError_t build_device_index(const DeviceIndex& ix, int* iota, int* keys_out, int* perm, int* lm_slot,
                                void* sort_temp, size_t sort_temp_bytes, const LaunchCfg& lc);
@@ -263,7 +265,9 @@ void launch_cost(const DeviceState& d, const ModelParams& mp, bool joint, const 
 void launch_flag_to_double(const DeviceState& d, const LaunchCfg& lc);
 void launch_lin_landmark(const DeviceState& d, const ModelParams& mp, bool joint, bool scale_jl,
                          const LaunchCfg& lc);
-void launch_prep_landmark(const DeviceState& d, bool joint, double lambda_lm, const LaunchCfg& lc);
+// hinv_by_landmark: also store Hll^-1 of the sliced-ELL landmarks by landmark (PCG / CHOLESKY read it camera-major)
+void launch_prep_landmark(const DeviceState& d, bool joint, double lambda_lm, bool hinv_by_landmark,
+                          const LaunchCfg& lc);
 void launch_backsub_varpro(const DeviceState& d, const ModelParams& mp, const double* inc,
                            const LaunchCfg& lc);
 void launch_backsub_poba(const DeviceState& d, const ModelParams& mp, const double* y,

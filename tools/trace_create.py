@@ -13,13 +13,20 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 sp = synthetic.generate_named(workload)
 hp = capi.HostProblem.from_unordered(sp.num_cams, sp.num_lms, sp.obs_cam, sp.obs_lm, sp.obs_xy, sp.cam_params)
 opt = capi.default_options(alpha=0.1, power_sc_iterations=20, verbosity_level=0, robust_norm=capi.NORM_CAUCHY)
+# page-locked inputs and outputs, as bench.py's end-to-end leg has them
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+rt = torch.cuda.cudart()
+out = (np.zeros((hp.num_cams, 3, 4)), np.zeros((hp.num_lms, 4)))
+for arr in (hp.lm_ptr, hp.obs_cam, hp.obs_uv, hp.cam_P) + out:
+    rt.cudaHostRegister(arr.ctypes.data, arr.nbytes, 0)
 for r in range(reps):
     t0 = time.perf_counter()
     s = capi.Solver(hp, opt)
     t1 = time.perf_counter()
     its, summ = s.bundle_adjust()
     t2 = time.perf_counter()
-    P, X = s.get_state(capi.STATE_JOINT)
+    P, X = s.get_state(capi.STATE_JOINT, out=out)
     t3 = time.perf_counter()
     s.close()
     t4 = time.perf_counter()
