@@ -44,8 +44,9 @@ __device__ __forceinline__ void load_rec(const double* __restrict__ rec, int lm,
                                          double (&h)[4]) {
   const double* p = rec + kLmRec * static_cast<size_t>(lm);
   double a[4], b[4];   // [X0 X1 H0 H1], [X2 X3 H2 H3]
-  load4_256(p, a);
-  load4_256(p + 4, b);
+  const unsigned long long keep = l2_keep();
+  load4_256(p, a, keep);
+  load4_256(p + 4, b, keep);
   x[0] = a[0], x[1] = a[1], x[2] = b[0], x[3] = b[1];
   h[0] = a[2], h[1] = a[3], h[2] = b[2], h[3] = b[3];
 }

@@ -529,8 +529,9 @@ k_prep_sell(int slots, const int* __restrict__ sell_lm, const double* __restrict
   }
   static_assert(kLmRecX0 == 0 && kLmRecH0 == 2 && kLmRecX2 == 4 && kLmRecH2 == 6, "two sectors: [X0 X1 H0 H1] [X2 X3 H2 H3]");
   double* rec = lm_rec + kLmRec * static_cast<size_t>(lm);
-  store4_256(rec, x[0], x[1], H[0], H[1]);
-  store4_256(rec + 4, x[2], x[3], H[2], H[3]);
+  const unsigned long long keep = l2_keep();
+  store4_256(rec, x[0], x[1], H[0], H[1], keep);
+  store4_256(rec + 4, x[2], x[3], H[2], H[3], keep);
 }
 
 // landmark-level tail shared by the E0 pass: G (sum of Jl_raw^T a over the landmark) -> H
@@ -1002,9 +1003,9 @@ struct LinLandmarkOp : WalkBase {
                                         unsigned long long* bar) const {
     const size_t slot = kSellWidth * static_cast<size_t>(row);
     mbar_expect_tx(bar, kStageLin);
-    bulk_copy_g2s(stage, ix.sell_cam + slot, 128u, bar);
-    bulk_copy_g2s(stage + 128, ix.sell_uv + slot, 512u, bar);
-    bulk_copy_g2s(stage + 640, ix.sell_row_e0 + slot, 32u, bar);
+    bulk_stream_g2s(stage, ix.sell_cam + slot, 128u, bar);
+    bulk_stream_g2s(stage + 128, ix.sell_uv + slot, 512u, bar);
+    bulk_stream_g2s(stage + 640, ix.sell_row_e0 + slot, 32u, bar);
   }
 
   __device__ __forceinline__ void open(Lane& st, const DeviceIndex& ix, int sl, int lane, int last) const {

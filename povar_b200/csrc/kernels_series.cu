@@ -207,12 +207,12 @@ struct E0LandmarkOp {
                                         unsigned long long* bar) const {
     const size_t slot = kSellWidth * static_cast<size_t>(row);
     mbar_expect_tx(bar, kStage);
-    bulk_copy_g2s(stage, ix.sell_cam_e0 + slot, 128u, bar);
+    bulk_stream_g2s(stage, ix.sell_cam_e0 + slot, 128u, bar);
     if (JOINT) {
-      bulk_copy_g2s(stage + 128, sell_d + 3 * slot, 768u, bar);
+      bulk_stream_g2s(stage + 128, sell_d + 3 * slot, 768u, bar);
     } else {
-      bulk_copy_g2s(stage + 128, ix.sell_uv_e0 + slot, 512u, bar);
-      if (HASW) bulk_copy_g2s(stage + 640, sell_w + slot, 256u, bar);
+      bulk_stream_g2s(stage + 128, ix.sell_uv_e0 + slot, 512u, bar);
+      if (HASW) bulk_stream_g2s(stage + 640, sell_w + slot, 256u, bar);
     }
   }
 
@@ -260,9 +260,11 @@ struct E0LandmarkOp {
     for (int i = 0; i < 10; ++i) F[i] = (JOINT || i < 6) ? __ldcs(fp + i * kSellWidth) : 0.0;
     fold_apply<JOINT>(F, st.G, H);
     if (st.lm >= 0) {
+      // (evict_last: the camera half gathers these records next; a streaming store sent half of them to DRAM)
       double* out = lm_rec + kLmRec * static_cast<size_t>(st.lm);
-      __stcs(reinterpret_cast<double2*>(out + kLmRecH0), make_double2(H[0], H[1]));
-      __stcs(reinterpret_cast<double2*>(out + kLmRecH2), make_double2(H[2], H[3]));
+      const unsigned long long keep = l2_keep();
+      store2(out + kLmRecH0, H[0], H[1], keep);
+      store2(out + kLmRecH2, H[2], H[3], keep);
     }
   }
 
@@ -309,7 +311,9 @@ struct E0LandmarkOp {
 // landmark indices of the next trip are loaded before the records of this one are used.
 // The kernel waits for the record gather (long_scoreboard; L2, half of it DRAM).  Measured and dropped: a ring
 // of register stages refilled right after use (ptxas puts the loads of all stages on one scoreboard, so every
-// step waits for the youngest load: 63 -> 118 us).
+// step waits for the youngest load: 63 -> 118 us); the gathers as LDGSTS copies into a per-warp shared-memory ring,
+// four or six steps deep (copying in and reading out costs more L1 wavefronts than the depth wins: 75 / 85 us);
+// four blocks per SM at 64 registers (40 bytes of spills: 79 us).
 // ------------------------------------------------------------------------------------------
 template <bool JOINT, bool HASW, int kSteps, int kOcc = (kSteps <= 2 ? 3 : 2)>
 __global__ void __launch_bounds__(kBlock, kOcc)
@@ -323,9 +327,10 @@ k_passB_e0_v2(DeviceIndex ix, const double* __restrict__ P, const double* __rest
   const int pr = lane >> 1, j = lane & 1;
   const int c = __ldg(ix.item_cam + warp);
   const int eb = __ldg(ix.item_ptr + warp), ee = __ldg(ix.item_ptr + warp + 1);
+  const unsigned long long keep = l2_keep(), stream = l2_stream();   // records / entry lists (device_math.cuh)
   int lmn[kSteps];
 #pragma unroll
-  for (int s = 0; s < kSteps; ++s) lmn[s] = __ldg(ix.csc_lm + min(eb + 16 * s + pr, ee - 1));
+  for (int s = 0; s < kSteps; ++s) lmn[s] = ldg1(ix.csc_lm + min(eb + 16 * s + pr, ee - 1), stream);
   double Ma[3], Mb[3];   // M[r][2j], M[r][2j+1]
   {
     const double* p = P + 12 * static_cast<size_t>(c);
@@ -349,24 +354,24 @@ k_passB_e0_v2(DeviceIndex ix, const double* __restrict__ P, const double* __rest
       act[s] = e < ee;
       const int ec = act[s] ? e : ee - 1;
       double t[4];   // this lane's half of the record: X[2j], X[2j+1], H[2j], H[2j+1]
-      load4_256(lm_rec + kLmRec * static_cast<size_t>(lmn[s]) + 4 * j, t);
+      load4_256(lm_rec + kLmRec * static_cast<size_t>(lmn[s]) + 4 * j, t, keep);
       xe[s] = make_double2(t[0], t[1]);
       he[s] = make_double2(t[2], t[3]);
       if (JOINT) {
         const double* dp = csc_d + 3 * static_cast<size_t>(ec);
-        kc[s].a = __ldg(dp);
-        kc[s].b = __ldg(dp + 1);
-        kc[s].c = __ldg(dp + 2);
+        kc[s].a = ldg1(dp, stream);
+        kc[s].b = ldg1(dp + 1, stream);
+        kc[s].c = ldg1(dp + 2, stream);
       } else {
-        const double2 uv = ix.csc_uv[ec];
+        const double2 uv = load2(ix.csc_uv + ec, stream);
         kc[s].a = uv.x;
         kc[s].b = uv.y;
-        kc[s].c = HASW ? __ldg(csc_w + ec) : 1.0;
+        kc[s].c = HASW ? ldg1(csc_w + ec, stream) : 1.0;
       }
     }
     if (e0 + 16 * kSteps < ee) {
 #pragma unroll
-      for (int s = 0; s < kSteps; ++s) lmn[s] = __ldg(ix.csc_lm + min(e0 + 16 * kSteps + 16 * s + pr, ee - 1));
+      for (int s = 0; s < kSteps; ++s) lmn[s] = ldg1(ix.csc_lm + min(e0 + 16 * kSteps + 16 * s + pr, ee - 1), stream);
     }
 #pragma unroll
     for (int s = 0; s < kSteps; ++s) {

@@ -60,6 +60,16 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, unsign
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// the same for data that are read once per kernel (the observation streams): evict_first in L2 (device_math.cuh)
+__device__ __forceinline__ void bulk_stream_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  unsigned long long policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
   unsigned done = 0;
   while (!done) {
@@ -82,8 +92,8 @@ __device__ __forceinline__ void issue_cam_uv(const DeviceIndex& ix, int row, uns
                                              unsigned long long* bar) {
   const size_t slot = kSellWidth * static_cast<size_t>(row);
   mbar_expect_tx(bar, kStagePose);
-  bulk_copy_g2s(stage, ix.sell_cam + slot, 128u, bar);
-  bulk_copy_g2s(stage + 128, ix.sell_uv + slot, 512u, bar);
+  bulk_stream_g2s(stage, ix.sell_cam + slot, 128u, bar);
+  bulk_stream_g2s(stage + 128, ix.sell_uv + slot, 512u, bar);
 }
 
 #ifdef POVAR_WALK_TRACE
