@@ -474,7 +474,8 @@ LmPlanHost plan_landmark_half(const SellLayout& sell, int num_cams, int num_long
 }
 
 int choose_item_len(long long nnz) {
-  // enough items to fill every SM with 64 warps a couple of times, at most 256 entries per item
+  // enough items to fill every SM with 64 warps a couple of times, at most 256 entries per item (measured on the
+  // venice-1778 shape: 128 -> camera half 67.8 us, 256 -> 58.7 us, 512 -> 61.8 us)
   long long len = nnz / (static_cast<long long>(sm_count()) * 64 * 2);
   len = (len + 31) / 32 * 32;
   if (len < 32) len = 32;
