@@ -108,12 +108,18 @@ k_sell_rows(int quarters, const int* __restrict__ slice_ptr, const int* __restri
   // per row: eight 4-bit counters, one per camera class; a column of shared memory per thread (indexed by row at
   // run time: in registers it would live in local memory)
   __shared__ unsigned int hist_s[32][128];
+  __shared__ unsigned char rmax_s[32][128];   // the fullest class of each row (kept beside the counters: the
+                                              // search below looks at it once per row and observation)
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= quarters) return;
   const int sl = q >> 2;
   const int len = slice_ptr[sl + 1] - slice_ptr[sl];   // 1..32 rows
   unsigned int (*hist)[128] = reinterpret_cast<unsigned int (*)[128]>(&hist_s[0][threadIdx.x]);
-  for (int r = 0; r < len; ++r) hist[r][0] = 0u;
+  unsigned char (*rmax)[128] = reinterpret_cast<unsigned char (*)[128]>(&rmax_s[0][threadIdx.x]);
+  for (int r = 0; r < len; ++r) {
+    hist[r][0] = 0u;
+    rmax[r][0] = 0;
+  }
   auto row_max = [](unsigned int h) {
     unsigned int m = 0u;
 #pragma unroll
@@ -127,7 +133,12 @@ k_sell_rows(int quarters, const int* __restrict__ slice_ptr, const int* __restri
       if (lm < 0) continue;
       const int ob = lm_ptr[lm], oe = lm_ptr[lm + 1];
       if (sweep > 0) {
-        for (int o = ob; o < oe; ++o) hist[obs_row[o]][0] -= 1u << (4 * (obs_cam[o] & 7));
+        for (int o = ob; o < oe; ++o) {
+          const int r = obs_row[o];
+          const unsigned int h = hist[r][0] - (1u << (4 * (obs_cam[o] & 7)));
+          hist[r][0] = h;
+          rmax[r][0] = static_cast<unsigned char>(row_max(h));
+        }
       }
       unsigned int used = 0u;
       for (int o = ob; o < oe; ++o) {
@@ -137,16 +148,17 @@ k_sell_rows(int quarters, const int* __restrict__ slice_ptr, const int* __restri
         for (int r = 0; r < len; ++r) {
           if ((used >> r) & 1u) continue;
           // what the row costs is its fullest class: first the rows where this observation does not raise it
-          const unsigned int h = hist[r][0];
-          const unsigned int cnt = (h >> shift) & 0xfu;
-          const unsigned int key = (cnt + 1u > row_max(h) ? 16u : 0u) + cnt;
+          const unsigned int cnt = (hist[r][0] >> shift) & 0xfu;
+          const unsigned int key = (cnt + 1u > rmax[r][0] ? 16u : 0u) + cnt;
           if (key < best_key) {
             best_key = key;
             best = r;
           }
         }
         used |= 1u << best;
-        hist[best][0] += 1u << shift;
+        const unsigned int h = hist[best][0] + (1u << shift);
+        hist[best][0] = h;
+        rmax[best][0] = static_cast<unsigned char>(max(static_cast<unsigned int>(rmax[best][0]), (h >> shift) & 0xfu));
         obs_row[o] = static_cast<unsigned char>(best);
       }
     }

@@ -260,7 +260,9 @@ struct E0LandmarkOp {
     for (int i = 0; i < 10; ++i) F[i] = (JOINT || i < 6) ? __ldcs(fp + i * kSellWidth) : 0.0;
     fold_apply<JOINT>(F, st.G, H);
     if (st.lm >= 0) {
-      // (evict_last: the camera half gathers these records next; a streaming store sent half of them to DRAM)
+      // evict_last: the camera half gathers these records next (a streaming store sent half of them to DRAM).
+      // Measured and dropped: whole sectors [X | H] as two 256-bit stores, which spares the read-back of
+      // half-written sectors that leave L2 (33 MB per launch) but costs the store path more: 78.9 -> 81.6 us
       double* out = lm_rec + kLmRec * static_cast<size_t>(st.lm);
       const unsigned long long keep = l2_keep();
       store2(out + kLmRecH0, H[0], H[1], keep);
