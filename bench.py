@@ -386,14 +386,42 @@ def main():
     h2d = (hp.lm_ptr.nbytes // 2 + hp.obs_cam.nbytes + hp.obs_uv.nbytes + hp.cam_P.nbytes)
     d2h = hp.cam_P.nbytes + hp.num_lms * 4 * 8
 
-    def e2e_step():
+    # host phases of a step and the link it crosses, for the record: end-to-end differs from the resident number by
+    # povar_create (H2D + index build), the read-back and the destruction of the handle, and on a shared host the
+    # PCIe link is the part of that which varies from box to box (the same build measured 118 to 420 ms per step)
+    e2e_phases = {"create": 0.0, "solve": 0.0, "read_back": 0.0, "destroy": 0.0}
+
+    def e2e_step(timed=True):
+        t_a = time.perf_counter()
         s = capi.Solver(hp, opt, comm)
+        t_b = time.perf_counter()
         its_, summ_ = s.bundle_adjust()
+        t_c = time.perf_counter()
         s.get_state(capi.STATE_JOINT, out=(out_P, out_X))
+        t_d = time.perf_counter()
         s.close()
+        t_e = time.perf_counter()
+        if timed:
+            for k, v in zip(e2e_phases, (t_b - t_a, t_c - t_b, t_d - t_c, t_e - t_d)):
+                e2e_phases[k] += v
         return len(its_)
 
-    e2e_step()
+    def link_gbs():
+        n = 64 << 20
+        hbuf = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+        dbuf = torch.empty(n, dtype=torch.uint8, device="cuda")
+        a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        dbuf.copy_(hbuf, non_blocking=True)
+        a.record()
+        dbuf.copy_(hbuf, non_blocking=True)
+        b.record()
+        hbuf.copy_(dbuf, non_blocking=True)
+        c.record()
+        torch.cuda.synchronize()
+        return {"h2d": n / (a.elapsed_time(b) * 1e-3) / 1e9, "d2h": n / (b.elapsed_time(c) * 1e-3) / 1e9}
+
+    link = link_gbs()
+    e2e_step(timed=False)
     # every step makes (and destroys) its own handle and stream and ends with a blocking read-back, so
     # the bracket is two events on torch's stream: device timestamps taken while nothing is in flight
     ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -443,7 +471,9 @@ def main():
         # device time of the phases of a solve (CUDA events inside the library, rank 0), like the reference's log
         "phase_ms_per_solve": {k.replace("_time", ""): 1e3 * v / args.steps for k, v in phases.items()},
         "e2e": {"value": e2e_trials / t_e2e, "unit": "LM iterations/s", "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h), "solve_s": t_e2e / args.steps},
+                "d2h_bytes_per_step": int(d2h), "solve_s": t_e2e / args.steps,
+                "host_phase_ms_per_step": {k: 1e3 * v / args.steps for k, v in e2e_phases.items()},
+                "pinned_copy_gbs_measured": link},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,

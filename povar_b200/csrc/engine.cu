@@ -79,6 +79,41 @@ static std::map<std::string, void*>& comm_cache() {
   static std::map<std::string, void*> cache;
   return cache;
 }
+// Stream, events and the page-locked scratch of a handle are kept for the next handle on the same device instead of
+// being destroyed: cudaHostAlloc / cudaFreeHost are the erratic part of povar_create / povar_destroy (3 ms and 0.5 ms
+// as a rule, 130 ms for one cudaFreeHost in a trace, and the likely cause of end-to-end steps of 420 to 580 ms on
+// some hosts).  A kit goes back only after its stream was synchronised.
+struct HostKit {
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  double* pinned = nullptr;   // 256 bytes
+};
+static std::mutex& kit_mutex() {
+  static std::mutex m;
+  return m;
+}
+static std::vector<HostKit>& kit_cache() {
+  static std::vector<HostKit> cache;
+  return cache;
+}
+static bool take_kit(int device, HostKit* out) {
+  std::lock_guard<std::mutex> lock(kit_mutex());
+  auto& cache = kit_cache();
+  for (size_t i = 0; i < cache.size(); ++i) {
+    if (cache[i].device == device) {
+      *out = cache[i];
+      cache.erase(cache.begin() + static_cast<long>(i));
+      return true;
+    }
+  }
+  return false;
+}
+static void give_kit(const HostKit& kit) {
+  std::lock_guard<std::mutex> lock(kit_mutex());
+  kit_cache().push_back(kit);
+}
+
 struct PeerShared {
   void* mem = nullptr;            // this rank's receive buffer + flags (cudaMalloc, IPC-exported)
   std::vector<void*> opened;      // the peers' buffers as mapped here
@@ -557,6 +592,7 @@ int Engine::create(const povar_problem_desc* desc, const povar_options* opt,
     if (err) *err = "povar_create: more than 2^31 observations in one shard";
     return POVAR_ERR_UNSUPPORTED;
   }
+  const auto t_create = std::chrono::steady_clock::now();
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     if (err) *err = "povar_create: no CUDA device (this library has no CPU fallback)";
@@ -580,9 +616,16 @@ int Engine::create(const povar_problem_desc* desc, const povar_options* opt,
       cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
   }
-  if (rc == POVAR_OK) rc = e->check(cudaStreamCreateWithFlags(&e->stream_, cudaStreamNonBlocking), "cudaStreamCreate");
-  for (int i = 0; i < 8 && rc == POVAR_OK; ++i) rc = e->check(cudaEventCreate(&e->ev_[i]), "cudaEventCreate");
-  if (rc == POVAR_OK) rc = e->check(cudaHostAlloc(reinterpret_cast<void**>(&e->host_out_), 256, cudaHostAllocDefault), "cudaHostAlloc");
+  HostKit kit;
+  if (rc == POVAR_OK && take_kit(e->device_, &kit)) {
+    e->stream_ = kit.stream;
+    for (int i = 0; i < 8; ++i) e->ev_[i] = kit.ev[i];
+    e->host_out_ = kit.pinned;
+  } else {
+    if (rc == POVAR_OK) rc = e->check(cudaStreamCreateWithFlags(&e->stream_, cudaStreamNonBlocking), "cudaStreamCreate");
+    for (int i = 0; i < 8 && rc == POVAR_OK; ++i) rc = e->check(cudaEventCreate(&e->ev_[i]), "cudaEventCreate");
+    if (rc == POVAR_OK) rc = e->check(cudaHostAlloc(reinterpret_cast<void**>(&e->host_out_), 256, cudaHostAllocDefault), "cudaHostAlloc");
+  }
   if (rc == POVAR_OK && e->world_ > 1 && opt->solver_type_step_1 == POVAR_CHOLESKY) {
     // the direct solver's reduced camera system is not sharded (solver/linearizor_sc.cpp:121-128 is serial too)
     rc = e->fail(POVAR_ERR_UNSUPPORTED, "CHOLESKY is single-GPU: create the handle without a communicator");
@@ -622,6 +665,10 @@ int Engine::create(const povar_problem_desc* desc, const povar_options* opt,
       }
     }
   }
+  if (getenv("POVAR_TRACE_CREATE") != nullptr) {
+    std::fprintf(stderr, "povar_create: %-28s %8.3f ms\n", "device, stream, scratch",
+                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_create).count());
+  }
   if (rc == POVAR_OK) rc = e->upload(desc);
   if (rc == POVAR_OK) rc = e->setup_peer_exchange();
   if (rc != POVAR_OK) {
@@ -634,24 +681,48 @@ int Engine::create(const povar_problem_desc* desc, const povar_options* opt,
 }
 
 Engine::~Engine() {
+  static const bool trace = getenv("POVAR_TRACE_CREATE") != nullptr;   // phase times of povar_destroy on stderr
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!trace) return;
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "povar_destroy: %-27s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+    t_prev = now;
+  };
   if (device_ >= 0) cudaSetDevice(device_);
   if (stream_) cudaStreamSynchronize(stream_);
+  lap("synchronize");
   // the communicator belongs to the process-wide cache (povar_comm_finalize releases it)
   for (void*& g : series_graph_) {
     if (g) cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(g));
     g = nullptr;
   }
-  if (host_out_) cudaFreeHost(host_out_);
+  lap("graphs");
   if (peer_owned_ && peer_) {
     peer_->release();
     delete peer_;
   }
   for (void* p : allocs_) cudaFreeAsync(p, stream_);
-  if (stream_) cudaStreamSynchronize(stream_);
-  for (auto& ev : ev_) {
-    if (ev) cudaEventDestroy(ev);
+  lap("free (enqueue)");
+  bool clean = stream_ != nullptr && host_out_ != nullptr && cudaStreamSynchronize(stream_) == cudaSuccess;
+  for (auto& ev : ev_) clean = clean && ev != nullptr;
+  lap("free (synchronize)");
+  if (clean) {
+    // stream, events and scratch wait for the next handle on this device (HostKit)
+    HostKit kit;
+    kit.device = device_;
+    kit.stream = stream_;
+    for (int i = 0; i < 8; ++i) kit.ev[i] = ev_[i];
+    kit.pinned = host_out_;
+    give_kit(kit);
+  } else {
+    if (host_out_) cudaFreeHost(host_out_);
+    for (auto& ev : ev_) {
+      if (ev) cudaEventDestroy(ev);
+    }
+    if (stream_) cudaStreamDestroy(stream_);
   }
-  if (stream_) cudaStreamDestroy(stream_);
+  lap("stream, events, scratch");
 }
 
 int Engine::upload(const povar_problem_desc* desc) {
