@@ -331,6 +331,7 @@ def main():
     dom_bytes = own_a if dom == 0 else own_b
     dom_name = "k_sell_walk<E0LandmarkOp<pose>>" if dom == 0 else "k_passB_e0_v2<pose>"
     traffic = None
+    tj = {}
     try:   # measured DRAM bytes per launch of that kernel (one ncu --set full capture, committed)
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tj = json.load(f).get(args.workload, {})
@@ -345,8 +346,11 @@ def main():
         "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
         "traffic": traffic,
         "traffic_source": ("profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full "
-                           "capture of this kernel on this workload (static, not re-measured in this run)"
+                           "--cache-control none capture of this kernel on this workload (static, not re-measured in "
+                           "this run; L2 as the previous launch left it -- with ncu's default flush before every "
+                           "pass: traffic_cold_l2)"
                            if traffic is not None else None),
+        "traffic_cold_l2": tj.get(dom_name + "_cold_l2") if traffic is not None else None,
         "series_exchange": series_exchange,
         "solve_result": solve_result,
         "bytes_per_launch": dom_bytes, "kernel_us": 1e6 * ksec[dom],
