@@ -181,6 +181,9 @@ int povar_comm_finalize(void);
  * comm == NULL means a single GPU (device 0). */
 int povar_create(const povar_problem_desc* desc, const povar_options* opt,
                  const povar_comm_desc* comm, povar_handle** out);
+/* povar_destroy frees the device state (back to the device's memory pool, which keeps it for the next handle) and
+ * hands the handle's stream, events and 256 bytes of page-locked scratch to the next povar_create on the same device
+ * instead of destroying them: a process keeps one such set per handle it ever had alive at the same time. */
 void povar_destroy(povar_handle* h);
 const char* povar_last_error(const povar_handle* h);
 
