@@ -391,8 +391,9 @@ def main():
     d2h = hp.cam_P.nbytes + hp.num_lms * 4 * 8
 
     # host phases of a step and the link it crosses, for the record: end-to-end differs from the resident number by
-    # povar_create (H2D + index build), the read-back and the destruction of the handle, and on a shared host the
-    # PCIe link is the part of that which varies from box to box (the same build measured 118 to 420 ms per step)
+    # povar_create (H2D + index build), the read-back and the destruction of the handle, which depend on the host
+    # (one build measured 118 to 420 ms per step on different boxes; cudaHostAlloc / cudaFreeHost of the handle's
+    # scratch, 130 ms in one trace, were a cause and are gone: DESIGN.md 6)
     e2e_phases = {"create": 0.0, "solve": 0.0, "read_back": 0.0, "destroy": 0.0}
 
     def e2e_step(timed=True):
